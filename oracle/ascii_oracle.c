@@ -1,0 +1,981 @@
+/*
+ * oracle/ascii_oracle.c — TEST INFRASTRUCTURE ONLY (see ascii_oracle.h).
+ *
+ * A from-scratch CPU restatement of the reference render path.  It is deliberately
+ * written in the "cell-local rule" form the CUDA kernels use (every cell decides
+ * from its own pixels, its left neighbour and its run what bytes it owns), not as
+ * the reference's sequential state machines, so that agreement with the compiled
+ * reference (oracle/_ref) also proves that reformulation.
+ *
+ * Each function cites the reference file:line it restates (paths relative to the
+ * reference checkout).  Parity: pinned by tests/test_oracle_vs_ref.py + tests/golden/.
+ */
+#define _GNU_SOURCE
+#include "ascii_oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdbool.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ------------------------------------------------------------------ byte sink */
+typedef struct {
+  char *p;
+  size_t n, cap;
+} bb_t;
+
+static void bb_need(bb_t *b, size_t extra) {
+  if (b->n + extra + 1 <= b->cap) return;
+  size_t c = b->cap ? b->cap : 4096;
+  while (c < b->n + extra + 1) c += c / 2;
+  b->p = (char *)realloc(b->p, c);
+  if (!b->p) abort();
+  b->cap = c;
+}
+static void bb_put(bb_t *b, const void *s, size_t n) {
+  bb_need(b, n);
+  memcpy(b->p + b->n, s, n);
+  b->n += n;
+}
+static void bb_c(bb_t *b, char c) { bb_put(b, &c, 1); }
+static void bb_dec(bb_t *b, uint32_t v) { /* decimal, no leading zeros (common.c:546-570, output_buffer.c:92-104) */
+  char t[10];
+  int i = 0;
+  do {
+    t[i++] = (char)('0' + v % 10u);
+    v /= 10u;
+  } while (v);
+  while (i--) bb_c(b, t[i]);
+}
+static char *bb_finish(bb_t *b, size_t *out_len) {
+  bb_need(b, 0);
+  b->p[b->n] = '\0';
+  if (out_len) *out_len = b->n;
+  return b->p;
+}
+
+/* ------------------------------------------------------------- scalar arithmetic */
+int orc_luma(int r, int g, int b) { return (77 * r + 150 * g + 29 * b + 128) >> 8; } /* foreground.c:93 */
+
+int orc_rgb_to_256(int r, int g, int b) { /* ansi.c:360-379 */
+  int avg = (r + g + b) / 3;
+  int d = abs(r - avg) + abs(g - avg) + abs(b - avg);
+  if (d < 30) return 232 + (avg * 23) / 255;
+  return 16 + 36 * ((r * 5) / 255) + 6 * ((g * 5) / 255) + (b * 5) / 255;
+}
+
+static const uint8_t k_ansi16[16][3] = { /* ansi.c:442-459 */
+    {0, 0, 0},       {128, 0, 0},   {0, 128, 0},   {128, 128, 0}, {0, 0, 128},   {128, 0, 128},
+    {0, 128, 128},   {192, 192, 192}, {128, 128, 128}, {255, 0, 0},   {0, 255, 0},   {255, 255, 0},
+    {0, 0, 255},     {255, 0, 255}, {0, 255, 255}, {255, 255, 255}};
+
+int orc_rgb_to_16(int r, int g, int b) { /* ansi.c:437-477: first minimum wins */
+  int best = 0, bestd = INT_MAX;
+  for (int i = 0; i < 16; i++) {
+    int dr = r - k_ansi16[i][0], dg = g - k_ansi16[i][1], db = b - k_ansi16[i][2];
+    int d = dr * dr + dg * dg + db * db;
+    if (d < bestd) {
+      bestd = d;
+      best = i;
+    }
+  }
+  return best;
+}
+
+int orc_digits_u32(uint32_t v) { /* util/number.h:62 */
+  int d = 1;
+  while (v >= 10u) {
+    v /= 10u;
+    d++;
+  }
+  return d;
+}
+
+int orc_rep_is_profitable(uint32_t run) { /* output_buffer.c:148-154 */
+  if (run <= 2) return 0;
+  uint32_t k = run - 1;
+  return k > (uint32_t)(orc_digits_u32(k) + 3);
+}
+
+/* aspect_ratio.c:17-93.  Float expressions kept operand-for-operand (FLT_EVAL_METHOD 0). */
+static long fit_w_from_h(long height, long iw, long ih) {
+  if (ih == 0) return 1;
+  float w = (float)height * (float)iw / (float)ih * 2.0f;
+  int r = (int)(0.5f + w);
+  return r > 0 ? r : 1;
+}
+static long fit_h_from_w(long width, long iw, long ih) {
+  if (iw == 0) return 1;
+  float h = ((float)width / 2.0f) * (float)ih / (float)iw;
+  int r = (int)(0.5f + h);
+  return r > 0 ? r : 1;
+}
+void orc_aspect_ratio(long img_w, long img_h, long width, long height, int stretch, long *out_w, long *out_h) {
+  if (img_w <= 0 || img_h <= 0) {
+    *out_w = 1;
+    *out_h = 1;
+    return;
+  }
+  if (stretch) {
+    *out_w = width;
+    *out_h = height;
+    return;
+  }
+  long wfh = fit_w_from_h(height, img_w, img_h), hfw = fit_h_from_w(width, img_w, img_h);
+  if (wfh <= width) {
+    *out_w = wfh;
+    *out_h = height;
+  } else {
+    *out_w = width;
+    *out_h = hfw;
+  }
+  if (*out_w <= 0) *out_w = 1;
+  if (*out_h <= 0) *out_h = 1;
+}
+
+/* ------------------------------------------------------------------ glyph tables */
+typedef struct {
+  uint8_t len, b[4];
+} glyph_t;
+
+/* common.c:380-430 (parse rule 397-410) */
+static int parse_palette(const char *pal, glyph_t chars[256]) {
+  int n = 0;
+  const unsigned char *p = (const unsigned char *)pal;
+  while (*p && n < 255) {
+    int len = 1;
+    if ((*p & 0xE0) == 0xC0) len = 2;
+    else if ((*p & 0xF0) == 0xE0) len = 3;
+    else if ((*p & 0xF8) == 0xF0) len = 4;
+    chars[n].len = (uint8_t)len;
+    memset(chars[n].b, 0, 4);
+    int i = 0;
+    for (; i < len && p[i]; i++) chars[n].b[i] = p[i];
+    n++;
+    if (i < len) break; /* truncated sequence at end of string (reference would read past the NUL) */
+    p += len;
+  }
+  return n;
+}
+static int idx256(int i, int n) { /* common.c:420 */
+  int c = n > 1 ? (i * (n - 1) + 127) / 255 : 0;
+  return c >= n ? n - 1 : c;
+}
+static int idx64(int i, int n) { /* common.c:476 */
+  int c = n > 1 ? (i * (n - 1) + 31) / 63 : 0;
+  return c >= n ? n - 1 : c;
+}
+
+int orc_build_glyph_lut(const char *palette, int which, uint8_t out[256][5], uint8_t key_out[256]) {
+  glyph_t chars[256];
+  if (!palette || !palette[0]) return -1;
+  int n = parse_palette(palette, chars);
+  if (n <= 0) return -1;
+  for (int y = 0; y < 256; y++) {
+    int ramp = idx64(y >> 2, n); /* char_index_ramp[Y>>2] */
+    int gi;
+    if (which == 0) gi = idx256(y, n);                    /* Q3: cache[Y] (foreground.c:279,487) */
+    else if (which == 1) gi = idx64(ramp < 64 ? ramp : 63, n); /* Q1: cache64[char_idx] (foreground.c:97-102);
+                                                             char_idx >= 64 is an out-of-bounds read in the
+                                                             reference (palettes > 64 glyphs): clamped here */
+    else gi = idx256(ramp, n);                            /* Q2: cache[char_idx] (foreground.c:596-599) */
+    out[y][0] = chars[gi].len;
+    memcpy(&out[y][1], chars[gi].b, 4);
+    if (key_out) key_out[y] = (uint8_t)ramp;
+  }
+  return n;
+}
+
+/* ---------------------------------------------------------------------- downscale */
+void orc_resize_nn(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh) { /* image.c:267-328 */
+  uint32_t xr = (uint32_t)((((uint64_t)sw << 16) / (uint64_t)dw) + 1);
+  uint32_t yr = (uint32_t)((((uint64_t)sh << 16) / (uint64_t)dh) + 1);
+  for (int y = 0; y < dh; y++) {
+    uint32_t sy = ((uint32_t)y * yr) >> 16;
+    if (sy >= (uint32_t)sh) sy = (uint32_t)sh - 1;
+    for (int x = 0; x < dw; x++) {
+      uint32_t sx = ((uint32_t)x * xr) >> 16;
+      if (sx >= (uint32_t)sw) sx = (uint32_t)sw - 1;
+      memcpy(dst + ((size_t)y * dw + x) * 3, src + ((size_t)sy * sw + sx) * 3, 3);
+    }
+  }
+}
+
+/* Box filter — OUR specification (the reference has none):
+ * dst (dx,dy) averages src x in [floor(dx*sw/dw), max(x0+1, floor((dx+1)*sw/dw))), y likewise,
+ * per channel (sum + n/2) / n in unsigned integers. */
+void orc_resize_box(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh) {
+  for (int dy = 0; dy < dh; dy++) {
+    int y0 = (int)(((int64_t)dy * sh) / dh), y1 = (int)(((int64_t)(dy + 1) * sh) / dh);
+    if (y1 <= y0) y1 = y0 + 1;
+    if (y1 > sh) y1 = sh;
+    if (y0 >= sh) y0 = sh - 1;
+    for (int dx = 0; dx < dw; dx++) {
+      int x0 = (int)(((int64_t)dx * sw) / dw), x1 = (int)(((int64_t)(dx + 1) * sw) / dw);
+      if (x1 <= x0) x1 = x0 + 1;
+      if (x1 > sw) x1 = sw;
+      if (x0 >= sw) x0 = sw - 1;
+      uint32_t s[3] = {0, 0, 0};
+      for (int y = y0; y < y1; y++) {
+        const uint8_t *row = src + ((size_t)y * sw + x0) * 3;
+        for (int x = x0; x < x1; x++, row += 3) {
+          s[0] += row[0];
+          s[1] += row[1];
+          s[2] += row[2];
+        }
+      }
+      uint32_t n = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+      uint8_t *d = dst + ((size_t)dy * dw + dx) * 3;
+      d[0] = (uint8_t)((s[0] + n / 2) / n);
+      d[1] = (uint8_t)((s[1] + n / 2) / n);
+      d[2] = (uint8_t)((s[2] + n / 2) / n);
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------- emitters */
+static void put_sgr_rgb(bb_t *o, int layer /*38|48*/, int r, int g, int b) { /* ansi.c:143-195, output_buffer.c:186-214 */
+  bb_put(o, "\033[", 2);
+  bb_dec(o, (uint32_t)layer);
+  bb_put(o, ";2;", 3);
+  bb_dec(o, (uint32_t)r);
+  bb_c(o, ';');
+  bb_dec(o, (uint32_t)g);
+  bb_c(o, ';');
+  bb_dec(o, (uint32_t)b);
+  bb_c(o, 'm');
+}
+static void put_sgr_256(bb_t *o, int layer, int idx) { /* ansi.c:326-357 */
+  bb_put(o, "\033[", 2);
+  bb_dec(o, (uint32_t)layer);
+  bb_put(o, ";5;", 3);
+  bb_dec(o, (uint32_t)idx);
+  bb_c(o, 'm');
+}
+static void put_sgr_16(bb_t *o, int bg, int idx) { /* ansi.c:384-435: 30-37/90-97, 40-47/100-107 */
+  int code = (idx < 8 ? 30 + idx : 90 + (idx - 8)) + (bg ? 10 : 0);
+  bb_put(o, "\033[", 2);
+  bb_dec(o, (uint32_t)code);
+  bb_c(o, 'm');
+}
+static void put_reset(bb_t *o) { bb_put(o, "\033[0m", 4); }
+static void put_rep(bb_t *o, uint32_t extra) { /* output_buffer.c:156-164 */
+  bb_put(o, "\033[", 2);
+  bb_dec(o, extra);
+  bb_c(o, 'b');
+}
+static void put_glyph(bb_t *o, const uint8_t g[5]) { bb_put(o, &g[1], g[0]); }
+
+/* run bookkeeping shared by all run-length modes: head[x] and len-of-run-containing-x */
+static void runs_from_keys(const uint64_t *key, int w, int *head_of, int *run_len) {
+  int h = 0;
+  for (int x = 0; x < w; x++) {
+    if (x == 0 || key[x] != key[x - 1]) h = x;
+    head_of[x] = h;
+  }
+  int end = w;
+  for (int x = w - 1; x >= 0; x--) {
+    run_len[x] = end - head_of[x];
+    if (head_of[x] == x) end = x;
+  }
+}
+
+/* mono foreground — image_print (foreground.c:27-138), quirk Q1 */
+static char *print_mono_fg(const uint8_t *rgb, int w, int h, const char *pal, size_t *out_len) {
+  uint8_t lut[256][5], keyl[256];
+  if (orc_build_glyph_lut(pal, 1, lut, keyl) < 0) return NULL;
+  bb_t o = {0};
+  uint64_t *key = malloc(sizeof(uint64_t) * (size_t)w);
+  int *hd = malloc(sizeof(int) * (size_t)w), *rl = malloc(sizeof(int) * (size_t)w);
+  for (int y = 0; y < h; y++) {
+    const uint8_t *row = rgb + (size_t)y * w * 3;
+    for (int x = 0; x < w; x++) key[x] = keyl[orc_luma(row[3 * x], row[3 * x + 1], row[3 * x + 2])];
+    runs_from_keys(key, w, hd, rl);
+    for (int x = 0; x < w; x++) {
+      const uint8_t *g = lut[orc_luma(row[3 * hd[x]], row[3 * hd[x] + 1], row[3 * hd[x] + 2])];
+      bool rep = orc_rep_is_profitable((uint32_t)rl[x]);
+      if (hd[x] == x) {
+        put_glyph(&o, g);
+        if (rep) put_rep(&o, (uint32_t)rl[x] - 1);
+      } else if (!rep) {
+        put_glyph(&o, g);
+      }
+    }
+    if (y != h - 1) bb_c(&o, '\n');
+  }
+  free(key);
+  free(hd);
+  free(rl);
+  return bb_finish(&o, out_len);
+}
+
+/* 256-colour foreground — image_print_256color (foreground.c:433-509) */
+static char *print_256_fg(const uint8_t *rgb, int w, int h, const char *pal, size_t *out_len) {
+  uint8_t lut[256][5];
+  if (orc_build_glyph_lut(pal, 0, lut, NULL) < 0) return NULL;
+  bb_t o = {0};
+  for (int y = 0; y < h; y++) {
+    const uint8_t *p = rgb + (size_t)y * w * 3;
+    for (int x = 0; x < w; x++, p += 3) {
+      put_sgr_256(&o, 38, orc_rgb_to_256(p[0], p[1], p[2]));
+      put_glyph(&o, lut[orc_luma(p[0], p[1], p[2])]);
+    }
+    put_reset(&o);
+    if (y < h - 1) bb_c(&o, '\n');
+  }
+  return bb_finish(&o, out_len);
+}
+
+/* 16-colour foreground — image_print_16color (foreground.c:535-624), quirk Q2 */
+static char *print_16_fg(const uint8_t *rgb, int w, int h, const char *pal, size_t *out_len) {
+  uint8_t lut[256][5];
+  if (orc_build_glyph_lut(pal, 2, lut, NULL) < 0) return NULL;
+  bb_t o = {0};
+  for (int y = 0; y < h; y++) {
+    const uint8_t *p = rgb + (size_t)y * w * 3;
+    for (int x = 0; x < w; x++, p += 3) {
+      put_sgr_16(&o, 0, orc_rgb_to_16(p[0], p[1], p[2]));
+      put_glyph(&o, lut[orc_luma(p[0], p[1], p[2])]);
+    }
+    put_reset(&o);
+    if (y < h - 1) bb_c(&o, '\n');
+  }
+  return bb_finish(&o, out_len);
+}
+
+/* truecolor foreground — image_print_color (foreground.c:195-308) + ansi_rle_* (ansi.c:248-314).
+ * Cell rule: an ASCII-glyph cell owns an SGR iff no earlier ASCII-glyph cell exists in raster
+ * order or that cell's colour differs; multi-byte cells always own an SGR and are invisible
+ * to the comparison.  One reset at the very end, '\n' between rows, no per-row reset. */
+static char *print_true_fg(const uint8_t *rgb, int w, int h, const char *pal, size_t *out_len) {
+  uint8_t lut[256][5];
+  if (orc_build_glyph_lut(pal, 0, lut, NULL) < 0) return NULL;
+  bb_t o = {0};
+  long prev_ascii = -1; /* pixel index of the latest ASCII-glyph cell */
+  for (int y = 0; y < h; y++) {
+    for (int x = 0; x < w; x++) {
+      long i = (long)y * w + x;
+      const uint8_t *p = rgb + i * 3;
+      const uint8_t *g = lut[orc_luma(p[0], p[1], p[2])];
+      bool ascii = g[0] == 1 && g[1] < 128;
+      if (ascii) {
+        bool own = prev_ascii < 0 || memcmp(rgb + prev_ascii * 3, p, 3) != 0;
+        if (own) put_sgr_rgb(&o, 38, p[0], p[1], p[2]);
+        bb_c(&o, (char)g[1]);
+        prev_ascii = i;
+      } else {
+        put_sgr_rgb(&o, 38, p[0], p[1], p[2]);
+        put_glyph(&o, g);
+      }
+    }
+    if (y != h - 1) bb_c(&o, '\n');
+  }
+  put_reset(&o);
+  return bb_finish(&o, out_len);
+}
+
+/* 16-colour Floyd–Steinberg with background — image_print_16color_dithered_with_background
+ * (foreground.c:752-846) + rgb_to_16color_dithered (ansi.c:511-583).  Reached for
+ * TRUECOLOR+BACKGROUND in SIMD builds (sgr.c:429-430, quirk Q4).  Serial by nature. */
+static char *print_dither_bg(const uint8_t *rgb, int w, int h, const char *pal, size_t *out_len) {
+  uint8_t lut[256][5];
+  if (orc_build_glyph_lut(pal, 0, lut, NULL) < 0) return NULL;
+  int *err = calloc((size_t)w * h * 3, sizeof(int));
+  bb_t o = {0};
+  for (int y = 0; y < h; y++) {
+    for (int x = 0; x < w; x++) {
+      size_t i = (size_t)y * w + x;
+      const uint8_t *p = rgb + i * 3;
+      int v[3], c[3];
+      for (int k = 0; k < 3; k++) {
+        v[k] = p[k] + err[i * 3 + k];
+        c[k] = v[k] < 0 ? 0 : (v[k] > 255 ? 255 : v[k]);
+      }
+      int q = orc_rgb_to_16(c[0], c[1], c[2]);
+      for (int k = 0; k < 3; k++) {
+        int e = v[k] - (int)k_ansi16[q][k];
+        if (x + 1 < w) err[(i + 1) * 3 + k] += (e * 7) / 16;
+        if (y + 1 < h) {
+          if (x - 1 >= 0) err[(i + w - 1) * 3 + k] += (e * 3) / 16;
+          err[(i + w) * 3 + k] += (e * 5) / 16;
+          if (x + 1 < w) err[(i + w + 1) * 3 + k] += (e * 1) / 16;
+        }
+      }
+      int bl = (k_ansi16[q][0] * 77 + k_ansi16[q][1] * 150 + k_ansi16[q][2] * 29) / 256;
+      put_sgr_16(&o, 1, q);
+      put_sgr_16(&o, 0, bl < 127 ? 15 : 0);
+      put_glyph(&o, lut[orc_luma(p[0], p[1], p[2])]);
+    }
+    put_reset(&o);
+    if (y < h - 1) bb_c(&o, '\n');
+  }
+  free(err);
+  return bb_finish(&o, out_len);
+}
+
+/* half-block family — halfblock.c:48-165 (truecolor), 416-524 (256), 297-405 (16), 184-286 (mono).
+ * depth: 3 truecolor, 2 256c, 1 16c, 0 mono shades. */
+static char *print_halfblock(const uint8_t *rgb, int w, int h, int depth, size_t *out_len) {
+  static const char HB[3] = {(char)0xE2, (char)0x96, (char)0x80};
+  static const char SH[4][3] = {{(char)0xE2, (char)0x96, (char)0x91}, {(char)0xE2, (char)0x96, (char)0x92},
+                                {(char)0xE2, (char)0x96, (char)0x93}, {(char)0xE2, (char)0x96, (char)0x88}};
+  bb_t o = {0};
+  if (w <= 0 || h <= 0) return bb_finish(&o, out_len);
+  uint64_t *key = malloc(sizeof(uint64_t) * (size_t)w);
+  int *hd = malloc(sizeof(int) * (size_t)w), *rl = malloc(sizeof(int) * (size_t)w);
+  for (int y = 0; y < h; y += 2) {
+    const uint8_t *T = rgb + (size_t)y * w * 3;
+    const uint8_t *B = (y + 1 < h) ? T + (size_t)w * 3 : T; /* odd tail: bottom := top */
+    for (int x = 0; x < w; x++) {
+      const uint8_t *t = T + 3 * x, *b = B + 3 * x;
+      if (depth == 3 || depth == 0)
+        key[x] = ((uint64_t)t[0] << 40) | ((uint64_t)t[1] << 32) | ((uint64_t)t[2] << 24) | ((uint64_t)b[0] << 16) |
+                 ((uint64_t)b[1] << 8) | b[2];
+      else if (depth == 2)
+        key[x] = ((uint64_t)orc_rgb_to_256(t[0], t[1], t[2]) << 8) | (uint64_t)orc_rgb_to_256(b[0], b[1], b[2]);
+      else
+        key[x] = ((uint64_t)orc_rgb_to_16(t[0], t[1], t[2]) << 8) | (uint64_t)orc_rgb_to_16(b[0], b[1], b[2]);
+    }
+    runs_from_keys(key, w, hd, rl);
+    for (int x = 0; x < w; x++) {
+      /* everything about a run is decided by its head pixel pair (halfblock.c:111, 357, 476) */
+      int hx = hd[x];
+      const uint8_t *t = T + 3 * hx, *b = B + 3 * hx;
+      bool is_head = hx == x;
+      bool rep = orc_rep_is_profitable((uint32_t)rl[x]);
+      if (depth == 0) {
+        int lt = (t[0] * 76 + t[1] * 150 + t[2] * 29) >> 8, lb = (b[0] * 76 + b[1] * 150 + b[2] * 29) >> 8;
+        if (lt < 16 && lb < 16) {
+          bb_c(&o, ' ');
+        } else if (is_head) {
+          bb_put(&o, SH[lt >> 6], 3);
+          if (rep) put_rep(&o, (uint32_t)rl[x] - 1);
+        } else if (!rep) {
+          bb_put(&o, SH[lt >> 6], 3);
+        }
+        continue;
+      }
+      bool transparent = !(t[0] | t[1] | t[2] | b[0] | b[1] | b[2]);
+      /* colour state in front of this run = previous run's colours unless that run was transparent
+       * (it reset/cleared them) or this is the first run of the row (state cleared per row) */
+      bool prev_set = false;
+      uint64_t pk = 0;
+      if (hx > 0) {
+        int phx = hd[hx - 1];
+        const uint8_t *pt = T + 3 * phx, *pb = B + 3 * phx;
+        prev_set = (pt[0] | pt[1] | pt[2] | pb[0] | pb[1] | pb[2]) != 0;
+        pk = key[phx];
+      }
+      if (transparent) {
+        if (is_head && prev_set) put_reset(&o);
+        bb_c(&o, ' ');
+        continue;
+      }
+      if (is_head) {
+        uint64_t k = key[hx];
+        if (depth == 3) {
+          if (!prev_set || (pk >> 24) != (k >> 24)) put_sgr_rgb(&o, 38, t[0], t[1], t[2]);
+          if (!prev_set || (pk & 0xFFFFFF) != (k & 0xFFFFFF)) put_sgr_rgb(&o, 48, b[0], b[1], b[2]);
+        } else if (depth == 2) {
+          if (!prev_set || (pk >> 8) != (k >> 8)) put_sgr_256(&o, 38, (int)(k >> 8));
+          if (!prev_set || (pk & 0xFF) != (k & 0xFF)) put_sgr_256(&o, 48, (int)(k & 0xFF));
+        } else {
+          if (!prev_set || (pk >> 8) != (k >> 8)) put_sgr_16(&o, 0, (int)(k >> 8));
+          if (!prev_set || (pk & 0xFF) != (k & 0xFF)) put_sgr_16(&o, 1, (int)(k & 0xFF));
+        }
+        bb_put(&o, HB, 3);
+        if (rep) put_rep(&o, (uint32_t)rl[x] - 1);
+      } else if (!rep) {
+        bb_put(&o, HB, 3);
+      }
+    }
+    if (depth != 0) put_reset(&o);
+    if (y + 2 < h) bb_c(&o, '\n');
+  }
+  free(key);
+  free(hd);
+  free(rl);
+  return bb_finish(&o, out_len);
+}
+
+/* image_print_with_capabilities — ascii.c:955-1002 (SIMD_SUPPORT build) */
+char *orc_print(const uint8_t *rgb, int w, int h, int color_level, int render_mode, const char *palette,
+                size_t *out_len) {
+  if (!rgb || !palette) return NULL;
+  if (render_mode == ORC_MODE_HALF) {
+    int depth = color_level == ORC_COLOR_TRUE ? 3 : color_level == ORC_COLOR_256 ? 2 : color_level == ORC_COLOR_16 ? 1 : 0;
+    return print_halfblock(rgb, w, h, depth, out_len);
+  }
+  if (w <= 0 || h <= 0) return NULL;
+  switch (color_level) {
+  case ORC_COLOR_TRUE:
+    return render_mode == ORC_MODE_BG ? print_dither_bg(rgb, w, h, palette, out_len)
+                                      : print_true_fg(rgb, w, h, palette, out_len);
+  case ORC_COLOR_256:
+    return print_256_fg(rgb, w, h, palette, out_len);
+  case ORC_COLOR_16:
+    return print_16_fg(rgb, w, h, palette, out_len);
+  default:
+    return print_mono_fg(rgb, w, h, palette, out_len);
+  }
+}
+
+/* ------------------------------------------------------------------------- padding */
+char *orc_pad_width(const char *frame, size_t pad_left) { /* ascii.c:457-517 */
+  if (!frame) return NULL;
+  size_t n = strlen(frame), lines = 1;
+  for (size_t i = 0; i < n; i++) lines += frame[i] == '\n';
+  char *out = malloc(n + (pad_left ? lines * pad_left : 0) + 1), *q = out;
+  if (pad_left == 0) {
+    memcpy(out, frame, n + 1);
+    return out;
+  }
+  bool bol = true;
+  for (size_t i = 0; i < n; i++) {
+    if (bol) {
+      memset(q, ' ', pad_left);
+      q += pad_left;
+      bol = false;
+    }
+    *q++ = frame[i];
+    if (frame[i] == '\n') bol = true;
+  }
+  *q = '\0';
+  return out;
+}
+char *orc_pad_height(const char *frame, size_t pad_top) { /* ascii.c:902-941 */
+  if (!frame) return NULL;
+  size_t n = strlen(frame);
+  char *out = malloc(n + pad_top + 1);
+  memset(out, '\n', pad_top);
+  memcpy(out + pad_top, frame, n + 1);
+  return out;
+}
+
+static char *finish_convert(const uint8_t *rgb, int w, int h, long rw, long rh, int color_level, int render_mode,
+                            const char *palette, int scale, size_t pad_w, size_t pad_h, size_t *out_len) {
+  if (rw <= 0 || rh <= 0 || rw > INT_MAX || rh > INT_MAX) return NULL;
+  /* image_new limits (image.c:38-85, image.h:166-193): 3840x2160 max */
+  if (rw > 3840 || rh > 2160) return NULL;
+  uint8_t *small = malloc((size_t)rw * (size_t)rh * 3);
+  if (scale == ORC_SCALE_BOX) orc_resize_box(rgb, w, h, small, (int)rw, (int)rh);
+  else orc_resize_nn(rgb, w, h, small, (int)rw, (int)rh);
+  size_t n = 0;
+  char *s = orc_print(small, (int)rw, (int)rh, color_level, render_mode, palette, &n);
+  free(small);
+  if (!s) return NULL;
+  if (n == 0) { /* ascii.c:355-361 */
+    free(s);
+    return NULL;
+  }
+  char *a = orc_pad_width(s, pad_w);
+  free(s);
+  char *b = orc_pad_height(a, pad_h);
+  free(a);
+  if (out_len) *out_len = strlen(b);
+  return b;
+}
+
+/* ascii_convert_with_capabilities — ascii.c:194-387 */
+char *orc_convert_caps(const uint8_t *rgb, int w, int h, long width, long height, int color_level, int render_mode,
+                       int wants_padding, int use_aspect_ratio, int stretch, const char *palette, int scale,
+                       size_t *out_len) {
+  if (!rgb) return NULL;
+  if (w <= 0 || w > 10000 || h <= 0 || h > 10000) return NULL;
+  long rw = width, rh = height;
+  if (use_aspect_ratio) orc_aspect_ratio(w, h, rw, rh, stretch, &rw, &rh);
+  long ow = rw, oh = rh;
+  if (render_mode == ORC_MODE_HALF) rh *= 2;
+  size_t pw = 0, ph = 0;
+  if (use_aspect_ratio && wants_padding) {
+    pw = (size_t)(width > ow ? (width - ow) / 2 : 0);
+    ph = (size_t)(height > oh ? (height - oh) / 2 : 0);
+  }
+  if (!palette) return NULL; /* image_print_with_capabilities rejects NULL palette (ascii.c:956) */
+  return finish_convert(rgb, w, h, rw, rh, color_level, render_mode, palette, scale, pw, ph, out_len);
+}
+
+/* ascii_convert — ascii.c:72-191; opt_render_mode = GET_OPTION(render_mode) */
+char *orc_convert(const uint8_t *rgb, int w, int h, long width, long height, int color, int aspect, int stretch,
+                  const char *palette, int opt_render_mode, size_t *out_len) {
+  if (!rgb || !palette || !palette[0]) return NULL;
+  long rw = width, rh = height;
+  if (aspect) orc_aspect_ratio(w, h, rw, rh, stretch, &rw, &rh);
+  size_t pw = 0, ph = 0;
+  if (aspect) {
+    pw = (size_t)(width > rw ? (width - rw) / 2 : 0);
+    ph = (size_t)(height > rh ? (height - rh) / 2 : 0);
+  }
+  int level = color ? ORC_COLOR_TRUE : ORC_COLOR_NONE;
+  int mode = ORC_MODE_FG;
+  if (color) mode = opt_render_mode == ORC_MODE_HALF ? ORC_MODE_HALF : opt_render_mode == ORC_MODE_BG ? ORC_MODE_BG : ORC_MODE_FG;
+  return finish_convert(rgb, w, h, rw, rh, level, mode, palette, ORC_SCALE_NN, pw, ph, out_len);
+}
+
+/* ------------------------------------------------------------------ text-space grid */
+static int visible_width(const char *d, int n) { /* ascii.c:527-551 */
+  int v = 0, i = 0;
+  while (i < n) {
+    if (d[i] == '\033' && i + 1 < n && d[i + 1] == '[') {
+      i += 2;
+      while (i < n) {
+        char c = d[i++];
+        if (c >= '@' && c <= '~') break;
+      }
+    } else {
+      v++;
+      i++;
+    }
+  }
+  return v;
+}
+static int truncate_visible(const char *d, int n, int target) { /* ascii.c:562-586 */
+  int v = 0, i = 0;
+  while (i < n && v < target) {
+    if (d[i] == '\033' && i + 1 < n && d[i + 1] == '[') {
+      i += 2;
+      while (i < n) {
+        char c = d[i++];
+        if (c >= '@' && c <= '~') break;
+      }
+    } else {
+      v++;
+      i++;
+    }
+  }
+  return i;
+}
+
+char *orc_create_grid(const char *const *frames, const size_t *sizes, int n, int width, int height,
+                      size_t *out_size) { /* ascii.c:602-885 */
+  if (!frames || n <= 0 || width <= 0 || height <= 0 || !out_size) return NULL;
+  size_t W = (size_t)width, H = (size_t)height, total = W * H + H + 1;
+  if (n == 1) {
+    char *r = malloc(total);
+    memset(r, ' ', total - 1);
+    r[total - 1] = '\0';
+    for (int row = 0; row < height; row++) r[(size_t)row * (W + 1) + W] = '\n';
+    const char *s = frames[0];
+    int sn = (int)sizes[0];
+    *out_size = total - 1;
+    if (!s || sn <= 0) return r;
+    int lines = 0;
+    for (int i = 0; i < sn; i++) lines += s[i] == '\n';
+    int vpad = (height - lines) / 2;
+    if (vpad < 0) vpad = 0;
+    int row = vpad, pos = 0;
+    while (pos < sn && row < height) {
+      int ls = pos;
+      while (pos < sn && s[pos] != '\n') pos++;
+      int ll = pos - ls;
+      int hp = (width - visible_width(s + ls, ll)) / 2;
+      if (hp < 0) hp = 0;
+      size_t dst = (size_t)row * (W + 1) + (size_t)hp;
+      int cl = truncate_visible(s + ls, ll, width - hp);
+      if (cl > 0 && dst + (size_t)cl < total) memcpy(r + dst, s + ls, (size_t)cl);
+      if (pos < sn && s[pos] == '\n') pos++;
+      row++;
+    }
+    return r;
+  }
+  float best = -1.0f;
+  int bc = 1, br = n;
+  for (int c = 1; c <= n; c++) {
+    int rws = (int)ceil((double)n / c);
+    if (c * rws - n > n / 2) continue;
+    int cw = (width - (c - 1)) / c, ch = (height - (rws - 1)) / rws;
+    if (cw < 10 || ch < 3) continue;
+    float cell_aspect = ((float)cw / (float)ch) / 2.0f;
+    float as = 1.0f - fabsf(logf(cell_aspect));
+    if (as < 0) as = 0;
+    float util = (float)n / (float)(c * rws);
+    float score = n == 2 ? as * 0.9f + util * 0.1f : as * 0.7f + util * 0.3f;
+    if (c == rws) score += 0.05f;
+    if (score > best) {
+      best = score;
+      bc = c;
+      br = rws;
+    }
+  }
+  int cw = (width - (bc - 1)) / bc, ch = (height - (br - 1)) / br;
+  if (cw < 10 || ch < 3) {
+    char *r = malloc(sizes[0] + 1);
+    if (frames[0] && sizes[0] > 0) {
+      memcpy(r, frames[0], sizes[0]);
+      r[sizes[0]] = '\0';
+      *out_size = sizes[0];
+    } else {
+      r[0] = '\0';
+      *out_size = 0;
+    }
+    return r;
+  }
+  char *m = malloc(total);
+  memset(m, ' ', total - 1);
+  m[total - 1] = '\0';
+  for (int row = 0; row < height; row++) m[(size_t)row * (W + 1) + W] = '\n';
+  for (int s = 0; s < n; s++) {
+    int gr = s / bc, gc = s % bc, r0 = gr * (ch + 1), c0 = gc * (cw + 1);
+    const char *d = frames[s];
+    int sn = (int)sizes[s], pos = 0, srow = 0;
+    while (pos < sn && srow < ch && r0 + srow < height) {
+      int ls = pos;
+      while (pos < sn && d[pos] != '\n') pos++;
+      int ll = pos - ls;
+      int cl = truncate_visible(d + ls, ll, cw);
+      int tv = visible_width(d + ls, cl);
+      if (cl > 0 && c0 + tv <= width) {
+        /* SAFE_MEMCPY (ascii.c:844) = platform_memcpy (lib/platform/posix/system.c:653-666): silently refuses
+         * when count > remaining size.  ANSI bytes make cl exceed the cell, so accepted copies spill over the
+         * following cells/newlines exactly as in the reference. */
+        size_t pos = (size_t)(r0 + srow) * (W + 1) + (size_t)c0;
+        if ((size_t)cl <= total - pos) memcpy(m + pos, d + ls, (size_t)cl);
+      }
+      if (pos < sn && d[pos] == '\n') pos++;
+      srow++;
+    }
+    if (gc < bc - 1 && c0 + cw < width)
+      for (int row = r0; row < r0 + ch && row < height; row++) {
+        size_t idx = (size_t)row * (W + 1) + (size_t)(c0 + cw);
+        if (idx < total - 1) m[idx] = '|';
+      }
+    if (gr < br - 1 && r0 + ch < height) {
+      for (int col = c0; col < c0 + cw && col < width; col++) {
+        size_t idx = (size_t)(r0 + ch) * (W + 1) + (size_t)col;
+        if (idx < total - 1) m[idx] = '_';
+      }
+      if (gc < bc - 1 && c0 + cw < width) {
+        size_t idx = (size_t)(r0 + ch) * (W + 1) + (size_t)(c0 + cw);
+        if (idx < total - 1) m[idx] = '+';
+      }
+    }
+  }
+  m[total - 1] = '\0'; /* a spill may land on the terminator; the reference's strlen would then run off the
+                          buffer (UB) — we re-terminate, which only differs in that UB case */
+  *out_size = strlen(m);
+  return m;
+}
+
+/* -------------------------------------------------------- server pixel-space composite */
+void orc_grid_layout(const int *ws, const int *hs, int n, int term_w, int term_h, int *cols, int *rows) {
+  /* calculate_optimal_grid_layout — stream.c:523-651 */
+  if (n == 0) {
+    *cols = *rows = 0;
+    return;
+  }
+  if (n == 1) {
+    *cols = *rows = 1;
+    return;
+  }
+  float avg = 0.0f;
+  for (int i = 0; i < n; i++) avg += (float)ws[i] / (float)hs[i];
+  avg /= n;
+  int bc = 1, br = n;
+  float best = 0.0f;
+  for (int c = 1; c <= n; c++) {
+    int r = (n + c - 1) / c;
+    if (c * r - n > c) continue;
+    int cw = term_w / c, ch = term_h / r;
+    if (cw < 20 || ch < 10) continue;
+    float used = 0.0f;
+    int area = cw * ch;
+    for (int i = 0; i < n; i++) {
+      float cva = (float)cw / ((float)ch * 2.0f);
+      int fw, fh;
+      if (avg > cva) {
+        fw = cw;
+        fh = (int)((cw / avg) / 2.0f);
+      } else {
+        fh = ch;
+        fw = (int)(ch * 2.0f * avg);
+      }
+      if (fw > cw) fw = cw;
+      if (fh > ch) fh = ch;
+      used += fw * fh;
+    }
+    float util = used / (float)(area * n);
+    if (util > best) {
+      best = util;
+      bc = c;
+      br = r;
+    }
+  }
+  *cols = bc;
+  *rows = br;
+}
+
+int orc_composite(const uint8_t *const *srcs, const int *ws, const int *hs, int n, int width, int height,
+                  uint8_t *out, int *cols_out, int *rows_out) { /* create_multi_source_composite — stream.c:664-779 */
+  int gc, gr;
+  orc_grid_layout(ws, hs, n, width, height, &gc, &gr);
+  if (cols_out) *cols_out = gc;
+  if (rows_out) *rows_out = gr;
+  int CW = width, CH = height * 2;
+  memset(out, 0, (size_t)CW * CH * 3);
+  if (gc <= 0 || gr <= 0) return 0;
+  for (int i = 0, v = 0; i < n && v < 9; i++, v++) {
+    int row = v / gc, col = v % gc;
+    int cw = CW / gc, ch = CH / gr;
+    float sa = (float)ws[i] / (float)hs[i], ca = (float)cw / (float)ch;
+    int tw, th;
+    if (sa > ca) {
+      tw = cw;
+      th = (int)((cw / sa) + 0.5f);
+    } else {
+      th = ch;
+      tw = (int)((ch * sa) + 0.5f);
+    }
+    if (tw <= 0 || th <= 0) continue; /* image_new_from_pool rejects 0-sized (image.c:129); reference would crash */
+    uint8_t *rs = malloc((size_t)tw * th * 3);
+    orc_resize_nn(srcs[i], ws[i], hs[i], rs, tw, th);
+    int x0 = col * cw, y0 = row * ch, xp = (cw - tw) / 2, yp = (ch - th) / 2;
+    for (int y = 0; y < th; y++)
+      for (int x = 0; x < tw; x++) {
+        int dx = x0 + xp + x, dy = y0 + yp + y;
+        if (dx < x0 || dx > x0 + cw - 1 || dy < y0 || dy > y0 + ch - 1) continue;
+        if (dx < 0 || dx >= CW || dy < 0 || dy >= CH) continue;
+        memcpy(out + ((size_t)dy * CW + dx) * 3, rs + ((size_t)y * tw + x) * 3, 3);
+      }
+    free(rs);
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ synthetic inputs */
+void orc_gen_pattern(int kind, uint32_t frame, uint8_t *dst, int w, int h) { /* SURVEY.md Appendix C */
+  size_t npx = (size_t)w * h;
+  switch (kind) {
+  case 0: {
+    uint32_t s = 12345u + frame;
+    for (size_t i = 0; i < npx * 3; i++) {
+      s = s * 1664525u + 1013904223u;
+      dst[i] = (uint8_t)(s >> 24);
+    }
+    break;
+  }
+  case 1:
+    for (size_t i = 0; i < npx; i++) {
+      uint8_t v = (uint8_t)(((uint64_t)i * 255u) / npx + frame);
+      dst[3 * i] = v;
+      dst[3 * i + 1] = v / 2;
+      dst[3 * i + 2] = (uint8_t)(255 - v);
+    }
+    break;
+  case 2: {
+    int bw = w / 8 ? w / 8 : 1, bh = h / 8 ? h / 8 : 1;
+    for (int y = 0; y < h; y++)
+      for (int x = 0; x < w; x++) {
+        uint8_t *p = dst + ((size_t)y * w + x) * 3;
+        int g = ((x + (int)frame) / bw) % 3;
+        p[0] = g == 0 ? 255 : 0;
+        p[1] = g == 1 ? 255 : 0;
+        p[2] = g == 2 ? 255 : 0;
+        if ((x + (int)frame) % bw == 0 || y % bh == 0) p[0] = p[1] = p[2] = 0;
+      }
+    break;
+  }
+  case 3:
+    for (int y = 0; y < h; y++)
+      for (int x = 0; x < w; x++) {
+        uint8_t v = (uint8_t)(w > 1 ? ((uint64_t)x * 255u) / (uint64_t)(w - 1) : 0);
+        v = (uint8_t)(v + frame);
+        uint8_t *p = dst + ((size_t)y * w + x) * 3;
+        p[0] = p[1] = p[2] = v;
+      }
+    break;
+  default:
+    memset(dst, (int)(frame & 255u), npx * 3);
+  }
+}
+
+uint32_t orc_fnv1a32(const uint8_t *p, size_t n) {
+  uint32_t h = 2166136261u;
+  for (size_t i = 0; i < n; i++) {
+    h ^= p[i];
+    h *= 16777619u;
+  }
+  return h;
+}
+
+/* exhaustive 2^24-entry quantiser tables (index = r<<16 | g<<8 | b).  which: 0 = 256-colour, 1 = 16-colour,
+ * 2 = call fn (a uint8_t(*)(uint8_t,uint8_t,uint8_t), e.g. the compiled reference's rgb_to_256color). */
+void orc_fill_table(int which, void *fn, uint8_t *out) {
+  uint8_t (*f)(uint8_t, uint8_t, uint8_t) = (uint8_t(*)(uint8_t, uint8_t, uint8_t))fn;
+  for (int r = 0; r < 256; r++)
+    for (int g = 0; g < 256; g++)
+      for (int b = 0; b < 256; b++) {
+        size_t i = ((size_t)r << 16) | ((size_t)g << 8) | (size_t)b;
+        out[i] = which == 0   ? (uint8_t)orc_rgb_to_256(r, g, b)
+                 : which == 1 ? (uint8_t)orc_rgb_to_16(r, g, b)
+                              : f((uint8_t)r, (uint8_t)g, (uint8_t)b);
+      }
+}
+
+/* ------------------------------------------------------------------ CPU bench helper */
+typedef struct { /* layout-compatible with the reference's image_t (image.h:143-148) */
+  int w, h;
+  void *pixels;
+  uint8_t alloc_method;
+} ref_image_t;
+typedef char *(*ref_convert_fn)(ref_image_t *, long, long, const void *, bool, bool, const char *);
+
+typedef struct {
+  const uint8_t *src;
+  int ring, w, h;
+  long width, height;
+  int color_level, render_mode, scale, frames, threads, tid;
+  const char *palette;
+  ref_convert_fn ref_fn;
+  const void *ref_caps;
+  uint64_t bytes;
+} bench_arg_t;
+
+static void *bench_worker(void *vp) {
+  bench_arg_t *a = (bench_arg_t *)vp;
+  size_t fsz = (size_t)a->w * a->h * 3;
+  for (int i = a->tid; i < a->frames; i += a->threads) {
+    const uint8_t *px = a->src + (size_t)(i % a->ring) * fsz;
+    char *s;
+    size_t n = 0;
+    if (a->ref_fn) {
+      ref_image_t img = {a->w, a->h, (void *)px, 0};
+      s = a->ref_fn(&img, a->width, a->height, a->ref_caps, false, false, a->palette);
+      n = s ? strlen(s) : 0;
+    } else {
+      s = orc_convert_caps(px, a->w, a->h, a->width, a->height, a->color_level, a->render_mode, 0, 0, 0, a->palette,
+                           a->scale, &n);
+    }
+    a->bytes += n;
+    free(s);
+  }
+  return NULL;
+}
+
+double orc_bench_convert(const uint8_t *src, int ring, int w, int h, long width, long height, int color_level,
+                         int render_mode, const char *palette, int scale, int frames, int threads, void *ref_fn,
+                         const void *ref_caps, uint64_t *out_bytes) {
+  if (threads < 1) threads = 1;
+  pthread_t *th = malloc(sizeof(pthread_t) * (size_t)threads);
+  bench_arg_t *args = calloc((size_t)threads, sizeof(bench_arg_t));
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int t = 0; t < threads; t++) {
+    args[t] = (bench_arg_t){src, ring, w, h, width, height, color_level, render_mode, scale, frames, threads, t,
+                            palette, (ref_convert_fn)ref_fn, ref_caps, 0};
+    pthread_create(&th[t], NULL, bench_worker, &args[t]);
+  }
+  uint64_t bytes = 0;
+  for (int t = 0; t < threads; t++) {
+    pthread_join(th[t], NULL);
+    bytes += args[t].bytes;
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (out_bytes) *out_bytes = bytes;
+  free(th);
+  free(args);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}

@@ -1,0 +1,87 @@
+/*
+ * oracle/ascii_oracle.h — TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement ("port") of the reference's RGB -> glyph/ANSI render path.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library; the product (libasciichat_b200.so) never does.
+ *
+ * Parity status: PINNED.  Every function is checked in tests/test_oracle_vs_ref.py
+ * against oracle/_ref/libasciichat_ref.so (the reference's own sources compiled
+ * unmodified) and against the committed golden vectors in tests/golden/.
+ */
+#ifndef ASCII_ORACLE_H
+#define ASCII_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* colour depth / render mode values are the reference's (platform/terminal.h:578-589, 660-667) */
+enum { ORC_COLOR_AUTO = -1, ORC_COLOR_NONE = 0, ORC_COLOR_16 = 1, ORC_COLOR_256 = 2, ORC_COLOR_TRUE = 3 };
+enum { ORC_MODE_FG = 0, ORC_MODE_BG = 1, ORC_MODE_HALF = 2 };
+enum { ORC_SCALE_NN = 0, ORC_SCALE_BOX = 1 };
+
+/* scalar arithmetic */
+int orc_luma(int r, int g, int b);                           /* foreground.c:93 */
+int orc_rgb_to_256(int r, int g, int b);                     /* ansi.c:360-379 */
+int orc_rgb_to_16(int r, int g, int b);                      /* ansi.c:437-477 */
+int orc_rep_is_profitable(uint32_t run);                     /* output_buffer.c:148-154 */
+int orc_digits_u32(uint32_t v);                              /* util/number.h:62 */
+void orc_aspect_ratio(long img_w, long img_h, long width, long height, int stretch, long *out_w,
+                      long *out_h);                          /* aspect_ratio.c:70-93 */
+
+/* glyph tables: out[256][5] = {len, b0, b1, b2, b3}, indexed by luminance Y.
+ * which: 0 = cache[Y] (256c/truecolor, Q3); 1 = mono double mapping (Q1); 2 = 16-colour mapping (Q2).
+ * key_out (may be NULL) receives char_index_ramp[Y>>2] for Y in 0..255 (mono run key).
+ * returns glyph count or -1. */
+int orc_build_glyph_lut(const char *palette, int which, uint8_t out[256][5], uint8_t key_out[256]);
+
+/* downscale */
+void orc_resize_nn(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh);   /* image.c:267-328 */
+void orc_resize_box(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh);  /* our spec, DESIGN.md */
+
+/* print an already-resized image (image_print_with_capabilities, ascii.c:955-1002).
+ * Returns malloc'd NUL-terminated string, *out_len = strlen. */
+char *orc_print(const uint8_t *rgb, int w, int h, int color_level, int render_mode, const char *palette,
+                size_t *out_len);
+
+/* full convert (ascii_convert_with_capabilities, ascii.c:194-387), scale = ORC_SCALE_* */
+char *orc_convert_caps(const uint8_t *rgb, int w, int h, long width, long height, int color_level, int render_mode,
+                       int wants_padding, int use_aspect_ratio, int stretch, const char *palette, int scale,
+                       size_t *out_len);
+/* ascii_convert (ascii.c:72-191); opt_render_mode stands in for GET_OPTION(render_mode) */
+char *orc_convert(const uint8_t *rgb, int w, int h, long width, long height, int color, int aspect, int stretch,
+                  const char *palette, int opt_render_mode, size_t *out_len);
+
+char *orc_pad_width(const char *frame, size_t pad_left);     /* ascii.c:457-517 */
+char *orc_pad_height(const char *frame, size_t pad_top);     /* ascii.c:902-941 */
+
+/* text-space grid (ascii_create_grid, ascii.c:602-885) */
+char *orc_create_grid(const char *const *frames, const size_t *sizes, int n, int width, int height, size_t *out_size);
+
+/* server pixel-space composite (stream.c:523-651, 664-779).  srcs[i] = RGB24 w[i] x h[i].
+ * out must hold width * (2*height) * 3 bytes.  Returns 0, fills cols/rows. */
+void orc_grid_layout(const int *ws, const int *hs, int n, int term_w, int term_h, int *cols, int *rows);
+int orc_composite(const uint8_t *const *srcs, const int *ws, const int *hs, int n, int width, int height,
+                  uint8_t *out, int *cols, int *rows);
+
+/* synthetic inputs: 0 noise, 1 gradient, 2 bars, 3 grey, 4 solid(seed&255) */
+void orc_gen_pattern(int kind, uint32_t frame, uint8_t *dst, int w, int h);
+uint32_t orc_fnv1a32(const uint8_t *p, size_t n);
+/* exhaustive quantiser table, index r<<16|g<<8|b; which 0 = 256c, 1 = 16c, 2 = call fn(r,g,b) */
+void orc_fill_table(int which, void *fn, uint8_t *out);
+
+/* bench helper: render `frames` frames (frame i uses src + (i % ring) * w*h*3) with `threads`
+ * pthreads, frame-parallel; returns seconds, sums output bytes into *out_bytes.
+ * fn: 0 = this port, else a function pointer to the compiled reference's
+ * ascii_convert_with_capabilities (passed as void* by the harness, with its caps blob). */
+double orc_bench_convert(const uint8_t *src, int ring, int w, int h, long width, long height, int color_level,
+                         int render_mode, const char *palette, int scale, int frames, int threads,
+                         void *ref_fn, const void *ref_caps, uint64_t *out_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

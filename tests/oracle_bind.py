@@ -1,0 +1,308 @@
+"""ctypes bindings for the two CPU checkers (TEST INFRASTRUCTURE ONLY).
+
+* ``port()``  -> oracle/liboracle_port.so   : our CPU restatement (oracle/ascii_oracle.c)
+* ``ref()``   -> oracle/_ref/libasciichat_ref.so : the reference's own sources compiled
+                 unmodified by oracle/Makefile (None when it was never built)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+import this module.  Nothing under ascii-chat_b200/ does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+PORT_SO = os.path.join(ORACLE_DIR, "liboracle_port.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libasciichat_ref.so")
+REFERENCE_ROOT = "/root/reference"
+
+PALETTES = {  # include/ascii-chat/video/ascii/palette.h:161-197
+    "standard": "   ...',;:clodxkO0KXNWM",
+    "blocks": "   ░░▒▒▓▓██",
+    "digital": "   -=≡≣▰▱◼",
+    "minimal": "   .-+*#",
+    "cool": "   ▁▂▃▄▅▆▇█",
+}
+PATTERNS = {"noise": 0, "gradient": 1, "bars": 2, "grey": 3, "solid": 4}
+
+COLOR_NONE, COLOR_16, COLOR_256, COLOR_TRUE = 0, 1, 2, 3
+MODE_FG, MODE_BG, MODE_HALF = 0, 1, 2
+SCALE_NN, SCALE_BOX = 0, 1
+
+
+class Caps(C.Structure):
+    """terminal_capabilities_t — include/ascii-chat/platform/terminal.h:707-738 (240 bytes on LP64)."""
+
+    _fields_ = [
+        ("color_level", C.c_int), ("capabilities", C.c_uint32), ("color_count", C.c_uint32),
+        ("utf8_support", C.c_bool), ("detection_reliable", C.c_bool), ("render_mode", C.c_int),
+        ("term_type", C.c_char * 64), ("colorterm", C.c_char * 64), ("wants_background", C.c_bool),
+        ("palette_type", C.c_int), ("palette_custom", C.c_char * 64), ("desired_fps", C.c_uint8),
+        ("color_filter", C.c_int), ("wants_padding", C.c_bool), ("pad_height", C.c_size_t),
+    ]
+
+
+class Image(C.Structure):
+    """image_t — include/ascii-chat/video/rgba/image.h:143-148."""
+
+    _fields_ = [("w", C.c_int), ("h", C.c_int), ("pixels", C.c_void_p), ("alloc_method", C.c_uint8)]
+
+
+class FrameSource(C.Structure):
+    """ascii_frame_source_t — include/ascii-chat/video/ascii/ascii.h:358-361."""
+
+    _fields_ = [("frame_data", C.c_char_p), ("frame_size", C.c_size_t)]
+
+
+def make_caps(level, mode, pad=False):
+    c = Caps()
+    c.color_level, c.render_mode, c.utf8_support, c.wants_padding = level, mode, True, pad
+    return c
+
+
+def _make(target):
+    subprocess.run(["make", "-C", ORACLE_DIR, target], check=True, stdout=subprocess.DEVNULL)
+
+
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+
+
+def _take(ptr, n=None):
+    """copy a malloc'd C string into bytes and free it"""
+    if not ptr:
+        return None
+    out = C.string_at(ptr) if n is None else C.string_at(ptr, n)
+    _libc.free(ptr)
+    return out
+
+
+def as_u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+_port = None
+
+
+def port():
+    global _port
+    if _port is not None:
+        return _port
+    src = os.path.join(ORACLE_DIR, "ascii_oracle.c")
+    if not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(src):
+        _make("port")
+    L = C.CDLL(PORT_SO)
+    u8p = C.POINTER(C.c_uint8)
+    L.orc_print.restype = C.c_void_p
+    L.orc_print.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_size_t)]
+    L.orc_convert_caps.restype = C.c_void_p
+    L.orc_convert_caps.argtypes = [u8p, C.c_int, C.c_int, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_size_t)]
+    L.orc_convert.restype = C.c_void_p
+    L.orc_convert.argtypes = [u8p, C.c_int, C.c_int, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                              C.c_int, C.POINTER(C.c_size_t)]
+    L.orc_pad_width.restype = C.c_void_p
+    L.orc_pad_width.argtypes = [C.c_char_p, C.c_size_t]
+    L.orc_pad_height.restype = C.c_void_p
+    L.orc_pad_height.argtypes = [C.c_char_p, C.c_size_t]
+    L.orc_resize_nn.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
+    L.orc_resize_box.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
+    L.orc_gen_pattern.argtypes = [C.c_int, C.c_uint32, u8p, C.c_int, C.c_int]
+    L.orc_fnv1a32.restype = C.c_uint32
+    L.orc_fnv1a32.argtypes = [C.c_char_p, C.c_size_t]
+    L.orc_fill_table.argtypes = [C.c_int, C.c_void_p, u8p]
+    L.orc_rgb_to_256.argtypes = [C.c_int] * 3
+    L.orc_rgb_to_16.argtypes = [C.c_int] * 3
+    L.orc_rep_is_profitable.argtypes = [C.c_uint32]
+    L.orc_digits_u32.argtypes = [C.c_uint32]
+    L.orc_aspect_ratio.argtypes = [C.c_long] * 4 + [C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+    L.orc_build_glyph_lut.argtypes = [C.c_char_p, C.c_int, u8p, u8p]
+    L.orc_create_grid.restype = C.c_void_p
+    L.orc_create_grid.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_size_t)]
+    L.orc_grid_layout.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.orc_composite.argtypes = [C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
+                                u8p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.orc_bench_convert.restype = C.c_double
+    L.orc_bench_convert.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_long, C.c_int, C.c_int, C.c_char_p,
+                                    C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    _port = L
+    return L
+
+
+_ref = False
+
+
+def ref():
+    """the compiled reference, or None if oracle/_ref was never built and cannot be built here"""
+    global _ref
+    if _ref is not False:
+        return _ref
+    if not os.path.exists(REF_SO) and os.path.isdir(os.path.join(REFERENCE_ROOT, "lib", "video", "ascii")):
+        _make("ref")
+    if not os.path.exists(REF_SO):
+        _ref = None
+        return None
+    L = C.CDLL(REF_SO)
+    ip, cp = C.POINTER(Image), C.POINTER(Caps)
+    L.ascii_convert_with_capabilities.restype = C.c_void_p
+    L.ascii_convert_with_capabilities.argtypes = [ip, C.c_ssize_t, C.c_ssize_t, cp, C.c_bool, C.c_bool, C.c_char_p]
+    L.ascii_convert.restype = C.c_void_p
+    L.ascii_convert.argtypes = [ip, C.c_ssize_t, C.c_ssize_t, C.c_bool, C.c_bool, C.c_bool, C.c_char_p, C.c_char_p]
+    L.image_print_with_capabilities.restype = C.c_void_p
+    L.image_print_with_capabilities.argtypes = [ip, cp, C.c_char_p]
+    L.image_resize.argtypes = [ip, ip]
+    L.ascii_create_grid.restype = C.c_void_p
+    L.ascii_create_grid.argtypes = [C.POINTER(FrameSource), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+    L.ascii_pad_frame_width.restype = C.c_void_p
+    L.ascii_pad_frame_width.argtypes = [C.c_char_p, C.c_size_t]
+    L.ascii_pad_frame_height.restype = C.c_void_p
+    L.ascii_pad_frame_height.argtypes = [C.c_char_p, C.c_size_t]
+    L.rgb_to_256color.restype = C.c_uint8
+    L.rgb_to_256color.argtypes = [C.c_uint8] * 3
+    L.rgb_to_16color.restype = C.c_uint8
+    L.rgb_to_16color.argtypes = [C.c_uint8] * 3
+    L.rep_is_profitable.restype = C.c_bool
+    L.rep_is_profitable.argtypes = [C.c_uint32]
+    L.aspect_ratio.argtypes = [C.c_ssize_t] * 4 + [C.c_bool, C.POINTER(C.c_ssize_t), C.POINTER(C.c_ssize_t)]
+    L.append_truecolor_fg.restype = C.c_void_p
+    L.append_truecolor_fg.argtypes = [C.c_char_p, C.c_uint8, C.c_uint8, C.c_uint8]
+    L.append_truecolor_bg.restype = C.c_void_p
+    L.append_truecolor_bg.argtypes = [C.c_char_p, C.c_uint8, C.c_uint8, C.c_uint8]
+    L.append_256color_fg.restype = C.c_void_p
+    L.append_256color_fg.argtypes = [C.c_char_p, C.c_uint8]
+    L.append_16color_fg.restype = C.c_void_p
+    L.append_16color_fg.argtypes = [C.c_char_p, C.c_uint8]
+    L.append_16color_bg.restype = C.c_void_p
+    L.append_16color_bg.argtypes = [C.c_char_p, C.c_uint8]
+    L.ansi_fast_init_256color.restype = None
+    L.ansi_fast_init_16color.restype = None
+    L.ascii_simd_init.restype = None
+    L.ref_oracle_set_render_mode.argtypes = [C.c_int]
+    L.ascii_simd_init()
+    L.ansi_fast_init_256color()
+    L.ansi_fast_init_16color()
+    _ref = L
+    return L
+
+
+# ----------------------------------------------------------------------------- helpers
+def gen(kind, w, h, frame=0):
+    """synthetic RGB24 frame (SURVEY.md Appendix C generators), shape (h, w, 3) uint8"""
+    out = np.empty((h, w, 3), np.uint8)
+    port().orc_gen_pattern(PATTERNS[kind] if isinstance(kind, str) else kind, frame,
+                           out.ctypes.data_as(C.POINTER(C.c_uint8)), w, h)
+    return out
+
+
+def fnv(b):
+    return int(port().orc_fnv1a32(b, len(b)))
+
+
+def pal_bytes(p):
+    return PALETTES.get(p, p).encode() if isinstance(p, str) else p
+
+
+def port_convert(img, cols, rows, level, mode, palette="standard", aspect=False, stretch=False, pad=False,
+                 scale=SCALE_NN):
+    a, p = as_u8(img)
+    n = C.c_size_t(0)
+    r = port().orc_convert_caps(p, a.shape[1], a.shape[0], cols, rows, level, mode, int(pad), int(aspect),
+                                int(stretch), pal_bytes(palette), scale, C.byref(n))
+    return _take(r)
+
+
+def port_print(img, level, mode, palette="standard"):
+    a, p = as_u8(img)
+    n = C.c_size_t(0)
+    return _take(port().orc_print(p, a.shape[1], a.shape[0], level, mode, pal_bytes(palette), C.byref(n)))
+
+
+def port_convert_legacy(img, cols, rows, color, aspect, stretch, palette="standard", opt_mode=0):
+    a, p = as_u8(img)
+    n = C.c_size_t(0)
+    return _take(port().orc_convert(p, a.shape[1], a.shape[0], cols, rows, int(color), int(aspect), int(stretch),
+                                    pal_bytes(palette), opt_mode, C.byref(n)))
+
+
+def port_resize(img, dw, dh, scale=SCALE_NN):
+    a, p = as_u8(img)
+    out = np.empty((dh, dw, 3), np.uint8)
+    fn = port().orc_resize_box if scale == SCALE_BOX else port().orc_resize_nn
+    fn(p, a.shape[1], a.shape[0], out.ctypes.data_as(C.POINTER(C.c_uint8)), dw, dh)
+    return out
+
+
+def ref_convert(img, cols, rows, level, mode, palette="standard", aspect=False, stretch=False, pad=False):
+    a, _ = as_u8(img)
+    im = Image(a.shape[1], a.shape[0], a.ctypes.data, 0)
+    caps = make_caps(level, mode, pad)
+    return _take(ref().ascii_convert_with_capabilities(C.byref(im), cols, rows, C.byref(caps), aspect, stretch,
+                                                       pal_bytes(palette)))
+
+
+def ref_print(img, level, mode, palette="standard"):
+    a, _ = as_u8(img)
+    im = Image(a.shape[1], a.shape[0], a.ctypes.data, 0)
+    caps = make_caps(level, mode)
+    return _take(ref().image_print_with_capabilities(C.byref(im), C.byref(caps), pal_bytes(palette)))
+
+
+def ref_convert_legacy(img, cols, rows, color, aspect, stretch, palette="standard", opt_mode=0):
+    a, _ = as_u8(img)
+    im = Image(a.shape[1], a.shape[0], a.ctypes.data, 0)
+    ref().ref_oracle_set_render_mode(opt_mode)
+    lum = bytes(range(1, 256)) + b"\x01"
+    r = _take(ref().ascii_convert(C.byref(im), cols, rows, color, aspect, stretch, pal_bytes(palette), lum))
+    ref().ref_oracle_set_render_mode(0)
+    return r
+
+
+def ref_resize(img, dw, dh):
+    a, _ = as_u8(img)
+    out = np.zeros((dh, dw, 3), np.uint8)
+    s = Image(a.shape[1], a.shape[0], a.ctypes.data, 0)
+    d = Image(dw, dh, out.ctypes.data, 0)
+    ref().image_resize(C.byref(s), C.byref(d))
+    return out
+
+
+def ref_create_grid(frames, width, height):
+    arr = (FrameSource * len(frames))()
+    keep = []
+    for i, f in enumerate(frames):
+        if f is None:
+            arr[i].frame_data, arr[i].frame_size = None, 0
+        else:
+            keep.append(f)
+            arr[i].frame_data, arr[i].frame_size = f, len(f)
+    n = C.c_size_t(0)
+    r = ref().ascii_create_grid(arr, len(frames), width, height, C.byref(n))
+    return _take(r), n.value
+
+
+def port_create_grid(frames, width, height):
+    k = len(frames)
+    ptrs = (C.c_char_p * k)(*[f for f in frames])
+    sizes = (C.c_size_t * k)(*[0 if f is None else len(f) for f in frames])
+    n = C.c_size_t(0)
+    r = port().orc_create_grid(ptrs, sizes, k, width, height, C.byref(n))
+    return _take(r), n.value
+
+
+def port_composite(srcs, width, height):
+    k = len(srcs)
+    arrs = [np.ascontiguousarray(s, np.uint8) for s in srcs]
+    u8p = C.POINTER(C.c_uint8)
+    ptrs = (u8p * k)(*[a.ctypes.data_as(u8p) for a in arrs])
+    ws = (C.c_int * k)(*[a.shape[1] for a in arrs])
+    hs = (C.c_int * k)(*[a.shape[0] for a in arrs])
+    out = np.empty((height * 2, width, 3), np.uint8)
+    c, r = C.c_int(0), C.c_int(0)
+    port().orc_composite(ptrs, ws, hs, k, width, height, out.ctypes.data_as(u8p), C.byref(c), C.byref(r))
+    return out, c.value, r.value

@@ -1,0 +1,250 @@
+"""CPU tests that PIN the oracle (oracle/ascii_oracle.c, "the port").
+
+Three anchors, strongest first:
+  1. the compiled reference itself (oracle/_ref, built from /root/reference by oracle/Makefile)
+     on randomised matrices — skipped only where that library was never built;
+  2. committed fingerprints of the compiled reference's output (tests/golden/reference_vectors.json,
+     made by tests/golden/make_golden.py), incl. the survey's Appendix-C anchors;
+  3. the known-answer values the reference's own unit tests hold for this path
+     (tests/unit/util/ansi_fast_test.c, output_buffer_test.c, aspect_ratio_test.c).
+"""
+import ctypes as C
+import itertools
+
+import numpy as np
+import pytest
+
+LEVELS = (0, 1, 2, 3)
+MODES = (0, 1, 2)
+
+
+# ----------------------------------------------------------------- 2. golden fingerprints
+def test_port_matches_golden_frames(ob, golden):
+    bad = []
+    for rec in golden["frames"]:
+        img = ob.gen(rec["pattern"], rec["W"], rec["H"], 0)
+        s = ob.port_convert(img, rec["cols"], rec["rows"], rec["level"], rec["mode"], rec["palette"],
+                            bool(rec["aspect"]), False, bool(rec["pad"]))
+        got = (len(s), s.count(b"\n"), "%08x" % ob.fnv(s))
+        if got != (rec["bytes"], rec["newlines"], rec["fnv"]):
+            bad.append((rec, got))
+    assert not bad, bad[:3]
+
+
+def test_port_quantiser_tables_match_golden(ob, golden):
+    tab = np.empty(1 << 24, np.uint8)
+    p = tab.ctypes.data_as(C.POINTER(C.c_uint8))
+    ob.port().orc_fill_table(0, None, p)
+    assert "%08x" % ob.fnv(tab.tobytes()) == golden["rgb_to_256color_table_fnv"]
+    ob.port().orc_fill_table(1, None, p)
+    assert "%08x" % ob.fnv(tab.tobytes()) == golden["rgb_to_16color_table_fnv"]
+
+
+def test_port_quirk_literals(ob, golden):
+    """SURVEY.md §8a Q1-Q5 on an all-white 8x2 image."""
+    white = np.full((2, 8, 3), 255, np.uint8)
+    q = golden["quirks"]
+    assert ob.port_print(white, 0, 0) == q["Q1_mono"].encode("latin-1") == b";\x1b[7b\n;\x1b[7b"
+    assert ob.port_print(white, 1, 0) == q["Q2_16"].encode("latin-1")
+    assert ob.port_print(white, 2, 0) == q["Q3_256"].encode("latin-1")
+    assert ob.port_print(white, 3, 0) == q["Q3_true"].encode("latin-1")
+    assert ob.port_print(white, 3, 1) == q["Q4_true_bg"].encode("latin-1")
+    assert ob.port_print(white, 3, 2) == q["Q5_half"].encode("latin-1")
+
+
+def test_port_glyph_tables_match_golden(ob, golden):
+    ramp = np.repeat(np.arange(256, dtype=np.uint8)[None, :, None], 3, axis=2)
+    for pal, h in golden["glyph_tables"].items():
+        assert "%08x" % ob.fnv(ob.port_print(ramp, 0, 0, pal)) == h["mono"], pal
+        assert "%08x" % ob.fnv(ob.port_print(ramp, 1, 0, pal)) == h["c16"], pal
+        assert "%08x" % ob.fnv(ob.port_print(ramp, 2, 0, pal)) == h["c256"], pal
+        assert "%08x" % ob.fnv(ob.port_print(ramp, 3, 0, pal)) == h["true"], pal
+
+
+def _nn_src(sw, sh):
+    src = np.zeros((sh, sw, 3), np.uint8)
+    xs = np.arange(sw, dtype=np.uint32)
+    ys = np.arange(sh, dtype=np.uint32)
+    src[:, :, 0] = (xs & 255)[None, :]
+    src[:, :, 1] = ((xs >> 8) & 255)[None, :] | ((ys[:, None] >> 8) << 6).astype(np.uint8)
+    src[:, :, 2] = (ys & 255)[:, None]
+    return src
+
+
+def test_port_nn_resize_matches_golden(ob, golden):
+    for rec in golden["nn_resize"]:
+        out = ob.port_resize(_nn_src(rec["sw"], rec["sh"]), rec["dw"], rec["dh"])
+        assert "%08x" % ob.fnv(out.tobytes()) == rec["fnv"], rec
+
+
+def test_port_text_grid_matches_golden(ob, golden):
+    for rec in golden["text_grids"]:
+        srcs = [ob.port_convert(ob.gen("noise" if i % 2 else "bars", 160, 120, i), rec["cols"], rec["rows"],
+                                rec["level"], rec["mode"]) for i in range(rec["n"])]
+        g, sz = ob.port_create_grid(srcs, rec["W"], rec["H"])
+        assert (sz, "%08x" % ob.fnv(g)) == (rec["size"], rec["fnv"]), rec
+
+
+# ----------------------------------------------------------------- 3. the reference's own KATs
+def test_kat_sgr_strings(ob):
+    """ansi_fast_test.c:60,102,300,312,316,383-455 — observed through 1x1 renders of the port."""
+    px = lambda r, g, b: np.array([[[r, g, b]]], np.uint8)  # noqa: E731
+    s = ob.port_print(px(255, 128, 64), 3, 0)
+    assert s.startswith(b"\033[38;2;255;128;64m") and s.endswith(b"\033[0m")
+    s = ob.port_print(np.array([[[255, 128, 64]], [[100, 200, 50]]], np.uint8), 3, 2)
+    assert s == b"\033[38;2;255;128;64m\033[48;2;100;200;50m\xe2\x96\x80\033[0m"
+    assert ob.port_print(px(255, 255, 255), 2, 0).startswith(b"\033[38;5;255m")
+    assert ob.port_print(px(0, 0, 0), 2, 0).startswith(b"\033[38;5;232m")
+    assert ob.port_print(px(128, 0, 0), 1, 0).startswith(b"\033[31m")
+    assert ob.port_print(px(0, 128, 0), 1, 0).startswith(b"\033[32m")
+    assert ob.port_print(px(255, 255, 255), 1, 0).startswith(b"\033[97m")
+
+
+def test_kat_rgb_to_16color(ob):
+    """ansi_fast_test.c:458-492"""
+    P = ob.port()
+    for rgb, idx in (((255, 0, 0), 9), ((0, 255, 0), 10), ((0, 0, 255), 12), ((0, 0, 0), 0), ((255, 255, 255), 15),
+                     ((128, 0, 0), 1), ((0, 128, 0), 2), ((0, 0, 128), 4), ((192, 192, 192), 7)):
+        assert P.orc_rgb_to_16(*rgb) == idx
+
+
+def test_kat_rgb_to_256color_ranges(ob):
+    """ansi_fast_test.c:319-366 only range-checks: greys -> 232..255, colours -> cube 16..231"""
+    P = ob.port()
+    for v in range(256):
+        assert 232 <= P.orc_rgb_to_256(v, v, v) <= 255
+    for rgb in ((255, 0, 0), (0, 255, 0), (0, 0, 255), (255, 255, 0), (40, 200, 90)):
+        assert 16 <= P.orc_rgb_to_256(*rgb) <= 231
+
+
+def test_kat_rep_and_digits(ob):
+    """output_buffer_test.c:297-305, 337-350"""
+    P = ob.port()
+    assert [bool(P.orc_rep_is_profitable(n)) for n in (0, 1, 2, 3, 4, 5, 6, 10, 100)] == [False] * 6 + [True] * 3
+    for v, d in ((0, 1), (9, 1), (10, 2), (99, 2), (100, 3), (999, 3), (1000, 4), (9999, 4), (10000, 5),
+                 (100000, 6), (1000000, 7), (10000000, 8), (100000000, 9), (1000000000, 10), (4294967295, 10)):
+        assert P.orc_digits_u32(v) == d
+
+
+def _aspect(ob, iw, ih, w, h, stretch=False):
+    ow, oh = C.c_long(0), C.c_long(0)
+    ob.port().orc_aspect_ratio(iw, ih, w, h, int(stretch), C.byref(ow), C.byref(oh))
+    return ow.value, oh.value
+
+
+def test_kat_aspect_ratio(ob):
+    """aspect_ratio_test.c:36-39 (stretch), :100-103 (degenerate -> 1x1); SURVEY §8a a2 worked values"""
+    assert _aspect(ob, 1920, 1080, 80, 24, True) == (80, 24)
+    for iw, ih in ((0, 1080), (1920, 0), (-1920, 1080), (1920, -1080)):
+        assert _aspect(ob, iw, ih, 80, 24) == (1, 1)
+    assert _aspect(ob, 3840, 2160, 320, 96) == (320, 90)
+    assert _aspect(ob, 1920, 1080, 160, 48) == (160, 45)
+
+
+# ----------------------------------------------------------------- 1. against the compiled reference
+def test_port_vs_ref_matrix(ob, ref_lib):
+    shapes = [(64, 48, 16, 8), (100, 37, 33, 11), (17, 9, 5, 3), (320, 240, 80, 24), (8, 2, 8, 2), (31, 64, 40, 20)]
+    n = 0
+    for pat, (W, H, c, r) in itertools.product(("noise", "gradient", "bars", "grey", "solid"), shapes):
+        img = ob.gen(pat, W, H, 3)
+        for level, mode, pal in itertools.product(LEVELS, MODES, ("standard", "blocks", "digital", "minimal")):
+            for aspect, pad in ((False, False), (True, True), (True, False)):
+                a = ob.ref_convert(img, c, r, level, mode, pal, aspect, False, pad)
+                b = ob.port_convert(img, c, r, level, mode, pal, aspect, False, pad)
+                assert a == b, (pat, W, H, c, r, level, mode, pal, aspect, pad)
+                n += 1
+    assert n > 3000
+
+
+def test_port_vs_ref_random_images(ob, ref_lib):
+    """low-entropy random images: long runs, black holes, near-grey colours, 2-colour stripes"""
+    rng = np.random.default_rng(7)
+    for it in range(60):
+        w, h = int(rng.integers(1, 70)), int(rng.integers(1, 40))
+        kind = it % 4
+        if kind == 0:
+            img = rng.integers(0, 2, (h, w, 1), dtype=np.uint8).repeat(3, axis=2) * 255
+        elif kind == 1:
+            img = (rng.integers(0, 3, (h, w, 3)) * 20).astype(np.uint8)
+        elif kind == 2:
+            img = np.repeat(rng.integers(0, 256, (h, (w + 6) // 7, 3), dtype=np.uint8), 7, axis=1)[:, :w]
+        else:
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            img[rng.random((h, w)) < 0.4] = 0
+        for level, mode in itertools.product(LEVELS, MODES):
+            for pal in ("standard", "cool"):
+                assert ob.ref_print(img, level, mode, pal) == ob.port_print(img, level, mode, pal), (it, level, mode)
+
+
+def test_port_vs_ref_legacy_ascii_convert(ob, ref_lib):
+    img = ob.gen("noise", 120, 90, 1)
+    for color, aspect, stretch, opt in itertools.product((False, True), (False, True), (False, True), MODES):
+        a = ob.ref_convert_legacy(img, 40, 20, color, aspect, stretch, "standard", opt)
+        b = ob.port_convert_legacy(img, 40, 20, color, aspect, stretch, "standard", opt)
+        assert a == b, (color, aspect, stretch, opt)
+
+
+def test_port_vs_ref_resize_and_aspect(ob, ref_lib):
+    rng = np.random.default_rng(3)
+    for _ in range(40):
+        sw, sh, dw, dh = (int(rng.integers(1, 300)) for _ in range(4))
+        src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(ob.ref_resize(src, dw, dh), ob.port_resize(src, dw, dh)), (sw, sh, dw, dh)
+    for _ in range(3000):
+        iw, ih, w, h = (int(rng.integers(1, 4000)) for _ in range(4))
+        ow, oh = C.c_ssize_t(0), C.c_ssize_t(0)
+        ref_lib.aspect_ratio(iw, ih, w, h, False, C.byref(ow), C.byref(oh))
+        assert (ow.value, oh.value) == _aspect(ob, iw, ih, w, h), (iw, ih, w, h)
+
+
+def test_port_vs_ref_quantiser_tables(ob, ref_lib, golden):
+    a = np.empty(1 << 24, np.uint8)
+    b = np.empty(1 << 24, np.uint8)
+    u8p = C.POINTER(C.c_uint8)
+    for which, fn in ((0, ref_lib.rgb_to_256color), (1, ref_lib.rgb_to_16color)):
+        ob.port().orc_fill_table(2, C.cast(fn, C.c_void_p), a.ctypes.data_as(u8p))
+        ob.port().orc_fill_table(which, None, b.ctypes.data_as(u8p))
+        assert np.array_equal(a, b)
+
+
+def test_port_vs_ref_text_grid(ob, ref_lib):
+    rng = np.random.default_rng(11)
+    for it in range(40):
+        n = int(rng.integers(1, 10))
+        level, mode = int(rng.integers(0, 4)), int(rng.choice([0, 2]))
+        cols, rows = int(rng.integers(8, 50)), int(rng.integers(3, 16))
+        srcs = [ob.ref_convert(ob.gen(("noise", "bars", "gradient")[i % 3], 96, 64, i), cols, rows, level, mode)
+                for i in range(n)]
+        W, H = int(rng.integers(10, 200)), int(rng.integers(3, 60))
+        a = ob.ref_create_grid(srcs, W, H)
+        b = ob.port_create_grid(srcs, W, H)
+        assert a == b, (it, n, W, H)
+
+
+def test_port_vs_ref_padding(ob, ref_lib):
+    s = b"ab\ncd\n\nxyz"
+    for pad in (0, 1, 5):
+        a = ob._take(ref_lib.ascii_pad_frame_width(s, pad))
+        assert a == ob._take(ob.port().orc_pad_width(s, pad))
+        a = ob._take(ref_lib.ascii_pad_frame_height(s, pad))
+        assert a == ob._take(ob.port().orc_pad_height(s, pad))
+
+
+def test_box_filter_spec(ob):
+    """our box-filter specification: identity at 1:1, exact means, rounding half up"""
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 256, (48, 64, 3), dtype=np.uint8)
+    assert np.array_equal(ob.port_resize(src, 64, 48, ob.SCALE_BOX), src)
+    out = ob.port_resize(src, 16, 12, ob.SCALE_BOX)
+    blk = src.reshape(12, 4, 16, 4, 3).astype(np.uint32).sum(axis=(1, 3))
+    assert np.array_equal(out, ((blk + 8) // 16).astype(np.uint8))
+    # ragged boundaries: floor(dx*sw/dw) partition covers every source pixel exactly once
+    src = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    out = ob.port_resize(src, 10, 7, ob.SCALE_BOX)
+    xs = [(d * 53) // 10 for d in range(11)]
+    ys = [(d * 37) // 7 for d in range(8)]
+    for dy in range(7):
+        for dx in range(10):
+            b = src[ys[dy]:ys[dy + 1], xs[dx]:xs[dx + 1]].astype(np.uint32)
+            n = b.shape[0] * b.shape[1]
+            assert np.array_equal(out[dy, dx], ((b.sum(axis=(0, 1)) + n // 2) // n).astype(np.uint8))
