@@ -1,0 +1,300 @@
+"""ctypes mirror of include/asciichat_b200.h.
+
+Function names, argument meaning and error behaviour are the reference's (libasciichat):
+``ascii_convert_with_capabilities`` returns the frame string or ``None`` where the C function
+returns NULL.  Buffers are numpy (host) or raw device pointers (batch API); torch is used by
+callers only for device memory and process groups.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libasciichat_b200.so")
+
+TERM_COLOR_NONE, TERM_COLOR_16, TERM_COLOR_256, TERM_COLOR_TRUECOLOR = 0, 1, 2, 3
+RENDER_MODE_FOREGROUND, RENDER_MODE_BACKGROUND, RENDER_MODE_HALF_BLOCK = 0, 1, 2
+SCALE_NN, SCALE_BOX = 0, 1
+
+PALETTE_CHARS_STANDARD = "   ...',;:clodxkO0KXNWM"  # palette.h:161
+PALETTE_CHARS_BLOCKS = "   ░░▒▒▓▓██"
+PALETTE_CHARS_DIGITAL = "   -=≡≣▰▱◼"
+PALETTE_CHARS_MINIMAL = "   .-+*#"
+PALETTE_CHARS_COOL = "   ▁▂▃▄▅▆▇█"
+PALETTES = {"standard": PALETTE_CHARS_STANDARD, "blocks": PALETTE_CHARS_BLOCKS, "digital": PALETTE_CHARS_DIGITAL,
+            "minimal": PALETTE_CHARS_MINIMAL, "cool": PALETTE_CHARS_COOL}
+
+
+class image_t(C.Structure):  # image.h:143-148
+    _fields_ = [("w", C.c_int), ("h", C.c_int), ("pixels", C.c_void_p), ("alloc_method", C.c_uint8)]
+
+
+class terminal_capabilities_t(C.Structure):  # platform/terminal.h:707-738
+    _fields_ = [
+        ("color_level", C.c_int), ("capabilities", C.c_uint32), ("color_count", C.c_uint32),
+        ("utf8_support", C.c_bool), ("detection_reliable", C.c_bool), ("render_mode", C.c_int),
+        ("term_type", C.c_char * 64), ("colorterm", C.c_char * 64), ("wants_background", C.c_bool),
+        ("palette_type", C.c_int), ("palette_custom", C.c_char * 64), ("desired_fps", C.c_uint8),
+        ("color_filter", C.c_int), ("wants_padding", C.c_bool), ("pad_height", C.c_size_t),
+    ]
+
+
+class ascii_frame_source_t(C.Structure):  # ascii.h:358-361
+    _fields_ = [("frame_data", C.c_char_p), ("frame_size", C.c_size_t)]
+
+
+class acb200_render_cfg_t(C.Structure):
+    _fields_ = [("src_w", C.c_int), ("src_h", C.c_int), ("cols", C.c_int), ("rows_px", C.c_int),
+                ("color_level", C.c_int), ("render_mode", C.c_int), ("scale", C.c_int), ("pad_left", C.c_int),
+                ("pad_top", C.c_int), ("palette", C.c_char_p)]
+
+
+EXPORTS = [  # every symbol include/asciichat_b200.h declares
+    "ascii_convert", "ascii_convert_with_capabilities", "image_print_with_capabilities", "image_resize",
+    "image_print", "image_print_color", "image_print_256color", "image_print_16color",
+    "image_print_16color_dithered_with_background", "rgb_to_truecolor_halfblocks_scalar", "rgb_to_halfblocks_scalar",
+    "rgb_to_16color_halfblocks_scalar", "rgb_to_256color_halfblocks_scalar", "ascii_create_grid", "ascii_simd_init",
+    "simd_caches_destroy_all", "acb200_init", "acb200_shutdown", "acb200_last_error", "acb200_last_error_message",
+    "acb200_set_allocator", "acb200_set_option_render_mode", "acb200_set_default_scale", "acb200_frame_capacity",
+    "acb200_scratch_bytes", "acb200_render_batch_device", "acb200_render_batch_host", "acb200_time_batch_device",
+    "acb200_composite_host", "acb200_grid_layout", "acb200_aspect_ratio", "acb200_launch_count", "acb200_version",
+    "acb200_create_grid_device",
+]
+
+
+def build_library(force=False):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("acb200_build", os.path.join(HERE, "build.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.build(force=force)
+
+
+_lib = None
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+
+
+def lib():
+    """load libasciichat_b200.so (raises if it was never built: there is no fallback)"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libasciichat_b200.so is not built: run `python ascii-chat_b200/build.py` "
+                           "(or __graft_entry__.build()); this package has no non-CUDA path")
+    L = C.CDLL(LIB_PATH)
+    ip, cp = C.POINTER(image_t), C.POINTER(terminal_capabilities_t)
+    u8p = C.POINTER(C.c_uint8)
+    cfgp = C.POINTER(acb200_render_cfg_t)
+    L.ascii_convert_with_capabilities.restype = C.c_void_p
+    L.ascii_convert_with_capabilities.argtypes = [ip, C.c_ssize_t, C.c_ssize_t, cp, C.c_bool, C.c_bool, C.c_char_p]
+    L.ascii_convert.restype = C.c_void_p
+    L.ascii_convert.argtypes = [ip, C.c_ssize_t, C.c_ssize_t, C.c_bool, C.c_bool, C.c_bool, C.c_char_p, C.c_char_p]
+    L.image_print_with_capabilities.restype = C.c_void_p
+    L.image_print_with_capabilities.argtypes = [ip, cp, C.c_char_p]
+    L.image_resize.restype = None
+    L.image_resize.argtypes = [ip, ip]
+    for name in ("image_print", "image_print_color", "image_print_256color", "image_print_16color"):
+        getattr(L, name).restype = C.c_void_p
+        getattr(L, name).argtypes = [ip, C.c_char_p]
+    L.image_print_16color_dithered_with_background.restype = C.c_void_p
+    L.image_print_16color_dithered_with_background.argtypes = [ip, C.c_bool, C.c_char_p]
+    L.rgb_to_truecolor_halfblocks_scalar.restype = C.c_void_p
+    L.rgb_to_truecolor_halfblocks_scalar.argtypes = [u8p, C.c_int, C.c_int, C.c_int]
+    for name in ("rgb_to_halfblocks_scalar", "rgb_to_16color_halfblocks_scalar", "rgb_to_256color_halfblocks_scalar"):
+        getattr(L, name).restype = C.c_void_p
+        getattr(L, name).argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_char_p]
+    L.ascii_create_grid.restype = C.c_void_p
+    L.ascii_create_grid.argtypes = [C.POINTER(ascii_frame_source_t), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+    L.ascii_simd_init.restype = None
+    L.simd_caches_destroy_all.restype = None
+    L.acb200_init.argtypes = [C.c_int]
+    L.acb200_last_error_message.restype = C.c_char_p
+    L.acb200_set_option_render_mode.argtypes = [C.c_int]
+    L.acb200_set_default_scale.argtypes = [C.c_int]
+    L.acb200_frame_capacity.restype = C.c_size_t
+    L.acb200_frame_capacity.argtypes = [cfgp]
+    L.acb200_scratch_bytes.restype = C.c_size_t
+    L.acb200_scratch_bytes.argtypes = [cfgp, C.c_int]
+    L.acb200_render_batch_device.argtypes = [cfgp, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]
+    L.acb200_render_batch_host.argtypes = [cfgp, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_size_t)]
+    L.acb200_time_batch_device.argtypes = [cfgp, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                           C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.acb200_composite_host.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.acb200_grid_layout.restype = None
+    L.acb200_grid_layout.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.acb200_aspect_ratio.restype = None
+    L.acb200_aspect_ratio.argtypes = [C.c_ssize_t] * 4 + [C.c_bool, C.POINTER(C.c_ssize_t), C.POINTER(C.c_ssize_t)]
+    L.acb200_launch_count.restype = C.c_uint64
+    L.acb200_version.restype = C.c_char_p
+    L.acb200_create_grid_device.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p]
+    _lib = L
+    return L
+
+
+def last_error():
+    L = lib()
+    return L.acb200_last_error(), (L.acb200_last_error_message() or b"").decode("utf-8", "replace")
+
+
+def _take(ptr):
+    if not ptr:
+        return None
+    s = C.string_at(ptr)
+    _libc.free(ptr)
+    return s
+
+
+def _pal(p):
+    if p is None:
+        return None
+    return PALETTES.get(p, p).encode() if isinstance(p, str) else p
+
+
+def _img(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    assert a.ndim == 3 and a.shape[2] == 3
+    return a, image_t(a.shape[1], a.shape[0], a.ctypes.data, 0)
+
+
+def make_caps(color_level, render_mode, wants_padding=False):
+    c = terminal_capabilities_t()
+    c.color_level, c.render_mode, c.utf8_support, c.wants_padding = color_level, render_mode, True, wants_padding
+    return c
+
+
+def make_cfg(src_w, src_h, cols, rows_px, color_level, render_mode, palette="standard", scale=SCALE_NN, pad_left=0,
+             pad_top=0):
+    return acb200_render_cfg_t(src_w, src_h, cols, rows_px, color_level, render_mode, scale, pad_left, pad_top,
+                               _pal(palette))
+
+
+# ---- the reference's entry points -------------------------------------------------------------
+def ascii_convert_with_capabilities(image, width, height, caps, use_aspect_ratio, stretch, palette_chars):
+    a, im = _img(image)
+    return _take(lib().ascii_convert_with_capabilities(C.byref(im), width, height, C.byref(caps), use_aspect_ratio,
+                                                       stretch, _pal(palette_chars)))
+
+
+def ascii_convert(image, width, height, color, aspect_ratio, stretch, palette_chars, luminance_palette=None):
+    a, im = _img(image)
+    lum = luminance_palette if luminance_palette is not None else bytes(range(1, 256)) + b"\x01"
+    return _take(lib().ascii_convert(C.byref(im), width, height, color, aspect_ratio, stretch, _pal(palette_chars), lum))
+
+
+def image_print_with_capabilities(image, caps, palette):
+    a, im = _img(image)
+    return _take(lib().image_print_with_capabilities(C.byref(im), C.byref(caps), _pal(palette)))
+
+
+def image_resize(image, dw, dh):
+    a, src = _img(image)
+    out = np.zeros((dh, dw, 3), np.uint8)
+    dst = image_t(dw, dh, out.ctypes.data, 0)
+    lib().image_resize(C.byref(src), C.byref(dst))
+    return out
+
+
+def ascii_create_grid(frames, width, height):
+    arr = (ascii_frame_source_t * len(frames))()
+    for i, f in enumerate(frames):
+        arr[i].frame_data, arr[i].frame_size = (f, len(f)) if f is not None else (None, 0)
+    n = C.c_size_t(0)
+    r = lib().ascii_create_grid(arr, len(frames), width, height, C.byref(n))
+    return _take(r), n.value
+
+
+def composite(srcs, width, height):
+    """server pixel-space composite (stream.c:664-779): list of (h,w,3) arrays -> (2*height, width, 3)"""
+    arrs = [np.ascontiguousarray(s, np.uint8) for s in srcs]
+    k = len(arrs)
+    ptrs = (C.c_void_p * k)(*[a.ctypes.data for a in arrs])
+    ws = (C.c_int * k)(*[a.shape[1] for a in arrs])
+    hs = (C.c_int * k)(*[a.shape[0] for a in arrs])
+    out = np.empty((height * 2, width, 3), np.uint8)
+    c, r = C.c_int(0), C.c_int(0)
+    rc = lib().acb200_composite_host(ptrs, ws, hs, k, width, height, out.ctypes.data, C.byref(c), C.byref(r))
+    if rc:
+        raise RuntimeError("acb200_composite_host failed: %s" % (last_error(),))
+    return out, c.value, r.value
+
+
+def aspect_ratio(img_w, img_h, width, height, stretch=False):
+    ow, oh = C.c_ssize_t(0), C.c_ssize_t(0)
+    lib().acb200_aspect_ratio(img_w, img_h, width, height, stretch, C.byref(ow), C.byref(oh))
+    return ow.value, oh.value
+
+
+# ---- batch interface --------------------------------------------------------------------------
+def render_batch_host(cfg, frames):
+    """frames: list of contiguous uint8 arrays (h,w,3) on the host -> list of bytes"""
+    arrs = [np.ascontiguousarray(f, np.uint8) for f in frames]
+    k = len(arrs)
+    ptrs = (C.c_void_p * k)(*[a.ctypes.data for a in arrs])
+    outs = (C.c_void_p * k)()
+    lens = (C.c_size_t * k)()
+    rc = lib().acb200_render_batch_host(C.byref(cfg), ptrs, k, outs, lens)
+    if rc:
+        raise RuntimeError("acb200_render_batch_host failed: %s" % (last_error(),))
+    res = []
+    for i in range(k):
+        res.append(C.string_at(outs[i], lens[i]))
+        _libc.free(outs[i])
+    return res
+
+
+def render_batch_host_ptrs(cfg, ptr_array, k, outs, lens):
+    """zero-overhead variant for timing loops: caller owns the ctypes arrays; strings must be freed"""
+    return lib().acb200_render_batch_host(C.byref(cfg), ptr_array, k, outs, lens)
+
+
+def free_strings(outs, k):
+    for i in range(k):
+        if outs[i]:
+            _libc.free(outs[i])
+            outs[i] = None
+
+
+def frame_capacity(cfg):
+    return lib().acb200_frame_capacity(C.byref(cfg))
+
+
+def scratch_bytes(cfg, n):
+    return lib().acb200_scratch_bytes(C.byref(cfg), n)
+
+
+def render_batch_device(cfg, d_frames, n, d_out, out_pitch, d_out_len, d_scratch, stream=None):
+    rc = lib().acb200_render_batch_device(C.byref(cfg), d_frames, n, d_out, out_pitch, d_out_len, d_scratch, stream)
+    if rc:
+        raise RuntimeError("acb200_render_batch_device failed: %s" % (last_error(),))
+
+
+def time_batch_device(cfg, d_frames, n, d_out, out_pitch, d_out_len, d_scratch, iters):
+    tot, ker = C.c_float(0), C.c_float(0)
+    rc = lib().acb200_time_batch_device(C.byref(cfg), d_frames, n, d_out, out_pitch, d_out_len, d_scratch, iters,
+                                        C.byref(tot), C.byref(ker))
+    if rc:
+        raise RuntimeError("acb200_time_batch_device failed: %s" % (last_error(),))
+    return tot.value, ker.value
+
+
+def create_grid_device(d_ptrs, sizes, width, height, d_out, stream=None):
+    k = len(d_ptrs)
+    ptrs = (C.c_void_p * k)(*d_ptrs)
+    sz = (C.c_size_t * k)(*sizes)
+    n = C.c_size_t(0)
+    rc = lib().acb200_create_grid_device(ptrs, sz, k, width, height, d_out, C.byref(n), stream)
+    if rc:
+        raise RuntimeError("acb200_create_grid_device failed: %s" % (last_error(),))
+    return n.value
+
+
+def launch_count():
+    return int(lib().acb200_launch_count())

@@ -1,0 +1,559 @@
+// engine.cu — host engine of libasciichat_b200: plans, per-thread streams and staging,
+// device LUT cache, the batch API (include/asciichat_b200.h Part 2).
+//
+// There is no CPU rendering path in this file: every byte of every frame string is produced by
+// the kernels in render_kernels.cu.  Host work is limited to validation, the float aspect fit
+// (kept on the host on purpose), building the 256-entry glyph tables from the
+// palette string, moving buffers, and copying finished strings into caller-owned memory.
+#include "engine.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+// forwarded to when the host binary provides it (include/ascii-chat/asciichat_errno.h:429)
+extern "C" void asciichat_set_errno_with_message(int code, const char *file, int line, const char *function,
+                                                 const char *format, ...) __attribute__((weak));
+
+namespace acb {
+
+// ------------------------------------------------------------------ errors / knobs
+static thread_local int t_err = 0;
+static thread_local char t_errmsg[256] = "";
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_opt_render_mode{0};
+static std::atomic<int> g_default_scale{ACB200_SCALE_NN};
+static void *(*g_alloc)(size_t) = malloc;
+static void (*g_free)(void *) = free;
+
+int set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_errmsg, sizeof(t_errmsg), fmt, ap);
+  va_end(ap);
+  t_err = code;
+  if (asciichat_set_errno_with_message) asciichat_set_errno_with_message(code, "asciichat_b200", 0, "", "%s", t_errmsg);
+  return code;
+}
+void *user_alloc(size_t n) { return g_alloc(n ? n : 1); }
+void user_free(void *p) { g_free(p); }
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+int option_render_mode() { return g_opt_render_mode.load(); }
+int default_scale() { return g_default_scale.load(); }
+
+// ------------------------------------------------------------------ device / thread context
+static std::once_flag g_dev_once;
+static int g_dev_status = -1;
+static int g_device = -1;
+
+int ensure_device() {
+  std::call_once(g_dev_once, [] {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+      g_dev_status = set_error(E_INVALID_STATE, "asciichat_b200: no CUDA device (%s); this library has no CPU path",
+                               e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+      return;
+    }
+    if (g_device >= 0) cudaSetDevice(g_device);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp pr;
+    cudaGetDeviceProperties(&pr, dev);
+    if (pr.major < 10) {
+      g_dev_status = set_error(E_INVALID_STATE, "asciichat_b200: device %s is sm_%d%d; this build is sm_100a only",
+                               pr.name, pr.major, pr.minor);
+      return;
+    }
+    g_device = dev;
+    g_dev_status = 0;
+  });
+  if (g_dev_status != 0 && t_err == 0) set_error(E_INVALID_STATE, "asciichat_b200: CUDA device unavailable");
+  return g_dev_status;
+}
+
+bool grow_pinned(uint8_t **p, size_t *cap, size_t need) {
+  if (need <= *cap) return true;
+  size_t n = need + need / 4 + 4096;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr;
+  *cap = 0;
+  if (cudaHostAlloc((void **)p, n, cudaHostAllocDefault) != cudaSuccess) {
+    set_error(E_MEMORY, "cudaHostAlloc(%zu) failed", n);
+    return false;
+  }
+  *cap = n;
+  return true;
+}
+bool grow_device(uint8_t **p, size_t *cap, size_t need) {
+  if (need <= *cap) return true;
+  size_t n = need + need / 4 + 4096;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  if (cudaMalloc((void **)p, n) != cudaSuccess) {
+    set_error(E_MEMORY, "cudaMalloc(%zu) failed", n);
+    return false;
+  }
+  *cap = n;
+  return true;
+}
+
+struct CtxHolder {
+  ThreadCtx c;
+  bool ok = false;
+  ~CtxHolder() {
+    if (!ok) return;
+    // thread exit: release this thread's stream and staging (errors ignored: the context may be gone)
+    if (c.h_in) cudaFreeHost(c.h_in);
+    if (c.h_out) cudaFreeHost(c.h_out);
+    if (c.h_len) cudaFreeHost(c.h_len);
+    if (c.d_in) cudaFree(c.d_in);
+    if (c.d_out) cudaFree(c.d_out);
+    if (c.d_scratch) cudaFree(c.d_scratch);
+    if (c.d_len) cudaFree(c.d_len);
+    for (auto &e : c.ev)
+      if (e) cudaEventDestroy(e);
+    if (c.stream) cudaStreamDestroy(c.stream);
+  }
+};
+
+ThreadCtx *thread_ctx() {
+  static thread_local CtxHolder h;
+  if (h.ok) return &h.c;
+  if (ensure_device() != 0) return nullptr;
+  if (cudaSetDevice(g_device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h.c.stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error(E_INVALID_STATE, "cannot create CUDA stream");
+    return nullptr;
+  }
+  for (auto &e : h.c.ev) cudaEventCreate(&e);
+  h.ok = true;
+  return &h.c;
+}
+
+// ------------------------------------------------------------------ glyph LUTs
+// Host restatement of build_utf8_luminance_cache / build_utf8_ramp64_cache (common.c:380-490) reduced to
+// what the renderers read: per luminance Y the UTF-8 bytes of the glyph (with the mode's index mapping,
+// quirks Q1/Q2 of SURVEY.md §8a) and the mono run key char_index_ramp[Y>>2].
+static bool build_lut_host(const char *palette, int which, GlyphLut &L) {
+  struct G {
+    uint8_t len, b[4];
+  } chars[256];
+  int n = 0;
+  const unsigned char *p = reinterpret_cast<const unsigned char *>(palette);
+  while (*p && n < 255) { // lead-byte length rule, common.c:397-410
+    int len = (*p & 0xE0) == 0xC0 ? 2 : (*p & 0xF0) == 0xE0 ? 3 : (*p & 0xF8) == 0xF0 ? 4 : 1;
+    G g{(uint8_t)len, {0, 0, 0, 0}};
+    int i = 0;
+    for (; i < len && p[i]; i++) g.b[i] = p[i];
+    chars[n++] = g;
+    if (i < len) break; // truncated trailing sequence
+    p += len;
+  }
+  if (n == 0) return false;
+  auto map256 = [n](int i) { // common.c:420
+    int c = n > 1 ? (i * (n - 1) + 127) / 255 : 0;
+    return c >= n ? n - 1 : c;
+  };
+  auto map64 = [n](int i) { // common.c:476
+    int c = n > 1 ? (i * (n - 1) + 31) / 63 : 0;
+    return c >= n ? n - 1 : c;
+  };
+  memset(&L, 0, sizeof(L));
+  for (int y = 0; y < 256; y++) {
+    int ramp = map64(y >> 2);
+    int gi = which == 0 ? map256(y)                       // cache[Y]            foreground.c:279,487
+             : which == 1 ? map64(ramp < 64 ? ramp : 63)  // cache64[char_idx]   foreground.c:97-102 (Q1)
+                          : map256(ramp);                 // cache[char_idx]     foreground.c:596-599 (Q2)
+    L.glyph[y][0] = chars[gi].len;
+    memcpy(&L.glyph[y][1], chars[gi].b, 4);
+    L.key[y] = (uint8_t)ramp;
+  }
+  return true;
+}
+
+static std::mutex g_lut_mu;
+static std::map<std::string, GlyphLut *> g_luts; // key = which + palette bytes
+
+const GlyphLut *device_lut(const char *palette, int which) {
+  std::string key(1, (char)('0' + which));
+  key += palette;
+  std::lock_guard<std::mutex> lk(g_lut_mu);
+  auto it = g_luts.find(key);
+  if (it != g_luts.end()) return it->second;
+  GlyphLut h;
+  if (!build_lut_host(palette, which, h)) {
+    set_error(E_INVALID_STATE, "empty palette");
+    return nullptr;
+  }
+  GlyphLut *d = nullptr;
+  if (cudaMalloc((void **)&d, sizeof(GlyphLut)) != cudaSuccess ||
+      cudaMemcpy(d, &h, sizeof(GlyphLut), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error(E_MEMORY, "cannot upload glyph LUT");
+    return nullptr;
+  }
+  if (g_luts.size() >= 2048) { // same bound as the reference's palette cache (common.c:132)
+    for (auto &kv : g_luts) cudaFree(kv.second);
+    g_luts.clear();
+  }
+  g_luts[key] = d;
+  return d;
+}
+void destroy_lut_cache() {
+  std::lock_guard<std::mutex> lk(g_lut_mu);
+  for (auto &kv : g_luts) cudaFree(kv.second);
+  g_luts.clear();
+}
+
+// ------------------------------------------------------------------ plans
+static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
+  if (cfg.src_w <= 0 || cfg.src_w > 10000 || cfg.src_h <= 0 || cfg.src_h > 10000) { // ascii.c:204
+    set_error(E_INVALID_PARAM, "invalid source dimensions %dx%d", cfg.src_w, cfg.src_h);
+    return false;
+  }
+  if (cfg.cols <= 0 || cfg.rows_px <= 0 || cfg.cols > 3840 || cfg.rows_px > 2160) { // image.h:166,179 via image_new
+    set_error(E_INVALID_PARAM, "invalid resized dimensions %dx%d", cfg.cols, cfg.rows_px);
+    return false;
+  }
+  if (!cfg.palette) {
+    set_error(E_INVALID_PARAM, "palette is NULL");
+    return false;
+  }
+  const bool half = cfg.render_mode == RENDER_MODE_HALF_BLOCK;
+  if (half) {
+    pl.mode = cfg.color_level == TERM_COLOR_TRUECOLOR ? EM_HB_TRUE
+              : cfg.color_level == TERM_COLOR_256     ? EM_HB_256
+              : cfg.color_level == TERM_COLOR_16      ? EM_HB_16
+                                                      : EM_HB_MONO;
+  } else { // ascii.c:981-1001 with SIMD_SUPPORT defined
+    pl.mode = cfg.color_level == TERM_COLOR_TRUECOLOR
+                  ? (cfg.render_mode == RENDER_MODE_BACKGROUND ? EM_DITHER_BG : EM_TRUE_FG)
+              : cfg.color_level == TERM_COLOR_256 ? EM_256_FG
+              : cfg.color_level == TERM_COLOR_16  ? EM_16_FG
+                                                  : EM_MONO_FG;
+  }
+  if (!half && cfg.palette[0] == '\0') { // get_utf8_palette_cache rejects "" (common.c:275)
+    set_error(E_INVALID_STATE, "empty palette");
+    return false;
+  }
+  pl.text_rows = half ? (cfg.rows_px + 1) / 2 : cfg.rows_px;
+  pl.lut_which = pl.mode == EM_MONO_FG ? 1 : pl.mode == EM_16_FG ? 2 : 0;
+  pl.row_pitch = row_capacity_bytes(pl.mode, cfg.cols, cfg.pad_left);
+
+  int sp = SP_NN;
+  if (cfg.scale == ACB200_SCALE_BOX) {
+    const int band = cfg.src_h / cfg.rows_px + 2;
+    sp = ((3 * cfg.src_w) % 16 == 0 && band <= 256) ? SP_BOX_STREAM : SP_BOX_GENERIC;
+  } else if (cfg.scale != ACB200_SCALE_NN) {
+    set_error(E_INVALID_PARAM, "unknown scale mode %d", cfg.scale);
+    return false;
+  }
+  const int kmode = pl.mode == EM_DITHER_BG ? (int)EM_256_FG : pl.mode;
+  pl.use_smem_out = pl.row_pitch <= (uint32_t)kSmemOutMax;
+  size_t sm = rows_smem_total(kmode, sp, cfg.cols, cfg.src_w, pl.use_smem_out ? pl.row_pitch : 0);
+  if (sm > 227u * 1024u && sp == SP_BOX_STREAM) {
+    sp = SP_BOX_GENERIC;
+    sm = rows_smem_total(kmode, sp, cfg.cols, cfg.src_w, pl.use_smem_out ? pl.row_pitch : 0);
+  }
+  if (sm > 227u * 1024u && pl.use_smem_out) {
+    pl.use_smem_out = 0;
+    sm = rows_smem_total(kmode, sp, cfg.cols, cfg.src_w, 0);
+  }
+  if (sm > 227u * 1024u) {
+    set_error(E_INVALID_PARAM, "row of %d cells does not fit shared memory", cfg.cols);
+    return false;
+  }
+  pl.scale_path = sp;
+  pl.frame_capacity = (((size_t)cfg.pad_top + (size_t)pl.text_rows * pl.row_pitch + 1) + 15) & ~(size_t)15;
+  pl.rows_bytes = (size_t)pl.text_rows * pl.row_pitch;
+  pl.meta_bytes = (size_t)pl.text_rows * sizeof(RowMeta);
+  pl.cells_bytes = pl.mode == EM_DITHER_BG ? (size_t)cfg.cols * cfg.rows_px * 3 : 0;
+  pl.err_bytes = pl.mode == EM_DITHER_BG ? (size_t)cfg.cols * cfg.rows_px * 3 * sizeof(int) : 0;
+  return true;
+}
+
+static size_t scratch_bytes(const Plan &pl, int n) {
+  return al256(pl.rows_bytes * n) + al256(pl.meta_bytes * n) + al256(pl.cells_bytes * n) + al256(pl.err_bytes * n);
+}
+
+// ------------------------------------------------------------------ the device pipeline
+int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t *d_frames, size_t frame_stride,
+                  int pregathered, int n_frames, uint8_t *d_out, size_t out_pitch, uint32_t *d_out_len,
+                  uint8_t *d_scratch, cudaStream_t st, cudaEvent_t k0, cudaEvent_t k1) {
+  if (n_frames <= 0) return E_OK;
+  const GlyphLut *lut = device_lut(cfg.palette[0] ? cfg.palette : " ", pl.lut_which);
+  if (!lut) return t_err;
+  uint8_t *rows = d_scratch;
+  RowMeta *meta = reinterpret_cast<RowMeta *>(rows + al256(pl.rows_bytes * n_frames));
+  uint8_t *cells = reinterpret_cast<uint8_t *>(meta) + al256(pl.meta_bytes * n_frames);
+  int *err = reinterpret_cast<int *>(cells + al256(pl.cells_bytes * n_frames));
+
+  RenderParams rp{};
+  rp.frames = d_frames;
+  rp.frame_stride = frame_stride;
+  rp.src_w = cfg.src_w;
+  rp.src_h = cfg.src_h;
+  rp.pregathered = pregathered;
+  rp.cols = cfg.cols;
+  rp.rows_px = cfg.rows_px;
+  rp.text_rows = pl.text_rows;
+  rp.pad_left = cfg.pad_left;
+  rp.use_smem_out = pl.use_smem_out;
+  rp.row_pitch = pl.row_pitch;
+  rp.rows = rows;
+  rp.meta = meta;
+  rp.lut = lut;
+  rp.cells_out = nullptr;
+  rp.n_frames = n_frames;
+
+  if (k0) cudaEventRecord(k0, st);
+  if (pl.mode != EM_DITHER_BG) {
+    ACB_CUDA(launch_render_rows(rp, pl.mode, pl.scale_path, st));
+    count_launch();
+  } else {
+    rp.rows = nullptr;
+    rp.cells_out = cells;
+    rp.use_smem_out = 0;
+    ACB_CUDA(launch_render_rows(rp, EM_256_FG, pl.scale_path, st)); // resize-only pass
+    ACB_CUDA(cudaMemsetAsync(err, 0, pl.err_bytes * n_frames, st));
+    ACB_CUDA(launch_dither_bg(cells, cfg.cols, cfg.rows_px, n_frames, cfg.pad_left, lut, rows, pl.row_pitch, meta, err,
+                              st));
+    count_launch(2);
+  }
+  if (k1) cudaEventRecord(k1, st);
+
+  StitchParams sp{};
+  sp.rows = rows;
+  sp.meta = meta;
+  sp.row_pitch = pl.row_pitch;
+  sp.text_rows = pl.text_rows;
+  sp.pad_top = cfg.pad_top;
+  sp.mode = pl.mode;
+  sp.out = d_out;
+  sp.out_pitch = out_pitch;
+  sp.out_len = d_out_len;
+  sp.rows_per_cta = 8;
+  ACB_CUDA(launch_stitch(sp, n_frames, st));
+  count_launch();
+  return E_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer path
+static inline uint32_t nn_src_row(int y, int src_h, int rows_px) { // image.c:294,300-302
+  uint32_t yr = (uint32_t)((((uint64_t)src_h << 16) / (uint64_t)rows_px) + 1);
+  uint32_t sy = ((uint32_t)y * yr) >> 16;
+  return sy >= (uint32_t)src_h ? (uint32_t)src_h - 1 : sy;
+}
+
+static bool is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t *const *frames, int n_frames,
+                                  char **out, size_t *out_len) {
+  Plan pl;
+  if (!make_plan(cfg, pl)) return t_err;
+  ThreadCtx *cx = thread_ctx();
+  if (!cx) return t_err;
+  const size_t R = (size_t)cfg.src_w * 3;
+  // nearest neighbour reads rows_px of the src_h rows: move only those (row-granular transfer plan);
+  // the box filter reads every row.
+  const bool gather = cfg.scale == ACB200_SCALE_NN && cfg.rows_px < cfg.src_h;
+  const size_t in_per_frame = gather ? R * cfg.rows_px : R * cfg.src_h;
+  int chunk = (int)((size_t)(96u << 20) / (in_per_frame + pl.frame_capacity + 1));
+  if (chunk < 1) chunk = 1;
+  if (chunk > n_frames) chunk = n_frames;
+  if (!grow_device(&cx->d_in, &cx->d_in_cap, in_per_frame * chunk) ||
+      !grow_device(&cx->d_out, &cx->d_out_cap, pl.frame_capacity * chunk) ||
+      !grow_device(&cx->d_scratch, &cx->d_scratch_cap, scratch_bytes(pl, chunk)) ||
+      !grow_device((uint8_t **)&cx->d_len, &cx->d_len_cap, sizeof(uint32_t) * chunk) ||
+      !grow_pinned((uint8_t **)&cx->h_len, &cx->h_len_cap, sizeof(uint32_t) * chunk))
+    return t_err;
+  for (int i = 0; i < n_frames; i++) out[i] = nullptr;
+  bool need_stage = gather;
+  for (int i = 0; i < n_frames && !need_stage; i++) need_stage = frames[i] && !is_pinned(frames[i]);
+  if (need_stage && !grow_pinned(&cx->h_in, &cx->h_in_cap, in_per_frame * chunk)) return t_err;
+
+  for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+    const int n = (n_frames - f0 < chunk) ? n_frames - f0 : chunk;
+    for (int i = 0; i < n; i++) {
+      const uint8_t *src = frames[f0 + i];
+      if (!src) return set_error(E_INVALID_PARAM, "frame %d is NULL", f0 + i);
+      uint8_t *dst = cx->d_in + (size_t)i * in_per_frame;
+      if (gather) {
+        uint8_t *st = cx->h_in + (size_t)i * in_per_frame;
+        for (int y = 0; y < cfg.rows_px; y++)
+          memcpy(st + (size_t)y * R, src + (size_t)nn_src_row(y, cfg.src_h, cfg.rows_px) * R, R);
+        ACB_CUDA(cudaMemcpyAsync(dst, st, in_per_frame, cudaMemcpyHostToDevice, cx->stream));
+      } else if (is_pinned(src)) {
+        ACB_CUDA(cudaMemcpyAsync(dst, src, in_per_frame, cudaMemcpyHostToDevice, cx->stream));
+      } else {
+        uint8_t *st = cx->h_in + (size_t)i * in_per_frame;
+        memcpy(st, src, in_per_frame);
+        ACB_CUDA(cudaMemcpyAsync(dst, st, in_per_frame, cudaMemcpyHostToDevice, cx->stream));
+      }
+    }
+    int rc = render_device(cfg, pl, cx->d_in, in_per_frame, gather ? 1 : 0, n, cx->d_out, pl.frame_capacity, cx->d_len,
+                           cx->d_scratch, cx->stream);
+    if (rc) return rc;
+    ACB_CUDA(cudaMemcpyAsync(cx->h_len, cx->d_len, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, cx->stream));
+    ACB_CUDA(cudaStreamSynchronize(cx->stream));
+    size_t tot = 0;
+    for (int i = 0; i < n; i++) tot += (size_t)cx->h_len[i] + 1;
+    if (!grow_pinned(&cx->h_out, &cx->h_out_cap, tot)) return t_err;
+    size_t o = 0;
+    for (int i = 0; i < n; i++) {
+      ACB_CUDA(cudaMemcpyAsync(cx->h_out + o, cx->d_out + (size_t)i * pl.frame_capacity, (size_t)cx->h_len[i] + 1,
+                               cudaMemcpyDeviceToHost, cx->stream));
+      o += (size_t)cx->h_len[i] + 1;
+    }
+    ACB_CUDA(cudaStreamSynchronize(cx->stream));
+    o = 0;
+    for (int i = 0; i < n; i++) {
+      const size_t len = cx->h_len[i];
+      char *s = (char *)user_alloc(len + 1);
+      if (!s) return set_error(E_MEMORY, "allocator returned NULL for %zu bytes", len + 1);
+      memcpy(s, cx->h_out + o, len + 1);
+      s[len] = '\0';
+      out[f0 + i] = s;
+      if (out_len) out_len[f0 + i] = len;
+      o += len + 1;
+    }
+  }
+  return E_OK;
+}
+
+char *render_one_host(const acb200_render_cfg_t &cfg, const uint8_t *rgb, size_t *out_len) {
+  char *s = nullptr;
+  size_t n = 0;
+  const uint8_t *fr[1] = {rgb};
+  if (render_batch_host_impl(cfg, fr, 1, &s, &n) != E_OK) {
+    if (s) user_free(s);
+    return nullptr;
+  }
+  if (out_len) *out_len = n;
+  return s;
+}
+
+} // namespace acb
+
+// ====================================================================== C ABI (Part 2)
+using namespace acb;
+
+extern "C" {
+
+int acb200_init(int device) {
+  if (device >= 0 && g_dev_status == -1) g_device = device;
+  if (ensure_device() != 0) return t_err ? t_err : E_INVALID_STATE;
+  return thread_ctx() ? E_OK : t_err;
+}
+void acb200_shutdown(void) { destroy_lut_cache(); }
+int acb200_last_error(void) {
+  int e = t_err;
+  t_err = 0;
+  return e;
+}
+const char *acb200_last_error_message(void) { return t_errmsg; }
+void acb200_set_allocator(void *(*alloc_fn)(size_t), void (*free_fn)(void *)) {
+  g_alloc = alloc_fn ? alloc_fn : malloc;
+  g_free = free_fn ? free_fn : free;
+}
+void acb200_set_option_render_mode(int render_mode) { g_opt_render_mode.store(render_mode); }
+void acb200_set_default_scale(int scale) { g_default_scale.store(scale); }
+
+size_t acb200_frame_capacity(const acb200_render_cfg_t *cfg) {
+  Plan pl;
+  if (!cfg || !make_plan(*cfg, pl)) return 0;
+  return pl.frame_capacity;
+}
+size_t acb200_scratch_bytes(const acb200_render_cfg_t *cfg, int n_frames) {
+  Plan pl;
+  if (!cfg || n_frames <= 0 || !make_plan(*cfg, pl)) return 0;
+  return scratch_bytes(pl, n_frames);
+}
+
+int acb200_render_batch_device(const acb200_render_cfg_t *cfg, const uint8_t *d_frames, int n_frames, uint8_t *d_out,
+                               size_t out_pitch, uint32_t *d_out_len, void *d_scratch, void *stream) {
+  if (!cfg || !d_frames || !d_out || !d_out_len || !d_scratch || n_frames < 0)
+    return set_error(E_INVALID_PARAM, "acb200_render_batch_device: NULL argument");
+  Plan pl;
+  if (!make_plan(*cfg, pl)) return t_err;
+  if (out_pitch < pl.frame_capacity) return set_error(E_INVALID_PARAM, "out_pitch %zu < capacity %zu", out_pitch, pl.frame_capacity);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!st) {
+    ThreadCtx *cx = thread_ctx();
+    if (!cx) return t_err;
+    st = cx->stream;
+  } else if (ensure_device() != 0) {
+    return t_err;
+  }
+  return render_device(*cfg, pl, d_frames, (size_t)cfg->src_w * cfg->src_h * 3, 0, n_frames, d_out, out_pitch, d_out_len,
+                       (uint8_t *)d_scratch, st);
+}
+
+int acb200_render_batch_host(const acb200_render_cfg_t *cfg, const uint8_t *const *frames, int n_frames, char **out,
+                             size_t *out_len) {
+  if (!cfg || !frames || !out || n_frames < 0) return set_error(E_INVALID_PARAM, "acb200_render_batch_host: NULL argument");
+  int rc = render_batch_host_impl(*cfg, frames, n_frames, out, out_len);
+  if (rc != E_OK)
+    for (int i = 0; i < n_frames; i++)
+      if (out[i]) {
+        user_free(out[i]);
+        out[i] = nullptr;
+      }
+  return rc;
+}
+
+int acb200_time_batch_device(const acb200_render_cfg_t *cfg, const uint8_t *d_frames, int n_frames, uint8_t *d_out,
+                             size_t out_pitch, uint32_t *d_out_len, void *d_scratch, int iters, float *ms_total,
+                             float *ms_kernel) {
+  if (!cfg || !d_frames || !d_out || !d_out_len || !d_scratch || iters <= 0)
+    return set_error(E_INVALID_PARAM, "acb200_time_batch_device: bad argument");
+  Plan pl;
+  if (!make_plan(*cfg, pl)) return t_err;
+  ThreadCtx *cx = thread_ctx();
+  if (!cx) return t_err;
+  std::vector<cudaEvent_t> ev((size_t)2 * iters);
+  for (auto &e : ev) ACB_CUDA(cudaEventCreate(&e));
+  ACB_CUDA(cudaStreamSynchronize(cx->stream));
+  ACB_CUDA(cudaEventRecord(cx->ev[0], cx->stream));
+  int rc = E_OK;
+  for (int i = 0; i < iters && rc == E_OK; i++)
+    rc = render_device(*cfg, pl, d_frames, (size_t)cfg->src_w * cfg->src_h * 3, 0, n_frames, d_out, out_pitch, d_out_len,
+                       (uint8_t *)d_scratch, cx->stream, ev[2 * i], ev[2 * i + 1]);
+  cudaEventRecord(cx->ev[1], cx->stream);
+  cudaError_t se = cudaStreamSynchronize(cx->stream);
+  float tot = 0.f, ker = 0.f;
+  if (rc == E_OK && se == cudaSuccess) {
+    cudaEventElapsedTime(&tot, cx->ev[0], cx->ev[1]);
+    for (int i = 0; i < iters; i++) {
+      float k = 0.f;
+      cudaEventElapsedTime(&k, ev[2 * i], ev[2 * i + 1]);
+      ker += k;
+    }
+  }
+  for (auto &e : ev) cudaEventDestroy(e);
+  if (se != cudaSuccess) return set_error(E_INVALID_STATE, "CUDA: %s", cudaGetErrorString(se));
+  if (ms_total) *ms_total = tot;
+  if (ms_kernel) *ms_kernel = ker;
+  return rc;
+}
+
+uint64_t acb200_launch_count(void) { return g_launches.load(); }
+const char *acb200_version(void) { return "asciichat_b200 0.1 (sm_100a)"; }
+
+} // extern "C"

@@ -1,0 +1,70 @@
+// engine.h — internal host-side interface shared by engine.cu, dropin.cu and grid.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/asciichat_b200.h"
+#include "render.cuh"
+
+namespace acb {
+
+// reference error codes (include/ascii-chat/common/error_codes.h:51-109)
+enum { E_OK = 0, E_MEMORY = 3, E_INVALID_STATE = 85, E_INVALID_PARAM = 86 };
+
+// Everything derived from an acb200_render_cfg_t that the launches need.
+struct Plan {
+  int mode;        // EmitMode
+  int scale_path;  // ScalePath
+  int text_rows;
+  int lut_which;   // 0 cache[Y], 1 mono double map (Q1), 2 16-colour map (Q2)
+  uint32_t row_pitch;
+  int use_smem_out;
+  size_t frame_capacity; // bytes per frame in the output arena (multiple of 16, incl. NUL)
+  size_t rows_bytes, meta_bytes, cells_bytes, err_bytes; // per frame scratch
+};
+
+int set_error(int code, const char *fmt, ...);
+bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl); // false => error set
+int ensure_device();                                       // 0 or error code
+
+// per-thread stream + growable staging buffers
+struct ThreadCtx {
+  cudaStream_t stream = nullptr;
+  uint8_t *h_in = nullptr;   size_t h_in_cap = 0;   // pinned
+  uint8_t *h_out = nullptr;  size_t h_out_cap = 0;  // pinned
+  uint8_t *d_in = nullptr;   size_t d_in_cap = 0;
+  uint8_t *d_out = nullptr;  size_t d_out_cap = 0;
+  uint8_t *d_scratch = nullptr; size_t d_scratch_cap = 0;
+  uint32_t *d_len = nullptr; size_t d_len_cap = 0;
+  uint32_t *h_len = nullptr; size_t h_len_cap = 0;  // pinned
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+ThreadCtx *thread_ctx(); // nullptr => error set
+bool grow_pinned(uint8_t **p, size_t *cap, size_t need);
+bool grow_device(uint8_t **p, size_t *cap, size_t need);
+
+const GlyphLut *device_lut(const char *palette, int which); // cached per (palette, which); nullptr => error set
+void destroy_lut_cache();
+
+void *user_alloc(size_t n);
+void user_free(void *p);
+void count_launch(int n = 1);
+int option_render_mode();
+int default_scale();
+
+// the core: frames resident on the device -> strings in the device arena (async on st)
+int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t *d_frames, size_t frame_stride,
+                  int pregathered, int n_frames, uint8_t *d_out, size_t out_pitch, uint32_t *d_out_len,
+                  uint8_t *d_scratch, cudaStream_t st, cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr);
+
+// one frame from a host RGB24 buffer -> allocator-owned string (used by every drop-in entry point)
+char *render_one_host(const acb200_render_cfg_t &cfg, const uint8_t *rgb, size_t *out_len);
+
+#define ACB_CUDA(call)                                                                                                 \
+  do {                                                                                                                 \
+    cudaError_t _e = (call);                                                                                           \
+    if (_e != cudaSuccess) return acb::set_error(acb::E_INVALID_STATE, "CUDA: %s (%s)", cudaGetErrorString(_e), #call); \
+  } while (0)
+
+} // namespace acb

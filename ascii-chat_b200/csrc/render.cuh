@@ -1,0 +1,91 @@
+// render.cuh — shared declarations between the sm_100a kernels (render_kernels.cu)
+// and the host engine (engine.cu).  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace acb {
+
+// Emission grammars (SURVEY.md §8a "exact output grammar"); one per reference renderer.
+enum EmitMode : int {
+  EM_MONO_FG = 0,  // image_print                       foreground.c:27-138
+  EM_256_FG = 1,   // image_print_256color              foreground.c:433-509
+  EM_16_FG = 2,    // image_print_16color               foreground.c:535-624
+  EM_TRUE_FG = 3,  // image_print_color + ansi_rle_*    foreground.c:195-308, ansi.c:248-314
+  EM_HB_TRUE = 4,  // rgb_to_truecolor_halfblocks_scalar halfblock.c:48-165
+  EM_HB_256 = 5,   // rgb_to_256color_halfblocks_scalar  halfblock.c:416-524
+  EM_HB_16 = 6,    // rgb_to_16color_halfblocks_scalar   halfblock.c:297-405
+  EM_HB_MONO = 7,  // rgb_to_halfblocks_scalar           halfblock.c:184-286
+  EM_DITHER_BG = 8 // image_print_16color_dithered_with_background foreground.c:752-846 (own kernel)
+};
+
+enum ScalePath : int {
+  SP_NN = 0,        // nearest neighbour, image.c:267-328
+  SP_BOX_GENERIC = 1, // box filter, any geometry (byte loads)
+  SP_BOX_STREAM = 2   // box filter, 16-byte streaming loads (3*src_w % 16 == 0, band <= 256 rows)
+};
+
+// Brightness -> glyph tables for one (palette, mode) pair, built on the host
+// (common.c:380-490 mapping incl. quirks Q1/Q2) and kept in device memory.
+struct GlyphLut {
+  uint8_t glyph[256][8]; // [Y] = {len, b0, b1, b2, b3, 0, 0, 0}
+  uint8_t key[256];      // [Y] = char_index_ramp[Y >> 2]  (mono run key)
+};
+
+// Per text row bookkeeping produced by the row kernel, consumed by the stitch kernel.
+struct RowMeta {
+  uint32_t len;       // bytes written to the scratch row
+  uint32_t cond_off;  // EM_TRUE_FG: offset of the SGR owned by the row's first ASCII-glyph cell
+  uint32_t cond_len;  //             its length (0 = row has no ASCII-glyph cell)
+  uint32_t first_rgb; //             colour of that cell   (0x01RRGGBB, 0 = none)
+  uint32_t last_rgb;  //             colour of the row's last ASCII-glyph cell (0x01RRGGBB, 0 = none)
+  uint32_t _pad[3];
+};
+
+struct RenderParams {
+  const uint8_t *frames; // frame f at frames + f*frame_stride, packed RGB24, pitch 3*src_w
+  size_t frame_stride;
+  int src_w, src_h;
+  int pregathered;       // NN only: source holds exactly rows_px rows, row y = the row NN would sample
+  int cols, rows_px, text_rows;
+  int pad_left;
+  int use_smem_out;      // row fits the shared staging buffer
+  uint32_t row_pitch;    // bytes between scratch rows (multiple of 16)
+  uint8_t *rows;         // scratch: (f*text_rows + t) * row_pitch
+  RowMeta *meta;         // (f*text_rows + t)
+  const GlyphLut *lut;
+  uint8_t *cells_out;    // optional: resized RGB24 image, frame f at f*cols*rows_px*3 (image_resize, tests)
+  int n_frames;
+};
+
+struct StitchParams {
+  const uint8_t *rows;
+  const RowMeta *meta;
+  uint32_t row_pitch;
+  int text_rows;
+  int pad_top;
+  int mode;
+  uint8_t *out;      // frame f at f*out_pitch
+  size_t out_pitch;
+  uint32_t *out_len; // [f]
+  int rows_per_cta;
+};
+
+__host__ __device__ inline uint32_t al16(uint32_t v) { return (v + 15u) & ~15u; }
+
+size_t rows_smem_total(int mode, int scale_path, int cols, int src_w, uint32_t out_bytes);
+uint32_t row_capacity_bytes(int mode, int cols, int pad_left);
+static constexpr int kSmemOutMax = 48 * 1024; // rows up to this many bytes are staged in shared memory
+
+cudaError_t launch_render_rows(const RenderParams &p, int mode, int scale_path, cudaStream_t st);
+cudaError_t launch_stitch(const StitchParams &p, int n_frames, cudaStream_t st);
+cudaError_t launch_resize_nn_only(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh, int pregathered,
+                                  cudaStream_t st);
+// Floyd–Steinberg 16-colour background renderer (serial wavefront): one CTA per frame, reads the resized image
+cudaError_t launch_dither_bg(const uint8_t *cells, int w, int h, int n_frames, int pad_left, const GlyphLut *lut,
+                             uint8_t *rows, uint32_t row_pitch, RowMeta *meta, int *err_scratch, cudaStream_t st);
+// pixel-space composite blit (stream.c:752-773): NN-resize one source into its clipped cell of the composite
+cudaError_t launch_composite_cell(const uint8_t *src, int sw, int sh, uint8_t *comp, int cw, int ch, int tw, int th,
+                                  int x0, int y0, int cellw, int cellh, cudaStream_t st);
+
+} // namespace acb

@@ -1,0 +1,859 @@
+// render_kernels.cu — sm_100a kernels for the RGB -> glyph/ANSI render path.
+//
+// k_render_rows<MODE, SP>: one CTA per (frame, text row).  It (A) produces the row's resized
+// pixels in shared memory — nearest-neighbour sampling (image.c:267-328) or a box filter that
+// streams the whole source band with 16-byte loads — and (B) turns them into the exact byte
+// string of the reference's renderer for that mode (foreground.c / halfblock.c grammars) using
+// cell-local rules: every cell derives, from its run (head, length), its left run and the LUTs,
+// which bytes it owns; a block-wide exclusive scan of the byte counts places them.  The row is
+// staged in shared memory and leaves the SM as 16-byte stores.
+//
+// k_stitch: concatenates the fixed-pitch rows of a frame into the final NUL-terminated string
+// (row-length prefix sum; for truecolor-foreground also the cross-row colour carry of
+// ansi_rle_add_pixel, ansi.c:261-300).
+//
+// All arithmetic is integer; see oracle/ascii_oracle.c for the CPU restatement these kernels
+// are checked against byte for byte.
+#include "render.cuh"
+
+namespace acb {
+
+constexpr int BLOCK = 256;
+constexpr int NWARP = BLOCK / 32;
+constexpr uint16_t NONE16 = 0xFFFF;
+
+// ------------------------------------------------------------------ small integer helpers
+__device__ __forceinline__ int luma_of(uint32_t c) { // foreground.c:93  (77R+150G+29B+128)>>8
+  return (int)((77u * ((c >> 16) & 255u) + 150u * ((c >> 8) & 255u) + 29u * (c & 255u) + 128u) >> 8);
+}
+__device__ __forceinline__ int luma76_of(uint32_t c) { // halfblock.c:239-240  (76R+150G+29B)>>8
+  return (int)((76u * ((c >> 16) & 255u) + 150u * ((c >> 8) & 255u) + 29u * (c & 255u)) >> 8);
+}
+__device__ __forceinline__ int q256_of(uint32_t c) { // ansi.c:360-379
+  int r = (c >> 16) & 255, g = (c >> 8) & 255, b = c & 255;
+  int avg = (r + g + b) / 3;
+  int d = abs(r - avg) + abs(g - avg) + abs(b - avg);
+  if (d < 30) return 232 + (avg * 23) / 255;
+  return 16 + 36 * ((r * 5) / 255) + 6 * ((g * 5) / 255) + (b * 5) / 255;
+}
+__constant__ uint8_t c_ansi16[16][4] = { // ansi.c:442-459
+    {0, 0, 0, 0},       {128, 0, 0, 0},   {0, 128, 0, 0},   {128, 128, 0, 0}, {0, 0, 128, 0},   {128, 0, 128, 0},
+    {0, 128, 128, 0},   {192, 192, 192, 0}, {128, 128, 128, 0}, {255, 0, 0, 0},   {0, 255, 0, 0},   {255, 255, 0, 0},
+    {0, 0, 255, 0},     {255, 0, 255, 0}, {0, 255, 255, 0}, {255, 255, 255, 0}};
+__device__ __forceinline__ int q16_rgb(int r, int g, int b) { // ansi.c:437-477, first minimum wins
+  int best = 0, bestd = 0x7fffffff;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    int dr = r - c_ansi16[i][0], dg = g - c_ansi16[i][1], db = b - c_ansi16[i][2];
+    int d = dr * dr + dg * dg + db * db;
+    if (d < bestd) {
+      bestd = d;
+      best = i;
+    }
+  }
+  return best;
+}
+__device__ __forceinline__ int q16_of(uint32_t c) { return q16_rgb((c >> 16) & 255, (c >> 8) & 255, c & 255); }
+
+__device__ __forceinline__ bool rep_profitable(uint32_t run) { // output_buffer.c:148-154
+  if (run <= 2) return false;
+  uint32_t k = run - 1;
+  uint32_t digits = k >= 1000u ? (k >= 10000u ? 5u : 4u) : (k >= 100u ? 3u : (k >= 10u ? 2u : 1u)); // k < 100000 here
+  return k > digits + 3u;
+}
+
+// ------------------------------------------------------------------ byte sinks
+struct CountSink {
+  uint32_t n = 0;
+  __device__ __forceinline__ void put(uint8_t) { ++n; }
+};
+struct WriteSink {
+  uint8_t *p;
+  __device__ __forceinline__ void put(uint8_t c) { *p++ = c; }
+};
+
+template <class S> __device__ __forceinline__ void put_u8dec(S &s, uint32_t v) { // dec3 table, common.c:546-570
+  if (v >= 100u) {
+    uint32_t h = v / 100u, r = v - h * 100u;
+    s.put((uint8_t)('0' + h));
+    s.put((uint8_t)('0' + r / 10u));
+    s.put((uint8_t)('0' + r % 10u));
+  } else if (v >= 10u) {
+    s.put((uint8_t)('0' + v / 10u));
+    s.put((uint8_t)('0' + v % 10u));
+  } else {
+    s.put((uint8_t)('0' + v));
+  }
+}
+template <class S> __device__ __forceinline__ void put_u32dec(S &s, uint32_t v) { // ob_u32, output_buffer.c:92-104
+  uint8_t t[10];
+  int i = 0;
+  do {
+    t[i++] = (uint8_t)('0' + v % 10u);
+    v /= 10u;
+  } while (v);
+  while (i--) s.put(t[i]);
+}
+template <class S> __device__ __forceinline__ void put_sgr_rgb(S &s, bool bg, uint32_t c) { // ansi.c:143-195
+  s.put(0x1b);
+  s.put('[');
+  s.put(bg ? '4' : '3');
+  s.put('8');
+  s.put(';');
+  s.put('2');
+  s.put(';');
+  put_u8dec(s, (c >> 16) & 255u);
+  s.put(';');
+  put_u8dec(s, (c >> 8) & 255u);
+  s.put(';');
+  put_u8dec(s, c & 255u);
+  s.put('m');
+}
+template <class S> __device__ __forceinline__ void put_sgr_256(S &s, bool bg, uint32_t idx) { // ansi.c:326-357
+  s.put(0x1b);
+  s.put('[');
+  s.put(bg ? '4' : '3');
+  s.put('8');
+  s.put(';');
+  s.put('5');
+  s.put(';');
+  put_u8dec(s, idx);
+  s.put('m');
+}
+template <class S> __device__ __forceinline__ void put_sgr_16(S &s, bool bg, uint32_t idx) { // ansi.c:384-435
+  uint32_t code = (idx < 8u ? 30u + idx : 82u + idx) + (bg ? 10u : 0u);
+  s.put(0x1b);
+  s.put('[');
+  put_u8dec(s, code);
+  s.put('m');
+}
+template <class S> __device__ __forceinline__ void put_reset(S &s) {
+  s.put(0x1b);
+  s.put('[');
+  s.put('0');
+  s.put('m');
+}
+template <class S> __device__ __forceinline__ void put_rep(S &s, uint32_t extra) { // output_buffer.c:156-164
+  s.put(0x1b);
+  s.put('[');
+  put_u32dec(s, extra);
+  s.put('b');
+}
+template <class S> __device__ __forceinline__ void put_glyph(S &s, const uint8_t *g) {
+  int n = g[0];
+  for (int i = 0; i < n; i++) s.put(g[1 + i]);
+}
+template <class S> __device__ __forceinline__ void put3(S &s, uint8_t a, uint8_t b, uint8_t c) {
+  s.put(a);
+  s.put(b);
+  s.put(c);
+}
+
+// ------------------------------------------------------------------ block-wide row scans
+struct OpAdd {
+  static __device__ __forceinline__ int id() { return 0; }
+  static __device__ __forceinline__ int ap(int a, int b) { return a + b; }
+};
+struct OpMax {
+  static __device__ __forceinline__ int id() { return -1; }
+  static __device__ __forceinline__ int ap(int a, int b) { return a > b ? a : b; }
+};
+
+// Scans value_of(x), x in [0,w), in x order over the CTA; calls store(x, inclusive, exclusive).
+// Returns the total (valid in every thread).  s_tmp: NWARP+1 ints of shared memory.
+template <class Op, class F, class G>
+__device__ __forceinline__ int row_scan(int w, F value_of, G store, int *s_tmp) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tmp[NWARP] = Op::id();
+  __syncthreads();
+  for (int base = 0; base < w; base += BLOCK) {
+    int x = base + tid;
+    int v = x < w ? value_of(x) : Op::id();
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc = Op::ap(o, inc);
+    }
+    int up = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 31) s_tmp[warp] = inc;
+    __syncthreads();
+    int pre = s_tmp[NWARP];
+    for (int i = 0; i < warp; i++) pre = Op::ap(pre, s_tmp[i]);
+    int incl = Op::ap(pre, inc);
+    int excl = lane == 0 ? pre : Op::ap(pre, up);
+    if (x < w) store(x, incl, excl);
+    __syncthreads();
+    if (tid == BLOCK - 1) s_tmp[NWARP] = incl;
+    __syncthreads();
+  }
+  const int total = s_tmp[NWARP];
+  __syncthreads(); // the next scan re-initialises s_tmp[NWARP]
+  return total;
+}
+
+// ------------------------------------------------------------------ shared-memory layout
+struct Layout {
+  uint32_t lut, cT, cB, key, hpos, rend, off, V, outb, total;
+};
+__host__ __device__ inline Layout make_layout(int mode, int sp, int cols, int src_w, uint32_t out_bytes) {
+  Layout L;
+  uint32_t o = 0;
+  L.lut = o;
+  o += al16((uint32_t)sizeof(GlyphLut));
+  L.cT = o;
+  o += al16(4u * cols);
+  L.cB = o;
+  o += (mode >= EM_HB_TRUE && mode <= EM_HB_MONO) ? al16(4u * cols) : 0u;
+  L.key = o;
+  o += al16(2u * cols);
+  L.hpos = o;
+  o += al16(2u * cols);
+  L.rend = o;
+  o += al16(2u * cols);
+  L.off = o;
+  o += al16(4u * cols);
+  L.V = o;
+  o += sp == SP_BOX_STREAM ? al16(2u * 3u * src_w) : 0u;
+  L.outb = o;
+  o += al16(out_bytes);
+  L.total = o;
+  return L;
+}
+
+uint32_t row_capacity_bytes(int mode, int cols, int pad_left) { // SURVEY.md §8a grammar table maxima
+  uint32_t per;
+  switch (mode) {
+  case EM_MONO_FG: per = 4; break;
+  case EM_256_FG: per = 11 + 4; break;
+  case EM_16_FG: per = 5 + 4; break;
+  case EM_TRUE_FG: per = 19 + 4; break;
+  case EM_HB_TRUE: per = 19 + 19 + 3; break;
+  case EM_HB_256: per = 11 + 11 + 3; break;
+  case EM_HB_16: per = 5 + 6 + 3; break;
+  case EM_HB_MONO: per = 3; break;
+  default: per = 6 + 5 + 4; break; // EM_DITHER_BG
+  }
+  // a run head may also own a REP tail (<= 2+5+1 bytes) or a reset before a transparent run (4 bytes):
+  // both replace glyph bytes of other cells, so `per` per cell + 16 slack bounds the row
+  return al16((uint32_t)pad_left + per * (uint32_t)cols + 4u /*reset*/ + 1u /*\n*/ + 4u /*frame reset*/ + 16u);
+}
+
+// ------------------------------------------------------------------ phase A: resized pixels
+__device__ __forceinline__ uint32_t load_px(const uint8_t *p) {
+  return ((uint32_t)p[0] << 16) | ((uint32_t)p[1] << 8) | (uint32_t)p[2];
+}
+
+// nearest neighbour — image.c:293-325 (u32 fixed-point, wraps like the reference)
+__device__ __forceinline__ void cells_nn(const RenderParams &p, const uint8_t *frame, int y, uint32_t *out) {
+  const uint32_t xr = (uint32_t)((((uint64_t)p.src_w << 16) / (uint64_t)p.cols) + 1);
+  const uint32_t yr = (uint32_t)((((uint64_t)p.src_h << 16) / (uint64_t)p.rows_px) + 1);
+  uint32_t sy;
+  if (p.pregathered) {
+    sy = (uint32_t)y;
+  } else {
+    sy = ((uint32_t)y * yr) >> 16;
+    if (sy >= (uint32_t)p.src_h) sy = (uint32_t)p.src_h - 1;
+  }
+  const uint8_t *row = frame + (size_t)sy * (size_t)p.src_w * 3u;
+  for (int x = threadIdx.x; x < p.cols; x += BLOCK) {
+    uint32_t sx = ((uint32_t)x * xr) >> 16;
+    if (sx >= (uint32_t)p.src_w) sx = (uint32_t)p.src_w - 1;
+    out[x] = load_px(row + (size_t)sx * 3u);
+  }
+}
+
+__device__ __forceinline__ void box_range(int d, int src, int dst, int &a, int &b) {
+  a = (int)(((long long)d * src) / dst);
+  b = (int)(((long long)(d + 1) * src) / dst);
+  if (b <= a) b = a + 1;
+  if (b > src) b = src;
+  if (a >= src) a = src - 1;
+}
+
+// box filter, any geometry: one thread per destination pixel, byte loads
+__device__ __forceinline__ void cells_box_generic(const RenderParams &p, const uint8_t *frame, int y, uint32_t *out) {
+  int y0, y1;
+  box_range(y, p.src_h, p.rows_px, y0, y1);
+  for (int x = threadIdx.x; x < p.cols; x += BLOCK) {
+    int x0, x1;
+    box_range(x, p.src_w, p.cols, x0, x1);
+    uint32_t sr = 0, sg = 0, sb = 0;
+    for (int yy = y0; yy < y1; yy++) {
+      const uint8_t *q = frame + ((size_t)yy * p.src_w + x0) * 3u;
+      for (int xx = x0; xx < x1; xx++, q += 3) {
+        sr += q[0];
+        sg += q[1];
+        sb += q[2];
+      }
+    }
+    uint32_t n = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0), h = n >> 1;
+    out[x] = (((sr + h) / n) << 16) | (((sg + h) / n) << 8) | ((sb + h) / n);
+  }
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) { // read-once data: bypass L1 allocation
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void acc16(uint32_t (&a)[8], const uint4 &v) {
+  // 16 byte lanes -> 16 u16 partial sums, two per register (even bytes / odd bytes of each word)
+  a[0] += v.x & 0x00FF00FFu;
+  a[1] += (v.x >> 8) & 0x00FF00FFu;
+  a[2] += v.y & 0x00FF00FFu;
+  a[3] += (v.y >> 8) & 0x00FF00FFu;
+  a[4] += v.z & 0x00FF00FFu;
+  a[5] += (v.z >> 8) & 0x00FF00FFu;
+  a[6] += v.w & 0x00FF00FFu;
+  a[7] += (v.w >> 8) & 0x00FF00FFu;
+}
+
+// box filter, streaming: the band of source rows [y0,y1) is one contiguous byte range; every thread owns
+// 16-byte columns of it, sums them down the band in registers (u16 lanes, band <= 256 rows), parks the
+// column sums V[3*src_w] in shared memory, then one thread per destination pixel adds its x-range.
+__device__ __forceinline__ void cells_box_stream(const RenderParams &p, const uint8_t *frame, int y, uint32_t *out,
+                                                 uint16_t *V) {
+  int y0, y1;
+  box_range(y, p.src_h, p.rows_px, y0, y1);
+  const int R = p.src_w * 3;
+  const int nchunk = R >> 4;
+  const uint4 *band = reinterpret_cast<const uint4 *>(frame + (size_t)y0 * (size_t)R);
+  const int nrow = y1 - y0;
+  for (int c = threadIdx.x; c < nchunk; c += BLOCK) {
+    uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint4 *q = band + c;
+    int r = 0;
+    for (; r + 8 <= nrow; r += 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = ldg_stream(q + (size_t)k * nchunk);
+      q += (size_t)8 * nchunk;
+#pragma unroll
+      for (int k = 0; k < 8; k++) acc16(a, v[k]);
+    }
+    for (; r < nrow; r++) {
+      uint4 v = ldg_stream(q);
+      q += nchunk;
+      acc16(a, v);
+    }
+    // byte j of word k is column 16c + 4k + j:  even reg = {b0 | b2<<16}, odd reg = {b1 | b3<<16}
+    uint4 lo, hi;
+    lo.x = __byte_perm(a[0], a[1], 0x5410); // b0,b1
+    lo.y = __byte_perm(a[0], a[1], 0x7632); // b2,b3
+    lo.z = __byte_perm(a[2], a[3], 0x5410);
+    lo.w = __byte_perm(a[2], a[3], 0x7632);
+    hi.x = __byte_perm(a[4], a[5], 0x5410);
+    hi.y = __byte_perm(a[4], a[5], 0x7632);
+    hi.z = __byte_perm(a[6], a[7], 0x5410);
+    hi.w = __byte_perm(a[6], a[7], 0x7632);
+    uint4 *dst = reinterpret_cast<uint4 *>(V + (size_t)c * 16);
+    dst[0] = lo;
+    dst[1] = hi;
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < p.cols; x += BLOCK) {
+    int x0, x1;
+    box_range(x, p.src_w, p.cols, x0, x1);
+    uint32_t sr = 0, sg = 0, sb = 0;
+    const uint16_t *q = V + 3 * x0;
+    for (int xx = x0; xx < x1; xx++, q += 3) {
+      sr += q[0];
+      sg += q[1];
+      sb += q[2];
+    }
+    uint32_t n = (uint32_t)(x1 - x0) * (uint32_t)nrow, h = n >> 1;
+    out[x] = (((sr + h) / n) << 16) | (((sg + h) / n) << 8) | ((sb + h) / n);
+  }
+  __syncthreads(); // V is reused by the next pixel row
+}
+
+// ------------------------------------------------------------------ phase B: per-cell emission
+struct RowCtx {
+  const GlyphLut *lut;
+  const uint32_t *cT, *cB;
+  const uint16_t *key, *hpos, *rend;
+};
+
+template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int x, const RowCtx &c) {
+  if (MODE == EM_256_FG) {
+    uint32_t px = c.cT[x];
+    put_sgr_256(s, false, (uint32_t)q256_of(px));
+    put_glyph(s, c.lut->glyph[luma_of(px)]);
+  } else if (MODE == EM_16_FG) {
+    uint32_t px = c.cT[x];
+    put_sgr_16(s, false, (uint32_t)q16_of(px));
+    put_glyph(s, c.lut->glyph[luma_of(px)]);
+  } else if (MODE == EM_TRUE_FG) {
+    // ansi_rle_add_pixel (ansi.c:261-300) as a cell rule; hpos[x] = previous ASCII-glyph cell of this row
+    uint32_t px = c.cT[x];
+    const uint8_t *g = c.lut->glyph[luma_of(px)];
+    bool ascii = g[0] == 1 && g[1] < 128;
+    if (ascii) {
+      uint16_t pa = c.hpos[x];
+      if (pa == NONE16 || c.cT[pa] != px) put_sgr_rgb(s, false, px);
+      s.put(g[1]);
+    } else {
+      put_sgr_rgb(s, false, px);
+      put_glyph(s, g);
+    }
+  } else if (MODE == EM_MONO_FG) {
+    int h = c.hpos[x];
+    uint32_t run = (uint32_t)c.rend[h] - (uint32_t)h;
+    bool rep = rep_profitable(run);
+    const uint8_t *g = c.lut->glyph[luma_of(c.cT[x])]; // same glyph for every cell of the run (same key)
+    if (h == x) {
+      put_glyph(s, g);
+      if (rep) put_rep(s, run - 1);
+    } else if (!rep) {
+      put_glyph(s, g);
+    }
+  } else if (MODE == EM_HB_MONO) {
+    int h = c.hpos[x];
+    uint32_t run = (uint32_t)c.rend[h] - (uint32_t)h;
+    bool rep = rep_profitable(run);
+    int lt = luma76_of(c.cT[h]), lb = luma76_of(c.cB[h]);
+    if (lt < 16 && lb < 16) {
+      s.put(' ');
+    } else if (h == x || !rep) {
+      const uint8_t sh = (uint8_t)((lt >> 6) == 0 ? 0x91 : (lt >> 6) == 1 ? 0x92 : (lt >> 6) == 2 ? 0x93 : 0x88);
+      put3(s, 0xE2, 0x96, sh);
+      if (h == x && rep) put_rep(s, run - 1);
+    }
+  } else { // EM_HB_TRUE / EM_HB_256 / EM_HB_16
+    int h = c.hpos[x];
+    uint32_t run = (uint32_t)c.rend[h] - (uint32_t)h;
+    bool rep = rep_profitable(run);
+    uint32_t tH = c.cT[h], bH = c.cB[h];
+    bool prev_set = false;
+    int ph = 0;
+    if (h > 0) {
+      ph = c.hpos[h - 1];
+      prev_set = (c.cT[ph] | c.cB[ph]) != 0u; // a transparent run leaves the colour state cleared
+    }
+    if ((tH | bH) == 0u) { // transparent: decided by the run head's raw RGB (halfblock.c:111,357,476)
+      if (h == x && prev_set) put_reset(s);
+      s.put(' ');
+    } else if (h == x) {
+      if (MODE == EM_HB_TRUE) {
+        if (!prev_set || c.cT[ph] != tH) put_sgr_rgb(s, false, tH);
+        if (!prev_set || c.cB[ph] != bH) put_sgr_rgb(s, true, bH);
+      } else {
+        uint32_t k = c.key[h], pk = prev_set ? c.key[ph] : 0u;
+        if (MODE == EM_HB_256) {
+          if (!prev_set || (pk >> 8) != (k >> 8)) put_sgr_256(s, false, k >> 8);
+          if (!prev_set || (pk & 255u) != (k & 255u)) put_sgr_256(s, true, k & 255u);
+        } else {
+          if (!prev_set || (pk >> 8) != (k >> 8)) put_sgr_16(s, false, k >> 8);
+          if (!prev_set || (pk & 255u) != (k & 255u)) put_sgr_16(s, true, k & 255u);
+        }
+      }
+      put3(s, 0xE2, 0x96, 0x80);
+      if (rep) put_rep(s, run - 1);
+    } else if (!rep) {
+      put3(s, 0xE2, 0x96, 0x80);
+    }
+  }
+}
+
+template <int MODE, int SP> __global__ void __launch_bounds__(BLOCK) k_render_rows(const RenderParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ int s_tmp[NWARP + 1];
+  __shared__ uint32_t s_cond[4]; // TRUE_FG: {cond_off, cond_len, last_rgb, first_rgb}
+
+  constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
+  constexpr bool RUNS = MODE == EM_MONO_FG || HB;
+  constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
+
+  const int tid = threadIdx.x;
+  const int t = (int)(blockIdx.x % (unsigned)p.text_rows);
+  const int f = (int)(blockIdx.x / (unsigned)p.text_rows);
+  const int w = p.cols;
+  const bool last_row = t == p.text_rows - 1;
+
+  const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
+  const Layout L = make_layout(MODE, SP, w, p.src_w, cap);
+  GlyphLut *lut = reinterpret_cast<GlyphLut *>(smem + L.lut);
+  uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.cT);
+  uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.cB);
+  uint16_t *key = reinterpret_cast<uint16_t *>(smem + L.key);
+  uint16_t *hpos = reinterpret_cast<uint16_t *>(smem + L.hpos);
+  uint16_t *rend = reinterpret_cast<uint16_t *>(smem + L.rend);
+  uint32_t *off = reinterpret_cast<uint32_t *>(smem + L.off);
+  uint16_t *V = reinterpret_cast<uint16_t *>(smem + L.V);
+  uint8_t *outb = smem + L.outb;
+
+  if (USES_LUT) {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(lut);
+    for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += BLOCK) dst[i] = src[i];
+  }
+  if (tid < 4) s_cond[tid] = 0u;
+
+  // ---- phase A
+  const uint8_t *frame = p.frames + (size_t)f * p.frame_stride;
+  const int yT = HB ? 2 * t : t;
+  const bool hasB = HB && (2 * t + 1 < p.rows_px);
+  if (SP == SP_NN) {
+    cells_nn(p, frame, yT, cT);
+    if (hasB) cells_nn(p, frame, yT + 1, cB);
+  } else if (SP == SP_BOX_GENERIC) {
+    cells_box_generic(p, frame, yT, cT);
+    if (hasB) cells_box_generic(p, frame, yT + 1, cB);
+  } else {
+    cells_box_stream(p, frame, yT, cT, V);
+    if (hasB) cells_box_stream(p, frame, yT + 1, cB, V);
+  }
+  __syncthreads();
+  if (HB && !hasB) { // odd pixel height: bottom := top (halfblock.c:73,82-88)
+    for (int x = tid; x < w; x += BLOCK) cB[x] = cT[x];
+    __syncthreads();
+  }
+  if (p.cells_out) {
+    uint8_t *co = p.cells_out + ((size_t)f * p.rows_px + yT) * (size_t)w * 3u;
+    for (int x = tid; x < w; x += BLOCK) {
+      uint32_t c = cT[x];
+      co[3 * x] = (uint8_t)(c >> 16);
+      co[3 * x + 1] = (uint8_t)(c >> 8);
+      co[3 * x + 2] = (uint8_t)c;
+      if (hasB) {
+        uint32_t d = cB[x];
+        uint8_t *cb = co + (size_t)w * 3u;
+        cb[3 * x] = (uint8_t)(d >> 16);
+        cb[3 * x + 1] = (uint8_t)(d >> 8);
+        cb[3 * x + 2] = (uint8_t)d;
+      }
+    }
+  }
+  if (p.rows == nullptr) return; // resize-only invocation
+
+  // ---- phase B1: run keys
+  if (MODE == EM_MONO_FG) {
+    for (int x = tid; x < w; x += BLOCK) key[x] = lut->key[luma_of(cT[x])];
+  } else if (MODE == EM_HB_256) {
+    for (int x = tid; x < w; x += BLOCK) key[x] = (uint16_t)((q256_of(cT[x]) << 8) | q256_of(cB[x]));
+  } else if (MODE == EM_HB_16) {
+    for (int x = tid; x < w; x += BLOCK) key[x] = (uint16_t)((q16_of(cT[x]) << 8) | q16_of(cB[x]));
+  }
+  __syncthreads();
+
+  // ---- phase B2: run heads / previous-ASCII links
+  if (RUNS) {
+    auto is_head = [&](int x) -> bool {
+      if (x == 0) return true;
+      if (MODE == EM_HB_TRUE || MODE == EM_HB_MONO) return cT[x] != cT[x - 1] || cB[x] != cB[x - 1];
+      return key[x] != key[x - 1];
+    };
+    row_scan<OpMax>(
+        w, [&](int x) { return is_head(x) ? x : -1; }, [&](int x, int incl, int) { hpos[x] = (uint16_t)incl; },
+        s_tmp);
+    __syncthreads();
+    for (int x = tid; x < w; x += BLOCK) {
+      if (x > 0 && hpos[x] == x) rend[hpos[x - 1]] = (uint16_t)x; // this head closes the previous run
+      if (x == w - 1) rend[hpos[x]] = (uint16_t)w;
+    }
+    __syncthreads();
+  } else if (MODE == EM_TRUE_FG) {
+    int last_ascii = row_scan<OpMax>(
+        w,
+        [&](int x) {
+          const uint8_t *g = lut->glyph[luma_of(cT[x])];
+          return (g[0] == 1 && g[1] < 128) ? x : -1;
+        },
+        [&](int x, int, int excl) { hpos[x] = excl < 0 ? NONE16 : (uint16_t)excl; }, s_tmp);
+    if (tid == 0) s_cond[2] = last_ascii >= 0 ? (0x01000000u | cT[last_ascii]) : 0u;
+  }
+
+  // ---- phase B3: byte counts -> offsets
+  RowCtx ctx{lut, cT, cB, key, hpos, rend};
+  int cells_bytes = row_scan<OpAdd>(
+      w,
+      [&](int x) {
+        CountSink cs;
+        emit_cell<MODE>(cs, x, ctx);
+        return (int)cs.n;
+      },
+      [&](int x, int, int excl) { off[x] = (uint32_t)excl + (uint32_t)p.pad_left; }, s_tmp);
+  const uint32_t body_end = (uint32_t)p.pad_left + (uint32_t)cells_bytes;
+
+  // ---- phase B4: materialise
+  uint8_t *grow = p.rows + ((size_t)f * p.text_rows + t) * (size_t)p.row_pitch;
+  uint8_t *base = p.use_smem_out ? outb : grow;
+  for (int i = tid; i < p.pad_left; i += BLOCK) base[i] = ' ';
+  for (int x = tid; x < w; x += BLOCK) {
+    WriteSink ws{base + off[x]};
+    emit_cell<MODE>(ws, x, ctx);
+    if (MODE == EM_TRUE_FG && hpos[x] == NONE16) {
+      const uint8_t *g = lut->glyph[luma_of(cT[x])];
+      if (g[0] == 1 && g[1] < 128) { // the row's first ASCII-glyph cell: its SGR is conditional on the row above
+        CountSink cs;
+        put_sgr_rgb(cs, false, cT[x]);
+        s_cond[0] = off[x];
+        s_cond[1] = cs.n;
+        s_cond[3] = 0x01000000u | cT[x];
+      }
+    }
+  }
+  uint32_t len = body_end;
+  if (tid == 0) {
+    WriteSink ws{base + body_end};
+    if (MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16)
+      put_reset(ws);
+    if (MODE == EM_TRUE_FG && last_row) put_reset(ws); // ansi_rle_finish, ansi.c:303-314
+    if (!last_row) ws.put('\n');
+    len = (uint32_t)(ws.p - base);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    RowMeta m;
+    m.len = len;
+    m.cond_off = s_cond[0];
+    m.cond_len = s_cond[1];
+    m.first_rgb = s_cond[3];
+    m.last_rgb = s_cond[2];
+    m._pad[0] = m._pad[1] = m._pad[2] = 0;
+    p.meta[(size_t)f * p.text_rows + t] = m;
+    s_cond[0] = len;
+  }
+  __syncthreads();
+  if (p.use_smem_out) {
+    const uint32_t n16 = (s_cond[0] + 15u) >> 4;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(outb);
+    uint4 *d4 = reinterpret_cast<uint4 *>(grow);
+    for (uint32_t i = tid; i < n16; i += BLOCK) d4[i] = s4[i];
+  }
+}
+
+// ------------------------------------------------------------------ stitch rows -> frame string
+__global__ void __launch_bounds__(256) k_stitch(const StitchParams p) {
+  __shared__ uint32_t s_off[64], s_drop[64];
+  __shared__ uint32_t s_total;
+  const int groups = (p.text_rows + p.rows_per_cta - 1) / p.rows_per_cta;
+  const int f = (int)(blockIdx.x / (unsigned)groups);
+  const int g = (int)(blockIdx.x % (unsigned)groups);
+  const int r0 = g * p.rows_per_cta;
+  const int r1 = min(r0 + p.rows_per_cta, p.text_rows);
+  const RowMeta *meta = p.meta + (size_t)f * p.text_rows;
+  if (threadIdx.x == 0) {
+    // serial prefix over the rows above this group (row counts are tens to a few thousand)
+    uint32_t o = (uint32_t)p.pad_top, carry = 0;
+    const bool tf = p.mode == EM_TRUE_FG;
+    const int upto = (g == groups - 1) ? p.text_rows : r1;
+    for (int r = 0; r < upto; r++) {
+      const RowMeta m = meta[r];
+      uint32_t drop = 0;
+      if (tf) {
+        // ansi_rle_add_pixel state across rows: the first ASCII cell of a row re-emits its SGR only if its
+        // colour differs from the last ASCII cell seen anywhere above (ansi.c:263)
+        if (m.cond_len && carry && m.first_rgb == carry) drop = m.cond_len;
+        if (m.last_rgb) carry = m.last_rgb;
+      }
+      if (r >= r0 && r < r1) {
+        s_off[r - r0] = o;
+        s_drop[r - r0] = drop;
+      }
+      o += m.len - drop;
+    }
+    s_total = o;
+  }
+  __syncthreads();
+  uint8_t *out = p.out + (size_t)f * p.out_pitch;
+  if (g == 0)
+    for (int i = threadIdx.x; i < p.pad_top; i += blockDim.x) out[i] = '\n';
+  if (g == groups - 1 && threadIdx.x == 0) {
+    out[s_total] = 0;
+    p.out_len[f] = s_total;
+  }
+  for (int r = r0; r < r1; r++) {
+    const RowMeta m = meta[r];
+    const uint8_t *src = p.rows + ((size_t)f * p.text_rows + r) * (size_t)p.row_pitch;
+    uint8_t *dst = out + s_off[r - r0];
+    const uint32_t drop = s_drop[r - r0];
+    const uint32_t a = drop ? m.cond_off : m.len; // [0,a) then [a+drop, len)
+    for (uint32_t i = threadIdx.x; i < a; i += blockDim.x) dst[i] = src[i];
+    for (uint32_t i = a + drop + threadIdx.x; i < m.len; i += blockDim.x) dst[i - drop] = src[i];
+  }
+}
+
+// ------------------------------------------------------------------ NN resize only (image_resize drop-in)
+__global__ void k_resize_nn(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh, int pregathered) {
+  const uint32_t xr = (uint32_t)((((uint64_t)sw << 16) / (uint64_t)dw) + 1);
+  const uint32_t yr = (uint32_t)((((uint64_t)sh << 16) / (uint64_t)dh) + 1);
+  const size_t n = (size_t)dw * dh;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t y = (uint32_t)(i / dw), x = (uint32_t)(i % dw);
+    uint32_t sy = pregathered ? y : ((y * yr) >> 16);
+    if (!pregathered && sy >= (uint32_t)sh) sy = (uint32_t)sh - 1;
+    uint32_t sx = (x * xr) >> 16;
+    if (sx >= (uint32_t)sw) sx = (uint32_t)sw - 1;
+    const uint8_t *q = src + ((size_t)sy * sw + sx) * 3u;
+    uint8_t *d = dst + i * 3u;
+    d[0] = q[0];
+    d[1] = q[1];
+    d[2] = q[2];
+  }
+}
+
+// ------------------------------------------------------------------ pixel-space composite cell (stream.c:723-773)
+__global__ void k_composite_cell(const uint8_t *src, int sw, int sh, uint8_t *comp, int cw, int ch, int tw, int th,
+                                 int x0, int y0, int cellw, int cellh) {
+  const uint32_t xr = (uint32_t)((((uint64_t)sw << 16) / (uint64_t)tw) + 1);
+  const uint32_t yr = (uint32_t)((((uint64_t)sh << 16) / (uint64_t)th) + 1);
+  const int xp = (cellw - tw) / 2, yp = (cellh - th) / 2;
+  const int n = tw * th;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int y = i / tw, x = i % tw;
+    int dx = x0 + xp + x, dy = y0 + yp + y;
+    if (dx < x0 || dx > x0 + cellw - 1 || dy < y0 || dy > y0 + cellh - 1) continue;
+    if (dx < 0 || dx >= cw || dy < 0 || dy >= ch) continue;
+    uint32_t sy = ((uint32_t)y * yr) >> 16, sx = ((uint32_t)x * xr) >> 16;
+    if (sy >= (uint32_t)sh) sy = (uint32_t)sh - 1;
+    if (sx >= (uint32_t)sw) sx = (uint32_t)sw - 1;
+    const uint8_t *q = src + ((size_t)sy * sw + sx) * 3u;
+    uint8_t *d = comp + ((size_t)dy * cw + dx) * 3u;
+    d[0] = q[0];
+    d[1] = q[1];
+    d[2] = q[2];
+  }
+}
+
+// ------------------------------------------------------------------ Floyd–Steinberg 16-colour background renderer
+// rgb_to_16color_dithered (ansi.c:511-583) is a raster-order recurrence; pixel (x,y) only needs the errors pushed by
+// (x-1,y) and (x-1..x+1, y-1), so row y may trail row y-1 by 3 pixels: one thread per row, a skewed wavefront of
+// w + 3*(rows-1) steps.  Integer += is order independent, so the sums equal the serial ones.
+__global__ void __launch_bounds__(256) k_dither_bg(const uint8_t *cells, int w, int h, int pad_left, const GlyphLut *lut,
+                                                   uint8_t *rows, uint32_t row_pitch, RowMeta *meta, int *err_all) {
+  const int f = blockIdx.x;
+  const uint8_t *img = cells + (size_t)f * w * h * 3u;
+  int *err = err_all + (size_t)f * w * h * 3u;
+  for (int band = 0; band < h; band += blockDim.x) {
+    const int j = threadIdx.x;
+    const int y = band + j;
+    const int nrows = min((int)blockDim.x, h - band);
+    const bool active = y < h;
+    uint8_t *out = active ? rows + ((size_t)f * h + y) * (size_t)row_pitch : nullptr;
+    uint32_t o = 0;
+    if (active)
+      for (int i = 0; i < pad_left; i++) out[o++] = ' ';
+    const int steps = w + 3 * (nrows - 1);
+    for (int s = 0; s < steps; s++) {
+      const int x = s - 3 * j;
+      if (active && x >= 0 && x < w) {
+        const size_t i = (size_t)y * w + x;
+        const uint8_t *px = img + i * 3u;
+        int v[3], c[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          v[k] = (int)px[k] + err[i * 3 + k];
+          c[k] = v[k] < 0 ? 0 : (v[k] > 255 ? 255 : v[k]);
+        }
+        const int q = q16_rgb(c[0], c[1], c[2]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const int e = v[k] - (int)c_ansi16[q][k];
+          if (x + 1 < w) err[(i + 1) * 3 + k] += (e * 7) / 16;
+          if (y + 1 < h) {
+            if (x - 1 >= 0) err[(i + w - 1) * 3 + k] += (e * 3) / 16;
+            err[(i + w) * 3 + k] += (e * 5) / 16;
+            if (x + 1 < w) err[(i + w + 1) * 3 + k] += (e * 1) / 16;
+          }
+        }
+        const int bl = ((int)c_ansi16[q][0] * 77 + (int)c_ansi16[q][1] * 150 + (int)c_ansi16[q][2] * 29) / 256;
+        WriteSink ws{out + o};
+        put_sgr_16(ws, true, (uint32_t)q);                // foreground.c:807
+        put_sgr_16(ws, false, bl < 127 ? 15u : 0u);       // foreground.c:804-808
+        put_glyph(ws, lut->glyph[luma_of(load_px(px))]);  // cache[Y], foreground.c:820
+        o = (uint32_t)(ws.p - out);
+      }
+      __syncthreads();
+    }
+    if (active) {
+      WriteSink ws{out + o};
+      put_reset(ws);
+      if (y < h - 1) ws.put('\n');
+      RowMeta m{};
+      m.len = (uint32_t)(ws.p - out);
+      meta[(size_t)f * h + y] = m;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ launchers
+template <int MODE, int SP> static cudaError_t launch_rows_t(const RenderParams &p, cudaStream_t st) {
+  const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
+  const Layout L = make_layout(MODE, SP, p.cols, p.src_w, cap);
+  if (L.total > 227u * 1024u) return cudaErrorInvalidConfiguration;
+  static bool configured = false; // benign race: the attribute is idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_render_rows<MODE, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const unsigned grid = (unsigned)p.n_frames * (unsigned)p.text_rows;
+  k_render_rows<MODE, SP><<<grid, BLOCK, L.total, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int MODE> static cudaError_t launch_rows_sp(const RenderParams &p, int sp, cudaStream_t st) {
+  switch (sp) {
+  case SP_NN: return launch_rows_t<MODE, SP_NN>(p, st);
+  case SP_BOX_GENERIC: return launch_rows_t<MODE, SP_BOX_GENERIC>(p, st);
+  default: return launch_rows_t<MODE, SP_BOX_STREAM>(p, st);
+  }
+}
+
+cudaError_t launch_render_rows(const RenderParams &p, int mode, int sp, cudaStream_t st) {
+  switch (mode) {
+  case EM_MONO_FG: return launch_rows_sp<EM_MONO_FG>(p, sp, st);
+  case EM_256_FG: return launch_rows_sp<EM_256_FG>(p, sp, st);
+  case EM_16_FG: return launch_rows_sp<EM_16_FG>(p, sp, st);
+  case EM_TRUE_FG: return launch_rows_sp<EM_TRUE_FG>(p, sp, st);
+  case EM_HB_TRUE: return launch_rows_sp<EM_HB_TRUE>(p, sp, st);
+  case EM_HB_256: return launch_rows_sp<EM_HB_256>(p, sp, st);
+  case EM_HB_16: return launch_rows_sp<EM_HB_16>(p, sp, st);
+  case EM_HB_MONO: return launch_rows_sp<EM_HB_MONO>(p, sp, st);
+  default: return cudaErrorInvalidValue;
+  }
+}
+
+size_t rows_smem_total(int mode, int sp, int cols, int src_w, uint32_t out_bytes) {
+  return make_layout(mode, sp, cols, src_w, out_bytes).total;
+}
+
+cudaError_t launch_stitch(const StitchParams &p, int n_frames, cudaStream_t st) {
+  const int groups = (p.text_rows + p.rows_per_cta - 1) / p.rows_per_cta;
+  k_stitch<<<(unsigned)n_frames * (unsigned)groups, 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resize_nn_only(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh, int pregathered,
+                                  cudaStream_t st) {
+  size_t n = (size_t)dw * dh;
+  unsigned grid = (unsigned)((n + 255) / 256);
+  if (grid > 148u * 16u) grid = 148u * 16u;
+  if (grid == 0) grid = 1;
+  k_resize_nn<<<grid, 256, 0, st>>>(src, sw, sh, dst, dw, dh, pregathered);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dither_bg(const uint8_t *cells, int w, int h, int n_frames, int pad_left, const GlyphLut *lut,
+                             uint8_t *rows, uint32_t row_pitch, RowMeta *meta, int *err_scratch, cudaStream_t st) {
+  k_dither_bg<<<(unsigned)n_frames, 256, 0, st>>>(cells, w, h, pad_left, lut, rows, row_pitch, meta, err_scratch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_composite_cell(const uint8_t *src, int sw, int sh, uint8_t *comp, int cw, int ch, int tw, int th,
+                                  int x0, int y0, int cellw, int cellh, cudaStream_t st) {
+  int n = tw * th;
+  unsigned grid = (unsigned)((n + 255) / 256);
+  if (grid > 148u * 8u) grid = 148u * 8u;
+  if (grid == 0) grid = 1;
+  k_composite_cell<<<grid, 256, 0, st>>>(src, sw, sh, comp, cw, ch, tw, th, x0, y0, cellw, cellh);
+  return cudaGetLastError();
+}
+
+} // namespace acb

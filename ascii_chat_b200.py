@@ -1,0 +1,12 @@
+"""Import shim: the package directory is `ascii-chat_b200/` (project name, with a hyphen), which
+Python cannot import by name.  `import ascii_chat_b200` loads it under this importable alias."""
+import importlib.util as _u
+import os as _os
+import sys as _sys
+
+_pkg_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "ascii-chat_b200")
+_spec = _u.spec_from_file_location("ascii_chat_b200", _os.path.join(_pkg_dir, "__init__.py"),
+                                   submodule_search_locations=[_pkg_dir])
+_mod = _u.module_from_spec(_spec)
+_sys.modules["ascii_chat_b200"] = _mod
+_spec.loader.exec_module(_mod)

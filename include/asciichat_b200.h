@@ -1,0 +1,217 @@
+/*
+ * asciichat_b200.h — C-ABI of libasciichat_b200.so
+ *
+ * A Blackwell (sm_100a) implementation of zfogg/ascii-chat's per-frame
+ * RGB -> glyph + ANSI render path behind libasciichat's own entry points.
+ * Plain C, plain pointers and sizes; no CUDA or torch types appear here.
+ *
+ * Part 1 re-declares, with identical names / argument meaning / ownership / error
+ * behaviour, the reference entry points this library replaces (the file:line each one
+ * replaces is cited; paths are relative to the reference checkout).  A host build that
+ * already includes the reference headers defines ASCIICHAT_B200_NO_TYPES and gets only
+ * the prototypes it does not have (Part 2).
+ *
+ * Part 2 is the batch interface the drop-in calls are built on: frames resident in
+ * HBM, many frames per launch, device-side timing for the roofline numbers.
+ *
+ * Every function fails loudly (NULL / negative code + acb200_last_error()) when no
+ * CUDA device is usable.  There is no CPU fallback in this library.
+ */
+#ifndef ASCIICHAT_B200_H
+#define ASCIICHAT_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <sys/types.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+
+/* ======================================================================== Part 1
+ * types crossing the boundary (layout-identical to the reference's)            */
+#ifndef ASCIICHAT_B200_NO_TYPES
+
+/* include/ascii-chat/video/rgba/image.h:81-85 — packed RGB24 */
+typedef struct {
+  uint8_t r, g, b;
+} __attribute__((packed)) rgb_pixel_t;
+
+/* include/ascii-chat/video/rgba/image.h:143-148 */
+typedef struct {
+  int w, h;
+  rgb_pixel_t *pixels;  /* w*h pixels, row-major, pitch 3*w */
+  uint8_t alloc_method; /* untouched by this library */
+} image_t;
+
+/* include/ascii-chat/platform/terminal.h:578-589 */
+typedef enum {
+  TERM_COLOR_AUTO = -1,
+  TERM_COLOR_NONE = 0,
+  TERM_COLOR_16 = 1,
+  TERM_COLOR_256 = 2,
+  TERM_COLOR_TRUECOLOR = 3
+} terminal_color_mode_t;
+
+/* include/ascii-chat/platform/terminal.h:660-667 */
+typedef enum { RENDER_MODE_FOREGROUND = 0, RENDER_MODE_BACKGROUND = 1, RENDER_MODE_HALF_BLOCK = 2 } render_mode_t;
+
+/* include/ascii-chat/platform/terminal.h:707-738 (sizeof == 240 on LP64).
+ * Fields read by the render path: color_level, render_mode, wants_padding. */
+typedef struct {
+  terminal_color_mode_t color_level;
+  uint32_t capabilities;
+  uint32_t color_count;
+  bool utf8_support;
+  bool detection_reliable;
+  render_mode_t render_mode;
+  char term_type[64];
+  char colorterm[64];
+  bool wants_background;
+  int palette_type;
+  char palette_custom[64];
+  uint8_t desired_fps;
+  int color_filter; /* color_filter_t */
+  bool wants_padding;
+  size_t pad_height;
+} terminal_capabilities_t;
+
+/* include/ascii-chat/video/ascii/ascii.h:358-361 */
+typedef struct {
+  const char *frame_data;
+  size_t frame_size;
+} ascii_frame_source_t;
+
+#endif /* ASCIICHAT_B200_NO_TYPES */
+
+/* ---- drop-in entry points.  Inputs are borrowed and never modified; every returned
+ * string is NUL-terminated and allocated with the allocator set by acb200_set_allocator()
+ * (default malloc), to be released by the caller's SAFE_FREE.  NULL on error (the caller
+ * skips the frame, src/server/render.c:629); the error code (ERROR_INVALID_PARAM = 86,
+ * ERROR_MEMORY = 3, ERROR_INVALID_STATE = 85) is readable through acb200_last_error() and is
+ * forwarded to asciichat_set_errno_with_message() when the host binary defines it. */
+
+/* lib/video/ascii/ascii.c:72-191 (include/ascii-chat/video/ascii/ascii.h:172).
+ * GET_OPTION(render_mode) is supplied through acb200_set_option_render_mode(). */
+char *ascii_convert(image_t *original, const ssize_t width, const ssize_t height, const bool color,
+                    const bool aspect_ratio, const bool stretch, const char *palette_chars,
+                    const char luminance_palette[256]);
+
+/* lib/video/ascii/ascii.c:194-387 (ascii.h:213) */
+char *ascii_convert_with_capabilities(image_t *original, const ssize_t width, const ssize_t height,
+                                      const terminal_capabilities_t *caps, const bool use_aspect_ratio,
+                                      const bool stretch, const char *palette_chars);
+
+/* lib/video/ascii/ascii.c:955-1002 (ascii.h:230) — prints an already-resized image */
+char *image_print_with_capabilities(const image_t *image, const terminal_capabilities_t *caps, const char *palette);
+
+/* lib/video/rgba/image.c:256-328 (image.h:574) — nearest-neighbour resize into dest->pixels */
+void image_resize(const image_t *source, image_t *dest);
+
+/* leaf printers, lib/video/ascii/scalar/foreground.c:27,195,433,535,752 and halfblock.c:48,184,297,416 */
+char *image_print(const image_t *p, const char *palette);
+char *image_print_color(const image_t *p, const char *palette);
+char *image_print_256color(const image_t *image, const char *palette);
+char *image_print_16color(const image_t *image, const char *palette);
+char *image_print_16color_dithered_with_background(const image_t *image, bool use_background, const char *palette);
+char *rgb_to_truecolor_halfblocks_scalar(const uint8_t *rgb, int width, int height, int stride_bytes);
+char *rgb_to_halfblocks_scalar(const uint8_t *rgb, int width, int height, int stride_bytes, const char *palette);
+char *rgb_to_16color_halfblocks_scalar(const uint8_t *rgb, int width, int height, int stride_bytes,
+                                       const char *palette);
+char *rgb_to_256color_halfblocks_scalar(const uint8_t *rgb, int width, int height, int stride_bytes,
+                                        const char *palette);
+
+/* ascii_pad_frame_width / ascii_pad_frame_height (ascii.c:457-517, 902-941) have no caller outside
+ * ascii_convert*(); their work (left pad per row, leading newlines) is fused into the render kernels
+ * (acb200_render_cfg_t.pad_left / pad_top), so they are not re-exported. */
+
+/* lib/video/ascii/ascii.c:602-885 (ascii.h:400) — text-space grid of N rendered frames */
+char *ascii_create_grid(ascii_frame_source_t *sources, int source_count, int width, int height, size_t *out_size);
+
+/* lib/video/ascii/common.c:601-604, 497-538 — table init / teardown (device LUT cache here) */
+void ascii_simd_init(void);
+void simd_caches_destroy_all(void);
+
+/* ======================================================================== Part 2
+ * B200 batch interface                                                         */
+
+enum { ACB200_SCALE_NN = 0,   /* reference-exact nearest neighbour (image.c:267-328) */
+       ACB200_SCALE_BOX = 1 }; /* full-coverage box filter: reads every source pixel */
+
+/* One render configuration shared by every frame of a batch. */
+typedef struct {
+  int src_w, src_h;  /* source frame, packed RGB24, pitch 3*src_w */
+  int cols;          /* resized width  = text columns */
+  int rows_px;       /* resized height in pixels (text rows, or 2*text rows in half-block mode) */
+  int color_level;   /* terminal_color_mode_t */
+  int render_mode;   /* render_mode_t */
+  int scale;         /* ACB200_SCALE_* */
+  int pad_left;      /* spaces in front of every text row (ascii_pad_frame_width) */
+  int pad_top;       /* leading newlines (ascii_pad_frame_height) */
+  const char *palette; /* NUL-terminated UTF-8, <= 255 glyphs */
+} acb200_render_cfg_t;
+
+/* 0 on success, else an ERROR_* code.  device < 0 keeps the current device. */
+int acb200_init(int device);
+void acb200_shutdown(void);
+int acb200_last_error(void);            /* thread-local, cleared on read */
+const char *acb200_last_error_message(void);
+void acb200_set_allocator(void *(*alloc_fn)(size_t), void (*free_fn)(void *));
+void acb200_set_option_render_mode(int render_mode); /* stands in for GET_OPTION(render_mode), ascii.c:138,152 */
+void acb200_set_default_scale(int scale);            /* what the drop-in calls use; default ACB200_SCALE_NN */
+
+/* bytes one rendered frame can occupy at most (fixed pitch of the output arena), incl. NUL */
+size_t acb200_frame_capacity(const acb200_render_cfg_t *cfg);
+/* bytes of device scratch acb200_render_batch_device needs for n_frames */
+size_t acb200_scratch_bytes(const acb200_render_cfg_t *cfg, int n_frames);
+
+/* Render n_frames frames that are ALREADY RESIDENT in device memory.
+ *   d_frames : n_frames * src_w*src_h*3 bytes, frame-major
+ *   d_out    : n_frames * out_pitch bytes; frame f's string starts at f*out_pitch, NUL-terminated
+ *   d_out_len: n_frames uint32 string lengths
+ *   d_scratch: acb200_scratch_bytes() bytes
+ *   stream   : a cudaStream_t cast to void* (NULL = this thread's internal stream)
+ * Asynchronous with respect to the host.  Returns 0 or an ERROR_* code. */
+int acb200_render_batch_device(const acb200_render_cfg_t *cfg, const uint8_t *d_frames, int n_frames, uint8_t *d_out,
+                               size_t out_pitch, uint32_t *d_out_len, void *d_scratch, void *stream);
+
+/* Same work from HOST buffers (H2D and D2H inside the call): frames[i] points at src_w*src_h*3 host bytes;
+ * out[i] receives an allocator-owned NUL-terminated string, out_len[i] its length. */
+int acb200_render_batch_host(const acb200_render_cfg_t *cfg, const uint8_t *const *frames, int n_frames, char **out,
+                             size_t *out_len);
+
+/* Device-timed repetition of acb200_render_batch_device (CUDA events on the launch stream):
+ * `iters` passes over the batch, returns total milliseconds in *ms_total and the dominant
+ * kernel's summed milliseconds in *ms_kernel (events around that kernel only). */
+int acb200_time_batch_device(const acb200_render_cfg_t *cfg, const uint8_t *d_frames, int n_frames, uint8_t *d_out,
+                             size_t out_pitch, uint32_t *d_out_len, void *d_scratch, int iters, float *ms_total,
+                             float *ms_kernel);
+
+/* Server pixel-space grid compositor (src/server/stream.c:523-651 layout, 664-779 composite):
+ * n sources (host RGB24) -> one width x 2*height composite written to out_rgb (host). */
+int acb200_composite_host(const uint8_t *const *srcs, const int *ws, const int *hs, int n, int width, int height,
+                          uint8_t *out_rgb, int *out_cols, int *out_rows);
+/* layout only (host float arithmetic, stream.c:523-651) */
+void acb200_grid_layout(const int *ws, const int *hs, int n, int term_w, int term_h, int *cols, int *rows);
+/* aspect fit (host float arithmetic, lib/util/aspect_ratio.c:70-93) */
+void acb200_aspect_ratio(ssize_t img_w, ssize_t img_h, ssize_t width, ssize_t height, bool stretch, ssize_t *out_w,
+                         ssize_t *out_h);
+
+/* number of kernel launches issued by this library since load (bench "gpu_launches") */
+uint64_t acb200_launch_count(void);
+const char *acb200_version(void);
+
+/* Text-space grid from frames that are already on the device (the multi-GPU gather path):
+ * d_srcs[i] = device pointer to source i (host array of n pointers), sizes[i] its length.
+ * d_out must hold width*height + height + 1 bytes.  Same result as ascii_create_grid().
+ * Returns 0 and the layout-dependent string length in *out_size. */
+int acb200_create_grid_device(const uint8_t *const *d_srcs, const size_t *sizes, int n, int width, int height,
+                              uint8_t *d_out, size_t *out_size, void *stream);
+
+#pragma GCC visibility pop
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASCIICHAT_B200_H */

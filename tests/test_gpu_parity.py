@@ -1,0 +1,253 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle.
+
+Checker = the compiled reference (oracle/_ref) when its .so travelled with the snapshot, else the pinned
+port.  Bar: byte-for-byte equality of every frame string (the path is all-integer; no tolerance).
+"""
+import ctypes as C
+import itertools
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LEVELS = (0, 1, 2, 3)
+MODES = (0, 1, 2)
+
+
+@pytest.fixture(scope="module")
+def acb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import ascii_chat_b200 as m
+    assert m.lib().acb200_init(0) == 0, m.last_error()
+    return m
+
+
+@pytest.fixture(scope="module")
+def want(ob):
+    """oracle convert: compiled reference if present, else the port"""
+    if ob.ref() is not None:
+        return ob.ref_convert
+    return ob.port_convert
+
+
+def _conv(acb, img, c, r, level, mode, pal="standard", aspect=False, stretch=False, pad=False):
+    return acb.ascii_convert_with_capabilities(img, c, r, acb.make_caps(level, mode, pad), aspect, stretch, pal)
+
+
+# ---------------------------------------------------------------- drop-in calls, NN (reference-exact) mode
+def test_matrix_vs_oracle(acb, ob, want):
+    shapes = [(64, 48, 16, 8), (100, 37, 33, 11), (17, 9, 5, 3), (320, 240, 80, 24), (8, 2, 8, 2), (31, 64, 40, 20)]
+    n = 0
+    for pat, (W, H, c, r) in itertools.product(("noise", "gradient", "bars", "grey", "solid"), shapes):
+        img = ob.gen(pat, W, H, 3)
+        for level, mode, pal in itertools.product(LEVELS, MODES, ("standard", "blocks", "digital", "minimal")):
+            for aspect, pad in ((False, False), (True, True), (True, False)):
+                got = _conv(acb, img, c, r, level, mode, pal, aspect, False, pad)
+                exp = want(img, c, r, level, mode, pal, aspect, False, pad)
+                assert got == exp, (pat, W, H, c, r, level, mode, pal, aspect, pad)
+                n += 1
+    assert n > 3000
+
+
+def test_golden_fingerprints(acb, ob, golden):
+    """committed fingerprints of the compiled reference, incl. the BASELINE configs C1/C2/C3 at full size"""
+    for rec in golden["frames"]:
+        img = ob.gen(rec["pattern"], rec["W"], rec["H"], 0)
+        s = _conv(acb, img, rec["cols"], rec["rows"], rec["level"], rec["mode"], rec["palette"], bool(rec["aspect"]),
+                  False, bool(rec["pad"]))
+        assert s is not None, (rec, acb.last_error())
+        assert (len(s), s.count(b"\n"), "%08x" % ob.fnv(s)) == (rec["bytes"], rec["newlines"], rec["fnv"]), rec
+
+
+def test_low_entropy_images(acb, ob):
+    """long runs, black holes, near-grey colours, stripes: the REP / reset / SGR-dedupe rules"""
+    rng = np.random.default_rng(7)
+    chk = ob.ref_print if ob.ref() is not None else ob.port_print
+    for it in range(60):
+        w, h = int(rng.integers(1, 70)), int(rng.integers(1, 40))
+        kind = it % 4
+        if kind == 0:
+            img = rng.integers(0, 2, (h, w, 1), dtype=np.uint8).repeat(3, axis=2) * 255
+        elif kind == 1:
+            img = (rng.integers(0, 3, (h, w, 3)) * 20).astype(np.uint8)
+        elif kind == 2:
+            img = np.repeat(rng.integers(0, 256, (h, (w + 6) // 7, 3), dtype=np.uint8), 7, axis=1)[:, :w]
+        else:
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            img[rng.random((h, w)) < 0.4] = 0
+        for level, mode, pal in itertools.product(LEVELS, MODES, ("standard", "cool")):
+            got = acb.image_print_with_capabilities(img, acb.make_caps(level, mode), pal)
+            assert got == chk(img, level, mode, pal), (it, w, h, level, mode, pal)
+
+
+def test_wide_rows(acb, ob, want):
+    """rows wider than one CTA pass (multi-segment scans) and wider than the shared staging buffer"""
+    for W, c, r in ((1400, 700, 3), (3840, 1500, 2), (2000, 2000, 2), (3840, 3840, 1)):
+        img = ob.gen("noise", W, 16, 1)
+        img[:, W // 3: W // 2] = 0
+        img[:, : W // 8] = (9, 200, 30)
+        for level, mode in itertools.product(LEVELS, (0, 2)):
+            assert _conv(acb, img, c, r, level, mode) == want(img, c, r, level, mode), (W, c, r, level, mode)
+
+
+def test_legacy_ascii_convert(acb, ob):
+    img = ob.gen("noise", 120, 90, 1)
+    chk = ob.ref_convert_legacy if ob.ref() is not None else ob.port_convert_legacy
+    for color, aspect, stretch, opt in itertools.product((False, True), (False, True), (False, True), MODES):
+        acb.lib().acb200_set_option_render_mode(opt)
+        got = acb.ascii_convert(img, 40, 20, color, aspect, stretch, "standard")
+        acb.lib().acb200_set_option_render_mode(0)
+        assert got == chk(img, 40, 20, color, aspect, stretch, "standard", opt), (color, aspect, stretch, opt)
+
+
+def test_image_resize(acb, ob):
+    rng = np.random.default_rng(3)
+    chk = ob.ref_resize if ob.ref() is not None else ob.port_resize
+    for _ in range(25):
+        sw, sh, dw, dh = (int(rng.integers(1, 300)) for _ in range(4))
+        src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(acb.image_resize(src, dw, dh), chk(src, dw, dh)), (sw, sh, dw, dh)
+
+
+def test_error_behaviour(acb):
+    """NULL / invalid arguments: NULL result + ERROR_INVALID_PARAM, as ascii.c:198-212, 256-265"""
+    caps = acb.make_caps(3, 0)
+    img = np.zeros((4, 4, 3), np.uint8)
+    L = acb.lib()
+    assert L.ascii_convert_with_capabilities(None, 4, 4, C.byref(caps), False, False, b"ab") is None
+    assert acb.last_error()[0] == 86
+    assert acb.ascii_convert_with_capabilities(img, 0, 4, caps, False, False, "standard") is None
+    assert acb.last_error()[0] == 86
+    assert acb.ascii_convert_with_capabilities(img, 4000, 4, caps, False, False, "standard") is None  # > IMAGE_MAX_WIDTH
+    assert acb.ascii_convert_with_capabilities(img, 4, 4, caps, False, False, None) is None
+    assert acb.ascii_convert_with_capabilities(img, 4, 4, caps, False, False, "") is None  # empty palette (common.c:275)
+    assert acb.ascii_convert(img, 4, 4, True, False, False, "") is None
+    # a healthy call still works afterwards
+    assert acb.ascii_convert_with_capabilities(img, 4, 4, caps, False, False, "standard") is not None
+
+
+def test_concurrent_callers(acb, ob, want):
+    """one render thread per client (src/server/render.c:340): per-thread streams, shared LUT cache"""
+    imgs = [ob.gen("noise", 160, 120, i) for i in range(8)]
+    exp = [want(im, 40, 15, 3, 2) for im in imgs]
+    errs = []
+
+    def worker(i):
+        for _ in range(20):
+            if _conv(acb, imgs[i], 40, 15, 3, 2) != exp[i]:
+                errs.append(i)
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+
+
+# ---------------------------------------------------------------- box-filter mode (our spec; oracle = CPU box + oracle print)
+def test_box_mode_vs_oracle(acb, ob):
+    cases = [(640, 480, 80, 24), (320, 240, 64, 20), (333, 127, 47, 13), (64, 64, 64, 32), (1920, 1080, 160, 48),
+             (100, 50, 130, 70), (48, 2000, 7, 5)]  # streaming path, generic path, upscale, tall bands
+    for (W, H, c, r), pat in itertools.product(cases, ("noise", "bars")):
+        img = ob.gen(pat, W, H, 2)
+        for level, mode in ((0, 0), (2, 0), (3, 0), (3, 2), (1, 2), (0, 2), (2, 2), (3, 1)):
+            rows_px = r * 2 if mode == 2 else r
+            cfg = acb.make_cfg(W, H, c, rows_px, level, mode, "standard", scale=acb.SCALE_BOX)
+            got = acb.render_batch_host(cfg, [img])[0]
+            exp = ob.port_convert(img, c, r, level, mode, "standard", scale=ob.SCALE_BOX)
+            assert got == exp, (W, H, c, r, pat, level, mode)
+
+
+# ---------------------------------------------------------------- batch API on resident frames
+def _device_batch(acb, frames, cfg):
+    import torch
+    n = len(frames)
+    d_in = torch.from_numpy(np.stack(frames)).cuda()
+    cap = acb.frame_capacity(cfg)
+    d_out = torch.empty(n * cap, dtype=torch.uint8, device="cuda")
+    d_len = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_scr = torch.empty(acb.scratch_bytes(cfg, n), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    acb.render_batch_device(cfg, d_in.data_ptr(), n, d_out.data_ptr(), cap, d_len.data_ptr(), d_scr.data_ptr(), None)
+    tot, ker = acb.time_batch_device(cfg, d_in.data_ptr(), n, d_out.data_ptr(), cap, d_len.data_ptr(),
+                                     d_scr.data_ptr(), 1)
+    assert tot > 0 and ker > 0 and ker <= tot * 1.05
+    lens = d_len.cpu().numpy()
+    out = d_out.cpu().numpy().reshape(n, cap)
+    res = []
+    for i in range(n):
+        assert out[i, lens[i]] == 0  # NUL terminated
+        res.append(out[i, : lens[i]].tobytes())
+    return res
+
+
+def test_batch_device_matches_oracle(acb, ob, want):
+    frames = [ob.gen(("noise", "bars", "gradient")[i % 3], 320, 240, i) for i in range(7)]
+    for level, mode in ((0, 0), (2, 0), (3, 0), (3, 2), (3, 1)):
+        cfg = acb.make_cfg(320, 240, 80, 48 if mode == 2 else 24, level, mode)
+        res = _device_batch(acb, frames, cfg)
+        for i, f in enumerate(frames):
+            assert res[i] == want(f, 80, 24, level, mode), (level, mode, i)
+
+
+def test_full_size_batches_properties(acb, ob):
+    """BASELINE shapes at full size: every frame of a resident batch equals its own single-frame render (both
+    scalers), strings are NUL-free, have exactly rows-1 newlines, and each text row covers exactly `cols` cells
+    once REP sequences are expanded (the consumer-side codec, lib/video/ascii/rle.c)."""
+    import re
+    for (W, H, c, r, level, mode) in ((1920, 1080, 160, 48, 2, 0), (3840, 2160, 320, 96, 3, 2)):
+        frames = [ob.gen("noise" if i % 2 else "bars", W, H, i) for i in range(4)]
+        for scale in (acb.SCALE_NN, acb.SCALE_BOX):
+            cfg = acb.make_cfg(W, H, c, r * 2 if mode == 2 else r, level, mode, scale=scale)
+            res = _device_batch(acb, frames, cfg)
+            single = acb.render_batch_host(cfg, frames)
+            for i in range(len(frames)):
+                assert res[i] == single[i]
+                assert b"\0" not in res[i] and res[i].count(b"\n") == r - 1
+                exp = ob.port_convert(frames[i], c, r, level, mode, scale=scale)
+                assert res[i] == exp
+                for line in res[i].split(b"\n"):
+                    txt = line.decode("utf-8")
+                    txt = re.sub("(.)\x1b\\[(\\d+)b", lambda m: m.group(1) * (int(m.group(2)) + 1), txt)
+                    txt = re.sub("\x1b\\[[0-9;]*m", "", txt)
+                    assert len(txt) == c
+
+
+# ---------------------------------------------------------------- grid compositors
+def test_text_grid(acb, ob):
+    rng = np.random.default_rng(11)
+    chk = ob.ref_create_grid if ob.ref() is not None else ob.port_create_grid
+    for it in range(40):
+        n = int(rng.integers(1, 10))
+        level, mode = int(rng.integers(0, 4)), int(rng.choice([0, 2]))
+        cols, rows = int(rng.integers(8, 50)), int(rng.integers(3, 16))
+        srcs = [ob.port_convert(ob.gen(("noise", "bars", "gradient")[i % 3], 96, 64, i), cols, rows, level, mode)
+                for i in range(n)]
+        W, H = int(rng.integers(10, 200)), int(rng.integers(3, 60))
+        assert acb.ascii_create_grid(srcs, W, H) == chk(srcs, W, H), (it, n, W, H)
+
+
+def test_text_grid_golden(acb, ob, golden):
+    for rec in golden["text_grids"]:
+        srcs = [ob.port_convert(ob.gen("noise" if i % 2 else "bars", 160, 120, i), rec["cols"], rec["rows"],
+                                rec["level"], rec["mode"]) for i in range(rec["n"])]
+        g, sz = acb.ascii_create_grid(srcs, rec["W"], rec["H"])
+        assert (sz, "%08x" % ob.fnv(g)) == (rec["size"], rec["fnv"]), rec
+
+
+def test_pixel_composite(acb, ob):
+    """server grid: create_multi_source_composite (stream.c:664-779) then the viewer's convert (stream.c:841)"""
+    rng = np.random.default_rng(5)
+    for it in range(12):
+        n = int(rng.integers(1, 10))
+        srcs = [ob.gen(("noise", "bars", "gradient")[i % 3], int(rng.integers(40, 400)), int(rng.integers(30, 300)), i)
+                for i in range(n)]
+        W, H = int(rng.integers(40, 200)), int(rng.integers(20, 60))
+        got, gc, gr = acb.composite(srcs, W, H)
+        exp, ec, er = ob.port_composite(srcs, W, H)
+        assert (gc, gr) == (ec, er) and np.array_equal(got, exp), (it, n, W, H)
+        caps = acb.make_caps(3, 2, True)
+        a = acb.ascii_convert_with_capabilities(got, W, H * 2, caps, True, False, "standard")
+        assert a == ob.port_convert(exp, W, H * 2, 3, 2, "standard", True, False, True)
