@@ -260,15 +260,15 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
   const int kmode = pl.mode == EM_DITHER_BG ? (int)EM_256_FG : pl.mode;
   pl.use_smem_out = pl.row_pitch <= (uint32_t)kSmemOutMax;
   size_t sm = rows_smem_total(kmode, sp, cfg.cols, cfg.src_w, pl.use_smem_out ? pl.row_pitch : 0);
-  if (sm > 227u * 1024u && sp == SP_BOX_STREAM) {
+  if (sm > kMaxDynSmem && sp == SP_BOX_STREAM) {
     sp = SP_BOX_GENERIC;
     sm = rows_smem_total(kmode, sp, cfg.cols, cfg.src_w, pl.use_smem_out ? pl.row_pitch : 0);
   }
-  if (sm > 227u * 1024u && pl.use_smem_out) {
+  if (sm > kMaxDynSmem && pl.use_smem_out) {
     pl.use_smem_out = 0;
     sm = rows_smem_total(kmode, sp, cfg.cols, cfg.src_w, 0);
   }
-  if (sm > 227u * 1024u) {
+  if (sm > kMaxDynSmem) {
     set_error(E_INVALID_PARAM, "row of %d cells does not fit shared memory", cfg.cols);
     return false;
   }

@@ -785,11 +785,12 @@ __global__ void __launch_bounds__(256) k_dither_bg(const uint8_t *cells, int w, 
 template <int MODE, int SP> static cudaError_t launch_rows_t(const RenderParams &p, cudaStream_t st) {
   const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
   const Layout L = make_layout(MODE, SP, p.cols, p.src_w, cap);
-  if (L.total > 227u * 1024u) return cudaErrorInvalidConfiguration;
+  if (L.total > kMaxDynSmem) return cudaErrorInvalidConfiguration;
   static bool configured = false; // benign race: the attribute is idempotent
   if (!configured) {
+    // opt-in limit is 227 KB per CTA for static + dynamic together; the kernel has < 1 KB static
     cudaError_t e = cudaFuncSetAttribute(k_render_rows<MODE, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+                                         (int)kMaxDynSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
