@@ -84,7 +84,7 @@ bool grow_pinned(uint8_t **p, size_t *cap, size_t need) {
   if (*p) cudaFreeHost(*p);
   *p = nullptr;
   *cap = 0;
-  if (cudaHostAlloc((void **)p, n, cudaHostAllocDefault) != cudaSuccess) {
+  if (cudaHostAlloc((void **)p, n, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
     set_error(E_MEMORY, "cudaHostAlloc(%zu) failed", n);
     return false;
   }
@@ -105,37 +105,64 @@ bool grow_device(uint8_t **p, size_t *cap, size_t need) {
   return true;
 }
 
-struct CtxHolder {
-  ThreadCtx c;
-  bool ok = false;
-  ~CtxHolder() {
-    if (!ok) return;
-    // thread exit: release this thread's stream and staging (errors ignored: the context may be gone)
-    if (c.h_in) cudaFreeHost(c.h_in);
-    if (c.h_out) cudaFreeHost(c.h_out);
-    if (c.h_len) cudaFreeHost(c.h_len);
-    if (c.d_in) cudaFree(c.d_in);
-    if (c.d_out) cudaFree(c.d_out);
-    if (c.d_scratch) cudaFree(c.d_scratch);
-    if (c.d_len) cudaFree(c.d_len);
-    for (auto &e : c.ev)
-      if (e) cudaEventDestroy(e);
-    if (c.stream) cudaStreamDestroy(c.stream);
+// Streams and pinned staging are expensive to create (cudaHostAlloc is a multi-millisecond call), while the
+// reference's callers are threads that come and go with clients.  A thread leases a context on first use and
+// hands it back to a process-wide pool when it exits; a new thread picks up a warm one.
+static std::mutex g_pool_mu;
+static std::vector<ThreadCtx *> g_pool;
+
+struct CtxLease {
+  ThreadCtx *c = nullptr;
+  ~CtxLease() {
+    if (!c) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool.push_back(c);
   }
 };
 
 ThreadCtx *thread_ctx() {
-  static thread_local CtxHolder h;
-  if (h.ok) return &h.c;
+  static thread_local CtxLease lease;
+  if (lease.c) return lease.c;
   if (ensure_device() != 0) return nullptr;
-  if (cudaSetDevice(g_device) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h.c.stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaSetDevice(g_device) != cudaSuccess) {
+    set_error(E_INVALID_STATE, "cudaSetDevice(%d) failed", g_device);
+    return nullptr;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_pool.empty()) {
+      lease.c = g_pool.back();
+      g_pool.pop_back();
+      return lease.c;
+    }
+  }
+  ThreadCtx *c = new ThreadCtx();
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
     set_error(E_INVALID_STATE, "cannot create CUDA stream");
     return nullptr;
   }
-  for (auto &e : h.c.ev) cudaEventCreate(&e);
-  h.ok = true;
-  return &h.c;
+  for (auto &e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDefault);
+  lease.c = c;
+  return c;
+}
+
+static void destroy_ctx_pool() { // acb200_shutdown: contexts still leased by live threads stay with them
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (ThreadCtx *c : g_pool) {
+    if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_len) cudaFreeHost(c->h_len);
+    if (c->d_in) cudaFree(c->d_in);
+    if (c->d_out) cudaFree(c->d_out);
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->d_len) cudaFree(c->d_len);
+    for (auto &e : c->ev)
+      if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+  }
+  g_pool.clear();
 }
 
 // ------------------------------------------------------------------ glyph LUTs
@@ -374,67 +401,80 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
   // the box filter reads every row.
   const bool gather = cfg.scale == ACB200_SCALE_NN && cfg.rows_px < cfg.src_h;
   const size_t in_per_frame = gather ? R * cfg.rows_px : R * cfg.src_h;
-  int chunk = (int)((size_t)(96u << 20) / (in_per_frame + pl.frame_capacity + 1));
+  const size_t cap = pl.frame_capacity;
+  int chunk = (int)((size_t)(64u << 20) / (in_per_frame + cap));
   if (chunk < 1) chunk = 1;
   if (chunk > n_frames) chunk = n_frames;
-  if (!grow_device(&cx->d_in, &cx->d_in_cap, in_per_frame * chunk) ||
-      !grow_device(&cx->d_out, &cx->d_out_cap, pl.frame_capacity * chunk) ||
-      !grow_device(&cx->d_scratch, &cx->d_scratch_cap, scratch_bytes(pl, chunk)) ||
-      !grow_device((uint8_t **)&cx->d_len, &cx->d_len_cap, sizeof(uint32_t) * chunk) ||
-      !grow_pinned((uint8_t **)&cx->h_len, &cx->h_len_cap, sizeof(uint32_t) * chunk))
-    return t_err;
+  const int nchunks = (n_frames + chunk - 1) / chunk;
+  const int nslot = nchunks > 1 ? 2 : 1; // two slots: the host drains chunk k-1 while the GPU works on chunk k
+  const size_t in_slot = al256(in_per_frame * chunk), out_slot = al256(cap * chunk), len_slot = al256(4u * chunk);
   for (int i = 0; i < n_frames; i++) out[i] = nullptr;
   bool need_stage = gather;
   for (int i = 0; i < n_frames && !need_stage; i++) need_stage = frames[i] && !is_pinned(frames[i]);
-  if (need_stage && !grow_pinned(&cx->h_in, &cx->h_in_cap, in_per_frame * chunk)) return t_err;
+  if (!grow_device(&cx->d_in, &cx->d_in_cap, in_slot * nslot) ||
+      !grow_device(&cx->d_scratch, &cx->d_scratch_cap, scratch_bytes(pl, chunk)) ||
+      !grow_pinned(&cx->h_out, &cx->h_out_cap, out_slot * nslot) ||
+      !grow_pinned((uint8_t **)&cx->h_len, &cx->h_len_cap, len_slot * nslot) ||
+      (need_stage && !grow_pinned(&cx->h_in, &cx->h_in_cap, in_slot * nslot)))
+    return t_err;
 
-  for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+  // The stitch kernel writes the finished strings and their lengths straight into mapped pinned host memory
+  // (UVA: the host pointer is the device pointer), so a chunk costs one event wait, no D2H memcpy calls.
+  auto issue = [&](int k) -> int {
+    const int slot = k & 1, f0 = k * chunk;
     const int n = (n_frames - f0 < chunk) ? n_frames - f0 : chunk;
+    uint8_t *d_in = cx->d_in + (size_t)slot * in_slot;
+    uint8_t *st_base = need_stage ? cx->h_in + (size_t)slot * in_slot : nullptr;
     for (int i = 0; i < n; i++) {
       const uint8_t *src = frames[f0 + i];
       if (!src) return set_error(E_INVALID_PARAM, "frame %d is NULL", f0 + i);
-      uint8_t *dst = cx->d_in + (size_t)i * in_per_frame;
+      uint8_t *dst = d_in + (size_t)i * in_per_frame;
       if (gather) {
-        uint8_t *st = cx->h_in + (size_t)i * in_per_frame;
+        uint8_t *st = st_base + (size_t)i * in_per_frame;
         for (int y = 0; y < cfg.rows_px; y++)
           memcpy(st + (size_t)y * R, src + (size_t)nn_src_row(y, cfg.src_h, cfg.rows_px) * R, R);
         ACB_CUDA(cudaMemcpyAsync(dst, st, in_per_frame, cudaMemcpyHostToDevice, cx->stream));
       } else if (is_pinned(src)) {
         ACB_CUDA(cudaMemcpyAsync(dst, src, in_per_frame, cudaMemcpyHostToDevice, cx->stream));
       } else {
-        uint8_t *st = cx->h_in + (size_t)i * in_per_frame;
+        uint8_t *st = st_base + (size_t)i * in_per_frame;
         memcpy(st, src, in_per_frame);
         ACB_CUDA(cudaMemcpyAsync(dst, st, in_per_frame, cudaMemcpyHostToDevice, cx->stream));
       }
     }
-    int rc = render_device(cfg, pl, cx->d_in, in_per_frame, gather ? 1 : 0, n, cx->d_out, pl.frame_capacity, cx->d_len,
+    int rc = render_device(cfg, pl, d_in, in_per_frame, gather ? 1 : 0, n, cx->h_out + (size_t)slot * out_slot, cap,
+                           reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(cx->h_len) + (size_t)slot * len_slot),
                            cx->d_scratch, cx->stream);
     if (rc) return rc;
-    ACB_CUDA(cudaMemcpyAsync(cx->h_len, cx->d_len, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, cx->stream));
-    ACB_CUDA(cudaStreamSynchronize(cx->stream));
-    size_t tot = 0;
-    for (int i = 0; i < n; i++) tot += (size_t)cx->h_len[i] + 1;
-    if (!grow_pinned(&cx->h_out, &cx->h_out_cap, tot)) return t_err;
-    size_t o = 0;
+    ACB_CUDA(cudaEventRecord(cx->ev[2 + slot], cx->stream));
+    return E_OK;
+  };
+  auto collect = [&](int k) -> int {
+    const int slot = k & 1, f0 = k * chunk;
+    const int n = (n_frames - f0 < chunk) ? n_frames - f0 : chunk;
+    ACB_CUDA(cudaEventSynchronize(cx->ev[2 + slot]));
+    const uint32_t *lens =
+        reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(cx->h_len) + (size_t)slot * len_slot);
+    const uint8_t *arena = cx->h_out + (size_t)slot * out_slot;
     for (int i = 0; i < n; i++) {
-      ACB_CUDA(cudaMemcpyAsync(cx->h_out + o, cx->d_out + (size_t)i * pl.frame_capacity, (size_t)cx->h_len[i] + 1,
-                               cudaMemcpyDeviceToHost, cx->stream));
-      o += (size_t)cx->h_len[i] + 1;
-    }
-    ACB_CUDA(cudaStreamSynchronize(cx->stream));
-    o = 0;
-    for (int i = 0; i < n; i++) {
-      const size_t len = cx->h_len[i];
-      char *s = (char *)user_alloc(len + 1);
-      if (!s) return set_error(E_MEMORY, "allocator returned NULL for %zu bytes", len + 1);
-      memcpy(s, cx->h_out + o, len + 1);
-      s[len] = '\0';
-      out[f0 + i] = s;
+      const size_t len = lens[i];
+      char *sp = (char *)user_alloc(len + 1);
+      if (!sp) return set_error(E_MEMORY, "allocator returned NULL for %zu bytes", len + 1);
+      memcpy(sp, arena + (size_t)i * cap, len);
+      sp[len] = '\0';
+      out[f0 + i] = sp;
       if (out_len) out_len[f0 + i] = len;
-      o += len + 1;
     }
+    return E_OK;
+  };
+  int rc = E_OK;
+  for (int k = 0; k < nchunks && rc == E_OK; k++) {
+    rc = issue(k);
+    if (rc == E_OK && k >= 1) rc = collect(k - 1);
   }
-  return E_OK;
+  if (rc == E_OK) rc = collect(nchunks - 1);
+  if (rc != E_OK) cudaStreamSynchronize(cx->stream); // leave no work in flight that targets our staging
+  return rc;
 }
 
 char *render_one_host(const acb200_render_cfg_t &cfg, const uint8_t *rgb, size_t *out_len) {
@@ -461,7 +501,10 @@ int acb200_init(int device) {
   if (ensure_device() != 0) return t_err ? t_err : E_INVALID_STATE;
   return thread_ctx() ? E_OK : t_err;
 }
-void acb200_shutdown(void) { destroy_lut_cache(); }
+void acb200_shutdown(void) {
+  destroy_lut_cache();
+  destroy_ctx_pool();
+}
 int acb200_last_error(void) {
   int e = t_err;
   t_err = 0;

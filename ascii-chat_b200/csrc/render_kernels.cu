@@ -21,6 +21,7 @@ namespace acb {
 constexpr int BLOCK = 256;
 constexpr int NWARP = BLOCK / 32;
 constexpr uint16_t NONE16 = 0xFFFF;
+constexpr int kBandUnroll = 12; // independent 16-byte loads in flight per thread in the streaming box filter
 
 // ------------------------------------------------------------------ small integer helpers
 __device__ __forceinline__ int luma_of(uint32_t c) { // foreground.c:93  (77R+150G+29B+128)>>8
@@ -325,19 +326,20 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
   for (int c = threadIdx.x; c < nchunk; c += BLOCK) {
     uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const uint4 *q = band + c;
-    int r = 0;
-    for (; r + 8 <= nrow; r += 8) {
-      uint4 v[8];
+    // One batch of kBandUnroll independent, predicated 16-byte loads per trip: a typical band (11-12 rows at
+    // 4K -> 192 pixel rows) is a single trip, i.e. one memory latency per column instead of one per tail row.
+    for (int r = 0; r < nrow; r += kBandUnroll) {
+      uint4 v[kBandUnroll];
 #pragma unroll
-      for (int k = 0; k < 8; k++) v[k] = ldg_stream(q + (size_t)k * nchunk);
-      q += (size_t)8 * nchunk;
+      for (int k = 0; k < kBandUnroll; k++) {
+        if (r + k < nrow)
+          v[k] = ldg_stream(q + (size_t)k * nchunk);
+        else
+          v[k] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      q += (size_t)kBandUnroll * nchunk;
 #pragma unroll
-      for (int k = 0; k < 8; k++) acc16(a, v[k]);
-    }
-    for (; r < nrow; r++) {
-      uint4 v = ldg_stream(q);
-      q += nchunk;
-      acc16(a, v);
+      for (int k = 0; k < kBandUnroll; k++) acc16(a, v[k]);
     }
     // byte j of word k is column 16c + 4k + j:  even reg = {b0 | b2<<16}, odd reg = {b1 | b3<<16}
     uint4 lo, hi;
@@ -627,37 +629,78 @@ template <int MODE, int SP> __global__ void __launch_bounds__(BLOCK) k_render_ro
 }
 
 // ------------------------------------------------------------------ stitch rows -> frame string
+// Block-cooperative copy of n bytes for any mutual alignment: destination-aligned 4-byte stores assembled from
+// two source-aligned words with one byte permute (the scratch rows keep >= 16 bytes of slack, so reading one
+// word past the range stays inside the row).
+__device__ __forceinline__ void copy_shifted(uint8_t *dst, const uint8_t *src, uint32_t n) {
+  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
+  if (head > n) head = n;
+  if (tid < head) dst[tid] = src[tid];
+  dst += head;
+  src += head;
+  n -= head;
+  const uint32_t nw = n >> 2;
+  const uint32_t r = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+  const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - r);
+  const uint32_t sel = 0x3210u + 0x1111u * r;
+  uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
+  for (uint32_t j = tid; j < nw; j += nt) dw[j] = __byte_perm(sw[j], sw[j + 1], sel);
+  const uint32_t tail = n & 3u;
+  if (tid < tail) dst[4u * nw + tid] = src[4u * nw + tid];
+}
+
 __global__ void __launch_bounds__(256) k_stitch(const StitchParams p) {
+  constexpr int CH = 256; // rows of metadata staged per pass
+  __shared__ uint32_t s_len[CH], s_cl[CH], s_first[CH], s_last[CH];
   __shared__ uint32_t s_off[64], s_drop[64];
-  __shared__ uint32_t s_total;
+  __shared__ uint32_t s_total, s_o, s_carry;
   const int groups = (p.text_rows + p.rows_per_cta - 1) / p.rows_per_cta;
   const int f = (int)(blockIdx.x / (unsigned)groups);
   const int g = (int)(blockIdx.x % (unsigned)groups);
   const int r0 = g * p.rows_per_cta;
   const int r1 = min(r0 + p.rows_per_cta, p.text_rows);
   const RowMeta *meta = p.meta + (size_t)f * p.text_rows;
+  const bool tf = p.mode == EM_TRUE_FG;
+  const int upto = (g == groups - 1) ? p.text_rows : r1;
   if (threadIdx.x == 0) {
-    // serial prefix over the rows above this group (row counts are tens to a few thousand)
-    uint32_t o = (uint32_t)p.pad_top, carry = 0;
-    const bool tf = p.mode == EM_TRUE_FG;
-    const int upto = (g == groups - 1) ? p.text_rows : r1;
-    for (int r = 0; r < upto; r++) {
-      const RowMeta m = meta[r];
-      uint32_t drop = 0;
-      if (tf) {
-        // ansi_rle_add_pixel state across rows: the first ASCII cell of a row re-emits its SGR only if its
-        // colour differs from the last ASCII cell seen anywhere above (ansi.c:263)
-        if (m.cond_len && carry && m.first_rgb == carry) drop = m.cond_len;
-        if (m.last_rgb) carry = m.last_rgb;
-      }
-      if (r >= r0 && r < r1) {
-        s_off[r - r0] = o;
-        s_drop[r - r0] = drop;
-      }
-      o += m.len - drop;
-    }
-    s_total = o;
+    s_o = (uint32_t)p.pad_top;
+    s_carry = 0;
   }
+  for (int base = 0; base < upto; base += CH) {
+    const int nrows = min(CH, upto - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nrows; i += blockDim.x) { // parallel fetch, 16 bytes of each 32-byte record
+      const uint4 m = *reinterpret_cast<const uint4 *>(&meta[base + i]);
+      s_len[i] = m.x;
+      s_cl[i] = m.z;
+      s_first[i] = m.w;
+      s_last[i] = tf ? meta[base + i].last_rgb : 0u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t o = s_o, carry = s_carry;
+      for (int i = 0; i < nrows; i++) {
+        uint32_t drop = 0;
+        if (tf) {
+          // ansi_rle_add_pixel state across rows: the first ASCII cell of a row re-emits its SGR only if its
+          // colour differs from the last ASCII cell seen anywhere above (ansi.c:263)
+          if (s_cl[i] && carry && s_first[i] == carry) drop = s_cl[i];
+          if (s_last[i]) carry = s_last[i];
+        }
+        const int r = base + i;
+        if (r >= r0 && r < r1) {
+          s_off[r - r0] = o;
+          s_drop[r - r0] = drop;
+        }
+        o += s_len[i] - drop;
+      }
+      s_o = o;
+      s_carry = carry;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_total = s_o;
   __syncthreads();
   uint8_t *out = p.out + (size_t)f * p.out_pitch;
   if (g == 0)
@@ -672,8 +715,8 @@ __global__ void __launch_bounds__(256) k_stitch(const StitchParams p) {
     uint8_t *dst = out + s_off[r - r0];
     const uint32_t drop = s_drop[r - r0];
     const uint32_t a = drop ? m.cond_off : m.len; // [0,a) then [a+drop, len)
-    for (uint32_t i = threadIdx.x; i < a; i += blockDim.x) dst[i] = src[i];
-    for (uint32_t i = a + drop + threadIdx.x; i < m.len; i += blockDim.x) dst[i - drop] = src[i];
+    copy_shifted(dst, src, a);
+    if (drop) copy_shifted(dst + a, src + a + drop, m.len - a - drop);
   }
 }
 

@@ -6,12 +6,15 @@ with the reference's CPU path timed on the same box.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU)
 
-Workload (config.workload): BASELINE configs[2]/[4] — 3840x2160 RGB24 -> 320x96 truecolor half-block cells,
-box-filter downscale (every source pixel read once: 3 B/px algorithmic), a ring of 256 distinct frames
-resident in HBM (6.37 GB per pass >> 126 MB L2, so no L2 flush is needed between iterations).
-A step = one pass of the render path over the 256-frame batch.  Frames are independent, so ranks take
-disjoint rings with no data-path collective ("scaling": "weak").
-
+Workload (config.workload): BASELINE configs[2]/[4] — 3840x2160 RGB24 -> 320x96 truecolor half-block cells.
+  value     resident path: box-filter downscale (every source pixel read once: 3 B/px algorithmic), a ring of 256
+            distinct frames per GPU already in HBM (6.37 GB per pass >> 126 MB L2, so no L2 flush is needed).
+            A step = one pass of the render path over the 256-frame batch, device-timed with CUDA events.
+  e2e       the reference-facing call ascii_convert_with_capabilities() (reference-exact nearest-neighbour mode:
+            same bytes as the reference) from HOST frames, driven by the same neutral pthread harness as the
+            reference arm (bench_harness/caller_threads.c: one caller thread per client, like src/server/render.c).
+  e2e_box   same call with the library's downscale switched to the box filter: full frames cross PCIe.
+Frames are independent, so ranks take disjoint rings with no data-path collective ("scaling": "weak").
 One JSON line is printed by rank 0.  See DESIGN.md §6 for what each field means.
 """
 import argparse
@@ -29,9 +32,11 @@ sys.path.insert(0, ROOT)
 SRC_W, SRC_H, COLS, ROWS = 3840, 2160, 320, 96
 LEVEL, MODE = 3, 2  # truecolor, half-block
 RING = 256
+HOST_RING = 16
 FRAME_BYTES = SRC_W * SRC_H * 3
 MPIX = SRC_W * SRC_H / 1e6
 METRIC = "Mpixels/s fused RGB->glyph render at 4K"
+PALETTE = b"   ...',;:clodxkO0KXNWM"
 
 
 def peaks():
@@ -49,7 +54,7 @@ def traffic_from_profiles():
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("render_rows_4k_hb_box_bytes_per_launch")
+            return json.load(open(p)).get("render_rows_4k_hb_box_bytes_per_256_frame_launch")
         except Exception:
             return None
     return None
@@ -68,16 +73,17 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.3)  # let the sampler come up before the timed region starts
         except Exception:
             self.proc = None
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
+        time.sleep(0.1)
+        self.proc.terminate()  # the exact PID we started
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
@@ -100,34 +106,69 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_leg(threads, seconds_target=12.0):
-    """The reference's own CPU implementation of the path (oracle/_ref, else the pinned port), frame-parallel
-    over `threads` host threads like the reference's one-render-thread-per-client model, on the same 4K ->
-    320x96 truecolor half-block call.  Returns (Mpix/s nominal, kind, cores, sample description, seconds)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import numpy as np
-    import oracle_bind as ob
-    ring = 8
-    frames = np.stack([ob.gen("noise", SRC_W, SRC_H, i) for i in range(ring)])
-    u8p = C.POINTER(C.c_uint8)
-    R = ob.ref()
-    caps = ob.make_caps(LEVEL, MODE)
-    fn = C.cast(R.ascii_convert_with_capabilities, C.c_void_p) if R is not None else None
-    kind = "reference" if R is not None else "port"
-    pal = ob.PALETTES["standard"].encode()
-    nbytes = C.c_uint64(0)
+# ------------------------------------------------------------------------------------------- shared harness
+def load_harness():
+    so = os.path.join(ROOT, "bench_harness", "libcaller_threads.so")
+    src = os.path.join(ROOT, "bench_harness", "caller_threads.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "bench_harness")], check=True, stdout=subprocess.DEVNULL)
+    H = C.CDLL(so)
+    H.harness_run.restype = C.c_double
+    H.harness_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_long, C.c_void_p,
+                              C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    H.harness_ring_fingerprint.restype = C.c_uint64
+    H.harness_ring_fingerprint.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_long,
+                                           C.c_void_p, C.c_char_p]
+    return H
 
-    def run(n):
-        return ob.port().orc_bench_convert(frames.ctypes.data_as(u8p), ring, SRC_W, SRC_H, COLS, ROWS, LEVEL, MODE,
-                                           pal, ob.SCALE_NN, n, threads, fn, C.byref(caps) if fn else None,
-                                           C.byref(nbytes))
-    run(threads * 2)  # warm tables / caches
-    t = run(threads * 4)
-    per = t / (threads * 4)
-    n = max(threads * 4, int(seconds_target / max(per, 1e-6)))
-    t = run(n)
-    return n * MPIX / t, kind, threads, "%d renders of a ring of %d LCG-noise 4K frames, %d threads, %.1f s" % (
-        n, ring, threads, t), t, n
+
+def host_ring(n=HOST_RING, seed=12345):
+    """deterministic uniform-noise RGB24 frames in ordinary (pageable) host memory, identical in both arms"""
+    import numpy as np
+    return np.random.default_rng(seed).integers(0, 256, (n, SRC_H, SRC_W, 3), dtype=np.uint8)
+
+
+def run_callers(H, fn_ptr, frames, caps, threads, seconds_target, warm_calls=None):
+    """calibrate, then time `calls` renders; returns dict(seconds, calls, bytes, failures)"""
+    ring = frames.shape[0]
+    nb, nf = C.c_uint64(0), C.c_uint64(0)
+
+    def run(calls):
+        return H.harness_run(fn_ptr, frames.ctypes.data, ring, SRC_W, SRC_H, COLS, ROWS, C.byref(caps), PALETTE, calls,
+                             threads, C.byref(nb), C.byref(nf))
+    w = warm_calls or threads * 2
+    run(w)
+    t = run(w)
+    calls = max(threads * 2, int(seconds_target / max(t / w, 1e-7)))
+    t = run(calls)
+    return {"seconds": t, "calls": calls, "bytes": nb.value, "failures": nf.value}
+
+
+def reference_entry():
+    """(fn pointer, caps struct, kind) of the reference's own CPU implementation: oracle/_ref, else the port shim"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_bind as ob
+    R = ob.ref()
+    if R is None:
+        return None, None, "port", ob
+    return C.cast(R.ascii_convert_with_capabilities, C.c_void_p), ob.make_caps(LEVEL, MODE), "reference", ob
+
+
+def cpu_reference_leg(H, frames, threads, seconds_target):
+    """The reference's own CPU path (its nearest-neighbour resize + half-block printer), frame-parallel over
+    `threads` caller threads.  Falls back to the pinned port only if oracle/_ref was never built."""
+    fn, caps, kind, ob = reference_entry()
+    if fn is None:  # port: time it through its own helper (kind = "port")
+        u8p = C.POINTER(C.c_uint8)
+        nb = C.c_uint64(0)
+        calls = max(threads * 4, 64)
+        t = ob.port().orc_bench_convert(frames.ctypes.data_as(u8p), frames.shape[0], SRC_W, SRC_H, COLS, ROWS, LEVEL,
+                                        MODE, PALETTE, ob.SCALE_NN, calls, threads, None, None, C.byref(nb))
+        return {"seconds": t, "calls": calls, "bytes": nb.value, "failures": 0}, kind, None
+    r = run_callers(H, fn, frames, caps, threads, seconds_target)
+    fp = H.harness_ring_fingerprint(fn, frames.ctypes.data, frames.shape[0], SRC_W, SRC_H, COLS, ROWS, C.byref(caps),
+                                    PALETTE)
+    return r, kind, fp
 
 
 def main():
@@ -137,7 +178,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ring", type=int, default=RING)
-    ap.add_argument("--e2e-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -155,30 +195,33 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        H = load_harness()
+        frames = host_ring()
         steps = max(1, args.steps)
-        per_step = max(4.0, min(20.0, 120.0 / (steps + args.warmup)))
-        vals = []
+        per_step = max(1.0, min(10.0, 100.0 / (steps + args.warmup)))
+        tot_s = tot_n = 0
+        kind = "reference"
         for i in range(args.warmup + steps):
-            v, kind, cores, sample, secs, n = cpu_reference_leg(ncores, seconds_target=per_step if i >= args.warmup else 2.0)
+            r, kind, _ = cpu_reference_leg(H, frames, ncores, per_step if i >= args.warmup else 0.5)
             if i >= args.warmup:
-                vals.append((v, secs, n))
-        tot_n = sum(x[2] for x in vals)
-        tot_s = sum(x[1] for x in vals)
+                tot_s += r["seconds"]
+                tot_n += r["calls"]
         value = tot_n * MPIX / tot_s
         cfg = dict(config)
-        cfg["downscale"] = "nearest-neighbour (the reference has no box filter; its own path samples 1 px per cell, " \
-                           "so Mpix/s is nominal = source pixels / time)"
+        cfg["downscale"] = ("nearest-neighbour: the reference has no box filter; its own path samples 1 px per cell, "
+                            "so its Mpix/s is nominal (source pixels / time)")
+        sample = "%d calls of ascii_convert_with_capabilities over a ring of %d uniform-noise 4K frames, %d caller " \
+                 "threads, %.1f s" % (tot_n, frames.shape[0], ncores, tot_s)
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": args.gpus,
                           "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / steps,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-                          "data": "synthetic (LCG noise RGB24)", "config": cfg,
-                          "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": kind,
+                          "data": "synthetic (uniform-noise RGB24)", "config": cfg,
+                          "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": ncores, "kind": kind,
                                            "sample": sample},
                           "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0,
                                   "d2h_bytes_per_step": 0}}))
         return
 
-    import numpy as np
     import torch
     import ascii_chat_b200 as acb
 
@@ -188,6 +231,19 @@ def main():
     torch.cuda.set_device(local_rank)
     assert acb.lib().acb200_init(local_rank) == 0, acb.last_error()
 
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor(x, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    # ---- resident (HBM -> HBM) throughput: device-timed with CUDA events on the launch stream
     n = args.ring
     cfg = acb.make_cfg(SRC_W, SRC_H, COLS, ROWS * 2, LEVEL, MODE, "standard", scale=acb.SCALE_BOX)
     cap = acb.frame_capacity(cfg)
@@ -198,72 +254,47 @@ def main():
     d_len = torch.empty(n, dtype=torch.int32, device="cuda")
     d_scr = torch.empty(acb.scratch_bytes(cfg, n), dtype=torch.uint8, device="cuda")
     targs = (cfg, d_in.data_ptr(), n, d_out.data_ptr(), cap, d_len.data_ptr(), d_scr.data_ptr())
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # ---- resident (HBM -> HBM) throughput: device-timed with CUDA events on the launch stream
     acb.time_batch_device(*targs, max(3, args.warmup))
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+    barrier()
     l0 = acb.launch_count()
     ms_total, ms_kernel = acb.time_batch_device(*targs, args.steps)
     launches = acb.launch_count() - l0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max, ms_kernel_max = float(t[0]), float(t[1])
+    ms_total_max, ms_kernel_max = max_over_ranks([ms_total, ms_kernel])
     out_bytes = int(d_len.sum().item())
+    del d_in, d_out, d_scr
+    torch.cuda.empty_cache()
 
-    # ---- end to end through the C ABI with HOST buffers (pinned), H2D + render + D2H + malloc'd strings
-    eb = max(1, min(args.e2e_batch, n))
-    h_in = torch.empty((eb, SRC_H, SRC_W, 3), dtype=torch.uint8, pin_memory=True)
-    h_in.copy_(d_in[:eb])
-    torch.cuda.synchronize()
-    ptrs = (C.c_void_p * eb)(*[h_in[i].data_ptr() for i in range(eb)])
-    outs = (C.c_void_p * eb)()
-    lens = (C.c_size_t * eb)()
-
-    def e2e_step():
-        rc = acb.render_batch_host_ptrs(cfg, ptrs, eb, outs, lens)
-        assert rc == 0, acb.last_error()
-        b = sum(lens[i] for i in range(eb))
-        acb.free_strings(outs, eb)
-        return b
-
-    for _ in range(max(1, args.warmup)):
-        e2e_step()
-    e2e_steps = max(3, min(args.steps, 10))
-    barrier()
-    t0 = time.perf_counter()
-    d2h = 0
-    for _ in range(e2e_steps):
-        d2h = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te[0])
-    e2e_val = world * e2e_steps * eb * MPIX / e2e_s
-
-    # ---- the drop-in call in its reference-exact (nearest-neighbour) mode, one frame per call, host buffers
+    # ---- end to end: the reference-facing call from host frames, T caller threads (one per "client")
+    H = load_harness()
+    frames = host_ring()
+    threads = max(4, min(32, ncores // max(1, world)))  # MAX_CLIENTS is 32 (include/ascii-chat/common/limits.h:26)
     caps = acb.make_caps(LEVEL, MODE)
-    fr0 = h_in[0].numpy()
-    for _ in range(3):
-        acb.ascii_convert_with_capabilities(fr0, COLS, ROWS, caps, False, False, "standard")
-    t0 = time.perf_counter()
-    nn_calls = 50
-    for i in range(nn_calls):
-        acb.ascii_convert_with_capabilities(h_in[i % eb].numpy(), COLS, ROWS, caps, False, False, "standard")
-    nn_s = time.perf_counter() - t0
+    fn = C.cast(acb.lib().ascii_convert_with_capabilities, C.c_void_p)
+    acb.lib().acb200_set_default_scale(acb.SCALE_NN)
+    barrier()
+    e_nn = run_callers(H, fn, frames, caps, threads, 4.0)
+    barrier()
+    fp_nn = H.harness_ring_fingerprint(fn, frames.ctypes.data, frames.shape[0], SRC_W, SRC_H, COLS, ROWS,
+                                       C.byref(caps), PALETTE)
+    acb.lib().acb200_set_default_scale(acb.SCALE_BOX)
+    barrier()
+    e_box = run_callers(H, fn, frames, caps, threads, 4.0)
+    barrier()
+    acb.lib().acb200_set_default_scale(acb.SCALE_NN)
+    nn_s, box_s = max_over_ranks([e_nn["seconds"], e_box["seconds"]])
+    calls_nn, calls_box = e_nn["calls"], e_box["calls"]  # same calibration on every rank is not guaranteed: sum them
+    tc = torch.tensor([calls_nn, calls_box, e_nn["failures"] + e_box["failures"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+    calls_nn_all, calls_box_all, failures = float(tc[0]), float(tc[1]), int(tc[2])
+
+    # single-caller latency of the drop-in call (what one render thread sees)
+    one = run_callers(H, fn, frames, caps, 1, 1.0, warm_calls=8)
 
     if rank != 0:
         if world > 1:
@@ -274,6 +305,7 @@ def main():
     alg_bytes_launch = n * FRAME_BYTES  # 3 B per source pixel, x frames per launch
     achieved = alg_bytes_launch / (ms_kernel_max / args.steps * 1e-3) / 1e9
     value = world * args.steps * n * MPIX / (ms_total_max * 1e-3)
+    gathered = ROWS * 2 * SRC_W * 3  # NN mode moves only the 192 sampled source rows per frame
     line = {
         "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
@@ -284,18 +316,29 @@ def main():
                      "algorithmic_bytes_per_launch": alg_bytes_launch,
                      "kernel_ms_per_launch": ms_kernel_max / args.steps,
                      "output_bytes_per_launch": out_bytes, "traffic": traffic_from_profiles()},
-        "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": eb * FRAME_BYTES,
-                "d2h_bytes_per_step": int(d2h) + 4 * eb, "frames_per_step": eb, "steps": e2e_steps,
-                "api": "acb200_render_batch_host (pinned host RGB24 in, malloc'd strings out), box-filter mode"},
-        "e2e_dropin_nn": {"value": nn_calls * MPIX / nn_s, "unit": "Mpix/s (nominal)", "ms_per_call": 1e3 * nn_s / nn_calls,
-                          "api": "ascii_convert_with_capabilities, one frame per call, reference-exact NN mode, "
-                                 "host image in, malloc'd string out"},
+        "e2e": {"value": calls_nn_all * MPIX / nn_s, "unit": "Mpix/s", "h2d_bytes_per_step": gathered,
+                "d2h_bytes_per_step": int(e_nn["bytes"] / max(1, e_nn["calls"])) + 4, "step": "one frame through the call",
+                "calls": int(calls_nn_all), "seconds": nn_s, "caller_threads_per_gpu": threads, "failures": failures,
+                "api": "ascii_convert_with_capabilities() — reference-exact nearest-neighbour mode, pageable host "
+                       "RGB24 in, malloc'd string out, same pthread harness as the reference arm",
+                "ring_fingerprint": "%016x" % fp_nn},
+        "e2e_box": {"value": calls_box_all * MPIX / box_s, "unit": "Mpix/s", "h2d_bytes_per_step": FRAME_BYTES,
+                    "d2h_bytes_per_step": int(e_box["bytes"] / max(1, e_box["calls"])) + 4, "calls": int(calls_box_all),
+                    "seconds": box_s, "api": "same call, acb200_set_default_scale(ACB200_SCALE_BOX): whole frames "
+                                             "cross PCIe (24.9 MB per frame)"},
+        "dropin_single_caller": {"ms_per_call": 1e3 * one["seconds"] / one["calls"],
+                                 "mpix_s": one["calls"] * MPIX / one["seconds"]},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if not args.no_cpu_baseline:
-        v, kind, cores, sample, _, _ = cpu_reference_leg(ncores)
-        line["cpu_baseline"] = {"value": v, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample,
+        r, kind, fp_ref = cpu_reference_leg(H, frames, ncores, 12.0)
+        line["cpu_baseline"] = {"value": r["calls"] * MPIX / r["seconds"], "unit": "Mpix/s", "cores": ncores,
+                                "kind": kind,
+                                "sample": "%d calls over a ring of %d uniform-noise 4K frames, %d caller threads, %.1f s"
+                                          % (r["calls"], frames.shape[0], ncores, r["seconds"]),
                                 "note": "reference path is nearest-neighbour: Mpix/s nominal (source px / time)"}
+        if fp_ref is not None:
+            line["e2e"]["bytes_identical_to_cpu_baseline"] = bool(fp_ref == fp_nn)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
