@@ -341,6 +341,18 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
   rp.lut = lut;
   rp.cells_out = nullptr;
   rp.n_frames = n_frames;
+  // measurement knobs (never set in production): ACB200_TUNE_NOALIAS=1, ACB200_PHASE_A_ONLY=1
+  static const int tune_noalias = getenv("ACB200_TUNE_NOALIAS") ? atoi(getenv("ACB200_TUNE_NOALIAS")) : 0;
+  static const int phase_a_only = getenv("ACB200_PHASE_A_ONLY") ? atoi(getenv("ACB200_PHASE_A_ONLY")) : 0;
+  rp.tune_flags = tune_noalias ? 1 : 0;
+  if (phase_a_only && pl.mode != EM_DITHER_BG) { // downscale only: rows == nullptr makes the kernel return after phase A
+    rp.rows = nullptr;
+    if (k0) cudaEventRecord(k0, st);
+    ACB_CUDA(launch_render_rows(rp, pl.mode, pl.scale_path, st));
+    if (k1) cudaEventRecord(k1, st);
+    count_launch();
+    return E_OK;
+  }
 
   if (k0) cudaEventRecord(k0, st);
   if (pl.mode != EM_DITHER_BG) {

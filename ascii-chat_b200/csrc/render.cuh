@@ -56,6 +56,7 @@ struct RenderParams {
   const GlyphLut *lut;
   uint8_t *cells_out;    // optional: resized RGB24 image, frame f at f*cols*rows_px*3 (image_resize, tests)
   int n_frames;
+  int tune_flags;         // bit0: do not alias V with the row staging buffer (measurement knob)
 };
 
 struct StitchParams {

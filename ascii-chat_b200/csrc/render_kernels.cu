@@ -197,7 +197,10 @@ __device__ __forceinline__ int row_scan(int w, F value_of, G store, int *s_tmp) 
 struct Layout {
   uint32_t lut, cT, cB, key, hpos, rend, off, V, outb, total;
 };
-__host__ __device__ inline Layout make_layout(int mode, int sp, int cols, int src_w, uint32_t out_bytes) {
+// V (column sums, phase A only) and the row staging buffer (phase B4 only) never live at the same time, so they
+// share one region unless `no_alias` (tuning knob ACB200_TUNE_NOALIAS) asks for separate ones.
+__host__ __device__ inline Layout make_layout(int mode, int sp, int cols, int src_w, uint32_t out_bytes,
+                                              int no_alias = 0) {
   Layout L;
   uint32_t o = 0;
   L.lut = o;
@@ -214,10 +217,16 @@ __host__ __device__ inline Layout make_layout(int mode, int sp, int cols, int sr
   o += al16(2u * cols);
   L.off = o;
   o += al16(4u * cols);
+  const uint32_t vbytes = sp == SP_BOX_STREAM ? al16(2u * 3u * src_w) : 0u;
   L.V = o;
-  o += sp == SP_BOX_STREAM ? al16(2u * 3u * src_w) : 0u;
-  L.outb = o;
-  o += al16(out_bytes);
+  if (no_alias) {
+    o += vbytes;
+    L.outb = o;
+    o += al16(out_bytes);
+  } else {
+    L.outb = o;
+    o += vbytes > al16(out_bytes) ? vbytes : al16(out_bytes);
+  }
   L.total = o;
   return L;
 }
@@ -476,7 +485,7 @@ template <int MODE, int SP> __global__ void __launch_bounds__(BLOCK) k_render_ro
   const bool last_row = t == p.text_rows - 1;
 
   const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
-  const Layout L = make_layout(MODE, SP, w, p.src_w, cap);
+  const Layout L = make_layout(MODE, SP, w, p.src_w, cap, p.tune_flags & 1);
   GlyphLut *lut = reinterpret_cast<GlyphLut *>(smem + L.lut);
   uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.cT);
   uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.cB);
@@ -827,7 +836,7 @@ __global__ void __launch_bounds__(256) k_dither_bg(const uint8_t *cells, int w, 
 // ------------------------------------------------------------------ launchers
 template <int MODE, int SP> static cudaError_t launch_rows_t(const RenderParams &p, cudaStream_t st) {
   const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
-  const Layout L = make_layout(MODE, SP, p.cols, p.src_w, cap);
+  const Layout L = make_layout(MODE, SP, p.cols, p.src_w, cap, p.tune_flags & 1);
   if (L.total > kMaxDynSmem) return cudaErrorInvalidConfiguration;
   static bool configured = false; // benign race: the attribute is idempotent
   if (!configured) {
@@ -865,7 +874,7 @@ cudaError_t launch_render_rows(const RenderParams &p, int mode, int sp, cudaStre
 }
 
 size_t rows_smem_total(int mode, int sp, int cols, int src_w, uint32_t out_bytes) {
-  return make_layout(mode, sp, cols, src_w, out_bytes).total;
+  return make_layout(mode, sp, cols, src_w, out_bytes, 1).total; // worst case (no aliasing)
 }
 
 cudaError_t launch_stitch(const StitchParams &p, int n_frames, cudaStream_t st) {

@@ -1,0 +1,100 @@
+"""Multi-GPU plumbing for the grid path (BASELINE config 4): one process per GPU, torch.distributed.
+
+The render path shards embarrassingly: client streams (or frames) are independent, so rank r renders the
+clients c with c % world == r on its own GPU with no data-path collective.  The ONE real exchange step of
+the reference's design is the grid: rendered client frames are gathered to the composing rank, which
+builds the final canvas (text-space: ascii_create_grid, lib/video/ascii/ascii.c:602-885; host.c:696-717).
+
+Everything here is backend-agnostic tensor plumbing (NCCL over NVLink on the GPU box, gloo on CPU for the
+world_size-2 tests); the rendering and the composition are C-ABI calls into libasciichat_b200.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_items, rank, world):
+    """client c -> rank c % world"""
+    return list(range(rank, n_items, world))
+
+
+def owner_of(item, world):
+    return item % world
+
+
+def gather_variable(local, n_items, dst=0, device=None, group=None):
+    """Gather variable-length byte strings to `dst`.
+
+    local: dict {item_index: 1-D uint8 tensor} for the items this rank owns (sharded with shard_indices).
+    Returns on dst a list of n_items uint8 tensors (on `device`), elsewhere None.
+
+    Two collectives, both fixed-shape so they map onto NCCL directly:
+      1. all_gather of the per-item lengths (int64, n_items slots, zero where not owned, then summed),
+      2. all_gather of each rank's payload packed at fixed pitch = the global max length
+         (payloads are <= ~1.2 MB per 4K frame: latency-bound, so one batched call beats per-item sends).
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    device = device or (next(iter(local.values())).device if local else torch.device("cpu"))
+    lens = torch.zeros(n_items, dtype=torch.int64, device=device)
+    for i, t in local.items():
+        lens[i] = t.numel()
+    dist.all_reduce(lens, op=dist.ReduceOp.SUM, group=group)
+    per_rank = (n_items + world - 1) // world
+    pitch = int(lens.max().item()) if n_items else 0
+    pitch = (pitch + 15) // 16 * 16
+    mine = torch.zeros(per_rank * max(pitch, 16), dtype=torch.uint8, device=device)
+    for slot, i in enumerate(shard_indices(n_items, rank, world)):
+        t = local[i]
+        mine[slot * pitch: slot * pitch + t.numel()] = t
+    allbuf = torch.empty(world * mine.numel(), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(allbuf, mine, group=group)
+    if rank != dst:
+        return None
+    out = []
+    stride = mine.numel()
+    for i in range(n_items):
+        r, slot = owner_of(i, world), i // world
+        base = r * stride + slot * pitch
+        out.append(allbuf[base: base + int(lens[i].item())])
+    return out
+
+
+def render_clients_to_grid(acb, client_frames, cfg, grid_w, grid_h, dst=0, group=None):
+    """BASELINE config 4 on N GPUs.
+
+    client_frames: dict {client_index: (h,w,3) uint8 torch tensor ON THIS RANK'S GPU} for the clients this rank
+                   owns; every client is rendered with the same acb200_render_cfg_t `cfg` (resident batch API),
+                   the strings are gathered to `dst` over NCCL and composed there with the device grid kernel.
+    Returns (bytes of the grid, n_clients) on dst, None elsewhere.
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n_clients = torch.tensor([len(client_frames)], dtype=torch.int64, device="cuda")
+    dist.all_reduce(n_clients, group=group)
+    n_clients = int(n_clients.item())
+    mine = shard_indices(n_clients, rank, world)
+    assert sorted(client_frames) == mine, "clients must be sharded round-robin (client c on rank c % world)"
+    local = {}
+    if mine:
+        batch = torch.stack([client_frames[i] for i in mine]).contiguous()
+        n = batch.shape[0]
+        cap = acb.frame_capacity(cfg)
+        d_out = torch.empty(n * cap, dtype=torch.uint8, device="cuda")
+        d_len = torch.empty(n, dtype=torch.int32, device="cuda")
+        d_scr = torch.empty(acb.scratch_bytes(cfg, n), dtype=torch.uint8, device="cuda")
+        stream = torch.cuda.current_stream().cuda_stream
+        acb.render_batch_device(cfg, batch.data_ptr(), n, d_out.data_ptr(), cap, d_len.data_ptr(), d_scr.data_ptr(),
+                                stream)
+        lens = d_len.cpu()
+        for slot, i in enumerate(mine):
+            local[i] = d_out[slot * cap: slot * cap + int(lens[slot])]
+    gathered = gather_variable(local, n_clients, dst=dst, device=torch.device("cuda"), group=group)
+    if rank != dst:
+        return None
+    srcs = [t.contiguous() for t in gathered]
+    canvas = torch.empty(max(grid_w * grid_h + grid_h + 1, max(t.numel() for t in srcs) + 1) + 16, dtype=torch.uint8,
+                         device="cuda")
+    size = acb.create_grid_device([t.data_ptr() for t in srcs], [t.numel() for t in srcs], grid_w, grid_h,
+                                  canvas.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.current_stream().synchronize()
+    return canvas[:size].cpu().numpy().tobytes(), n_clients

@@ -1,0 +1,66 @@
+"""Multi-GPU grid path (BASELINE config 4) on real GPUs: 8 client streams sharded round-robin over the ranks,
+rendered with the resident batch API, gathered over NCCL, composed on rank 0 with the device grid kernel.
+The result must equal the single-process oracle composition byte for byte.  Skipped on a 1-GPU box
+(run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`)."""
+import os
+import socket
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_clients, level, mode, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import ascii_chat_b200 as acb
+    from ascii_chat_b200 import multi
+    import oracle_bind as ob
+    assert acb.lib().acb200_init(rank) == 0
+    W, H, cols, rows = 480, 270, 80, 24
+    cfg = acb.make_cfg(W, H, cols, rows * 2 if mode == 2 else rows, level, mode)
+    mine = {c: torch.from_numpy(ob.gen(("noise", "bars", "gradient")[c % 3], W, H, c)).cuda()
+            for c in multi.shard_indices(n_clients, rank, world)}
+    res = multi.render_clients_to_grid(acb, mine, cfg, 160, 48)
+    if rank == 0:
+        q.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_clients,level,mode", [(8, 0, 0), (8, 3, 2), (5, 2, 0)])
+def test_grid_over_nccl(n_clients, level, mode):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    sys.path[:0] = [os.path.join(ROOT, "tests")]
+    import oracle_bind as ob
+    world = min(torch.cuda.device_count(), 4)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_clients, level, mode, q)) for r in range(world)]
+    [p.start() for p in procs]
+    grid, n = q.get(timeout=300)
+    [p.join(timeout=120) for p in procs]
+    assert n == n_clients and all(p.exitcode == 0 for p in procs)
+    frames = [ob.port_convert(ob.gen(("noise", "bars", "gradient")[c % 3], 480, 270, c), 80, 24, level, mode)
+              for c in range(n_clients)]
+    exp, size = ob.port_create_grid(frames, 160, 48)
+    assert grid == exp[:size] or grid == exp
