@@ -17,6 +17,7 @@ struct Plan {
   int mode;        // EmitMode
   int scale_path;  // ScalePath
   int text_rows;
+  int ring_depth;  // SP_BOX_TMA: rows in the producer ring
   int lut_which;   // 0 cache[Y], 1 mono double map (Q1), 2 16-colour map (Q2)
   uint32_t row_pitch;
   int use_smem_out;

@@ -22,7 +22,8 @@ enum EmitMode : int {
 enum ScalePath : int {
   SP_NN = 0,        // nearest neighbour, image.c:267-328
   SP_BOX_GENERIC = 1, // box filter, any geometry (byte loads)
-  SP_BOX_STREAM = 2   // box filter, 16-byte streaming loads (3*src_w % 16 == 0, band <= 256 rows)
+  SP_BOX_STREAM = 2,  // box filter, 16-byte streaming loads (3*src_w % 16 == 0, band <= 256 rows)
+  SP_BOX_TMA = 3      // box filter, persistent warp-specialised kernel: bulk-TMA row ring + consumer warps
 };
 
 // Brightness -> glyph tables for one (palette, mode) pair, built on the host
@@ -56,6 +57,7 @@ struct RenderParams {
   const GlyphLut *lut;
   uint8_t *cells_out;    // optional: resized RGB24 image, frame f at f*cols*rows_px*3 (image_resize, tests)
   int n_frames;
+  int ring_depth;         // warp-specialised kernel: source rows kept in flight by the producer warp
   int tune_flags;         // bit0: do not alias V with the row staging buffer (measurement knob)
 };
 
@@ -80,6 +82,8 @@ static constexpr int kSmemOutMax = 48 * 1024;      // rows up to this many bytes
 static constexpr uint32_t kMaxDynSmem = 226u * 1024u; // dynamic smem ceiling (227 KB opt-in minus static)
 
 cudaError_t launch_render_rows(const RenderParams &p, int mode, int scale_path, cudaStream_t st);
+cudaError_t launch_render_rows_ws(const RenderParams &p, int mode, cudaStream_t st);
+int ws_ring_depth(int mode, int cols, int src_w, uint32_t row_pitch);
 cudaError_t launch_stitch(const StitchParams &p, int n_frames, cudaStream_t st);
 cudaError_t launch_resize_nn_only(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh, int pregathered,
                                   cudaStream_t st);

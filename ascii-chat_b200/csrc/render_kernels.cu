@@ -160,13 +160,22 @@ struct OpMax {
   static __device__ __forceinline__ int ap(int a, int b) { return a > b ? a : b; }
 };
 
-// Scans value_of(x), x in [0,w), in x order over the CTA; calls store(x, inclusive, exclusive).
+// Barrier policies: the one-tile-per-CTA kernel synchronises the whole CTA; in the warp-specialised persistent
+// kernel only the 8 consumer warps (threads 0..255) take part, on named barrier 1, while the producer warp runs ahead.
+struct SyncAll {
+  static __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+struct SyncConsumers {
+  static __device__ __forceinline__ void sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+};
+
+// Scans value_of(x), x in [0,w), in x order over BLOCK threads; calls store(x, inclusive, exclusive).
 // Returns the total (valid in every thread).  s_tmp: NWARP+1 ints of shared memory.
-template <class Op, class F, class G>
+template <class Op, class Sync, class F, class G>
 __device__ __forceinline__ int row_scan(int w, F value_of, G store, int *s_tmp) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tmp[NWARP] = Op::id();
-  __syncthreads();
+  Sync::sync();
   for (int base = 0; base < w; base += BLOCK) {
     int x = base + tid;
     int v = x < w ? value_of(x) : Op::id();
@@ -178,18 +187,18 @@ __device__ __forceinline__ int row_scan(int w, F value_of, G store, int *s_tmp) 
     }
     int up = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 31) s_tmp[warp] = inc;
-    __syncthreads();
+    Sync::sync();
     int pre = s_tmp[NWARP];
     for (int i = 0; i < warp; i++) pre = Op::ap(pre, s_tmp[i]);
     int incl = Op::ap(pre, inc);
     int excl = lane == 0 ? pre : Op::ap(pre, up);
     if (x < w) store(x, incl, excl);
-    __syncthreads();
+    Sync::sync();
     if (tid == BLOCK - 1) s_tmp[NWARP] = incl;
-    __syncthreads();
+    Sync::sync();
   }
   const int total = s_tmp[NWARP];
-  __syncthreads(); // the next scan re-initialises s_tmp[NWARP]
+  Sync::sync(); // the next scan re-initialises s_tmp[NWARP]
   return total;
 }
 
@@ -469,20 +478,129 @@ template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int
   }
 }
 
+// Phase B for one text row whose resized pixels are in cT/cB: keys -> runs -> byte counts -> offsets -> bytes,
+// staged in shared memory (or written straight to the scratch row when it is too wide) and copied out.
+template <int MODE, class Sync>
+__device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT, uint32_t *cB,
+                                         uint16_t *key, uint16_t *hpos, uint16_t *rend, uint32_t *off, uint8_t *outb,
+                                         int *s_tmp, uint32_t *s_cond) {
+  constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
+  constexpr bool RUNS = MODE == EM_MONO_FG || HB;
+  const int tid = threadIdx.x;
+  const int w = p.cols;
+  const bool last_row = t == p.text_rows - 1;
+  if (tid < 4) s_cond[tid] = 0u;
+  Sync::sync();
+
+  // ---- phase B1: run keys
+  if (MODE == EM_MONO_FG) {
+    for (int x = tid; x < w; x += BLOCK) key[x] = lut->key[luma_of(cT[x])];
+  } else if (MODE == EM_HB_256) {
+    for (int x = tid; x < w; x += BLOCK) key[x] = (uint16_t)((q256_of(cT[x]) << 8) | q256_of(cB[x]));
+  } else if (MODE == EM_HB_16) {
+    for (int x = tid; x < w; x += BLOCK) key[x] = (uint16_t)((q16_of(cT[x]) << 8) | q16_of(cB[x]));
+  }
+  Sync::sync();
+
+  // ---- phase B2: run heads / previous-ASCII links
+  if (RUNS) {
+    auto is_head = [&](int x) -> bool {
+      if (x == 0) return true;
+      if (MODE == EM_HB_TRUE || MODE == EM_HB_MONO) return cT[x] != cT[x - 1] || cB[x] != cB[x - 1];
+      return key[x] != key[x - 1];
+    };
+    row_scan<OpMax, Sync>(
+        w, [&](int x) { return is_head(x) ? x : -1; }, [&](int x, int incl, int) { hpos[x] = (uint16_t)incl; },
+        s_tmp);
+    Sync::sync();
+    for (int x = tid; x < w; x += BLOCK) {
+      if (x > 0 && hpos[x] == x) rend[hpos[x - 1]] = (uint16_t)x; // this head closes the previous run
+      if (x == w - 1) rend[hpos[x]] = (uint16_t)w;
+    }
+    Sync::sync();
+  } else if (MODE == EM_TRUE_FG) {
+    int last_ascii = row_scan<OpMax, Sync>(
+        w,
+        [&](int x) {
+          const uint8_t *g = lut->glyph[luma_of(cT[x])];
+          return (g[0] == 1 && g[1] < 128) ? x : -1;
+        },
+        [&](int x, int, int excl) { hpos[x] = excl < 0 ? NONE16 : (uint16_t)excl; }, s_tmp);
+    if (tid == 0) s_cond[2] = last_ascii >= 0 ? (0x01000000u | cT[last_ascii]) : 0u;
+  }
+
+  // ---- phase B3: byte counts -> offsets
+  RowCtx ctx{lut, cT, cB, key, hpos, rend};
+  int cells_bytes = row_scan<OpAdd, Sync>(
+      w,
+      [&](int x) {
+        CountSink cs;
+        emit_cell<MODE>(cs, x, ctx);
+        return (int)cs.n;
+      },
+      [&](int x, int, int excl) { off[x] = (uint32_t)excl + (uint32_t)p.pad_left; }, s_tmp);
+  const uint32_t body_end = (uint32_t)p.pad_left + (uint32_t)cells_bytes;
+
+  // ---- phase B4: materialise
+  uint8_t *grow = p.rows + ((size_t)f * p.text_rows + t) * (size_t)p.row_pitch;
+  uint8_t *base = p.use_smem_out ? outb : grow;
+  for (int i = tid; i < p.pad_left; i += BLOCK) base[i] = ' ';
+  for (int x = tid; x < w; x += BLOCK) {
+    WriteSink ws{base + off[x]};
+    emit_cell<MODE>(ws, x, ctx);
+    if (MODE == EM_TRUE_FG && hpos[x] == NONE16) {
+      const uint8_t *g = lut->glyph[luma_of(cT[x])];
+      if (g[0] == 1 && g[1] < 128) { // the row's first ASCII-glyph cell: its SGR is conditional on the row above
+        CountSink cs;
+        put_sgr_rgb(cs, false, cT[x]);
+        s_cond[0] = off[x];
+        s_cond[1] = cs.n;
+        s_cond[3] = 0x01000000u | cT[x];
+      }
+    }
+  }
+  uint32_t len = body_end;
+  if (tid == 0) {
+    WriteSink ws{base + body_end};
+    if (MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16)
+      put_reset(ws);
+    if (MODE == EM_TRUE_FG && last_row) put_reset(ws); // ansi_rle_finish, ansi.c:303-314
+    if (!last_row) ws.put('\n');
+    len = (uint32_t)(ws.p - base);
+  }
+  Sync::sync();
+  if (tid == 0) {
+    RowMeta m;
+    m.len = len;
+    m.cond_off = s_cond[0];
+    m.cond_len = s_cond[1];
+    m.first_rgb = s_cond[3];
+    m.last_rgb = s_cond[2];
+    m._pad[0] = m._pad[1] = m._pad[2] = 0;
+    p.meta[(size_t)f * p.text_rows + t] = m;
+    s_cond[0] = len;
+  }
+  Sync::sync();
+  if (p.use_smem_out) {
+    const uint32_t n16 = (s_cond[0] + 15u) >> 4;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(outb);
+    uint4 *d4 = reinterpret_cast<uint4 *>(grow);
+    for (uint32_t i = tid; i < n16; i += BLOCK) d4[i] = s4[i];
+  }
+}
+
 template <int MODE, int SP> __global__ void __launch_bounds__(BLOCK) k_render_rows(const RenderParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ int s_tmp[NWARP + 1];
   __shared__ uint32_t s_cond[4]; // TRUE_FG: {cond_off, cond_len, last_rgb, first_rgb}
 
   constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
-  constexpr bool RUNS = MODE == EM_MONO_FG || HB;
   constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
 
   const int tid = threadIdx.x;
   const int t = (int)(blockIdx.x % (unsigned)p.text_rows);
   const int f = (int)(blockIdx.x / (unsigned)p.text_rows);
   const int w = p.cols;
-  const bool last_row = t == p.text_rows - 1;
 
   const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
   const Layout L = make_layout(MODE, SP, w, p.src_w, cap, p.tune_flags & 1);
@@ -501,7 +619,6 @@ template <int MODE, int SP> __global__ void __launch_bounds__(BLOCK) k_render_ro
     uint32_t *dst = reinterpret_cast<uint32_t *>(lut);
     for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += BLOCK) dst[i] = src[i];
   }
-  if (tid < 4) s_cond[tid] = 0u;
 
   // ---- phase A
   const uint8_t *frame = p.frames + (size_t)f * p.frame_stride;
@@ -540,100 +657,193 @@ template <int MODE, int SP> __global__ void __launch_bounds__(BLOCK) k_render_ro
   }
   if (p.rows == nullptr) return; // resize-only invocation
 
-  // ---- phase B1: run keys
-  if (MODE == EM_MONO_FG) {
-    for (int x = tid; x < w; x += BLOCK) key[x] = lut->key[luma_of(cT[x])];
-  } else if (MODE == EM_HB_256) {
-    for (int x = tid; x < w; x += BLOCK) key[x] = (uint16_t)((q256_of(cT[x]) << 8) | q256_of(cB[x]));
-  } else if (MODE == EM_HB_16) {
-    for (int x = tid; x < w; x += BLOCK) key[x] = (uint16_t)((q16_of(cT[x]) << 8) | q16_of(cB[x]));
-  }
-  __syncthreads();
+  emit_row<MODE, SyncAll>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond);
+}
 
-  // ---- phase B2: run heads / previous-ASCII links
-  if (RUNS) {
-    auto is_head = [&](int x) -> bool {
-      if (x == 0) return true;
-      if (MODE == EM_HB_TRUE || MODE == EM_HB_MONO) return cT[x] != cT[x - 1] || cB[x] != cB[x - 1];
-      return key[x] != key[x - 1];
-    };
-    row_scan<OpMax>(
-        w, [&](int x) { return is_head(x) ? x : -1; }, [&](int x, int incl, int) { hpos[x] = (uint16_t)incl; },
-        s_tmp);
-    __syncthreads();
-    for (int x = tid; x < w; x += BLOCK) {
-      if (x > 0 && hpos[x] == x) rend[hpos[x - 1]] = (uint16_t)x; // this head closes the previous run
-      if (x == w - 1) rend[hpos[x]] = (uint16_t)w;
+// ------------------------------------------------------------------ warp-specialised persistent row kernel
+// Box-filter streaming with the copy engine instead of the LSU: a producer warp keeps a ring of whole source rows
+// in flight with 1-D bulk TMA copies (cp.async.bulk, completion on an mbarrier), eight consumer warps sum the rows
+// out of shared memory and then emit the text row.  CTAs are persistent (tile = blockIdx.x + k*gridDim.x over
+// (frame, text row)), so while the consumers are in the emission phase of tile k the producer is already filling
+// the ring with the first rows of tile k+1: HBM traffic never pauses for the byte-emission work.
+//
+//   full[s]  : producer arms it with expect_tx(row bytes); the bulk copy completes it        (count 1 + tx)
+//   empty[s] : one arrival per consumer warp when the warp has read slot s                   (count 8)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int WS_THREADS = BLOCK + 32; // 8 consumer warps + 1 producer warp
+constexpr int WS_MAXD = 16;            // ring slots (source rows) at most
+
+struct WsBand {
+  int a0, a1, b1; // top pixel row sums source rows [a0,a1), bottom [a1,b1)  (contiguous when downscaling)
+  bool hasB;
+};
+template <bool HB> __device__ __forceinline__ WsBand ws_band(const RenderParams &p, int t) {
+  WsBand b;
+  const int yT = HB ? 2 * t : t;
+  box_range(yT, p.src_h, p.rows_px, b.a0, b.a1);
+  b.hasB = HB && (2 * t + 1 < p.rows_px);
+  b.b1 = b.a1;
+  if (b.hasB) {
+    int b0;
+    box_range(yT + 1, p.src_h, p.rows_px, b0, b.b1);
+  }
+  return b;
+}
+
+template <int MODE, int CPT>
+__global__ void __launch_bounds__(WS_THREADS) k_render_rows_ws(const RenderParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ int s_tmp[NWARP + 1];
+  __shared__ uint32_t s_cond[4];
+  __shared__ __align__(8) uint64_t s_full[WS_MAXD], s_empty[WS_MAXD];
+
+  constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
+  constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int w = p.cols;
+  const uint32_t R = (uint32_t)p.src_w * 3u;
+  const int nchunk = (int)(R >> 4);
+  const uint32_t D = (uint32_t)p.ring_depth;
+  const int total = p.n_frames * p.text_rows;
+
+  const Layout L = make_layout(MODE, SP_BOX_STREAM, w, p.src_w, p.row_pitch, 0);
+  GlyphLut *lut = reinterpret_cast<GlyphLut *>(smem + L.lut);
+  uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.cT);
+  uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.cB);
+  uint16_t *key = reinterpret_cast<uint16_t *>(smem + L.key);
+  uint16_t *hpos = reinterpret_cast<uint16_t *>(smem + L.hpos);
+  uint16_t *rend = reinterpret_cast<uint16_t *>(smem + L.rend);
+  uint32_t *off = reinterpret_cast<uint32_t *>(smem + L.off);
+  uint16_t *V = reinterpret_cast<uint16_t *>(smem + L.V);
+  uint8_t *outb = smem + L.outb;
+  uint8_t *ring = smem + ((L.total + 127u) & ~127u);
+
+  if (tid == 0) {
+    for (uint32_t s = 0; s < D; s++) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], NWARP);
     }
-    __syncthreads();
-  } else if (MODE == EM_TRUE_FG) {
-    int last_ascii = row_scan<OpMax>(
-        w,
-        [&](int x) {
-          const uint8_t *g = lut->glyph[luma_of(cT[x])];
-          return (g[0] == 1 && g[1] < 128) ? x : -1;
-        },
-        [&](int x, int, int excl) { hpos[x] = excl < 0 ? NONE16 : (uint16_t)excl; }, s_tmp);
-    if (tid == 0) s_cond[2] = last_ascii >= 0 ? (0x01000000u | cT[last_ascii]) : 0u;
+    mbar_fence_init();
   }
+  if (USES_LUT && tid < BLOCK) {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(lut);
+    for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += BLOCK) dst[i] = src[i];
+  }
+  __syncthreads(); // the only CTA-wide barrier: after it the producer warp and the consumer warps part ways
 
-  // ---- phase B3: byte counts -> offsets
-  RowCtx ctx{lut, cT, cB, key, hpos, rend};
-  int cells_bytes = row_scan<OpAdd>(
-      w,
-      [&](int x) {
-        CountSink cs;
-        emit_cell<MODE>(cs, x, ctx);
-        return (int)cs.n;
-      },
-      [&](int x, int, int excl) { off[x] = (uint32_t)excl + (uint32_t)p.pad_left; }, s_tmp);
-  const uint32_t body_end = (uint32_t)p.pad_left + (uint32_t)cells_bytes;
-
-  // ---- phase B4: materialise
-  uint8_t *grow = p.rows + ((size_t)f * p.text_rows + t) * (size_t)p.row_pitch;
-  uint8_t *base = p.use_smem_out ? outb : grow;
-  for (int i = tid; i < p.pad_left; i += BLOCK) base[i] = ' ';
-  for (int x = tid; x < w; x += BLOCK) {
-    WriteSink ws{base + off[x]};
-    emit_cell<MODE>(ws, x, ctx);
-    if (MODE == EM_TRUE_FG && hpos[x] == NONE16) {
-      const uint8_t *g = lut->glyph[luma_of(cT[x])];
-      if (g[0] == 1 && g[1] < 128) { // the row's first ASCII-glyph cell: its SGR is conditional on the row above
-        CountSink cs;
-        put_sgr_rgb(cs, false, cT[x]);
-        s_cond[0] = off[x];
-        s_cond[1] = cs.n;
-        s_cond[3] = 0x01000000u | cT[x];
+  if (warp == NWARP) { // ---------------- producer: one lane walks the same tile/row sequence as the consumers
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int t = tile % p.text_rows, f = tile / p.text_rows;
+        const WsBand b = ws_band<HB>(p, t);
+        const uint8_t *src = p.frames + (size_t)f * p.frame_stride + (size_t)b.a0 * R;
+        for (int r = b.a0; r < b.b1; r++, g++, src += R) {
+          const uint32_t slot = g % D, ph = (g / D) & 1u;
+          mbar_wait(&s_empty[slot], ph ^ 1u); // a fresh barrier passes the parity-1 wait: the ring starts empty
+          mbar_expect_tx(&s_full[slot], R);
+          bulk_g2s(ring + (size_t)slot * R, src, R, &s_full[slot]);
+        }
       }
     }
+    return;
   }
-  uint32_t len = body_end;
-  if (tid == 0) {
-    WriteSink ws{base + body_end};
-    if (MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16)
-      put_reset(ws);
-    if (MODE == EM_TRUE_FG && last_row) put_reset(ws); // ansi_rle_finish, ansi.c:303-314
-    if (!last_row) ws.put('\n');
-    len = (uint32_t)(ws.p - base);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    RowMeta m;
-    m.len = len;
-    m.cond_off = s_cond[0];
-    m.cond_len = s_cond[1];
-    m.first_rgb = s_cond[3];
-    m.last_rgb = s_cond[2];
-    m._pad[0] = m._pad[1] = m._pad[2] = 0;
-    p.meta[(size_t)f * p.text_rows + t] = m;
-    s_cond[0] = len;
-  }
-  __syncthreads();
-  if (p.use_smem_out) {
-    const uint32_t n16 = (s_cond[0] + 15u) >> 4;
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(outb);
-    uint4 *d4 = reinterpret_cast<uint4 *>(grow);
-    for (uint32_t i = tid; i < n16; i += BLOCK) d4[i] = s4[i];
+
+  // ---------------- consumers (threads 0..255)
+  uint32_t g = 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int t = tile % p.text_rows, f = tile / p.text_rows;
+    const WsBand b = ws_band<HB>(p, t);
+#pragma unroll 1
+    for (int half = 0; half < (HB ? 2 : 1); half++) {
+      uint32_t *out = half ? cB : cT;
+      if (half && !b.hasB) { // odd pixel height: bottom := top (halfblock.c:73,82-88)
+        for (int x = tid; x < w; x += BLOCK) cB[x] = cT[x];
+        break;
+      }
+      const int r0 = half ? b.a1 : b.a0, r1 = half ? b.b1 : b.a1;
+      uint32_t a[CPT][8];
+#pragma unroll
+      for (int j = 0; j < CPT; j++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[j][k] = 0u;
+      for (int r = r0; r < r1; r++, g++) {
+        const uint32_t slot = g % D, ph = (g / D) & 1u;
+        mbar_wait(&s_full[slot], ph);
+        const uint4 *row = reinterpret_cast<const uint4 *>(ring + (size_t)slot * R);
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+          const int c = tid + j * BLOCK;
+          if (c < nchunk) acc16(a[j], row[c]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[slot]);
+      }
+#pragma unroll
+      for (int j = 0; j < CPT; j++) {
+        const int c = tid + j * BLOCK;
+        if (c < nchunk) {
+          uint4 lo, hi;
+          lo.x = __byte_perm(a[j][0], a[j][1], 0x5410);
+          lo.y = __byte_perm(a[j][0], a[j][1], 0x7632);
+          lo.z = __byte_perm(a[j][2], a[j][3], 0x5410);
+          lo.w = __byte_perm(a[j][2], a[j][3], 0x7632);
+          hi.x = __byte_perm(a[j][4], a[j][5], 0x5410);
+          hi.y = __byte_perm(a[j][4], a[j][5], 0x7632);
+          hi.z = __byte_perm(a[j][6], a[j][7], 0x5410);
+          hi.w = __byte_perm(a[j][6], a[j][7], 0x7632);
+          uint4 *dst = reinterpret_cast<uint4 *>(V + (size_t)c * 16);
+          dst[0] = lo;
+          dst[1] = hi;
+        }
+      }
+      SyncConsumers::sync();
+      const uint32_t nrow = (uint32_t)(r1 - r0);
+      for (int x = tid; x < w; x += BLOCK) {
+        int x0, x1;
+        box_range(x, p.src_w, p.cols, x0, x1);
+        uint32_t sr = 0, sg = 0, sb = 0;
+        const uint16_t *q = V + 3 * x0;
+        for (int xx = x0; xx < x1; xx++, q += 3) {
+          sr += q[0];
+          sg += q[1];
+          sb += q[2];
+        }
+        const uint32_t n = (uint32_t)(x1 - x0) * nrow, h = n >> 1;
+        out[x] = (((sr + h) / n) << 16) | (((sg + h) / n) << 8) | ((sb + h) / n);
+      }
+      SyncConsumers::sync(); // V is reused by the other pixel row / aliased by the row staging buffer
+    }
+    SyncConsumers::sync();
+    emit_row<MODE, SyncConsumers>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond);
+    SyncConsumers::sync(); // the staging buffer aliases V: finish copying out before the next tile's sums land
   }
 }
 
@@ -871,6 +1081,70 @@ cudaError_t launch_render_rows(const RenderParams &p, int mode, int sp, cudaStre
   case EM_HB_MONO: return launch_rows_sp<EM_HB_MONO>(p, sp, st);
   default: return cudaErrorInvalidValue;
   }
+}
+
+template <int MODE, int CPT> static cudaError_t launch_ws_t(const RenderParams &p, cudaStream_t st) {
+  const Layout L = make_layout(MODE, SP_BOX_STREAM, p.cols, p.src_w, p.row_pitch, 0);
+  const size_t smem = ((L.total + 127u) & ~127u) + (size_t)p.ring_depth * p.src_w * 3u;
+  if (smem > kMaxDynSmem) return cudaErrorInvalidConfiguration;
+  static bool configured = false;
+  static int ctas_per_sm = 1, sms = 148;
+  static size_t cfg_smem = 0;
+  if (!configured || smem != cfg_smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_render_rows_ws<MODE, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kMaxDynSmem);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_render_rows_ws<MODE, CPT>, WS_THREADS, smem);
+    if (e != cudaSuccess || ctas_per_sm < 1) return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
+    cfg_smem = smem;
+    configured = true;
+  }
+  const long long total = (long long)p.n_frames * p.text_rows;
+  long long grid = (long long)sms * ctas_per_sm;
+  if (grid > total) grid = total;
+  k_render_rows_ws<MODE, CPT><<<(unsigned)grid, WS_THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+template <int MODE> static cudaError_t launch_ws_cpt(const RenderParams &p, cudaStream_t st) {
+  const int nchunk = (p.src_w * 3) >> 4;
+  const int cpt = (nchunk + BLOCK - 1) / BLOCK;
+  if (cpt <= 1) return launch_ws_t<MODE, 1>(p, st);
+  if (cpt <= 2) return launch_ws_t<MODE, 2>(p, st);
+  if (cpt <= 3) return launch_ws_t<MODE, 3>(p, st);
+  if (cpt <= 4) return launch_ws_t<MODE, 4>(p, st);
+  if (cpt <= 8) return launch_ws_t<MODE, 8>(p, st);
+  return cudaErrorInvalidConfiguration;
+}
+cudaError_t launch_render_rows_ws(const RenderParams &p, int mode, cudaStream_t st) {
+  switch (mode) {
+  case EM_MONO_FG: return launch_ws_cpt<EM_MONO_FG>(p, st);
+  case EM_256_FG: return launch_ws_cpt<EM_256_FG>(p, st);
+  case EM_16_FG: return launch_ws_cpt<EM_16_FG>(p, st);
+  case EM_TRUE_FG: return launch_ws_cpt<EM_TRUE_FG>(p, st);
+  case EM_HB_TRUE: return launch_ws_cpt<EM_HB_TRUE>(p, st);
+  case EM_HB_256: return launch_ws_cpt<EM_HB_256>(p, st);
+  case EM_HB_16: return launch_ws_cpt<EM_HB_16>(p, st);
+  case EM_HB_MONO: return launch_ws_cpt<EM_HB_MONO>(p, st);
+  default: return cudaErrorInvalidValue;
+  }
+}
+// ring depth for the warp-specialised kernel: as many source rows as fit half an SM's shared memory (two CTAs per
+// SM), 0 if the geometry does not qualify
+int ws_ring_depth(int mode, int cols, int src_w, uint32_t row_pitch) {
+  const Layout L = make_layout(mode, SP_BOX_STREAM, cols, src_w, row_pitch, 0);
+  const size_t fixed = (L.total + 127u) & ~127u;
+  const size_t R = (size_t)src_w * 3u;
+  const size_t budget = (227u * 1024u) / 2u - 2048u;
+  if (fixed + 3 * R > budget) {
+    if (fixed + 3 * R > kMaxDynSmem) return 0;
+    size_t d1 = (kMaxDynSmem - fixed) / R; // one CTA per SM
+    return (int)(d1 > WS_MAXD ? WS_MAXD : d1);
+  }
+  size_t d = (budget - fixed) / R;
+  return (int)(d > WS_MAXD ? WS_MAXD : d);
 }
 
 size_t rows_smem_total(int mode, int sp, int cols, int src_w, uint32_t out_bytes) {
