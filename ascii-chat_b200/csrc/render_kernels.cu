@@ -14,231 +14,10 @@
 //
 // All arithmetic is integer; see oracle/ascii_oracle.c for the CPU restatement these kernels
 // are checked against byte for byte.
-#include "render.cuh"
+#include "render_dev.cuh"
 
 namespace acb {
 
-constexpr int BLOCK = 256;
-constexpr int NWARP = BLOCK / 32;
-constexpr uint16_t NONE16 = 0xFFFF;
-constexpr int kBandUnroll = 12; // independent 16-byte loads in flight per thread in the streaming box filter
-
-// ------------------------------------------------------------------ small integer helpers
-__device__ __forceinline__ int luma_of(uint32_t c) { // foreground.c:93  (77R+150G+29B+128)>>8
-  return (int)((77u * ((c >> 16) & 255u) + 150u * ((c >> 8) & 255u) + 29u * (c & 255u) + 128u) >> 8);
-}
-__device__ __forceinline__ int luma76_of(uint32_t c) { // halfblock.c:239-240  (76R+150G+29B)>>8
-  return (int)((76u * ((c >> 16) & 255u) + 150u * ((c >> 8) & 255u) + 29u * (c & 255u)) >> 8);
-}
-__device__ __forceinline__ int q256_of(uint32_t c) { // ansi.c:360-379
-  int r = (c >> 16) & 255, g = (c >> 8) & 255, b = c & 255;
-  int avg = (r + g + b) / 3;
-  int d = abs(r - avg) + abs(g - avg) + abs(b - avg);
-  if (d < 30) return 232 + (avg * 23) / 255;
-  return 16 + 36 * ((r * 5) / 255) + 6 * ((g * 5) / 255) + (b * 5) / 255;
-}
-__constant__ uint8_t c_ansi16[16][4] = { // ansi.c:442-459
-    {0, 0, 0, 0},       {128, 0, 0, 0},   {0, 128, 0, 0},   {128, 128, 0, 0}, {0, 0, 128, 0},   {128, 0, 128, 0},
-    {0, 128, 128, 0},   {192, 192, 192, 0}, {128, 128, 128, 0}, {255, 0, 0, 0},   {0, 255, 0, 0},   {255, 255, 0, 0},
-    {0, 0, 255, 0},     {255, 0, 255, 0}, {0, 255, 255, 0}, {255, 255, 255, 0}};
-__device__ __forceinline__ int q16_rgb(int r, int g, int b) { // ansi.c:437-477, first minimum wins
-  int best = 0, bestd = 0x7fffffff;
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    int dr = r - c_ansi16[i][0], dg = g - c_ansi16[i][1], db = b - c_ansi16[i][2];
-    int d = dr * dr + dg * dg + db * db;
-    if (d < bestd) {
-      bestd = d;
-      best = i;
-    }
-  }
-  return best;
-}
-__device__ __forceinline__ int q16_of(uint32_t c) { return q16_rgb((c >> 16) & 255, (c >> 8) & 255, c & 255); }
-
-__device__ __forceinline__ bool rep_profitable(uint32_t run) { // output_buffer.c:148-154
-  if (run <= 2) return false;
-  uint32_t k = run - 1;
-  uint32_t digits = k >= 1000u ? (k >= 10000u ? 5u : 4u) : (k >= 100u ? 3u : (k >= 10u ? 2u : 1u)); // k < 100000 here
-  return k > digits + 3u;
-}
-
-// ------------------------------------------------------------------ byte sinks
-struct CountSink {
-  uint32_t n = 0;
-  __device__ __forceinline__ void put(uint8_t) { ++n; }
-};
-struct WriteSink {
-  uint8_t *p;
-  __device__ __forceinline__ void put(uint8_t c) { *p++ = c; }
-};
-
-template <class S> __device__ __forceinline__ void put_u8dec(S &s, uint32_t v) { // dec3 table, common.c:546-570
-  if (v >= 100u) {
-    uint32_t h = v / 100u, r = v - h * 100u;
-    s.put((uint8_t)('0' + h));
-    s.put((uint8_t)('0' + r / 10u));
-    s.put((uint8_t)('0' + r % 10u));
-  } else if (v >= 10u) {
-    s.put((uint8_t)('0' + v / 10u));
-    s.put((uint8_t)('0' + v % 10u));
-  } else {
-    s.put((uint8_t)('0' + v));
-  }
-}
-template <class S> __device__ __forceinline__ void put_u32dec(S &s, uint32_t v) { // ob_u32, output_buffer.c:92-104
-  uint8_t t[10];
-  int i = 0;
-  do {
-    t[i++] = (uint8_t)('0' + v % 10u);
-    v /= 10u;
-  } while (v);
-  while (i--) s.put(t[i]);
-}
-template <class S> __device__ __forceinline__ void put_sgr_rgb(S &s, bool bg, uint32_t c) { // ansi.c:143-195
-  s.put(0x1b);
-  s.put('[');
-  s.put(bg ? '4' : '3');
-  s.put('8');
-  s.put(';');
-  s.put('2');
-  s.put(';');
-  put_u8dec(s, (c >> 16) & 255u);
-  s.put(';');
-  put_u8dec(s, (c >> 8) & 255u);
-  s.put(';');
-  put_u8dec(s, c & 255u);
-  s.put('m');
-}
-template <class S> __device__ __forceinline__ void put_sgr_256(S &s, bool bg, uint32_t idx) { // ansi.c:326-357
-  s.put(0x1b);
-  s.put('[');
-  s.put(bg ? '4' : '3');
-  s.put('8');
-  s.put(';');
-  s.put('5');
-  s.put(';');
-  put_u8dec(s, idx);
-  s.put('m');
-}
-template <class S> __device__ __forceinline__ void put_sgr_16(S &s, bool bg, uint32_t idx) { // ansi.c:384-435
-  uint32_t code = (idx < 8u ? 30u + idx : 82u + idx) + (bg ? 10u : 0u);
-  s.put(0x1b);
-  s.put('[');
-  put_u8dec(s, code);
-  s.put('m');
-}
-template <class S> __device__ __forceinline__ void put_reset(S &s) {
-  s.put(0x1b);
-  s.put('[');
-  s.put('0');
-  s.put('m');
-}
-template <class S> __device__ __forceinline__ void put_rep(S &s, uint32_t extra) { // output_buffer.c:156-164
-  s.put(0x1b);
-  s.put('[');
-  put_u32dec(s, extra);
-  s.put('b');
-}
-template <class S> __device__ __forceinline__ void put_glyph(S &s, const uint8_t *g) {
-  int n = g[0];
-  for (int i = 0; i < n; i++) s.put(g[1 + i]);
-}
-template <class S> __device__ __forceinline__ void put3(S &s, uint8_t a, uint8_t b, uint8_t c) {
-  s.put(a);
-  s.put(b);
-  s.put(c);
-}
-
-// ------------------------------------------------------------------ block-wide row scans
-struct OpAdd {
-  static __device__ __forceinline__ int id() { return 0; }
-  static __device__ __forceinline__ int ap(int a, int b) { return a + b; }
-};
-struct OpMax {
-  static __device__ __forceinline__ int id() { return -1; }
-  static __device__ __forceinline__ int ap(int a, int b) { return a > b ? a : b; }
-};
-
-// Barrier policies: the one-tile-per-CTA kernel synchronises the whole CTA; in the warp-specialised persistent
-// kernel only the 8 consumer warps (threads 0..255) take part, on named barrier 1, while the producer warp runs ahead.
-struct SyncAll {
-  static __device__ __forceinline__ void sync() { __syncthreads(); }
-};
-struct SyncConsumers {
-  static __device__ __forceinline__ void sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-};
-
-// Scans value_of(x), x in [0,w), in x order over BLOCK threads; calls store(x, inclusive, exclusive).
-// Returns the total (valid in every thread).  s_tmp: NWARP+1 ints of shared memory.
-template <class Op, class Sync, class F, class G>
-__device__ __forceinline__ int row_scan(int w, F value_of, G store, int *s_tmp) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tmp[NWARP] = Op::id();
-  Sync::sync();
-  for (int base = 0; base < w; base += BLOCK) {
-    int x = base + tid;
-    int v = x < w ? value_of(x) : Op::id();
-    int inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int o = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc = Op::ap(o, inc);
-    }
-    int up = __shfl_up_sync(0xffffffffu, inc, 1);
-    if (lane == 31) s_tmp[warp] = inc;
-    Sync::sync();
-    int pre = s_tmp[NWARP];
-    for (int i = 0; i < warp; i++) pre = Op::ap(pre, s_tmp[i]);
-    int incl = Op::ap(pre, inc);
-    int excl = lane == 0 ? pre : Op::ap(pre, up);
-    if (x < w) store(x, incl, excl);
-    Sync::sync();
-    if (tid == BLOCK - 1) s_tmp[NWARP] = incl;
-    Sync::sync();
-  }
-  const int total = s_tmp[NWARP];
-  Sync::sync(); // the next scan re-initialises s_tmp[NWARP]
-  return total;
-}
-
-// ------------------------------------------------------------------ shared-memory layout
-struct Layout {
-  uint32_t lut, cT, cB, key, hpos, rend, off, V, outb, total;
-};
-// V (column sums, phase A only) and the row staging buffer (phase B4 only) never live at the same time, so they
-// share one region unless `no_alias` (tuning knob ACB200_TUNE_NOALIAS) asks for separate ones.
-__host__ __device__ inline Layout make_layout(int mode, int sp, int cols, int src_w, uint32_t out_bytes,
-                                              int no_alias = 0) {
-  Layout L;
-  uint32_t o = 0;
-  L.lut = o;
-  o += al16((uint32_t)sizeof(GlyphLut));
-  L.cT = o;
-  o += al16(4u * cols);
-  L.cB = o;
-  o += (mode >= EM_HB_TRUE && mode <= EM_HB_MONO) ? al16(4u * cols) : 0u;
-  L.key = o;
-  o += al16(2u * cols);
-  L.hpos = o;
-  o += al16(2u * cols);
-  L.rend = o;
-  o += al16(2u * cols);
-  L.off = o;
-  o += al16(4u * cols);
-  const uint32_t vbytes = sp == SP_BOX_STREAM ? al16(2u * 3u * src_w) : 0u;
-  L.V = o;
-  if (no_alias) {
-    o += vbytes;
-    L.outb = o;
-    o += al16(out_bytes);
-  } else {
-    L.outb = o;
-    o += vbytes > al16(out_bytes) ? vbytes : al16(out_bytes);
-  }
-  L.total = o;
-  return L;
-}
 
 uint32_t row_capacity_bytes(int mode, int cols, int pad_left) { // SURVEY.md §8a grammar table maxima
   uint32_t per;
@@ -258,594 +37,6 @@ uint32_t row_capacity_bytes(int mode, int cols, int pad_left) {
   return al16((uint32_t)pad_left + per * (uint32_t)cols + 4u /*reset*/ + 1u /*\n*/ + 4u /*frame reset*/ + 16u);
 }
 
-// ------------------------------------------------------------------ phase A: resized pixels
-__device__ __forceinline__ uint32_t load_px(const uint8_t *p) {
-  return ((uint32_t)p[0] << 16) | ((uint32_t)p[1] << 8) | (uint32_t)p[2];
-}
-
-// nearest neighbour — image.c:293-325 (u32 fixed-point, wraps like the reference)
-__device__ __forceinline__ void cells_nn(const RenderParams &p, const uint8_t *frame, int y, uint32_t *out) {
-  const uint32_t xr = (uint32_t)((((uint64_t)p.src_w << 16) / (uint64_t)p.cols) + 1);
-  const uint32_t yr = (uint32_t)((((uint64_t)p.src_h << 16) / (uint64_t)p.rows_px) + 1);
-  uint32_t sy;
-  if (p.pregathered) {
-    sy = (uint32_t)y;
-  } else {
-    sy = ((uint32_t)y * yr) >> 16;
-    if (sy >= (uint32_t)p.src_h) sy = (uint32_t)p.src_h - 1;
-  }
-  const uint8_t *row = frame + (size_t)sy * (size_t)p.src_w * 3u;
-  for (int x = threadIdx.x; x < p.cols; x += BLOCK) {
-    uint32_t sx = ((uint32_t)x * xr) >> 16;
-    if (sx >= (uint32_t)p.src_w) sx = (uint32_t)p.src_w - 1;
-    out[x] = load_px(row + (size_t)sx * 3u);
-  }
-}
-
-__device__ __forceinline__ void box_range(int d, int src, int dst, int &a, int &b) {
-  a = (int)(((long long)d * src) / dst);
-  b = (int)(((long long)(d + 1) * src) / dst);
-  if (b <= a) b = a + 1;
-  if (b > src) b = src;
-  if (a >= src) a = src - 1;
-}
-
-// box filter, any geometry: one thread per destination pixel, byte loads
-__device__ __forceinline__ void cells_box_generic(const RenderParams &p, const uint8_t *frame, int y, uint32_t *out) {
-  int y0, y1;
-  box_range(y, p.src_h, p.rows_px, y0, y1);
-  for (int x = threadIdx.x; x < p.cols; x += BLOCK) {
-    int x0, x1;
-    box_range(x, p.src_w, p.cols, x0, x1);
-    uint32_t sr = 0, sg = 0, sb = 0;
-    for (int yy = y0; yy < y1; yy++) {
-      const uint8_t *q = frame + ((size_t)yy * p.src_w + x0) * 3u;
-      for (int xx = x0; xx < x1; xx++, q += 3) {
-        sr += q[0];
-        sg += q[1];
-        sb += q[2];
-      }
-    }
-    uint32_t n = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0), h = n >> 1;
-    out[x] = (((sr + h) / n) << 16) | (((sg + h) / n) << 8) | ((sb + h) / n);
-  }
-}
-
-__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) { // read-once data: bypass L1 allocation
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void acc16(uint32_t (&a)[8], const uint4 &v) {
-  // 16 byte lanes -> 16 u16 partial sums, two per register (even bytes / odd bytes of each word)
-  a[0] += v.x & 0x00FF00FFu;
-  a[1] += (v.x >> 8) & 0x00FF00FFu;
-  a[2] += v.y & 0x00FF00FFu;
-  a[3] += (v.y >> 8) & 0x00FF00FFu;
-  a[4] += v.z & 0x00FF00FFu;
-  a[5] += (v.z >> 8) & 0x00FF00FFu;
-  a[6] += v.w & 0x00FF00FFu;
-  a[7] += (v.w >> 8) & 0x00FF00FFu;
-}
-
-// box filter, streaming: the band of source rows [y0,y1) is one contiguous byte range; every thread owns
-// 16-byte columns of it, sums them down the band in registers (u16 lanes, band <= 256 rows), parks the
-// column sums V[3*src_w] in shared memory, then one thread per destination pixel adds its x-range.
-__device__ __forceinline__ void cells_box_stream(const RenderParams &p, const uint8_t *frame, int y, uint32_t *out,
-                                                 uint16_t *V) {
-  int y0, y1;
-  box_range(y, p.src_h, p.rows_px, y0, y1);
-  const int R = p.src_w * 3;
-  const int nchunk = R >> 4;
-  const uint4 *band = reinterpret_cast<const uint4 *>(frame + (size_t)y0 * (size_t)R);
-  const int nrow = y1 - y0;
-  for (int c = threadIdx.x; c < nchunk; c += BLOCK) {
-    uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const uint4 *q = band + c;
-    // One batch of kBandUnroll independent, predicated 16-byte loads per trip: a typical band (11-12 rows at
-    // 4K -> 192 pixel rows) is a single trip, i.e. one memory latency per column instead of one per tail row.
-    for (int r = 0; r < nrow; r += kBandUnroll) {
-      uint4 v[kBandUnroll];
-#pragma unroll
-      for (int k = 0; k < kBandUnroll; k++) {
-        if (r + k < nrow)
-          v[k] = ldg_stream(q + (size_t)k * nchunk);
-        else
-          v[k] = make_uint4(0u, 0u, 0u, 0u);
-      }
-      q += (size_t)kBandUnroll * nchunk;
-#pragma unroll
-      for (int k = 0; k < kBandUnroll; k++) acc16(a, v[k]);
-    }
-    // byte j of word k is column 16c + 4k + j:  even reg = {b0 | b2<<16}, odd reg = {b1 | b3<<16}
-    uint4 lo, hi;
-    lo.x = __byte_perm(a[0], a[1], 0x5410); // b0,b1
-    lo.y = __byte_perm(a[0], a[1], 0x7632); // b2,b3
-    lo.z = __byte_perm(a[2], a[3], 0x5410);
-    lo.w = __byte_perm(a[2], a[3], 0x7632);
-    hi.x = __byte_perm(a[4], a[5], 0x5410);
-    hi.y = __byte_perm(a[4], a[5], 0x7632);
-    hi.z = __byte_perm(a[6], a[7], 0x5410);
-    hi.w = __byte_perm(a[6], a[7], 0x7632);
-    uint4 *dst = reinterpret_cast<uint4 *>(V + (size_t)c * 16);
-    dst[0] = lo;
-    dst[1] = hi;
-  }
-  __syncthreads();
-  for (int x = threadIdx.x; x < p.cols; x += BLOCK) {
-    int x0, x1;
-    box_range(x, p.src_w, p.cols, x0, x1);
-    uint32_t sr = 0, sg = 0, sb = 0;
-    const uint16_t *q = V + 3 * x0;
-    for (int xx = x0; xx < x1; xx++, q += 3) {
-      sr += q[0];
-      sg += q[1];
-      sb += q[2];
-    }
-    uint32_t n = (uint32_t)(x1 - x0) * (uint32_t)nrow, h = n >> 1;
-    out[x] = (((sr + h) / n) << 16) | (((sg + h) / n) << 8) | ((sb + h) / n);
-  }
-  __syncthreads(); // V is reused by the next pixel row
-}
-
-// ------------------------------------------------------------------ phase B: per-cell emission
-struct RowCtx {
-  const GlyphLut *lut;
-  const uint32_t *cT, *cB;
-  const uint16_t *key, *hpos, *rend;
-};
-
-template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int x, const RowCtx &c) {
-  if (MODE == EM_256_FG) {
-    uint32_t px = c.cT[x];
-    put_sgr_256(s, false, (uint32_t)q256_of(px));
-    put_glyph(s, c.lut->glyph[luma_of(px)]);
-  } else if (MODE == EM_16_FG) {
-    uint32_t px = c.cT[x];
-    put_sgr_16(s, false, (uint32_t)q16_of(px));
-    put_glyph(s, c.lut->glyph[luma_of(px)]);
-  } else if (MODE == EM_TRUE_FG) {
-    // ansi_rle_add_pixel (ansi.c:261-300) as a cell rule; hpos[x] = previous ASCII-glyph cell of this row
-    uint32_t px = c.cT[x];
-    const uint8_t *g = c.lut->glyph[luma_of(px)];
-    bool ascii = g[0] == 1 && g[1] < 128;
-    if (ascii) {
-      uint16_t pa = c.hpos[x];
-      if (pa == NONE16 || c.cT[pa] != px) put_sgr_rgb(s, false, px);
-      s.put(g[1]);
-    } else {
-      put_sgr_rgb(s, false, px);
-      put_glyph(s, g);
-    }
-  } else if (MODE == EM_MONO_FG) {
-    int h = c.hpos[x];
-    uint32_t run = (uint32_t)c.rend[h] - (uint32_t)h;
-    bool rep = rep_profitable(run);
-    const uint8_t *g = c.lut->glyph[luma_of(c.cT[x])]; // same glyph for every cell of the run (same key)
-    if (h == x) {
-      put_glyph(s, g);
-      if (rep) put_rep(s, run - 1);
-    } else if (!rep) {
-      put_glyph(s, g);
-    }
-  } else if (MODE == EM_HB_MONO) {
-    int h = c.hpos[x];
-    uint32_t run = (uint32_t)c.rend[h] - (uint32_t)h;
-    bool rep = rep_profitable(run);
-    int lt = luma76_of(c.cT[h]), lb = luma76_of(c.cB[h]);
-    if (lt < 16 && lb < 16) {
-      s.put(' ');
-    } else if (h == x || !rep) {
-      const uint8_t sh = (uint8_t)((lt >> 6) == 0 ? 0x91 : (lt >> 6) == 1 ? 0x92 : (lt >> 6) == 2 ? 0x93 : 0x88);
-      put3(s, 0xE2, 0x96, sh);
-      if (h == x && rep) put_rep(s, run - 1);
-    }
-  } else { // EM_HB_TRUE / EM_HB_256 / EM_HB_16
-    int h = c.hpos[x];
-    uint32_t run = (uint32_t)c.rend[h] - (uint32_t)h;
-    bool rep = rep_profitable(run);
-    uint32_t tH = c.cT[h], bH = c.cB[h];
-    bool prev_set = false;
-    int ph = 0;
-    if (h > 0) {
-      ph = c.hpos[h - 1];
-      prev_set = (c.cT[ph] | c.cB[ph]) != 0u; // a transparent run leaves the colour state cleared
-    }
-    if ((tH | bH) == 0u) { // transparent: decided by the run head's raw RGB (halfblock.c:111,357,476)
-      if (h == x && prev_set) put_reset(s);
-      s.put(' ');
-    } else if (h == x) {
-      if (MODE == EM_HB_TRUE) {
-        if (!prev_set || c.cT[ph] != tH) put_sgr_rgb(s, false, tH);
-        if (!prev_set || c.cB[ph] != bH) put_sgr_rgb(s, true, bH);
-      } else {
-        uint32_t k = c.key[h], pk = prev_set ? c.key[ph] : 0u;
-        if (MODE == EM_HB_256) {
-          if (!prev_set || (pk >> 8) != (k >> 8)) put_sgr_256(s, false, k >> 8);
-          if (!prev_set || (pk & 255u) != (k & 255u)) put_sgr_256(s, true, k & 255u);
-        } else {
-          if (!prev_set || (pk >> 8) != (k >> 8)) put_sgr_16(s, false, k >> 8);
-          if (!prev_set || (pk & 255u) != (k & 255u)) put_sgr_16(s, true, k & 255u);
-        }
-      }
-      put3(s, 0xE2, 0x96, 0x80);
-      if (rep) put_rep(s, run - 1);
-    } else if (!rep) {
-      put3(s, 0xE2, 0x96, 0x80);
-    }
-  }
-}
-
-// Phase B for one text row whose resized pixels are in cT/cB: keys -> runs -> byte counts -> offsets -> bytes,
-// staged in shared memory (or written straight to the scratch row when it is too wide) and copied out.
-template <int MODE, class Sync>
-__device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT, uint32_t *cB,
-                                         uint16_t *key, uint16_t *hpos, uint16_t *rend, uint32_t *off, uint8_t *outb,
-                                         int *s_tmp, uint32_t *s_cond) {
-  constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
-  constexpr bool RUNS = MODE == EM_MONO_FG || HB;
-  const int tid = threadIdx.x;
-  const int w = p.cols;
-  const bool last_row = t == p.text_rows - 1;
-  if (tid < 4) s_cond[tid] = 0u;
-  Sync::sync();
-
-  // ---- phase B1: run keys
-  if (MODE == EM_MONO_FG) {
-    for (int x = tid; x < w; x += BLOCK) key[x] = lut->key[luma_of(cT[x])];
-  } else if (MODE == EM_HB_256) {
-    for (int x = tid; x < w; x += BLOCK) key[x] = (uint16_t)((q256_of(cT[x]) << 8) | q256_of(cB[x]));
-  } else if (MODE == EM_HB_16) {
-    for (int x = tid; x < w; x += BLOCK) key[x] = (uint16_t)((q16_of(cT[x]) << 8) | q16_of(cB[x]));
-  }
-  Sync::sync();
-
-  // ---- phase B2: run heads / previous-ASCII links
-  if (RUNS) {
-    auto is_head = [&](int x) -> bool {
-      if (x == 0) return true;
-      if (MODE == EM_HB_TRUE || MODE == EM_HB_MONO) return cT[x] != cT[x - 1] || cB[x] != cB[x - 1];
-      return key[x] != key[x - 1];
-    };
-    row_scan<OpMax, Sync>(
-        w, [&](int x) { return is_head(x) ? x : -1; }, [&](int x, int incl, int) { hpos[x] = (uint16_t)incl; },
-        s_tmp);
-    Sync::sync();
-    for (int x = tid; x < w; x += BLOCK) {
-      if (x > 0 && hpos[x] == x) rend[hpos[x - 1]] = (uint16_t)x; // this head closes the previous run
-      if (x == w - 1) rend[hpos[x]] = (uint16_t)w;
-    }
-    Sync::sync();
-  } else if (MODE == EM_TRUE_FG) {
-    int last_ascii = row_scan<OpMax, Sync>(
-        w,
-        [&](int x) {
-          const uint8_t *g = lut->glyph[luma_of(cT[x])];
-          return (g[0] == 1 && g[1] < 128) ? x : -1;
-        },
-        [&](int x, int, int excl) { hpos[x] = excl < 0 ? NONE16 : (uint16_t)excl; }, s_tmp);
-    if (tid == 0) s_cond[2] = last_ascii >= 0 ? (0x01000000u | cT[last_ascii]) : 0u;
-  }
-
-  // ---- phase B3: byte counts -> offsets
-  RowCtx ctx{lut, cT, cB, key, hpos, rend};
-  int cells_bytes = row_scan<OpAdd, Sync>(
-      w,
-      [&](int x) {
-        CountSink cs;
-        emit_cell<MODE>(cs, x, ctx);
-        return (int)cs.n;
-      },
-      [&](int x, int, int excl) { off[x] = (uint32_t)excl + (uint32_t)p.pad_left; }, s_tmp);
-  const uint32_t body_end = (uint32_t)p.pad_left + (uint32_t)cells_bytes;
-
-  // ---- phase B4: materialise
-  uint8_t *grow = p.rows + ((size_t)f * p.text_rows + t) * (size_t)p.row_pitch;
-  uint8_t *base = p.use_smem_out ? outb : grow;
-  for (int i = tid; i < p.pad_left; i += BLOCK) base[i] = ' ';
-  for (int x = tid; x < w; x += BLOCK) {
-    WriteSink ws{base + off[x]};
-    emit_cell<MODE>(ws, x, ctx);
-    if (MODE == EM_TRUE_FG && hpos[x] == NONE16) {
-      const uint8_t *g = lut->glyph[luma_of(cT[x])];
-      if (g[0] == 1 && g[1] < 128) { // the row's first ASCII-glyph cell: its SGR is conditional on the row above
-        CountSink cs;
-        put_sgr_rgb(cs, false, cT[x]);
-        s_cond[0] = off[x];
-        s_cond[1] = cs.n;
-        s_cond[3] = 0x01000000u | cT[x];
-      }
-    }
-  }
-  uint32_t len = body_end;
-  if (tid == 0) {
-    WriteSink ws{base + body_end};
-    if (MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16)
-      put_reset(ws);
-    if (MODE == EM_TRUE_FG && last_row) put_reset(ws); // ansi_rle_finish, ansi.c:303-314
-    if (!last_row) ws.put('\n');
-    len = (uint32_t)(ws.p - base);
-  }
-  Sync::sync();
-  if (tid == 0) {
-    RowMeta m;
-    m.len = len;
-    m.cond_off = s_cond[0];
-    m.cond_len = s_cond[1];
-    m.first_rgb = s_cond[3];
-    m.last_rgb = s_cond[2];
-    m._pad[0] = m._pad[1] = m._pad[2] = 0;
-    p.meta[(size_t)f * p.text_rows + t] = m;
-    s_cond[0] = len;
-  }
-  Sync::sync();
-  if (p.use_smem_out) {
-    const uint32_t n16 = (s_cond[0] + 15u) >> 4;
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(outb);
-    uint4 *d4 = reinterpret_cast<uint4 *>(grow);
-    for (uint32_t i = tid; i < n16; i += BLOCK) d4[i] = s4[i];
-  }
-}
-
-template <int MODE, int SP> __global__ void __launch_bounds__(BLOCK) k_render_rows(const RenderParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ int s_tmp[NWARP + 1];
-  __shared__ uint32_t s_cond[4]; // TRUE_FG: {cond_off, cond_len, last_rgb, first_rgb}
-
-  constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
-  constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
-
-  const int tid = threadIdx.x;
-  const int t = (int)(blockIdx.x % (unsigned)p.text_rows);
-  const int f = (int)(blockIdx.x / (unsigned)p.text_rows);
-  const int w = p.cols;
-
-  const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
-  const Layout L = make_layout(MODE, SP, w, p.src_w, cap, p.tune_flags & 1);
-  GlyphLut *lut = reinterpret_cast<GlyphLut *>(smem + L.lut);
-  uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.cT);
-  uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.cB);
-  uint16_t *key = reinterpret_cast<uint16_t *>(smem + L.key);
-  uint16_t *hpos = reinterpret_cast<uint16_t *>(smem + L.hpos);
-  uint16_t *rend = reinterpret_cast<uint16_t *>(smem + L.rend);
-  uint32_t *off = reinterpret_cast<uint32_t *>(smem + L.off);
-  uint16_t *V = reinterpret_cast<uint16_t *>(smem + L.V);
-  uint8_t *outb = smem + L.outb;
-
-  if (USES_LUT) {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(lut);
-    for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += BLOCK) dst[i] = src[i];
-  }
-
-  // ---- phase A
-  const uint8_t *frame = p.frames + (size_t)f * p.frame_stride;
-  const int yT = HB ? 2 * t : t;
-  const bool hasB = HB && (2 * t + 1 < p.rows_px);
-  if (SP == SP_NN) {
-    cells_nn(p, frame, yT, cT);
-    if (hasB) cells_nn(p, frame, yT + 1, cB);
-  } else if (SP == SP_BOX_GENERIC) {
-    cells_box_generic(p, frame, yT, cT);
-    if (hasB) cells_box_generic(p, frame, yT + 1, cB);
-  } else {
-    cells_box_stream(p, frame, yT, cT, V);
-    if (hasB) cells_box_stream(p, frame, yT + 1, cB, V);
-  }
-  __syncthreads();
-  if (HB && !hasB) { // odd pixel height: bottom := top (halfblock.c:73,82-88)
-    for (int x = tid; x < w; x += BLOCK) cB[x] = cT[x];
-    __syncthreads();
-  }
-  if (p.cells_out) {
-    uint8_t *co = p.cells_out + ((size_t)f * p.rows_px + yT) * (size_t)w * 3u;
-    for (int x = tid; x < w; x += BLOCK) {
-      uint32_t c = cT[x];
-      co[3 * x] = (uint8_t)(c >> 16);
-      co[3 * x + 1] = (uint8_t)(c >> 8);
-      co[3 * x + 2] = (uint8_t)c;
-      if (hasB) {
-        uint32_t d = cB[x];
-        uint8_t *cb = co + (size_t)w * 3u;
-        cb[3 * x] = (uint8_t)(d >> 16);
-        cb[3 * x + 1] = (uint8_t)(d >> 8);
-        cb[3 * x + 2] = (uint8_t)d;
-      }
-    }
-  }
-  if (p.rows == nullptr) return; // resize-only invocation
-
-  emit_row<MODE, SyncAll>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond);
-}
-
-// ------------------------------------------------------------------ warp-specialised persistent row kernel
-// Box-filter streaming with the copy engine instead of the LSU: a producer warp keeps a ring of whole source rows
-// in flight with 1-D bulk TMA copies (cp.async.bulk, completion on an mbarrier), eight consumer warps sum the rows
-// out of shared memory and then emit the text row.  CTAs are persistent (tile = blockIdx.x + k*gridDim.x over
-// (frame, text row)), so while the consumers are in the emission phase of tile k the producer is already filling
-// the ring with the first rows of tile k+1: HBM traffic never pauses for the byte-emission work.
-//
-//   full[s]  : producer arms it with expect_tx(row bytes); the bulk copy completes it        (count 1 + tx)
-//   empty[s] : one arrival per consumer warp when the warp has read slot s                   (count 8)
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(done)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-constexpr int WS_THREADS = BLOCK + 32; // 8 consumer warps + 1 producer warp
-constexpr int WS_MAXD = 16;            // ring slots (source rows) at most
-
-struct WsBand {
-  int a0, a1, b1; // top pixel row sums source rows [a0,a1), bottom [a1,b1)  (contiguous when downscaling)
-  bool hasB;
-};
-template <bool HB> __device__ __forceinline__ WsBand ws_band(const RenderParams &p, int t) {
-  WsBand b;
-  const int yT = HB ? 2 * t : t;
-  box_range(yT, p.src_h, p.rows_px, b.a0, b.a1);
-  b.hasB = HB && (2 * t + 1 < p.rows_px);
-  b.b1 = b.a1;
-  if (b.hasB) {
-    int b0;
-    box_range(yT + 1, p.src_h, p.rows_px, b0, b.b1);
-  }
-  return b;
-}
-
-template <int MODE, int CPT>
-__global__ void __launch_bounds__(WS_THREADS) k_render_rows_ws(const RenderParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ int s_tmp[NWARP + 1];
-  __shared__ uint32_t s_cond[4];
-  __shared__ __align__(8) uint64_t s_full[WS_MAXD], s_empty[WS_MAXD];
-
-  constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
-  constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int w = p.cols;
-  const uint32_t R = (uint32_t)p.src_w * 3u;
-  const int nchunk = (int)(R >> 4);
-  const uint32_t D = (uint32_t)p.ring_depth;
-  const int total = p.n_frames * p.text_rows;
-
-  const Layout L = make_layout(MODE, SP_BOX_STREAM, w, p.src_w, p.row_pitch, 0);
-  GlyphLut *lut = reinterpret_cast<GlyphLut *>(smem + L.lut);
-  uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.cT);
-  uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.cB);
-  uint16_t *key = reinterpret_cast<uint16_t *>(smem + L.key);
-  uint16_t *hpos = reinterpret_cast<uint16_t *>(smem + L.hpos);
-  uint16_t *rend = reinterpret_cast<uint16_t *>(smem + L.rend);
-  uint32_t *off = reinterpret_cast<uint32_t *>(smem + L.off);
-  uint16_t *V = reinterpret_cast<uint16_t *>(smem + L.V);
-  uint8_t *outb = smem + L.outb;
-  uint8_t *ring = smem + ((L.total + 127u) & ~127u);
-
-  if (tid == 0) {
-    for (uint32_t s = 0; s < D; s++) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], NWARP);
-    }
-    mbar_fence_init();
-  }
-  if (USES_LUT && tid < BLOCK) {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(lut);
-    for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += BLOCK) dst[i] = src[i];
-  }
-  __syncthreads(); // the only CTA-wide barrier: after it the producer warp and the consumer warps part ways
-
-  if (warp == NWARP) { // ---------------- producer: one lane walks the same tile/row sequence as the consumers
-    if (lane == 0) {
-      uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int t = tile % p.text_rows, f = tile / p.text_rows;
-        const WsBand b = ws_band<HB>(p, t);
-        const uint8_t *src = p.frames + (size_t)f * p.frame_stride + (size_t)b.a0 * R;
-        for (int r = b.a0; r < b.b1; r++, g++, src += R) {
-          const uint32_t slot = g % D, ph = (g / D) & 1u;
-          mbar_wait(&s_empty[slot], ph ^ 1u); // a fresh barrier passes the parity-1 wait: the ring starts empty
-          mbar_expect_tx(&s_full[slot], R);
-          bulk_g2s(ring + (size_t)slot * R, src, R, &s_full[slot]);
-        }
-      }
-    }
-    return;
-  }
-
-  // ---------------- consumers (threads 0..255)
-  uint32_t g = 0;
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const int t = tile % p.text_rows, f = tile / p.text_rows;
-    const WsBand b = ws_band<HB>(p, t);
-#pragma unroll 1
-    for (int half = 0; half < (HB ? 2 : 1); half++) {
-      uint32_t *out = half ? cB : cT;
-      if (half && !b.hasB) { // odd pixel height: bottom := top (halfblock.c:73,82-88)
-        for (int x = tid; x < w; x += BLOCK) cB[x] = cT[x];
-        break;
-      }
-      const int r0 = half ? b.a1 : b.a0, r1 = half ? b.b1 : b.a1;
-      uint32_t a[CPT][8];
-#pragma unroll
-      for (int j = 0; j < CPT; j++)
-#pragma unroll
-        for (int k = 0; k < 8; k++) a[j][k] = 0u;
-      for (int r = r0; r < r1; r++, g++) {
-        const uint32_t slot = g % D, ph = (g / D) & 1u;
-        mbar_wait(&s_full[slot], ph);
-        const uint4 *row = reinterpret_cast<const uint4 *>(ring + (size_t)slot * R);
-#pragma unroll
-        for (int j = 0; j < CPT; j++) {
-          const int c = tid + j * BLOCK;
-          if (c < nchunk) acc16(a[j], row[c]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[slot]);
-      }
-#pragma unroll
-      for (int j = 0; j < CPT; j++) {
-        const int c = tid + j * BLOCK;
-        if (c < nchunk) {
-          uint4 lo, hi;
-          lo.x = __byte_perm(a[j][0], a[j][1], 0x5410);
-          lo.y = __byte_perm(a[j][0], a[j][1], 0x7632);
-          lo.z = __byte_perm(a[j][2], a[j][3], 0x5410);
-          lo.w = __byte_perm(a[j][2], a[j][3], 0x7632);
-          hi.x = __byte_perm(a[j][4], a[j][5], 0x5410);
-          hi.y = __byte_perm(a[j][4], a[j][5], 0x7632);
-          hi.z = __byte_perm(a[j][6], a[j][7], 0x5410);
-          hi.w = __byte_perm(a[j][6], a[j][7], 0x7632);
-          uint4 *dst = reinterpret_cast<uint4 *>(V + (size_t)c * 16);
-          dst[0] = lo;
-          dst[1] = hi;
-        }
-      }
-      SyncConsumers::sync();
-      const uint32_t nrow = (uint32_t)(r1 - r0);
-      for (int x = tid; x < w; x += BLOCK) {
-        int x0, x1;
-        box_range(x, p.src_w, p.cols, x0, x1);
-        uint32_t sr = 0, sg = 0, sb = 0;
-        const uint16_t *q = V + 3 * x0;
-        for (int xx = x0; xx < x1; xx++, q += 3) {
-          sr += q[0];
-          sg += q[1];
-          sb += q[2];
-        }
-        const uint32_t n = (uint32_t)(x1 - x0) * nrow, h = n >> 1;
-        out[x] = (((sr + h) / n) << 16) | (((sg + h) / n) << 8) | ((sb + h) / n);
-      }
-      SyncConsumers::sync(); // V is reused by the other pixel row / aliased by the row staging buffer
-    }
-    SyncConsumers::sync();
-    emit_row<MODE, SyncConsumers>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond);
-    SyncConsumers::sync(); // the staging buffer aliases V: finish copying out before the next tile's sums land
-  }
-}
 
 // ------------------------------------------------------------------ stitch rows -> frame string
 // Block-cooperative copy of n bytes for any mutual alignment: destination-aligned 4-byte stores assembled from
@@ -1044,90 +235,46 @@ __global__ void __launch_bounds__(256) k_dither_bg(const uint8_t *cells, int w, 
 }
 
 // ------------------------------------------------------------------ launchers
-template <int MODE, int SP> static cudaError_t launch_rows_t(const RenderParams &p, cudaStream_t st) {
-  const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
-  const Layout L = make_layout(MODE, SP, p.cols, p.src_w, cap, p.tune_flags & 1);
-  if (L.total > kMaxDynSmem) return cudaErrorInvalidConfiguration;
-  static bool configured = false; // benign race: the attribute is idempotent
-  if (!configured) {
-    // opt-in limit is 227 KB per CTA for static + dynamic together; the kernel has < 1 KB static
-    cudaError_t e = cudaFuncSetAttribute(k_render_rows<MODE, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kMaxDynSmem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  const unsigned grid = (unsigned)p.n_frames * (unsigned)p.text_rows;
-  k_render_rows<MODE, SP><<<grid, BLOCK, L.total, st>>>(p);
-  return cudaGetLastError();
-}
-
-template <int MODE> static cudaError_t launch_rows_sp(const RenderParams &p, int sp, cudaStream_t st) {
-  switch (sp) {
-  case SP_NN: return launch_rows_t<MODE, SP_NN>(p, st);
-  case SP_BOX_GENERIC: return launch_rows_t<MODE, SP_BOX_GENERIC>(p, st);
-  default: return launch_rows_t<MODE, SP_BOX_STREAM>(p, st);
-  }
-}
+cudaError_t launch_rows_m0(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_ws_m0(const RenderParams &p, cudaStream_t st);
+cudaError_t launch_rows_m1(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_ws_m1(const RenderParams &p, cudaStream_t st);
+cudaError_t launch_rows_m2(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_ws_m2(const RenderParams &p, cudaStream_t st);
+cudaError_t launch_rows_m3(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_ws_m3(const RenderParams &p, cudaStream_t st);
+cudaError_t launch_rows_m4(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_ws_m4(const RenderParams &p, cudaStream_t st);
+cudaError_t launch_rows_m5(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_ws_m5(const RenderParams &p, cudaStream_t st);
+cudaError_t launch_rows_m6(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_ws_m6(const RenderParams &p, cudaStream_t st);
+cudaError_t launch_rows_m7(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_ws_m7(const RenderParams &p, cudaStream_t st);
 
 cudaError_t launch_render_rows(const RenderParams &p, int mode, int sp, cudaStream_t st) {
   switch (mode) {
-  case EM_MONO_FG: return launch_rows_sp<EM_MONO_FG>(p, sp, st);
-  case EM_256_FG: return launch_rows_sp<EM_256_FG>(p, sp, st);
-  case EM_16_FG: return launch_rows_sp<EM_16_FG>(p, sp, st);
-  case EM_TRUE_FG: return launch_rows_sp<EM_TRUE_FG>(p, sp, st);
-  case EM_HB_TRUE: return launch_rows_sp<EM_HB_TRUE>(p, sp, st);
-  case EM_HB_256: return launch_rows_sp<EM_HB_256>(p, sp, st);
-  case EM_HB_16: return launch_rows_sp<EM_HB_16>(p, sp, st);
-  case EM_HB_MONO: return launch_rows_sp<EM_HB_MONO>(p, sp, st);
+  case EM_MONO_FG: return launch_rows_m0(p, sp, st);
+  case EM_256_FG: return launch_rows_m1(p, sp, st);
+  case EM_16_FG: return launch_rows_m2(p, sp, st);
+  case EM_TRUE_FG: return launch_rows_m3(p, sp, st);
+  case EM_HB_TRUE: return launch_rows_m4(p, sp, st);
+  case EM_HB_256: return launch_rows_m5(p, sp, st);
+  case EM_HB_16: return launch_rows_m6(p, sp, st);
+  case EM_HB_MONO: return launch_rows_m7(p, sp, st);
   default: return cudaErrorInvalidValue;
   }
 }
-
-template <int MODE, int CPT> static cudaError_t launch_ws_t(const RenderParams &p, cudaStream_t st) {
-  const Layout L = make_layout(MODE, SP_BOX_STREAM, p.cols, p.src_w, p.row_pitch, 0);
-  const size_t smem = ((L.total + 127u) & ~127u) + (size_t)p.ring_depth * p.src_w * 3u;
-  if (smem > kMaxDynSmem) return cudaErrorInvalidConfiguration;
-  static bool configured = false;
-  static int ctas_per_sm = 1, sms = 148;
-  static size_t cfg_smem = 0;
-  if (!configured || smem != cfg_smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_render_rows_ws<MODE, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kMaxDynSmem);
-    if (e != cudaSuccess) return e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_render_rows_ws<MODE, CPT>, WS_THREADS, smem);
-    if (e != cudaSuccess || ctas_per_sm < 1) return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
-    cfg_smem = smem;
-    configured = true;
-  }
-  const long long total = (long long)p.n_frames * p.text_rows;
-  long long grid = (long long)sms * ctas_per_sm;
-  if (grid > total) grid = total;
-  k_render_rows_ws<MODE, CPT><<<(unsigned)grid, WS_THREADS, smem, st>>>(p);
-  return cudaGetLastError();
-}
-template <int MODE> static cudaError_t launch_ws_cpt(const RenderParams &p, cudaStream_t st) {
-  const int nchunk = (p.src_w * 3) >> 4;
-  const int cpt = (nchunk + BLOCK - 1) / BLOCK;
-  if (cpt <= 1) return launch_ws_t<MODE, 1>(p, st);
-  if (cpt <= 2) return launch_ws_t<MODE, 2>(p, st);
-  if (cpt <= 3) return launch_ws_t<MODE, 3>(p, st);
-  if (cpt <= 4) return launch_ws_t<MODE, 4>(p, st);
-  if (cpt <= 8) return launch_ws_t<MODE, 8>(p, st);
-  return cudaErrorInvalidConfiguration;
-}
 cudaError_t launch_render_rows_ws(const RenderParams &p, int mode, cudaStream_t st) {
   switch (mode) {
-  case EM_MONO_FG: return launch_ws_cpt<EM_MONO_FG>(p, st);
-  case EM_256_FG: return launch_ws_cpt<EM_256_FG>(p, st);
-  case EM_16_FG: return launch_ws_cpt<EM_16_FG>(p, st);
-  case EM_TRUE_FG: return launch_ws_cpt<EM_TRUE_FG>(p, st);
-  case EM_HB_TRUE: return launch_ws_cpt<EM_HB_TRUE>(p, st);
-  case EM_HB_256: return launch_ws_cpt<EM_HB_256>(p, st);
-  case EM_HB_16: return launch_ws_cpt<EM_HB_16>(p, st);
-  case EM_HB_MONO: return launch_ws_cpt<EM_HB_MONO>(p, st);
+  case EM_MONO_FG: return launch_ws_m0(p, st);
+  case EM_256_FG: return launch_ws_m1(p, st);
+  case EM_16_FG: return launch_ws_m2(p, st);
+  case EM_TRUE_FG: return launch_ws_m3(p, st);
+  case EM_HB_TRUE: return launch_ws_m4(p, st);
+  case EM_HB_256: return launch_ws_m5(p, st);
+  case EM_HB_16: return launch_ws_m6(p, st);
+  case EM_HB_MONO: return launch_ws_m7(p, st);
   default: return cudaErrorInvalidValue;
   }
 }
