@@ -1,6 +1,8 @@
 // render_dev.cuh — device code of the row kernels (templates), shared by the per-mode instantiation units
 // (rk_mode*.cu) and render_kernels.cu.  See render_kernels.cu for the overview.
 #pragma once
+#include <cstdlib>
+
 #include "render.cuh"
 
 namespace acb {
@@ -56,6 +58,13 @@ struct CountSink {
 struct WriteSink {
   uint8_t *p;
   __device__ __forceinline__ void put(uint8_t c) { *p++ = c; }
+};
+struct SmemSink { // same, but the destination is known to be shared memory: STS with a 32-bit address
+  uint32_t a;
+  __device__ __forceinline__ void put(uint8_t c) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"((uint32_t)c) : "memory");
+    ++a;
+  }
 };
 
 template <class S> __device__ __forceinline__ void put_u8dec(S &s, uint32_t v) { // dec3 table, common.c:546-570
@@ -325,19 +334,20 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
   const int nrow = y1 - y0;
   for (int c = threadIdx.x; c < nchunk; c += NT) {
     uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const uint4 *q = band + c;
+    const uint8_t *q = reinterpret_cast<const uint8_t *>(band + c);
     // One batch of kBandUnroll independent, predicated 16-byte loads per trip: a typical band (11-12 rows at
     // 4K -> 192 pixel rows) is a single trip, i.e. one memory latency per column instead of one per tail row.
+    // The row pointer advances by the 32-bit row pitch (one wide multiply-add per load, no 64-bit index maths).
     for (int r = 0; r < nrow; r += kBandUnroll) {
       uint4 v[kBandUnroll];
 #pragma unroll
       for (int k = 0; k < kBandUnroll; k++) {
         if (r + k < nrow)
-          v[k] = ldg_stream(q + (size_t)k * nchunk);
+          v[k] = ldg_stream(reinterpret_cast<const uint4 *>(q));
         else
           v[k] = make_uint4(0u, 0u, 0u, 0u);
+        q += (uint32_t)R;
       }
-      q += (size_t)kBandUnroll * nchunk;
 #pragma unroll
       for (int k = 0; k < kBandUnroll; k += 2) acc16x2(a, v[k], v[k + 1]);
     }
@@ -361,6 +371,7 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
     box_range(x, p.src_w, p.cols, x0, x1);
     uint32_t sr = 0, sg = 0, sb = 0;
     const uint16_t *q = V + 3 * x0;
+#pragma unroll 4
     for (int xx = x0; xx < x1; xx++, q += 3) {
       sr += q[0];
       sg += q[1];
@@ -528,8 +539,13 @@ __device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, Gl
   uint8_t *base = p.use_smem_out ? outb : grow;
   for (int i = tid; i < p.pad_left; i += NT) base[i] = ' ';
   for (int x = tid; x < w; x += NT) {
-    WriteSink ws{base + off[x]};
-    emit_cell<MODE>(ws, x, ctx);
+    if (p.use_smem_out) {
+      SmemSink ss{(uint32_t)__cvta_generic_to_shared(outb) + off[x]};
+      emit_cell<MODE>(ss, x, ctx);
+    } else {
+      WriteSink ws{base + off[x]};
+      emit_cell<MODE>(ws, x, ctx);
+    }
     if (MODE == EM_TRUE_FG && hpos[x] == NONE16) {
       const uint8_t *g = lut->glyph[luma_of(cT[x])];
       if (g[0] == 1 && g[1] < 128) { // the row's first ASCII-glyph cell: its SGR is conditional on the row above
@@ -825,6 +841,7 @@ __global__ void __launch_bounds__(NT + 32) k_render_rows_ws(const RenderParams p
         box_range(x, p.src_w, p.cols, x0, x1);
         uint32_t sr = 0, sg = 0, sb = 0;
         const uint16_t *q = V + 3 * x0;
+#pragma unroll 4
         for (int xx = x0; xx < x1; xx++, q += 3) {
           sr += q[0];
           sg += q[1];
@@ -844,7 +861,9 @@ __global__ void __launch_bounds__(NT + 32) k_render_rows_ws(const RenderParams p
 // ------------------------------------------------------------------ per-mode launch templates
 // NT (threads that own cells / byte columns) is chosen so that one pass of the CTA covers the text row:
 // 128, 256, 384 or 512.
-__host__ inline int pick_nt(int cols) { return cols <= 128 ? 128 : cols <= 256 ? 256 : cols <= 384 ? 384 : 512; }
+// (measured on B200: 256 threads beat 384/512 for the one-tile-per-CTA kernels even when the row then needs two
+// passes, because five CTAs per SM keep more loads in flight than three)
+__host__ inline int pick_nt(int cols) { return cols <= 128 ? 128 : 256; }
 
 template <int MODE, int SP, int NT> static cudaError_t launch_rows_t(const RenderParams &p, cudaStream_t st) {
   const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
@@ -865,9 +884,7 @@ template <int MODE, int SP, int NT> static cudaError_t launch_rows_t(const Rende
 template <int MODE, int SP> static cudaError_t launch_rows_nt(const RenderParams &p, cudaStream_t st) {
   switch (pick_nt(p.cols)) {
   case 128: return launch_rows_t<MODE, SP, 128>(p, st);
-  case 256: return launch_rows_t<MODE, SP, 256>(p, st);
-  case 384: return launch_rows_t<MODE, SP, 384>(p, st);
-  default: return launch_rows_t<MODE, SP, 512>(p, st);
+  default: return launch_rows_t<MODE, SP, 256>(p, st);
   }
 }
 template <int MODE> static cudaError_t launch_rows_mode(const RenderParams &p, int sp, cudaStream_t st) {
@@ -915,6 +932,8 @@ template <int MODE, int NT> static cudaError_t launch_ws_cpt(const RenderParams 
 // the warp-specialised kernel always runs with >= 256 consumer threads (the sums need the issue slots)
 __host__ inline int pick_ws_nt(int cols, int src_w) {
   int nt = cols <= 256 ? 256 : cols <= 384 ? 384 : 512;
+  static const int nt_env = getenv("ACB200_WS_NT") ? atoi(getenv("ACB200_WS_NT")) : 0; // tuning knob
+  if (nt_env == 256 || nt_env == 384 || nt_env == 512) nt = nt_env;
   while (nt < 512 && (((src_w * 3) >> 4) + nt - 1) / nt > 4) nt += 128;
   return nt;
 }
