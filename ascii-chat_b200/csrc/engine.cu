@@ -301,17 +301,22 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
   }
   pl.scale_path = sp;
   pl.ring_depth = 0;
-  // Warp-specialised persistent kernel (bulk-TMA row ring): downscaling box filter whose rows are 16-byte multiples
-  // and whose text row fits the shared staging buffer.  ACB200_NO_TMA=1 keeps the one-tile-per-CTA kernel (A/B knob).
-  static const int no_tma = getenv("ACB200_NO_TMA") ? atoi(getenv("ACB200_NO_TMA")) : 0;
-  if (sp == SP_BOX_STREAM && !no_tma && pl.mode != EM_DITHER_BG && pl.use_smem_out && cfg.src_h >= cfg.rows_px &&
-      ((3 * cfg.src_w) >> 4) <= 2048) {
-    int d = ws_ring_depth(pl.mode, cfg.cols, cfg.src_w, pl.row_pitch);
-    static const int d_env = getenv("ACB200_RING_DEPTH") ? atoi(getenv("ACB200_RING_DEPTH")) : 0; // tuning knob
-    if (d_env >= 2 && d_env <= d) d = d_env;
-    if (d >= 2) {
-      pl.scale_path = SP_BOX_TMA;
-      pl.ring_depth = d;
+  // Persistent variants of the streaming box kernel (downscaling geometry whose text row fits the shared staging
+  // buffer).  Default: the role-split kernel (streamer warps + emitter warp).  ACB200_BOX_KERNEL=ldg|tma|split
+  // selects one explicitly (A/B measurements; "ldg" is the one-tile-per-CTA kernel).
+  if (sp == SP_BOX_STREAM && pl.mode != EM_DITHER_BG && pl.use_smem_out && cfg.src_h >= cfg.rows_px) {
+    static const char *which_env = getenv("ACB200_BOX_KERNEL");
+    const char *which = which_env ? which_env : "split";
+    if (!strcmp(which, "split") && ws2_smem_total(cfg.cols, cfg.src_w, pl.row_pitch) <= kMaxDynSmem) {
+      pl.scale_path = SP_BOX_SPLIT;
+    } else if (!strcmp(which, "tma") && ((3 * cfg.src_w) >> 4) <= 2048) {
+      int d = ws_ring_depth(pl.mode, cfg.cols, cfg.src_w, pl.row_pitch);
+      static const int d_env = getenv("ACB200_RING_DEPTH") ? atoi(getenv("ACB200_RING_DEPTH")) : 0; // tuning knob
+      if (d_env >= 2 && d_env <= d) d = d_env;
+      if (d >= 2) {
+        pl.scale_path = SP_BOX_TMA;
+        pl.ring_depth = d;
+      }
     }
   }
   pl.frame_capacity = (((size_t)cfg.pad_top + (size_t)pl.text_rows * pl.row_pitch + 1) + 15) & ~(size_t)15;
@@ -362,17 +367,20 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
   if (phase_a_only && pl.mode != EM_DITHER_BG) { // downscale only: rows == nullptr makes the kernel return after phase A
     rp.rows = nullptr;
     if (k0) cudaEventRecord(k0, st);
-    ACB_CUDA(launch_render_rows(rp, pl.mode, pl.scale_path == SP_BOX_TMA ? (int)SP_BOX_STREAM : pl.scale_path, st));
+    ACB_CUDA(launch_render_rows(rp, pl.mode, pl.scale_path >= SP_BOX_TMA ? (int)SP_BOX_STREAM : pl.scale_path, st));
     if (k1) cudaEventRecord(k1, st);
     count_launch();
     return E_OK;
   }
 
   if (k0) cudaEventRecord(k0, st);
-  const int kernel_sp = pl.scale_path == SP_BOX_TMA ? (int)SP_BOX_STREAM : pl.scale_path;
+  const int kernel_sp = pl.scale_path >= SP_BOX_TMA ? (int)SP_BOX_STREAM : pl.scale_path;
   if (pl.mode != EM_DITHER_BG && pl.scale_path == SP_BOX_TMA) {
     rp.ring_depth = pl.ring_depth;
     ACB_CUDA(launch_render_rows_ws(rp, pl.mode, st));
+    count_launch();
+  } else if (pl.mode != EM_DITHER_BG && pl.scale_path == SP_BOX_SPLIT) {
+    ACB_CUDA(launch_render_rows_ws2(rp, pl.mode, st));
     count_launch();
   } else if (pl.mode != EM_DITHER_BG) {
     ACB_CUDA(launch_render_rows(rp, pl.mode, kernel_sp, st));

@@ -23,7 +23,8 @@ enum ScalePath : int {
   SP_NN = 0,        // nearest neighbour, image.c:267-328
   SP_BOX_GENERIC = 1, // box filter, any geometry (byte loads)
   SP_BOX_STREAM = 2,  // box filter, 16-byte streaming loads (3*src_w % 16 == 0, band <= 256 rows)
-  SP_BOX_TMA = 3      // box filter, persistent warp-specialised kernel: bulk-TMA row ring + consumer warps
+  SP_BOX_TMA = 3,     // box filter, persistent warp-specialised kernel: bulk-TMA row ring + consumer warps
+  SP_BOX_SPLIT = 4    // box filter, persistent role-split kernel: 8 streamer warps + 1 emitter warp
 };
 
 // Brightness -> glyph tables for one (palette, mode) pair, built on the host
@@ -83,6 +84,8 @@ static constexpr uint32_t kMaxDynSmem = 226u * 1024u; // dynamic smem ceiling (2
 
 cudaError_t launch_render_rows(const RenderParams &p, int mode, int scale_path, cudaStream_t st);
 cudaError_t launch_render_rows_ws(const RenderParams &p, int mode, cudaStream_t st);
+cudaError_t launch_render_rows_ws2(const RenderParams &p, int mode, cudaStream_t st);
+size_t ws2_smem_total(int cols, int src_w, uint32_t row_pitch);
 int ws_ring_depth(int mode, int cols, int src_w, uint32_t row_pitch);
 cudaError_t launch_stitch(const StitchParams &p, int n_frames, cudaStream_t st);
 cudaError_t launch_resize_nn_only(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh, int pregathered,

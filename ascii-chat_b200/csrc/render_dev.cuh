@@ -50,6 +50,18 @@ __device__ __forceinline__ bool rep_profitable(uint32_t run) { // output_buffer.
   return k > digits + 3u;
 }
 
+// Barrier policies: the one-tile-per-CTA kernel synchronises the whole CTA; in the warp-specialised persistent
+// kernel only the 8 consumer warps (threads 0..255) take part, on named barrier 1, while the producer warp runs ahead.
+struct SyncAll {
+  static __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+struct SyncWarp { // a single warp owns the data: warp-level barrier only
+  static __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+template <int NT> struct SyncConsumers {
+  static __device__ __forceinline__ void sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+};
+
 // ------------------------------------------------------------------ byte sinks
 struct CountSink {
   uint32_t n = 0;
@@ -154,20 +166,11 @@ struct OpMax {
   static __device__ __forceinline__ int ap(int a, int b) { return a > b ? a : b; }
 };
 
-// Barrier policies: the one-tile-per-CTA kernel synchronises the whole CTA; in the warp-specialised persistent
-// kernel only the 8 consumer warps (threads 0..255) take part, on named barrier 1, while the producer warp runs ahead.
-struct SyncAll {
-  static __device__ __forceinline__ void sync() { __syncthreads(); }
-};
-template <int NT> struct SyncConsumers {
-  static __device__ __forceinline__ void sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
-};
-
 // Scans value_of(x), x in [0,w), in x order over NT threads; calls store(x, inclusive, exclusive).
 // Returns the total (valid in every thread).  s_tmp: (NT / 32)+1 ints of shared memory.
 template <class Op, class Sync, int NT, class F, class G>
-__device__ __forceinline__ int row_scan(int w, F value_of, G store, int *s_tmp) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ int row_scan(int w, F value_of, G store, int *s_tmp, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tmp[(NT / 32)] = Op::id();
   Sync::sync();
   for (int base = 0; base < w; base += NT) {
@@ -323,7 +326,7 @@ __device__ __forceinline__ void acc16x2(uint32_t (&a)[8], const uint4 &u, const 
 // box filter, streaming: the band of source rows [y0,y1) is one contiguous byte range; every thread owns
 // 16-byte columns of it, sums them down the band in registers (u16 lanes, band <= 256 rows), parks the
 // column sums V[3*src_w] in shared memory, then one thread per destination pixel adds its x-range.
-template <int NT>
+template <int NT, class Sync = SyncAll>
 __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const uint8_t *frame, int y, uint32_t *out,
                                                  uint16_t *V) {
   int y0, y1;
@@ -365,7 +368,7 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
     dst[0] = lo;
     dst[1] = hi;
   }
-  __syncthreads();
+  Sync::sync();
   for (int x = threadIdx.x; x < p.cols; x += NT) {
     int x0, x1;
     box_range(x, p.src_w, p.cols, x0, x1);
@@ -380,7 +383,7 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
     uint32_t n = (uint32_t)(x1 - x0) * (uint32_t)nrow, h = n >> 1;
     out[x] = (((sr + h) / n) << 16) | (((sg + h) / n) << 8) | ((sb + h) / n);
   }
-  __syncthreads(); // V is reused by the next pixel row
+  Sync::sync(); // V is reused by the next pixel row
 }
 
 // ------------------------------------------------------------------ phase B: per-cell emission
@@ -476,10 +479,9 @@ template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int
 template <int MODE, class Sync, int NT>
 __device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT, uint32_t *cB,
                                          uint16_t *key, uint16_t *hpos, uint16_t *rend, uint32_t *off, uint8_t *outb,
-                                         int *s_tmp, uint32_t *s_cond) {
+                                         int *s_tmp, uint32_t *s_cond, int tid) {
   constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
   constexpr bool RUNS = MODE == EM_MONO_FG || HB;
-  const int tid = threadIdx.x;
   const int w = p.cols;
   const bool last_row = t == p.text_rows - 1;
   if (tid < 4) s_cond[tid] = 0u;
@@ -504,7 +506,7 @@ __device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, Gl
     };
     row_scan<OpMax, Sync, NT>(
         w, [&](int x) { return is_head(x) ? x : -1; }, [&](int x, int incl, int) { hpos[x] = (uint16_t)incl; },
-        s_tmp);
+        s_tmp, tid);
     Sync::sync();
     for (int x = tid; x < w; x += NT) {
       if (x > 0 && hpos[x] == x) rend[hpos[x - 1]] = (uint16_t)x; // this head closes the previous run
@@ -518,7 +520,7 @@ __device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, Gl
           const uint8_t *g = lut->glyph[luma_of(cT[x])];
           return (g[0] == 1 && g[1] < 128) ? x : -1;
         },
-        [&](int x, int, int excl) { hpos[x] = excl < 0 ? NONE16 : (uint16_t)excl; }, s_tmp);
+        [&](int x, int, int excl) { hpos[x] = excl < 0 ? NONE16 : (uint16_t)excl; }, s_tmp, tid);
     if (tid == 0) s_cond[2] = last_ascii >= 0 ? (0x01000000u | cT[last_ascii]) : 0u;
   }
 
@@ -531,7 +533,7 @@ __device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, Gl
         emit_cell<MODE>(cs, x, ctx);
         return (int)cs.n;
       },
-      [&](int x, int, int excl) { off[x] = (uint32_t)excl + (uint32_t)p.pad_left; }, s_tmp);
+      [&](int x, int, int excl) { off[x] = (uint32_t)excl + (uint32_t)p.pad_left; }, s_tmp, tid);
   const uint32_t body_end = (uint32_t)p.pad_left + (uint32_t)cells_bytes;
 
   // ---- phase B4: materialise
@@ -588,7 +590,7 @@ __device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, Gl
 }
 
 template <int MODE, int SP, int NT> __global__ void __launch_bounds__(NT) k_render_rows(const RenderParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_tmp[(NT / 32) + 1];
   __shared__ uint32_t s_cond[4]; // TRUE_FG: {cond_off, cond_len, last_rgb, first_rgb}
 
@@ -655,7 +657,7 @@ template <int MODE, int SP, int NT> __global__ void __launch_bounds__(NT) k_rend
   }
   if (p.rows == nullptr) return; // resize-only invocation
 
-  emit_row<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond);
+  emit_row<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond, tid);
 }
 
 // ------------------------------------------------------------------ warp-specialised persistent row kernel
@@ -853,9 +855,142 @@ __global__ void __launch_bounds__(NT + 32) k_render_rows_ws(const RenderParams p
       SyncConsumers<NT>::sync(); // V is reused by the other pixel row / aliased by the row staging buffer
     }
     SyncConsumers<NT>::sync();
-    emit_row<MODE, SyncConsumers<NT>, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond);
+    emit_row<MODE, SyncConsumers<NT>, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond, tid);
     SyncConsumers<NT>::sync(); // the staging buffer aliases V: finish copying out before the next tile's sums land
   }
+}
+
+// ------------------------------------------------------------------ role-split persistent row kernel (LDG streamers)
+// Measured on B200: the streaming phase alone runs at ~98% of the copy-measured HBM peak, the one-tile-per-CTA fused
+// kernel at ~79%, because every CTA stops issuing loads for the ~20% of its life it spends in the latency-bound
+// emission phase.  Here the two phases run side by side inside one persistent CTA: eight streamer warps sum band
+// after band into double-buffered cell rows and never wait for emission; one emitter warp turns tile k into bytes
+// (the same emit_row code, instantiated for a single warp) while the streamers are already summing tile k+1.
+//   named barriers: 1 streamers only (256) | 2,3 cells[b] full (256 arrive + 32 sync) | 4,5 cells[b] empty (32 arrive + 256 sync)
+constexpr int WS2_ST = 256; // streamer threads
+template <int ID, int N> __device__ __forceinline__ void nbar_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory");
+}
+template <int ID, int N> __device__ __forceinline__ void nbar_arrive() {
+  asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(N) : "memory");
+}
+
+struct Layout2 {
+  uint32_t lut, c[2][2], key, hpos, rend, off, V, outb, total;
+};
+__host__ __device__ inline Layout2 make_layout2(int cols, int src_w, uint32_t out_bytes) {
+  Layout2 L;
+  uint32_t o = 0;
+  L.lut = o;
+  o += al16((uint32_t)sizeof(GlyphLut));
+  for (int b = 0; b < 2; b++)
+    for (int h = 0; h < 2; h++) {
+      L.c[b][h] = o;
+      o += al16(4u * cols);
+    }
+  L.key = o;
+  o += al16(2u * cols);
+  L.hpos = o;
+  o += al16(2u * cols);
+  L.rend = o;
+  o += al16(2u * cols);
+  L.off = o;
+  o += al16(4u * cols);
+  L.V = o;
+  o += al16(2u * 3u * src_w);
+  L.outb = o; // not aliased with V: the emitter fills it while the streamers refill V
+  o += al16(out_bytes);
+  L.total = o;
+  return L;
+}
+
+template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows_ws2(const RenderParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ int s_tmp[2];
+  __shared__ uint32_t s_cond[4];
+  constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
+  constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
+  const int tid = threadIdx.x;
+  const int w = p.cols;
+  const int total = p.n_frames * p.text_rows;
+  const Layout2 L = make_layout2(w, p.src_w, p.row_pitch);
+  GlyphLut *lut = reinterpret_cast<GlyphLut *>(smem + L.lut);
+  uint16_t *V = reinterpret_cast<uint16_t *>(smem + L.V);
+
+  if (USES_LUT) {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(lut);
+    for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += WS2_ST + 32) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int my_tiles = blockIdx.x < total ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (tid < WS2_ST) { // ---------------- streamers
+    int k = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, k++) {
+      const int t = tile % p.text_rows, f = tile / p.text_rows, b = k & 1;
+      uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.c[b][0]);
+      uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.c[b][1]);
+      const uint8_t *frame = p.frames + (size_t)f * p.frame_stride;
+      const int yT = HB ? 2 * t : t;
+      const bool hasB = HB && (2 * t + 1 < p.rows_px);
+      if (k >= 2) { // the emitter has finished reading cells[b] (tile k-2)
+        if (b) nbar_sync<5, WS2_ST + 32>(); else nbar_sync<4, WS2_ST + 32>();
+      }
+      cells_box_stream<WS2_ST, SyncConsumers<WS2_ST>>(p, frame, yT, cT, V);
+      if (hasB) cells_box_stream<WS2_ST, SyncConsumers<WS2_ST>>(p, frame, yT + 1, cB, V);
+      if (HB && !hasB)
+        for (int x = tid; x < w; x += WS2_ST) cB[x] = cT[x];
+      __threadfence_block();
+      // cells[b] are complete: hand them to the emitter and move on
+      if (b) nbar_arrive<3, WS2_ST + 32>(); else nbar_arrive<2, WS2_ST + 32>();
+    }
+  } else { // ---------------- emitter warp
+    const int lane = tid - WS2_ST;
+    uint16_t *key = reinterpret_cast<uint16_t *>(smem + L.key);
+    uint16_t *hpos = reinterpret_cast<uint16_t *>(smem + L.hpos);
+    uint16_t *rend = reinterpret_cast<uint16_t *>(smem + L.rend);
+    uint32_t *off = reinterpret_cast<uint32_t *>(smem + L.off);
+    uint8_t *outb = smem + L.outb;
+    int k = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, k++) {
+      const int t = tile % p.text_rows, f = tile / p.text_rows, b = k & 1;
+      uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.c[b][0]);
+      uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.c[b][1]);
+      if (b) nbar_sync<3, WS2_ST + 32>(); else nbar_sync<2, WS2_ST + 32>();
+      emit_row<MODE, SyncWarp, 32>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond, lane);
+      __syncwarp();
+      if (k + 2 < my_tiles) {
+        __threadfence_block();
+        if (b) nbar_arrive<5, WS2_ST + 32>(); else nbar_arrive<4, WS2_ST + 32>();
+      }
+    }
+  }
+}
+
+template <int MODE> static cudaError_t launch_ws2_mode(const RenderParams &p, cudaStream_t st) {
+  const Layout2 L = make_layout2(p.cols, p.src_w, p.row_pitch);
+  if (L.total > kMaxDynSmem) return cudaErrorInvalidConfiguration;
+  static bool configured = false;
+  static int ctas_per_sm = 1, sms = 148;
+  static size_t cfg_smem = 0;
+  if (!configured || cfg_smem != L.total) {
+    cudaError_t e = cudaFuncSetAttribute(k_render_rows_ws2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kMaxDynSmem);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_render_rows_ws2<MODE>, WS2_ST + 32, L.total);
+    if (e != cudaSuccess || ctas_per_sm < 1) return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
+    cfg_smem = L.total;
+    configured = true;
+  }
+  const long long total = (long long)p.n_frames * p.text_rows;
+  long long grid = (long long)sms * ctas_per_sm;
+  if (grid > total) grid = total;
+  k_render_rows_ws2<MODE><<<(unsigned)grid, WS2_ST + 32, L.total, st>>>(p);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ per-mode launch templates
