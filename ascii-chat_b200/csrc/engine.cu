@@ -380,8 +380,19 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
     ACB_CUDA(launch_render_rows_ws(rp, pl.mode, st));
     count_launch();
   } else if (pl.mode != EM_DITHER_BG && pl.scale_path == SP_BOX_SPLIT) {
+    // direct output: rows land in the final arena, placed by the emitters' look-back; the per-row records (and the
+    // tile ticket behind them) live where the stitch path keeps its RowMeta array
+    rp.out = d_out;
+    rp.out_pitch = out_pitch;
+    rp.out_len = d_out_len;
+    rp.pad_top = cfg.pad_top;
+    rp.agg = reinterpret_cast<uint4 *>(meta);
+    ACB_CUDA(cudaMemsetAsync(meta, 0, ((size_t)n_frames * pl.text_rows + 1) * sizeof(uint4), st));
+    if (k0) cudaEventRecord(k0, st); // time the kernel alone
     ACB_CUDA(launch_render_rows_ws2(rp, pl.mode, st));
     count_launch();
+    if (k1) cudaEventRecord(k1, st);
+    return E_OK;
   } else if (pl.mode != EM_DITHER_BG) {
     ACB_CUDA(launch_render_rows(rp, pl.mode, kernel_sp, st));
     count_launch();

@@ -58,6 +58,12 @@ struct RenderParams {
   const GlyphLut *lut;
   uint8_t *cells_out;    // optional: resized RGB24 image, frame f at f*cols*rows_px*3 (image_resize, tests)
   int n_frames;
+  // direct output (role-split kernel): final arena + per-row look-back records (16 B each, + 16 B ticket)
+  uint8_t *out;
+  size_t out_pitch;
+  uint32_t *out_len;
+  uint4 *agg;
+  int pad_top;
   int ring_depth;         // warp-specialised kernel: source rows kept in flight by the producer warp
   int tune_flags;         // bit0: do not alias V with the row staging buffer (measurement knob)
 };

@@ -391,6 +391,7 @@ struct RowCtx {
   const GlyphLut *lut;
   const uint32_t *cT, *cB;
   const uint16_t *key, *hpos, *rend;
+  uint32_t drop_first; // EM_TRUE_FG, direct output: the row's first ASCII cell inherits the colour state of the rows above
 };
 
 template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int x, const RowCtx &c) {
@@ -409,7 +410,7 @@ template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int
     bool ascii = g[0] == 1 && g[1] < 128;
     if (ascii) {
       uint16_t pa = c.hpos[x];
-      if (pa == NONE16 || c.cT[pa] != px) put_sgr_rgb(s, false, px);
+      if (pa == NONE16 ? !c.drop_first : c.cT[pa] != px) put_sgr_rgb(s, false, px);
       s.put(g[1]);
     } else {
       put_sgr_rgb(s, false, px);
@@ -476,14 +477,14 @@ template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int
 
 // Phase B for one text row whose resized pixels are in cT/cB: keys -> runs -> byte counts -> offsets -> bytes,
 // staged in shared memory (or written straight to the scratch row when it is too wide) and copied out.
+// emit_prepare = B1..B3 (returns the byte count of the cells, offsets in off[]); emit_row adds B4 into the scratch row.
 template <int MODE, class Sync, int NT>
-__device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT, uint32_t *cB,
-                                         uint16_t *key, uint16_t *hpos, uint16_t *rend, uint32_t *off, uint8_t *outb,
-                                         int *s_tmp, uint32_t *s_cond, int tid) {
+__device__ __forceinline__ uint32_t emit_prepare(const RenderParams &p, GlyphLut *lut, uint32_t *cT, uint32_t *cB,
+                                                 uint16_t *key, uint16_t *hpos, uint16_t *rend, uint32_t *off,
+                                                 int *s_tmp, uint32_t *s_cond, int tid) {
   constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
   constexpr bool RUNS = MODE == EM_MONO_FG || HB;
   const int w = p.cols;
-  const bool last_row = t == p.text_rows - 1;
   if (tid < 4) s_cond[tid] = 0u;
   Sync::sync();
 
@@ -525,7 +526,7 @@ __device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, Gl
   }
 
   // ---- phase B3: byte counts -> offsets
-  RowCtx ctx{lut, cT, cB, key, hpos, rend};
+  RowCtx ctx{lut, cT, cB, key, hpos, rend, 0u};
   int cells_bytes = row_scan<OpAdd, Sync, NT>(
       w,
       [&](int x) {
@@ -534,7 +535,18 @@ __device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, Gl
         return (int)cs.n;
       },
       [&](int x, int, int excl) { off[x] = (uint32_t)excl + (uint32_t)p.pad_left; }, s_tmp, tid);
-  const uint32_t body_end = (uint32_t)p.pad_left + (uint32_t)cells_bytes;
+  return (uint32_t)cells_bytes;
+}
+
+template <int MODE, class Sync, int NT>
+__device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT, uint32_t *cB,
+                                         uint16_t *key, uint16_t *hpos, uint16_t *rend, uint32_t *off, uint8_t *outb,
+                                         int *s_tmp, uint32_t *s_cond, int tid) {
+  const int w = p.cols;
+  const bool last_row = t == p.text_rows - 1;
+  const uint32_t cells_bytes = emit_prepare<MODE, Sync, NT>(p, lut, cT, cB, key, hpos, rend, off, s_tmp, s_cond, tid);
+  RowCtx ctx{lut, cT, cB, key, hpos, rend, 0u};
+  const uint32_t body_end = (uint32_t)p.pad_left + cells_bytes;
 
   // ---- phase B4: materialise
   uint8_t *grow = p.rows + ((size_t)f * p.text_rows + t) * (size_t)p.row_pitch;
@@ -860,6 +872,133 @@ __global__ void __launch_bounds__(NT + 32) k_render_rows_ws(const RenderParams p
   }
 }
 
+// ------------------------------------------------------------------ direct output: row-length look-back
+// One warp finishes a text row AND places it in the final frame string, so no stitch pass and no scratch rows:
+// after the byte counts are known the warp publishes {ready, len, first_rgb, last_rgb} for its row, reads the
+// records of the rows above (spinning until each is ready — they are being produced concurrently by other CTAs, and
+// tiles are handed out by an atomic ticket so every lower tile is already running), and derives its byte offset in
+// the frame.  For truecolor-foreground the same look-back carries the colour state of ansi_rle_add_pixel across
+// rows (ansi.c:263): each row's first ASCII-cell SGR is dropped iff its colour equals the last ASCII colour above.
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t sgr_rgb_len(uint32_t c) { // bytes of ESC[38;2;R;G;Bm
+  uint32_t r = (c >> 16) & 255u, g = (c >> 8) & 255u, b = c & 255u;
+  return 10u + (r >= 100u ? 3u : r >= 10u ? 2u : 1u) + (g >= 100u ? 3u : g >= 10u ? 2u : 1u) +
+         (b >= 100u ? 3u : b >= 10u ? 2u : 1u);
+}
+
+template <int MODE>
+__device__ __forceinline__ void emit_row_direct(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT,
+                                                uint32_t *cB, uint16_t *key, uint16_t *hpos, uint16_t *rend,
+                                                uint32_t *off, uint8_t *outb, int *s_tmp, uint32_t *s_cond, int lane) {
+  const int w = p.cols;
+  const bool last_row = t == p.text_rows - 1;
+  const uint32_t cells_bytes = emit_prepare<MODE, SyncWarp, 32>(p, lut, cT, cB, key, hpos, rend, off, s_tmp, s_cond, lane);
+  if (MODE == EM_TRUE_FG) { // locate the row's first ASCII-glyph cell (s_cond[2] = last one, from the scan)
+    for (int x = lane; x < w; x += 32)
+      if (hpos[x] == NONE16) {
+        const uint8_t *g = lut->glyph[luma_of(cT[x])];
+        if (g[0] == 1 && g[1] < 128) {
+          s_cond[0] = (uint32_t)x;
+          s_cond[3] = 0x01000000u | cT[x];
+        }
+      }
+    __syncwarp();
+  }
+  const bool row_reset = MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16;
+  const uint32_t term_len = (row_reset ? 4u : 0u) + ((MODE == EM_TRUE_FG && last_row) ? 4u : 0u) + (last_row ? 0u : 1u);
+  const uint32_t body_end = (uint32_t)p.pad_left + cells_bytes;
+  const uint32_t row_len = body_end + term_len;
+  const uint32_t first = MODE == EM_TRUE_FG ? s_cond[3] : 0u, last = MODE == EM_TRUE_FG ? s_cond[2] : 0u;
+  const uint32_t first_x = s_cond[0];
+
+  uint32_t *agg = reinterpret_cast<uint32_t *>(p.agg + (size_t)f * p.text_rows); // 4 words per row
+  if (lane == 0) {
+    uint32_t *me = agg + 4 * (size_t)t;
+    me[1] = row_len;
+    me[2] = first;
+    me[3] = last;
+    __threadfence();
+    *reinterpret_cast<volatile uint32_t *>(me) = 1u;
+  }
+  uint32_t prefix = 0, carry = 0;
+  for (int base = 0; base < t; base += 32) {
+    const int j = base + lane;
+    uint32_t len = 0, fj = 0, lj = 0;
+    if (j < t) {
+      const uint32_t *rec = agg + 4 * (size_t)j;
+      while (ld_volatile_u32(rec) == 0u) {
+      }
+      __threadfence();
+      len = ld_volatile_u32(rec + 1);
+      fj = ld_volatile_u32(rec + 2);
+      lj = ld_volatile_u32(rec + 3);
+    }
+    if (MODE == EM_TRUE_FG) {
+      uint32_t inc = lj; // inclusive "last non-zero" scan = colour state after row j
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d && inc == 0u) inc = o;
+      }
+      uint32_t before = __shfl_up_sync(0xffffffffu, inc, 1);
+      if (lane == 0) before = 0u;
+      if (before == 0u) before = carry;
+      if (fj && before && fj == before) len -= sgr_rgb_len(fj);
+      const uint32_t tail = __shfl_sync(0xffffffffu, inc, 31);
+      if (tail) carry = tail;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) len += __shfl_xor_sync(0xffffffffu, len, d);
+    prefix += len;
+  }
+  const uint32_t drop = (MODE == EM_TRUE_FG && first && carry && first == carry) ? sgr_rgb_len(first) : 0u;
+  const uint32_t dst_off = (uint32_t)p.pad_top + prefix;
+  const uint32_t final_len = row_len - drop;
+  uint8_t *frame_out = p.out + (size_t)f * p.out_pitch;
+  uint8_t *dst = frame_out + dst_off;
+  const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u); // stage with the destination's alignment
+  uint8_t *sb = outb + shift;
+
+  // ---- B4: the row's bytes, already in their final form, into shared memory
+  RowCtx ctx{lut, cT, cB, key, hpos, rend, drop ? 1u : 0u};
+  for (int i = lane; i < p.pad_left; i += 32) sb[i] = ' ';
+  const uint32_t sb32 = (uint32_t)__cvta_generic_to_shared(sb);
+  for (int x = lane; x < w; x += 32) {
+    const uint32_t o = off[x] - ((MODE == EM_TRUE_FG && drop && (uint32_t)x > first_x) ? drop : 0u);
+    SmemSink ss{sb32 + o};
+    emit_cell<MODE>(ss, x, ctx);
+  }
+  if (lane == 0) {
+    WriteSink ws{sb + body_end - drop};
+    if (row_reset) put_reset(ws);
+    if (MODE == EM_TRUE_FG && last_row) put_reset(ws); // ansi_rle_finish, ansi.c:303-314
+    if (!last_row) ws.put('\n');
+  }
+  __syncwarp();
+
+  // ---- copy out: unaligned head bytes, 16-byte body (source and destination share their alignment), tail bytes
+  uint32_t head = (16u - shift) & 15u;
+  if (head > final_len) head = final_len;
+  if ((uint32_t)lane < head) dst[lane] = sb[lane];
+  const uint32_t nvec = (final_len - head) >> 4;
+  const uint4 *s4 = reinterpret_cast<const uint4 *>(sb + head);
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+  for (uint32_t i = lane; i < nvec; i += 32) d4[i] = s4[i];
+  const uint32_t done = head + (nvec << 4);
+  if ((uint32_t)lane < final_len - done) dst[done + lane] = sb[done + lane];
+  if (t == 0)
+    for (int i = lane; i < p.pad_top; i += 32) frame_out[i] = '\n';
+  if (last_row && lane == 0) {
+    frame_out[dst_off + final_len] = 0;
+    p.out_len[f] = dst_off + final_len;
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------ role-split persistent row kernel (LDG streamers)
 // Measured on B200: the streaming phase alone runs at ~98% of the copy-measured HBM peak, the one-tile-per-CTA fused
 // kernel at ~79%, because every CTA stops issuing loads for the ~20% of its life it spends in the latency-bound
@@ -899,7 +1038,7 @@ __host__ __device__ inline Layout2 make_layout2(int cols, int src_w, uint32_t ou
   L.V = o;
   o += al16(2u * 3u * src_w);
   L.outb = o; // not aliased with V: the emitter fills it while the streamers refill V
-  o += al16(out_bytes);
+  o += al16(out_bytes) + 16u; // + room to stage the row with the destination's 16-byte phase
   L.total = o;
   return L;
 }
@@ -908,6 +1047,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_tmp[2];
   __shared__ uint32_t s_cond[4];
+  __shared__ int s_tile[2];
   constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
   constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
   const int tid = threadIdx.x;
@@ -916,6 +1056,10 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
   const Layout2 L = make_layout2(w, p.src_w, p.row_pitch);
   GlyphLut *lut = reinterpret_cast<GlyphLut *>(smem + L.lut);
   uint16_t *V = reinterpret_cast<uint16_t *>(smem + L.V);
+  // tiles are handed out by an atomic ticket (the word after the last look-back record): whoever holds tile X knows
+  // every tile < X is already held by a running CTA, which makes the emitter's look-back spin deadlock-free even if
+  // the grid is not fully resident
+  int *ticket = reinterpret_cast<int *>(p.agg + (size_t)total);
 
   if (USES_LUT) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
@@ -923,20 +1067,32 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
     for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += WS2_ST + 32) dst[i] = src[i];
   }
   __syncthreads();
-  const int my_tiles = blockIdx.x < total ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (tid < WS2_ST) { // ---------------- streamers
-    int k = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, k++) {
-      const int t = tile % p.text_rows, f = tile / p.text_rows, b = k & 1;
+    for (int k = 0;; k++) {
+      const int b = k & 1;
+      if (k >= 2) { // the emitter has finished with cells[b] / s_tile[b] (tile k-2)
+        if (b) nbar_sync<5, WS2_ST + 32>(); else nbar_sync<4, WS2_ST + 32>();
+      }
+      if (tid == 0) {
+        const int tk = atomicAdd(ticket, 1);
+        s_tile[b] = tk < total ? tk : -1;
+      }
+      SyncConsumers<WS2_ST>::sync();
+      const int tile = s_tile[b];
+      if (tile < 0) { // no more work: pass the sentinel on, absorb the emitter's last "empty" arrival, leave
+        if (b) nbar_arrive<3, WS2_ST + 32>(); else nbar_arrive<2, WS2_ST + 32>();
+        if (k >= 1) {
+          if (b) nbar_sync<4, WS2_ST + 32>(); else nbar_sync<5, WS2_ST + 32>(); // barrier of buffer (k-1)&1
+        }
+        break;
+      }
+      const int t = tile % p.text_rows, f = tile / p.text_rows;
       uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.c[b][0]);
       uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.c[b][1]);
       const uint8_t *frame = p.frames + (size_t)f * p.frame_stride;
       const int yT = HB ? 2 * t : t;
       const bool hasB = HB && (2 * t + 1 < p.rows_px);
-      if (k >= 2) { // the emitter has finished reading cells[b] (tile k-2)
-        if (b) nbar_sync<5, WS2_ST + 32>(); else nbar_sync<4, WS2_ST + 32>();
-      }
       cells_box_stream<WS2_ST, SyncConsumers<WS2_ST>>(p, frame, yT, cT, V);
       if (hasB) cells_box_stream<WS2_ST, SyncConsumers<WS2_ST>>(p, frame, yT + 1, cB, V);
       if (HB && !hasB)
@@ -952,18 +1108,17 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
     uint16_t *rend = reinterpret_cast<uint16_t *>(smem + L.rend);
     uint32_t *off = reinterpret_cast<uint32_t *>(smem + L.off);
     uint8_t *outb = smem + L.outb;
-    int k = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, k++) {
-      const int t = tile % p.text_rows, f = tile / p.text_rows, b = k & 1;
+    for (int k = 0;; k++) {
+      const int b = k & 1;
+      if (b) nbar_sync<3, WS2_ST + 32>(); else nbar_sync<2, WS2_ST + 32>();
+      const int tile = s_tile[b];
+      if (tile < 0) break;
+      const int t = tile % p.text_rows, f = tile / p.text_rows;
       uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.c[b][0]);
       uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.c[b][1]);
-      if (b) nbar_sync<3, WS2_ST + 32>(); else nbar_sync<2, WS2_ST + 32>();
-      emit_row<MODE, SyncWarp, 32>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond, lane);
-      __syncwarp();
-      if (k + 2 < my_tiles) {
-        __threadfence_block();
-        if (b) nbar_arrive<5, WS2_ST + 32>(); else nbar_arrive<4, WS2_ST + 32>();
-      }
+      emit_row_direct<MODE>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond, lane);
+      __threadfence_block();
+      if (b) nbar_arrive<5, WS2_ST + 32>(); else nbar_arrive<4, WS2_ST + 32>();
     }
   }
 }

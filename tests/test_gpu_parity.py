@@ -152,12 +152,33 @@ def test_box_mode_vs_oracle(acb, ob):
              (100, 50, 130, 70), (48, 2000, 7, 5)]  # streaming path, generic path, upscale, tall bands
     for (W, H, c, r), pat in itertools.product(cases, ("noise", "bars")):
         img = ob.gen(pat, W, H, 2)
-        for level, mode in ((0, 0), (2, 0), (3, 0), (3, 2), (1, 2), (0, 2), (2, 2), (3, 1)):
+        for level, mode, pal in ((0, 0, "standard"), (2, 0, "standard"), (3, 0, "standard"), (3, 0, "blocks"),
+                                 (3, 0, "cool"), (3, 2, "standard"), (1, 2, "standard"), (0, 2, "standard"),
+                                 (2, 2, "standard"), (3, 1, "standard"), (1, 0, "digital")):
             rows_px = r * 2 if mode == 2 else r
-            cfg = acb.make_cfg(W, H, c, rows_px, level, mode, "standard", scale=acb.SCALE_BOX)
+            cfg = acb.make_cfg(W, H, c, rows_px, level, mode, pal, scale=acb.SCALE_BOX, pad_left=3, pad_top=2)
             got = acb.render_batch_host(cfg, [img])[0]
-            exp = ob.port_convert(img, c, r, level, mode, "standard", scale=ob.SCALE_BOX)
-            assert got == exp, (W, H, c, r, pat, level, mode)
+            exp = ob.port_convert(img, c, r, level, mode, pal, scale=ob.SCALE_BOX)
+            exp = ob._take(ob.port().orc_pad_height(ob._take(ob.port().orc_pad_width(exp, 3)), 2))
+            assert got == exp, (W, H, c, r, pat, level, mode, pal)
+
+
+def test_box_truecolor_fg_colour_carry(acb, ob):
+    """the cross-row colour state of ansi_rle_add_pixel through the look-back: flat colours make whole rows drop
+    their first SGR, multi-byte glyph rows must be transparent to the carry"""
+    rng = np.random.default_rng(2)
+    for it in range(12):
+        W, H, c, r = 640, 48 * (1 + it % 3), 40 + 8 * (it % 4), 6 + it % 5
+        img = np.zeros((H, W, 3), np.uint8)
+        band = max(1, H // (r * 2))
+        for y0 in range(0, H, band):  # horizontal bands of few colours: rows often start with the colour above
+            img[y0:y0 + band] = rng.choice([0, 40, 200, 255], 3)
+        img[:, W // 2:] = img[:, W // 2:] // 2 + rng.integers(0, 2, (H, W - W // 2, 1), dtype=np.uint8) * 100
+        for pal in ("standard", "blocks", "cool", "minimal"):
+            cfg = acb.make_cfg(W, H, c, r, 3, 0, pal, scale=acb.SCALE_BOX)
+            got = acb.render_batch_host(cfg, [img, img[::-1].copy()])
+            for g, src in zip(got, (img, img[::-1].copy())):
+                assert g == ob.port_convert(src, c, r, 3, 0, pal, scale=ob.SCALE_BOX), (it, pal)
 
 
 # ---------------------------------------------------------------- batch API on resident frames
