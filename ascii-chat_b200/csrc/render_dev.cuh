@@ -890,10 +890,11 @@ __device__ __forceinline__ uint32_t sgr_rgb_len(uint32_t c) { // bytes of ESC[38
          (b >= 100u ? 3u : b >= 10u ? 2u : 1u);
 }
 
+// prepare: B1..B3 for the row, then publish its record; never waits.  Returns the byte count of the cells.
 template <int MODE>
-__device__ __forceinline__ void emit_row_direct(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT,
-                                                uint32_t *cB, uint16_t *key, uint16_t *hpos, uint16_t *rend,
-                                                uint32_t *off, uint8_t *outb, int *s_tmp, uint32_t *s_cond, int lane) {
+__device__ __forceinline__ uint32_t emit_direct_prepare(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT,
+                                                        uint32_t *cB, uint16_t *key, uint16_t *hpos, uint16_t *rend,
+                                                        uint32_t *off, int *s_tmp, uint32_t *s_cond, int lane) {
   const int w = p.cols;
   const bool last_row = t == p.text_rows - 1;
   const uint32_t cells_bytes = emit_prepare<MODE, SyncWarp, 32>(p, lut, cT, cB, key, hpos, rend, off, s_tmp, s_cond, lane);
@@ -908,30 +909,43 @@ __device__ __forceinline__ void emit_row_direct(const RenderParams &p, int f, in
       }
     __syncwarp();
   }
-  const bool row_reset = MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16;
+  constexpr bool row_reset = MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16;
   const uint32_t term_len = (row_reset ? 4u : 0u) + ((MODE == EM_TRUE_FG && last_row) ? 4u : 0u) + (last_row ? 0u : 1u);
-  const uint32_t body_end = (uint32_t)p.pad_left + cells_bytes;
-  const uint32_t row_len = body_end + term_len;
-  const uint32_t first = MODE == EM_TRUE_FG ? s_cond[3] : 0u, last = MODE == EM_TRUE_FG ? s_cond[2] : 0u;
-  const uint32_t first_x = s_cond[0];
-
-  uint32_t *agg = reinterpret_cast<uint32_t *>(p.agg + (size_t)f * p.text_rows); // 4 words per row
   if (lane == 0) {
-    uint32_t *me = agg + 4 * (size_t)t;
-    me[1] = row_len;
-    me[2] = first;
-    me[3] = last;
+    uint32_t *me = reinterpret_cast<uint32_t *>(p.agg + (size_t)f * p.text_rows + t);
+    me[1] = (uint32_t)p.pad_left + cells_bytes + term_len;
+    me[2] = MODE == EM_TRUE_FG ? s_cond[3] : 0u;
+    me[3] = MODE == EM_TRUE_FG ? s_cond[2] : 0u;
     __threadfence();
     *reinterpret_cast<volatile uint32_t *>(me) = 1u;
   }
+  __syncwarp();
+  return cells_bytes;
+}
+
+// finish: look-back for the row's offset (and, truecolor-fg, the colour state above), materialise, store.
+template <int MODE>
+__device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT,
+                                                   uint32_t *cB, uint16_t *key, uint16_t *hpos, uint16_t *rend,
+                                                   uint32_t *off, uint8_t *outb, const uint32_t *s_cond,
+                                                   uint32_t cells_bytes, int lane) {
+  const int w = p.cols;
+  const bool last_row = t == p.text_rows - 1;
+  constexpr bool row_reset = MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16;
+  const uint32_t term_len = (row_reset ? 4u : 0u) + ((MODE == EM_TRUE_FG && last_row) ? 4u : 0u) + (last_row ? 0u : 1u);
+  const uint32_t body_end = (uint32_t)p.pad_left + cells_bytes;
+  const uint32_t row_len = body_end + term_len;
+  const uint32_t first = MODE == EM_TRUE_FG ? s_cond[3] : 0u;
+  const uint32_t first_x = s_cond[0];
+
+  const uint32_t *agg = reinterpret_cast<const uint32_t *>(p.agg + (size_t)f * p.text_rows); // 4 words per row
   uint32_t prefix = 0, carry = 0;
   for (int base = 0; base < t; base += 32) {
     const int j = base + lane;
     uint32_t len = 0, fj = 0, lj = 0;
     if (j < t) {
       const uint32_t *rec = agg + 4 * (size_t)j;
-      while (ld_volatile_u32(rec) == 0u) {
-      }
+      while (ld_volatile_u32(rec) == 0u) __nanosleep(64);
       __threadfence();
       len = ld_volatile_u32(rec + 1);
       fj = ld_volatile_u32(rec + 2);
@@ -1015,26 +1029,28 @@ template <int ID, int N> __device__ __forceinline__ void nbar_arrive() {
 }
 
 struct Layout2 {
-  uint32_t lut, c[2][2], key, hpos, rend, off, V, outb, total;
+  uint32_t lut, c[3][2], key[2], hpos[2], rend[2], off[2], V, outb, total;
 };
 __host__ __device__ inline Layout2 make_layout2(int cols, int src_w, uint32_t out_bytes) {
   Layout2 L;
   uint32_t o = 0;
   L.lut = o;
   o += al16((uint32_t)sizeof(GlyphLut));
-  for (int b = 0; b < 2; b++)
+  for (int b = 0; b < 3; b++) // cell rows: one being summed, one prepared, one being written out
     for (int h = 0; h < 2; h++) {
       L.c[b][h] = o;
       o += al16(4u * cols);
     }
-  L.key = o;
-  o += al16(2u * cols);
-  L.hpos = o;
-  o += al16(2u * cols);
-  L.rend = o;
-  o += al16(2u * cols);
-  L.off = o;
-  o += al16(4u * cols);
+  for (int b = 0; b < 2; b++) { // run/offset arrays: prepared tile + tile being written out
+    L.key[b] = o;
+    o += al16(2u * cols);
+    L.hpos[b] = o;
+    o += al16(2u * cols);
+    L.rend[b] = o;
+    o += al16(2u * cols);
+    L.off[b] = o;
+    o += al16(4u * cols);
+  }
   L.V = o;
   o += al16(2u * 3u * src_w);
   L.outb = o; // not aliased with V: the emitter fills it while the streamers refill V
@@ -1043,13 +1059,36 @@ __host__ __device__ inline Layout2 make_layout2(int cols, int src_w, uint32_t ou
   return L;
 }
 
+// named barriers: 1 = streamers only; FULL(c) = 2+c, EMPTY(c) = 5+c for cell buffer c in {0,1,2}
+template <int N> __device__ __forceinline__ void nbar_sync_id(int id) {
+  switch (id) {
+  case 2: nbar_sync<2, N>(); break;
+  case 3: nbar_sync<3, N>(); break;
+  case 4: nbar_sync<4, N>(); break;
+  case 5: nbar_sync<5, N>(); break;
+  case 6: nbar_sync<6, N>(); break;
+  default: nbar_sync<7, N>(); break;
+  }
+}
+template <int N> __device__ __forceinline__ void nbar_arrive_id(int id) {
+  switch (id) {
+  case 2: nbar_arrive<2, N>(); break;
+  case 3: nbar_arrive<3, N>(); break;
+  case 4: nbar_arrive<4, N>(); break;
+  case 5: nbar_arrive<5, N>(); break;
+  case 6: nbar_arrive<6, N>(); break;
+  default: nbar_arrive<7, N>(); break;
+  }
+}
+
 template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows_ws2(const RenderParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_tmp[2];
-  __shared__ uint32_t s_cond[4];
-  __shared__ int s_tile[2];
+  __shared__ uint32_t s_cond[2][4];
+  __shared__ int s_tile[3];
   constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
   constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
+  constexpr int NB = WS2_ST + 32;
   const int tid = threadIdx.x;
   const int w = p.cols;
   const int total = p.n_frames * p.text_rows;
@@ -1064,32 +1103,29 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
   if (USES_LUT) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
     uint32_t *dst = reinterpret_cast<uint32_t *>(lut);
-    for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += WS2_ST + 32) dst[i] = src[i];
+    for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += NB) dst[i] = src[i];
   }
   __syncthreads();
 
   if (tid < WS2_ST) { // ---------------- streamers
     for (int k = 0;; k++) {
-      const int b = k & 1;
-      if (k >= 2) { // the emitter has finished with cells[b] / s_tile[b] (tile k-2)
-        if (b) nbar_sync<5, WS2_ST + 32>(); else nbar_sync<4, WS2_ST + 32>();
-      }
+      const int c = k % 3;
+      if (k >= 3) nbar_sync_id<NB>(5 + c); // the emitter has written out tile k-3: cells[c] / s_tile[c] are free
       if (tid == 0) {
         const int tk = atomicAdd(ticket, 1);
-        s_tile[b] = tk < total ? tk : -1;
+        s_tile[c] = tk < total ? tk : -1;
       }
       SyncConsumers<WS2_ST>::sync();
-      const int tile = s_tile[b];
-      if (tile < 0) { // no more work: pass the sentinel on, absorb the emitter's last "empty" arrival, leave
-        if (b) nbar_arrive<3, WS2_ST + 32>(); else nbar_arrive<2, WS2_ST + 32>();
-        if (k >= 1) {
-          if (b) nbar_sync<4, WS2_ST + 32>(); else nbar_sync<5, WS2_ST + 32>(); // barrier of buffer (k-1)&1
-        }
+      const int tile = s_tile[c];
+      if (tile < 0) { // no more work: pass the sentinel on, absorb the emitter's last two "empty" arrivals, leave
+        nbar_arrive_id<NB>(2 + c);
+        if (k >= 2) nbar_sync_id<NB>(5 + (k - 2) % 3);
+        if (k >= 1) nbar_sync_id<NB>(5 + (k - 1) % 3);
         break;
       }
       const int t = tile % p.text_rows, f = tile / p.text_rows;
-      uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.c[b][0]);
-      uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.c[b][1]);
+      uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.c[c][0]);
+      uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.c[c][1]);
       const uint8_t *frame = p.frames + (size_t)f * p.frame_stride;
       const int yT = HB ? 2 * t : t;
       const bool hasB = HB && (2 * t + 1 < p.rows_px);
@@ -1098,27 +1134,44 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
       if (HB && !hasB)
         for (int x = tid; x < w; x += WS2_ST) cB[x] = cT[x];
       __threadfence_block();
-      // cells[b] are complete: hand them to the emitter and move on
-      if (b) nbar_arrive<3, WS2_ST + 32>(); else nbar_arrive<2, WS2_ST + 32>();
+      nbar_arrive_id<NB>(2 + c); // cells[c] are complete: hand them to the emitter and move on
     }
-  } else { // ---------------- emitter warp
+  } else { // ---------------- emitter warp, software-pipelined by one tile:
+    //   iteration k: prepare + publish tile k (never waits), then look-back + write-out of tile k-1, whose
+    //   predecessors have had a whole tile period to publish — so a late row cannot start a convoy
     const int lane = tid - WS2_ST;
-    uint16_t *key = reinterpret_cast<uint16_t *>(smem + L.key);
-    uint16_t *hpos = reinterpret_cast<uint16_t *>(smem + L.hpos);
-    uint16_t *rend = reinterpret_cast<uint16_t *>(smem + L.rend);
-    uint32_t *off = reinterpret_cast<uint32_t *>(smem + L.off);
     uint8_t *outb = smem + L.outb;
+    uint32_t prev_bytes = 0;
+    int prev_tile = -1;
     for (int k = 0;; k++) {
-      const int b = k & 1;
-      if (b) nbar_sync<3, WS2_ST + 32>(); else nbar_sync<2, WS2_ST + 32>();
-      const int tile = s_tile[b];
+      const int c = k % 3, a = k & 1;
+      nbar_sync_id<NB>(2 + c);
+      const int tile = s_tile[c];
+      uint32_t bytes = 0;
+      if (tile >= 0) {
+        const int t = tile % p.text_rows, f = tile / p.text_rows;
+        bytes = emit_direct_prepare<MODE>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[c][0]),
+                                          reinterpret_cast<uint32_t *>(smem + L.c[c][1]),
+                                          reinterpret_cast<uint16_t *>(smem + L.key[a]),
+                                          reinterpret_cast<uint16_t *>(smem + L.hpos[a]),
+                                          reinterpret_cast<uint16_t *>(smem + L.rend[a]),
+                                          reinterpret_cast<uint32_t *>(smem + L.off[a]), s_tmp, s_cond[a], lane);
+      }
+      if (prev_tile >= 0) {
+        const int pc = (k - 1) % 3, pa = (k - 1) & 1;
+        const int t = prev_tile % p.text_rows, f = prev_tile / p.text_rows;
+        emit_direct_finish<MODE>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[pc][0]),
+                                 reinterpret_cast<uint32_t *>(smem + L.c[pc][1]),
+                                 reinterpret_cast<uint16_t *>(smem + L.key[pa]),
+                                 reinterpret_cast<uint16_t *>(smem + L.hpos[pa]),
+                                 reinterpret_cast<uint16_t *>(smem + L.rend[pa]),
+                                 reinterpret_cast<uint32_t *>(smem + L.off[pa]), outb, s_cond[pa], prev_bytes, lane);
+        __threadfence_block();
+        nbar_arrive_id<NB>(5 + pc);
+      }
       if (tile < 0) break;
-      const int t = tile % p.text_rows, f = tile / p.text_rows;
-      uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.c[b][0]);
-      uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.c[b][1]);
-      emit_row_direct<MODE>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond, lane);
-      __threadfence_block();
-      if (b) nbar_arrive<5, WS2_ST + 32>(); else nbar_arrive<4, WS2_ST + 32>();
+      prev_tile = tile;
+      prev_bytes = bytes;
     }
   }
 }
