@@ -328,7 +328,8 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
 }
 
 static size_t scratch_bytes(const Plan &pl, int n) {
-  return al256(pl.rows_bytes * n) + al256(pl.meta_bytes * n) + al256(pl.cells_bytes * n) + al256(pl.err_bytes * n);
+  return al256(pl.rows_bytes * n) + al256(pl.meta_bytes * n) + al256(pl.cells_bytes * n) + al256(pl.err_bytes * n) +
+         256; // + the tile ticket of the persistent kernels
 }
 
 // ------------------------------------------------------------------ the device pipeline
@@ -386,13 +387,19 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
     rp.out_pitch = out_pitch;
     rp.out_len = d_out_len;
     rp.pad_top = cfg.pad_top;
+    static const int direct_env = getenv("ACB200_DIRECT") ? atoi(getenv("ACB200_DIRECT")) : 1; // measurement knob
+    rp.direct = direct_env;
+    // look-back records (direct) live where the stitch path keeps RowMeta; the tile ticket sits in its own word
     rp.agg = reinterpret_cast<uint4 *>(meta);
-    ACB_CUDA(cudaMemsetAsync(meta, 0, ((size_t)n_frames * pl.text_rows + 1) * sizeof(uint4), st));
+    rp.ticket = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(err) + al256(pl.err_bytes * n_frames));
+    if (direct_env) ACB_CUDA(cudaMemsetAsync(meta, 0, (size_t)n_frames * pl.text_rows * sizeof(uint4), st));
+    ACB_CUDA(cudaMemsetAsync(rp.ticket, 0, sizeof(int), st));
     if (k0) cudaEventRecord(k0, st); // time the kernel alone
     ACB_CUDA(launch_render_rows_ws2(rp, pl.mode, st));
     count_launch();
     if (k1) cudaEventRecord(k1, st);
-    return E_OK;
+    if (direct_env) return E_OK;
+    goto stitch;
   } else if (pl.mode != EM_DITHER_BG) {
     ACB_CUDA(launch_render_rows(rp, pl.mode, kernel_sp, st));
     count_launch();
@@ -408,6 +415,7 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
   }
   if (k1) cudaEventRecord(k1, st);
 
+stitch:
   StitchParams sp{};
   sp.rows = rows;
   sp.meta = meta;

@@ -63,7 +63,9 @@ struct RenderParams {
   size_t out_pitch;
   uint32_t *out_len;
   uint4 *agg;
+  int *ticket;            // atomic tile ticket (zeroed per launch)
   int pad_top;
+  int direct;             // 1: emitters place rows in the final arena (look-back); 0: scratch rows + k_stitch
   int ring_depth;         // warp-specialised kernel: source rows kept in flight by the producer warp
   int tune_flags;         // bit0: do not alias V with the row staging buffer (measurement knob)
 };

@@ -1098,7 +1098,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
   // tiles are handed out by an atomic ticket (the word after the last look-back record): whoever holds tile X knows
   // every tile < X is already held by a running CTA, which makes the emitter's look-back spin deadlock-free even if
   // the grid is not fully resident
-  int *ticket = reinterpret_cast<int *>(p.agg + (size_t)total);
+  int *ticket = p.ticket;
 
   if (USES_LUT) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
@@ -1148,6 +1148,18 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
       nbar_sync_id<NB>(2 + c);
       const int tile = s_tile[c];
       uint32_t bytes = 0;
+      if (tile >= 0 && !p.direct) { // measurement knob: scratch rows + k_stitch instead of look-back placement
+        const int t = tile % p.text_rows, f = tile / p.text_rows;
+        emit_row<MODE, SyncWarp, 32>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[c][0]),
+                                     reinterpret_cast<uint32_t *>(smem + L.c[c][1]),
+                                     reinterpret_cast<uint16_t *>(smem + L.key[a]),
+                                     reinterpret_cast<uint16_t *>(smem + L.hpos[a]),
+                                     reinterpret_cast<uint16_t *>(smem + L.rend[a]),
+                                     reinterpret_cast<uint32_t *>(smem + L.off[a]), outb, s_tmp, s_cond[a], lane);
+        __threadfence_block();
+        nbar_arrive_id<NB>(5 + c);
+        continue;
+      }
       if (tile >= 0) {
         const int t = tile % p.text_rows, f = tile / p.text_rows;
         bytes = emit_direct_prepare<MODE>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[c][0]),
