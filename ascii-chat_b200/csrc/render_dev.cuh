@@ -1108,12 +1108,17 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
   __syncthreads();
 
   if (tid < WS2_ST) { // ---------------- streamers
+    // The ticket for tile k+1 is requested while tile k is being summed: all CTAs ask in bursts, and a same-address
+    // atomic that is waited for on the spot costs a queueing delay per tile (measured: +20% kernel time).
+    int pending = 0;
+    if (tid == 0) pending = atomicAdd(ticket, 1);
     for (int k = 0;; k++) {
       const int c = k % 3;
       if (k >= 3) nbar_sync_id<NB>(5 + c); // the emitter has written out tile k-3: cells[c] / s_tile[c] are free
       if (tid == 0) {
-        const int tk = atomicAdd(ticket, 1);
+        const int tk = pending;
         s_tile[c] = tk < total ? tk : -1;
+        if (tk < total) pending = atomicAdd(ticket, 1);
       }
       SyncConsumers<WS2_ST>::sync();
       const int tile = s_tile[c];
