@@ -307,7 +307,7 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
   if (sp == SP_BOX_STREAM && pl.mode != EM_DITHER_BG && pl.use_smem_out && cfg.src_h >= cfg.rows_px) {
     static const char *which_env = getenv("ACB200_BOX_KERNEL");
     const char *which = which_env ? which_env : "split";
-    if (!strcmp(which, "split") && ws2_smem_total(cfg.cols, cfg.src_w, pl.row_pitch) <= kMaxDynSmem) {
+    if (!strcmp(which, "split") && ws2_smem_total(pl.mode, cfg.cols, cfg.src_w, pl.row_pitch) <= kMaxDynSmem) {
       pl.scale_path = SP_BOX_SPLIT;
     } else if (!strcmp(which, "tma") && ((3 * cfg.src_w) >> 4) <= 2048) {
       int d = ws_ring_depth(pl.mode, cfg.cols, cfg.src_w, pl.row_pitch);

@@ -93,7 +93,7 @@ static constexpr uint32_t kMaxDynSmem = 226u * 1024u; // dynamic smem ceiling (2
 cudaError_t launch_render_rows(const RenderParams &p, int mode, int scale_path, cudaStream_t st);
 cudaError_t launch_render_rows_ws(const RenderParams &p, int mode, cudaStream_t st);
 cudaError_t launch_render_rows_ws2(const RenderParams &p, int mode, cudaStream_t st);
-size_t ws2_smem_total(int cols, int src_w, uint32_t row_pitch);
+size_t ws2_smem_total(int mode, int cols, int src_w, uint32_t row_pitch);
 int ws_ring_depth(int mode, int cols, int src_w, uint32_t row_pitch);
 cudaError_t launch_stitch(const StitchParams &p, int n_frames, cudaStream_t st);
 cudaError_t launch_resize_nn_only(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh, int pregathered,

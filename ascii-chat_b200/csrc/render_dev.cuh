@@ -478,9 +478,9 @@ template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int
 // Phase B for one text row whose resized pixels are in cT/cB: keys -> runs -> byte counts -> offsets -> bytes,
 // staged in shared memory (or written straight to the scratch row when it is too wide) and copied out.
 // emit_prepare = B1..B3 (returns the byte count of the cells, offsets in off[]); emit_row adds B4 into the scratch row.
-template <int MODE, class Sync, int NT>
+template <int MODE, class Sync, int NT, class OffT = uint32_t>
 __device__ __forceinline__ uint32_t emit_prepare(const RenderParams &p, GlyphLut *lut, uint32_t *cT, uint32_t *cB,
-                                                 uint16_t *key, uint16_t *hpos, uint16_t *rend, uint32_t *off,
+                                                 uint16_t *key, uint16_t *hpos, uint16_t *rend, OffT *off,
                                                  int *s_tmp, uint32_t *s_cond, int tid) {
   constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
   constexpr bool RUNS = MODE == EM_MONO_FG || HB;
@@ -534,7 +534,7 @@ __device__ __forceinline__ uint32_t emit_prepare(const RenderParams &p, GlyphLut
         emit_cell<MODE>(cs, x, ctx);
         return (int)cs.n;
       },
-      [&](int x, int, int excl) { off[x] = (uint32_t)excl + (uint32_t)p.pad_left; }, s_tmp, tid);
+      [&](int x, int, int excl) { off[x] = (OffT)((uint32_t)excl + (uint32_t)p.pad_left); }, s_tmp, tid);
   return (uint32_t)cells_bytes;
 }
 
@@ -894,10 +894,10 @@ __device__ __forceinline__ uint32_t sgr_rgb_len(uint32_t c) { // bytes of ESC[38
 template <int MODE>
 __device__ __forceinline__ uint32_t emit_direct_prepare(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT,
                                                         uint32_t *cB, uint16_t *key, uint16_t *hpos, uint16_t *rend,
-                                                        uint32_t *off, int *s_tmp, uint32_t *s_cond, int lane) {
+                                                        uint16_t *off, int *s_tmp, uint32_t *s_cond, int lane) {
   const int w = p.cols;
   const bool last_row = t == p.text_rows - 1;
-  const uint32_t cells_bytes = emit_prepare<MODE, SyncWarp, 32>(p, lut, cT, cB, key, hpos, rend, off, s_tmp, s_cond, lane);
+  const uint32_t cells_bytes = emit_prepare<MODE, SyncWarp, 32, uint16_t>(p, lut, cT, cB, key, hpos, rend, off, s_tmp, s_cond, lane);
   if (MODE == EM_TRUE_FG) { // locate the row's first ASCII-glyph cell (s_cond[2] = last one, from the scan)
     for (int x = lane; x < w; x += 32)
       if (hpos[x] == NONE16) {
@@ -927,7 +927,7 @@ __device__ __forceinline__ uint32_t emit_direct_prepare(const RenderParams &p, i
 template <int MODE>
 __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT,
                                                    uint32_t *cB, uint16_t *key, uint16_t *hpos, uint16_t *rend,
-                                                   uint32_t *off, uint8_t *outb, const uint32_t *s_cond,
+                                                   const uint16_t *off, uint8_t *outb, const uint32_t *s_cond,
                                                    uint32_t cells_bytes, int lane) {
   const int w = p.cols;
   const bool last_row = t == p.text_rows - 1;
@@ -982,7 +982,7 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
   for (int i = lane; i < p.pad_left; i += 32) sb[i] = ' ';
   const uint32_t sb32 = (uint32_t)__cvta_generic_to_shared(sb);
   for (int x = lane; x < w; x += 32) {
-    const uint32_t o = off[x] - ((MODE == EM_TRUE_FG && drop && (uint32_t)x > first_x) ? drop : 0u);
+    const uint32_t o = (uint32_t)off[x] - ((MODE == EM_TRUE_FG && drop && (uint32_t)x > first_x) ? drop : 0u);
     SmemSink ss{sb32 + o};
     emit_cell<MODE>(ss, x, ctx);
   }
@@ -1031,25 +1031,29 @@ template <int ID, int N> __device__ __forceinline__ void nbar_arrive() {
 struct Layout2 {
   uint32_t lut, c[3][2], key[2], hpos[2], rend[2], off[2], V, outb, total;
 };
-__host__ __device__ inline Layout2 make_layout2(int cols, int src_w, uint32_t out_bytes) {
+// Shared memory is kept as small as the mode allows: four CTAs must fit under the 196 KB carve-out step, or the
+// L1 that backs the streamers' in-flight loads shrinks from 60 KB to 28 KB per SM (measured: -20% bandwidth).
+__host__ __device__ inline Layout2 make_layout2(int mode, int direct, int cols, int src_w, uint32_t out_bytes) {
   Layout2 L;
   uint32_t o = 0;
+  const bool uses_lut = mode <= EM_TRUE_FG;
+  const bool uses_key = mode == EM_MONO_FG || mode == EM_HB_256 || mode == EM_HB_16;
   L.lut = o;
-  o += al16((uint32_t)sizeof(GlyphLut));
+  o += uses_lut ? al16((uint32_t)sizeof(GlyphLut)) : 0u;
   for (int b = 0; b < 3; b++) // cell rows: one being summed, one prepared, one being written out
     for (int h = 0; h < 2; h++) {
       L.c[b][h] = o;
-      o += al16(4u * cols);
+      o += (h == 0 || (mode >= EM_HB_TRUE && mode <= EM_HB_MONO)) ? al16(4u * cols) : 0u;
     }
   for (int b = 0; b < 2; b++) { // run/offset arrays: prepared tile + tile being written out
     L.key[b] = o;
-    o += al16(2u * cols);
+    o += uses_key ? al16(2u * cols) : 0u;
     L.hpos[b] = o;
     o += al16(2u * cols);
     L.rend[b] = o;
     o += al16(2u * cols);
     L.off[b] = o;
-    o += al16(4u * cols);
+    o += al16((direct ? 2u : 4u) * cols); // row offsets fit 16 bits when the row is staged in shared memory
   }
   L.V = o;
   o += al16(2u * 3u * src_w);
@@ -1092,7 +1096,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
   const int tid = threadIdx.x;
   const int w = p.cols;
   const int total = p.n_frames * p.text_rows;
-  const Layout2 L = make_layout2(w, p.src_w, p.row_pitch);
+  const Layout2 L = make_layout2(MODE, p.direct, w, p.src_w, p.row_pitch);
   GlyphLut *lut = reinterpret_cast<GlyphLut *>(smem + L.lut);
   uint16_t *V = reinterpret_cast<uint16_t *>(smem + L.V);
   // tiles are handed out by an atomic ticket (the word after the last look-back record): whoever holds tile X knows
@@ -1172,7 +1176,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
                                           reinterpret_cast<uint16_t *>(smem + L.key[a]),
                                           reinterpret_cast<uint16_t *>(smem + L.hpos[a]),
                                           reinterpret_cast<uint16_t *>(smem + L.rend[a]),
-                                          reinterpret_cast<uint32_t *>(smem + L.off[a]), s_tmp, s_cond[a], lane);
+                                          reinterpret_cast<uint16_t *>(smem + L.off[a]), s_tmp, s_cond[a], lane);
       }
       if (prev_tile >= 0) {
         const int pc = (k - 1) % 3, pa = (k - 1) & 1;
@@ -1182,7 +1186,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
                                  reinterpret_cast<uint16_t *>(smem + L.key[pa]),
                                  reinterpret_cast<uint16_t *>(smem + L.hpos[pa]),
                                  reinterpret_cast<uint16_t *>(smem + L.rend[pa]),
-                                 reinterpret_cast<uint32_t *>(smem + L.off[pa]), outb, s_cond[pa], prev_bytes, lane);
+                                 reinterpret_cast<const uint16_t *>(smem + L.off[pa]), outb, s_cond[pa], prev_bytes, lane);
         __threadfence_block();
         nbar_arrive_id<NB>(5 + pc);
       }
@@ -1194,7 +1198,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
 }
 
 template <int MODE> static cudaError_t launch_ws2_mode(const RenderParams &p, cudaStream_t st) {
-  const Layout2 L = make_layout2(p.cols, p.src_w, p.row_pitch);
+  const Layout2 L = make_layout2(MODE, p.direct, p.cols, p.src_w, p.row_pitch);
   if (L.total > kMaxDynSmem) return cudaErrorInvalidConfiguration;
   static bool configured = false;
   static int ctas_per_sm = 1, sms = 148;

@@ -299,7 +299,9 @@ cudaError_t launch_render_rows_ws2(const RenderParams &p, int mode, cudaStream_t
   default: return cudaErrorInvalidValue;
   }
 }
-size_t ws2_smem_total(int cols, int src_w, uint32_t row_pitch) { return make_layout2(cols, src_w, row_pitch).total; }
+size_t ws2_smem_total(int mode, int cols, int src_w, uint32_t row_pitch) {
+  return make_layout2(mode, 0, cols, src_w, row_pitch).total; // worst case (scratch-row variant)
+}
 // ring depth for the warp-specialised kernel: as many source rows as fit half an SM's shared memory (two CTAs per
 // SM), 0 if the geometry does not qualify
 int ws_ring_depth(int mode, int cols, int src_w, uint32_t row_pitch) {
