@@ -312,7 +312,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic (uniform-noise RGB24, worst case "
         "for run-length: ~1.18 MB of ANSI per frame)", "config": config,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "kernel": "k_render_rows<EM_HB_TRUE, SP_BOX_STREAM>",
+                     "peak_source": peak_src, "kernel": "k_render_rows_ws2<EM_HB_TRUE> (role-split persistent, direct output)",
                      "algorithmic_bytes_per_launch": alg_bytes_launch,
                      "kernel_ms_per_launch": ms_kernel_max / args.steps,
                      "output_bytes_per_launch": out_bytes, "traffic": traffic_from_profiles()},
