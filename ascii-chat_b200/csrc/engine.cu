@@ -374,6 +374,25 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
     return E_OK;
   }
 
+  // Direct output (default wherever the text row is staged in shared memory): rows are placed in the final arena by a
+  // look-back over per-row records, so there is no stitch pass.  ACB200_DIRECT=0 forces scratch rows + k_stitch.
+  static const int direct_env = getenv("ACB200_DIRECT") ? atoi(getenv("ACB200_DIRECT")) : 1; // measurement knob
+  const bool direct = direct_env && pl.mode != EM_DITHER_BG && pl.use_smem_out && pl.scale_path != SP_BOX_TMA;
+  rp.direct = direct ? 1 : 0;
+  if (direct) {
+    rp.out = d_out;
+    rp.out_pitch = out_pitch;
+    rp.out_len = d_out_len;
+    rp.pad_top = cfg.pad_top;
+    // 16-byte look-back records live where the stitch path keeps its 32-byte RowMeta; the ticket word follows them,
+    // so one memset clears both
+    rp.agg = reinterpret_cast<uint4 *>(meta);
+    rp.ticket = reinterpret_cast<int *>(rp.agg + (size_t)n_frames * pl.text_rows);
+    ACB_CUDA(cudaMemsetAsync(meta, 0, ((size_t)n_frames * pl.text_rows + 1) * sizeof(uint4), st));
+  } else {
+    rp.ticket = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(err) + al256(pl.err_bytes * n_frames));
+    if (pl.scale_path == SP_BOX_SPLIT) ACB_CUDA(cudaMemsetAsync(rp.ticket, 0, sizeof(int), st));
+  }
   if (k0) cudaEventRecord(k0, st);
   const int kernel_sp = pl.scale_path >= SP_BOX_TMA ? (int)SP_BOX_STREAM : pl.scale_path;
   if (pl.mode != EM_DITHER_BG && pl.scale_path == SP_BOX_TMA) {
@@ -381,25 +400,8 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
     ACB_CUDA(launch_render_rows_ws(rp, pl.mode, st));
     count_launch();
   } else if (pl.mode != EM_DITHER_BG && pl.scale_path == SP_BOX_SPLIT) {
-    // direct output: rows land in the final arena, placed by the emitters' look-back; the per-row records (and the
-    // tile ticket behind them) live where the stitch path keeps its RowMeta array
-    rp.out = d_out;
-    rp.out_pitch = out_pitch;
-    rp.out_len = d_out_len;
-    rp.pad_top = cfg.pad_top;
-    static const int direct_env = getenv("ACB200_DIRECT") ? atoi(getenv("ACB200_DIRECT")) : 1; // measurement knob
-    rp.direct = direct_env;
-    // look-back records (direct) live where the stitch path keeps RowMeta; the tile ticket sits in its own word
-    rp.agg = reinterpret_cast<uint4 *>(meta);
-    rp.ticket = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(err) + al256(pl.err_bytes * n_frames));
-    if (direct_env) ACB_CUDA(cudaMemsetAsync(meta, 0, (size_t)n_frames * pl.text_rows * sizeof(uint4), st));
-    ACB_CUDA(cudaMemsetAsync(rp.ticket, 0, sizeof(int), st));
-    if (k0) cudaEventRecord(k0, st); // time the kernel alone
     ACB_CUDA(launch_render_rows_ws2(rp, pl.mode, st));
     count_launch();
-    if (k1) cudaEventRecord(k1, st);
-    if (direct_env) return E_OK;
-    goto stitch;
   } else if (pl.mode != EM_DITHER_BG) {
     ACB_CUDA(launch_render_rows(rp, pl.mode, kernel_sp, st));
     count_launch();
@@ -414,8 +416,8 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
     count_launch(2);
   }
   if (k1) cudaEventRecord(k1, st);
+  if (direct) return E_OK;
 
-stitch:
   StitchParams sp{};
   sp.rows = rows;
   sp.meta = meta;

@@ -224,14 +224,15 @@ __host__ __device__ inline Layout make_layout(int mode, int sp, int cols, int sr
   L.off = o;
   o += al16(4u * cols);
   const uint32_t vbytes = sp == SP_BOX_STREAM ? al16(2u * 3u * src_w) : 0u;
+  const uint32_t obytes = out_bytes ? al16(out_bytes) + 16u : 0u; // + room to stage with the destination's phase
   L.V = o;
   if (no_alias) {
     o += vbytes;
     L.outb = o;
-    o += al16(out_bytes);
+    o += obytes;
   } else {
     L.outb = o;
-    o += vbytes > al16(out_bytes) ? vbytes : al16(out_bytes);
+    o += vbytes > obytes ? vbytes : obytes;
   }
   L.total = o;
   return L;
@@ -601,6 +602,158 @@ __device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, Gl
   }
 }
 
+// ------------------------------------------------------------------ direct output: row-length look-back
+// One warp finishes a text row AND places it in the final frame string, so no stitch pass and no scratch rows:
+// after the byte counts are known the warp publishes {ready, len, first_rgb, last_rgb} for its row, reads the
+// records of the rows above (spinning until each is ready — they are being produced concurrently by other CTAs, and
+// tiles are handed out by an atomic ticket so every lower tile is already running), and derives its byte offset in
+// the frame.  For truecolor-foreground the same look-back carries the colour state of ansi_rle_add_pixel across
+// rows (ansi.c:263): each row's first ASCII-cell SGR is dropped iff its colour equals the last ASCII colour above.
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t sgr_rgb_len(uint32_t c) { // bytes of ESC[38;2;R;G;Bm
+  uint32_t r = (c >> 16) & 255u, g = (c >> 8) & 255u, b = c & 255u;
+  return 10u + (r >= 100u ? 3u : r >= 10u ? 2u : 1u) + (g >= 100u ? 3u : g >= 10u ? 2u : 1u) +
+         (b >= 100u ? 3u : b >= 10u ? 2u : 1u);
+}
+
+// prepare: B1..B3 for the row, then publish its record; never waits.  Returns the byte count of the cells.
+// NT threads (tid 0..NT-1) own the row: one warp in the role-split kernel, the whole CTA in the one-tile kernels.
+template <int MODE, class Sync, int NT>
+__device__ __forceinline__ uint32_t emit_direct_prepare(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT,
+                                                        uint32_t *cB, uint16_t *key, uint16_t *hpos, uint16_t *rend,
+                                                        uint16_t *off, int *s_tmp, uint32_t *s_cond, int tid) {
+  const int w = p.cols;
+  const bool last_row = t == p.text_rows - 1;
+  const uint32_t cells_bytes =
+      emit_prepare<MODE, Sync, NT, uint16_t>(p, lut, cT, cB, key, hpos, rend, off, s_tmp, s_cond, tid);
+  if (MODE == EM_TRUE_FG) { // locate the row's first ASCII-glyph cell (s_cond[2] = last one, from the scan)
+    for (int x = tid; x < w; x += NT)
+      if (hpos[x] == NONE16) {
+        const uint8_t *g = lut->glyph[luma_of(cT[x])];
+        if (g[0] == 1 && g[1] < 128) {
+          s_cond[0] = (uint32_t)x;
+          s_cond[3] = 0x01000000u | cT[x];
+        }
+      }
+    Sync::sync();
+  }
+  constexpr bool row_reset = MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16;
+  const uint32_t term_len = (row_reset ? 4u : 0u) + ((MODE == EM_TRUE_FG && last_row) ? 4u : 0u) + (last_row ? 0u : 1u);
+  if (tid == 0) {
+    uint32_t *me = reinterpret_cast<uint32_t *>(p.agg + (size_t)f * p.text_rows + t);
+    me[1] = (uint32_t)p.pad_left + cells_bytes + term_len;
+    me[2] = MODE == EM_TRUE_FG ? s_cond[3] : 0u;
+    me[3] = MODE == EM_TRUE_FG ? s_cond[2] : 0u;
+    __threadfence();
+    *reinterpret_cast<volatile uint32_t *>(me) = 1u;
+  }
+  return cells_bytes;
+}
+
+// finish: look-back for the row's offset (and, truecolor-fg, the colour state above), materialise, store.
+// The look-back is done by the first warp of the NT threads; s_lb (2 words of shared memory) broadcasts its result.
+template <int MODE, class Sync, int NT>
+__device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT,
+                                                   uint32_t *cB, uint16_t *key, uint16_t *hpos, uint16_t *rend,
+                                                   const uint16_t *off, uint8_t *outb, const uint32_t *s_cond,
+                                                   uint32_t *s_lb, uint32_t cells_bytes, int tid) {
+  const int w = p.cols;
+  const bool last_row = t == p.text_rows - 1;
+  constexpr bool row_reset = MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16;
+  const uint32_t term_len = (row_reset ? 4u : 0u) + ((MODE == EM_TRUE_FG && last_row) ? 4u : 0u) + (last_row ? 0u : 1u);
+  const uint32_t body_end = (uint32_t)p.pad_left + cells_bytes;
+  const uint32_t row_len = body_end + term_len;
+  const uint32_t first = MODE == EM_TRUE_FG ? s_cond[3] : 0u;
+  const uint32_t first_x = s_cond[0];
+
+  if (tid < 32) {
+    const int lane = tid;
+    const uint32_t *agg = reinterpret_cast<const uint32_t *>(p.agg + (size_t)f * p.text_rows); // 4 words per row
+    uint32_t prefix = 0, carry = 0;
+    for (int base = 0; base < t; base += 32) {
+      const int j = base + lane;
+      uint32_t len = 0, fj = 0, lj = 0;
+      if (j < t) {
+        const uint32_t *rec = agg + 4 * (size_t)j;
+        while (ld_volatile_u32(rec) == 0u) __nanosleep(64);
+        __threadfence();
+        len = ld_volatile_u32(rec + 1);
+        fj = ld_volatile_u32(rec + 2);
+        lj = ld_volatile_u32(rec + 3);
+      }
+      if (MODE == EM_TRUE_FG) {
+        uint32_t inc = lj; // inclusive "last non-zero" scan = colour state after row j
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d && inc == 0u) inc = o;
+        }
+        uint32_t before = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) before = 0u;
+        if (before == 0u) before = carry;
+        if (fj && before && fj == before) len -= sgr_rgb_len(fj);
+        const uint32_t tail = __shfl_sync(0xffffffffu, inc, 31);
+        if (tail) carry = tail;
+      }
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) len += __shfl_xor_sync(0xffffffffu, len, d);
+      prefix += len;
+    }
+    if (lane == 0) {
+      s_lb[0] = prefix;
+      s_lb[1] = carry;
+    }
+  }
+  Sync::sync();
+  const uint32_t prefix = s_lb[0], carry = s_lb[1];
+  const uint32_t drop = (MODE == EM_TRUE_FG && first && carry && first == carry) ? sgr_rgb_len(first) : 0u;
+  const uint32_t dst_off = (uint32_t)p.pad_top + prefix;
+  const uint32_t final_len = row_len - drop;
+  uint8_t *frame_out = p.out + (size_t)f * p.out_pitch;
+  uint8_t *dst = frame_out + dst_off;
+  const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u); // stage with the destination's alignment
+  uint8_t *sb = outb + shift;
+
+  // ---- B4: the row's bytes, already in their final form, into shared memory
+  RowCtx ctx{lut, cT, cB, key, hpos, rend, drop ? 1u : 0u};
+  for (int i = tid; i < p.pad_left; i += NT) sb[i] = ' ';
+  const uint32_t sb32 = (uint32_t)__cvta_generic_to_shared(sb);
+  for (int x = tid; x < w; x += NT) {
+    const uint32_t o = (uint32_t)off[x] - ((MODE == EM_TRUE_FG && drop && (uint32_t)x > first_x) ? drop : 0u);
+    SmemSink ss{sb32 + o};
+    emit_cell<MODE>(ss, x, ctx);
+  }
+  if (tid == 0) {
+    WriteSink ws{sb + body_end - drop};
+    if (row_reset) put_reset(ws);
+    if (MODE == EM_TRUE_FG && last_row) put_reset(ws); // ansi_rle_finish, ansi.c:303-314
+    if (!last_row) ws.put('\n');
+  }
+  Sync::sync();
+
+  // ---- copy out: unaligned head bytes, 16-byte body (source and destination share their alignment), tail bytes
+  uint32_t head = (16u - shift) & 15u;
+  if (head > final_len) head = final_len;
+  if ((uint32_t)tid < head) dst[tid] = sb[tid];
+  const uint32_t nvec = (final_len - head) >> 4;
+  const uint4 *s4 = reinterpret_cast<const uint4 *>(sb + head);
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+  for (uint32_t i = tid; i < nvec; i += NT) d4[i] = s4[i];
+  const uint32_t done = head + (nvec << 4);
+  if ((uint32_t)tid < final_len - done) dst[done + tid] = sb[done + tid];
+  if (t == 0)
+    for (int i = tid; i < p.pad_top; i += NT) frame_out[i] = '\n';
+  if (last_row && tid == 0) {
+    frame_out[dst_off + final_len] = 0;
+    p.out_len[f] = dst_off + final_len;
+  }
+  Sync::sync(); // the staging buffer and s_lb are reused by the next row
+}
+
 template <int MODE, int SP, int NT> __global__ void __launch_bounds__(NT) k_render_rows(const RenderParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_tmp[(NT / 32) + 1];
@@ -610,8 +763,17 @@ template <int MODE, int SP, int NT> __global__ void __launch_bounds__(NT) k_rend
   constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
 
   const int tid = threadIdx.x;
-  const int t = (int)(blockIdx.x % (unsigned)p.text_rows);
-  const int f = (int)(blockIdx.x / (unsigned)p.text_rows);
+  __shared__ int s_tile;
+  __shared__ uint32_t s_lb[2];
+  // direct output: rows find their place by look-back over earlier tiles, so tiles are taken from an atomic ticket
+  // (every lower tile is then known to be held by a running CTA); scratch-row output keeps the plain blockIdx mapping
+  if (p.direct) {
+    if (tid == 0) s_tile = atomicAdd(p.ticket, 1);
+    __syncthreads();
+  }
+  const unsigned tile = p.direct ? (unsigned)s_tile : blockIdx.x;
+  const int t = (int)(tile % (unsigned)p.text_rows);
+  const int f = (int)(tile / (unsigned)p.text_rows);
   const int w = p.cols;
 
   const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
@@ -669,6 +831,13 @@ template <int MODE, int SP, int NT> __global__ void __launch_bounds__(NT) k_rend
   }
   if (p.rows == nullptr) return; // resize-only invocation
 
+  if (p.direct) {
+    uint16_t *off16 = reinterpret_cast<uint16_t *>(off);
+    const uint32_t bytes =
+        emit_direct_prepare<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off16, s_tmp, s_cond, tid);
+    emit_direct_finish<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off16, outb, s_cond, s_lb, bytes, tid);
+    return;
+  }
   emit_row<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond, tid);
 }
 
@@ -872,147 +1041,6 @@ __global__ void __launch_bounds__(NT + 32) k_render_rows_ws(const RenderParams p
   }
 }
 
-// ------------------------------------------------------------------ direct output: row-length look-back
-// One warp finishes a text row AND places it in the final frame string, so no stitch pass and no scratch rows:
-// after the byte counts are known the warp publishes {ready, len, first_rgb, last_rgb} for its row, reads the
-// records of the rows above (spinning until each is ready — they are being produced concurrently by other CTAs, and
-// tiles are handed out by an atomic ticket so every lower tile is already running), and derives its byte offset in
-// the frame.  For truecolor-foreground the same look-back carries the colour state of ansi_rle_add_pixel across
-// rows (ansi.c:263): each row's first ASCII-cell SGR is dropped iff its colour equals the last ASCII colour above.
-__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint32_t sgr_rgb_len(uint32_t c) { // bytes of ESC[38;2;R;G;Bm
-  uint32_t r = (c >> 16) & 255u, g = (c >> 8) & 255u, b = c & 255u;
-  return 10u + (r >= 100u ? 3u : r >= 10u ? 2u : 1u) + (g >= 100u ? 3u : g >= 10u ? 2u : 1u) +
-         (b >= 100u ? 3u : b >= 10u ? 2u : 1u);
-}
-
-// prepare: B1..B3 for the row, then publish its record; never waits.  Returns the byte count of the cells.
-template <int MODE>
-__device__ __forceinline__ uint32_t emit_direct_prepare(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT,
-                                                        uint32_t *cB, uint16_t *key, uint16_t *hpos, uint16_t *rend,
-                                                        uint16_t *off, int *s_tmp, uint32_t *s_cond, int lane) {
-  const int w = p.cols;
-  const bool last_row = t == p.text_rows - 1;
-  const uint32_t cells_bytes = emit_prepare<MODE, SyncWarp, 32, uint16_t>(p, lut, cT, cB, key, hpos, rend, off, s_tmp, s_cond, lane);
-  if (MODE == EM_TRUE_FG) { // locate the row's first ASCII-glyph cell (s_cond[2] = last one, from the scan)
-    for (int x = lane; x < w; x += 32)
-      if (hpos[x] == NONE16) {
-        const uint8_t *g = lut->glyph[luma_of(cT[x])];
-        if (g[0] == 1 && g[1] < 128) {
-          s_cond[0] = (uint32_t)x;
-          s_cond[3] = 0x01000000u | cT[x];
-        }
-      }
-    __syncwarp();
-  }
-  constexpr bool row_reset = MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16;
-  const uint32_t term_len = (row_reset ? 4u : 0u) + ((MODE == EM_TRUE_FG && last_row) ? 4u : 0u) + (last_row ? 0u : 1u);
-  if (lane == 0) {
-    uint32_t *me = reinterpret_cast<uint32_t *>(p.agg + (size_t)f * p.text_rows + t);
-    me[1] = (uint32_t)p.pad_left + cells_bytes + term_len;
-    me[2] = MODE == EM_TRUE_FG ? s_cond[3] : 0u;
-    me[3] = MODE == EM_TRUE_FG ? s_cond[2] : 0u;
-    __threadfence();
-    *reinterpret_cast<volatile uint32_t *>(me) = 1u;
-  }
-  __syncwarp();
-  return cells_bytes;
-}
-
-// finish: look-back for the row's offset (and, truecolor-fg, the colour state above), materialise, store.
-template <int MODE>
-__device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT,
-                                                   uint32_t *cB, uint16_t *key, uint16_t *hpos, uint16_t *rend,
-                                                   const uint16_t *off, uint8_t *outb, const uint32_t *s_cond,
-                                                   uint32_t cells_bytes, int lane) {
-  const int w = p.cols;
-  const bool last_row = t == p.text_rows - 1;
-  constexpr bool row_reset = MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16;
-  const uint32_t term_len = (row_reset ? 4u : 0u) + ((MODE == EM_TRUE_FG && last_row) ? 4u : 0u) + (last_row ? 0u : 1u);
-  const uint32_t body_end = (uint32_t)p.pad_left + cells_bytes;
-  const uint32_t row_len = body_end + term_len;
-  const uint32_t first = MODE == EM_TRUE_FG ? s_cond[3] : 0u;
-  const uint32_t first_x = s_cond[0];
-
-  const uint32_t *agg = reinterpret_cast<const uint32_t *>(p.agg + (size_t)f * p.text_rows); // 4 words per row
-  uint32_t prefix = 0, carry = 0;
-  for (int base = 0; base < t; base += 32) {
-    const int j = base + lane;
-    uint32_t len = 0, fj = 0, lj = 0;
-    if (j < t) {
-      const uint32_t *rec = agg + 4 * (size_t)j;
-      while (ld_volatile_u32(rec) == 0u) __nanosleep(64);
-      __threadfence();
-      len = ld_volatile_u32(rec + 1);
-      fj = ld_volatile_u32(rec + 2);
-      lj = ld_volatile_u32(rec + 3);
-    }
-    if (MODE == EM_TRUE_FG) {
-      uint32_t inc = lj; // inclusive "last non-zero" scan = colour state after row j
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d && inc == 0u) inc = o;
-      }
-      uint32_t before = __shfl_up_sync(0xffffffffu, inc, 1);
-      if (lane == 0) before = 0u;
-      if (before == 0u) before = carry;
-      if (fj && before && fj == before) len -= sgr_rgb_len(fj);
-      const uint32_t tail = __shfl_sync(0xffffffffu, inc, 31);
-      if (tail) carry = tail;
-    }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) len += __shfl_xor_sync(0xffffffffu, len, d);
-    prefix += len;
-  }
-  const uint32_t drop = (MODE == EM_TRUE_FG && first && carry && first == carry) ? sgr_rgb_len(first) : 0u;
-  const uint32_t dst_off = (uint32_t)p.pad_top + prefix;
-  const uint32_t final_len = row_len - drop;
-  uint8_t *frame_out = p.out + (size_t)f * p.out_pitch;
-  uint8_t *dst = frame_out + dst_off;
-  const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u); // stage with the destination's alignment
-  uint8_t *sb = outb + shift;
-
-  // ---- B4: the row's bytes, already in their final form, into shared memory
-  RowCtx ctx{lut, cT, cB, key, hpos, rend, drop ? 1u : 0u};
-  for (int i = lane; i < p.pad_left; i += 32) sb[i] = ' ';
-  const uint32_t sb32 = (uint32_t)__cvta_generic_to_shared(sb);
-  for (int x = lane; x < w; x += 32) {
-    const uint32_t o = (uint32_t)off[x] - ((MODE == EM_TRUE_FG && drop && (uint32_t)x > first_x) ? drop : 0u);
-    SmemSink ss{sb32 + o};
-    emit_cell<MODE>(ss, x, ctx);
-  }
-  if (lane == 0) {
-    WriteSink ws{sb + body_end - drop};
-    if (row_reset) put_reset(ws);
-    if (MODE == EM_TRUE_FG && last_row) put_reset(ws); // ansi_rle_finish, ansi.c:303-314
-    if (!last_row) ws.put('\n');
-  }
-  __syncwarp();
-
-  // ---- copy out: unaligned head bytes, 16-byte body (source and destination share their alignment), tail bytes
-  uint32_t head = (16u - shift) & 15u;
-  if (head > final_len) head = final_len;
-  if ((uint32_t)lane < head) dst[lane] = sb[lane];
-  const uint32_t nvec = (final_len - head) >> 4;
-  const uint4 *s4 = reinterpret_cast<const uint4 *>(sb + head);
-  uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
-  for (uint32_t i = lane; i < nvec; i += 32) d4[i] = s4[i];
-  const uint32_t done = head + (nvec << 4);
-  if ((uint32_t)lane < final_len - done) dst[done + lane] = sb[done + lane];
-  if (t == 0)
-    for (int i = lane; i < p.pad_top; i += 32) frame_out[i] = '\n';
-  if (last_row && lane == 0) {
-    frame_out[dst_off + final_len] = 0;
-    p.out_len[f] = dst_off + final_len;
-  }
-  __syncwarp();
-}
-
 // ------------------------------------------------------------------ role-split persistent row kernel (LDG streamers)
 // Measured on B200: the streaming phase alone runs at ~98% of the copy-measured HBM peak, the one-tile-per-CTA fused
 // kernel at ~79%, because every CTA stops issuing loads for the ~20% of its life it spends in the latency-bound
@@ -1090,6 +1118,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
   __shared__ int s_tmp[2];
   __shared__ uint32_t s_cond[2][4];
   __shared__ int s_tile[3];
+  __shared__ uint32_t s_lb[2];
   constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
   constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
   constexpr int NB = WS2_ST + 32;
@@ -1171,7 +1200,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
       }
       if (tile >= 0) {
         const int t = tile % p.text_rows, f = tile / p.text_rows;
-        bytes = emit_direct_prepare<MODE>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[c][0]),
+        bytes = emit_direct_prepare<MODE, SyncWarp, 32>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[c][0]),
                                           reinterpret_cast<uint32_t *>(smem + L.c[c][1]),
                                           reinterpret_cast<uint16_t *>(smem + L.key[a]),
                                           reinterpret_cast<uint16_t *>(smem + L.hpos[a]),
@@ -1181,12 +1210,12 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
       if (prev_tile >= 0) {
         const int pc = (k - 1) % 3, pa = (k - 1) & 1;
         const int t = prev_tile % p.text_rows, f = prev_tile / p.text_rows;
-        emit_direct_finish<MODE>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[pc][0]),
+        emit_direct_finish<MODE, SyncWarp, 32>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[pc][0]),
                                  reinterpret_cast<uint32_t *>(smem + L.c[pc][1]),
                                  reinterpret_cast<uint16_t *>(smem + L.key[pa]),
                                  reinterpret_cast<uint16_t *>(smem + L.hpos[pa]),
                                  reinterpret_cast<uint16_t *>(smem + L.rend[pa]),
-                                 reinterpret_cast<const uint16_t *>(smem + L.off[pa]), outb, s_cond[pa], prev_bytes, lane);
+                                 reinterpret_cast<const uint16_t *>(smem + L.off[pa]), outb, s_cond[pa], s_lb, prev_bytes, lane);
         __threadfence_block();
         nbar_arrive_id<NB>(5 + pc);
       }
