@@ -754,7 +754,9 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
   Sync::sync(); // the staging buffer and s_lb are reused by the next row
 }
 
-template <int MODE, int SP, int NT> __global__ void __launch_bounds__(NT) k_render_rows(const RenderParams p) {
+// Emission-bound variants (NN sampling) want occupancy: eight 256-thread CTAs per SM = 32 registers per thread.
+template <int MODE, int SP, int NT>
+__global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) : 1) k_render_rows(const RenderParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_tmp[(NT / 32) + 1];
   __shared__ uint32_t s_cond[4]; // TRUE_FG: {cond_off, cond_len, last_rgb, first_rgb}
