@@ -59,7 +59,7 @@ EXPORTS = [  # every symbol include/asciichat_b200.h declares
     "acb200_set_allocator", "acb200_set_option_render_mode", "acb200_set_default_scale", "acb200_frame_capacity",
     "acb200_scratch_bytes", "acb200_render_batch_device", "acb200_render_batch_host", "acb200_time_batch_device",
     "acb200_composite_host", "acb200_grid_layout", "acb200_aspect_ratio", "acb200_launch_count", "acb200_version",
-    "acb200_create_grid_device",
+    "acb200_create_grid_device", "acb200_synchronize",
 ]
 
 
@@ -268,6 +268,13 @@ def frame_capacity(cfg):
 
 def scratch_bytes(cfg, n):
     return lib().acb200_scratch_bytes(C.byref(cfg), n)
+
+
+def synchronize():
+    """wait for the calling thread's internal stream (used when stream=None was passed to the device API)"""
+    rc = lib().acb200_synchronize()
+    if rc:
+        raise RuntimeError("acb200_synchronize failed: %s" % (last_error(),))
 
 
 def render_batch_device(cfg, d_frames, n, d_out, out_pitch, d_out_len, d_scratch, stream=None):

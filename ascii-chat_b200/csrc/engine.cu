@@ -608,6 +608,13 @@ int acb200_render_batch_device(const acb200_render_cfg_t *cfg, const uint8_t *d_
                        (uint8_t *)d_scratch, st);
 }
 
+int acb200_synchronize(void) {
+  ThreadCtx *cx = thread_ctx();
+  if (!cx) return t_err;
+  ACB_CUDA(cudaStreamSynchronize(cx->stream));
+  return E_OK;
+}
+
 int acb200_render_batch_host(const acb200_render_cfg_t *cfg, const uint8_t *const *frames, int n_frames, char **out,
                              size_t *out_len) {
   if (!cfg || !frames || !out || n_frames < 0) return set_error(E_INVALID_PARAM, "acb200_render_batch_host: NULL argument");

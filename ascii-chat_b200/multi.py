@@ -69,6 +69,18 @@ def render_clients_to_grid(acb, client_frames, cfg, grid_w, grid_h, dst=0, group
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    # One explicit (non-default) torch stream carries everything — our kernels, the NCCL collectives and the copies —
+    # so their order is the program order.  (A NULL stream handle would mean the library's own internal stream, which
+    # does not synchronise with torch's legacy default stream.)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        res = _render_clients_to_grid(acb, client_frames, cfg, grid_w, grid_h, dst, group, world, rank)
+    torch.cuda.current_stream().wait_stream(side)
+    return res
+
+
+def _render_clients_to_grid(acb, client_frames, cfg, grid_w, grid_h, dst, group, world, rank):
     n_clients = torch.tensor([len(client_frames)], dtype=torch.int64, device="cuda")
     dist.all_reduce(n_clients, group=group)
     n_clients = int(n_clients.item())

@@ -172,10 +172,14 @@ size_t acb200_scratch_bytes(const acb200_render_cfg_t *cfg, int n_frames);
  *   d_out    : n_frames * out_pitch bytes; frame f's string starts at f*out_pitch, NUL-terminated
  *   d_out_len: n_frames uint32 string lengths
  *   d_scratch: acb200_scratch_bytes() bytes
- *   stream   : a cudaStream_t cast to void* (NULL = this thread's internal stream)
+ *   stream   : a cudaStream_t cast to void*.  NULL = this thread's internal (non-blocking) stream, which does NOT
+ *              synchronise with the legacy default stream: wait for it with acb200_synchronize().
  * Asynchronous with respect to the host.  Returns 0 or an ERROR_* code. */
 int acb200_render_batch_device(const acb200_render_cfg_t *cfg, const uint8_t *d_frames, int n_frames, uint8_t *d_out,
                                size_t out_pitch, uint32_t *d_out_len, void *d_scratch, void *stream);
+
+/* Block until the calling thread's internal stream has drained.  0 or an ERROR_* code. */
+int acb200_synchronize(void);
 
 /* Same work from HOST buffers (H2D and D2H inside the call): frames[i] points at src_w*src_h*3 host bytes;
  * out[i] receives an allocator-owned NUL-terminated string, out_len[i] its length. */

@@ -192,6 +192,7 @@ def _device_batch(acb, frames, cfg):
     d_scr = torch.empty(acb.scratch_bytes(cfg, n), dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
     acb.render_batch_device(cfg, d_in.data_ptr(), n, d_out.data_ptr(), cap, d_len.data_ptr(), d_scr.data_ptr(), None)
+    acb.synchronize()
     tot, ker = acb.time_batch_device(cfg, d_in.data_ptr(), n, d_out.data_ptr(), cap, d_len.data_ptr(),
                                      d_scr.data_ptr(), 1)
     assert tot > 0 and ker > 0 and ker <= tot * 1.05
