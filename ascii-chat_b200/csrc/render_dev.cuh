@@ -595,7 +595,7 @@ __device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, Gl
   }
   Sync::sync();
   if (p.use_smem_out) {
-    const uint32_t n16 = (s_cond[0] + 15u) >> 4;
+    const uint32_t n16 = (s_cond[0] + 4u + 15u) >> 4; // k_stitch reads up to one word past the row (copy_shifted)
     const uint4 *s4 = reinterpret_cast<const uint4 *>(outb);
     uint4 *d4 = reinterpret_cast<uint4 *>(grow);
     for (uint32_t i = tid; i < n16; i += NT) d4[i] = s4[i];

@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(256) k_dither_bg(const uint8_t *cells, int w, 
       if (y < h - 1) ws.put('\n');
       RowMeta m{};
       m.len = (uint32_t)(ws.p - out);
+      for (int z = 0; z < 4; z++) ws.put(0); // k_stitch reads up to one word past the row (copy_shifted)
       meta[(size_t)f * h + y] = m;
     }
     __syncthreads();
