@@ -364,7 +364,8 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
   // measurement knobs (never set in production): ACB200_TUNE_NOALIAS=1, ACB200_PHASE_A_ONLY=1
   static const int tune_noalias = getenv("ACB200_TUNE_NOALIAS") ? atoi(getenv("ACB200_TUNE_NOALIAS")) : 0;
   static const int phase_a_only = getenv("ACB200_PHASE_A_ONLY") ? atoi(getenv("ACB200_PHASE_A_ONLY")) : 0;
-  rp.tune_flags = tune_noalias ? 1 : 0;
+  static const int ws2_noemit = getenv("ACB200_WS2_NOEMIT") ? atoi(getenv("ACB200_WS2_NOEMIT")) : 0;
+  rp.tune_flags = (tune_noalias ? 1 : 0) | (ws2_noemit ? 2 : 0);
   if (phase_a_only && pl.mode != EM_DITHER_BG) { // downscale only: rows == nullptr makes the kernel return after phase A
     rp.rows = nullptr;
     if (k0) cudaEventRecord(k0, st);

@@ -1188,6 +1188,11 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
       nbar_sync_id<NB>(2 + c);
       const int tile = s_tile[c];
       uint32_t bytes = 0;
+      if (tile >= 0 && (p.tune_flags & 2)) { // measurement knob ACB200_WS2_NOEMIT: streamers alone (output is garbage)
+        __threadfence_block();
+        nbar_arrive_id<NB>(5 + c);
+        continue;
+      }
       if (tile >= 0 && !p.direct) { // measurement knob: scratch rows + k_stitch instead of look-back placement
         const int t = tile % p.text_rows, f = tile / p.text_rows;
         emit_row<MODE, SyncWarp, 32>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[c][0]),
