@@ -327,7 +327,7 @@ __device__ __forceinline__ void acc16x2(uint32_t (&a)[8], const uint4 &u, const 
 // box filter, streaming: the band of source rows [y0,y1) is one contiguous byte range; every thread owns
 // 16-byte columns of it, sums them down the band in registers (u16 lanes, band <= 256 rows), parks the
 // column sums V[3*src_w] in shared memory, then one thread per destination pixel adds its x-range.
-template <int NT, class Sync = SyncAll, int UNROLL = kBandUnroll>
+template <int NT, class Sync = SyncAll>
 __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const uint8_t *frame, int y, uint32_t *out,
                                                  uint16_t *V) {
   int y0, y1;
@@ -339,13 +339,13 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
   for (int c = threadIdx.x; c < nchunk; c += NT) {
     uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const uint8_t *q = reinterpret_cast<const uint8_t *>(band + c);
-    // One batch of UNROLL independent, predicated 16-byte loads per trip: a typical band (11-12 rows at
+    // One batch of kBandUnroll independent, predicated 16-byte loads per trip: a typical band (11-12 rows at
     // 4K -> 192 pixel rows) is a single trip, i.e. one memory latency per column instead of one per tail row.
     // The row pointer advances by the 32-bit row pitch (one wide multiply-add per load, no 64-bit index maths).
-    for (int r = 0; r < nrow; r += UNROLL) {
-      uint4 v[UNROLL];
+    for (int r = 0; r < nrow; r += kBandUnroll) {
+      uint4 v[kBandUnroll];
 #pragma unroll
-      for (int k = 0; k < UNROLL; k++) {
+      for (int k = 0; k < kBandUnroll; k++) {
         if (r + k < nrow)
           v[k] = ldg_stream(reinterpret_cast<const uint4 *>(q));
         else
@@ -353,7 +353,7 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
         q += (uint32_t)R;
       }
 #pragma unroll
-      for (int k = 0; k < UNROLL; k += 2) acc16x2(a, v[k], v[k + 1]);
+      for (int k = 0; k < kBandUnroll; k += 2) acc16x2(a, v[k], v[k + 1]);
     }
     // byte j of word k is column 16c + 4k + j:  even reg = {b0 | b2<<16}, odd reg = {b1 | b3<<16}
     uint4 lo, hi;
@@ -1051,11 +1051,6 @@ __global__ void __launch_bounds__(NT + 32) k_render_rows_ws(const RenderParams p
 // (the same emit_row code, instantiated for a single warp) while the streamers are already summing tile k+1.
 //   named barriers: 1 streamers only (256) | 2,3 cells[b] full (256 arrive + 32 sync) | 4,5 cells[b] empty (32 arrive + 256 sync)
 constexpr int WS2_ST = 256; // streamer threads
-constexpr int WS2_EM = 64;  // emitter threads (two warps: one alone cannot keep up with eight streamer warps)
-constexpr int WS2_UNROLL = 8; // loads in flight per streamer thread (keeps the kernel at 48 registers: 4 CTAs/SM)
-struct SyncEmit { // the emitter warps of the role-split kernel, named barrier 8
-  static __device__ __forceinline__ void sync() { asm volatile("bar.sync 8, %0;" ::"n"(WS2_EM) : "memory"); }
-};
 template <int ID, int N> __device__ __forceinline__ void nbar_sync() {
   asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory");
 }
@@ -1120,15 +1115,15 @@ template <int N> __device__ __forceinline__ void nbar_arrive_id(int id) {
   }
 }
 
-template <int MODE> __global__ void __launch_bounds__(WS2_ST + WS2_EM, 4) k_render_rows_ws2(const RenderParams p) {
+template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows_ws2(const RenderParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ int s_tmp[WS2_EM / 32 + 1];
+  __shared__ int s_tmp[2];
   __shared__ uint32_t s_cond[2][4];
   __shared__ int s_tile[3];
   __shared__ uint32_t s_lb[2];
   constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
   constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
-  constexpr int NB = WS2_ST + WS2_EM;
+  constexpr int NB = WS2_ST + 32;
   const int tid = threadIdx.x;
   const int w = p.cols;
   const int total = p.n_frames * p.text_rows;
@@ -1174,14 +1169,14 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + WS2_EM, 4) k_rend
       const uint8_t *frame = p.frames + (size_t)f * p.frame_stride;
       const int yT = HB ? 2 * t : t;
       const bool hasB = HB && (2 * t + 1 < p.rows_px);
-      cells_box_stream<WS2_ST, SyncConsumers<WS2_ST>, WS2_UNROLL>(p, frame, yT, cT, V);
-      if (hasB) cells_box_stream<WS2_ST, SyncConsumers<WS2_ST>, WS2_UNROLL>(p, frame, yT + 1, cB, V);
+      cells_box_stream<WS2_ST, SyncConsumers<WS2_ST>>(p, frame, yT, cT, V);
+      if (hasB) cells_box_stream<WS2_ST, SyncConsumers<WS2_ST>>(p, frame, yT + 1, cB, V);
       if (HB && !hasB)
         for (int x = tid; x < w; x += WS2_ST) cB[x] = cT[x];
       __threadfence_block();
       nbar_arrive_id<NB>(2 + c); // cells[c] are complete: hand them to the emitter and move on
     }
-  } else { // ---------------- emitter warps, software-pipelined by one tile:
+  } else { // ---------------- emitter warp, software-pipelined by one tile:
     //   iteration k: prepare + publish tile k (never waits), then look-back + write-out of tile k-1, whose
     //   predecessors have had a whole tile period to publish — so a late row cannot start a convoy
     const int lane = tid - WS2_ST;
@@ -1200,7 +1195,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + WS2_EM, 4) k_rend
       }
       if (tile >= 0 && !p.direct) { // measurement knob: scratch rows + k_stitch instead of look-back placement
         const int t = tile % p.text_rows, f = tile / p.text_rows;
-        emit_row<MODE, SyncEmit, WS2_EM>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[c][0]),
+        emit_row<MODE, SyncWarp, 32>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[c][0]),
                                      reinterpret_cast<uint32_t *>(smem + L.c[c][1]),
                                      reinterpret_cast<uint16_t *>(smem + L.key[a]),
                                      reinterpret_cast<uint16_t *>(smem + L.hpos[a]),
@@ -1212,7 +1207,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + WS2_EM, 4) k_rend
       }
       if (tile >= 0) {
         const int t = tile % p.text_rows, f = tile / p.text_rows;
-        bytes = emit_direct_prepare<MODE, SyncEmit, WS2_EM>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[c][0]),
+        bytes = emit_direct_prepare<MODE, SyncWarp, 32>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[c][0]),
                                           reinterpret_cast<uint32_t *>(smem + L.c[c][1]),
                                           reinterpret_cast<uint16_t *>(smem + L.key[a]),
                                           reinterpret_cast<uint16_t *>(smem + L.hpos[a]),
@@ -1222,7 +1217,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + WS2_EM, 4) k_rend
       if (prev_tile >= 0) {
         const int pc = (k - 1) % 3, pa = (k - 1) & 1;
         const int t = prev_tile % p.text_rows, f = prev_tile / p.text_rows;
-        emit_direct_finish<MODE, SyncEmit, WS2_EM>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[pc][0]),
+        emit_direct_finish<MODE, SyncWarp, 32>(p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.c[pc][0]),
                                  reinterpret_cast<uint32_t *>(smem + L.c[pc][1]),
                                  reinterpret_cast<uint16_t *>(smem + L.key[pa]),
                                  reinterpret_cast<uint16_t *>(smem + L.hpos[pa]),
@@ -1251,7 +1246,7 @@ template <int MODE> static cudaError_t launch_ws2_mode(const RenderParams &p, cu
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_render_rows_ws2<MODE>, WS2_ST + WS2_EM, L.total);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_render_rows_ws2<MODE>, WS2_ST + 32, L.total);
     if (e != cudaSuccess || ctas_per_sm < 1) return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
     cfg_smem = L.total;
     configured = true;
@@ -1259,7 +1254,7 @@ template <int MODE> static cudaError_t launch_ws2_mode(const RenderParams &p, cu
   const long long total = (long long)p.n_frames * p.text_rows;
   long long grid = (long long)sms * ctas_per_sm;
   if (grid > total) grid = total;
-  k_render_rows_ws2<MODE><<<(unsigned)grid, WS2_ST + WS2_EM, L.total, st>>>(p);
+  k_render_rows_ws2<MODE><<<(unsigned)grid, WS2_ST + 32, L.total, st>>>(p);
   return cudaGetLastError();
 }
 
