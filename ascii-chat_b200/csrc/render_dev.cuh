@@ -63,19 +63,48 @@ template <int NT> struct SyncConsumers {
 };
 
 // ------------------------------------------------------------------ byte sinks
+// Decimal strings of 0..255 for the emitters: s_dec3[v] = ASCII digits, most significant first, in bytes 0..2 and
+// the digit count in byte 3 (the dec3 table of common.c:546-570).  put_dec3 stores all three digit bytes blindly and
+// advances by the count: the one or two surplus bytes are overwritten by whatever the same thread emits next (every
+// number on this path is followed by ';' or 'm' plus at least one glyph byte), which removes all digit branching.
+static __shared__ uint32_t s_dec3[256];
+template <int NT> __device__ __forceinline__ void init_dec3(int tid) {
+  for (int v = tid; v < 256; v += NT) {
+    const uint32_t h = (uint32_t)v / 100u, r = (uint32_t)v - h * 100u, t = r / 10u, u = r - t * 10u;
+    uint32_t e;
+    if (h) e = ('0' + h) | (('0' + t) << 8) | (('0' + u) << 16) | (3u << 24);
+    else if (t) e = ('0' + t) | (('0' + u) << 8) | (2u << 24);
+    else e = ('0' + u) | (1u << 24);
+    s_dec3[v] = e;
+  }
+}
+
 struct CountSink {
   uint32_t n = 0;
   __device__ __forceinline__ void put(uint8_t) { ++n; }
+  __device__ __forceinline__ void put_dec3(uint32_t e) { n += e >> 24; }
 };
 struct WriteSink {
   uint8_t *p;
   __device__ __forceinline__ void put(uint8_t c) { *p++ = c; }
+  __device__ __forceinline__ void put_dec3(uint32_t e) {
+    p[0] = (uint8_t)e;
+    p[1] = (uint8_t)(e >> 8);
+    p[2] = (uint8_t)(e >> 16);
+    p += e >> 24;
+  }
 };
 struct SmemSink { // same, but the destination is known to be shared memory: STS with a 32-bit address
   uint32_t a;
   __device__ __forceinline__ void put(uint8_t c) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"((uint32_t)c) : "memory");
     ++a;
+  }
+  __device__ __forceinline__ void put_dec3(uint32_t e) {
+    asm volatile("st.shared.u8 [%0], %1;\n\tst.shared.u8 [%0+1], %2;\n\tst.shared.u8 [%0+2], %3;" ::"r"(a), "r"(e & 255u),
+                 "r"((e >> 8) & 255u), "r"((e >> 16) & 255u)
+                 : "memory");
+    a += e >> 24;
   }
 };
 
@@ -132,6 +161,40 @@ template <class S> __device__ __forceinline__ void put_sgr_16(S &s, bool bg, uin
   s.put(0x1b);
   s.put('[');
   put_u8dec(s, code);
+  s.put('m');
+}
+// table-driven variants used by the row emitters (the arithmetic ones above stay for the serial dither kernel)
+template <class S> __device__ __forceinline__ void put_sgr_rgb_l(S &s, bool bg, uint32_t c) {
+  s.put(0x1b);
+  s.put('[');
+  s.put(bg ? '4' : '3');
+  s.put('8');
+  s.put(';');
+  s.put('2');
+  s.put(';');
+  s.put_dec3(s_dec3[(c >> 16) & 255u]);
+  s.put(';');
+  s.put_dec3(s_dec3[(c >> 8) & 255u]);
+  s.put(';');
+  s.put_dec3(s_dec3[c & 255u]);
+  s.put('m');
+}
+template <class S> __device__ __forceinline__ void put_sgr_256_l(S &s, bool bg, uint32_t idx) {
+  s.put(0x1b);
+  s.put('[');
+  s.put(bg ? '4' : '3');
+  s.put('8');
+  s.put(';');
+  s.put('5');
+  s.put(';');
+  s.put_dec3(s_dec3[idx & 255u]);
+  s.put('m');
+}
+template <class S> __device__ __forceinline__ void put_sgr_16_l(S &s, bool bg, uint32_t idx) {
+  const uint32_t code = (idx < 8u ? 30u + idx : 82u + idx) + (bg ? 10u : 0u);
+  s.put(0x1b);
+  s.put('[');
+  s.put_dec3(s_dec3[code]);
   s.put('m');
 }
 template <class S> __device__ __forceinline__ void put_reset(S &s) {
@@ -398,11 +461,11 @@ struct RowCtx {
 template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int x, const RowCtx &c) {
   if (MODE == EM_256_FG) {
     uint32_t px = c.cT[x];
-    put_sgr_256(s, false, (uint32_t)q256_of(px));
+    put_sgr_256_l(s, false, (uint32_t)q256_of(px));
     put_glyph(s, c.lut->glyph[luma_of(px)]);
   } else if (MODE == EM_16_FG) {
     uint32_t px = c.cT[x];
-    put_sgr_16(s, false, (uint32_t)q16_of(px));
+    put_sgr_16_l(s, false, (uint32_t)q16_of(px));
     put_glyph(s, c.lut->glyph[luma_of(px)]);
   } else if (MODE == EM_TRUE_FG) {
     // ansi_rle_add_pixel (ansi.c:261-300) as a cell rule; hpos[x] = previous ASCII-glyph cell of this row
@@ -411,10 +474,10 @@ template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int
     bool ascii = g[0] == 1 && g[1] < 128;
     if (ascii) {
       uint16_t pa = c.hpos[x];
-      if (pa == NONE16 ? !c.drop_first : c.cT[pa] != px) put_sgr_rgb(s, false, px);
+      if (pa == NONE16 ? !c.drop_first : c.cT[pa] != px) put_sgr_rgb_l(s, false, px);
       s.put(g[1]);
     } else {
-      put_sgr_rgb(s, false, px);
+      put_sgr_rgb_l(s, false, px);
       put_glyph(s, g);
     }
   } else if (MODE == EM_MONO_FG) {
@@ -456,16 +519,16 @@ template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int
       s.put(' ');
     } else if (h == x) {
       if (MODE == EM_HB_TRUE) {
-        if (!prev_set || c.cT[ph] != tH) put_sgr_rgb(s, false, tH);
-        if (!prev_set || c.cB[ph] != bH) put_sgr_rgb(s, true, bH);
+        if (!prev_set || c.cT[ph] != tH) put_sgr_rgb_l(s, false, tH);
+        if (!prev_set || c.cB[ph] != bH) put_sgr_rgb_l(s, true, bH);
       } else {
         uint32_t k = c.key[h], pk = prev_set ? c.key[ph] : 0u;
         if (MODE == EM_HB_256) {
-          if (!prev_set || (pk >> 8) != (k >> 8)) put_sgr_256(s, false, k >> 8);
-          if (!prev_set || (pk & 255u) != (k & 255u)) put_sgr_256(s, true, k & 255u);
+          if (!prev_set || (pk >> 8) != (k >> 8)) put_sgr_256_l(s, false, k >> 8);
+          if (!prev_set || (pk & 255u) != (k & 255u)) put_sgr_256_l(s, true, k & 255u);
         } else {
-          if (!prev_set || (pk >> 8) != (k >> 8)) put_sgr_16(s, false, k >> 8);
-          if (!prev_set || (pk & 255u) != (k & 255u)) put_sgr_16(s, true, k & 255u);
+          if (!prev_set || (pk >> 8) != (k >> 8)) put_sgr_16_l(s, false, k >> 8);
+          if (!prev_set || (pk & 255u) != (k & 255u)) put_sgr_16_l(s, true, k & 255u);
         }
       }
       put3(s, 0xE2, 0x96, 0x80);
@@ -564,10 +627,9 @@ __device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, Gl
     if (MODE == EM_TRUE_FG && hpos[x] == NONE16) {
       const uint8_t *g = lut->glyph[luma_of(cT[x])];
       if (g[0] == 1 && g[1] < 128) { // the row's first ASCII-glyph cell: its SGR is conditional on the row above
-        CountSink cs;
-        put_sgr_rgb(cs, false, cT[x]);
         s_cond[0] = off[x];
-        s_cond[1] = cs.n;
+        s_cond[1] = 10u + (s_dec3[(cT[x] >> 16) & 255u] >> 24) + (s_dec3[(cT[x] >> 8) & 255u] >> 24) +
+                    (s_dec3[cT[x] & 255u] >> 24);
         s_cond[3] = 0x01000000u | cT[x];
       }
     }
@@ -795,6 +857,7 @@ __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) :
     uint32_t *dst = reinterpret_cast<uint32_t *>(lut);
     for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += NT) dst[i] = src[i];
   }
+  init_dec3<NT>(tid);
 
   // ---- phase A
   const uint8_t *frame = p.frames + (size_t)f * p.frame_stride;
@@ -938,6 +1001,7 @@ __global__ void __launch_bounds__(NT + 32) k_render_rows_ws(const RenderParams p
     uint32_t *dst = reinterpret_cast<uint32_t *>(lut);
     for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += NT) dst[i] = src[i];
   }
+  if (tid < NT) init_dec3<NT>(tid);
   __syncthreads(); // the only CTA-wide barrier: after it the producer warp and the consumer warps part ways
 
   if (warp == (NT / 32)) { // ---------------- producer: one lane walks the same tile/row sequence as the consumers
@@ -1140,6 +1204,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
     uint32_t *dst = reinterpret_cast<uint32_t *>(lut);
     for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += NB) dst[i] = src[i];
   }
+  init_dec3<NB>(tid);
   __syncthreads();
 
   if (tid < WS2_ST) { // ---------------- streamers
