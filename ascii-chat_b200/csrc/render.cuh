@@ -88,7 +88,7 @@ __host__ __device__ inline uint32_t al16(uint32_t v) { return (v + 15u) & ~15u; 
 size_t rows_smem_total(int mode, int scale_path, int cols, int src_w, uint32_t out_bytes);
 uint32_t row_capacity_bytes(int mode, int cols, int pad_left);
 static constexpr int kSmemOutMax = 48 * 1024;      // rows up to this many bytes are staged in shared memory
-static constexpr uint32_t kMaxDynSmem = 226u * 1024u; // dynamic smem ceiling (227 KB opt-in minus static)
+static constexpr uint32_t kMaxDynSmem = 224u * 1024u; // dynamic smem ceiling (227 KB opt-in minus static, incl. the 1 KB digit table)
 
 cudaError_t launch_render_rows(const RenderParams &p, int mode, int scale_path, cudaStream_t st);
 cudaError_t launch_render_rows_ws(const RenderParams &p, int mode, cudaStream_t st);

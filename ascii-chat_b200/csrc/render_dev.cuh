@@ -1305,8 +1305,7 @@ template <int MODE> static cudaError_t launch_ws2_mode(const RenderParams &p, cu
   static int ctas_per_sm = 1, sms = 148;
   static size_t cfg_smem = 0;
   if (!configured || cfg_smem != L.total) {
-    cudaError_t e = cudaFuncSetAttribute(k_render_rows_ws2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kMaxDynSmem);
+    cudaError_t e = allow_max_dyn_smem(k_render_rows_ws2<MODE>);
     if (e != cudaSuccess) return e;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1323,6 +1322,14 @@ template <int MODE> static cudaError_t launch_ws2_mode(const RenderParams &p, cu
   return cudaGetLastError();
 }
 
+// opt in to the largest dynamic shared memory the kernel can have: 227 KB per CTA minus its static allocation
+template <class K> static cudaError_t allow_max_dyn_smem(K kernel) {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
+}
+
 // ------------------------------------------------------------------ per-mode launch templates
 // NT (threads that own cells / byte columns) is chosen so that one pass of the CTA covers the text row:
 // 128, 256, 384 or 512.
@@ -1337,8 +1344,7 @@ template <int MODE, int SP, int NT> static cudaError_t launch_rows_t(const Rende
   static bool configured = false; // benign race: the attribute is idempotent
   if (!configured) {
     // opt-in limit is 227 KB per CTA for static + dynamic together; the kernel has < 1 KB static
-    cudaError_t e = cudaFuncSetAttribute(k_render_rows<MODE, SP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kMaxDynSmem);
+    cudaError_t e = allow_max_dyn_smem(k_render_rows<MODE, SP, NT>);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -1368,8 +1374,7 @@ template <int MODE, int CPT, int NT> static cudaError_t launch_ws_t(const Render
   static int ctas_per_sm = 1, sms = 148;
   static size_t cfg_smem = 0;
   if (!configured || smem != cfg_smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_render_rows_ws<MODE, CPT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kMaxDynSmem);
+    cudaError_t e = allow_max_dyn_smem(k_render_rows_ws<MODE, CPT, NT>);
     if (e != cudaSuccess) return e;
     int dev = 0;
     cudaGetDevice(&dev);
