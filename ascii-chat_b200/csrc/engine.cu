@@ -365,7 +365,22 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
   static const int tune_noalias = getenv("ACB200_TUNE_NOALIAS") ? atoi(getenv("ACB200_TUNE_NOALIAS")) : 0;
   static const int phase_a_only = getenv("ACB200_PHASE_A_ONLY") ? atoi(getenv("ACB200_PHASE_A_ONLY")) : 0;
   static const int ws2_noemit = getenv("ACB200_WS2_NOEMIT") ? atoi(getenv("ACB200_WS2_NOEMIT")) : 0;
-  rp.tune_flags = (tune_noalias ? 1 : 0) | (ws2_noemit ? 2 : 0);
+  static const int ws2_dbg = getenv("ACB200_WS2_DBG") ? atoi(getenv("ACB200_WS2_DBG")) : 0;
+  static unsigned long long *d_dbg = nullptr;
+  if (ws2_dbg && !d_dbg) {
+    cudaMalloc((void **)&d_dbg, 4 * sizeof(unsigned long long));
+    cudaMemset(d_dbg, 0, 4 * sizeof(unsigned long long));
+  }
+  rp.dbg = d_dbg;
+  rp.tune_flags = (tune_noalias ? 1 : 0) | (ws2_noemit ? 2 : 0) | (ws2_dbg ? 4 : 0);
+  if (ws2_dbg && getenv("ACB200_WS2_DBG_PRINT")) { // print-and-reset on demand (set by the measurement script)
+    unsigned long long h[4];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    if (h[3]) fprintf(stderr, "[ws2 dbg] per emitter iteration: streamers wait-empty %.0f cyc, emitter wait-full %.0f cyc, emitter busy %.0f cyc (n=%llu)\n",
+                      (double)h[0] / h[3], (double)h[1] / h[3], (double)h[2] / h[3], h[3]);
+    cudaMemset(d_dbg, 0, sizeof(h));
+  }
   if (phase_a_only && pl.mode != EM_DITHER_BG) { // downscale only: rows == nullptr makes the kernel return after phase A
     rp.rows = nullptr;
     if (k0) cudaEventRecord(k0, st);

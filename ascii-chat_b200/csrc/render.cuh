@@ -67,6 +67,7 @@ struct RenderParams {
   int pad_top;
   int direct;             // 1: emitters place rows in the final arena (look-back); 0: scratch rows + k_stitch
   int ring_depth;         // warp-specialised kernel: source rows kept in flight by the producer warp
+  unsigned long long *dbg; // measurement counters (tune_flags bit 2): streamer wait, emitter wait, emitter busy, tiles
   int tune_flags;         // bit0: do not alias V with the row staging buffer (measurement knob)
 };
 

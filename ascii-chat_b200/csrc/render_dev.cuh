@@ -1214,7 +1214,11 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
     if (tid == 0) pending = atomicAdd(ticket, 1);
     for (int k = 0;; k++) {
       const int c = k % 3;
-      if (k >= 3) nbar_sync_id<NB>(5 + c); // the emitter has written out tile k-3: cells[c] / s_tile[c] are free
+      if (k >= 3) { // the emitter has written out tile k-3: cells[c] / s_tile[c] are free
+        const long long t0 = (p.tune_flags & 4) ? clock64() : 0;
+        nbar_sync_id<NB>(5 + c);
+        if ((p.tune_flags & 4) && tid == 0) atomicAdd(p.dbg + 0, (unsigned long long)(clock64() - t0));
+      }
       if (tid == 0) {
         const int tk = pending;
         s_tile[c] = tk < total ? tk : -1;
@@ -1248,9 +1252,18 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
     uint8_t *outb = smem + L.outb;
     uint32_t prev_bytes = 0;
     int prev_tile = -1;
+    long long t_prev = 0;
     for (int k = 0;; k++) {
       const int c = k % 3, a = k & 1;
+      const long long t0 = (p.tune_flags & 4) ? clock64() : 0;
       nbar_sync_id<NB>(2 + c);
+      const long long t1 = (p.tune_flags & 4) ? clock64() : 0;
+      if ((p.tune_flags & 4) && lane == 0) {
+        atomicAdd(p.dbg + 1, (unsigned long long)(t1 - t0));          // emitter waiting for cells
+        if (k > 0) atomicAdd(p.dbg + 2, (unsigned long long)(t0 - t_prev)); // emitter busy with the previous iteration
+        atomicAdd(p.dbg + 3, 1ull);
+      }
+      t_prev = t1;
       const int tile = s_tile[c];
       uint32_t bytes = 0;
       if (tile >= 0 && (p.tune_flags & 2)) { // measurement knob ACB200_WS2_NOEMIT: streamers alone (output is garbage)
