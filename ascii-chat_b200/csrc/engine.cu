@@ -328,18 +328,18 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
 }
 
 static size_t scratch_bytes(const Plan &pl, int n) {
-  return al256(pl.rows_bytes * n) + al256(pl.meta_bytes * n) + al256(pl.cells_bytes * n) + al256(pl.err_bytes * n) +
-         256; // + the tile ticket of the persistent kernels
+  return 256 /* header: tile ticket */ + al256(pl.rows_bytes * n) + al256(pl.meta_bytes * n) +
+         al256(pl.cells_bytes * n) + al256(pl.err_bytes * n);
 }
 
 // ------------------------------------------------------------------ the device pipeline
 int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t *d_frames, size_t frame_stride,
                   int pregathered, int n_frames, uint8_t *d_out, size_t out_pitch, uint32_t *d_out_len,
-                  uint8_t *d_scratch, cudaStream_t st, cudaEvent_t k0, cudaEvent_t k1) {
+                  uint8_t *d_scratch, cudaStream_t st, cudaEvent_t k0, cudaEvent_t k1, LookbackState *ls) {
   if (n_frames <= 0) return E_OK;
   const GlyphLut *lut = device_lut(cfg.palette[0] ? cfg.palette : " ", pl.lut_which);
   if (!lut) return t_err;
-  uint8_t *rows = d_scratch;
+  uint8_t *rows = d_scratch + 256; // the first 256 bytes hold the tile ticket (fixed place for any plan)
   RowMeta *meta = reinterpret_cast<RowMeta *>(rows + al256(pl.rows_bytes * n_frames));
   uint8_t *cells = reinterpret_cast<uint8_t *>(meta) + al256(pl.meta_bytes * n_frames);
   int *err = reinterpret_cast<int *>(cells + al256(pl.cells_bytes * n_frames));
@@ -395,20 +395,29 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
   static const int direct_env = getenv("ACB200_DIRECT") ? atoi(getenv("ACB200_DIRECT")) : 1; // measurement knob
   const bool direct = direct_env && pl.mode != EM_DITHER_BG && pl.use_smem_out && pl.scale_path != SP_BOX_TMA;
   rp.direct = direct ? 1 : 0;
+  rp.ticket = reinterpret_cast<int *>(d_scratch);
+  const bool uses_ticket = direct || pl.scale_path == SP_BOX_SPLIT;
+  const uint32_t tickets_taken =
+      pl.scale_path == SP_BOX_SPLIT ? 0u /* + grid, added below */ : (uint32_t)n_frames * (uint32_t)pl.text_rows;
+  if (ls && uses_ticket) {
+    // library-owned scratch (host path): it was zeroed when allocated; instead of clearing per launch, every launch
+    // gets a fresh epoch for the look-back records and knows how many tickets its predecessors took
+    if (++ls->epoch == 0) ls->epoch = 1;
+    rp.epoch = ls->epoch;
+    rp.ticket_base = ls->tickets;
+  } else {
+    rp.epoch = 1;
+    rp.ticket_base = 0;
+  }
   if (direct) {
     rp.out = d_out;
     rp.out_pitch = out_pitch;
     rp.out_len = d_out_len;
     rp.pad_top = cfg.pad_top;
-    // 16-byte look-back records live where the stitch path keeps its 32-byte RowMeta; the ticket word follows them,
-    // so one memset clears both
-    rp.agg = reinterpret_cast<uint4 *>(meta);
-    rp.ticket = reinterpret_cast<int *>(rp.agg + (size_t)n_frames * pl.text_rows);
-    ACB_CUDA(cudaMemsetAsync(meta, 0, ((size_t)n_frames * pl.text_rows + 1) * sizeof(uint4), st));
-  } else {
-    rp.ticket = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(err) + al256(pl.err_bytes * n_frames));
-    if (pl.scale_path == SP_BOX_SPLIT) ACB_CUDA(cudaMemsetAsync(rp.ticket, 0, sizeof(int), st));
+    rp.agg = reinterpret_cast<uint4 *>(meta); // 16-byte look-back records live where the stitch path keeps RowMeta
+    if (!ls) ACB_CUDA(cudaMemsetAsync(meta, 0, (size_t)n_frames * pl.text_rows * sizeof(uint4), st));
   }
+  if (uses_ticket && !ls) ACB_CUDA(cudaMemsetAsync(rp.ticket, 0, sizeof(int), st));
   if (k0) cudaEventRecord(k0, st);
   const int kernel_sp = pl.scale_path >= SP_BOX_TMA ? (int)SP_BOX_STREAM : pl.scale_path;
   if (pl.mode != EM_DITHER_BG && pl.scale_path == SP_BOX_TMA) {
@@ -416,8 +425,10 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
     ACB_CUDA(launch_render_rows_ws(rp, pl.mode, st));
     count_launch();
   } else if (pl.mode != EM_DITHER_BG && pl.scale_path == SP_BOX_SPLIT) {
-    ACB_CUDA(launch_render_rows_ws2(rp, pl.mode, st));
+    unsigned grid = 0;
+    ACB_CUDA(launch_render_rows_ws2(rp, pl.mode, st, &grid));
     count_launch();
+    if (ls) ls->tickets += (uint32_t)n_frames * (uint32_t)pl.text_rows + grid; // every CTA draws one ticket past the end
   } else if (pl.mode != EM_DITHER_BG) {
     ACB_CUDA(launch_render_rows(rp, pl.mode, kernel_sp, st));
     count_launch();
@@ -432,6 +443,7 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
     count_launch(2);
   }
   if (k1) cudaEventRecord(k1, st);
+  if (ls && uses_ticket && pl.scale_path != SP_BOX_SPLIT) ls->tickets += tickets_taken;
   if (direct) return E_OK;
 
   StitchParams sp{};
@@ -487,12 +499,24 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
   for (int i = 0; i < n_frames; i++) out[i] = nullptr;
   bool need_stage = gather;
   for (int i = 0; i < n_frames && !need_stage; i++) need_stage = frames[i] && !is_pinned(frames[i]);
+  uint8_t *scratch_before = cx->d_scratch;
   if (!grow_device(&cx->d_in, &cx->d_in_cap, in_slot * nslot) ||
       !grow_device(&cx->d_scratch, &cx->d_scratch_cap, scratch_bytes(pl, chunk)) ||
       !grow_pinned(&cx->h_out, &cx->h_out_cap, out_slot * nslot) ||
       !grow_pinned((uint8_t **)&cx->h_len, &cx->h_len_cap, len_slot * nslot) ||
       (need_stage && !grow_pinned(&cx->h_in, &cx->h_in_cap, in_slot * nslot)))
     return t_err;
+  if (cx->d_scratch != scratch_before) cx->scratch_dirty = true;
+  // library-owned scratch keeps its look-back state across calls (epochs + ticket base) as long as nothing else
+  // wrote into it; otherwise it is zeroed once here and the state restarts
+  {
+    const bool will_be_direct = pl.mode != EM_DITHER_BG && pl.use_smem_out && pl.scale_path != SP_BOX_TMA;
+    if (cx->scratch_dirty || !will_be_direct) {
+      ACB_CUDA(cudaMemsetAsync(cx->d_scratch, 0, cx->d_scratch_cap, cx->stream));
+      cx->lb = LookbackState();
+      cx->scratch_dirty = !will_be_direct; // a stitch-path launch leaves RowMeta words behind
+    }
+  }
 
   // The stitch kernel writes the finished strings and their lengths straight into mapped pinned host memory
   // (UVA: the host pointer is the device pointer), so a chunk costs one event wait, no D2H memcpy calls.
@@ -520,15 +544,16 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
     }
     int rc = render_device(cfg, pl, d_in, in_per_frame, gather ? 1 : 0, n, cx->h_out + (size_t)slot * out_slot, cap,
                            reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(cx->h_len) + (size_t)slot * len_slot),
-                           cx->d_scratch, cx->stream);
+                           cx->d_scratch, cx->stream, nullptr, nullptr, &cx->lb);
     if (rc) return rc;
-    ACB_CUDA(cudaEventRecord(cx->ev[2 + slot], cx->stream));
+    if (nchunks > 1) ACB_CUDA(cudaEventRecord(cx->ev[2 + slot], cx->stream)); // single chunk: collect() waits on the stream
     return E_OK;
   };
   auto collect = [&](int k) -> int {
     const int slot = k & 1, f0 = k * chunk;
     const int n = (n_frames - f0 < chunk) ? n_frames - f0 : chunk;
-    ACB_CUDA(cudaEventSynchronize(cx->ev[2 + slot]));
+    if (nchunks > 1) ACB_CUDA(cudaEventSynchronize(cx->ev[2 + slot]));
+    else ACB_CUDA(cudaStreamSynchronize(cx->stream));
     const uint32_t *lens =
         reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(cx->h_len) + (size_t)slot * len_slot);
     const uint8_t *arena = cx->h_out + (size_t)slot * out_slot;

@@ -29,8 +29,15 @@ int set_error(int code, const char *fmt, ...);
 bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl); // false => error set
 int ensure_device();                                       // 0 or error code
 
+// look-back bookkeeping for a library-owned scratch buffer (zeroed once when allocated)
+struct LookbackState {
+  uint32_t epoch = 0, tickets = 0;
+};
+
 // per-thread stream + growable staging buffers
 struct ThreadCtx {
+  LookbackState lb;
+  bool scratch_dirty = true; // d_scratch holds something other than zeros / look-back records
   cudaStream_t stream = nullptr;
   uint8_t *h_in = nullptr;   size_t h_in_cap = 0;   // pinned
   uint8_t *h_out = nullptr;  size_t h_out_cap = 0;  // pinned
@@ -57,7 +64,8 @@ int default_scale();
 // the core: frames resident on the device -> strings in the device arena (async on st)
 int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t *d_frames, size_t frame_stride,
                   int pregathered, int n_frames, uint8_t *d_out, size_t out_pitch, uint32_t *d_out_len,
-                  uint8_t *d_scratch, cudaStream_t st, cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr);
+                  uint8_t *d_scratch, cudaStream_t st, cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr,
+                  LookbackState *ls = nullptr);
 
 // one frame from a host RGB24 buffer -> allocator-owned string (used by every drop-in entry point)
 char *render_one_host(const acb200_render_cfg_t &cfg, const uint8_t *rgb, size_t *out_len);

@@ -234,6 +234,7 @@ static int text_grid_device(const uint8_t *const *d_srcs, const size_t *sizes, i
   const size_t bytes = al16((uint32_t)(n * sizeof(void *))) + al16((uint32_t)(n * 4)) + 4 * al16((uint32_t)(nl * 4)) +
                        2 * al16((uint32_t)(n * 4));
   if (!grow_device(&cx->d_scratch, &cx->d_scratch_cap, bytes)) return acb200_last_error();
+  cx->scratch_dirty = true; // the render path must re-zero its look-back area before reusing this buffer
   std::vector<uint8_t> h(al16((uint32_t)(n * sizeof(void *))) + al16((uint32_t)(n * 4)));
   for (int i = 0; i < n; i++) {
     reinterpret_cast<const uint8_t **>(h.data())[i] = d_srcs[i];

@@ -63,7 +63,9 @@ struct RenderParams {
   size_t out_pitch;
   uint32_t *out_len;
   uint4 *agg;
-  int *ticket;            // atomic tile ticket (zeroed per launch)
+  int *ticket;            // atomic tile ticket: tile = fetched value - ticket_base
+  uint32_t ticket_base;   // tickets handed out by earlier launches on this scratch (0 after a clear)
+  uint32_t epoch;         // value a look-back record's ready word takes in this launch (never 0)
   int pad_top;
   int direct;             // 1: emitters place rows in the final arena (look-back); 0: scratch rows + k_stitch
   int ring_depth;         // warp-specialised kernel: source rows kept in flight by the producer warp
@@ -93,7 +95,7 @@ static constexpr uint32_t kMaxDynSmem = 224u * 1024u; // dynamic smem ceiling (2
 
 cudaError_t launch_render_rows(const RenderParams &p, int mode, int scale_path, cudaStream_t st);
 cudaError_t launch_render_rows_ws(const RenderParams &p, int mode, cudaStream_t st);
-cudaError_t launch_render_rows_ws2(const RenderParams &p, int mode, cudaStream_t st);
+cudaError_t launch_render_rows_ws2(const RenderParams &p, int mode, cudaStream_t st, unsigned *grid_out);
 size_t ws2_smem_total(int mode, int cols, int src_w, uint32_t row_pitch);
 int ws_ring_depth(int mode, int cols, int src_w, uint32_t row_pitch);
 cudaError_t launch_stitch(const StitchParams &p, int n_frames, cudaStream_t st);

@@ -711,7 +711,7 @@ __device__ __forceinline__ uint32_t emit_direct_prepare(const RenderParams &p, i
     me[2] = MODE == EM_TRUE_FG ? s_cond[3] : 0u;
     me[3] = MODE == EM_TRUE_FG ? s_cond[2] : 0u;
     __threadfence();
-    *reinterpret_cast<volatile uint32_t *>(me) = 1u;
+    *reinterpret_cast<volatile uint32_t *>(me) = p.epoch; // "ready" = this launch's epoch: no clearing between launches
   }
   return cells_bytes;
 }
@@ -741,7 +741,7 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
       uint32_t len = 0, fj = 0, lj = 0;
       if (j < t) {
         const uint32_t *rec = agg + 4 * (size_t)j;
-        while (ld_volatile_u32(rec) == 0u) __nanosleep(64);
+        while (ld_volatile_u32(rec) != p.epoch) __nanosleep(64);
         __threadfence();
         len = ld_volatile_u32(rec + 1);
         fj = ld_volatile_u32(rec + 2);
@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) :
   // direct output: rows find their place by look-back over earlier tiles, so tiles are taken from an atomic ticket
   // (every lower tile is then known to be held by a running CTA); scratch-row output keeps the plain blockIdx mapping
   if (p.direct) {
-    if (tid == 0) s_tile = atomicAdd(p.ticket, 1);
+    if (tid == 0) s_tile = (int)((uint32_t)atomicAdd(p.ticket, 1) - p.ticket_base);
     __syncthreads();
   }
   const unsigned tile = p.direct ? (unsigned)s_tile : blockIdx.x;
@@ -1211,7 +1211,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
     // The ticket for tile k+1 is requested while tile k is being summed: all CTAs ask in bursts, and a same-address
     // atomic that is waited for on the spot costs a queueing delay per tile (measured: +20% kernel time).
     int pending = 0;
-    if (tid == 0) pending = atomicAdd(ticket, 1);
+    if (tid == 0) pending = (int)((uint32_t)atomicAdd(ticket, 1) - p.ticket_base);
     for (int k = 0;; k++) {
       const int c = k % 3;
       if (k >= 3) { // the emitter has written out tile k-3: cells[c] / s_tile[c] are free
@@ -1222,7 +1222,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
       if (tid == 0) {
         const int tk = pending;
         s_tile[c] = tk < total ? tk : -1;
-        if (tk < total) pending = atomicAdd(ticket, 1);
+        if (tk < total) pending = (int)((uint32_t)atomicAdd(ticket, 1) - p.ticket_base);
       }
       SyncConsumers<WS2_ST>::sync();
       const int tile = s_tile[c];
@@ -1311,7 +1311,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
   }
 }
 
-template <int MODE> static cudaError_t launch_ws2_mode(const RenderParams &p, cudaStream_t st) {
+template <int MODE> static cudaError_t launch_ws2_mode(const RenderParams &p, cudaStream_t st, unsigned *grid_out) {
   const Layout2 L = make_layout2(MODE, p.direct, p.cols, p.src_w, p.row_pitch);
   if (L.total > kMaxDynSmem) return cudaErrorInvalidConfiguration;
   static bool configured = false;
@@ -1331,6 +1331,7 @@ template <int MODE> static cudaError_t launch_ws2_mode(const RenderParams &p, cu
   const long long total = (long long)p.n_frames * p.text_rows;
   long long grid = (long long)sms * ctas_per_sm;
   if (grid > total) grid = total;
+  if (grid_out) *grid_out = (unsigned)grid;
   k_render_rows_ws2<MODE><<<(unsigned)grid, WS2_ST + 32, L.total, st>>>(p);
   return cudaGetLastError();
 }

@@ -252,14 +252,14 @@ cudaError_t launch_rows_m6(const RenderParams &p, int sp, cudaStream_t st);
 cudaError_t launch_ws_m6(const RenderParams &p, cudaStream_t st);
 cudaError_t launch_rows_m7(const RenderParams &p, int sp, cudaStream_t st);
 cudaError_t launch_ws_m7(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_ws2_m0(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_ws2_m1(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_ws2_m2(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_ws2_m3(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_ws2_m4(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_ws2_m5(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_ws2_m6(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_ws2_m7(const RenderParams &p, cudaStream_t st);
+cudaError_t launch_ws2_m0(const RenderParams &p, cudaStream_t st, unsigned *grid_out);
+cudaError_t launch_ws2_m1(const RenderParams &p, cudaStream_t st, unsigned *grid_out);
+cudaError_t launch_ws2_m2(const RenderParams &p, cudaStream_t st, unsigned *grid_out);
+cudaError_t launch_ws2_m3(const RenderParams &p, cudaStream_t st, unsigned *grid_out);
+cudaError_t launch_ws2_m4(const RenderParams &p, cudaStream_t st, unsigned *grid_out);
+cudaError_t launch_ws2_m5(const RenderParams &p, cudaStream_t st, unsigned *grid_out);
+cudaError_t launch_ws2_m6(const RenderParams &p, cudaStream_t st, unsigned *grid_out);
+cudaError_t launch_ws2_m7(const RenderParams &p, cudaStream_t st, unsigned *grid_out);
 
 cudaError_t launch_render_rows(const RenderParams &p, int mode, int sp, cudaStream_t st) {
   switch (mode) {
@@ -287,16 +287,16 @@ cudaError_t launch_render_rows_ws(const RenderParams &p, int mode, cudaStream_t 
   default: return cudaErrorInvalidValue;
   }
 }
-cudaError_t launch_render_rows_ws2(const RenderParams &p, int mode, cudaStream_t st) {
+cudaError_t launch_render_rows_ws2(const RenderParams &p, int mode, cudaStream_t st, unsigned *grid_out) {
   switch (mode) {
-  case EM_MONO_FG: return launch_ws2_m0(p, st);
-  case EM_256_FG: return launch_ws2_m1(p, st);
-  case EM_16_FG: return launch_ws2_m2(p, st);
-  case EM_TRUE_FG: return launch_ws2_m3(p, st);
-  case EM_HB_TRUE: return launch_ws2_m4(p, st);
-  case EM_HB_256: return launch_ws2_m5(p, st);
-  case EM_HB_16: return launch_ws2_m6(p, st);
-  case EM_HB_MONO: return launch_ws2_m7(p, st);
+  case EM_MONO_FG: return launch_ws2_m0(p, st, grid_out);
+  case EM_256_FG: return launch_ws2_m1(p, st, grid_out);
+  case EM_16_FG: return launch_ws2_m2(p, st, grid_out);
+  case EM_TRUE_FG: return launch_ws2_m3(p, st, grid_out);
+  case EM_HB_TRUE: return launch_ws2_m4(p, st, grid_out);
+  case EM_HB_256: return launch_ws2_m5(p, st, grid_out);
+  case EM_HB_16: return launch_ws2_m6(p, st, grid_out);
+  case EM_HB_MONO: return launch_ws2_m7(p, st, grid_out);
   default: return cudaErrorInvalidValue;
   }
 }

@@ -3,5 +3,7 @@
 namespace acb {
 cudaError_t launch_rows_m7(const RenderParams &p, int sp, cudaStream_t st) { return launch_rows_mode<7>(p, sp, st); }
 cudaError_t launch_ws_m7(const RenderParams &p, cudaStream_t st) { return launch_ws_mode<7>(p, st); }
-cudaError_t launch_ws2_m7(const RenderParams &p, cudaStream_t st) { return launch_ws2_mode<7>(p, st); }
+cudaError_t launch_ws2_m7(const RenderParams &p, cudaStream_t st, unsigned *grid_out) {
+  return launch_ws2_mode<7>(p, st, grid_out);
+}
 } // namespace acb

@@ -315,7 +315,9 @@ def main():
                      "peak_source": peak_src, "kernel": "k_render_rows_ws2<EM_HB_TRUE> (role-split persistent, direct output)",
                      "algorithmic_bytes_per_launch": alg_bytes_launch,
                      "kernel_ms_per_launch": ms_kernel_max / args.steps,
-                     "output_bytes_per_launch": out_bytes, "traffic": traffic_from_profiles()},
+                     "output_bytes_per_launch": out_bytes,
+                     "achieved_incl_output_GBs": (alg_bytes_launch + out_bytes) / (ms_kernel_max / args.steps * 1e-3) / 1e9,
+                     "traffic": traffic_from_profiles()},
         "e2e": {"value": calls_nn_all * MPIX / nn_s, "unit": "Mpix/s", "h2d_bytes_per_step": gathered,
                 "d2h_bytes_per_step": int(e_nn["bytes"] / max(1, e_nn["calls"])) + 4, "step": "one frame through the call",
                 "calls": int(calls_nn_all), "seconds": nn_s, "caller_threads_per_gpu": threads, "failures": failures,
