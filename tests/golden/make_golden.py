@@ -127,11 +127,23 @@ def main():
         grids.append(dict(n=n, cols=cols, rows=rows, W=W, H=H, level=level, mode=mode, size=sz,
                           fnv="%08x" % ob.fnv(g)))
 
+    # server pixel-space compositor (stream.c:523-779 compiled through oracle/ref_stream_shim.c)
+    comps = []
+    rng = np.random.default_rng(5)
+    for it in range(30):
+        n = int(rng.integers(1, 10))
+        pats = [("noise", "bars", "gradient")[i % 3] for i in range(n)]
+        dims = [(int(rng.integers(40, 400)), int(rng.integers(30, 300))) for _ in range(n)]
+        W, H = int(rng.integers(40, 200)), int(rng.integers(20, 60))
+        srcs = [ob.gen(p, w, h, i) for i, (p, (w, h)) in enumerate(zip(pats, dims))]
+        out, c, r = ob.ref_composite(srcs, W, H)
+        comps.append(dict(n=n, W=W, H=H, cols=c, rows=r, fnv="%08x" % ob.fnv(out.tobytes())))
+
     with open(os.path.join(HERE, "reference_vectors.json"), "w") as f:
         json.dump(dict(generated_by="tests/golden/make_golden.py",
                        reference_commit="73fe49337008f687add06622c012ac1df0ab3dcc",
                        frames=frames, rgb_to_256color_table_fnv=h256, rgb_to_16color_table_fnv=h16,
-                       quirks=quirks, nn_resize=nn, glyph_tables=glyphs, text_grids=grids), f, indent=1)
+                       quirks=quirks, nn_resize=nn, glyph_tables=glyphs, text_grids=grids, pixel_composites=comps), f, indent=1)
     print("wrote", len(frames), "frame fingerprints;", "q256", h256, "q16", h16)
 
 

@@ -184,6 +184,12 @@ def ref():
     L.ansi_fast_init_16color.restype = None
     L.ascii_simd_init.restype = None
     L.ref_oracle_set_render_mode.argtypes = [C.c_int]
+    u8pp = C.POINTER(C.POINTER(C.c_uint8))
+    L.ref_oracle_composite.argtypes = [u8pp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(C.c_uint8)]
+    L.ref_oracle_grid_layout.restype = None
+    L.ref_oracle_grid_layout.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ascii_simd_init()
     L.ansi_fast_init_256color()
     L.ansi_fast_init_16color()
@@ -305,4 +311,21 @@ def port_composite(srcs, width, height):
     out = np.empty((height * 2, width, 3), np.uint8)
     c, r = C.c_int(0), C.c_int(0)
     port().orc_composite(ptrs, ws, hs, k, width, height, out.ctypes.data_as(u8p), C.byref(c), C.byref(r))
+    return out, c.value, r.value
+
+
+def ref_composite(srcs, width, height):
+    """the reference's own create_multi_source_composite / calculate_optimal_grid_layout (src/server/stream.c:523-779),
+    compiled into oracle/_ref through oracle/ref_stream_shim.c"""
+    k = len(srcs)
+    arrs = [np.ascontiguousarray(s, np.uint8) for s in srcs]
+    u8p = C.POINTER(C.c_uint8)
+    ptrs = (u8p * k)(*[a.ctypes.data_as(u8p) for a in arrs])
+    ws = (C.c_int * k)(*[a.shape[1] for a in arrs])
+    hs = (C.c_int * k)(*[a.shape[0] for a in arrs])
+    out = np.empty((height * 2, width, 3), np.uint8)
+    rc = ref().ref_oracle_composite(ptrs, ws, hs, k, width, height, out.ctypes.data_as(u8p))
+    assert rc == 0
+    c, r = C.c_int(0), C.c_int(0)
+    ref().ref_oracle_grid_layout(ws, hs, k, width, height, C.byref(c), C.byref(r))
     return out, c.value, r.value

@@ -268,7 +268,7 @@ def test_pixel_composite(acb, ob):
                 for i in range(n)]
         W, H = int(rng.integers(40, 200)), int(rng.integers(20, 60))
         got, gc, gr = acb.composite(srcs, W, H)
-        exp, ec, er = ob.port_composite(srcs, W, H)
+        exp, ec, er = (ob.ref_composite if ob.ref() is not None else ob.port_composite)(srcs, W, H)
         assert (gc, gr) == (ec, er) and np.array_equal(got, exp), (it, n, W, H)
         caps = acb.make_caps(3, 2, True)
         a = acb.ascii_convert_with_capabilities(got, W, H * 2, caps, True, False, "standard")

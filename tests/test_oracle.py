@@ -248,3 +248,28 @@ def test_box_filter_spec(ob):
             b = src[ys[dy]:ys[dy + 1], xs[dx]:xs[dx + 1]].astype(np.uint32)
             n = b.shape[0] * b.shape[1]
             assert np.array_equal(out[dy, dx], ((b.sum(axis=(0, 1)) + n // 2) // n).astype(np.uint8))
+
+
+def _composite_cases():
+    rng = np.random.default_rng(5)
+    for it in range(30):
+        n = int(rng.integers(1, 10))
+        srcs = [("noise", "bars", "gradient")[i % 3] for i in range(n)]
+        dims = [(int(rng.integers(40, 400)), int(rng.integers(30, 300))) for _ in range(n)]
+        yield it, srcs, dims, int(rng.integers(40, 200)), int(rng.integers(20, 60))
+
+
+def test_port_vs_ref_pixel_composite(ob, ref_lib):
+    """server grid: the reference's own create_multi_source_composite (stream.c:664-779), compiled into oracle/_ref"""
+    for it, pats, dims, W, H in _composite_cases():
+        srcs = [ob.gen(p, w, h, i) for i, (p, (w, h)) in enumerate(zip(pats, dims))]
+        a, ac, ar = ob.ref_composite(srcs, W, H)
+        b, bc, br = ob.port_composite(srcs, W, H)
+        assert (ac, ar) == (bc, br) and np.array_equal(a, b), (it, W, H)
+
+
+def test_port_pixel_composite_matches_golden(ob, golden):
+    for rec, (it, pats, dims, W, H) in zip(golden["pixel_composites"], _composite_cases()):
+        srcs = [ob.gen(p, w, h, i) for i, (p, (w, h)) in enumerate(zip(pats, dims))]
+        b, bc, br = ob.port_composite(srcs, W, H)
+        assert (bc, br, "%08x" % ob.fnv(b.tobytes())) == (rec["cols"], rec["rows"], rec["fnv"]), rec
