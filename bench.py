@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ring", type=int, default=RING)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--resident-only", action="store_true", help="profiling aid: only the device-timed resident loop")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -268,6 +269,14 @@ def main():
     out_bytes = int(d_len.sum().item())
     del d_in, d_out, d_scr
     torch.cuda.empty_cache()
+
+    if args.resident_only:
+        if rank == 0:
+            print(json.dumps({"resident_only": True, "ms_per_step": ms_total_max / args.steps,
+                              "kernel_ms_per_launch": ms_kernel_max / args.steps, "gpu_launches": int(launches)}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end: the reference-facing call from host frames, T caller threads (one per "client")
     H = load_harness()
