@@ -59,7 +59,8 @@ EXPORTS = [  # every symbol include/asciichat_b200.h declares
     "acb200_set_allocator", "acb200_set_option_render_mode", "acb200_set_default_scale", "acb200_frame_capacity",
     "acb200_scratch_bytes", "acb200_render_batch_device", "acb200_render_batch_host", "acb200_time_batch_device",
     "acb200_composite_host", "acb200_grid_layout", "acb200_aspect_ratio", "acb200_launch_count", "acb200_version",
-    "acb200_create_grid_device", "acb200_synchronize",
+    "acb200_create_grid_device", "acb200_synchronize", "acb200_source_update", "acb200_source_clear",
+    "acb200_mixed_frame",
 ]
 
 
@@ -135,6 +136,12 @@ def lib():
     L.acb200_version.restype = C.c_char_p
     L.acb200_create_grid_device.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int,
                                             C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p]
+    L.acb200_source_update.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.acb200_source_clear.argtypes = [C.c_int]
+    L.acb200_mixed_frame.restype = C.c_void_p
+    L.acb200_mixed_frame.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_ushort, C.c_ushort,
+                                     C.POINTER(terminal_capabilities_t), C.c_char_p, C.POINTER(C.c_size_t),
+                                     C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -224,6 +231,34 @@ def composite(srcs, width, height):
     if rc:
         raise RuntimeError("acb200_composite_host failed: %s" % (last_error(),))
     return out, c.value, r.value
+
+
+# ---- the server's per-client frame with resident sources (src/server/stream.c:958-1191) --------
+MAX_SOURCES = 32
+
+
+def source_update(slot, image):
+    a = np.ascontiguousarray(image, dtype=np.uint8)
+    assert a.ndim == 3 and a.shape[2] == 3
+    return lib().acb200_source_update(slot, a.ctypes.data, a.shape[1], a.shape[0])
+
+
+def source_clear(slot):
+    return lib().acb200_source_clear(slot)
+
+
+def mixed_frame(slots, width, height, caps, palette_chars):
+    """-> (bytes | None, out_size, sources_with_video), like create_mixed_ascii_frame_for_client"""
+    k = len(slots)
+    arr = (C.c_int * max(k, 1))(*slots)
+    n, cnt = C.c_size_t(0), C.c_int(0)
+    r = lib().acb200_mixed_frame(arr, k, width, height, C.byref(caps) if caps is not None else None,
+                                 _pal(palette_chars), C.byref(n), C.byref(cnt))
+    if not r:
+        return None, n.value, cnt.value
+    s = C.string_at(r, n.value)
+    _libc.free(r)
+    return s, n.value, cnt.value
 
 
 def aspect_ratio(img_w, img_h, width, height, stretch=False):

@@ -74,6 +74,49 @@ static char *convert_common(const uint8_t *rgb, int w, int h, ssize_t rw, ssize_
   return render_one_host(cfg, rgb, nullptr);
 }
 
+namespace acb {
+bool plan_convert_with_caps(int w, int h, ssize_t width, ssize_t height, const terminal_capabilities_t *caps,
+                            bool use_aspect_ratio, bool stretch, const char *palette, acb200_render_cfg_t *cfg) {
+  if (w <= 0 || w > 10000 || h <= 0 || h > 10000) { // ascii.c:204
+    set_error(E_INVALID_PARAM, "Invalid original image dimensions: w=%d, h=%d", w, h);
+    return false;
+  }
+  ssize_t rw = width, rh = height;
+  if (use_aspect_ratio) acb200_aspect_ratio(w, h, rw, rh, stretch, &rw, &rh); // :220
+  const ssize_t out_w = rw, out_h = rh;
+  if (caps->render_mode == RENDER_MODE_HALF_BLOCK) rh = rh * 2; // :230
+  size_t pad_w = 0, pad_h = 0;
+  if (use_aspect_ratio && caps->wants_padding) { // :238-243
+    pad_w = (size_t)(width > out_w ? (width - out_w) / 2 : 0);
+    pad_h = (size_t)(height > out_h ? (height - out_h) / 2 : 0);
+  }
+  if (rw <= 0 || rh <= 0) { // :256-259
+    set_error(E_INVALID_PARAM, "Invalid dimensions for resize: width=%zd, height=%zd", rw, rh);
+    return false;
+  }
+  if (rw > INT_MAX || rh > INT_MAX) {
+    set_error(E_INVALID_PARAM, "Dimensions exceed INT_MAX");
+    return false;
+  }
+  if (!palette) { // image_print_with_capabilities rejects it, ascii.c:956
+    set_error(E_INVALID_PARAM, "palette is NULL");
+    return false;
+  }
+  *cfg = acb200_render_cfg_t{};
+  cfg->src_w = w;
+  cfg->src_h = h;
+  cfg->cols = (int)rw;
+  cfg->rows_px = (int)rh;
+  cfg->color_level = (int)caps->color_level;
+  cfg->render_mode = (int)caps->render_mode;
+  cfg->scale = default_scale();
+  cfg->pad_left = (int)pad_w;
+  cfg->pad_top = (int)pad_h;
+  cfg->palette = palette;
+  return true;
+}
+} // namespace acb
+
 extern "C" {
 
 // lib/video/ascii/ascii.c:194-387
@@ -84,29 +127,16 @@ char *ascii_convert_with_capabilities(image_t *original, const ssize_t width, co
     set_error(E_INVALID_PARAM, "Invalid parameters for ascii_convert_with_capabilities");
     return nullptr;
   }
-  if (original->w <= 0 || original->w > 10000 || original->h <= 0 || original->h > 10000) { // :204
-    set_error(E_INVALID_PARAM, "Invalid original image dimensions: w=%d, h=%d", original->w, original->h);
-    return nullptr;
-  }
-  if (original->pixels == nullptr) { // :209
+  if (original->w > 0 && original->w <= 10000 && original->h > 0 && original->h <= 10000 &&
+      original->pixels == nullptr) { // :209 (after the dimension check of :204)
     set_error(E_INVALID_PARAM, "Original image pixels pointer is NULL");
     return nullptr;
   }
-  ssize_t rw = width, rh = height;
-  if (use_aspect_ratio) acb200_aspect_ratio(original->w, original->h, rw, rh, stretch, &rw, &rh); // :220
-  const ssize_t out_w = rw, out_h = rh;
-  if (caps->render_mode == RENDER_MODE_HALF_BLOCK) rh = rh * 2; // :230
-  size_t pad_w = 0, pad_h = 0;
-  if (use_aspect_ratio && caps->wants_padding) { // :238-243
-    pad_w = (size_t)(width > out_w ? (width - out_w) / 2 : 0);
-    pad_h = (size_t)(height > out_h ? (height - out_h) / 2 : 0);
-  }
-  if (!palette_chars) { // image_print_with_capabilities rejects it, ascii.c:956
-    set_error(E_INVALID_PARAM, "palette is NULL");
+  acb200_render_cfg_t cfg;
+  if (!plan_convert_with_caps(original->w, original->h, width, height, caps, use_aspect_ratio, stretch, palette_chars,
+                              &cfg))
     return nullptr;
-  }
-  return convert_common(reinterpret_cast<const uint8_t *>(original->pixels), original->w, original->h, rw, rh,
-                        (int)caps->color_level, (int)caps->render_mode, pad_w, pad_h, palette_chars);
+  return render_one_host(cfg, reinterpret_cast<const uint8_t *>(original->pixels), nullptr);
 }
 
 // lib/video/ascii/ascii.c:72-191

@@ -578,6 +578,40 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
   return rc;
 }
 
+// one frame that is already resident on the device -> allocator-owned string (server path with resident sources)
+char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, size_t *out_len) {
+  Plan pl;
+  if (!make_plan(cfg, pl)) return nullptr;
+  ThreadCtx *cx = thread_ctx();
+  if (!cx) return nullptr;
+  uint8_t *scratch_before = cx->d_scratch;
+  if (!grow_device(&cx->d_scratch, &cx->d_scratch_cap, scratch_bytes(pl, 1)) ||
+      !grow_pinned(&cx->h_out, &cx->h_out_cap, pl.frame_capacity) ||
+      !grow_pinned((uint8_t **)&cx->h_len, &cx->h_len_cap, 256))
+    return nullptr;
+  if (cx->d_scratch != scratch_before) cx->scratch_dirty = true;
+  const bool will_be_direct = pl.mode != EM_DITHER_BG && pl.use_smem_out && pl.scale_path != SP_BOX_TMA;
+  if (cx->scratch_dirty || !will_be_direct) {
+    if (cudaMemsetAsync(cx->d_scratch, 0, cx->d_scratch_cap, cx->stream) != cudaSuccess) return nullptr;
+    cx->lb = LookbackState();
+    cx->scratch_dirty = !will_be_direct;
+  }
+  if (render_device(cfg, pl, d_rgb, (size_t)cfg.src_w * cfg.src_h * 3, 0, 1, cx->h_out, pl.frame_capacity, cx->h_len,
+                    cx->d_scratch, cx->stream, nullptr, nullptr, &cx->lb) != E_OK)
+    return nullptr;
+  if (cudaStreamSynchronize(cx->stream) != cudaSuccess) {
+    set_error(E_INVALID_STATE, "CUDA failure while rendering a resident frame");
+    return nullptr;
+  }
+  const size_t len = cx->h_len[0];
+  char *sp = (char *)user_alloc(len + 1);
+  if (!sp) return nullptr;
+  memcpy(sp, cx->h_out, len);
+  sp[len] = '\0';
+  if (out_len) *out_len = len;
+  return sp;
+}
+
 char *render_one_host(const acb200_render_cfg_t &cfg, const uint8_t *rgb, size_t *out_len) {
   char *s = nullptr;
   size_t n = 0;
@@ -603,6 +637,7 @@ int acb200_init(int device) {
   return thread_ctx() ? E_OK : t_err;
 }
 void acb200_shutdown(void) {
+  destroy_sources();
   destroy_lut_cache();
   destroy_ctx_pool();
 }

@@ -54,6 +54,7 @@ bool grow_device(uint8_t **p, size_t *cap, size_t need);
 
 const GlyphLut *device_lut(const char *palette, int which); // cached per (palette, which); nullptr => error set
 void destroy_lut_cache();
+void destroy_sources(); // server.cu: resident client frames
 
 void *user_alloc(size_t n);
 void user_free(void *p);
@@ -69,6 +70,10 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
 
 // one frame from a host RGB24 buffer -> allocator-owned string (used by every drop-in entry point)
 char *render_one_host(const acb200_render_cfg_t &cfg, const uint8_t *rgb, size_t *out_len);
+char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, size_t *out_len);
+// ascii_convert_with_capabilities' front half (ascii.c:194-265): validation, aspect fit, padding -> a render cfg
+bool plan_convert_with_caps(int w, int h, ssize_t width, ssize_t height, const terminal_capabilities_t *caps,
+                            bool use_aspect_ratio, bool stretch, const char *palette, acb200_render_cfg_t *cfg);
 
 #define ACB_CUDA(call)                                                                                                 \
   do {                                                                                                                 \

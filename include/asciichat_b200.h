@@ -214,6 +214,36 @@ const char *acb200_version(void);
 int acb200_create_grid_device(const uint8_t *const *d_srcs, const size_t *sizes, int n, int width, int height,
                               uint8_t *d_out, size_t *out_size, void *stream);
 
+/* ---- the server's per-client frame generation with RESIDENT sources ------------------------------------
+ * Replaces src/server/stream.c:958-1191 create_mixed_ascii_frame_for_client() and what it calls
+ * (collect_video_sources :221-455, create_single_source_composite :476-500, create_multi_source_composite
+ * :664-779, convert_composite_to_ascii :789-853).  The reference reads every client's newest frame from its
+ * host-side incoming_video_buffer for every (receiving client x output frame); here each received frame is
+ * uploaded ONCE into a device-resident slot and all the per-client renders read it from HBM.
+ *
+ * slot = the client's index in g_client_manager.clients[] (0 .. ACB200_MAX_SOURCES-1 = MAX_CLIENTS-1,
+ * include/ascii-chat/common/limits.h:26). */
+#define ACB200_MAX_SOURCES 32
+/* A client's receive thread stores its newest RGB24 frame (src/server/protocol.c image-frame handler ->
+ * video_frame_commit).  Dimensions 0, > 4096 wide or > 2160 tall are what collect_video_sources rejects
+ * (stream.c:342): the slot is cleared and ERROR_INVALID_PARAM returned.  Thread-safe against
+ * acb200_mixed_frame(); returns when the frame is resident. */
+int acb200_source_update(int slot, const uint8_t *rgb, int w, int h);
+/* client stopped sending video / disconnected (is_sending_video = false) */
+int acb200_source_clear(int slot);
+/* One output frame for one receiving client.  `slots` lists the active clients in g_client_manager order;
+ * slots without a resident frame are the reference's "no video" clients.  0 sources with video: returns
+ * NULL with *out_size = 0 and no error (stream.c:1036).  1 source: that frame is converted directly;
+ * 2..9+: W x 2H pixel-space grid composite (first 9), then ascii_convert_with_capabilities(composite, width,
+ * HALF_BLOCK ? 2*height : height, caps, aspect=true, stretch=false, palette) and the trailing-ESC[0m fix-up of
+ * stream.c:1085-1127.  Returns an allocator-owned NUL-terminated string, *out_size its length,
+ * *out_sources_count (optional) = sources with video.  Bit-identical to the reference for every input on
+ * which the reference itself does not crash (a source whose fitted cell size rounds to 0 px NULL-derefs
+ * there, stream.c:723-749; here that cell stays black). */
+char *acb200_mixed_frame(const int *slots, int n, unsigned short width, unsigned short height,
+                         const terminal_capabilities_t *caps, const char *palette, size_t *out_size,
+                         int *out_sources_count);
+
 #pragma GCC visibility pop
 #ifdef __cplusplus
 }

@@ -4,15 +4,25 @@
  * Pulls the reference's server-side pixel-space grid compositor into the oracle library: the translation
  * unit below IS the reference's src/server/stream.c (included where it lies, never copied), so its static
  * functions calculate_optimal_grid_layout() (stream.c:523-651) and create_multi_source_composite()
- * (stream.c:664-779) can be called through the two thin wrappers at the bottom.  The handful of server
- * globals/functions stream.c references elsewhere are defined as inert stubs; the wrappers never reach them.
+ * (stream.c:664-779) can be called through the two thin wrappers at the bottom, and the whole per-client
+ * entry create_mixed_ascii_frame_for_client() (stream.c:958-1191) through ref_oracle_mixed_frame(), which
+ * fills g_client_manager with synthetic clients whose "incoming video buffer" is served by the
+ * video_frame_get_latest() defined here (the wire layout [be32 w][be32 h][rgb24] collect_video_sources()
+ * parses at stream.c:314-431).  The other server globals/functions stream.c references are inert stubs.
  */
 #include "src/server/stream.c"
 
 client_manager_t g_client_manager;
 atomic_t g_should_exit;
 bool atomic_load_bool_impl(const atomic_t *a) { return a->impl != 0; }
-const video_frame_t *video_frame_get_latest(video_frame_buffer_t *vfb) { (void)vfb; return NULL; }
+#define SHIM_MAX_SRC 32
+static video_frame_t shim_frames[SHIM_MAX_SRC];
+/* a synthetic client's incoming_video_buffer is the tagged integer (slot+1) */
+const video_frame_t *video_frame_get_latest(video_frame_buffer_t *vfb) {
+  uintptr_t k = (uintptr_t)vfb;
+  if (k == 0 || k > SHIM_MAX_SRC || !shim_frames[k - 1].data) return NULL;
+  return &shim_frames[k - 1];
+}
 const char *named_register(uintptr_t key, const char *base_name, const char *type, const char *format_spec,
                            const char *file, int line, const char *func, uintptr_t parent_key) {
   (void)key; (void)type; (void)format_spec; (void)file; (void)line; (void)func; (void)parent_key;
@@ -58,4 +68,44 @@ void ref_oracle_grid_layout(const int *ws, const int *hs, int n, int term_w, int
   static const unsigned char *none[32];
   if (wrap_sources(s, imgs, none, ws, hs, n)) return;
   calculate_optimal_grid_layout(s, n, n, term_w, term_h, cols, rows);
+}
+
+/* The reference's full per-client server entry.  srcs[i] == NULL models a connected client with no video.
+ * Client 0 is the target (its caps/palette drive the conversion).  Returns the reference's malloc'd frame
+ * (free with free()) or NULL; *out_size as the reference sets it; *sources = sources_with_video. */
+char *ref_oracle_mixed_frame(const unsigned char *const *srcs, const int *ws, const int *hs, int n, int width, int height,
+                             const terminal_capabilities_t *caps, const char *palette, size_t *out_size, int *sources) {
+  if (n < 1 || n > SHIM_MAX_SRC || n > MAX_CLIENTS) return NULL;
+  memset(&g_client_manager, 0, sizeof(g_client_manager));
+  for (int i = 0; i < n; i++) {
+    client_info_t *c = &g_client_manager.clients[i];
+    snprintf(c->client_id, sizeof(c->client_id), "oracle.%d", i);
+    c->active.impl = 1;
+    c->is_sending_video.impl = srcs[i] != NULL;
+    c->incoming_video_buffer = (video_frame_buffer_t *)(uintptr_t)(i + 1);
+    memset(&shim_frames[i], 0, sizeof(shim_frames[i]));
+    if (srcs[i]) {
+      size_t px = (size_t)ws[i] * (size_t)hs[i] * 3;
+      unsigned char *d = malloc(px + 8);
+      uint32_t wn = HOST_TO_NET_U32((uint32_t)ws[i]), hn = HOST_TO_NET_U32((uint32_t)hs[i]);
+      memcpy(d, &wn, 4);
+      memcpy(d + 4, &hn, 4);
+      memcpy(d + 8, srcs[i], px);
+      shim_frames[i].data = d;
+      shim_frames[i].size = px + 8;
+    }
+  }
+  client_info_t *t = &g_client_manager.clients[0];
+  t->terminal_caps = *caps;
+  t->has_terminal_caps = true;
+  t->client_palette_initialized = true;
+  snprintf(t->client_palette_chars, sizeof(t->client_palette_chars), "%s", palette);
+  bool changed = false;
+  char *out = create_mixed_ascii_frame_for_client("oracle.0", (unsigned short)width, (unsigned short)height, false,
+                                                  out_size, &changed, sources);
+  for (int i = 0; i < n; i++) {
+    free(shim_frames[i].data);
+    shim_frames[i].data = NULL;
+  }
+  return out;
 }

@@ -139,11 +139,21 @@ def main():
         out, c, r = ob.ref_composite(srcs, W, H)
         comps.append(dict(n=n, W=W, H=H, cols=c, rows=r, fnv="%08x" % ob.fnv(out.tobytes())))
 
+    # the server's whole per-client entry create_mixed_ascii_frame_for_client (stream.c:958-1191), run inside
+    # the compiled reference by oracle/ref_stream_shim.c's synthetic clients
+    mixed = []
+    for case in ob.mixed_cases():
+        srcs = ob.mixed_sources(case)
+        s, sz, cnt = ob.ref_mixed_frame(srcs, case["W"], case["H"], case["level"], case["mode"], case["palette"],
+                                        bool(case["pad"]))
+        mixed.append(dict(case, size=sz, sources=cnt, fnv=None if s is None else "%08x" % ob.fnv(s)))
+
     with open(os.path.join(HERE, "reference_vectors.json"), "w") as f:
         json.dump(dict(generated_by="tests/golden/make_golden.py",
                        reference_commit="73fe49337008f687add06622c012ac1df0ab3dcc",
                        frames=frames, rgb_to_256color_table_fnv=h256, rgb_to_16color_table_fnv=h16,
-                       quirks=quirks, nn_resize=nn, glyph_tables=glyphs, text_grids=grids, pixel_composites=comps), f, indent=1)
+                       quirks=quirks, nn_resize=nn, glyph_tables=glyphs, text_grids=grids, pixel_composites=comps,
+                       mixed_frames=mixed), f, indent=1)
     print("wrote", len(frames), "frame fingerprints;", "q256", h256, "q16", h16)
 
 

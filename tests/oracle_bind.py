@@ -329,3 +329,108 @@ def ref_composite(srcs, width, height):
     c, r = C.c_int(0), C.c_int(0)
     ref().ref_oracle_grid_layout(ws, hs, k, width, height, C.byref(c), C.byref(r))
     return out, c.value, r.value
+
+
+def ref_mixed_frame(srcs, width, height, level, mode, palette="standard", pad=False):
+    """the reference's own create_mixed_ascii_frame_for_client (src/server/stream.c:958-1191), run end to end
+    inside oracle/_ref (oracle/ref_stream_shim.c feeds it synthetic clients).  srcs[i] may be None (client
+    connected, no video).  Returns (bytes | None, out_size, sources_with_video)."""
+    k = len(srcs)
+    arrs = [None if s is None else np.ascontiguousarray(s, np.uint8) for s in srcs]
+    u8p = C.POINTER(C.c_uint8)
+    ptrs = (u8p * k)(*[u8p() if a is None else a.ctypes.data_as(u8p) for a in arrs])
+    ws = (C.c_int * k)(*[0 if a is None else a.shape[1] for a in arrs])
+    hs = (C.c_int * k)(*[0 if a is None else a.shape[0] for a in arrs])
+    caps = make_caps(level, mode, pad)
+    n, cnt = C.c_size_t(0), C.c_int(0)
+    f = ref().ref_oracle_mixed_frame
+    f.restype = C.c_void_p
+    r = f(ptrs, ws, hs, k, width, height, C.byref(caps), pal_bytes(palette), C.byref(n), C.byref(cnt))
+    if not r:
+        return None, n.value, cnt.value
+    s = C.string_at(r, n.value)
+    _libc.free(C.c_void_p(r))
+    return s, n.value, cnt.value
+
+
+def mixed_frame_fixup(s):
+    """stream.c:1085-1127: a frame that does not end in ESC[0m is cut after its last ESC[0m (if it has one)"""
+    rst = b"\x1b[0m"
+    if len(s) >= 4 and not s.endswith(rst):
+        k = s.rfind(rst)
+        if k >= 0:
+            return s[:k + 4]
+    return s
+
+
+def port_mixed_frame(srcs, width, height, level, mode, palette="standard", pad=False, scale=0):
+    """the same entry restated on the port: count sources -> (the source | the W x 2H composite) ->
+    orc_convert_caps(aspect=1, stretch=0) with h doubled for half-block (stream.c:829) -> reset fix-up"""
+    live = [s for s in srcs if s is not None]
+    if not live:
+        return None, 0, 0
+    comp = live[0] if len(live) == 1 else port_composite(live, width, height)[0]
+    h = height * 2 if mode == 2 else height
+    s = port_convert(comp, width, h, level, mode, palette, aspect=True, stretch=False, pad=pad, scale=scale)
+    if s is None:
+        return None, 0, len(live)
+    s = mixed_frame_fixup(s)
+    return s, len(s), len(live)
+
+
+def composite_degenerate(srcs, width, height):
+    """True when some source's fitted target is 0 px wide or tall.  The reference dereferences the NULL that
+    image_new_from_pool(0, h) returns there (stream.c:723-749) and crashes, so such inputs have no reference
+    answer; the product and the port skip that source instead (DESIGN.md §2 divergences)."""
+    live = [s for s in srcs if s is not None][:9]
+    if len(live) < 2:
+        return False
+    k = len(live)
+    ws = (C.c_int * k)(*[s.shape[1] for s in live])
+    hs = (C.c_int * k)(*[s.shape[0] for s in live])
+    c, r = C.c_int(0), C.c_int(0)
+    port().orc_grid_layout(ws, hs, k, width, height, C.byref(c), C.byref(r))
+    cw, ch = width // c.value, (height * 2) // r.value
+    if cw <= 0 or ch <= 0:
+        return True
+    f32 = np.float32
+    for s in live:
+        a = f32(s.shape[1]) / f32(s.shape[0])
+        if a > f32(cw) / f32(ch):
+            tw, th = cw, int(f32(cw) / a + f32(0.5))
+        else:
+            tw, th = int(f32(ch) * a + f32(0.5)), ch
+        if tw <= 0 or th <= 0:
+            return True
+    return False
+
+
+def mixed_cases(count=60, seed=11):
+    """deterministic server-path cases: per client (pattern, w, h) or None, terminal W x H, caps"""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        n = int(rng.integers(1, 12))
+        clients = []
+        for i in range(n):
+            if rng.random() < 0.2:
+                clients.append(None)
+            else:
+                clients.append([("noise", "bars", "gradient", "grey")[int(rng.integers(0, 4))],
+                                int(rng.integers(32, 480)), int(rng.integers(24, 360))])
+        case = dict(clients=clients, W=int(rng.integers(30, 220)), H=int(rng.integers(10, 70)),
+                    level=int(rng.integers(0, 4)), mode=int(rng.integers(0, 3)), pad=int(rng.integers(0, 2)),
+                    palette=("standard", "blocks", "cool")[int(rng.integers(0, 3))])
+        if composite_degenerate(mixed_sources(case), case["W"], case["H"]):
+            continue
+        out.append(case)
+    # hand-picked: nobody sends video; one 1080p sender; nine 720p senders on a large terminal
+    out.append(dict(clients=[None, None], W=80, H=24, level=3, mode=0, pad=1, palette="standard"))
+    out.append(dict(clients=[None, ["noise", 1920, 1080]], W=203, H=61, level=3, mode=2, pad=1, palette="standard"))
+    out.append(dict(clients=[["noise", 1280, 720]] * 9, W=240, H=67, level=2, mode=0, pad=0, palette="standard"))
+    out.append(dict(clients=[["gradient", 640, 480]] * 4, W=160, H=48, level=1, mode=1, pad=1, palette="blocks"))
+    return out
+
+
+def mixed_sources(case):
+    return [None if c is None else gen(c[0], c[1], c[2], i) for i, c in enumerate(case["clients"])]

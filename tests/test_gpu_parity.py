@@ -273,3 +273,98 @@ def test_pixel_composite(acb, ob):
         caps = acb.make_caps(3, 2, True)
         a = acb.ascii_convert_with_capabilities(got, W, H * 2, caps, True, False, "standard")
         assert a == ob.port_convert(exp, W, H * 2, 3, 2, "standard", True, False, True)
+
+
+# ---------------------------------------------------------------- server per-client entry with resident sources
+def _load_slots(acb, srcs):
+    slots = list(range(len(srcs)))
+    for i, s in enumerate(srcs):
+        if s is None:
+            assert acb.source_clear(i) == 0
+        else:
+            assert acb.source_update(i, s) == 0, acb.last_error()
+    return slots
+
+
+def test_mixed_frame_golden(acb, ob, golden):
+    """acb200_mixed_frame against the reference's create_mixed_ascii_frame_for_client (stream.c:958-1191):
+    committed fingerprints of the compiled reference + the port on the same inputs, byte for byte"""
+    for rec, case in zip(golden["mixed_frames"], ob.mixed_cases()):
+        srcs = ob.mixed_sources(case)
+        slots = _load_slots(acb, srcs)
+        caps = acb.make_caps(case["level"], case["mode"], bool(case["pad"]))
+        s, sz, cnt = acb.mixed_frame(slots, case["W"], case["H"], caps, case["palette"])
+        assert (sz, cnt, None if s is None else "%08x" % ob.fnv(s)) == (rec["size"], rec["sources"], rec["fnv"]), case
+        exp = ob.port_mixed_frame(srcs, case["W"], case["H"], case["level"], case["mode"], case["palette"],
+                                  bool(case["pad"]))
+        assert (s, sz, cnt) == exp
+    for i in range(acb.MAX_SOURCES):
+        acb.source_clear(i)
+
+
+def test_mixed_frame_errors_and_slot_rules(acb, ob):
+    caps = acb.make_caps(3, 0, True)
+    img = ob.gen("noise", 64, 48, 0)
+    for i in range(acb.MAX_SOURCES):
+        acb.source_clear(i)
+    acb.last_error()
+    assert acb.mixed_frame([0, 1], 80, 24, caps, "standard") == (None, 0, 0)  # nobody sends video: no frame, no error
+    assert acb.last_error()[0] == 0
+    assert acb.mixed_frame([0], 0, 24, caps, "standard")[0] is None and acb.last_error()[0] == 86
+    assert acb.mixed_frame([99], 80, 24, caps, "standard")[0] is None and acb.last_error()[0] == 86
+    assert acb.source_update(acb.MAX_SOURCES, img) == 86
+    acb.last_error()
+    # the dimensions collect_video_sources rejects (stream.c:342) drop the client's video
+    assert acb.source_update(1, img) == 0
+    assert acb.source_update(1, np.zeros((2161, 8, 3), np.uint8)) == 86
+    acb.last_error()
+    assert acb.mixed_frame([0, 1], 80, 24, caps, "standard") == (None, 0, 0)
+    # caps not received yet (stream.c:816): error, no frame
+    assert acb.source_update(1, img) == 0
+    assert acb.mixed_frame([0, 1], 80, 24, None, "standard")[0] is None and acb.last_error()[0] == 85
+    # a source that changes size between frames
+    for (w, h) in ((64, 48), (320, 200), (33, 17), (1280, 720)):
+        im = ob.gen("bars", w, h, 1)
+        assert acb.source_update(1, im) == 0
+        assert acb.mixed_frame([0, 1], 80, 24, caps, "standard") == ob.port_mixed_frame([None, im], 80, 24, 3, 0, "standard", True)
+    acb.source_clear(1)
+
+
+def test_mixed_frame_concurrent_render_and_update(acb, ob):
+    """one render thread per receiving client (src/server/render.c) while a receive thread keeps replacing one
+    sender's frame: every output equals the reference's answer for one of the two frames, never a torn mix"""
+    base = [ob.gen(("noise", "bars", "gradient")[i % 3], 320, 240, i) for i in range(4)]
+    alt = ob.gen("grey", 200, 150, 9)
+    for i, s in enumerate(base):
+        assert acb.source_update(i, s) == 0
+    views = [(120, 40, 3, 2), (80, 24, 2, 0), (100, 30, 3, 1), (64, 20, 0, 0), (150, 50, 1, 0), (90, 33, 3, 0)]
+    exp = []
+    for (W, H, level, mode) in views:
+        exp.append({ob.port_mixed_frame(v, W, H, level, mode, "standard", True)[0]
+                    for v in (base, [base[0], alt] + base[2:])})
+    errs, stop = [], threading.Event()
+
+    def receiver():
+        k = 0
+        while not stop.is_set():
+            acb.source_update(1, alt if k & 1 == 0 else base[1])
+            k += 1
+
+    def render(j):
+        W, H, level, mode = views[j]
+        caps = acb.make_caps(level, mode, True)
+        for _ in range(40):
+            s, sz, cnt = acb.mixed_frame([0, 1, 2, 3], W, H, caps, "standard")
+            if s not in exp[j] or cnt != 4:
+                errs.append(j)
+
+    rt = threading.Thread(target=receiver)
+    rt.start()
+    ts = [threading.Thread(target=render, args=(j,)) for j in range(len(views))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    stop.set()
+    rt.join()
+    for i in range(4):
+        acb.source_clear(i)
+    assert not errs

@@ -273,3 +273,42 @@ def test_port_pixel_composite_matches_golden(ob, golden):
         srcs = [ob.gen(p, w, h, i) for i, (p, (w, h)) in enumerate(zip(pats, dims))]
         b, bc, br = ob.port_composite(srcs, W, H)
         assert (bc, br, "%08x" % ob.fnv(b.tobytes())) == (rec["cols"], rec["rows"], rec["fnv"]), rec
+
+
+# ----------------------------------------------------------------- server per-client entry (stream.c:958-1191)
+def test_port_mixed_frame_matches_golden(ob, golden):
+    """the port's composition of the server entry against fingerprints of the reference's own
+    create_mixed_ascii_frame_for_client, run end to end inside oracle/_ref"""
+    recs = golden["mixed_frames"]
+    cases = ob.mixed_cases()
+    assert len(recs) == len(cases)
+    for rec, case in zip(recs, cases):
+        assert rec["clients"] == case["clients"] and rec["W"] == case["W"]
+        s, sz, cnt = ob.port_mixed_frame(ob.mixed_sources(case), case["W"], case["H"], case["level"], case["mode"],
+                                         case["palette"], bool(case["pad"]))
+        got = (sz, cnt, None if s is None else "%08x" % ob.fnv(s))
+        assert got == (rec["size"], rec["sources"], rec["fnv"]), case
+
+
+def test_port_vs_ref_mixed_frame(ob, ref_lib):
+    rng = np.random.default_rng(3)
+    done = 0
+    while done < 40:
+        n = int(rng.integers(1, 11))
+        srcs = [None if rng.random() < 0.2 else
+                ob.gen(("noise", "bars", "gradient", "grey")[i % 4], int(rng.integers(20, 400)), int(rng.integers(16, 300)), i)
+                for i in range(n)]
+        W, H = int(rng.integers(20, 200)), int(rng.integers(8, 60))
+        level, mode, pad = int(rng.integers(0, 4)), int(rng.integers(0, 3)), bool(rng.integers(0, 2))
+        if ob.composite_degenerate(srcs, W, H):
+            continue
+        done += 1
+        assert ob.ref_mixed_frame(srcs, W, H, level, mode, "standard", pad) == \
+            ob.port_mixed_frame(srcs, W, H, level, mode, "standard", pad), (n, W, H, level, mode, pad)
+
+
+def test_mixed_frame_reset_fixup(ob):
+    assert ob.mixed_frame_fixup(b"ab\x1b[0mcd") == b"ab\x1b[0m"
+    assert ob.mixed_frame_fixup(b"ab\x1b[0m") == b"ab\x1b[0m"
+    assert ob.mixed_frame_fixup(b"plain text") == b"plain text"
+    assert ob.mixed_frame_fixup(b"x") == b"x"
