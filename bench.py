@@ -171,6 +171,59 @@ def cpu_reference_leg(H, frames, threads, seconds_target):
     return r, kind, fp
 
 
+def server_path_leg(acb, with_reference):
+    """the server's per-client entry (stream.c:958-1191) with the senders' frames resident in
+    HBM — 9 clients sending 720p, each receiving client a 240x67 truecolor half-block terminal, one render thread
+    per receiving client as in src/server/render.c.  The reference leg is its own create_mixed_ascii_frame_for_client
+    inside oracle/_ref (single thread: it works on the server's global client table)."""
+    import threading
+    import numpy as np
+    n, sw, sh, W, H = 9, 1280, 720, 240, 67
+    rng = np.random.default_rng(777)
+    srcs = [rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8) for _ in range(n)]
+    t0 = time.perf_counter()
+    for i, s in enumerate(srcs):
+        if acb.source_update(i, s) != 0:
+            return {"error": str(acb.last_error())}
+    upd = (time.perf_counter() - t0) / n
+    caps = acb.make_caps(LEVEL, MODE, True)
+    slots = list(range(n))
+    first = acb.mixed_frame(slots, W, H, caps, "standard")
+    per = 150
+
+    def render():
+        for _ in range(per):
+            acb.mixed_frame(slots, W, H, caps, "standard")
+    render()
+    t0 = time.perf_counter()
+    render()
+    one = (time.perf_counter() - t0) / per
+    ts = [threading.Thread(target=render) for _ in range(n)]
+    t0 = time.perf_counter()
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    allc = time.perf_counter() - t0
+    out = {"workload": "9 senders x 1280x720 RGB24 resident, 9 receiving clients x 240x67 truecolor half-block, padded",
+           "api": "acb200_source_update() per received frame + acb200_mixed_frame() per (client, output frame)",
+           "frames_per_s_9_render_threads": n * per / allc, "ms_per_frame_single_thread": one * 1e3,
+           "ms_per_source_update": upd * 1e3, "frame_bytes": first[1]}
+    if with_reference:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_bind as ob
+        fn = ob.ref_mixed_frame if ob.ref() is not None else ob.port_mixed_frame
+        exp = fn(srcs, W, H, LEVEL, MODE, "standard", True)
+        R = 8
+        t0 = time.perf_counter()
+        for _ in range(R):
+            fn(srcs, W, H, LEVEL, MODE, "standard", True)
+        ref = (time.perf_counter() - t0) / R
+        out.update({"bytes_identical_to_reference": bool(exp == first), "reference_ms_per_frame_single_thread": ref * 1e3,
+                    "reference_kind": "reference" if ob.ref() is not None else "port"})
+    for i in range(n):
+        acb.source_clear(i)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -350,6 +403,8 @@ def main():
                                 "note": "reference path is nearest-neighbour: Mpix/s nominal (source px / time)"}
         if fp_ref is not None:
             line["e2e"]["bytes_identical_to_cpu_baseline"] = bool(fp_ref == fp_nn)
+    if world == 1:
+        line["server_path"] = server_path_leg(acb, not args.no_cpu_baseline)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
