@@ -47,7 +47,8 @@ class ascii_frame_source_t(C.Structure):  # ascii.h:358-361
 class acb200_render_cfg_t(C.Structure):
     _fields_ = [("src_w", C.c_int), ("src_h", C.c_int), ("cols", C.c_int), ("rows_px", C.c_int),
                 ("color_level", C.c_int), ("render_mode", C.c_int), ("scale", C.c_int), ("pad_left", C.c_int),
-                ("pad_top", C.c_int), ("palette", C.c_char_p)]
+                ("pad_top", C.c_int), ("palette", C.c_char_p),
+                ("flip_x", C.c_int), ("flip_y", C.c_int), ("color_filter", C.c_int), ("filter_time", C.c_float)]
 
 
 EXPORTS = [  # every symbol include/asciichat_b200.h declares
@@ -60,7 +61,9 @@ EXPORTS = [  # every symbol include/asciichat_b200.h declares
     "acb200_scratch_bytes", "acb200_render_batch_device", "acb200_render_batch_host", "acb200_time_batch_device",
     "acb200_composite_host", "acb200_grid_layout", "acb200_aspect_ratio", "acb200_launch_count", "acb200_version",
     "acb200_create_grid_device", "acb200_synchronize", "acb200_source_update", "acb200_source_clear",
-    "acb200_mixed_frame",
+    "acb200_mixed_frame", "apply_color_filter", "color_filter_calculate_rainbow", "acb200_display_convert",
+    "acb200_color_filter_device", "acb200_frame_packets_device", "acb200_mixed_frame_packet",
+    "acb200_trailing_reset_fixup_device",
 ]
 
 
@@ -142,6 +145,19 @@ def lib():
     L.acb200_mixed_frame.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_ushort, C.c_ushort,
                                      C.POINTER(terminal_capabilities_t), C.c_char_p, C.POINTER(C.c_size_t),
                                      C.POINTER(C.c_int)]
+    L.apply_color_filter.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_float]
+    L.color_filter_calculate_rainbow.restype = None
+    L.color_filter_calculate_rainbow.argtypes = [C.c_float, u8p, u8p, u8p]
+    L.acb200_display_convert.restype = C.c_void_p
+    L.acb200_display_convert.argtypes = [ip, C.c_ssize_t, C.c_ssize_t, cp, C.c_bool, C.c_bool, C.c_char_p, C.c_bool,
+                                         C.c_bool, C.c_int, C.c_float]
+    L.acb200_color_filter_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_float,
+                                             C.c_void_p]
+    L.acb200_frame_packets_device.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
+                                              C.c_void_p, C.c_void_p]
+    L.acb200_trailing_reset_fixup_device.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
+    L.acb200_mixed_frame_packet.restype = C.c_void_p
+    L.acb200_mixed_frame_packet.argtypes = L.acb200_mixed_frame.argtypes
     _lib = L
     return L
 
@@ -178,9 +194,9 @@ def make_caps(color_level, render_mode, wants_padding=False):
 
 
 def make_cfg(src_w, src_h, cols, rows_px, color_level, render_mode, palette="standard", scale=SCALE_NN, pad_left=0,
-             pad_top=0):
+             pad_top=0, flip_x=False, flip_y=False, color_filter=0, filter_time=0.0):
     return acb200_render_cfg_t(src_w, src_h, cols, rows_px, color_level, render_mode, scale, pad_left, pad_top,
-                               _pal(palette))
+                               _pal(palette), int(flip_x), int(flip_y), int(color_filter), float(filter_time))
 
 
 # ---- the reference's entry points -------------------------------------------------------------
@@ -259,6 +275,65 @@ def mixed_frame(slots, width, height, caps, palette_chars):
     s = C.string_at(r, n.value)
     _libc.free(r)
     return s, n.value, cnt.value
+
+
+def mixed_frame_packet(slots, width, height, caps, palette_chars):
+    """-> (header||frame bytes | None, out_size, sources_with_video): acb200_mixed_frame + acip_send_ascii_frame's
+    24-byte ascii_frame_packet_t (lib/network/acip/server.c:188-236)"""
+    k = len(slots)
+    arr = (C.c_int * max(k, 1))(*slots)
+    n, cnt = C.c_size_t(0), C.c_int(0)
+    r = lib().acb200_mixed_frame_packet(arr, k, width, height, C.byref(caps) if caps is not None else None,
+                                        _pal(palette_chars), C.byref(n), C.byref(cnt))
+    if not r:
+        return None, n.value, cnt.value
+    s = C.string_at(r, n.value)
+    _libc.free(r)
+    return s, n.value, cnt.value
+
+
+# ---- the client's display conversion (src/common/session/display.c:484-671) ---------------------
+COLOR_FILTERS = {"none": 0, "black": 1, "white": 2, "green": 3, "magenta": 4, "fuchsia": 5, "orange": 6, "teal": 7,
+                 "cyan": 8, "pink": 9, "red": 10, "yellow": 11, "rainbow": 12}  # platform/terminal.h:601-627
+
+
+def display_convert(image, width, height, caps, preserve_aspect_ratio, stretch, palette_chars, flip_x=False,
+                    flip_y=False, color_filter=0, time_seconds=0.0):
+    a, im = _img(image)
+    return _take(lib().acb200_display_convert(C.byref(im), width, height, C.byref(caps), preserve_aspect_ratio, stretch,
+                                              _pal(palette_chars), flip_x, flip_y, int(color_filter),
+                                              float(time_seconds)))
+
+
+def apply_color_filter(image, color_filter, time_seconds=0.0, stride=None):
+    """in place on a copy, like the reference on its copy (display.c:612-623): -> (rc, filtered array)"""
+    a = np.array(image, dtype=np.uint8, copy=True, order="C")
+    st = a.shape[1] * 3 if stride is None else stride
+    rc = lib().apply_color_filter(a.ctypes.data, a.shape[1], a.shape[0], st, int(color_filter), float(time_seconds))
+    return rc, a
+
+
+def calculate_rainbow(t):
+    r, g, b = C.c_uint8(0), C.c_uint8(0), C.c_uint8(0)
+    lib().color_filter_calculate_rainbow(float(t), C.byref(r), C.byref(g), C.byref(b))
+    return r.value, g.value, b.value
+
+
+def color_filter_device(d_pixels, width, height, stride, color_filter, time_seconds=0.0, stream=None):
+    return lib().acb200_color_filter_device(d_pixels, width, height, stride, int(color_filter), float(time_seconds),
+                                            stream)
+
+
+def frame_packets_device(d_out, out_pitch, d_out_len, n, width, height, d_headers, stream=None):
+    rc = lib().acb200_frame_packets_device(d_out, out_pitch, d_out_len, n, width, height, d_headers, stream)
+    if rc:
+        raise RuntimeError("acb200_frame_packets_device failed: %s" % (last_error(),))
+
+
+def trailing_reset_fixup_device(d_out, out_pitch, d_out_len, n, stream=None):
+    rc = lib().acb200_trailing_reset_fixup_device(d_out, out_pitch, d_out_len, n, stream)
+    if rc:
+        raise RuntimeError("acb200_trailing_reset_fixup_device failed: %s" % (last_error(),))
 
 
 def aspect_ratio(img_w, img_h, width, height, stretch=False):

@@ -1,0 +1,478 @@
+// effects.cu — the steps either side of the convert:
+//
+//   * client display path, src/common/session/display.c:484-671: flip / colour filter / rainbow replace are fused
+//     into the render kernels (render_dev.cuh: cells_nn, filter_px, fg_print); this file holds the host entry
+//     acb200_display_convert, the host float rainbow hue, and the standalone whole-image filter kernel
+//     k_color_filter behind apply_color_filter / acb200_color_filter_device (lib/video/rgba/color_filter.c:274-346).
+//   * wire packaging, lib/network/acip/server.c:188-236 + lib/network/crc32.c: CRC32-C of every finished frame while
+//     it is still in HBM (k_crc32c_chunks + k_crc32c_finish) and the 24-byte big-endian ascii_frame_packet_t;
+//     k_trailing_reset_fixup is the device form of the server's "frame must end in ESC[0m" cut (stream.c:1085-1127).
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "engine.h"
+
+using namespace acb;
+
+// ====================================================================== whole-image colour filter
+// In-place map over packed RGB24: out = T[gray(r,g,b)], T = 256-entry table of the filter (the filtered pixel depends
+// on the pixel only through its BT.601 grey value, color_filter.c:238-267).  HBM-bound: 3 B read + 3 B written per
+// pixel.  Each thread owns 16 pixels = three 16-byte words; grey by DP4A, table in shared memory.
+namespace {
+
+__device__ __forceinline__ uint32_t filt_entry(uint32_t gray, int mode, uint32_t frgb) { // -> 0x00BBGGRR (memory order)
+  if (mode == FM_RAINBOW) gray = 179u + (gray * 76u) / 255u; // color_filter.c:315
+  const uint32_t fr = (frgb >> 16) & 255u, fg = (frgb >> 8) & 255u, fb = frgb & 255u;
+  uint32_t r, g, b;
+  if (mode == FM_ON_WHITE) { // :254-260
+    const uint32_t w = 255u * gray, ig = 255u - gray;
+    r = (fr * ig + w) / 255u, g = (fg * ig + w) / 255u, b = (fb * ig + w) / 255u;
+  } else { // :262-265
+    r = (fr * gray) / 255u, g = (fg * gray) / 255u, b = (fb * gray) / 255u;
+  }
+  return r | (g << 8) | (b << 16);
+}
+
+__device__ __forceinline__ uint32_t gray_of_bytes(uint32_t rgbx) { // bytes r,g,b,(ignored): (77r+150g+29b)>>8
+  return __dp4a(rgbx, 0x001D964Du, 0u) >> 8;                       // color_filter.h:172 (no rounding term)
+}
+
+constexpr int CF_NT = 256;
+
+__global__ void __launch_bounds__(CF_NT) k_color_filter(uint8_t *pixels, size_t n_bytes, int mode, uint32_t frgb) {
+  __shared__ uint32_t T[256];
+  for (int i = threadIdx.x; i < 256; i += CF_NT) T[i] = filt_entry((uint32_t)i, mode, frgb);
+  __syncthreads();
+  const size_t ngroups = n_bytes / 48; // 16 pixels per group
+  uint4 *base = reinterpret_cast<uint4 *>(pixels);
+  for (size_t gidx = (size_t)blockIdx.x * CF_NT + threadIdx.x; gidx < ngroups; gidx += (size_t)gridDim.x * CF_NT) {
+    uint4 *q = base + gidx * 3;
+    const uint4 a = q[0], b = q[1], c = q[2];
+    const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    uint32_t o[12];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { // 4 pixels live in 3 consecutive words
+      const uint32_t w0 = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
+      const uint32_t p0 = T[gray_of_bytes(w0)];                           // bytes 0..2
+      const uint32_t p1 = T[gray_of_bytes(__byte_perm(w0, w1, 0x6543))];  // bytes 3..5
+      const uint32_t p2 = T[gray_of_bytes(__byte_perm(w1, w2, 0x5432))];  // bytes 6..8
+      const uint32_t p3 = T[gray_of_bytes(w2 >> 8)];                      // bytes 9..11
+      o[3 * k] = p0 | (p1 << 24);
+      o[3 * k + 1] = (p1 >> 8) | (p2 << 16);
+      o[3 * k + 2] = (p2 >> 16) | (p3 << 8);
+    }
+    q[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    q[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    q[2] = make_uint4(o[8], o[9], o[10], o[11]);
+  }
+  // tail (< 16 pixels) and nothing else: byte-wise by the first threads of block 0
+  if (blockIdx.x == 0) {
+    const size_t done = ngroups * 48;
+    for (size_t i = done + 3u * threadIdx.x; i + 2 < n_bytes; i += 3u * CF_NT) {
+      const uint32_t t = T[(77u * pixels[i] + 150u * pixels[i + 1] + 29u * pixels[i + 2]) >> 8];
+      pixels[i] = (uint8_t)t;
+      pixels[i + 1] = (uint8_t)(t >> 8);
+      pixels[i + 2] = (uint8_t)(t >> 16);
+    }
+  }
+}
+
+// strided rows (stride != 3*width) or a base that is not 16-byte aligned: one thread per pixel
+__global__ void __launch_bounds__(CF_NT) k_color_filter_rows(uint8_t *pixels, uint32_t width, uint32_t height,
+                                                             uint32_t stride, int mode, uint32_t frgb) {
+  __shared__ uint32_t T[256];
+  for (int i = threadIdx.x; i < 256; i += CF_NT) T[i] = filt_entry((uint32_t)i, mode, frgb);
+  __syncthreads();
+  const size_t total = (size_t)width * height;
+  for (size_t i = (size_t)blockIdx.x * CF_NT + threadIdx.x; i < total; i += (size_t)gridDim.x * CF_NT) {
+    uint8_t *p = pixels + (i / width) * stride + (i % width) * 3u;
+    const uint32_t t = T[(77u * p[0] + 150u * p[1] + 29u * p[2]) >> 8];
+    p[0] = (uint8_t)t;
+    p[1] = (uint8_t)(t >> 8);
+    p[2] = (uint8_t)(t >> 16);
+  }
+}
+
+int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int filter_device(uint8_t *d_pixels, uint32_t width, uint32_t height, uint32_t stride, int mode, uint32_t frgb,
+                  cudaStream_t st) {
+  const size_t total_px = (size_t)width * height;
+  if (stride == width * 3u && (reinterpret_cast<uintptr_t>(d_pixels) & 15u) == 0) {
+    const size_t groups = total_px * 3 / 48;
+    size_t want = (groups + CF_NT - 1) / CF_NT;
+    const size_t cap = (size_t)sm_count() * 8; // 8 resident 256-thread CTAs per SM, grid-stride
+    unsigned grid = (unsigned)(want < 1 ? 1 : want > cap ? cap : want);
+    k_color_filter<<<grid, CF_NT, 0, st>>>(d_pixels, total_px * 3, mode, frgb);
+  } else {
+    size_t want = (total_px + CF_NT - 1) / CF_NT;
+    const size_t cap = (size_t)sm_count() * 8;
+    unsigned grid = (unsigned)(want < 1 ? 1 : want > cap ? cap : want);
+    k_color_filter_rows<<<grid, CF_NT, 0, st>>>(d_pixels, width, height, stride, mode, frgb);
+  }
+  ACB_CUDA(cudaGetLastError());
+  count_launch();
+  return E_OK;
+}
+
+} // namespace
+
+// ====================================================================== CRC32-C of finished frames
+// Standard CRC-32C (init ~0, reflected 0x82F63B78, final ~): crc(A||B) = crc(A) * x^(8|B|) mod P  xor  crc(B), so a
+// frame is cut into 64-byte segments (one per thread, slice-by-4 tables in shared memory), every segment CRC is
+// multiplied by x^(8 * bytes-after-it) and the products are XORed — first inside a 16 KB chunk (k_crc32c_chunks),
+// then over the chunks of a frame (k_crc32c_finish, which also writes the packet header).
+namespace {
+
+constexpr uint32_t CRC_POLY = 0x82F63B78u;
+constexpr int CRC_NT = 256, CRC_SEG = 64, CRC_CHUNK = CRC_NT * CRC_SEG; // 16 KB per CTA
+
+struct CrcTables {
+  uint32_t x2n[32];   // x^(2^k) mod P, reflected
+  uint32_t seg[256];  // x^(8 * 64 * k) mod P: shift past k whole segments
+};
+__constant__ CrcTables c_crc;
+
+__host__ __device__ inline uint32_t gf_mul(uint32_t a, uint32_t b) { // a * b mod P (reflected representation)
+  uint32_t p = 0;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    p ^= (a & (0x80000000u >> i)) ? b : 0u;
+    b = (b >> 1) ^ ((b & 1u) ? CRC_POLY : 0u);
+  }
+  return p;
+}
+__host__ __device__ inline uint32_t gf_xpow8(const uint32_t *x2n, uint64_t n_bytes) { // x^(8 n) mod P
+  uint32_t p = 0x80000000u;                                                         // the polynomial "1"
+  uint64_t n = n_bytes;
+  for (int k = 3; n; n >>= 1, k = (k + 1) & 31)
+    if (n & 1u) p = gf_mul(x2n[k], p);
+  return p;
+}
+
+std::once_flag g_crc_once;
+cudaError_t g_crc_status = cudaSuccess;
+void crc_tables_init() {
+  std::call_once(g_crc_once, [] {
+    CrcTables t;
+    uint32_t p = 0x40000000u; // x^1
+    t.x2n[0] = p;
+    for (int k = 1; k < 32; k++) t.x2n[k] = p = gf_mul(p, p);
+    for (int k = 0; k < 256; k++) t.seg[k] = gf_xpow8(t.x2n, (uint64_t)CRC_SEG * k);
+    g_crc_status = cudaMemcpyToSymbol(c_crc, &t, sizeof(t));
+  });
+}
+
+// grid (chunks, frames).  part[f * max_chunks + c] = standard CRC of chunk c of frame f (0 for chunks past the end).
+// copy_dst != nullptr: the bytes are also streamed to copy_dst + f*copy_pitch (mapped host memory on the one-frame
+// path), so the frame leaves HBM once for both purposes.
+__global__ void __launch_bounds__(CRC_NT) k_crc32c_chunks(const uint8_t *out, size_t out_pitch, const uint32_t *out_len,
+                                                          uint32_t *part, int max_chunks, uint8_t *copy_dst,
+                                                          size_t copy_pitch) {
+  __shared__ uint32_t T[4][256];
+  __shared__ uint32_t s_red[CRC_NT / 32];
+  const int tid = threadIdx.x, f = blockIdx.y, c = blockIdx.x;
+  const uint32_t L = out_len[f];
+  const size_t c0 = (size_t)c * CRC_CHUNK;
+  if (c0 >= L) {
+    if (tid == 0) part[(size_t)f * max_chunks + c] = 0u;
+    return;
+  }
+  { // slice-by-4 tables: T[0] the byte table, T[k][i] = T[0][T[k-1][i] & 255] ^ (T[k-1][i] >> 8)
+    uint32_t v = (uint32_t)tid;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v = (v >> 1) ^ ((v & 1u) ? CRC_POLY : 0u);
+    T[0][tid] = v;
+  }
+  __syncthreads();
+  {
+    uint32_t v = T[0][tid];
+#pragma unroll
+    for (int k = 1; k < 4; k++) {
+      v = T[0][v & 255u] ^ (v >> 8);
+      T[k][tid] = v;
+    }
+  }
+  __syncthreads();
+
+  const uint32_t n = (uint32_t)((L - c0) < (size_t)CRC_CHUNK ? (L - c0) : (size_t)CRC_CHUNK); // bytes in this chunk
+  const uint32_t tl = (n - 1u) / CRC_SEG, rem = n - tl * CRC_SEG;                            // last segment, 1..64 bytes
+  const uint8_t *src = out + (size_t)f * out_pitch + c0 + (size_t)tid * CRC_SEG;
+  uint8_t *dst = copy_dst ? copy_dst + (size_t)f * copy_pitch + c0 + (size_t)tid * CRC_SEG : nullptr;
+  uint32_t contrib = 0u;
+  if ((uint32_t)tid < tl) { // a whole segment: four 16-byte loads, slice-by-4
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = s4[k];
+    if (dst) {
+      uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+      for (int k = 0; k < 4; k++) d4[k] = v[k];
+    }
+    uint32_t crc = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        crc ^= w[j];
+        crc = T[3][crc & 255u] ^ T[2][(crc >> 8) & 255u] ^ T[1][(crc >> 16) & 255u] ^ T[0][crc >> 24];
+      }
+    }
+    contrib = gf_mul(c_crc.seg[tl - 1u - (uint32_t)tid], ~crc); // shifted past the whole segments that follow
+  } else if ((uint32_t)tid == tl) {                               // the chunk's last segment: rem bytes
+    uint32_t crc = 0xFFFFFFFFu;
+    for (uint32_t i = 0; i < rem; i++) {
+      const uint8_t b = src[i];
+      if (dst) dst[i] = b;
+      crc = T[0][(crc ^ b) & 255u] ^ (crc >> 8);
+    }
+    contrib = ~crc;
+  }
+  // XOR-reduce the whole segments, shift them past the last one, add it
+  uint32_t whole = ((uint32_t)tid < tl) ? contrib : 0u;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) whole ^= __shfl_xor_sync(0xffffffffu, whole, d);
+  if ((tid & 31) == 0) s_red[tid >> 5] = whole;
+  __syncthreads();
+  if ((uint32_t)tid == tl) {
+    uint32_t w = 0u;
+#pragma unroll
+    for (int i = 0; i < CRC_NT / 32; i++) w ^= s_red[i];
+    if (tl) w = gf_mul(gf_xpow8(c_crc.x2n, rem), w);
+    part[(size_t)f * max_chunks + c] = w ^ contrib;
+  }
+}
+
+// one warp per frame: combine the chunk CRCs, write the header (server.c:206-214, all fields big-endian)
+__global__ void __launch_bounds__(32) k_crc32c_finish(const uint32_t *part, int max_chunks, const uint32_t *out_len,
+                                                      uint32_t width, uint32_t height, uint8_t *headers,
+                                                      size_t header_pitch) {
+  const int f = blockIdx.x, lane = threadIdx.x;
+  const uint32_t L = out_len[f];
+  const uint32_t nchunks = (L + CRC_CHUNK - 1u) / CRC_CHUNK;
+  uint32_t acc = 0u;
+  for (uint32_t c = lane; c < nchunks; c += 32) {
+    const uint64_t end = (uint64_t)(c + 1u) * CRC_CHUNK;
+    const uint64_t after = end < L ? L - end : 0u;
+    const uint32_t p = part[(size_t)f * max_chunks + c];
+    acc ^= after ? gf_mul(gf_xpow8(c_crc.x2n, after), p) : p;
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, d);
+  if (lane < 6) {
+    const uint32_t v = lane == 0 ? width : lane == 1 ? height : lane == 2 ? L : lane == 4 ? acc : 0u;
+    uint8_t *h = headers + (size_t)f * header_pitch + 4 * lane;
+    h[0] = (uint8_t)(v >> 24);
+    h[1] = (uint8_t)(v >> 16);
+    h[2] = (uint8_t)(v >> 8);
+    h[3] = (uint8_t)v;
+  }
+}
+
+// stream.c:1085-1127 on the device: a frame that does not end in ESC[0m is cut after its last ESC[0m, if it has one.
+// One CTA per frame, scanning backwards; almost always decided by the first four bytes looked at.
+__global__ void __launch_bounds__(256) k_trailing_reset_fixup(uint8_t *out, size_t out_pitch, uint32_t *out_len) {
+  __shared__ int s_found;
+  const int f = blockIdx.x, tid = threadIdx.x;
+  uint8_t *s = out + (size_t)f * out_pitch;
+  const uint32_t L = out_len[f];
+  if (L < 4u) return;
+  auto is_reset = [&](uint32_t p) { return s[p] == 0x1b && s[p + 1] == '[' && s[p + 2] == '0' && s[p + 3] == 'm'; };
+  if (is_reset(L - 4u)) return; // uniform: every thread reads the same bytes
+  if (tid == 0) s_found = -1;
+  __syncthreads();
+  for (long long hi = (long long)L - 4; hi >= 0; hi -= 256) { // candidate starts hi, hi-1, ... in blocks of 256
+    const long long p = hi - tid;
+    if (p >= 0 && is_reset((uint32_t)p)) atomicMax(&s_found, (int)p);
+    __syncthreads();
+    if (s_found >= 0) break;
+  }
+  if (tid == 0 && s_found >= 0) {
+    s[s_found + 4] = 0;
+    out_len[f] = (uint32_t)s_found + 4u;
+  }
+}
+
+} // namespace
+
+namespace acb {
+
+int max_crc_chunks(size_t frame_capacity) { return (int)((frame_capacity + CRC_CHUNK - 1) / CRC_CHUNK); }
+
+int launch_reset_fixup(uint8_t *d_out, size_t out_pitch, uint32_t *d_out_len, int n_frames, cudaStream_t st) {
+  k_trailing_reset_fixup<<<(unsigned)n_frames, 256, 0, st>>>(d_out, out_pitch, d_out_len);
+  ACB_CUDA(cudaGetLastError());
+  count_launch();
+  return E_OK;
+}
+
+// d_part: n_frames * max_chunks words of device scratch
+int launch_frame_packets(const uint8_t *d_out, size_t out_pitch, const uint32_t *d_out_len, int n_frames, int max_chunks,
+                         uint32_t width, uint32_t height, uint32_t *d_part, uint8_t *headers, size_t header_pitch,
+                         uint8_t *copy_dst, size_t copy_pitch, cudaStream_t st) {
+  crc_tables_init();
+  if (g_crc_status != cudaSuccess) return set_error(E_INVALID_STATE, "CUDA: CRC table upload failed");
+  for (int f0 = 0; f0 < n_frames; f0 += 65535) { // gridDim.y limit
+    const int nf = n_frames - f0 < 65535 ? n_frames - f0 : 65535;
+    k_crc32c_chunks<<<dim3((unsigned)max_chunks, (unsigned)nf), CRC_NT, 0, st>>>(
+        d_out + (size_t)f0 * out_pitch, out_pitch, d_out_len + f0, d_part + (size_t)f0 * max_chunks, max_chunks,
+        copy_dst ? copy_dst + (size_t)f0 * copy_pitch : nullptr, copy_pitch);
+    ACB_CUDA(cudaGetLastError());
+  }
+  k_crc32c_finish<<<(unsigned)n_frames, 32, 0, st>>>(d_part, max_chunks, d_out_len, width, height, headers, header_pitch);
+  ACB_CUDA(cudaGetLastError());
+  count_launch(2);
+  return E_OK;
+}
+
+} // namespace acb
+
+// ====================================================================== C ABI
+extern "C" {
+
+// lib/video/rgba/color_filter.c:165-236 — host float on purpose, expression for expression (like aspect_ratio):
+// fmodf / floorf / fminf are exactly rounded, so the host compiler's result is the reference's.
+void color_filter_calculate_rainbow(float time, uint8_t *r, uint8_t *g, uint8_t *b) {
+  const float cycle_period = 3.5f;
+  float phase = fmodf(time, cycle_period) / cycle_period;
+  float hue = phase * 360.0f;
+  float h = hue / 60.0f;
+  int i = (int)floorf(h);
+  float f = h - (float)i;
+  float q = 1.0f - f;
+  float t = f;
+  switch (i % 6) {
+  case 0: *r = 255; *g = (uint8_t)(t * 255.0f + 0.5f); *b = 0; break;
+  case 1: *r = (uint8_t)(q * 255.0f + 0.5f); *g = 255; *b = 0; break;
+  case 2: *r = 0; *g = 255; *b = (uint8_t)(t * 255.0f + 0.5f); break;
+  case 3: *r = 0; *g = (uint8_t)(q * 255.0f + 0.5f); *b = 255; break;
+  case 4: *r = (uint8_t)(t * 255.0f + 0.5f); *g = 0; *b = 255; break;
+  case 5: *r = 255; *g = 0; *b = (uint8_t)(q * 255.0f + 0.5f); break;
+  default: *r = 255; *g = 0; *b = 0; break;
+  }
+  const float min_luminance = 120.0f;
+  float luminance = 0.2126f * *r + 0.7152f * *g + 0.0722f * *b;
+  if (luminance < min_luminance) {
+    float boost = (min_luminance - luminance) / 3.0f;
+    *r = (uint8_t)fminf(255.0f, *r + boost);
+    *g = (uint8_t)fminf(255.0f, *g + boost);
+    *b = (uint8_t)fminf(255.0f, *b + boost);
+  }
+}
+
+int acb200_color_filter_device(uint8_t *d_pixels, uint32_t width, uint32_t height, uint32_t stride, int filter,
+                               float time, void *stream) {
+  if (!d_pixels || width == 0 || height == 0 || stride == 0) return -1; // color_filter.c:276
+  if (filter == 0) return 0;
+  int mode;
+  uint32_t rgb;
+  if (!resolve_pixel_filter(filter, time, &mode, &rgb)) return -1; // :326-329
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!st) {
+    ThreadCtx *cx = thread_ctx();
+    if (!cx) return -1;
+    st = cx->stream;
+  } else if (ensure_device() != 0) {
+    return -1;
+  }
+  return filter_device(d_pixels, width, height, stride, mode, rgb, st) == E_OK ? 0 : -1;
+}
+
+int apply_color_filter(uint8_t *pixels, uint32_t width, uint32_t height, uint32_t stride, int filter, float time) {
+  if (!pixels || width == 0 || height == 0 || stride == 0) return -1;
+  if (filter == 0) return 0;
+  int mode;
+  uint32_t rgb;
+  if (!resolve_pixel_filter(filter, time, &mode, &rgb)) return -1;
+  ThreadCtx *cx = thread_ctx();
+  if (!cx) return -1;
+  const size_t bytes = (size_t)stride * (height - 1) + (size_t)width * 3; // the last row has no trailing stride
+  if (!grow_pinned(&cx->h_in, &cx->h_in_cap, bytes) || !grow_device(&cx->d_in, &cx->d_in_cap, bytes + 48)) return -1;
+  memcpy(cx->h_in, pixels, bytes);
+  if (cudaMemcpyAsync(cx->d_in, cx->h_in, bytes, cudaMemcpyHostToDevice, cx->stream) != cudaSuccess ||
+      filter_device(cx->d_in, width, height, stride, mode, rgb, cx->stream) != E_OK ||
+      cudaMemcpyAsync(cx->h_in, cx->d_in, bytes, cudaMemcpyDeviceToHost, cx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(cx->stream) != cudaSuccess) {
+    set_error(E_INVALID_STATE, "apply_color_filter: CUDA failure (%s)", cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  if (stride == width * 3u) {
+    memcpy(pixels, cx->h_in, bytes);
+  } else { // only the pixel bytes of each row were touched on the device; copy just those back
+    for (uint32_t y = 0; y < height; y++)
+      memcpy(pixels + (size_t)y * stride, cx->h_in + (size_t)y * stride, (size_t)width * 3);
+  }
+  return 0;
+}
+
+// src/common/session/display.c:484-671 (flip -> filter -> convert -> rainbow), one fused pass
+char *acb200_display_convert(const image_t *image, ssize_t width, ssize_t height, const terminal_capabilities_t *caps,
+                             bool preserve_aspect_ratio, bool stretch, const char *palette_chars, bool flip_x,
+                             bool flip_y, int color_filter, float time_seconds) {
+  if (image == nullptr || caps == nullptr) { // ascii.c:198
+    set_error(E_INVALID_PARAM, "Invalid parameters for acb200_display_convert");
+    return nullptr;
+  }
+  if (image->w > 0 && image->w <= 10000 && image->h > 0 && image->h <= 10000 && image->pixels == nullptr) { // :209
+    set_error(E_INVALID_PARAM, "Original image pixels pointer is NULL");
+    return nullptr;
+  }
+  acb200_render_cfg_t cfg;
+  if (!plan_convert_with_caps(image->w, image->h, width, height, caps, preserve_aspect_ratio, stretch, palette_chars,
+                              &cfg))
+    return nullptr;
+  cfg.flip_x = flip_x ? 1 : 0;
+  cfg.flip_y = flip_y ? 1 : 0;
+  cfg.color_filter = color_filter;
+  cfg.filter_time = time_seconds;
+  return render_one_host(cfg, reinterpret_cast<const uint8_t *>(image->pixels), nullptr);
+}
+
+int acb200_trailing_reset_fixup_device(uint8_t *d_out, size_t out_pitch, uint32_t *d_out_len, int n_frames,
+                                       void *stream) {
+  if (!d_out || !d_out_len || n_frames < 0) return set_error(E_INVALID_PARAM, "acb200_trailing_reset_fixup_device: bad argument");
+  if (n_frames == 0) return E_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!st) {
+    ThreadCtx *cx = thread_ctx();
+    if (!cx) return acb200_last_error();
+    st = cx->stream;
+  } else if (ensure_device() != 0) {
+    return acb200_last_error();
+  }
+  return launch_reset_fixup(d_out, out_pitch, d_out_len, n_frames, st);
+}
+
+int acb200_frame_packets_device(const uint8_t *d_out, size_t out_pitch, const uint32_t *d_out_len, int n_frames,
+                                uint32_t width, uint32_t height, uint8_t *d_headers, void *stream) {
+  if (!d_out || !d_out_len || !d_headers || n_frames < 0 || out_pitch == 0)
+    return set_error(E_INVALID_PARAM, "acb200_frame_packets_device: bad argument");
+  if ((reinterpret_cast<uintptr_t>(d_out) & 15u) || (out_pitch & 15u))
+    return set_error(E_INVALID_PARAM, "acb200_frame_packets_device: arena base and pitch must be multiples of 16");
+  if (n_frames == 0) return E_OK;
+  ThreadCtx *cx = thread_ctx();
+  if (!cx) return acb200_last_error();
+  cudaStream_t st = stream ? (cudaStream_t)stream : cx->stream;
+  const int mc = max_crc_chunks(out_pitch);
+  // chunk CRCs live in this thread's context; a foreign stream must not race the next call on the same thread
+  if (!grow_device((uint8_t **)&cx->d_len, &cx->d_len_cap, (size_t)n_frames * mc * sizeof(uint32_t)))
+    return acb200_last_error();
+  int rc = launch_frame_packets(d_out, out_pitch, d_out_len, n_frames, mc, width, height, cx->d_len, d_headers,
+                                ACB200_FRAME_HEADER_BYTES, nullptr, 0, st);
+  if (rc == E_OK && stream) ACB_CUDA(cudaStreamSynchronize(st)); // see above: d_len is reused by the next call
+  return rc;
+}
+
+} // extern "C"

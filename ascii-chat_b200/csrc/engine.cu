@@ -157,6 +157,7 @@ static void destroy_ctx_pool() { // acb200_shutdown: contexts still leased by li
     if (c->d_out) cudaFree(c->d_out);
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_len) cudaFree(c->d_len);
+    if (c->d_frame) cudaFree(c->d_frame);
     for (auto &e : c->ev)
       if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -239,6 +240,53 @@ void destroy_lut_cache() {
   g_luts.clear();
 }
 
+// ------------------------------------------------------------------ client display steps (display.c:484-671)
+// color_filter_registry, lib/video/rgba/color_filter.c:23-142: {r, g, b, foreground_on_bg}
+static const struct {
+  uint8_t r, g, b, on_white;
+} k_filter_registry[13] = {{0, 0, 0, 0},       {0, 0, 0, 1},     {255, 255, 255, 0}, {0, 255, 65, 0},  {255, 0, 255, 0},
+                           {255, 0, 170, 0},   {255, 136, 0, 0}, {0, 221, 221, 0},   {0, 255, 255, 0}, {255, 182, 193, 0},
+                           {255, 51, 51, 0},   {255, 235, 153, 0}, {255, 0, 0, 0}};
+
+// apply_color_filter semantics (color_filter.c:274-346): which arithmetic, which colour.  false = no-op / invalid.
+bool resolve_pixel_filter(int filter, float time, int *mode, uint32_t *rgb) {
+  *mode = FM_NONE;
+  *rgb = 0;
+  if (filter <= 0 || filter >= 13) return false;
+  if (filter == 12) { // COLOR_FILTER_RAINBOW as a PIXEL filter (direct apply_color_filter call, :286-322)
+    uint8_t r, g, b;
+    color_filter_calculate_rainbow(time, &r, &g, &b);
+    *mode = FM_RAINBOW;
+    *rgb = ((uint32_t)r << 16) | ((uint32_t)g << 8) | b;
+    return true;
+  }
+  *mode = k_filter_registry[filter].on_white ? FM_ON_WHITE : FM_SCALE;
+  *rgb = ((uint32_t)k_filter_registry[filter].r << 16) | ((uint32_t)k_filter_registry[filter].g << 8) |
+         k_filter_registry[filter].b;
+  return true;
+}
+
+// what session_display_convert_to_ascii does with (flip_x, flip_y, color_filter) around the convert
+struct DisplayOps {
+  int flip_x = 0, flip_y = 0, filt_mode = FM_NONE;
+  uint32_t filt_rgb = 0, fg_over = 0;
+};
+static DisplayOps display_ops(const acb200_render_cfg_t &cfg) {
+  DisplayOps d;
+  if ((cfg.flip_x || cfg.flip_y) && cfg.src_w > 1 && cfg.src_h > 1) { // display.c:548
+    d.flip_x = cfg.flip_x ? 1 : 0;
+    d.flip_y = cfg.flip_y ? 1 : 0;
+  }
+  if (cfg.color_filter == 12) { // rainbow: the pixels stay, the string's truecolor-fg SGRs are replaced (:640-649)
+    uint8_t r, g, b;
+    color_filter_calculate_rainbow(cfg.filter_time, &r, &g, &b);
+    d.fg_over = 0x01000000u | ((uint32_t)r << 16) | ((uint32_t)g << 8) | b;
+  } else {
+    resolve_pixel_filter(cfg.color_filter, cfg.filter_time, &d.filt_mode, &d.filt_rgb); // :609-624
+  }
+  return d;
+}
+
 // ------------------------------------------------------------------ plans
 static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -279,7 +327,9 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
   int sp = SP_NN;
   if (cfg.scale == ACB200_SCALE_BOX) {
     const int band = cfg.src_h / cfg.rows_px + 2;
-    sp = ((3 * cfg.src_w) % 16 == 0 && band <= 256) ? SP_BOX_STREAM : SP_BOX_GENERIC;
+    // a pixel filter is not linear (truncating /255 per pixel), so the band cannot be summed as raw bytes
+    const bool pixel_filter = cfg.color_filter >= 1 && cfg.color_filter <= 11;
+    sp = ((3 * cfg.src_w) % 16 == 0 && band <= 256 && !pixel_filter) ? SP_BOX_STREAM : SP_BOX_GENERIC;
   } else if (cfg.scale != ACB200_SCALE_NN) {
     set_error(E_INVALID_PARAM, "unknown scale mode %d", cfg.scale);
     return false;
@@ -309,7 +359,7 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
     const char *which = which_env ? which_env : "split";
     if (!strcmp(which, "split") && ws2_smem_total(pl.mode, cfg.cols, cfg.src_w, pl.row_pitch) <= kMaxDynSmem) {
       pl.scale_path = SP_BOX_SPLIT;
-    } else if (!strcmp(which, "tma") && ((3 * cfg.src_w) >> 4) <= 2048) {
+    } else if (!strcmp(which, "tma") && ((3 * cfg.src_w) >> 4) <= 2048 && !cfg.flip_x && !cfg.flip_y) {
       int d = ws_ring_depth(pl.mode, cfg.cols, cfg.src_w, pl.row_pitch);
       static const int d_env = getenv("ACB200_RING_DEPTH") ? atoi(getenv("ACB200_RING_DEPTH")) : 0; // tuning knob
       if (d_env >= 2 && d_env <= d) d = d_env;
@@ -361,6 +411,14 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
   rp.lut = lut;
   rp.cells_out = nullptr;
   rp.n_frames = n_frames;
+  {
+    const DisplayOps d = display_ops(cfg);
+    rp.flip_x = d.flip_x;
+    rp.flip_y = pregathered ? 0 : d.flip_y; // the host gather already picked the mirrored rows
+    rp.filt_mode = d.filt_mode;
+    rp.filt_rgb = d.filt_rgb;
+    rp.fg_over = d.fg_over;
+  }
   // measurement knobs (never set in production): ACB200_TUNE_NOALIAS=1, ACB200_PHASE_A_ONLY=1
   static const int tune_noalias = getenv("ACB200_TUNE_NOALIAS") ? atoi(getenv("ACB200_TUNE_NOALIAS")) : 0;
   static const int phase_a_only = getenv("ACB200_PHASE_A_ONLY") ? atoi(getenv("ACB200_PHASE_A_ONLY")) : 0;
@@ -488,6 +546,7 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
   // nearest neighbour reads rows_px of the src_h rows: move only those (row-granular transfer plan);
   // the box filter reads every row.
   const bool gather = cfg.scale == ACB200_SCALE_NN && cfg.rows_px < cfg.src_h;
+  const bool gather_flip_y = cfg.flip_y && cfg.src_w > 1 && cfg.src_h > 1; // display.c:548,580-590
   const size_t in_per_frame = gather ? R * cfg.rows_px : R * cfg.src_h;
   const size_t cap = pl.frame_capacity;
   int chunk = (int)((size_t)(64u << 20) / (in_per_frame + cap));
@@ -531,8 +590,11 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
       uint8_t *dst = d_in + (size_t)i * in_per_frame;
       if (gather) {
         uint8_t *st = st_base + (size_t)i * in_per_frame;
-        for (int y = 0; y < cfg.rows_px; y++)
-          memcpy(st + (size_t)y * R, src + (size_t)nn_src_row(y, cfg.src_h, cfg.rows_px) * R, R);
+        for (int y = 0; y < cfg.rows_px; y++) {
+          uint32_t sy = nn_src_row(y, cfg.src_h, cfg.rows_px);
+          if (gather_flip_y) sy = (uint32_t)cfg.src_h - 1u - sy;
+          memcpy(st + (size_t)y * R, src + (size_t)sy * R, R);
+        }
         ACB_CUDA(cudaMemcpyAsync(dst, st, in_per_frame, cudaMemcpyHostToDevice, cx->stream));
       } else if (is_pinned(src)) {
         ACB_CUDA(cudaMemcpyAsync(dst, src, in_per_frame, cudaMemcpyHostToDevice, cx->stream));
@@ -579,15 +641,19 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
 }
 
 // one frame that is already resident on the device -> allocator-owned string (server path with resident sources)
-char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, size_t *out_len) {
+char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, size_t *out_len, const OneFrameOpts &opts) {
   Plan pl;
   if (!make_plan(cfg, pl)) return nullptr;
   ThreadCtx *cx = thread_ctx();
   if (!cx) return nullptr;
   uint8_t *scratch_before = cx->d_scratch;
+  const int mc = max_crc_chunks(pl.frame_capacity);
   if (!grow_device(&cx->d_scratch, &cx->d_scratch_cap, scratch_bytes(pl, 1)) ||
-      !grow_pinned(&cx->h_out, &cx->h_out_cap, pl.frame_capacity) ||
+      !grow_pinned(&cx->h_out, &cx->h_out_cap, pl.frame_capacity + 32) ||
       !grow_pinned((uint8_t **)&cx->h_len, &cx->h_len_cap, 256))
+    return nullptr;
+  if (opts.packet && (!grow_device(&cx->d_frame, &cx->d_frame_cap, pl.frame_capacity) ||
+                      !grow_device((uint8_t **)&cx->d_len, &cx->d_len_cap, (size_t)(16 + mc) * sizeof(uint32_t))))
     return nullptr;
   if (cx->d_scratch != scratch_before) cx->scratch_dirty = true;
   const bool will_be_direct = pl.mode != EM_DITHER_BG && pl.use_smem_out && pl.scale_path != SP_BOX_TMA;
@@ -596,12 +662,30 @@ char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, si
     cx->lb = LookbackState();
     cx->scratch_dirty = !will_be_direct;
   }
-  if (render_device(cfg, pl, d_rgb, (size_t)cfg.src_w * cfg.src_h * 3, 0, 1, cx->h_out, pl.frame_capacity, cx->h_len,
+  // plain: the kernels write the string straight into mapped pinned host memory.  packet: the string stays in HBM for
+  // the fix-up and the CRC scan, which streams it to the host buffer (at +32: 8 spare, 24 header, frame 16-aligned).
+  uint8_t *arena = opts.packet ? cx->d_frame : cx->h_out;
+  uint32_t *lens = opts.packet ? cx->d_len : cx->h_len;
+  if (render_device(cfg, pl, d_rgb, (size_t)cfg.src_w * cfg.src_h * 3, 0, 1, arena, pl.frame_capacity, lens,
                     cx->d_scratch, cx->stream, nullptr, nullptr, &cx->lb) != E_OK)
+    return nullptr;
+  if (opts.reset_fixup && launch_reset_fixup(arena, pl.frame_capacity, lens, 1, cx->stream) != E_OK) return nullptr;
+  if (opts.packet && launch_frame_packets(arena, pl.frame_capacity, lens, 1, mc, opts.pk_w, opts.pk_h, cx->d_len + 16,
+                                          cx->h_out + 8, 24, cx->h_out + 32, 0, cx->stream) != E_OK)
     return nullptr;
   if (cudaStreamSynchronize(cx->stream) != cudaSuccess) {
     set_error(E_INVALID_STATE, "CUDA failure while rendering a resident frame");
     return nullptr;
+  }
+  if (opts.packet) {
+    const uint8_t *h = cx->h_out + 8;
+    const size_t len = ((size_t)h[8] << 24) | ((size_t)h[9] << 16) | ((size_t)h[10] << 8) | h[11]; // original_size
+    char *sp = (char *)user_alloc(24 + len + 1);
+    if (!sp) return nullptr;
+    memcpy(sp, h, 24 + len); // header and frame are adjacent in the staging buffer
+    sp[24 + len] = '\0';
+    if (out_len) *out_len = 24 + len;
+    return sp;
   }
   const size_t len = cx->h_len[0];
   char *sp = (char *)user_alloc(len + 1);

@@ -44,7 +44,8 @@ struct ThreadCtx {
   uint8_t *d_in = nullptr;   size_t d_in_cap = 0;
   uint8_t *d_out = nullptr;  size_t d_out_cap = 0;
   uint8_t *d_scratch = nullptr; size_t d_scratch_cap = 0;
-  uint32_t *d_len = nullptr; size_t d_len_cap = 0;
+  uint32_t *d_len = nullptr; size_t d_len_cap = 0;   // [0..15] frame lengths, [16..] CRC chunk words (effects.cu)
+  uint8_t *d_frame = nullptr; size_t d_frame_cap = 0; // device arena of the one-frame packet path
   uint32_t *h_len = nullptr; size_t h_len_cap = 0;  // pinned
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -55,6 +56,9 @@ bool grow_device(uint8_t **p, size_t *cap, size_t need);
 const GlyphLut *device_lut(const char *palette, int which); // cached per (palette, which); nullptr => error set
 void destroy_lut_cache();
 void destroy_sources(); // server.cu: resident client frames
+
+// apply_color_filter's arithmetic for `filter` (color_filter.c:274-346): FilterMode + 0x00RRGGBB; false = no-op/invalid
+bool resolve_pixel_filter(int filter, float time, int *mode, uint32_t *rgb);
 
 void *user_alloc(size_t n);
 void user_free(void *p);
@@ -70,7 +74,21 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
 
 // one frame from a host RGB24 buffer -> allocator-owned string (used by every drop-in entry point)
 char *render_one_host(const acb200_render_cfg_t &cfg, const uint8_t *rgb, size_t *out_len);
-char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, size_t *out_len);
+// reset_fixup: apply stream.c:1085-1127 (cut after the last ESC[0m) on the device.  packet: return header||frame
+// (lib/network/acip/server.c:203-236) for a terminal of pk_w x pk_h; *out_len then counts the 24 header bytes too.
+struct OneFrameOpts {
+  bool reset_fixup = false, packet = false;
+  uint32_t pk_w = 0, pk_h = 0;
+};
+char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, size_t *out_len,
+                        const OneFrameOpts &opts = OneFrameOpts());
+
+// effects.cu
+int max_crc_chunks(size_t frame_capacity);
+int launch_reset_fixup(uint8_t *d_out, size_t out_pitch, uint32_t *d_out_len, int n_frames, cudaStream_t st);
+int launch_frame_packets(const uint8_t *d_out, size_t out_pitch, const uint32_t *d_out_len, int n_frames, int max_chunks,
+                         uint32_t width, uint32_t height, uint32_t *d_part, uint8_t *headers, size_t header_pitch,
+                         uint8_t *copy_dst, size_t copy_pitch, cudaStream_t st);
 // ascii_convert_with_capabilities' front half (ascii.c:194-265): validation, aspect fit, padding -> a render cfg
 bool plan_convert_with_caps(int w, int h, ssize_t width, ssize_t height, const terminal_capabilities_t *caps,
                             bool use_aspect_ratio, bool stretch, const char *palette, acb200_render_cfg_t *cfg);

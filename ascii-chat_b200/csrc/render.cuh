@@ -69,8 +69,22 @@ struct RenderParams {
   int pad_top;
   int direct;             // 1: emitters place rows in the final arena (look-back); 0: scratch rows + k_stitch
   int ring_depth;         // warp-specialised kernel: source rows kept in flight by the producer warp
+  // client display path (src/common/session/display.c:484-671), fused into the sampling and the emission:
+  int flip_x, flip_y;     // the source is read mirrored (display.c:548-591); flip_y is already applied when pregathered
+  int filt_mode;          // apply_color_filter (color_filter.c:238-346): FM_* below, on every pixel that is read
+  uint32_t filt_rgb;      // the filter's colour, 0x00RRGGBB
+  uint32_t fg_over;       // rainbow_replace_ansi_colors (color_filter.c:348-408): 0, or 0x01RRGGBB printed in place of
+                          // every truecolor-foreground SGR colour (run/dedupe decisions still use the pixel colours)
   unsigned long long *dbg; // measurement counters (tune_flags bit 2): streamer wait, emitter wait, emitter busy, tiles
   int tune_flags;         // bit0: do not alias V with the row staging buffer (measurement knob)
+};
+
+// colour filter arithmetic variants (colorize_grayscale_pixel, color_filter.c:238-267)
+enum FilterMode : int {
+  FM_NONE = 0,
+  FM_SCALE = 1,   // white-on-colour: c * gray / 255
+  FM_ON_WHITE = 2, // colour-on-white ("black" filter): (c * (255 - gray) + 255 * gray) / 255
+  FM_RAINBOW = 3  // FM_SCALE with gray lifted to 179 + gray * 76 / 255 (color_filter.c:305-318)
 };
 
 struct StitchParams {

@@ -306,7 +306,23 @@ __device__ __forceinline__ uint32_t load_px(const uint8_t *p) {
   return ((uint32_t)p[0] << 16) | ((uint32_t)p[1] << 8) | (uint32_t)p[2];
 }
 
-// nearest neighbour — image.c:293-325 (u32 fixed-point, wraps like the reference)
+// apply_color_filter on one pixel (color_filter.c:238-267, 305-318, 338-341; rgb_to_grayscale color_filter.h:172).
+// A pointwise map commutes with nearest-neighbour sampling, so the reference's whole-image pre-pass
+// (display.c:609-624) costs one evaluation per sampled pixel here.
+__device__ __forceinline__ uint32_t filter_px(uint32_t c, int mode, uint32_t frgb) {
+  if (mode == FM_NONE) return c;
+  uint32_t gray = (77u * ((c >> 16) & 255u) + 150u * ((c >> 8) & 255u) + 29u * (c & 255u)) >> 8;
+  if (mode == FM_RAINBOW) gray = 179u + (gray * 76u) / 255u;
+  const uint32_t fr = (frgb >> 16) & 255u, fg = (frgb >> 8) & 255u, fb = frgb & 255u;
+  if (mode == FM_ON_WHITE) {
+    const uint32_t w = 255u * gray, ig = 255u - gray;
+    return (((fr * ig + w) / 255u) << 16) | (((fg * ig + w) / 255u) << 8) | ((fb * ig + w) / 255u);
+  }
+  return (((fr * gray) / 255u) << 16) | (((fg * gray) / 255u) << 8) | ((fb * gray) / 255u);
+}
+
+// nearest neighbour — image.c:293-325 (u32 fixed-point, wraps like the reference); the sampled coordinate is
+// mirrored when the display path flips the image first (display.c:563-590)
 template <int NT>
 __device__ __forceinline__ void cells_nn(const RenderParams &p, const uint8_t *frame, int y, uint32_t *out) {
   const uint32_t xr = (uint32_t)((((uint64_t)p.src_w << 16) / (uint64_t)p.cols) + 1);
@@ -317,12 +333,14 @@ __device__ __forceinline__ void cells_nn(const RenderParams &p, const uint8_t *f
   } else {
     sy = ((uint32_t)y * yr) >> 16;
     if (sy >= (uint32_t)p.src_h) sy = (uint32_t)p.src_h - 1;
+    if (p.flip_y) sy = (uint32_t)p.src_h - 1u - sy;
   }
   const uint8_t *row = frame + (size_t)sy * (size_t)p.src_w * 3u;
   for (int x = threadIdx.x; x < p.cols; x += NT) {
     uint32_t sx = ((uint32_t)x * xr) >> 16;
     if (sx >= (uint32_t)p.src_w) sx = (uint32_t)p.src_w - 1;
-    out[x] = load_px(row + (size_t)sx * 3u);
+    if (p.flip_x) sx = (uint32_t)p.src_w - 1u - sx;
+    out[x] = filter_px(load_px(row + (size_t)sx * 3u), p.filt_mode, p.filt_rgb);
   }
 }
 
@@ -343,12 +361,24 @@ __device__ __forceinline__ void cells_box_generic(const RenderParams &p, const u
     int x0, x1;
     box_range(x, p.src_w, p.cols, x0, x1);
     uint32_t sr = 0, sg = 0, sb = 0;
+    // the box is taken over the flipped, filtered image (display.c order): mirror the range, filter every pixel
+    const int xs = p.flip_x ? p.src_w - x1 : x0;
     for (int yy = y0; yy < y1; yy++) {
-      const uint8_t *q = frame + ((size_t)yy * p.src_w + x0) * 3u;
-      for (int xx = x0; xx < x1; xx++, q += 3) {
-        sr += q[0];
-        sg += q[1];
-        sb += q[2];
+      const int ys = p.flip_y ? p.src_h - 1 - yy : yy;
+      const uint8_t *q = frame + ((size_t)ys * p.src_w + xs) * 3u;
+      if (p.filt_mode == FM_NONE) {
+        for (int xx = x0; xx < x1; xx++, q += 3) {
+          sr += q[0];
+          sg += q[1];
+          sb += q[2];
+        }
+      } else {
+        for (int xx = x0; xx < x1; xx++, q += 3) {
+          const uint32_t c = filter_px(load_px(q), p.filt_mode, p.filt_rgb);
+          sr += c >> 16;
+          sg += (c >> 8) & 255u;
+          sb += c & 255u;
+        }
       }
     }
     uint32_t n = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0), h = n >> 1;
@@ -397,8 +427,9 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
   box_range(y, p.src_h, p.rows_px, y0, y1);
   const int R = p.src_w * 3;
   const int nchunk = R >> 4;
-  const uint4 *band = reinterpret_cast<const uint4 *>(frame + (size_t)y0 * (size_t)R);
   const int nrow = y1 - y0;
+  if (p.flip_y) y0 = p.src_h - y1; // the band of the mirrored image is the mirrored band (sums do not care about order)
+  const uint4 *band = reinterpret_cast<const uint4 *>(frame + (size_t)y0 * (size_t)R);
   for (int c = threadIdx.x; c < nchunk; c += NT) {
     uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const uint8_t *q = reinterpret_cast<const uint8_t *>(band + c);
@@ -437,7 +468,7 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
     int x0, x1;
     box_range(x, p.src_w, p.cols, x0, x1);
     uint32_t sr = 0, sg = 0, sb = 0;
-    const uint16_t *q = V + 3 * x0;
+    const uint16_t *q = V + 3 * (p.flip_x ? p.src_w - x1 : x0);
 #pragma unroll 4
     for (int xx = x0; xx < x1; xx++, q += 3) {
       sr += q[0];
@@ -456,7 +487,9 @@ struct RowCtx {
   const uint32_t *cT, *cB;
   const uint16_t *key, *hpos, *rend;
   uint32_t drop_first; // EM_TRUE_FG, direct output: the row's first ASCII cell inherits the colour state of the rows above
+  uint32_t fg_over;    // 0, or 0x01RRGGBB: colour printed by every truecolor-foreground SGR (rainbow replace)
 };
+__device__ __forceinline__ uint32_t fg_print(uint32_t px, uint32_t over) { return over ? over : px; }
 
 template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int x, const RowCtx &c) {
   if (MODE == EM_256_FG) {
@@ -474,10 +507,10 @@ template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int
     bool ascii = g[0] == 1 && g[1] < 128;
     if (ascii) {
       uint16_t pa = c.hpos[x];
-      if (pa == NONE16 ? !c.drop_first : c.cT[pa] != px) put_sgr_rgb_l(s, false, px);
+      if (pa == NONE16 ? !c.drop_first : c.cT[pa] != px) put_sgr_rgb_l(s, false, fg_print(px, c.fg_over));
       s.put(g[1]);
     } else {
-      put_sgr_rgb_l(s, false, px);
+      put_sgr_rgb_l(s, false, fg_print(px, c.fg_over));
       put_glyph(s, g);
     }
   } else if (MODE == EM_MONO_FG) {
@@ -519,7 +552,7 @@ template <int MODE, class S> __device__ __forceinline__ void emit_cell(S &s, int
       s.put(' ');
     } else if (h == x) {
       if (MODE == EM_HB_TRUE) {
-        if (!prev_set || c.cT[ph] != tH) put_sgr_rgb_l(s, false, tH);
+        if (!prev_set || c.cT[ph] != tH) put_sgr_rgb_l(s, false, fg_print(tH, c.fg_over));
         if (!prev_set || c.cB[ph] != bH) put_sgr_rgb_l(s, true, bH);
       } else {
         uint32_t k = c.key[h], pk = prev_set ? c.key[ph] : 0u;
@@ -590,7 +623,7 @@ __device__ __forceinline__ uint32_t emit_prepare(const RenderParams &p, GlyphLut
   }
 
   // ---- phase B3: byte counts -> offsets
-  RowCtx ctx{lut, cT, cB, key, hpos, rend, 0u};
+  RowCtx ctx{lut, cT, cB, key, hpos, rend, 0u, p.fg_over};
   int cells_bytes = row_scan<OpAdd, Sync, NT>(
       w,
       [&](int x) {
@@ -609,7 +642,7 @@ __device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, Gl
   const int w = p.cols;
   const bool last_row = t == p.text_rows - 1;
   const uint32_t cells_bytes = emit_prepare<MODE, Sync, NT>(p, lut, cT, cB, key, hpos, rend, off, s_tmp, s_cond, tid);
-  RowCtx ctx{lut, cT, cB, key, hpos, rend, 0u};
+  RowCtx ctx{lut, cT, cB, key, hpos, rend, 0u, p.fg_over};
   const uint32_t body_end = (uint32_t)p.pad_left + cells_bytes;
 
   // ---- phase B4: materialise
@@ -628,8 +661,8 @@ __device__ __forceinline__ void emit_row(const RenderParams &p, int f, int t, Gl
       const uint8_t *g = lut->glyph[luma_of(cT[x])];
       if (g[0] == 1 && g[1] < 128) { // the row's first ASCII-glyph cell: its SGR is conditional on the row above
         s_cond[0] = off[x];
-        s_cond[1] = 10u + (s_dec3[(cT[x] >> 16) & 255u] >> 24) + (s_dec3[(cT[x] >> 8) & 255u] >> 24) +
-                    (s_dec3[cT[x] & 255u] >> 24);
+        const uint32_t pc = fg_print(cT[x], p.fg_over);
+        s_cond[1] = 10u + (s_dec3[(pc >> 16) & 255u] >> 24) + (s_dec3[(pc >> 8) & 255u] >> 24) + (s_dec3[pc & 255u] >> 24);
         s_cond[3] = 0x01000000u | cT[x];
       }
     }
@@ -757,7 +790,7 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
         uint32_t before = __shfl_up_sync(0xffffffffu, inc, 1);
         if (lane == 0) before = 0u;
         if (before == 0u) before = carry;
-        if (fj && before && fj == before) len -= sgr_rgb_len(fj);
+        if (fj && before && fj == before) len -= sgr_rgb_len(fg_print(fj, p.fg_over));
         const uint32_t tail = __shfl_sync(0xffffffffu, inc, 31);
         if (tail) carry = tail;
       }
@@ -772,7 +805,8 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
   }
   Sync::sync();
   const uint32_t prefix = s_lb[0], carry = s_lb[1];
-  const uint32_t drop = (MODE == EM_TRUE_FG && first && carry && first == carry) ? sgr_rgb_len(first) : 0u;
+  const uint32_t drop =
+      (MODE == EM_TRUE_FG && first && carry && first == carry) ? sgr_rgb_len(fg_print(first, p.fg_over)) : 0u;
   const uint32_t dst_off = (uint32_t)p.pad_top + prefix;
   const uint32_t final_len = row_len - drop;
   uint8_t *frame_out = p.out + (size_t)f * p.out_pitch;
@@ -781,7 +815,7 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
   uint8_t *sb = outb + shift;
 
   // ---- B4: the row's bytes, already in their final form, into shared memory
-  RowCtx ctx{lut, cT, cB, key, hpos, rend, drop ? 1u : 0u};
+  RowCtx ctx{lut, cT, cB, key, hpos, rend, drop ? 1u : 0u, p.fg_over};
   for (int i = tid; i < p.pad_left; i += NT) sb[i] = ' ';
   const uint32_t sb32 = (uint32_t)__cvta_generic_to_shared(sb);
   for (int x = tid; x < w; x += NT) {

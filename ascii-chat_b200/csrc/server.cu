@@ -10,7 +10,8 @@
 //   create_multi_source_composite (:664-779)    k_composite_cell per source into a W x 2H device composite
 //   convert_composite_to_ascii (:789-853)       plan_convert_with_caps(width, HALF_BLOCK ? 2*height : height,
 //                                                 aspect=true, stretch=false) + render_one_device
-//   trailing-reset fix-up (:1085-1127)          same, on the host copy
+//   trailing-reset fix-up (:1085-1127)          k_trailing_reset_fixup (effects.cu), on the device
+//   acip_send_ascii_frame (acip/server.c:188)   acb200_mixed_frame_packet: CRC32-C scan + 24-byte header (effects.cu)
 //
 // Every client's render thread calls acb200_mixed_frame concurrently (one per client at 60 fps in the
 // reference, src/server/render.c); the N source frames cross PCIe once per update instead of once per
@@ -95,9 +96,9 @@ int acb200_source_update(int slot, const uint8_t *rgb, int w, int h) {
   return E_OK;
 }
 
-char *acb200_mixed_frame(const int *slots, int n, unsigned short width, unsigned short height,
-                         const terminal_capabilities_t *caps, const char *palette, size_t *out_size,
-                         int *out_sources_count) {
+static char *mixed_frame_impl(const int *slots, int n, unsigned short width, unsigned short height,
+                              const terminal_capabilities_t *caps, const char *palette, size_t *out_size,
+                              int *out_sources_count, bool packet) {
   if (out_sources_count) *out_sources_count = 0;
   if (!out_size || width == 0 || height == 0) { // stream.c:980
     set_error(E_INVALID_PARAM, "Invalid parameters for acb200_mixed_frame: width=%u, height=%u, out_size=%p", width,
@@ -178,23 +179,32 @@ char *acb200_mixed_frame(const int *slots, int n, unsigned short width, unsigned
   const ssize_t h = caps->render_mode == RENDER_MODE_HALF_BLOCK ? (ssize_t)height * 2 : (ssize_t)height;
   acb200_render_cfg_t cfg;
   if (!plan_convert_with_caps(comp_w, comp_h, width, h, caps, true, false, palette, &cfg)) return nullptr;
+  // stream.c:1085-1127 (a frame must end in ESC[0m; otherwise it is cut after its last ESC[0m, if it has one) runs
+  // on the device (k_trailing_reset_fixup); packet = also CRC32-C + ascii_frame_packet_t header in front
+  OneFrameOpts opts;
+  opts.reset_fixup = true;
+  opts.packet = packet;
+  opts.pk_w = width;
+  opts.pk_h = height;
   size_t len = 0;
-  char *frame = render_one_device(cfg, comp, &len);
+  char *frame = render_one_device(cfg, comp, &len, opts);
   if (!frame) return nullptr;
-
-  // stream.c:1085-1127: a frame must end in ESC[0m; otherwise it is cut after its last ESC[0m, if it has one
-  static const char rst[4] = {'\033', '[', '0', 'm'};
-  size_t out_len = len;
-  if (len >= 4 && memcmp(frame + len - 4, rst, 4) != 0) {
-    for (size_t p = len - 4 + 1; p-- > 0;)
-      if (memcmp(frame + p, rst, 4) == 0) {
-        out_len = p + 4;
-        frame[out_len] = '\0';
-        break;
-      }
-  }
-  *out_size = out_len;
+  *out_size = len;
   return frame;
+}
+
+char *acb200_mixed_frame(const int *slots, int n, unsigned short width, unsigned short height,
+                         const terminal_capabilities_t *caps, const char *palette, size_t *out_size,
+                         int *out_sources_count) {
+  return mixed_frame_impl(slots, n, width, height, caps, palette, out_size, out_sources_count, false);
+}
+
+// create_mixed_ascii_frame_for_client + acip_send_ascii_frame's packaging (lib/network/acip/server.c:188-236)
+uint8_t *acb200_mixed_frame_packet(const int *slots, int n, unsigned short width, unsigned short height,
+                                   const terminal_capabilities_t *caps, const char *palette, size_t *out_size,
+                                   int *out_sources_count) {
+  return reinterpret_cast<uint8_t *>(
+      mixed_frame_impl(slots, n, width, height, caps, palette, out_size, out_sources_count, true));
 }
 
 } // extern "C"

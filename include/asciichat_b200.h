@@ -130,6 +130,13 @@ char *rgb_to_256color_halfblocks_scalar(const uint8_t *rgb, int width, int heigh
 /* lib/video/ascii/ascii.c:602-885 (ascii.h:400) — text-space grid of N rendered frames */
 char *ascii_create_grid(ascii_frame_source_t *sources, int source_count, int width, int height, size_t *out_size);
 
+/* lib/video/rgba/color_filter.c:274-346 (color_filter.h) — monochrome tint of an RGB24 image, IN PLACE on the
+ * host buffer (H2D, k_color_filter, D2H).  0 on success, -1 on NULL / zero size / unknown filter, like the
+ * reference.  filter = color_filter_t (0 none .. 12 rainbow, include/ascii-chat/platform/terminal.h:601-627). */
+int apply_color_filter(uint8_t *pixels, uint32_t width, uint32_t height, uint32_t stride, int filter, float time);
+/* lib/video/rgba/color_filter.c:165-236 — hue of the rainbow filter at `time` (host float, like aspect_ratio) */
+void color_filter_calculate_rainbow(float time, uint8_t *r, uint8_t *g, uint8_t *b);
+
 /* lib/video/ascii/common.c:601-604, 497-538 — table init / teardown (device LUT cache here) */
 void ascii_simd_init(void);
 void simd_caches_destroy_all(void);
@@ -151,6 +158,11 @@ typedef struct {
   int pad_left;      /* spaces in front of every text row (ascii_pad_frame_width) */
   int pad_top;       /* leading newlines (ascii_pad_frame_height) */
   const char *palette; /* NUL-terminated UTF-8, <= 255 glyphs */
+  /* client display pre/post steps, fused (src/common/session/display.c:484-671); all zero = plain convert */
+  int flip_x, flip_y;  /* mirror the source first (display.c:548-591; ignored unless src_w > 1 && src_h > 1) */
+  int color_filter;    /* color_filter_t 0..12: 1..11 = apply_color_filter on the pixels before the convert
+                          (display.c:609-624); 12 (rainbow) = rainbow_replace_ansi_colors on the result (:640-649) */
+  float filter_time;   /* seconds, drives the rainbow hue (color_filter_calculate_rainbow) */
 } acb200_render_cfg_t;
 
 /* 0 on success, else an ERROR_* code.  device < 0 keeps the current device. */
@@ -213,6 +225,40 @@ const char *acb200_version(void);
  * Returns 0 and the layout-dependent string length in *out_size. */
 int acb200_create_grid_device(const uint8_t *const *d_srcs, const size_t *sizes, int n, int width, int height,
                               uint8_t *d_out, size_t *out_size, void *stream);
+
+/* ---- the client's display conversion, one fused pass -------------------------------------------------------
+ * Replaces the body of session_display_convert_to_ascii (src/common/session/display.c:484-671) between its option
+ * reads and the digital-rain stage: copy+flip X/Y (:548-591), apply_color_filter on a copy (:609-624),
+ * ascii_convert_with_capabilities (:632) and rainbow_replace_ansi_colors (:640-649).  Here the flips are index
+ * arithmetic in the sampler, the filter is evaluated on the sampled pixels only, and the rainbow colour is printed
+ * by the emitter: no image copies, no second pass over the string.  Same result bytes, same NULL/errno behaviour
+ * as ascii_convert_with_capabilities. */
+char *acb200_display_convert(const image_t *image, ssize_t width, ssize_t height, const terminal_capabilities_t *caps,
+                             bool preserve_aspect_ratio, bool stretch, const char *palette_chars, bool flip_x,
+                             bool flip_y, int color_filter, float time_seconds);
+/* apply_color_filter on an image that is already resident in device memory (in place, asynchronous on `stream`,
+ * NULL = this thread's internal stream).  6 bytes of HBM traffic per pixel. */
+int acb200_color_filter_device(uint8_t *d_pixels, uint32_t width, uint32_t height, uint32_t stride, int filter,
+                               float time, void *stream);
+
+/* ---- wire packaging of finished frames -------------------------------------------------------------------
+ * acip_send_ascii_frame (lib/network/acip/server.c:188-236) computes asciichat_crc32 over the frame (CRC32-C,
+ * lib/network/crc32.c) and prepends the 24-byte big-endian ascii_frame_packet_t (packet.h:848-862:
+ * width, height, original_size, compressed_size = 0, checksum, flags = 0).  Here the checksum is a scan over the
+ * frame while it is still in HBM: d_headers[f] receives frame f's 24 header bytes. */
+/* The server's "a frame must end in ESC[0m" cut (src/server/stream.c:1085-1127) on frames in a device arena:
+ * a frame that does not end in ESC[0m is truncated after its last ESC[0m, if it has one (d_out_len updated). */
+int acb200_trailing_reset_fixup_device(uint8_t *d_out, size_t out_pitch, uint32_t *d_out_len, int n_frames,
+                                       void *stream);
+#define ACB200_FRAME_HEADER_BYTES 24
+int acb200_frame_packets_device(const uint8_t *d_out, size_t out_pitch, const uint32_t *d_out_len, int n_frames,
+                                uint32_t width, uint32_t height, uint8_t *d_headers, void *stream);
+/* acb200_mixed_frame + the packet header in front: returns header||frame (allocator-owned, *out_size =
+ * 24 + frame bytes, no NUL needed by the transport but one is appended), i.e. the buffer acip_send_ascii_frame
+ * hands to packet_send_via_transport.  NULL with *out_size = 0 when no client sends video. */
+uint8_t *acb200_mixed_frame_packet(const int *slots, int n, unsigned short width, unsigned short height,
+                                   const terminal_capabilities_t *caps, const char *palette, size_t *out_size,
+                                   int *out_sources_count);
 
 /* ---- the server's per-client frame generation with RESIDENT sources ------------------------------------
  * Replaces src/server/stream.c:958-1191 create_mixed_ascii_frame_for_client() and what it calls

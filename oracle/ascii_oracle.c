@@ -979,3 +979,166 @@ double orc_bench_convert(const uint8_t *src, int ring, int w, int h, long width,
   free(args);
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ------------------------------------------------------------------ client display path
+ * session_display_convert_to_ascii, src/common/session/display.c:484-671: flip -> colour filter -> convert ->
+ * rainbow replace.  The filter is restated as what it is: a 256-entry table over the BT.601 grey value. */
+static const struct {
+  uint8_t r, g, b, fg_on_bg;
+} k_filters[ORC_FILTER_COUNT] = { /* color_filter.c:23-142 */
+    {0, 0, 0, 0},       {0, 0, 0, 1},     {255, 255, 255, 0}, {0, 255, 65, 0},   {255, 0, 255, 0},
+    {255, 0, 170, 0},   {255, 136, 0, 0}, {0, 221, 221, 0},   {0, 255, 255, 0},  {255, 182, 193, 0},
+    {255, 51, 51, 0},   {255, 235, 153, 0}, {255, 0, 0, 0}};
+
+void orc_calculate_rainbow(float time, uint8_t *r, uint8_t *g, uint8_t *b) { /* color_filter.c:165-236 */
+  const float period = 3.5f;
+  float phase = fmodf(time, period) / period;
+  float hue = phase * 360.0f;
+  float h = hue / 60.0f;
+  int i = (int)floorf(h);
+  float f = h - (float)i;
+  uint8_t up = (uint8_t)(f * 255.0f + 0.5f), down = (uint8_t)((1.0f - f) * 255.0f + 0.5f);
+  switch (i % 6) {
+  case 0: *r = 255, *g = up, *b = 0; break;
+  case 1: *r = down, *g = 255, *b = 0; break;
+  case 2: *r = 0, *g = 255, *b = up; break;
+  case 3: *r = 0, *g = down, *b = 255; break;
+  case 4: *r = up, *g = 0, *b = 255; break;
+  case 5: *r = 255, *g = 0, *b = down; break;
+  default: *r = 255, *g = 0, *b = 0; break;
+  }
+  float lum = 0.2126f * *r + 0.7152f * *g + 0.0722f * *b;
+  if (lum < 120.0f) {
+    float boost = (120.0f - lum) / 3.0f;
+    *r = (uint8_t)fminf(255.0f, *r + boost);
+    *g = (uint8_t)fminf(255.0f, *g + boost);
+    *b = (uint8_t)fminf(255.0f, *b + boost);
+  }
+}
+
+/* table[gray] = filtered (r,g,b); returns 0 when the filter is a no-op / invalid (color_filter.c:238-346) */
+int orc_filter_table(int filter, float time, uint8_t table[256][3]) {
+  if (filter <= ORC_FILTER_NONE || filter >= ORC_FILTER_COUNT) return 0;
+  unsigned fr = k_filters[filter].r, fg = k_filters[filter].g, fb = k_filters[filter].b;
+  int on_bg = k_filters[filter].fg_on_bg;
+  if (filter == ORC_FILTER_RAINBOW) {
+    uint8_t r, g, b;
+    orc_calculate_rainbow(time, &r, &g, &b);
+    fr = r, fg = g, fb = b;
+  }
+  for (unsigned gray = 0; gray < 256; gray++) {
+    unsigned v = gray;
+    if (filter == ORC_FILTER_RAINBOW) v = (179u + (uint8_t)((gray * (255u - 179u)) / 255u)) & 255u; /* :315 */
+    if (on_bg) { /* :254-260 */
+      table[gray][0] = (uint8_t)((fr * (255u - v) + 255u * v) / 255u);
+      table[gray][1] = (uint8_t)((fg * (255u - v) + 255u * v) / 255u);
+      table[gray][2] = (uint8_t)((fb * (255u - v) + 255u * v) / 255u);
+    } else { /* :262-265 */
+      table[gray][0] = (uint8_t)((fr * v) / 255u);
+      table[gray][1] = (uint8_t)((fg * v) / 255u);
+      table[gray][2] = (uint8_t)((fb * v) / 255u);
+    }
+  }
+  return 1;
+}
+
+int orc_apply_color_filter(uint8_t *pixels, uint32_t width, uint32_t height, uint32_t stride, int filter, float time) {
+  if (!pixels || width == 0 || height == 0 || stride == 0) return -1; /* :276 */
+  if (filter == ORC_FILTER_NONE) return 0;
+  uint8_t tab[256][3];
+  if (!orc_filter_table(filter, time, tab)) return -1;
+  for (uint32_t y = 0; y < height; y++) {
+    uint8_t *p = pixels + (size_t)y * stride;
+    for (uint32_t x = 0; x < width; x++, p += 3) {
+      unsigned gray = (77u * p[0] + 150u * p[1] + 29u * p[2]) >> 8; /* color_filter.h:172 */
+      p[0] = tab[gray][0], p[1] = tab[gray][1], p[2] = tab[gray][2];
+    }
+  }
+  return 0;
+}
+
+/* rainbow_replace_ansi_colors, color_filter.c:348-408: every ESC[38;2;...m becomes the frame's rainbow SGR.
+ * NULL when the string holds no truecolor-foreground SGR at all. */
+char *orc_rainbow_replace(const char *s, float time_seconds) {
+  static const char key[] = "\x1b[38;2;";
+  if (!s || !strstr(s, key)) return NULL;
+  uint8_t r, g, b;
+  orc_calculate_rainbow(time_seconds, &r, &g, &b);
+  char code[32];
+  int cl = snprintf(code, sizeof(code), "\x1b[38;2;%d;%d;%dm", r, g, b);
+  bb_t o = {0};
+  size_t n = strlen(s), i = 0;
+  while (i < n) {
+    if (n - i >= 7 && memcmp(s + i, key, 7) == 0) {
+      const char *m = memchr(s + i + 7, 'm', n - i - 7);
+      if (m) {
+        bb_put(&o, code, (size_t)cl);
+        i = (size_t)(m - s) + 1;
+        continue;
+      }
+    }
+    bb_put(&o, s + i, 1);
+    i++;
+  }
+  bb_need(&o, 1);
+  o.p[o.n] = '\0';
+  return o.p;
+}
+
+char *orc_display_convert(const uint8_t *rgb, int w, int h, long width, long height, int color_level, int render_mode,
+                          int wants_padding, int preserve_aspect, int stretch, const char *palette, int flip_x,
+                          int flip_y, int filter, float time_seconds, int scale, size_t *out_len) {
+  if (!rgb || w <= 0 || h <= 0) return NULL;
+  size_t px = (size_t)w * (size_t)h;
+  uint8_t *img = (uint8_t *)malloc(px * 3);
+  const int fx = flip_x && w > 1 && h > 1, fy = flip_y && w > 1 && h > 1; /* display.c:548 */
+  for (int y = 0; y < h; y++) {
+    const uint8_t *srow = rgb + (size_t)(fy ? h - 1 - y : y) * (size_t)w * 3;
+    uint8_t *drow = img + (size_t)y * (size_t)w * 3;
+    for (int x = 0; x < w; x++) memcpy(drow + 3 * (size_t)x, srow + 3 * (size_t)(fx ? w - 1 - x : x), 3);
+  }
+  if (filter != ORC_FILTER_NONE && filter != ORC_FILTER_RAINBOW)
+    orc_apply_color_filter(img, (uint32_t)w, (uint32_t)h, (uint32_t)w * 3, filter, time_seconds);
+  char *res = orc_convert_caps(img, w, h, width, height, color_level, render_mode, wants_padding, preserve_aspect,
+                               stretch, palette, scale, out_len);
+  free(img);
+  if (res && filter == ORC_FILTER_RAINBOW) {
+    char *r2 = orc_rainbow_replace(res, time_seconds);
+    if (r2) {
+      free(res);
+      res = r2;
+    }
+  }
+  if (res && out_len) *out_len = strlen(res);
+  return res;
+}
+
+/* ------------------------------------------------------------------ wire packaging
+ * CRC32-C (Castagnoli, reflected 0x82F63B78; lib/network/crc32.c:168-189 and the SSE4.2/ARMv8 instructions of
+ * :95-121) and the 24-byte big-endian ascii_frame_packet_t acip_send_ascii_frame() builds
+ * (lib/network/acip/server.c:203-214, packet.h:848-862). */
+uint32_t orc_crc32c(const uint8_t *p, size_t n) {
+  static uint32_t tab[256];
+  static int init = 0;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; i++) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      tab[i] = c;
+    }
+    init = 1;
+  }
+  uint32_t crc = 0xFFFFFFFFu;
+  for (size_t i = 0; i < n; i++) crc = tab[(crc ^ p[i]) & 255u] ^ (crc >> 8);
+  return ~crc;
+}
+
+static void put_be32(uint8_t *d, uint32_t v) { d[0] = (uint8_t)(v >> 24), d[1] = (uint8_t)(v >> 16), d[2] = (uint8_t)(v >> 8), d[3] = (uint8_t)v; }
+void orc_frame_packet_header(const uint8_t *frame, size_t frame_size, uint32_t width, uint32_t height, uint8_t out24[24]) {
+  put_be32(out24 + 0, width);
+  put_be32(out24 + 4, height);
+  put_be32(out24 + 8, (uint32_t)frame_size);
+  put_be32(out24 + 12, 0);
+  put_be32(out24 + 16, orc_crc32c(frame, frame_size));
+  put_be32(out24 + 20, 0);
+}

@@ -67,6 +67,26 @@ void orc_grid_layout(const int *ws, const int *hs, int n, int term_w, int term_h
 int orc_composite(const uint8_t *const *srcs, const int *ws, const int *hs, int n, int width, int height,
                   uint8_t *out, int *cols, int *rows);
 
+/* ---- client display path (src/common/session/display.c:484-671): flip -> colour filter -> convert -> rainbow */
+enum { /* color_filter_t, include/ascii-chat/platform/terminal.h */
+  ORC_FILTER_NONE = 0, ORC_FILTER_BLACK, ORC_FILTER_WHITE, ORC_FILTER_GREEN, ORC_FILTER_MAGENTA, ORC_FILTER_FUCHSIA,
+  ORC_FILTER_ORANGE, ORC_FILTER_TEAL, ORC_FILTER_CYAN, ORC_FILTER_PINK, ORC_FILTER_RED, ORC_FILTER_YELLOW,
+  ORC_FILTER_RAINBOW, ORC_FILTER_COUNT
+};
+void orc_calculate_rainbow(float time, uint8_t *r, uint8_t *g, uint8_t *b);          /* color_filter.c:165-236 */
+int orc_filter_table(int filter, float time, uint8_t table[256][3]);                 /* color_filter.c:238-346 as a LUT */
+int orc_apply_color_filter(uint8_t *pixels, uint32_t width, uint32_t height, uint32_t stride, int filter,
+                           float time);                                              /* color_filter.c:274-346 */
+char *orc_rainbow_replace(const char *ansi_string, float time_seconds);              /* color_filter.c:348-408 */
+char *orc_display_convert(const uint8_t *rgb, int w, int h, long width, long height, int color_level, int render_mode,
+                          int wants_padding, int preserve_aspect, int stretch, const char *palette, int flip_x,
+                          int flip_y, int filter, float time_seconds, int scale, size_t *out_len);
+
+/* ---- wire packaging (lib/network/crc32.c, lib/network/acip/server.c:203-214) */
+uint32_t orc_crc32c(const uint8_t *p, size_t n);
+void orc_frame_packet_header(const uint8_t *frame, size_t frame_size, uint32_t width, uint32_t height,
+                             uint8_t out24[24]);
+
 /* synthetic inputs: 0 noise, 1 gradient, 2 bars, 3 grey, 4 solid(seed&255) */
 void orc_gen_pattern(int kind, uint32_t frame, uint8_t *dst, int w, int h);
 uint32_t orc_fnv1a32(const uint8_t *p, size_t n);

@@ -76,6 +76,13 @@ uint64_t atomic_fetch_add_u64_impl(atomic_t *a, uint64_t delta) { return atomic_
 bool atomic_cas_u64_impl(atomic_t *a, uint64_t *expected, uint64_t new_value) {
   return atomic_compare_exchange_strong(&a->impl, expected, new_value);
 }
+bool atomic_cas_bool_impl(atomic_t *a, uint64_t *expected, uint64_t new_value) { /* crc32.c:58 */
+  /* the caller passes a `bool *` cast to uint64_t* (atomic.h:161): widen it here */
+  uint64_t e = *(const bool *)expected ? 1u : 0u;
+  return atomic_compare_exchange_strong(&a->impl, &e, new_value);
+}
+void platform_sleep_us(unsigned int usec) { usleep(usec); }
+int platform_strcasecmp(const char *s1, const char *s2) { return strcasecmp(s1, s2); }
 
 /* ---- lifecycle: true exactly once per object ----------------------------- */
 bool lifecycle_init(lifecycle_t *lc, const char *name) {

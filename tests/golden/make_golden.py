@@ -148,12 +148,35 @@ def main():
                                         bool(case["pad"]))
         mixed.append(dict(case, size=sz, sources=cnt, fnv=None if s is None else "%08x" % ob.fnv(s)))
 
+    # client display path (display.c:484-671: flip -> apply_color_filter -> convert -> rainbow replace), every byte
+    # produced by reference code driven by oracle/ref_display_shim.c
+    display = []
+    for case in ob.display_cases():
+        img = ob.gen(case["pattern"], case["W"], case["H"], 0)
+        s = ob.ref_display_convert(img, **ob.display_args(case))
+        display.append(dict(case, bytes=None if s is None else len(s), fnv=None if s is None else "%08x" % ob.fnv(s)))
+    # whole-image colour filter (color_filter.c:274-346) and the rainbow hue (:165-236)
+    filt = []
+    img = ob.gen("noise", 333, 127, 0)
+    for f in range(13):
+        rc, out = ob.ref_color_filter(img, f, 1.7)
+        filt.append(dict(filter=f, time=1.7, rc=rc, fnv="%08x" % ob.fnv(out.tobytes())))
+    rainbow = [[round(float(t), 3)] + list(ob.rainbow_rgb(R.color_filter_calculate_rainbow, round(float(t), 3)))
+               for t in np.linspace(0.0, 9.0, 61)]
+    # wire packaging (acip/server.c:203-214 header, crc32.c): the reference's own CRC32-C and header bytes
+    crc = []
+    for L in (0, 1, 3, 63, 64, 65, 4095, 16384, 16385, 100001, 1180548):
+        d = ob.gen("noise", max(1, (L + 2) // 3), 1, 7).tobytes()[:L]
+        crc.append(dict(len=L, crc="%08x" % R.ref_oracle_crc32(d, L), header=ob.ref_packet_header(d, 320, 96).hex()))
+    crc.append(dict(literal="123456789", crc="%08x" % R.ref_oracle_crc32(b"123456789", 9)))
+
     with open(os.path.join(HERE, "reference_vectors.json"), "w") as f:
         json.dump(dict(generated_by="tests/golden/make_golden.py",
                        reference_commit="73fe49337008f687add06622c012ac1df0ab3dcc",
                        frames=frames, rgb_to_256color_table_fnv=h256, rgb_to_16color_table_fnv=h16,
                        quirks=quirks, nn_resize=nn, glyph_tables=glyphs, text_grids=grids, pixel_composites=comps,
-                       mixed_frames=mixed), f, indent=1)
+                       mixed_frames=mixed, display_frames=display, color_filter=filt, rainbow_hue=rainbow,
+                       crc32c=crc), f, indent=1)
     print("wrote", len(frames), "frame fingerprints;", "q256", h256, "q16", h16)
 
 

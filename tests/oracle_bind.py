@@ -131,6 +131,19 @@ def port():
     L.orc_bench_convert.restype = C.c_double
     L.orc_bench_convert.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_long, C.c_int, C.c_int, C.c_char_p,
                                     C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.orc_calculate_rainbow.restype = None
+    L.orc_calculate_rainbow.argtypes = [C.c_float, u8p, u8p, u8p]
+    L.orc_apply_color_filter.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_float]
+    L.orc_rainbow_replace.restype = C.c_void_p
+    L.orc_rainbow_replace.argtypes = [C.c_char_p, C.c_float]
+    L.orc_display_convert.restype = C.c_void_p
+    L.orc_display_convert.argtypes = [u8p, C.c_int, C.c_int, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                      C.POINTER(C.c_size_t)]
+    L.orc_crc32c.restype = C.c_uint32
+    L.orc_crc32c.argtypes = [C.c_char_p, C.c_size_t]
+    L.orc_frame_packet_header.restype = None
+    L.orc_frame_packet_header.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, C.c_uint32, u8p]
     _port = L
     return L
 
@@ -190,6 +203,21 @@ def ref():
     L.ref_oracle_grid_layout.restype = None
     L.ref_oracle_grid_layout.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
                                          C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    u8p = C.POINTER(C.c_uint8)
+    L.apply_color_filter.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_float]
+    L.color_filter_calculate_rainbow.restype = None
+    L.color_filter_calculate_rainbow.argtypes = [C.c_float, u8p, u8p, u8p]
+    L.rainbow_replace_ansi_colors.restype = C.c_void_p
+    L.rainbow_replace_ansi_colors.argtypes = [C.c_char_p, C.c_float]
+    L.ref_oracle_display_convert.restype = C.c_void_p
+    L.ref_oracle_display_convert.argtypes = [u8p, C.c_int, C.c_int, C.c_long, C.c_long, cp, C.c_int, C.c_int,
+                                             C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_size_t)]
+    L.ref_oracle_frame_packet_header.restype = None
+    L.ref_oracle_frame_packet_header.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, C.c_uint32, u8p]
+    L.ref_oracle_crc32.restype = C.c_uint32
+    L.ref_oracle_crc32.argtypes = [C.c_char_p, C.c_size_t]
+    L.ref_oracle_crc32_sw.restype = C.c_uint32
+    L.ref_oracle_crc32_sw.argtypes = [C.c_char_p, C.c_size_t]
     L.ascii_simd_init()
     L.ansi_fast_init_256color()
     L.ansi_fast_init_16color()
@@ -434,3 +462,97 @@ def mixed_cases(count=60, seed=11):
 
 def mixed_sources(case):
     return [None if c is None else gen(c[0], c[1], c[2], i) for i, c in enumerate(case["clients"])]
+
+
+# ----------------------------------------------------------------------------- client display path (8f rows 1, 3)
+FILTERS = {"none": 0, "black": 1, "white": 2, "green": 3, "magenta": 4, "fuchsia": 5, "orange": 6, "teal": 7,
+           "cyan": 8, "pink": 9, "red": 10, "yellow": 11, "rainbow": 12}
+
+
+def ref_display_convert(img, cols, rows, level, mode, palette="standard", aspect=False, stretch=False, pad=False,
+                        flip_x=False, flip_y=False, color_filter=0, time_s=0.0):
+    """flip -> apply_color_filter -> ascii_convert_with_capabilities -> rainbow_replace_ansi_colors, all reference
+    code, in the order of session_display_convert_to_ascii (display.c:484-671); see oracle/ref_display_shim.c"""
+    a, p = as_u8(img)
+    caps = make_caps(level, mode, pad)
+    n = C.c_size_t(0)
+    return _take(ref().ref_oracle_display_convert(p, a.shape[1], a.shape[0], cols, rows, C.byref(caps), int(aspect),
+                                                  int(stretch), pal_bytes(palette), int(flip_x), int(flip_y),
+                                                  int(color_filter), float(time_s), C.byref(n)))
+
+
+def port_display_convert(img, cols, rows, level, mode, palette="standard", aspect=False, stretch=False, pad=False,
+                         flip_x=False, flip_y=False, color_filter=0, time_s=0.0, scale=SCALE_NN):
+    a, p = as_u8(img)
+    n = C.c_size_t(0)
+    return _take(port().orc_display_convert(p, a.shape[1], a.shape[0], cols, rows, level, mode, int(pad), int(aspect),
+                                            int(stretch), pal_bytes(palette), int(flip_x), int(flip_y),
+                                            int(color_filter), float(time_s), scale, C.byref(n)))
+
+
+def ref_color_filter(img, color_filter, time_s=0.0):
+    a = np.array(img, dtype=np.uint8, copy=True, order="C")
+    rc = ref().apply_color_filter(a.ctypes.data_as(C.POINTER(C.c_uint8)), a.shape[1], a.shape[0], a.shape[1] * 3,
+                                  int(color_filter), float(time_s))
+    return rc, a
+
+
+def port_color_filter(img, color_filter, time_s=0.0):
+    a = np.array(img, dtype=np.uint8, copy=True, order="C")
+    rc = port().orc_apply_color_filter(a.ctypes.data_as(C.POINTER(C.c_uint8)), a.shape[1], a.shape[0],
+                                       a.shape[1] * 3, int(color_filter), float(time_s))
+    return rc, a
+
+
+def rainbow_rgb(lib_fn, t):
+    r, g, b = C.c_uint8(0), C.c_uint8(0), C.c_uint8(0)
+    lib_fn(float(t), C.byref(r), C.byref(g), C.byref(b))
+    return r.value, g.value, b.value
+
+
+def display_cases(count=48, seed=23):
+    """deterministic client-display cases: geometry x caps x flips x filter x time"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(count):
+        out.append(dict(pattern=("noise", "bars", "gradient", "grey")[int(rng.integers(0, 4))],
+                        W=int(rng.integers(24, 400)), H=int(rng.integers(16, 300)),
+                        cols=int(rng.integers(8, 120)), rows=int(rng.integers(4, 50)),
+                        level=int(rng.integers(0, 4)), mode=int(rng.integers(0, 3)),
+                        aspect=int(rng.integers(0, 2)), pad=int(rng.integers(0, 2)),
+                        flip_x=int(rng.integers(0, 2)), flip_y=int(rng.integers(0, 2)),
+                        filter=int(rng.integers(0, 13)), time=round(float(rng.random() * 20.0), 3),
+                        palette=("standard", "blocks", "cool")[int(rng.integers(0, 3))]))
+    # hand-picked: BASELINE shapes with the filters that matter, rainbow on both truecolor grammars, 1-px-wide source
+    out.append(dict(pattern="noise", W=3840, H=2160, cols=320, rows=96, level=3, mode=2, aspect=0, pad=0, flip_x=1,
+                    flip_y=0, filter=3, time=1.25, palette="standard"))
+    out.append(dict(pattern="noise", W=3840, H=2160, cols=320, rows=96, level=3, mode=2, aspect=1, pad=1, flip_x=0,
+                    flip_y=1, filter=12, time=2.5, palette="standard"))
+    out.append(dict(pattern="noise", W=1920, H=1080, cols=160, rows=48, level=3, mode=0, aspect=0, pad=0, flip_x=1,
+                    flip_y=1, filter=12, time=0.4, palette="standard"))
+    out.append(dict(pattern="bars", W=1920, H=1080, cols=160, rows=48, level=2, mode=0, aspect=0, pad=0, flip_x=0,
+                    flip_y=0, filter=1, time=0.0, palette="blocks"))
+    out.append(dict(pattern="noise", W=1, H=9, cols=4, rows=3, level=3, mode=0, aspect=0, pad=0, flip_x=1,
+                    flip_y=1, filter=5, time=0.0, palette="standard"))
+    out.append(dict(pattern="gradient", W=640, H=480, cols=80, rows=24, level=0, mode=0, aspect=0, pad=0, flip_x=1,
+                    flip_y=0, filter=12, time=3.3, palette="standard"))
+    return out
+
+
+def display_args(case):
+    return dict(cols=case["cols"], rows=case["rows"], level=case["level"], mode=case["mode"], palette=case["palette"],
+                aspect=bool(case["aspect"]), stretch=False, pad=bool(case["pad"]), flip_x=bool(case["flip_x"]),
+                flip_y=bool(case["flip_y"]), color_filter=case["filter"], time_s=case["time"])
+
+
+# ----------------------------------------------------------------------------- wire packaging (8f row 4)
+def ref_packet_header(frame, width, height):
+    out = (C.c_uint8 * 24)()
+    ref().ref_oracle_frame_packet_header(frame, len(frame), width, height, out)
+    return bytes(out)
+
+
+def port_packet_header(frame, width, height):
+    out = (C.c_uint8 * 24)()
+    port().orc_frame_packet_header(frame, len(frame), width, height, out)
+    return bytes(out)

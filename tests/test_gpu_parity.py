@@ -368,3 +368,182 @@ def test_mixed_frame_concurrent_render_and_update(acb, ob):
     for i in range(4):
         acb.source_clear(i)
     assert not errs
+
+
+# ---------------------------------------------------------------- client display path (display.c:484-671)
+def _want_display(ob):
+    return ob.ref_display_convert if ob.ref() is not None else ob.port_display_convert
+
+
+def _display(acb, img, cols, rows, level, mode, palette="standard", aspect=False, stretch=False, pad=False,
+             flip_x=False, flip_y=False, color_filter=0, time_s=0.0):
+    return acb.display_convert(img, cols, rows, acb.make_caps(level, mode, pad), aspect, stretch, palette, flip_x,
+                               flip_y, color_filter, time_s)
+
+
+def test_display_convert_golden(acb, ob, golden):
+    """flip + colour filter + convert + rainbow replace in one pass against fingerprints of the reference's own
+    functions run in display.c's order, incl. the 4K / 1080p BASELINE shapes"""
+    want = _want_display(ob)
+    for rec, case in zip(golden["display_frames"], ob.display_cases()):
+        img = ob.gen(case["pattern"], case["W"], case["H"], 0)
+        s = _display(acb, img, **ob.display_args(case))
+        got = (None, None) if s is None else (len(s), "%08x" % ob.fnv(s))
+        assert got == (rec["bytes"], rec["fnv"]), case
+        if case["W"] * case["H"] <= 400 * 300:
+            assert s == want(img, **ob.display_args(case)), case
+
+
+def test_display_convert_matrix(acb, ob):
+    want = _want_display(ob)
+    n = 0
+    for pat, (W, H, c, r) in itertools.product(("noise", "bars", "grey"), ((64, 48, 16, 8), (101, 37, 33, 11), (2, 2, 5, 3))):
+        img = ob.gen(pat, W, H, 5)
+        for level, mode in itertools.product(LEVELS, MODES):
+            for filt, (fx, fy) in itertools.product((0, 1, 3, 9, 11, 12, 13), ((0, 0), (1, 0), (0, 1), (1, 1))):
+                kw = dict(cols=c, rows=r, level=level, mode=mode, palette="standard" if n % 2 else "blocks",
+                          aspect=bool(n % 3 == 0), pad=bool(n % 3 == 0), flip_x=bool(fx), flip_y=bool(fy),
+                          color_filter=filt, time_s=0.31 * (n % 17))
+                assert _display(acb, img, **kw) == want(img, **kw), kw
+                n += 1
+    assert n > 3000
+    # rainbow colour and the hue function itself (host float, like the reference)
+    for t, r, g, b in ((0.0, 255, 0, 0), (1.75, None, None, None)):
+        if r is not None:
+            assert acb.calculate_rainbow(t) == (r, g, b)
+        assert acb.calculate_rainbow(t) == ob.rainbow_rgb(ob.port().orc_calculate_rainbow, t)
+
+
+def test_display_ops_in_box_mode(acb, ob):
+    """our box-filter spec over the flipped, filtered image (generic kernel when a filter is set, the streaming
+    kernels with mirrored bands / column ranges otherwise), against the port"""
+    for (W, H, c, r) in ((640, 480, 80, 24), (333, 127, 47, 13), (1920, 1080, 160, 48)):
+        img = ob.gen("noise", W, H, 2)
+        for level, mode in ((3, 2), (2, 0), (3, 0), (0, 0)):
+            for filt, fx, fy in ((0, 1, 0), (0, 0, 1), (0, 1, 1), (3, 0, 0), (1, 1, 1), (12, 1, 0)):
+                cfg = acb.make_cfg(W, H, c, r * 2 if mode == 2 else r, level, mode, scale=acb.SCALE_BOX, flip_x=fx,
+                                   flip_y=fy, color_filter=filt, filter_time=2.2)
+                got = acb.render_batch_host(cfg, [img])[0]
+                exp = ob.port_display_convert(img, c, r, level, mode, flip_x=fx, flip_y=fy, color_filter=filt,
+                                              time_s=2.2, scale=ob.SCALE_BOX)
+                assert got == exp, (W, H, level, mode, filt, fx, fy)
+                res = _device_batch(acb, [img, img], cfg)
+                assert res[0] == exp and res[1] == exp
+
+
+def test_color_filter_whole_image(acb, ob, golden):
+    """apply_color_filter (color_filter.c:274-346) as a device map: golden fingerprints, every filter, sizes whose
+    byte count is not a multiple of 48, strided rows, error returns"""
+    want = ob.ref_color_filter if ob.ref() is not None else ob.port_color_filter
+    img = ob.gen("noise", 333, 127, 0)
+    for rec in golden["color_filter"]:
+        rc, out = acb.apply_color_filter(img, rec["filter"], rec["time"])
+        assert (rc, "%08x" % ob.fnv(out.tobytes())) == (rec["rc"], rec["fnv"]), rec
+    for it, (W, H) in enumerate(((1, 1), (5, 3), (16, 1), (17, 2), (640, 480), (1920, 1080))):
+        src = ob.gen("noise" if it % 2 else "gradient", W, H, it)
+        for f in (-1, 0, 1, 2, 7, 12, 13):
+            a, b = acb.apply_color_filter(src, f, 0.9 * it), want(src, f, 0.9 * it)
+            assert a[0] == b[0] and (a[1] == b[1]).all(), (W, H, f)
+    # strided rows: only the pixel bytes of each row change
+    wide = ob.gen("noise", 40, 9, 1)
+    view = np.ascontiguousarray(wide[:, :31, :])
+    buf = wide.copy()
+    assert acb.lib().apply_color_filter(buf.ctypes.data, 31, 9, 40 * 3, 5, 0.0) == 0
+    assert (buf[:, :31, :] == want(view, 5, 0.0)[1]).all() and (buf[:, 31:, :] == wide[:, 31:, :]).all()
+    assert acb.lib().apply_color_filter(None, 4, 4, 12, 3, 0.0) == -1
+    assert acb.lib().apply_color_filter(buf.ctypes.data, 0, 4, 12, 3, 0.0) == -1
+    # device-resident image
+    import torch
+    big = ob.gen("noise", 3840, 2160, 4)
+    d = torch.from_numpy(big).cuda()
+    torch.cuda.synchronize()
+    assert acb.color_filter_device(d.data_ptr(), 3840, 2160, 3840 * 3, 3) == 0
+    acb.synchronize()
+    assert (d.cpu().numpy() == ob.port_color_filter(big, 3)[1]).all()
+
+
+# ---------------------------------------------------------------- wire packaging (acip/server.c:188-236, crc32.c)
+def test_frame_packets_device(acb, ob):
+    """CRC32-C + ascii_frame_packet_t headers of a resident batch against the oracle's header for the same strings"""
+    import torch
+    want = ob.ref_packet_header if ob.ref() is not None else ob.port_packet_header
+    for (W, H, c, r, level, mode, n) in ((320, 240, 80, 24, 3, 2, 6), (640, 480, 80, 24, 0, 0, 3),
+                                         (1920, 1080, 160, 48, 2, 0, 5), (3840, 2160, 320, 96, 3, 2, 3)):
+        frames = [ob.gen(("noise", "bars", "gradient")[i % 3], W, H, i) for i in range(n)]
+        cfg = acb.make_cfg(W, H, c, r * 2 if mode == 2 else r, level, mode)
+        cap = acb.frame_capacity(cfg)
+        d_in = torch.from_numpy(np.stack(frames)).cuda()
+        d_out = torch.zeros(n * cap, dtype=torch.uint8, device="cuda")
+        d_len = torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_scr = torch.empty(acb.scratch_bytes(cfg, n), dtype=torch.uint8, device="cuda")
+        d_hdr = torch.zeros(n * 24, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        acb.render_batch_device(cfg, d_in.data_ptr(), n, d_out.data_ptr(), cap, d_len.data_ptr(), d_scr.data_ptr(), None)
+        acb.frame_packets_device(d_out.data_ptr(), cap, d_len.data_ptr(), n, c, r, d_hdr.data_ptr(), None)
+        acb.synchronize()
+        lens, out, hdr = d_len.cpu().numpy(), d_out.cpu().numpy().reshape(n, cap), d_hdr.cpu().numpy().reshape(n, 24)
+        for i in range(n):
+            assert hdr[i].tobytes() == want(out[i, :lens[i]].tobytes(), c, r), (W, H, level, mode, i)
+
+
+def test_crc32c_lengths_and_fixup_device(acb, ob, golden):
+    """arbitrary byte strings in a device arena: chunk-boundary lengths (16 KB chunks, 64-byte segments), empty
+    frames, the golden CRCs; and the trailing-reset cut of stream.c:1085-1127 on synthetic strings"""
+    import torch
+    lens = [0, 1, 3, 63, 64, 65, 127, 128, 4095, 16383, 16384, 16385, 32768, 100001, 1180548]
+    pitch = (max(lens) + 1 + 15) & ~15
+    arena = np.zeros((len(lens), pitch), np.uint8)
+    data = []
+    for i, L in enumerate(lens):
+        d = ob.gen("noise", max(1, (L + 2) // 3), 1, 7).tobytes()[:L]
+        arena[i, :L] = np.frombuffer(d, np.uint8)
+        data.append(d)
+    d_out = torch.from_numpy(arena).cuda()
+    d_len = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    d_hdr = torch.zeros(len(lens) * 24, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    acb.frame_packets_device(d_out.data_ptr(), pitch, d_len.data_ptr(), len(lens), 320, 96, d_hdr.data_ptr(), None)
+    acb.synchronize()
+    hdr = d_hdr.cpu().numpy().reshape(len(lens), 24)
+    by_len = {rec["len"]: rec for rec in golden["crc32c"] if "len" in rec}
+    for i, L in enumerate(lens):
+        assert hdr[i].tobytes() == ob.port_packet_header(data[i], 320, 96), L
+        if L in by_len:
+            assert hdr[i].tobytes().hex() == by_len[L]["header"], L
+
+    rst = b"\x1b[0m"
+    cases = [b"", b"abc", rst, b"row" + rst, b"ab" + rst + b"cd", rst + b"x" * 1000, b"y" * 700 + rst + b"z" * 3,
+             b"plain text without any reset" * 40, (b"q" + rst) * 300 + b"tail", b"\x1b[0", b"a" + rst + rst + b"\x1b[0"]
+    pitch = 4096
+    arena = np.zeros((len(cases), pitch), np.uint8)
+    for i, s in enumerate(cases):
+        arena[i, :len(s)] = np.frombuffer(s, np.uint8)
+    d_out = torch.from_numpy(arena).cuda()
+    d_len = torch.tensor([len(s) for s in cases], dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    acb.trailing_reset_fixup_device(d_out.data_ptr(), pitch, d_len.data_ptr(), len(cases), None)
+    acb.synchronize()
+    got_len, got = d_len.cpu().numpy(), d_out.cpu().numpy()
+    for i, s in enumerate(cases):
+        exp = ob.mixed_frame_fixup(s)
+        assert got[i, :got_len[i]].tobytes() == exp, s[:40]
+
+
+def test_mixed_frame_packet(acb, ob, golden):
+    """create_mixed_ascii_frame_for_client + acip_send_ascii_frame's header in one call: header||frame equals the
+    oracle's header for the reference's frame, for every golden server case"""
+    for rec, case in zip(golden["mixed_frames"], ob.mixed_cases()):
+        srcs = ob.mixed_sources(case)
+        slots = _load_slots(acb, srcs)
+        caps = acb.make_caps(case["level"], case["mode"], bool(case["pad"]))
+        pkt, sz, cnt = acb.mixed_frame_packet(slots, case["W"], case["H"], caps, case["palette"])
+        frame, fsz, fcnt = acb.mixed_frame(slots, case["W"], case["H"], caps, case["palette"])
+        assert cnt == fcnt == rec["sources"]
+        if frame is None:
+            assert pkt is None and sz == 0
+            continue
+        assert "%08x" % ob.fnv(frame) == rec["fnv"]
+        assert sz == 24 + fsz and pkt[24:] == frame, case
+        assert pkt[:24] == ob.port_packet_header(frame, case["W"], case["H"]), case
+    for i in range(acb.MAX_SOURCES):
+        acb.source_clear(i)

@@ -312,3 +312,90 @@ def test_mixed_frame_reset_fixup(ob):
     assert ob.mixed_frame_fixup(b"ab\x1b[0m") == b"ab\x1b[0m"
     assert ob.mixed_frame_fixup(b"plain text") == b"plain text"
     assert ob.mixed_frame_fixup(b"x") == b"x"
+
+
+# ----------------------------------------------------------------- client display path (display.c:484-671)
+def test_port_display_matches_golden(ob, golden):
+    """flip -> colour filter -> convert -> rainbow replace: the port against fingerprints of the reference's own
+    functions driven in display.c's order (oracle/ref_display_shim.c)"""
+    recs, cases = golden["display_frames"], ob.display_cases()
+    assert len(recs) == len(cases)
+    for rec, case in zip(recs, cases):
+        assert all(rec[k] == case[k] for k in case)
+        img = ob.gen(case["pattern"], case["W"], case["H"], 0)
+        s = ob.port_display_convert(img, **ob.display_args(case))
+        got = (None, None) if s is None else (len(s), "%08x" % ob.fnv(s))
+        assert got == (rec["bytes"], rec["fnv"]), case
+
+
+def test_port_vs_ref_display(ob, ref_lib):
+    rng = np.random.default_rng(17)
+    for it in range(60):
+        W, H = int(rng.integers(2, 200)), int(rng.integers(2, 150))
+        img = ob.gen(("noise", "bars", "gradient", "grey", "solid")[it % 5], W, H, it)
+        kw = dict(cols=int(rng.integers(1, 90)), rows=int(rng.integers(1, 40)), level=int(rng.integers(0, 4)),
+                  mode=int(rng.integers(0, 3)), palette=("standard", "blocks")[it % 2], aspect=bool(rng.integers(0, 2)),
+                  pad=bool(rng.integers(0, 2)), flip_x=bool(rng.integers(0, 2)), flip_y=bool(rng.integers(0, 2)),
+                  color_filter=int(rng.integers(0, 13)), time_s=float(rng.random() * 10))
+        assert ob.ref_display_convert(img, **kw) == ob.port_display_convert(img, **kw), kw
+
+
+def test_port_color_filter_and_rainbow(ob, golden):
+    img = ob.gen("noise", 333, 127, 0)
+    for rec in golden["color_filter"]:
+        rc, out = ob.port_color_filter(img, rec["filter"], rec["time"])
+        assert (rc, "%08x" % ob.fnv(out.tobytes())) == (rec["rc"], rec["fnv"]), rec
+    for t, r, g, b in golden["rainbow_hue"]:
+        assert ob.rainbow_rgb(ob.port().orc_calculate_rainbow, t) == (r, g, b), t
+    # invalid arguments, color_filter.c:276-329
+    assert ob.port().orc_apply_color_filter(None, 4, 4, 12, 3, 0.0) == -1
+    assert ob.port_color_filter(img, 13)[0] == -1 and ob.port_color_filter(img, -1)[0] == -1
+    assert ob.port_color_filter(img, 0)[0] == 0
+
+
+def test_port_vs_ref_color_filter(ob, ref_lib):
+    for it, (W, H) in enumerate(((1, 1), (5, 3), (16, 16), (333, 127), (640, 480))):
+        img = ob.gen("noise" if it % 2 else "gradient", W, H, it)
+        for f in range(-1, 14):
+            a, b = ob.ref_color_filter(img, f, 0.37 * it), ob.port_color_filter(img, f, 0.37 * it)
+            assert a[0] == b[0] and (a[1] == b[1]).all(), (W, H, f)
+    for t in np.linspace(0, 40, 4001):
+        assert ob.rainbow_rgb(ref_lib.color_filter_calculate_rainbow, t) == \
+            ob.rainbow_rgb(ob.port().orc_calculate_rainbow, t), t
+
+
+def test_rainbow_replace(ob, ref_lib):
+    def both(s, t=1.0):
+        a = ob._take(ref_lib.rainbow_replace_ansi_colors(s, t))
+        b = ob._take(ob.port().orc_rainbow_replace(s, t))
+        assert a == b, s
+        return b
+    assert both(b"no colour here") is None
+    assert both(b"\x1b[48;2;1;2;3mX") is None                      # background SGRs are not touched
+    r, g, b = ob.rainbow_rgb(ob.port().orc_calculate_rainbow, 1.0)
+    code = b"\x1b[38;2;%d;%d;%dm" % (r, g, b)
+    assert both(b"a\x1b[38;2;1;2;3mb\x1b[0m") == b"a" + code + b"b\x1b[0m"
+    assert both(b"\x1b[38;2;9;9;9m\x1b[48;2;1;1;1m\xe2\x96\x80") == code + b"\x1b[48;2;1;1;1m\xe2\x96\x80"
+    both(b"\x1b[38;2;1;2;3")                                        # unterminated: copied byte by byte
+    both(b"\x1b[38;2;\x1b[38;2;4;5;6mz")                            # a start inside a replaced span is swallowed
+
+
+# ----------------------------------------------------------------- wire packaging (acip/server.c:203-214, crc32.c)
+def test_port_crc32c_and_packet_header(ob, golden):
+    for rec in golden["crc32c"]:
+        if "literal" in rec:
+            d = rec["literal"].encode()
+            assert "%08x" % ob.port().orc_crc32c(d, len(d)) == rec["crc"] == "e3069283"  # the CRC-32C check value
+            continue
+        L = rec["len"]
+        d = ob.gen("noise", max(1, (L + 2) // 3), 1, 7).tobytes()[:L]
+        assert "%08x" % ob.port().orc_crc32c(d, L) == rec["crc"], L
+        assert ob.port_packet_header(d, 320, 96).hex() == rec["header"], L
+
+
+def test_port_vs_ref_crc32c(ob, ref_lib):
+    rng = np.random.default_rng(9)
+    for L in [0, 1, 2, 7, 8, 9] + [int(v) for v in rng.integers(10, 200000, 40)]:
+        d = rng.integers(0, 256, L, dtype=np.uint8).tobytes()
+        assert ref_lib.ref_oracle_crc32(d, L) == ref_lib.ref_oracle_crc32_sw(d, L) == ob.port().orc_crc32c(d, L), L
+        assert ob.ref_packet_header(d, 203, 61) == ob.port_packet_header(d, 203, 61)
