@@ -466,13 +466,15 @@ int acb200_frame_packets_device(const uint8_t *d_out, size_t out_pitch, const ui
   if (!cx) return acb200_last_error();
   cudaStream_t st = stream ? (cudaStream_t)stream : cx->stream;
   const int mc = max_crc_chunks(out_pitch);
-  // chunk CRCs live in this thread's context; a foreign stream must not race the next call on the same thread
-  if (!grow_device((uint8_t **)&cx->d_len, &cx->d_len_cap, (size_t)n_frames * mc * sizeof(uint32_t)))
+  // the chunk CRCs live in this thread's context: work queued on a different stream by the previous call must have
+  // drained before they are overwritten (same stream = ordered anyway; cudaFree inside grow_device synchronises)
+  static thread_local cudaStream_t last_stream = nullptr;
+  if (last_stream && last_stream != st) ACB_CUDA(cudaStreamSynchronize(last_stream));
+  last_stream = st;
+  if (!grow_device((uint8_t **)&cx->d_len, &cx->d_len_cap, (size_t)(16 + (size_t)n_frames * mc) * sizeof(uint32_t)))
     return acb200_last_error();
-  int rc = launch_frame_packets(d_out, out_pitch, d_out_len, n_frames, mc, width, height, cx->d_len, d_headers,
-                                ACB200_FRAME_HEADER_BYTES, nullptr, 0, st);
-  if (rc == E_OK && stream) ACB_CUDA(cudaStreamSynchronize(st)); // see above: d_len is reused by the next call
-  return rc;
+  return launch_frame_packets(d_out, out_pitch, d_out_len, n_frames, mc, width, height, cx->d_len + 16, d_headers,
+                              ACB200_FRAME_HEADER_BYTES, nullptr, 0, st);
 }
 
 } // extern "C"

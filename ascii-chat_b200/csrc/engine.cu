@@ -652,9 +652,10 @@ char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, si
       !grow_pinned(&cx->h_out, &cx->h_out_cap, pl.frame_capacity + 32) ||
       !grow_pinned((uint8_t **)&cx->h_len, &cx->h_len_cap, 256))
     return nullptr;
-  if (opts.packet && (!grow_device(&cx->d_frame, &cx->d_frame_cap, pl.frame_capacity) ||
-                      !grow_device((uint8_t **)&cx->d_len, &cx->d_len_cap, (size_t)(16 + mc) * sizeof(uint32_t))))
+  // packet path: device arena, followed by the frame-length word (16 words reserved) and the CRC chunk words
+  if (opts.packet && !grow_device(&cx->d_frame, &cx->d_frame_cap, pl.frame_capacity + (size_t)(16 + mc) * sizeof(uint32_t)))
     return nullptr;
+  uint32_t *d_words = reinterpret_cast<uint32_t *>(cx->d_frame + pl.frame_capacity); // frame_capacity is a multiple of 16
   if (cx->d_scratch != scratch_before) cx->scratch_dirty = true;
   const bool will_be_direct = pl.mode != EM_DITHER_BG && pl.use_smem_out && pl.scale_path != SP_BOX_TMA;
   if (cx->scratch_dirty || !will_be_direct) {
@@ -665,12 +666,12 @@ char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, si
   // plain: the kernels write the string straight into mapped pinned host memory.  packet: the string stays in HBM for
   // the fix-up and the CRC scan, which streams it to the host buffer (at +32: 8 spare, 24 header, frame 16-aligned).
   uint8_t *arena = opts.packet ? cx->d_frame : cx->h_out;
-  uint32_t *lens = opts.packet ? cx->d_len : cx->h_len;
+  uint32_t *lens = opts.packet ? d_words : cx->h_len;
   if (render_device(cfg, pl, d_rgb, (size_t)cfg.src_w * cfg.src_h * 3, 0, 1, arena, pl.frame_capacity, lens,
                     cx->d_scratch, cx->stream, nullptr, nullptr, &cx->lb) != E_OK)
     return nullptr;
   if (opts.reset_fixup && launch_reset_fixup(arena, pl.frame_capacity, lens, 1, cx->stream) != E_OK) return nullptr;
-  if (opts.packet && launch_frame_packets(arena, pl.frame_capacity, lens, 1, mc, opts.pk_w, opts.pk_h, cx->d_len + 16,
+  if (opts.packet && launch_frame_packets(arena, pl.frame_capacity, lens, 1, mc, opts.pk_w, opts.pk_h, d_words + 16,
                                           cx->h_out + 8, 24, cx->h_out + 32, 0, cx->stream) != E_OK)
     return nullptr;
   if (cudaStreamSynchronize(cx->stream) != cudaSuccess) {

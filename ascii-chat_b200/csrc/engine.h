@@ -44,8 +44,8 @@ struct ThreadCtx {
   uint8_t *d_in = nullptr;   size_t d_in_cap = 0;
   uint8_t *d_out = nullptr;  size_t d_out_cap = 0;
   uint8_t *d_scratch = nullptr; size_t d_scratch_cap = 0;
-  uint32_t *d_len = nullptr; size_t d_len_cap = 0;   // [0..15] frame lengths, [16..] CRC chunk words (effects.cu)
-  uint8_t *d_frame = nullptr; size_t d_frame_cap = 0; // device arena of the one-frame packet path
+  uint32_t *d_len = nullptr; size_t d_len_cap = 0;   // CRC chunk words of acb200_frame_packets_device (effects.cu)
+  uint8_t *d_frame = nullptr; size_t d_frame_cap = 0; // one-frame packet path: device arena + length + CRC chunk words
   uint32_t *h_len = nullptr; size_t h_len_cap = 0;  // pinned
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };

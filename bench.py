@@ -224,6 +224,82 @@ def server_path_leg(acb, with_reference):
     return out
 
 
+def device_extras_leg(acb, torch, d_out, cap, d_len, n, peak):
+    """SURVEY.md §8f rows 1 and 4 on resident data, device-timed with CUDA events on torch's current stream (the
+    kernels are launched on that stream): the whole-image colour filter (apply_color_filter as an in-place map,
+    3 B read + 3 B written per pixel) and the CRC32-C + packet-header scan over the batch's finished strings."""
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+
+    def timed(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    d_hdr = torch.zeros(n * 24, dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: acb.frame_packets_device(d_out.data_ptr(), cap, d_len.data_ptr(), n, COLS, ROWS,
+                                                d_hdr.data_ptr(), st), 10)
+    sbytes = int(d_len.sum().item())
+    out["frame_packets"] = {"kernels": "k_crc32c_chunks + k_crc32c_finish", "frames": n, "string_bytes": sbytes,
+                            "ms_per_batch": ms, "GBs_of_string_bytes": sbytes / (ms * 1e-3) / 1e9,
+                            "note": "CRC32-C (lib/network/crc32.c) + 24-byte ascii_frame_packet_t per frame "
+                                    "(acip/server.c:203-214)"}
+    k = 64
+    img = torch.randint(0, 256, (k * SRC_H, SRC_W, 3), dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: acb.color_filter_device(img.data_ptr(), SRC_W, k * SRC_H, SRC_W * 3, 3, 0.0, st), 10)
+    traffic = 2 * k * FRAME_BYTES
+    out["color_filter"] = {"kernel": "k_color_filter", "frames": k, "ms_per_batch": ms, "bound": "hbm",
+                           "algorithmic_bytes": traffic, "achieved": traffic / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                           "peak": peak, "frac": traffic / (ms * 1e-3) / 1e9 / peak,
+                           "Mpix_s": k * MPIX / (ms * 1e-3),
+                           "note": "apply_color_filter (color_filter.c:274-346) in place on %d resident 4K frames: "
+                                   "3 B read + 3 B written per pixel" % k}
+    del img, d_hdr
+    return out
+
+
+def display_path_leg(acb, with_reference):
+    """SURVEY.md §8f rows 1+3: the client's display conversion (display.c:484-671) — flip X, green colour filter,
+    4K -> 320x96 truecolor half-block — as ONE call from a host frame; the reference leg runs its own functions in
+    display.c's order (copy+flip, copy+apply_color_filter, ascii_convert_with_capabilities)."""
+    import numpy as np
+    img = np.random.default_rng(4242).integers(0, 256, (SRC_H, SRC_W, 3), dtype=np.uint8)
+    caps = acb.make_caps(LEVEL, MODE)
+    args = (COLS, ROWS, caps, False, False, "standard", True, False, 3, 0.0)
+    first = acb.display_convert(img, *args)
+    if first is None:
+        return {"error": str(acb.last_error())}
+    R = 200
+    for _ in range(20):
+        acb.display_convert(img, *args)
+    t0 = time.perf_counter()
+    for _ in range(R):
+        acb.display_convert(img, *args)
+    ours = (time.perf_counter() - t0) / R
+    out = {"workload": "one 3840x2160 host frame, flip_x + green filter -> 320x96 truecolor half-block",
+           "api": "acb200_display_convert()", "ms_per_call": ours * 1e3, "frame_bytes": len(first)}
+    if with_reference:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_bind as ob
+        fn = ob.ref_display_convert if ob.ref() is not None else ob.port_display_convert
+        kw = dict(cols=COLS, rows=ROWS, level=LEVEL, mode=MODE, palette="standard", flip_x=True, color_filter=3)
+        exp = fn(img, **kw)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            fn(img, **kw)
+        out.update({"bytes_identical_to_reference": bool(exp == first),
+                    "reference_ms_per_call": (time.perf_counter() - t0) / 5 * 1e3,
+                    "reference_kind": "reference" if ob.ref() is not None else "port"})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -320,6 +396,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_total_max, ms_kernel_max = max_over_ranks([ms_total, ms_kernel])
     out_bytes = int(d_len.sum().item())
+    extras = None
+    if rank == 0 and world == 1 and not args.resident_only:
+        extras = device_extras_leg(acb, torch, d_out, cap, d_len, n, peaks()[0])
     del d_in, d_out, d_scr
     torch.cuda.empty_cache()
 
@@ -405,6 +484,9 @@ def main():
             line["e2e"]["bytes_identical_to_cpu_baseline"] = bool(fp_ref == fp_nn)
     if world == 1:
         line["server_path"] = server_path_leg(acb, not args.no_cpu_baseline)
+        line["display_path"] = display_path_leg(acb, not args.no_cpu_baseline)
+        if extras:
+            line.update(extras)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
