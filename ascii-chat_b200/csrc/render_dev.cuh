@@ -464,19 +464,44 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
     dst[1] = hi;
   }
   Sync::sync();
-  for (int x = threadIdx.x; x < p.cols; x += NT) {
-    int x0, x1;
-    box_range(x, p.src_w, p.cols, x0, x1);
-    uint32_t sr = 0, sg = 0, sb = 0;
-    const uint16_t *q = V + 3 * (p.flip_x ? p.src_w - x1 : x0);
-#pragma unroll 4
-    for (int xx = x0; xx < x1; xx++, q += 3) {
-      sr += q[0];
-      sg += q[1];
-      sb += q[2];
+  // Horizontal sums.  Uniform even box width (src_w = cols * bx, bx even — every BASELINE shape): a cell's column
+  // sums are bx/2 pixel pairs of three 32-bit words {r0|g0, b0|r1, g1|b1}, added as packed u16 lanes (3 adds per
+  // pair instead of 6 loads + 6 adds), and the three divisions by the uniform box area become multiply-highs with
+  // the exact reciprocal M = ceil(2^32 / n)  (exact for (s + h) * n < 2^32; here s + h < 256 n and n < 4096).
+  const int bx = p.src_w / p.cols;
+  if (bx * p.cols == p.src_w && (bx & 1) == 0 && (uint32_t)(bx >> 1) * (uint32_t)nrow * 255u < 65536u &&
+      (uint32_t)bx * (uint32_t)nrow < 4096u) {
+    const uint32_t n = (uint32_t)bx * (uint32_t)nrow, h = n >> 1;
+    const uint32_t M = 0xFFFFFFFFu / n + 1u;
+    const uint32_t *Vw = reinterpret_cast<const uint32_t *>(V);
+    const int half = bx >> 1;
+    for (int x = threadIdx.x; x < p.cols; x += NT) {
+      const uint32_t *q = Vw + 3 * half * (p.flip_x ? p.cols - 1 - x : x);
+      uint32_t a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 6
+      for (int k = 0; k < half; k++, q += 3) {
+        a0 += q[0];
+        a1 += q[1];
+        a2 += q[2];
+      }
+      const uint32_t sr = (a0 & 0xFFFFu) + (a1 >> 16), sg = (a0 >> 16) + (a2 & 0xFFFFu), sb = (a1 & 0xFFFFu) + (a2 >> 16);
+      out[x] = (__umulhi(sr + h, M) << 16) | (__umulhi(sg + h, M) << 8) | __umulhi(sb + h, M);
     }
-    uint32_t n = (uint32_t)(x1 - x0) * (uint32_t)nrow, h = n >> 1;
-    out[x] = (((sr + h) / n) << 16) | (((sg + h) / n) << 8) | ((sb + h) / n);
+  } else {
+    for (int x = threadIdx.x; x < p.cols; x += NT) {
+      int x0, x1;
+      box_range(x, p.src_w, p.cols, x0, x1);
+      uint32_t sr = 0, sg = 0, sb = 0;
+      const uint16_t *q = V + 3 * (p.flip_x ? p.src_w - x1 : x0);
+#pragma unroll 4
+      for (int xx = x0; xx < x1; xx++, q += 3) {
+        sr += q[0];
+        sg += q[1];
+        sb += q[2];
+      }
+      uint32_t n = (uint32_t)(x1 - x0) * (uint32_t)nrow, h = n >> 1;
+      out[x] = (((sr + h) / n) << 16) | (((sg + h) / n) << 8) | ((sb + h) / n);
+    }
   }
   Sync::sync(); // V is reused by the next pixel row
 }

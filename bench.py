@@ -181,11 +181,12 @@ def server_path_leg(acb, with_reference):
     n, sw, sh, W, H = 9, 1280, 720, 240, 67
     rng = np.random.default_rng(777)
     srcs = [rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8) for _ in range(n)]
-    t0 = time.perf_counter()
-    for i, s in enumerate(srcs):
-        if acb.source_update(i, s) != 0:
-            return {"error": str(acb.last_error())}
-    upd = (time.perf_counter() - t0) / n
+    for rnd in range(3):  # the first rounds size the slots' double buffers and the staging; time the steady state
+        t0 = time.perf_counter()
+        for i, s in enumerate(srcs):
+            if acb.source_update(i, s) != 0:
+                return {"error": str(acb.last_error())}
+        upd = (time.perf_counter() - t0) / n
     caps = acb.make_caps(LEVEL, MODE, True)
     slots = list(range(n))
     first = acb.mixed_frame(slots, W, H, caps, "standard")
@@ -228,19 +229,23 @@ def device_extras_leg(acb, torch, d_out, cap, d_len, n, peak):
     """SURVEY.md §8f rows 1 and 4 on resident data, device-timed with CUDA events on torch's current stream (the
     kernels are launched on that stream): the whole-image colour filter (apply_color_filter as an in-place map,
     3 B read + 3 B written per pixel) and the CRC32-C + packet-header scan over the batch's finished strings."""
-    st = torch.cuda.current_stream().cuda_stream
+    ts = torch.cuda.Stream()  # an explicit (non-NULL) stream: the library launches on it, the events are recorded on it
+    st = ts.cuda_stream
+    assert st, "need a non-default stream handle"
     out = {}
 
     def timed(fn, iters, warm=3):
-        for _ in range(warm):
-            fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
+        with torch.cuda.stream(ts):
+            for _ in range(warm):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ts.synchronize()
+            e0.record(ts)
+            for _ in range(iters):
+                fn()
+            e1.record(ts)
+            ts.synchronize()
         return e0.elapsed_time(e1) / iters
 
     d_hdr = torch.zeros(n * 24, dtype=torch.uint8, device="cuda")

@@ -408,10 +408,9 @@ def test_display_convert_matrix(acb, ob):
                 n += 1
     assert n > 3000
     # rainbow colour and the hue function itself (host float, like the reference)
-    for t, r, g, b in ((0.0, 255, 0, 0), (1.75, None, None, None)):
-        if r is not None:
-            assert acb.calculate_rainbow(t) == (r, g, b)
+    for t in (0.0, 0.6, 1.75, 2.9, 3.5, 1234.567):
         assert acb.calculate_rainbow(t) == ob.rainbow_rgb(ob.port().orc_calculate_rainbow, t)
+    assert acb.calculate_rainbow(0.0) == (255, 21, 21)  # pure red lifted to luminance 120 (color_filter.c:221-235)
 
 
 def test_display_ops_in_box_mode(acb, ob):
