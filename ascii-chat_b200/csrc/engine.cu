@@ -411,6 +411,14 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
   rp.lut = lut;
   rp.cells_out = nullptr;
   rp.n_frames = n_frames;
+  { // geometry of the packed horizontal sums (render_dev.cuh: cells_box_stream); bands are floor or floor+1 rows
+    const int bx = cfg.src_w / cfg.cols, n0 = cfg.src_h / cfg.rows_px;
+    const bool ok = bx * cfg.cols == cfg.src_w && (bx & 1) == 0 && n0 >= 1 &&
+                    (uint64_t)(bx >> 1) * (uint64_t)(n0 + 1) * 255u < 65536u && (uint64_t)bx * (uint64_t)(n0 + 1) < 4096u;
+    rp.box_bx = ok ? bx : 0;
+    rp.box_nrow0 = n0;
+    for (int d = 0; d < 2; d++) rp.box_M[d] = ok ? 0xFFFFFFFFu / ((uint32_t)bx * (uint32_t)(n0 + d)) + 1u : 0u;
+  }
   {
     const DisplayOps d = display_ops(cfg);
     rp.flip_x = d.flip_x;
@@ -430,7 +438,8 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
     cudaMemset(d_dbg, 0, 4 * sizeof(unsigned long long));
   }
   rp.dbg = d_dbg;
-  rp.tune_flags = (tune_noalias ? 1 : 0) | (ws2_noemit ? 2 : 0) | (ws2_dbg ? 4 : 0);
+  static const int slow_reduce = getenv("ACB200_SLOW_REDUCE") ? atoi(getenv("ACB200_SLOW_REDUCE")) : 0; // A/B knob
+  rp.tune_flags = (tune_noalias ? 1 : 0) | (ws2_noemit ? 2 : 0) | (ws2_dbg ? 4 : 0) | (slow_reduce ? 8 : 0);
   if (ws2_dbg && getenv("ACB200_WS2_DBG_PRINT")) { // print-and-reset on demand (set by the measurement script)
     unsigned long long h[4];
     cudaStreamSynchronize(st);

@@ -75,8 +75,12 @@ struct RenderParams {
   uint32_t filt_rgb;      // the filter's colour, 0x00RRGGBB
   uint32_t fg_over;       // rainbow_replace_ansi_colors (color_filter.c:348-408): 0, or 0x01RRGGBB printed in place of
                           // every truecolor-foreground SGR colour (run/dedupe decisions still use the pixel colours)
+  // streaming box filter, uniform even box width (src_w = cols * box_bx, box_bx even; 0 = use the generic sums):
+  // bands are box_nrow0 or box_nrow0 + 1 rows tall; box_M[d] = ceil(2^32 / (box_bx * (box_nrow0 + d)))
+  int box_bx, box_nrow0;
+  uint32_t box_M[2];
   unsigned long long *dbg; // measurement counters (tune_flags bit 2): streamer wait, emitter wait, emitter busy, tiles
-  int tune_flags;         // bit0: do not alias V with the row staging buffer (measurement knob)
+  int tune_flags;         // measurement knobs: bit0 no V/staging alias, bit1 no emission, bit2 counters, bit3 generic horizontal sums
 };
 
 // colour filter arithmetic variants (colorize_grayscale_pixel, color_filter.c:238-267)

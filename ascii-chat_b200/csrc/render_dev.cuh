@@ -345,8 +345,9 @@ __device__ __forceinline__ void cells_nn(const RenderParams &p, const uint8_t *f
 }
 
 __device__ __forceinline__ void box_range(int d, int src, int dst, int &a, int &b) {
-  a = (int)(((long long)d * src) / dst);
-  b = (int)(((long long)(d + 1) * src) / dst);
+  // d < dst <= 3840 and src <= 10000 (make_plan), so the products fit 32 bits: plain u32 divisions
+  a = (int)(((uint32_t)d * (uint32_t)src) / (uint32_t)dst);
+  b = (int)(((uint32_t)(d + 1) * (uint32_t)src) / (uint32_t)dst);
   if (b <= a) b = a + 1;
   if (b > src) b = src;
   if (a >= src) a = src - 1;
@@ -417,6 +418,20 @@ __device__ __forceinline__ void acc16x2(uint32_t (&a)[8], const uint4 &u, const 
   a[7] += __byte_perm(u.w, 0u, 0x4341) + __byte_perm(v.w, 0u, 0x4341);
 }
 
+// NR rows of one 16-byte column: NR independent, UNPREDICATED loads in flight, then the pairwise sums.  (A predicated
+// "row r+k exists" form costs an ISETP and four zeroing moves per load: 12% of the kernel's instructions, measured.)
+template <int NR> __device__ __forceinline__ void band_trip(uint32_t (&a)[8], const uint8_t *&q, uint32_t R) {
+  uint4 v[NR];
+#pragma unroll
+  for (int k = 0; k < NR; k++) {
+    v[k] = ldg_stream(reinterpret_cast<const uint4 *>(q));
+    q += R;
+  }
+#pragma unroll
+  for (int k = 0; k + 1 < NR; k += 2) acc16x2(a, v[k], v[k + 1]);
+  if (NR & 1) acc16x2(a, v[NR - 1], make_uint4(0u, 0u, 0u, 0u));
+}
+
 // box filter, streaming: the band of source rows [y0,y1) is one contiguous byte range; every thread owns
 // 16-byte columns of it, sums them down the band in registers (u16 lanes, band <= 256 rows), parks the
 // column sums V[3*src_w] in shared memory, then one thread per destination pixel adds its x-range.
@@ -425,29 +440,31 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
                                                  uint16_t *V) {
   int y0, y1;
   box_range(y, p.src_h, p.rows_px, y0, y1);
-  const int R = p.src_w * 3;
-  const int nchunk = R >> 4;
+  const uint32_t R = (uint32_t)p.src_w * 3u;
+  const int nchunk = (int)(R >> 4);
   const int nrow = y1 - y0;
   if (p.flip_y) y0 = p.src_h - y1; // the band of the mirrored image is the mirrored band (sums do not care about order)
-  const uint4 *band = reinterpret_cast<const uint4 *>(frame + (size_t)y0 * (size_t)R);
+  const uint8_t *band = frame + (size_t)y0 * (size_t)R;
   for (int c = threadIdx.x; c < nchunk; c += NT) {
     uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const uint8_t *q = reinterpret_cast<const uint8_t *>(band + c);
-    // One batch of kBandUnroll independent, predicated 16-byte loads per trip: a typical band (11-12 rows at
-    // 4K -> 192 pixel rows) is a single trip, i.e. one memory latency per column instead of one per tail row.
-    // The row pointer advances by the 32-bit row pitch (one wide multiply-add per load, no 64-bit index maths).
-    for (int r = 0; r < nrow; r += kBandUnroll) {
-      uint4 v[kBandUnroll];
-#pragma unroll
-      for (int k = 0; k < kBandUnroll; k++) {
-        if (r + k < nrow)
-          v[k] = ldg_stream(reinterpret_cast<const uint4 *>(q));
-        else
-          v[k] = make_uint4(0u, 0u, 0u, 0u);
-        q += (uint32_t)R;
-      }
-#pragma unroll
-      for (int k = 0; k < kBandUnroll; k += 2) acc16x2(a, v[k], v[k + 1]);
+    const uint8_t *q = band + ((size_t)c << 4);
+    // whole batches of kBandUnroll rows, then one batch of exactly the rows that are left (a typical band — 11 or 12
+    // rows at 4K -> 192 pixel rows — is a single batch: one memory latency per column)
+    int r = nrow;
+    for (; r >= kBandUnroll; r -= kBandUnroll) band_trip<kBandUnroll>(a, q, R);
+    switch (r) {
+    case 11: band_trip<11>(a, q, R); break;
+    case 10: band_trip<10>(a, q, R); break;
+    case 9: band_trip<9>(a, q, R); break;
+    case 8: band_trip<8>(a, q, R); break;
+    case 7: band_trip<7>(a, q, R); break;
+    case 6: band_trip<6>(a, q, R); break;
+    case 5: band_trip<5>(a, q, R); break;
+    case 4: band_trip<4>(a, q, R); break;
+    case 3: band_trip<3>(a, q, R); break;
+    case 2: band_trip<2>(a, q, R); break;
+    case 1: band_trip<1>(a, q, R); break;
+    default: break;
     }
     // byte j of word k is column 16c + 4k + j:  even reg = {b0 | b2<<16}, odd reg = {b1 | b3<<16}
     uint4 lo, hi;
@@ -468,11 +485,12 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
   // sums are bx/2 pixel pairs of three 32-bit words {r0|g0, b0|r1, g1|b1}, added as packed u16 lanes (3 adds per
   // pair instead of 6 loads + 6 adds), and the three divisions by the uniform box area become multiply-highs with
   // the exact reciprocal M = ceil(2^32 / n)  (exact for (s + h) * n < 2^32; here s + h < 256 n and n < 4096).
-  const int bx = p.src_w / p.cols;
-  if (bx * p.cols == p.src_w && (bx & 1) == 0 && (uint32_t)(bx >> 1) * (uint32_t)nrow * 255u < 65536u &&
-      (uint32_t)bx * (uint32_t)nrow < 4096u) {
+  // (box_bx / box_nrow0 / box_M[] come from the host: no per-thread divisions here.)
+  const int bx = p.box_bx;
+  const uint32_t dn = (uint32_t)(nrow - p.box_nrow0);
+  if (bx > 0 && dn < 2u && !(p.tune_flags & 8)) {
     const uint32_t n = (uint32_t)bx * (uint32_t)nrow, h = n >> 1;
-    const uint32_t M = 0xFFFFFFFFu / n + 1u;
+    const uint32_t M = p.box_M[dn];
     const uint32_t *Vw = reinterpret_cast<const uint32_t *>(V);
     const int half = bx >> 1;
     for (int x = threadIdx.x; x < p.cols; x += NT) {
@@ -929,8 +947,8 @@ __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) :
     cells_box_generic<NT>(p, frame, yT, cT);
     if (hasB) cells_box_generic<NT>(p, frame, yT + 1, cB);
   } else {
-    cells_box_stream<NT>(p, frame, yT, cT, V);
-    if (hasB) cells_box_stream<NT>(p, frame, yT + 1, cB, V);
+#pragma unroll 1
+    for (int hrow = 0; hrow < (hasB ? 2 : 1); hrow++) cells_box_stream<NT>(p, frame, yT + hrow, hrow ? cB : cT, V);
   }
   __syncthreads();
   if (HB && !hasB) { // odd pixel height: bottom := top (halfblock.c:73,82-88)
@@ -1238,7 +1256,8 @@ template <int N> __device__ __forceinline__ void nbar_arrive_id(int id) {
   }
 }
 
-template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows_ws2(const RenderParams p) {
+// four CTAs per SM (56 registers): the occupancy every measurement in DESIGN.md §7 was taken at
+template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32, 4) k_render_rows_ws2(const RenderParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_tmp[2];
   __shared__ uint32_t s_cond[2][4];
@@ -1297,8 +1316,9 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32) k_render_rows
       const uint8_t *frame = p.frames + (size_t)f * p.frame_stride;
       const int yT = HB ? 2 * t : t;
       const bool hasB = HB && (2 * t + 1 < p.rows_px);
-      cells_box_stream<WS2_ST, SyncConsumers<WS2_ST>>(p, frame, yT, cT, V);
-      if (hasB) cells_box_stream<WS2_ST, SyncConsumers<WS2_ST>>(p, frame, yT + 1, cB, V);
+#pragma unroll 1
+      for (int hrow = 0; hrow < (hasB ? 2 : 1); hrow++) // one inlined copy of the band code for both pixel rows
+        cells_box_stream<WS2_ST, SyncConsumers<WS2_ST>>(p, frame, yT + hrow, hrow ? cB : cT, V);
       if (HB && !hasB)
         for (int x = tid; x < w; x += WS2_ST) cB[x] = cT[x];
       __threadfence_block();
