@@ -40,31 +40,54 @@ __device__ __forceinline__ uint32_t gray_of_bytes(uint32_t rgbx) { // bytes r,g,
 
 constexpr int CF_NT = 256;
 
+// touched exactly once: keep it out of L1 on the way in, mark it evict-first on the way out
+__device__ __forceinline__ uint4 ld_once(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_once(uint4 *p, const uint4 &v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __global__ void __launch_bounds__(CF_NT) k_color_filter(uint8_t *pixels, size_t n_bytes, int mode, uint32_t frgb) {
   __shared__ uint32_t T[256];
   for (int i = threadIdx.x; i < 256; i += CF_NT) T[i] = filt_entry((uint32_t)i, mode, frgb);
   __syncthreads();
   const size_t ngroups = n_bytes / 48; // 16 pixels per group
   uint4 *base = reinterpret_cast<uint4 *>(pixels);
-  for (size_t gidx = (size_t)blockIdx.x * CF_NT + threadIdx.x; gidx < ngroups; gidx += (size_t)gridDim.x * CF_NT) {
-    uint4 *q = base + gidx * 3;
-    const uint4 a = q[0], b = q[1], c = q[2];
-    const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-    uint32_t o[12];
+  const size_t stride = (size_t)gridDim.x * CF_NT;
+  // two groups per trip: six 16-byte loads in flight per thread before the first table lookup
+  for (size_t gidx = (size_t)blockIdx.x * CF_NT + threadIdx.x; gidx < ngroups; gidx += 2 * stride) {
+    const bool two = gidx + stride < ngroups;
+    uint4 *q0 = base + gidx * 3, *q1 = base + (two ? gidx + stride : gidx) * 3;
+    uint4 in[6];
 #pragma unroll
-    for (int k = 0; k < 4; k++) { // 4 pixels live in 3 consecutive words
-      const uint32_t w0 = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
-      const uint32_t p0 = T[gray_of_bytes(w0)];                           // bytes 0..2
-      const uint32_t p1 = T[gray_of_bytes(__byte_perm(w0, w1, 0x6543))];  // bytes 3..5
-      const uint32_t p2 = T[gray_of_bytes(__byte_perm(w1, w2, 0x5432))];  // bytes 6..8
-      const uint32_t p3 = T[gray_of_bytes(w2 >> 8)];                      // bytes 9..11
-      o[3 * k] = p0 | (p1 << 24);
-      o[3 * k + 1] = (p1 >> 8) | (p2 << 16);
-      o[3 * k + 2] = (p2 >> 16) | (p3 << 8);
+    for (int k = 0; k < 3; k++) in[k] = ld_once(q0 + k);
+#pragma unroll
+    for (int k = 0; k < 3; k++) in[3 + k] = two ? ld_once(q1 + k) : in[k];
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+      if (g == 1 && !two) break;
+      const uint4 a = in[3 * g], b = in[3 * g + 1], c = in[3 * g + 2];
+      const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+      uint32_t o[12];
+#pragma unroll
+      for (int k = 0; k < 4; k++) { // 4 pixels live in 3 consecutive words
+        const uint32_t w0 = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
+        const uint32_t p0 = T[gray_of_bytes(w0)];                           // bytes 0..2
+        const uint32_t p1 = T[gray_of_bytes(__byte_perm(w0, w1, 0x6543))];  // bytes 3..5
+        const uint32_t p2 = T[gray_of_bytes(__byte_perm(w1, w2, 0x5432))];  // bytes 6..8
+        const uint32_t p3 = T[gray_of_bytes(w2 >> 8)];                      // bytes 9..11
+        o[3 * k] = p0 | (p1 << 24);
+        o[3 * k + 1] = (p1 >> 8) | (p2 << 16);
+        o[3 * k + 2] = (p2 >> 16) | (p3 << 8);
+      }
+      uint4 *q = g ? q1 : q0;
+      st_once(q, make_uint4(o[0], o[1], o[2], o[3]));
+      st_once(q + 1, make_uint4(o[4], o[5], o[6], o[7]));
+      st_once(q + 2, make_uint4(o[8], o[9], o[10], o[11]));
     }
-    q[0] = make_uint4(o[0], o[1], o[2], o[3]);
-    q[1] = make_uint4(o[4], o[5], o[6], o[7]);
-    q[2] = make_uint4(o[8], o[9], o[10], o[11]);
   }
   // tail (< 16 pixels) and nothing else: byte-wise by the first threads of block 0
   if (blockIdx.x == 0) {
@@ -129,17 +152,17 @@ int filter_device(uint8_t *d_pixels, uint32_t width, uint32_t height, uint32_t s
 
 // ====================================================================== CRC32-C of finished frames
 // Standard CRC-32C (init ~0, reflected 0x82F63B78, final ~): crc(A||B) = crc(A) * x^(8|B|) mod P  xor  crc(B), so a
-// frame is cut into 64-byte segments (one per thread, slice-by-4 tables in shared memory), every segment CRC is
-// multiplied by x^(8 * bytes-after-it) and the products are XORed — first inside a 16 KB chunk (k_crc32c_chunks),
+// frame is cut into 256-byte segments (one per thread, slice-by-4 tables in shared memory), every segment CRC is
+// multiplied by x^(8 * bytes-after-it) and the products are XORed — first inside a 64 KB chunk (k_crc32c_chunks),
 // then over the chunks of a frame (k_crc32c_finish, which also writes the packet header).
 namespace {
 
 constexpr uint32_t CRC_POLY = 0x82F63B78u;
-constexpr int CRC_NT = 256, CRC_SEG = 64, CRC_CHUNK = CRC_NT * CRC_SEG; // 16 KB per CTA
+constexpr int CRC_NT = 256, CRC_SEG = 256, CRC_CHUNK = CRC_NT * CRC_SEG; // 64 KB per CTA, 256 B per thread
 
 struct CrcTables {
   uint32_t x2n[32];   // x^(2^k) mod P, reflected
-  uint32_t seg[256];  // x^(8 * 64 * k) mod P: shift past k whole segments
+  uint32_t seg[256];  // x^(8 * CRC_SEG * k) mod P: shift past k whole segments
 };
 __constant__ CrcTables c_crc;
 
@@ -171,6 +194,12 @@ void crc_tables_init() {
     for (int k = 0; k < 256; k++) t.seg[k] = gf_xpow8(t.x2n, (uint64_t)CRC_SEG * k);
     g_crc_status = cudaMemcpyToSymbol(c_crc, &t, sizeof(t));
   });
+}
+
+// one 32-bit word into the running CRC: slice-by-4 (the four lookups are independent)
+__device__ __forceinline__ uint32_t crc_word(const uint32_t (*T)[256], uint32_t crc, uint32_t w) {
+  crc ^= w;
+  return T[3][crc & 255u] ^ T[2][(crc >> 8) & 255u] ^ T[1][(crc >> 16) & 255u] ^ T[0][crc >> 24];
 }
 
 // grid (chunks, frames).  part[f * max_chunks + c] = standard CRC of chunk c of frame f (0 for chunks past the end).
@@ -206,39 +235,38 @@ __global__ void __launch_bounds__(CRC_NT) k_crc32c_chunks(const uint8_t *out, si
   __syncthreads();
 
   const uint32_t n = (uint32_t)((L - c0) < (size_t)CRC_CHUNK ? (L - c0) : (size_t)CRC_CHUNK); // bytes in this chunk
-  const uint32_t tl = (n - 1u) / CRC_SEG, rem = n - tl * CRC_SEG;                            // last segment, 1..64 bytes
+  const uint32_t tl = (n - 1u) / CRC_SEG, rem = n - tl * CRC_SEG;                            // last segment, 1..SEG bytes
   const uint8_t *src = out + (size_t)f * out_pitch + c0 + (size_t)tid * CRC_SEG;
   uint8_t *dst = copy_dst ? copy_dst + (size_t)f * copy_pitch + c0 + (size_t)tid * CRC_SEG : nullptr;
   uint32_t contrib = 0u;
-  if ((uint32_t)tid < tl) { // a whole segment: four 16-byte loads, slice-by-4
+  if ((uint32_t)tid <= tl) {
+    const uint32_t mine = (uint32_t)tid < tl ? (uint32_t)CRC_SEG : rem; // bytes of this thread's segment
     const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-    uint4 v[4];
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    uint32_t crc = 0xFFFFFFFFu, done = 0;
+    for (; done + 64u <= mine; done += 64u, s4 += 4) { // four 16-byte loads in flight, then 16 dependent word steps
+      uint4 v[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) v[k] = s4[k];
-    if (dst) {
-      uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+      for (int k = 0; k < 4; k++) v[k] = s4[k];
+      if (dst) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) d4[k] = v[k];
-    }
-    uint32_t crc = 0xFFFFFFFFu;
+        for (int k = 0; k < 4; k++) d4[(done >> 4) + k] = v[k];
+      }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        crc ^= w[j];
-        crc = T[3][crc & 255u] ^ T[2][(crc >> 8) & 255u] ^ T[1][(crc >> 16) & 255u] ^ T[0][crc >> 24];
+      for (int k = 0; k < 4; k++) {
+        crc = crc_word(T, crc, v[k].x);
+        crc = crc_word(T, crc, v[k].y);
+        crc = crc_word(T, crc, v[k].z);
+        crc = crc_word(T, crc, v[k].w);
       }
     }
-    contrib = gf_mul(c_crc.seg[tl - 1u - (uint32_t)tid], ~crc); // shifted past the whole segments that follow
-  } else if ((uint32_t)tid == tl) {                               // the chunk's last segment: rem bytes
-    uint32_t crc = 0xFFFFFFFFu;
-    for (uint32_t i = 0; i < rem; i++) {
-      const uint8_t b = src[i];
-      if (dst) dst[i] = b;
+    for (; done < mine; done++) { // the frame's ragged end: < 64 bytes, once per chunk at most
+      const uint8_t b = src[done];
+      if (dst) dst[done] = b;
       crc = T[0][(crc ^ b) & 255u] ^ (crc >> 8);
     }
     contrib = ~crc;
+    if ((uint32_t)tid < tl) contrib = gf_mul(c_crc.seg[tl - 1u - (uint32_t)tid], contrib); // past the whole segments after it
   }
   // XOR-reduce the whole segments, shift them past the last one, add it
   uint32_t whole = ((uint32_t)tid < tl) ? contrib : 0u;

@@ -567,14 +567,14 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
   for (int i = 0; i < n_frames; i++) out[i] = nullptr;
   bool need_stage = gather;
   for (int i = 0; i < n_frames && !need_stage; i++) need_stage = frames[i] && !is_pinned(frames[i]);
-  uint8_t *scratch_before = cx->d_scratch;
+  const size_t scratch_cap_before = cx->d_scratch_cap; // a regrown buffer may come back at the same address
   if (!grow_device(&cx->d_in, &cx->d_in_cap, in_slot * nslot) ||
       !grow_device(&cx->d_scratch, &cx->d_scratch_cap, scratch_bytes(pl, chunk)) ||
       !grow_pinned(&cx->h_out, &cx->h_out_cap, out_slot * nslot) ||
       !grow_pinned((uint8_t **)&cx->h_len, &cx->h_len_cap, len_slot * nslot) ||
       (need_stage && !grow_pinned(&cx->h_in, &cx->h_in_cap, in_slot * nslot)))
     return t_err;
-  if (cx->d_scratch != scratch_before) cx->scratch_dirty = true;
+  if (cx->d_scratch_cap != scratch_cap_before) cx->scratch_dirty = true;
   // library-owned scratch keeps its look-back state across calls (epochs + ticket base) as long as nothing else
   // wrote into it; otherwise it is zeroed once here and the state restarts
   {
@@ -655,7 +655,7 @@ char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, si
   if (!make_plan(cfg, pl)) return nullptr;
   ThreadCtx *cx = thread_ctx();
   if (!cx) return nullptr;
-  uint8_t *scratch_before = cx->d_scratch;
+  const size_t scratch_cap_before = cx->d_scratch_cap; // a regrown buffer may come back at the same address
   const int mc = max_crc_chunks(pl.frame_capacity);
   if (!grow_device(&cx->d_scratch, &cx->d_scratch_cap, scratch_bytes(pl, 1)) ||
       !grow_pinned(&cx->h_out, &cx->h_out_cap, pl.frame_capacity + 32) ||
@@ -665,7 +665,7 @@ char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, si
   if (opts.packet && !grow_device(&cx->d_frame, &cx->d_frame_cap, pl.frame_capacity + (size_t)(16 + mc) * sizeof(uint32_t)))
     return nullptr;
   uint32_t *d_words = reinterpret_cast<uint32_t *>(cx->d_frame + pl.frame_capacity); // frame_capacity is a multiple of 16
-  if (cx->d_scratch != scratch_before) cx->scratch_dirty = true;
+  if (cx->d_scratch_cap != scratch_cap_before) cx->scratch_dirty = true;
   const bool will_be_direct = pl.mode != EM_DITHER_BG && pl.use_smem_out && pl.scale_path != SP_BOX_TMA;
   if (cx->scratch_dirty || !will_be_direct) {
     if (cudaMemsetAsync(cx->d_scratch, 0, cx->d_scratch_cap, cx->stream) != cudaSuccess) return nullptr;

@@ -22,4 +22,39 @@ srcs = [ob.port_convert(ob.gen("noise", 96, 64, i), 20, 6, 3, 0) for i in range(
 bad += acb.ascii_create_grid(srcs, 60, 20) != ob.port_create_grid(srcs, 60, 20)
 got, _, _ = acb.composite([ob.gen("bars", 80, 60, i) for i in range(3)], 60, 20)
 bad += not np.array_equal(got, ob.port_composite([ob.gen("bars", 80, 60, i) for i in range(3)], 60, 20)[0])
+# display path (flip / filter / rainbow), whole-image filter, wire packaging, trailing-reset cut
+img = ob.gen("noise", 64, 48, 3)
+for level, mode, filt, fx, fy in ((3, 2, 3, 1, 0), (3, 0, 12, 0, 1), (2, 0, 1, 1, 1), (0, 0, 9, 1, 0)):
+    got = acb.display_convert(img, 16, 8, acb.make_caps(level, mode), False, False, "standard", bool(fx), bool(fy), filt, 0.7)
+    bad += got != ob.port_display_convert(img, 16, 8, level, mode, flip_x=fx, flip_y=fy, color_filter=filt, time_s=0.7)
+    cfg = acb.make_cfg(64, 48, 16, 16 if mode == 2 else 8, level, mode, scale=acb.SCALE_BOX, flip_x=fx, flip_y=fy,
+                       color_filter=filt, filter_time=0.7)
+    bad += acb.render_batch_host(cfg, [img])[0] != ob.port_display_convert(
+        img, 16, 8, level, mode, flip_x=fx, flip_y=fy, color_filter=filt, time_s=0.7, scale=ob.SCALE_BOX)
+for (w, h) in ((37, 5), (64, 48)):
+    src = ob.gen("noise", w, h, 9)
+    for f in (1, 5, 12):
+        bad += not np.array_equal(acb.apply_color_filter(src, f, 0.3)[1], ob.port_color_filter(src, f, 0.3)[1])
+srcs = [ob.gen(("noise", "bars", "gradient")[i], 96, 64, i) for i in range(3)]
+for i, s_ in enumerate(srcs):
+    acb.source_update(i, s_)
+for level, mode in ((3, 2), (0, 0), (2, 0)):
+    caps = acb.make_caps(level, mode, True)
+    exp = ob.port_mixed_frame(srcs, 40, 12, level, mode, "standard", True)
+    bad += acb.mixed_frame([0, 1, 2], 40, 12, caps, "standard") != exp
+    pkt = acb.mixed_frame_packet([0, 1, 2], 40, 12, caps, "standard")
+    bad += pkt[0] != ob.port_packet_header(exp[0], 40, 12) + exp[0]
+import torch
+lens = [0, 1, 63, 64, 65, 16384, 16385, 40000]
+pitch = 40016
+arena = np.random.default_rng(1).integers(0, 256, (len(lens), pitch), dtype=np.uint8)
+d_out, d_len = torch.from_numpy(arena).cuda(), torch.tensor(lens, dtype=torch.int32, device="cuda")
+d_hdr = torch.zeros(len(lens) * 24, dtype=torch.uint8, device="cuda")
+torch.cuda.synchronize()
+acb.frame_packets_device(d_out.data_ptr(), pitch, d_len.data_ptr(), len(lens), 80, 24, d_hdr.data_ptr(), None)
+acb.trailing_reset_fixup_device(d_out.data_ptr(), pitch, d_len.data_ptr(), len(lens), None)
+acb.synchronize()
+hdr = d_hdr.cpu().numpy().reshape(len(lens), 24)
+for i, L in enumerate(lens):
+    bad += hdr[i].tobytes() != ob.port_packet_header(arena[i, :L].tobytes(), 80, 24)
 print("sanitize ladder mismatches:", bad)

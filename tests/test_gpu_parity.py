@@ -486,10 +486,11 @@ def test_frame_packets_device(acb, ob):
 
 
 def test_crc32c_lengths_and_fixup_device(acb, ob, golden):
-    """arbitrary byte strings in a device arena: chunk-boundary lengths (16 KB chunks, 64-byte segments), empty
+    """arbitrary byte strings in a device arena: chunk-boundary lengths (64 KB chunks, 256-byte segments), empty
     frames, the golden CRCs; and the trailing-reset cut of stream.c:1085-1127 on synthetic strings"""
     import torch
-    lens = [0, 1, 3, 63, 64, 65, 127, 128, 4095, 16383, 16384, 16385, 32768, 100001, 1180548]
+    lens = [0, 1, 3, 63, 64, 65, 127, 128, 255, 256, 257, 319, 320, 4095, 16383, 16384, 16385, 32768, 65535, 65536,
+            65537, 65600, 100001, 131072, 1180548]
     pitch = (max(lens) + 1 + 15) & ~15
     arena = np.zeros((len(lens), pitch), np.uint8)
     data = []
