@@ -8,6 +8,7 @@
 //     it is still in HBM (k_crc32c_chunks + k_crc32c_finish) and the 24-byte big-endian ascii_frame_packet_t;
 //     k_trailing_reset_fixup is the device form of the server's "frame must end in ESC[0m" cut (stream.c:1085-1127).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -133,8 +134,9 @@ int filter_device(uint8_t *d_pixels, uint32_t width, uint32_t height, uint32_t s
   const size_t total_px = (size_t)width * height;
   if (stride == width * 3u && (reinterpret_cast<uintptr_t>(d_pixels) & 15u) == 0) {
     const size_t groups = total_px * 3 / 48;
-    size_t want = (groups + CF_NT - 1) / CF_NT;
-    const size_t cap = (size_t)sm_count() * 8; // 8 resident 256-thread CTAs per SM, grid-stride
+    size_t want = (groups + 2 * CF_NT - 1) / (2 * CF_NT); // two groups per thread per trip
+    static const int cf_ctas = getenv("ACB200_CF_CTAS_PER_SM") ? atoi(getenv("ACB200_CF_CTAS_PER_SM")) : 0; // tuning knob
+    const size_t cap = cf_ctas > 0 ? (size_t)sm_count() * cf_ctas : want; // default: one trip per thread (no grid-stride)
     unsigned grid = (unsigned)(want < 1 ? 1 : want > cap ? cap : want);
     k_color_filter<<<grid, CF_NT, 0, st>>>(d_pixels, total_px * 3, mode, frgb);
   } else {
@@ -196,6 +198,14 @@ void crc_tables_init() {
   });
 }
 
+__device__ __forceinline__ uint4 ld_stream16(const uint4 *p) { // read once; volatile asm = issued where written
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
 // The byte table, replicated once per lane: entry i of lane l lives at word i*32 + l, i.e. in bank l.  A warp's 32
 // lookups (32 unrelated indices) then hit 32 different banks — one shared-memory wavefront per lookup instead of the
 // ~3.5 a shared 1 KB table costs (measured: the slice-by-4 version of this kernel was bank-conflict-bound).
@@ -247,21 +257,30 @@ __global__ void __launch_bounds__(CRC_NT) k_crc32c_chunks(const uint8_t *out, si
     const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
     uint4 *d4 = reinterpret_cast<uint4 *>(dst);
     uint32_t crc = 0xFFFFFFFFu, done = 0;
-    for (; done + 64u <= mine; done += 64u, s4 += 4) { // four 16-byte loads in flight, then 16 dependent word steps
-      uint4 v[4];
+    // 64-byte batches, software-pipelined: the four loads of batch i+1 are issued (asm volatile keeps them where they
+    // are written) before the 64 dependent table steps of batch i, so DRAM latency hides behind the recurrence
+    uint4 cur[4], nxt[4];
+    if (mine >= 64u) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) v[k] = s4[k];
+      for (int k = 0; k < 4; k++) cur[k] = ld_stream16(s4 + k);
+    }
+    for (; done + 64u <= mine; done += 64u) {
+      const bool more = done + 128u <= mine;
+#pragma unroll
+      for (int k = 0; k < 4; k++) nxt[k] = more ? ld_stream16(s4 + (done >> 4) + 4 + k) : make_uint4(0u, 0u, 0u, 0u);
       if (dst) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) d4[(done >> 4) + k] = v[k];
+        for (int k = 0; k < 4; k++) d4[(done >> 4) + k] = cur[k];
       }
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        crc = crc_word(Tl, crc, v[k].x);
-        crc = crc_word(Tl, crc, v[k].y);
-        crc = crc_word(Tl, crc, v[k].z);
-        crc = crc_word(Tl, crc, v[k].w);
+        crc = crc_word(Tl, crc, cur[k].x);
+        crc = crc_word(Tl, crc, cur[k].y);
+        crc = crc_word(Tl, crc, cur[k].z);
+        crc = crc_word(Tl, crc, cur[k].w);
       }
+#pragma unroll
+      for (int k = 0; k < 4; k++) cur[k] = nxt[k];
     }
     for (; done < mine; done++) { // the frame's ragged end: < 64 bytes, once per chunk at most
       const uint8_t b = src[done];
