@@ -122,6 +122,20 @@ cudaError_t launch_resize_nn_only(const uint8_t *src, int sw, int sh, uint8_t *d
 // Floyd–Steinberg 16-colour background renderer (serial wavefront): one CTA per frame, reads the resized image
 cudaError_t launch_dither_bg(const uint8_t *cells, int w, int h, int n_frames, int pad_left, const GlyphLut *lut,
                              uint8_t *rows, uint32_t row_pitch, RowMeta *meta, int *err_scratch, cudaStream_t st);
+// the whole pixel-space composite in one launch (stream.c:664-779): up to 9 sources (stream.c:687)
+struct CompositeCell {
+  const uint8_t *src; // nullptr: the cell stays black (no video / degenerate fit)
+  int sw, sh;         // source size
+  int tw, th;         // contain-fitted target size inside the cell (stream.c:708-716)
+  int xp, yp;         // centring offsets (cellw - tw) / 2, (cellh - th) / 2
+  uint32_t xr, yr;    // 16.16 NN ratios ((sw << 16) / tw) + 1, ((sh << 16) / th) + 1
+};
+struct CompositeParams {
+  uint8_t *comp;
+  int cw, ch, cellw, cellh, gcols, grows, n;
+  CompositeCell cell[9];
+};
+cudaError_t launch_composite_all(const CompositeParams &p, cudaStream_t st);
 // pixel-space composite blit (stream.c:752-773): NN-resize one source into its clipped cell of the composite
 cudaError_t launch_composite_cell(const uint8_t *src, int sw, int sh, uint8_t *comp, int cw, int ch, int tw, int th,
                                   int x0, int y0, int cellw, int cellh, cudaStream_t st);

@@ -172,6 +172,36 @@ __global__ void k_composite_cell(const uint8_t *src, int sw, int sh, uint8_t *co
   }
 }
 
+// The whole composite in one launch (server path with resident sources): every composite pixel finds its grid cell,
+// and inside the cell's centred target rectangle samples its source (same 16.16 NN arithmetic as image_resize,
+// image.c:293-325); everything else is the black canvas of image_clear (stream.c:683).  Cells are disjoint and every
+// blit is clipped to its own cell (stream.c:752-773), so this gather writes exactly what the reference's
+// clear + per-source blits leave behind — with one kernel instead of a memset and up to nine launches.
+__global__ void __launch_bounds__(256) k_composite_all(const CompositeParams p) {
+  const int n = p.cw * p.ch;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int dy = i / p.cw, dx = i - dy * p.cw;
+    const int col = dx / p.cellw, row = dy / p.cellh;
+    uint32_t r = 0, g = 0, b = 0;
+    const int v = row * p.gcols + col;
+    if (col < p.gcols && row < p.grows && v < p.n) {
+      const CompositeCell &c = p.cell[v];
+      const int x = dx - col * p.cellw - c.xp, y = dy - row * p.cellh - c.yp;
+      if (c.src && x >= 0 && x < c.tw && y >= 0 && y < c.th) {
+        uint32_t sy = ((uint32_t)y * c.yr) >> 16, sx = ((uint32_t)x * c.xr) >> 16;
+        if (sy >= (uint32_t)c.sh) sy = (uint32_t)c.sh - 1;
+        if (sx >= (uint32_t)c.sw) sx = (uint32_t)c.sw - 1;
+        const uint8_t *q = c.src + ((size_t)sy * c.sw + sx) * 3u;
+        r = q[0], g = q[1], b = q[2];
+      }
+    }
+    uint8_t *d = p.comp + (size_t)i * 3u;
+    d[0] = (uint8_t)r;
+    d[1] = (uint8_t)g;
+    d[2] = (uint8_t)b;
+  }
+}
+
 // ------------------------------------------------------------------ Floyd–Steinberg 16-colour background renderer
 // rgb_to_16color_dithered (ansi.c:511-583) is a raster-order recurrence; pixel (x,y) only needs the errors pushed by
 // (x-1,y) and (x-1..x+1, y-1), so row y may trail row y-1 by 3 pixels: one thread per row, a skewed wavefront of
@@ -352,6 +382,15 @@ cudaError_t launch_composite_cell(const uint8_t *src, int sw, int sh, uint8_t *c
   if (grid > 148u * 8u) grid = 148u * 8u;
   if (grid == 0) grid = 1;
   k_composite_cell<<<grid, 256, 0, st>>>(src, sw, sh, comp, cw, ch, tw, th, x0, y0, cellw, cellh);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_composite_all(const CompositeParams &p, cudaStream_t st) {
+  const int n = p.cw * p.ch;
+  unsigned grid = (unsigned)((n + 255) / 256);
+  if (grid > 148u * 8u) grid = 148u * 8u;
+  if (grid == 0) grid = 1;
+  k_composite_all<<<grid, 256, 0, st>>>(p);
   return cudaGetLastError();
 }
 

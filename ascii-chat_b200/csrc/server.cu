@@ -7,7 +7,7 @@
 //     double-buffered, stream.c:253/282)          frame into the slot's back buffer, then a pointer swap
 //   collect_video_sources (stream.c:221-455)    the slot table (valid slots = sources_with_video)
 //   create_single_source_composite (:476-500)   the slot's device buffer itself
-//   create_multi_source_composite (:664-779)    k_composite_cell per source into a W x 2H device composite
+//   create_multi_source_composite (:664-779)    k_composite_all: one launch writes the whole W x 2H device composite
 //   convert_composite_to_ascii (:789-853)       plan_convert_with_caps(width, HALF_BLOCK ? 2*height : height,
 //                                                 aspect=true, stretch=false) + render_one_device
 //   trailing-reset fix-up (:1085-1127)          k_trailing_reset_fixup (effects.cu), on the device
@@ -145,13 +145,17 @@ static char *mixed_frame_impl(const int *slots, int n, unsigned short width, uns
     const int CW = width, CH = (int)height * 2;
     const size_t comp_bytes = (size_t)CW * CH * 3;
     if (!grow_device(&cx->d_out, &cx->d_out_cap, comp_bytes + 16)) return nullptr;
-    if (cudaMemsetAsync(cx->d_out, 0, comp_bytes, cx->stream) != cudaSuccess) { // image_clear, :683
-      set_error(E_INVALID_STATE, "CUDA: clearing the composite failed");
-      return nullptr;
-    }
     const int cellw = CW / gc, cellh = CH / gr;
-    for (int v = 0; v < live && v < 9; v++) { // max 9 sources (:687)
-      const int row = v / gc, col = v % gc;
+    CompositeParams cp{};
+    cp.comp = cx->d_out;
+    cp.cw = CW;
+    cp.ch = CH;
+    cp.cellw = cellw;
+    cp.cellh = cellh;
+    cp.gcols = gc;
+    cp.grows = gr;
+    cp.n = live < 9 ? live : 9; // max 9 sources (:687)
+    for (int v = 0; v < cp.n; v++) {
       const float src_aspect = (float)ws[v] / (float)hs[v];
       const float cell_visual_aspect = (float)cellw / (float)cellh;
       int tw, th;
@@ -162,9 +166,26 @@ static char *mixed_frame_impl(const int *slots, int n, unsigned short width, uns
         th = cellh;
         tw = (int)((cellh * src_aspect) + 0.5f);
       }
+      CompositeCell &c = cp.cell[v];
       if (tw <= 0 || th <= 0) continue; // the reference crashes here (NULL image, :723); we leave the cell black
-      if (launch_composite_cell(src[v], ws[v], hs[v], cx->d_out, CW, CH, tw, th, col * cellw, row * cellh, cellw, cellh,
-                                cx->stream) != cudaSuccess) {
+      c.src = src[v];
+      c.sw = ws[v];
+      c.sh = hs[v];
+      c.tw = tw;
+      c.th = th;
+      c.xp = (cellw - tw) / 2; // :741-742
+      c.yp = (cellh - th) / 2;
+      c.xr = (uint32_t)((((uint64_t)ws[v] << 16) / (uint64_t)tw) + 1);
+      c.yr = (uint32_t)((((uint64_t)hs[v] << 16) / (uint64_t)th) + 1);
+    }
+    // clear (image_clear, :683) + every source's NN resize + clipped blit (:723-773) in one launch
+    if (cellw <= 0 || cellh <= 0) { // more grid columns/rows than pixels: nothing fits, the canvas stays black
+      if (cudaMemsetAsync(cx->d_out, 0, comp_bytes, cx->stream) != cudaSuccess) {
+        set_error(E_INVALID_STATE, "CUDA: clearing the composite failed");
+        return nullptr;
+      }
+    } else {
+      if (launch_composite_all(cp, cx->stream) != cudaSuccess) {
         set_error(E_INVALID_STATE, "CUDA: composite launch failed");
         return nullptr;
       }
