@@ -37,6 +37,13 @@ def _worker(rank, world, port, n_clients, level, mode, q):
     mine = {c: torch.from_numpy(ob.gen(("noise", "bars", "gradient")[c % 3], W, H, c)).cuda()
             for c in multi.shard_indices(n_clients, rank, world)}
     res = multi.render_clients_to_grid(acb, mine, cfg, 160, 48)
+    # the steady-state pipeline (buffers set up once) must produce the same grid, twice in a row
+    pipe = multi.GridPipeline(acb, cfg, n_clients, 160, 48)
+    batch = torch.stack([mine[c] for c in pipe.mine]).contiguous() if pipe.mine else None
+    for _ in range(2):
+        res2 = pipe.step(batch)
+        if rank == 0:
+            assert res2 == res[0], "GridPipeline differs from render_clients_to_grid"
     if rank == 0:
         q.put(res)
     dist.barrier()
