@@ -63,7 +63,7 @@ EXPORTS = [  # every symbol include/asciichat_b200.h declares
     "acb200_create_grid_device", "acb200_synchronize", "acb200_source_update", "acb200_source_clear",
     "acb200_mixed_frame", "apply_color_filter", "color_filter_calculate_rainbow", "acb200_display_convert",
     "acb200_color_filter_device", "acb200_frame_packets_device", "acb200_mixed_frame_packet",
-    "acb200_trailing_reset_fixup_device",
+    "acb200_trailing_reset_fixup_device", "acb200_source_update_wire",
 ]
 
 
@@ -141,6 +141,7 @@ def lib():
                                             C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p]
     L.acb200_source_update.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int]
     L.acb200_source_clear.argtypes = [C.c_int]
+    L.acb200_source_update_wire.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
     L.acb200_mixed_frame.restype = C.c_void_p
     L.acb200_mixed_frame.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_ushort, C.c_ushort,
                                      C.POINTER(terminal_capabilities_t), C.c_char_p, C.POINTER(C.c_size_t),
@@ -257,6 +258,11 @@ def source_update(slot, image):
     a = np.ascontiguousarray(image, dtype=np.uint8)
     assert a.ndim == 3 and a.shape[2] == 3
     return lib().acb200_source_update(slot, a.ctypes.data, a.shape[1], a.shape[0])
+
+
+def source_update_wire(slot, payload):
+    """payload: bytes of an IMAGE_FRAME packet body, [w:be32][h:be32][RGB24] (src/server/protocol.c:737-889)"""
+    return lib().acb200_source_update_wire(slot, payload, len(payload))
 
 
 def source_clear(slot):

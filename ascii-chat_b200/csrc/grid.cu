@@ -2,7 +2,7 @@
 //
 //  * text-space: ascii_create_grid (lib/video/ascii/ascii.c:602-885) — N rendered frames ->
 //    one W x H character canvas with '|', '_', '+' separators.  Layout scoring is host float
-//    (ceil/logf/fabsf, ascii.c:712-769); everything that touches frame bytes runs in k_text_grid.
+//    (ceil/logf/fabsf, ascii.c:712-769); everything that touches frame bytes runs in k_grid_lines / k_grid_place.
 //  * pixel-space: create_multi_source_composite (src/server/stream.c:664-779) with
 //    calculate_optimal_grid_layout (stream.c:523-651) — N RGB sources -> one W x 2H composite;
 //    the NN resize + clipped blit of every source is k_composite_cell (render_kernels.cu).
@@ -15,9 +15,12 @@
 namespace acb {
 
 // ------------------------------------------------------------------ text grid kernel
+constexpr int TG_INLINE = 32; // sources whose pointer/size tables travel in the kernel parameters (MAX_CLIENTS)
 struct TextGridParams {
-  const uint8_t *const *src; // [n] device pointers
-  const uint32_t *size;      // [n]
+  const uint8_t *const *src; // [n] device pointers    } device tables, used when n > TG_INLINE
+  const uint32_t *size;      // [n]                     }
+  const uint8_t *src_in[TG_INLINE]; // the same tables inline (n <= TG_INLINE): no upload, no lifetime to manage
+  uint32_t size_in[TG_INLINE];
   int n, W, H;
   int gcols, grows, cw, ch;  // layout (multi-source path)
   int single;                // n == 1: centre the lone frame (ascii.c:610-707)
@@ -26,6 +29,7 @@ struct TextGridParams {
   uint32_t total;            // W*H + H + 1
   uint32_t *lstart, *llen, *clen, *dcol; // [n * maxlines] scratch
   uint32_t *nlines, *nl_total;           // [n]
+  uint32_t *order;                       // [total] write-order id that owns each canvas byte (0 = blank canvas)
 };
 
 // ansi_truncate_to_visual_width (ascii.c:562-586); *vis = visible characters inside the returned prefix,
@@ -48,59 +52,101 @@ __device__ static int truncate_visible(const uint8_t *d, int n, int target, int 
   return i;
 }
 
-__global__ void __launch_bounds__(256) k_text_grid(const TextGridParams p) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  const uint32_t W1 = (uint32_t)p.W + 1u;
-  // phase 0: blank canvas, '\n' closing every row, NUL (ascii.c:633-640, 806-813)
-  for (uint32_t i = tid; i < p.total - 1; i += blockDim.x) p.out[i] = (i % W1 == (uint32_t)p.W) ? '\n' : ' ';
-  if (tid == 0) p.out[p.total - 1] = 0;
+// The grid is built by three launches, none of them serial in the number of sources or lines:
+//   k_grid_lines  (one CTA per source): newline table by a two-pass chunked scan, then per line the ANSI-aware
+//                 truncation and the copy decision; the CTAs also blank the canvas and clear the order map.
+//   k_grid_claim  (one CTA per line / separator set): every byte a writer would store takes part in an atomicMax on a
+//                 per-canvas-byte ORDER id — the reference writes source-major, line by line, then that source's
+//                 separators (ascii.c:829-880), and where ANSI bytes spill past a cell the LATER write wins.
+//   k_grid_write  (same enumeration): a writer stores its byte only where it holds the maximum.
+constexpr int TG_NT = 256;
 
-  // phase 1: line tables, one warp per source, 32 bytes per step
-  for (int s = warp; s < p.n; s += nwarp) {
-    const uint8_t *d = p.src[s];
-    const uint32_t size = d ? p.size[s] : 0u;
-    uint32_t line = 0, start = 0, nl = 0;
-    for (uint32_t base = 0; base < size; base += 32) {
-      uint32_t i = base + lane;
-      uint32_t m = __ballot_sync(0xffffffffu, i < size && d[i] == '\n');
-      nl += __popc(m);
-      while (m && line < (uint32_t)p.maxlines) {
-        uint32_t e = base + (uint32_t)(__ffs(m) - 1);
-        if (lane == 0) {
-          p.lstart[(size_t)s * p.maxlines + line] = start;
-          p.llen[(size_t)s * p.maxlines + line] = e - start;
-        }
-        line++;
-        start = e + 1;
-        m &= m - 1;
-      }
+__device__ __forceinline__ const uint8_t *tg_src(const TextGridParams &p, int s) {
+  return p.n <= TG_INLINE ? p.src_in[s] : p.src[s];
+}
+__device__ __forceinline__ uint32_t tg_size(const TextGridParams &p, int s) {
+  return p.n <= TG_INLINE ? p.size_in[s] : p.size[s];
+}
+__device__ __forceinline__ uint32_t tg_line_id(const TextGridParams &p, int s, int r) { // 1-based, reference order
+  return (uint32_t)s * (uint32_t)(p.maxlines + 4) + (uint32_t)r + 1u;
+}
+
+__global__ void __launch_bounds__(TG_NT) k_grid_lines(const TextGridParams p) {
+  __shared__ uint32_t s_cnt[TG_NT], s_tot;
+  const int tid = threadIdx.x, s = blockIdx.x;
+  const uint32_t W1 = (uint32_t)p.W + 1u;
+  // blank canvas, '\n' closing every row, NUL (ascii.c:633-640, 806-813); order map = 0 ("blank")
+  for (uint32_t i = blockIdx.x * TG_NT + tid; i < p.total; i += gridDim.x * TG_NT) {
+    p.out[i] = i == p.total - 1 ? 0 : (i % W1 == (uint32_t)p.W) ? '\n' : ' ';
+    p.order[i] = 0u;
+  }
+  const uint8_t *d = tg_src(p, s);
+  const uint32_t size = d ? tg_size(p, s) : 0u;
+  uint32_t *lstart = p.lstart + (size_t)s * p.maxlines, *llen = p.llen + (size_t)s * p.maxlines;
+  const uint32_t ML = (uint32_t)p.maxlines;
+
+  // pass 1: newlines per chunk
+  const uint32_t chunk = (size + TG_NT - 1) / TG_NT;
+  const uint32_t b0 = min((uint32_t)tid * chunk, size), b1 = min(b0 + chunk, size);
+  uint32_t cnt = 0;
+  for (uint32_t i = b0; i < b1; i++) cnt += d[i] == '\n';
+  s_cnt[tid] = cnt;
+  __syncthreads();
+  if (tid < 32) { // exclusive scan of 256 counts by one warp (8 per lane)
+    uint32_t v[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      v[k] = s_cnt[tid * 8 + k];
+      sum += v[k];
     }
-    if (start < size && line < (uint32_t)p.maxlines) { // last line without a trailing newline
-      if (lane == 0) {
-        p.lstart[(size_t)s * p.maxlines + line] = start;
-        p.llen[(size_t)s * p.maxlines + line] = size - start;
-      }
-      line++;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, inc, dd);
+      if (tid >= dd) inc += o;
     }
-    if (lane == 0) {
-      p.nlines[s] = line;
-      p.nl_total[s] = nl;
+    uint32_t run = inc - sum;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      s_cnt[tid * 8 + k] = run;
+      run += v[k];
     }
+    if (tid == 31) s_tot = inc;
+  }
+  __syncthreads();
+  const uint32_t nl_total = s_tot;
+  // pass 2: line L ends at its newline; line L+1 starts right after it (only the first maxlines lines are kept)
+  if (tid == 0 && ML > 0) lstart[0] = 0u;
+  uint32_t L = s_cnt[tid];
+  for (uint32_t i = b0; i < b1 && L < ML; i++)
+    if (d[i] == '\n') {
+      llen[L] = i; // end offset for now
+      if (L + 1 < ML) lstart[L + 1] = i + 1;
+      L++;
+    }
+  __syncthreads();
+  // lines closed by a newline, plus a last line without one (if there is room)
+  uint32_t nlines = min(nl_total, ML);
+  const bool tail = nl_total < ML && lstart[nl_total] < size; // lstart[nl_total] = byte after the last newline (0 if none)
+  for (uint32_t r = tid; r < nlines; r += TG_NT) llen[r] = llen[r] - lstart[r];
+  if (tid == 0 && tail) llen[nl_total] = size - lstart[nl_total];
+  if (tail) nlines++;
+  if (tid == 0) {
+    p.nlines[s] = nlines;
+    p.nl_total[s] = nl_total;
   }
   __syncthreads();
 
-  // phase 2: per line, ANSI-aware truncation and the copy decision
-  const int items = p.n * p.maxlines;
-  for (int it = tid; it < items; it += blockDim.x) {
-    const int s = it / p.maxlines, r = it % p.maxlines;
-    if ((uint32_t)r >= p.nlines[s]) continue;
-    const uint8_t *line = p.src[s] + p.lstart[it];
-    const int ll = (int)p.llen[it];
+  // per line: ANSI-aware truncation and the copy decision
+  for (uint32_t r = tid; r < nlines; r += TG_NT) {
+    const size_t it = (size_t)s * p.maxlines + r;
+    const uint8_t *line = d + lstart[r];
+    const int ll = (int)llen[r];
     uint32_t cl = 0, col = 0;
     if (p.single) { // ascii.c:661-703
-      int vpad = (p.H - (int)p.nl_total[0]) / 2;
+      int vpad = (p.H - (int)nl_total) / 2;
       if (vpad < 0) vpad = 0;
-      const int row = vpad + r;
+      const int row = vpad + (int)r;
       if (row < p.H) {
         int vis;
         truncate_visible(line, ll, 0x7fffffff, &vis); // ansi_visual_width of the whole line
@@ -117,10 +163,10 @@ __global__ void __launch_bounds__(256) k_text_grid(const TextGridParams p) {
     } else { // ascii.c:829-852
       const int gr = s / p.gcols, gc = s % p.gcols;
       const int r0 = gr * (p.ch + 1), c0 = gc * (p.cw + 1);
-      if (r < p.ch && r0 + r < p.H) {
+      if ((int)r < p.ch && r0 + (int)r < p.H) {
         int tv;
         int c = truncate_visible(line, ll, p.cw, &tv);
-        const size_t pos = (size_t)(r0 + r) * W1 + (size_t)c0;
+        const size_t pos = (size_t)(r0 + (int)r) * W1 + (size_t)c0;
         // SAFE_MEMCPY refuses when count > remaining size (lib/platform/posix/system.c:653-666)
         if (c > 0 && c0 + tv <= p.W && (size_t)c <= (size_t)p.total - pos) {
           cl = (uint32_t)c;
@@ -131,45 +177,44 @@ __global__ void __launch_bounds__(256) k_text_grid(const TextGridParams p) {
     p.clen[it] = cl;
     p.dcol[it] = col;
   }
-  __syncthreads();
+}
 
-  // phase 3: the writes, in the reference's order (later writes win where ANSI bytes spill over)
-  for (int s = 0; s < p.n; s++) {
-    const uint32_t nl = p.nlines[s];
-    for (uint32_t r = 0; r < nl; r++) {
-      const size_t it = (size_t)s * p.maxlines + r;
-      const uint32_t cl = p.clen[it];
-      if (cl) {
-        const uint8_t *line = p.src[s] + p.lstart[it];
-        uint8_t *dst = p.out + p.dcol[it];
-        for (uint32_t i = tid; i < cl; i += blockDim.x) dst[i] = line[i];
-      }
-      __syncthreads();
-    }
-    if (p.single) continue;
-    const int gr = s / p.gcols, gc = s % p.gcols;
-    const int r0 = gr * (p.ch + 1), c0 = gc * (p.cw + 1);
-    if (gc < p.gcols - 1 && c0 + p.cw < p.W) { // vertical separator, ascii.c:855-863
-      for (int row = r0 + tid; row < r0 + p.ch && row < p.H; row += blockDim.x) {
-        size_t idx = (size_t)row * W1 + (size_t)(c0 + p.cw);
-        if (idx < (size_t)p.total - 1) p.out[idx] = '|';
-      }
-    }
-    __syncthreads();
-    if (gr < p.grows - 1 && r0 + p.ch < p.H) { // horizontal separator + corner, ascii.c:865-880
-      for (int c = c0 + tid; c < c0 + p.cw && c < p.W; c += blockDim.x) {
-        size_t idx = (size_t)(r0 + p.ch) * W1 + (size_t)c;
-        if (idx < (size_t)p.total - 1) p.out[idx] = '_';
-      }
-      __syncthreads();
-      if (tid == 0 && gc < p.gcols - 1 && c0 + p.cw < p.W) {
-        size_t idx = (size_t)(r0 + p.ch) * W1 + (size_t)(c0 + p.cw);
-        if (idx < (size_t)p.total - 1) p.out[idx] = '+';
-      }
-    }
-    __syncthreads();
+// One CTA per writer: blockIdx.x < n*maxlines -> line (s, r); the n CTAs after that -> the separators of source s.
+// WRITE = false: claim the bytes (atomicMax of the order id); WRITE = true: store where the claim was won.
+// The canvas terminator (total - 1) is never claimed: a spill that reaches it is undone by the reference's callers
+// reading a C string; here it simply stays NUL.
+template <bool WRITE> __global__ void __launch_bounds__(128) k_grid_place(const TextGridParams p) {
+  const int tid = threadIdx.x;
+  const uint32_t W1 = (uint32_t)p.W + 1u, last = p.total - 1u;
+  const int items = p.n * p.maxlines;
+  auto put = [&](size_t idx, uint8_t c, uint32_t id) {
+    if (idx >= (size_t)last) return;
+    if (!WRITE) atomicMax(&p.order[idx], id);
+    else if (p.order[idx] == id) p.out[idx] = c;
+  };
+  if ((int)blockIdx.x < items) {
+    const int s = blockIdx.x / p.maxlines, r = blockIdx.x % p.maxlines;
+    if ((uint32_t)r >= p.nlines[s]) return;
+    const uint32_t cl = p.clen[blockIdx.x];
+    if (!cl) return;
+    const uint8_t *line = tg_src(p, s) + p.lstart[blockIdx.x];
+    const size_t pos = p.dcol[blockIdx.x];
+    const uint32_t id = tg_line_id(p, s, r);
+    for (uint32_t i = tid; i < cl; i += 128) put(pos + i, WRITE ? line[i] : 0, id);
+    return;
   }
-  if (tid == 0) p.out[p.total - 1] = 0; // a spill may have landed on the terminator (reference: UB)
+  if (p.single) return;
+  const int s = (int)blockIdx.x - items;
+  const int gr = s / p.gcols, gc = s % p.gcols;
+  const int r0 = gr * (p.ch + 1), c0 = gc * (p.cw + 1);
+  const uint32_t base = (uint32_t)s * (uint32_t)(p.maxlines + 4) + (uint32_t)p.maxlines;
+  if (gc < p.gcols - 1 && c0 + p.cw < p.W) // vertical separator, ascii.c:855-863
+    for (int row = r0 + tid; row < r0 + p.ch && row < p.H; row += 128)
+      put((size_t)row * W1 + (size_t)(c0 + p.cw), '|', base + 1u);
+  if (gr < p.grows - 1 && r0 + p.ch < p.H) { // horizontal separator + corner, ascii.c:865-880
+    for (int c = c0 + tid; c < c0 + p.cw && c < p.W; c += 128) put((size_t)(r0 + p.ch) * W1 + (size_t)c, '_', base + 2u);
+    if (tid == 0 && gc < p.gcols - 1 && c0 + p.cw < p.W) put((size_t)(r0 + p.ch) * W1 + (size_t)(c0 + p.cw), '+', base + 3u);
+  }
 }
 
 // ------------------------------------------------------------------ host float layouts
@@ -231,18 +276,25 @@ static int text_grid_device(const uint8_t *const *d_srcs, const size_t *sizes, i
   }
   // parameter block + scratch in one device allocation of the thread context
   const size_t nl = (size_t)n * p.maxlines;
-  const size_t bytes = al16((uint32_t)(n * sizeof(void *))) + al16((uint32_t)(n * 4)) + 4 * al16((uint32_t)(nl * 4)) +
-                       2 * al16((uint32_t)(n * 4));
+  const size_t head = al16((uint32_t)(n * sizeof(void *))) + al16((uint32_t)(n * 4));
+  const size_t bytes = head + 4 * al16((uint32_t)(nl * 4)) + 2 * al16((uint32_t)(n * 4)) + al16(total * 4u);
   if (!grow_device(&cx->d_scratch, &cx->d_scratch_cap, bytes)) return acb200_last_error();
   cx->scratch_dirty = true; // the render path must re-zero its look-back area before reusing this buffer
-  std::vector<uint8_t> h(al16((uint32_t)(n * sizeof(void *))) + al16((uint32_t)(n * 4)));
-  for (int i = 0; i < n; i++) {
-    reinterpret_cast<const uint8_t **>(h.data())[i] = d_srcs[i];
-    reinterpret_cast<uint32_t *>(h.data() + al16((uint32_t)(n * sizeof(void *))))[i] = d_srcs[i] ? (uint32_t)sizes[i] : 0u;
-  }
   uint8_t *b = cx->d_scratch;
-  ACB_CUDA(cudaMemcpyAsync(b, h.data(), h.size(), cudaMemcpyHostToDevice, st));
-  ACB_CUDA(cudaStreamSynchronize(st)); // h is a stack-lifetime buffer
+  if (n <= TG_INLINE) { // tables ride in the kernel parameters
+    for (int i = 0; i < n; i++) {
+      p.src_in[i] = d_srcs[i];
+      p.size_in[i] = d_srcs[i] ? (uint32_t)sizes[i] : 0u;
+    }
+  } else {
+    std::vector<uint8_t> h(head);
+    for (int i = 0; i < n; i++) {
+      reinterpret_cast<const uint8_t **>(h.data())[i] = d_srcs[i];
+      reinterpret_cast<uint32_t *>(h.data() + al16((uint32_t)(n * sizeof(void *))))[i] = d_srcs[i] ? (uint32_t)sizes[i] : 0u;
+    }
+    ACB_CUDA(cudaMemcpyAsync(b, h.data(), head, cudaMemcpyHostToDevice, st));
+    ACB_CUDA(cudaStreamSynchronize(st)); // h is a stack-lifetime buffer
+  }
   p.src = reinterpret_cast<const uint8_t *const *>(b);
   b += al16((uint32_t)(n * sizeof(void *)));
   p.size = reinterpret_cast<const uint32_t *>(b);
@@ -258,9 +310,14 @@ static int text_grid_device(const uint8_t *const *d_srcs, const size_t *sizes, i
   p.nlines = reinterpret_cast<uint32_t *>(b);
   b += al16((uint32_t)(n * 4));
   p.nl_total = reinterpret_cast<uint32_t *>(b);
-  k_text_grid<<<1, 256, 0, st>>>(p);
+  b += al16((uint32_t)(n * 4));
+  p.order = reinterpret_cast<uint32_t *>(b);
+  const unsigned writers = (unsigned)(nl + (size_t)n);
+  k_grid_lines<<<(unsigned)n, TG_NT, 0, st>>>(p);
+  k_grid_place<false><<<writers, 128, 0, st>>>(p);
+  k_grid_place<true><<<writers, 128, 0, st>>>(p);
   ACB_CUDA(cudaGetLastError());
-  count_launch();
+  count_launch(3);
   *out_size = total - 1;
   return E_OK;
 }

@@ -96,6 +96,22 @@ int acb200_source_update(int slot, const uint8_t *rgb, int w, int h) {
   return E_OK;
 }
 
+// The wire form of a received frame, IMAGE_FRAME payload = [width:be32][height:be32][RGB24] — the checks of
+// handle_image_frame_packet (src/server/protocol.c:737-889) before it commits the frame: payload >= 8 bytes (:748),
+// image_validate_dimensions (1..3840 x 1..2160, lib/util/image.c + image.h:166,179) (:775), exact length
+// 8 + w*h*3 (:799).  (The reference additionally drops packets above its 2 MB ring-buffer slot, :833 — a property of
+// that buffer, not of the format; resident slots here grow to the frame.)
+int acb200_source_update_wire(int slot, const uint8_t *payload, size_t len) {
+  if (!slot_ok(slot)) return set_error(E_INVALID_PARAM, "acb200_source_update_wire: slot %d out of range", slot);
+  if (!payload || len < 8) return set_error(E_INVALID_PARAM, "IMAGE_FRAME payload too small: %zu bytes", len);
+  const uint32_t w = ((uint32_t)payload[0] << 24) | ((uint32_t)payload[1] << 16) | ((uint32_t)payload[2] << 8) | payload[3];
+  const uint32_t h = ((uint32_t)payload[4] << 24) | ((uint32_t)payload[5] << 16) | ((uint32_t)payload[6] << 8) | payload[7];
+  if (w == 0 || h == 0 || w > 3840u || h > 2160u) return set_error(E_INVALID_PARAM, "IMAGE_FRAME invalid dimensions %ux%u", w, h);
+  const size_t expected = 8 + (size_t)w * h * 3;
+  if (len != expected) return set_error(E_INVALID_PARAM, "IMAGE_FRAME size mismatch: expected %zu bytes got %zu", expected, len);
+  return acb200_source_update(slot, payload + 8, (int)w, (int)h);
+}
+
 static char *mixed_frame_impl(const int *slots, int n, unsigned short width, unsigned short height,
                               const terminal_capabilities_t *caps, const char *palette, size_t *out_size,
                               int *out_sources_count, bool packet) {

@@ -275,6 +275,11 @@ uint8_t *acb200_mixed_frame_packet(const int *slots, int n, unsigned short width
  * (stream.c:342): the slot is cleared and ERROR_INVALID_PARAM returned.  Thread-safe against
  * acb200_mixed_frame(); returns when the frame is resident. */
 int acb200_source_update(int slot, const uint8_t *rgb, int w, int h);
+/* Same, from the wire form of the frame: IMAGE_FRAME payload [width:be32][height:be32][RGB24] as
+ * handle_image_frame_packet receives it (src/server/protocol.c:737-889): payload >= 8 bytes, dimensions
+ * 1..3840 x 1..2160 (image_validate_dimensions), len == 8 + w*h*3; anything else is ERROR_INVALID_PARAM and the slot
+ * keeps its previous frame (the reference disconnects the client, which then calls acb200_source_clear). */
+int acb200_source_update_wire(int slot, const uint8_t *payload, size_t len);
 /* client stopped sending video / disconnected (is_sending_video = false) */
 int acb200_source_clear(int slot);
 /* One output frame for one receiving client.  `slots` lists the active clients in g_client_manager order;

@@ -98,6 +98,17 @@ def test_no_gpu_means_loud_failure(acb):
         acb.render_batch_host(acb.make_cfg(8, 8, 4, 4, 3, 2), [np.zeros((8, 8, 3), np.uint8)])
 
 
+def test_wire_ingest_validation_needs_no_gpu(acb):
+    """the IMAGE_FRAME payload checks of handle_image_frame_packet (protocol.c:748-803) run before any device work"""
+    import struct
+    ok_hdr = struct.pack(">II", 4, 2)
+    for payload in (b"", b"\0" * 7, struct.pack(">II", 0, 2) + b"x" * 24, struct.pack(">II", 3841, 1) + b"x" * 11523,
+                    struct.pack(">II", 1, 2161) + b"x" * 6483, ok_hdr + b"x" * 23, ok_hdr + b"x" * 25):
+        assert acb.source_update_wire(0, payload) == 86, payload[:8]
+        assert acb.last_error()[0] == 86
+    assert acb.source_update_wire(99, ok_hdr + b"x" * 24) == 86
+
+
 def test_product_never_references_the_oracle():
     pkg = os.path.join(ROOT, "ascii-chat_b200")
     for dp, _, files in os.walk(pkg):

@@ -251,6 +251,19 @@ def test_text_grid(acb, ob):
         assert acb.ascii_create_grid(srcs, W, H) == chk(srcs, W, H), (it, n, W, H)
 
 
+def test_text_grid_edge_cases(acb, ob):
+    """more than 32 sources (device tables instead of inline ones), missing sources, trailing newlines, more lines
+    than the cell is tall, plain text, ANSI spills across cells in narrow grids: every byte as the reference writes it"""
+    chk = ob.ref_create_grid if ob.ref() is not None else ob.port_create_grid
+    col = [ob.port_convert(ob.gen(("noise", "bars", "gradient")[i % 3], 96, 64, i), 30, 20, 3, 0) for i in range(40)]
+    cases = [(col, 300, 80), (col[:33], 200, 70), (col[:5] + [None] + col[6:9], 120, 40),
+             ([c + b"\n" for c in col[:4]], 100, 30), ([c + b"\n\n\n" for c in col[:3]], 64, 9),
+             ([b"plain\ntext\nonly", b"second\nsource", b"x" * 500], 50, 12), ([b"", col[1]], 80, 24),
+             (col[:9], 33, 11), (col[:4], 21, 7), ([col[0]], 12, 4), ([col[0]], 200, 60), ([b"\n\n\n"], 20, 5)]
+    for i, (srcs, W, H) in enumerate(cases):
+        assert acb.ascii_create_grid(srcs, W, H) == chk(srcs, W, H), (i, len(srcs), W, H)
+
+
 def test_text_grid_golden(acb, ob, golden):
     for rec in golden["text_grids"]:
         srcs = [ob.port_convert(ob.gen("noise" if i % 2 else "bars", 160, 120, i), rec["cols"], rec["rows"],
@@ -299,6 +312,22 @@ def test_mixed_frame_golden(acb, ob, golden):
                                   bool(case["pad"]))
         assert (s, sz, cnt) == exp
     for i in range(acb.MAX_SOURCES):
+        acb.source_clear(i)
+
+
+def test_source_update_wire(acb, ob):
+    """frames ingested in their wire form ([w:be32][h:be32][RGB24], protocol.c:737-889) render like the same frames
+    ingested as (rgb, w, h); malformed payloads leave the slot untouched"""
+    import struct
+    srcs = [ob.gen(("noise", "bars", "gradient")[i], 200 + 17 * i, 120 + 9 * i, i) for i in range(3)]
+    for i, s_ in enumerate(srcs):
+        assert acb.source_update_wire(i, struct.pack(">II", s_.shape[1], s_.shape[0]) + s_.tobytes()) == 0, acb.last_error()
+    caps = acb.make_caps(3, 2, True)
+    got = acb.mixed_frame([0, 1, 2], 120, 40, caps, "standard")
+    assert got == ob.port_mixed_frame(srcs, 120, 40, 3, 2, "standard", True)
+    assert acb.source_update_wire(1, struct.pack(">II", 10, 10) + b"short") == 86
+    assert acb.mixed_frame([0, 1, 2], 120, 40, caps, "standard") == got  # slot 1 kept its frame
+    for i in range(3):
         acb.source_clear(i)
 
 
