@@ -5,7 +5,8 @@
 //    (ceil/logf/fabsf, ascii.c:712-769); everything that touches frame bytes runs in k_grid_lines / k_grid_place.
 //  * pixel-space: create_multi_source_composite (src/server/stream.c:664-779) with
 //    calculate_optimal_grid_layout (stream.c:523-651) — N RGB sources -> one W x 2H composite;
-//    the NN resize + clipped blit of every source is k_composite_cell (render_kernels.cu).
+//    the NN resize + clipped blit is k_composite_cell per host source here, k_composite_all for the server's
+//    resident sources (server.cu); both kernels live in render_kernels.cu.
 #include <cmath>
 #include <cstring>
 #include <vector>

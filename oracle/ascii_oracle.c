@@ -8,7 +8,7 @@
  * reference (oracle/_ref) also proves that reformulation.
  *
  * Each function cites the reference file:line it restates (paths relative to the
- * reference checkout).  Parity: pinned by tests/test_oracle_vs_ref.py + tests/golden/.
+ * reference checkout).  Parity: pinned by tests/test_oracle.py + tests/golden/.
  */
 #define _GNU_SOURCE
 #include "ascii_oracle.h"

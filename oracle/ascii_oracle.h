@@ -5,7 +5,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library; the product (libasciichat_b200.so) never does.
  *
- * Parity status: PINNED.  Every function is checked in tests/test_oracle_vs_ref.py
+ * Parity status: PINNED.  Every function is checked in tests/test_oracle.py
  * against oracle/_ref/libasciichat_ref.so (the reference's own sources compiled
  * unmodified) and against the committed golden vectors in tests/golden/.
  */

@@ -576,3 +576,45 @@ def test_mixed_frame_packet(acb, ob, golden):
         assert pkt[:24] == ob.port_packet_header(frame, case["W"], case["H"]), case
     for i in range(acb.MAX_SOURCES):
         acb.source_clear(i)
+
+
+def test_concurrent_callers_new_entries(acb, ob):
+    """the §8f entry points from many threads at once (each thread leases its own stream / staging): display
+    conversions with different flips and filters, packet-producing server frames, grids — all byte-exact"""
+    img = ob.gen("noise", 320, 240, 1)
+    srcs = [ob.gen(("noise", "bars", "gradient")[i % 3], 160, 120, i) for i in range(3)]
+    for i, s in enumerate(srcs):
+        assert acb.source_update(i, s) == 0
+    grid_srcs = [ob.port_convert(ob.gen("bars", 96, 64, i), 20, 8, 3, 0) for i in range(4)]
+    jobs = []
+    for j in range(12):
+        kw = dict(cols=40 + j, rows=12 + j % 5, level=(3, 2, 1, 0)[j % 4], mode=(2, 0, 1)[j % 3], flip_x=bool(j & 1),
+                  flip_y=bool(j & 2), color_filter=(0, 3, 12, 1)[j % 4], time_s=0.5 * j)
+        jobs.append(("display", kw, ob.port_display_convert(img, **kw)))
+    for j in range(6):
+        W, H, level, mode = 60 + 7 * j, 20 + j, (3, 2, 0)[j % 3], (2, 0)[j % 2]
+        frame = ob.port_mixed_frame(srcs, W, H, level, mode, "standard", True)[0]
+        jobs.append(("packet", (W, H, level, mode), ob.port_packet_header(frame, W, H) + frame))
+    for j in range(4):
+        jobs.append(("grid", (50 + 10 * j, 20 + j), ob.port_create_grid(grid_srcs, 50 + 10 * j, 20 + j)))
+    errs = []
+
+    def run(kind, arg, exp):
+        for _ in range(15):
+            if kind == "display":
+                got = _display(acb, img, **arg)
+            elif kind == "packet":
+                W, H, level, mode = arg
+                got = acb.mixed_frame_packet([0, 1, 2], W, H, acb.make_caps(level, mode, True), "standard")[0]
+            else:
+                got = acb.ascii_create_grid(grid_srcs, *arg)
+            if got != exp:
+                errs.append((kind, arg))
+                return
+
+    ts = [threading.Thread(target=run, args=j) for j in jobs]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for i in range(3):
+        acb.source_clear(i)
+    assert not errs, errs[:3]
