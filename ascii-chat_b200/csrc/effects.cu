@@ -165,7 +165,6 @@ constexpr int CRC_NT = 256, CRC_SEG = 256, CRC_CHUNK = CRC_NT * CRC_SEG; // 64 K
 struct CrcTables {
   uint32_t x2n[32];   // x^(2^k) mod P, reflected
   uint32_t seg[256];  // x^(8 * CRC_SEG * k) mod P: shift past k whole segments
-  uint32_t half;      // x^(8 * CRC_SEG / 2) mod P: joins the two half-segment recurrences of one thread
 };
 __constant__ CrcTables c_crc;
 
@@ -195,7 +194,6 @@ void crc_tables_init() {
     t.x2n[0] = p;
     for (int k = 1; k < 32; k++) t.x2n[k] = p = gf_mul(p, p);
     for (int k = 0; k < 256; k++) t.seg[k] = gf_xpow8(t.x2n, (uint64_t)CRC_SEG * k);
-    t.half = gf_xpow8(t.x2n, (uint64_t)CRC_SEG / 2);
     g_crc_status = cudaMemcpyToSymbol(c_crc, &t, sizeof(t));
   });
 }
@@ -223,7 +221,7 @@ __device__ __forceinline__ uint32_t crc_word(const uint32_t *Tl, uint32_t crc, u
 // path), so the frame leaves HBM once for both purposes.
 __global__ void __launch_bounds__(CRC_NT) k_crc32c_chunks(const uint8_t *out, size_t out_pitch, const uint32_t *out_len,
                                                           uint32_t *part, int max_chunks, uint8_t *copy_dst,
-                                                          size_t copy_pitch) {
+                                                          size_t copy_pitch, int noload) {
   __shared__ uint32_t T[256 * 32]; // 32 KB
   __shared__ uint32_t s_t0[256];
   __shared__ uint32_t s_red[CRC_NT / 32];
@@ -254,54 +252,44 @@ __global__ void __launch_bounds__(CRC_NT) k_crc32c_chunks(const uint8_t *out, si
   const uint8_t *src = out + (size_t)f * out_pitch + c0 + (size_t)tid * CRC_SEG;
   uint8_t *dst = copy_dst ? copy_dst + (size_t)f * copy_pitch + c0 + (size_t)tid * CRC_SEG : nullptr;
   uint32_t contrib = 0u;
-  const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-  uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-  if ((uint32_t)tid < tl) {
-    // A whole 256-byte segment as TWO independent recurrences (bytes 0..127 and 128..255) advanced in lock step: the
-    // table step is a dependent LDS chain, so two chains per thread put twice the lookups in flight.  The halves are
-    // joined by crc(A||B) = crc(A) * x^(8*128) ^ crc(B).  Per trip: 32 bytes of each half, loaded up front.
-    uint32_t ca = 0xFFFFFFFFu, cb = 0xFFFFFFFFu;
-    uint4 a[2], b[2];
-    a[0] = ld_stream16(s4), a[1] = ld_stream16(s4 + 1), b[0] = ld_stream16(s4 + 8), b[1] = ld_stream16(s4 + 9);
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      uint4 na[2], nb[2];
-      if (j < 3) {
-        na[0] = ld_stream16(s4 + 2 * j + 2), na[1] = ld_stream16(s4 + 2 * j + 3);
-        nb[0] = ld_stream16(s4 + 2 * j + 10), nb[1] = ld_stream16(s4 + 2 * j + 11);
-      }
-      if (dst) {
-        d4[2 * j] = a[0], d4[2 * j + 1] = a[1], d4[2 * j + 8] = b[0], d4[2 * j + 9] = b[1];
-      }
-#pragma unroll
-      for (int k = 0; k < 2; k++) {
-        ca = crc_word(Tl, ca, a[k].x), cb = crc_word(Tl, cb, b[k].x);
-        ca = crc_word(Tl, ca, a[k].y), cb = crc_word(Tl, cb, b[k].y);
-        ca = crc_word(Tl, ca, a[k].z), cb = crc_word(Tl, cb, b[k].z);
-        ca = crc_word(Tl, ca, a[k].w), cb = crc_word(Tl, cb, b[k].w);
-      }
-      if (j < 3) {
-        a[0] = na[0], a[1] = na[1], b[0] = nb[0], b[1] = nb[1];
-      }
-    }
-    contrib = gf_mul(c_crc.half, ~ca) ^ ~cb;
-    contrib = gf_mul(c_crc.seg[tl - 1u - (uint32_t)tid], contrib); // past the whole segments after it
-  } else if ((uint32_t)tid == tl) { // the chunk's last segment: rem bytes (1..256), one recurrence
+  if ((uint32_t)tid <= tl) {
+    const uint32_t mine = (uint32_t)tid < tl ? (uint32_t)CRC_SEG : rem; // bytes of this thread's segment
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
     uint32_t crc = 0xFFFFFFFFu, done = 0;
-    for (; done + 16u <= rem; done += 16u) {
-      const uint4 v = ld_stream16(s4 + (done >> 4));
-      if (dst) d4[done >> 4] = v;
-      crc = crc_word(Tl, crc, v.x);
-      crc = crc_word(Tl, crc, v.y);
-      crc = crc_word(Tl, crc, v.z);
-      crc = crc_word(Tl, crc, v.w);
+    // 64-byte batches, software-pipelined: the four loads of batch i+1 are issued (asm volatile keeps them where they
+    // are written) before the 64 dependent table steps of batch i, so DRAM latency hides behind the recurrence
+    uint4 cur[4], nxt[4];
+    if (mine >= 64u) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) cur[k] = noload ? make_uint4(k, tid, 0u, 0u) : ld_stream16(s4 + k);
     }
-    for (; done < rem; done++) { // the frame's ragged end: < 16 bytes
+    for (; done + 64u <= mine; done += 64u) {
+      const bool more = done + 128u <= mine;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        nxt[k] = (more && !noload) ? ld_stream16(s4 + (done >> 4) + 4 + k) : make_uint4(done, k, tid, 0u);
+      if (dst) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) d4[(done >> 4) + k] = cur[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        crc = crc_word(Tl, crc, cur[k].x);
+        crc = crc_word(Tl, crc, cur[k].y);
+        crc = crc_word(Tl, crc, cur[k].z);
+        crc = crc_word(Tl, crc, cur[k].w);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) cur[k] = nxt[k];
+    }
+    for (; done < mine; done++) { // the frame's ragged end: < 64 bytes, once per chunk at most
       const uint8_t b = src[done];
       if (dst) dst[done] = b;
       crc = Tl[((crc ^ b) & 255u) << 5] ^ (crc >> 8);
     }
     contrib = ~crc;
+    if ((uint32_t)tid < tl) contrib = gf_mul(c_crc.seg[tl - 1u - (uint32_t)tid], contrib); // past the whole segments after it
   }
   // XOR-reduce the whole segments, shift them past the last one, add it
   uint32_t whole = ((uint32_t)tid < tl) ? contrib : 0u;
@@ -387,11 +375,13 @@ int launch_frame_packets(const uint8_t *d_out, size_t out_pitch, const uint32_t 
                          uint8_t *copy_dst, size_t copy_pitch, cudaStream_t st) {
   crc_tables_init();
   if (g_crc_status != cudaSuccess) return set_error(E_INVALID_STATE, "CUDA: CRC table upload failed");
+  // measurement knob (never set in production): run the table recurrence on synthetic words, no global loads
+  static const int crc_noload = getenv("ACB200_CRC_NOLOAD") ? atoi(getenv("ACB200_CRC_NOLOAD")) : 0;
   for (int f0 = 0; f0 < n_frames; f0 += 65535) { // gridDim.y limit
     const int nf = n_frames - f0 < 65535 ? n_frames - f0 : 65535;
     k_crc32c_chunks<<<dim3((unsigned)max_chunks, (unsigned)nf), CRC_NT, 0, st>>>(
         d_out + (size_t)f0 * out_pitch, out_pitch, d_out_len + f0, d_part + (size_t)f0 * max_chunks, max_chunks,
-        copy_dst ? copy_dst + (size_t)f0 * copy_pitch : nullptr, copy_pitch);
+        copy_dst ? copy_dst + (size_t)f0 * copy_pitch : nullptr, copy_pitch, crc_noload);
     ACB_CUDA(cudaGetLastError());
   }
   k_crc32c_finish<<<(unsigned)n_frames, 32, 0, st>>>(d_part, max_chunks, d_out_len, width, height, headers, header_pitch);
