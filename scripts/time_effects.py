@@ -47,3 +47,12 @@ ts.synchronize()
 ms = timed(lambda: acb.frame_packets_device(d_out.data_ptr(), cap, d_len.data_ptr(), n, 320, 96, d_hdr.data_ptr(), st))
 sb = int(d_len.sum().item())
 print("frame_packets: %.4f ms  %.0f GB/s of string bytes" % (ms, sb / (ms * 1e-3) / 1e9))
+# filtered box render (generic kernel today) vs plain box render on the same 64 frames
+n = 64
+for filt in (0, 3):
+    cfg = acb.make_cfg(3840, 2160, 320, 192, 3, 2, "standard", scale=acb.SCALE_BOX, color_filter=filt)
+    cap = acb.frame_capacity(cfg)
+    d_scr = torch.empty(acb.scratch_bytes(cfg, n), dtype=torch.uint8, device="cuda")
+    tot, ker = acb.time_batch_device(cfg, d_in.data_ptr(), n, d_out.data_ptr(), cap, d_len.data_ptr(), d_scr.data_ptr(), 3)
+    print("box render, colour filter %d: %.3f ms per %d frames  %.0f GB/s of source bytes" % (
+        filt, tot / 3, n, n * 3840 * 2160 * 3 / (tot / 3 * 1e-3) / 1e9))
