@@ -618,3 +618,18 @@ def test_concurrent_callers_new_entries(acb, ob):
     for i in range(3):
         acb.source_clear(i)
     assert not errs, errs[:3]
+
+
+def test_display_ops_on_wide_rows(acb, ob):
+    """the rows-too-wide-for-shared-staging path (scratch rows + k_stitch) with the display steps: the rainbow colour's
+    digit count drives the conditional first-SGR drop of truecolor-fg across rows; flips and filters ride along"""
+    want = _want_display(ob)
+    for W, c, r in ((3840, 3000, 3), (2600, 2600, 2)):
+        img = ob.gen("noise", W, 12, 2)
+        img[:, : W // 6] = (40, 40, 40)        # long equal-colour stretches: SGR dedupe across rows matters
+        img[:, W // 2: W // 2 + 300] = 0
+        for level, mode in ((3, 0), (3, 2), (2, 0)):
+            for filt, fx, fy, t in ((12, 1, 0, 0.9), (12, 0, 1, 2.6), (3, 1, 1, 0.0), (0, 1, 0, 0.0)):
+                kw = dict(cols=c, rows=r, level=level, mode=mode, flip_x=bool(fx), flip_y=bool(fy), color_filter=filt,
+                          time_s=t)
+                assert _display(acb, img, **kw) == want(img, **kw), (W, c, r, level, mode, filt, fx, fy)
