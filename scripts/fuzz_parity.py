@@ -37,7 +37,7 @@ def rnd_img(i):
     img = ob.gen(PATS[int(rng.integers(0, 5))], W, H, i)
     if rng.random() < 0.3:  # black stripes: transparent half-block runs, REP runs
         x0 = int(rng.integers(0, W))
-        img[:, x0:x0 + int(rng.integers(1, 1 + W // 2))] = 0
+        img[:, x0:x0 + int(rng.integers(1, 2 + W // 2))] = 0
     return img
 
 
