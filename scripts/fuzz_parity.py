@@ -24,6 +24,16 @@ want_hdr = ob.ref_packet_header if use_ref else ob.port_packet_header
 PATS = ("noise", "bars", "gradient", "grey", "solid")
 PALS = ("standard", "blocks", "digital", "minimal", "cool")
 counts = {"display": 0, "mixed+packet": 0, "grid": 0, "filter": 0}
+_trace = open(os.environ["FUZZ_TRACE"], "w") if os.environ.get("FUZZ_TRACE") else None
+
+
+def trace(*a):  # last line of the trace file = the case that was running if the process dies
+    if _trace:
+        _trace.seek(0)
+        _trace.truncate()
+        _trace.write(repr(a) + "\n")
+        _trace.flush()
+
 t_end = time.time() + budget
 
 
@@ -51,6 +61,7 @@ while time.time() < t_end:
                   mode=int(rng.integers(0, 3)), palette=PALS[int(rng.integers(0, 5))], aspect=bool(rng.integers(0, 2)),
                   stretch=bool(rng.integers(0, 2)), pad=bool(rng.integers(0, 2)), flip_x=bool(rng.integers(0, 2)),
                   flip_y=bool(rng.integers(0, 2)), color_filter=int(rng.integers(-1, 14)), time_s=float(rng.random() * 30))
+        trace("display", i, img.shape, kw)
         got = acb.display_convert(img, kw["cols"], kw["rows"], acb.make_caps(kw["level"], kw["mode"], kw["pad"]),
                                   kw["aspect"], kw["stretch"], kw["palette"], kw["flip_x"], kw["flip_y"],
                                   kw["color_filter"], kw["time_s"])
@@ -65,6 +76,7 @@ while time.time() < t_end:
         level, mode, pad = int(rng.integers(0, 4)), int(rng.integers(0, 3)), bool(rng.integers(0, 2))
         if ob.composite_degenerate(srcs, W, H):
             continue
+        trace("mixed", i, n, W, H, level, mode, pad, [None if s is None else s.shape for s in srcs])
         for k, s in enumerate(srcs):
             if s is None:
                 acb.source_clear(k)
@@ -90,6 +102,7 @@ while time.time() < t_end:
         if rng.random() < 0.2:
             srcs[int(rng.integers(0, n))] = None
         W, H = int(rng.integers(10, 260)), int(rng.integers(3, 80))
+        trace("grid", i, n, level, mode, cols, rows, W, H, [None if s is None else len(s) for s in srcs])
         got, exp = acb.ascii_create_grid(srcs, W, H), want_grid(srcs, W, H)
         # When an ANSI spill lands on the canvas terminator the reference returns a string that runs past its own
         # allocation (strlen over the heap: undefined); the library keeps the terminator.  Compare the canvas proper.
@@ -100,6 +113,7 @@ while time.time() < t_end:
     else:
         img = rnd_img(i)
         f, t = int(rng.integers(-1, 14)), float(rng.random() * 20)
+        trace("filter", i, img.shape, f, t)
         a = acb.apply_color_filter(img, f, t)
         b = (ob.ref_color_filter if use_ref else ob.port_color_filter)(img, f, t)
         if a[0] != b[0] or not np.array_equal(a[1], b[1]):

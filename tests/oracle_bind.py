@@ -410,14 +410,15 @@ def composite_degenerate(srcs, width, height):
     """True when some source's fitted target is 0 px wide or tall.  The reference dereferences the NULL that
     image_new_from_pool(0, h) returns there (stream.c:723-749) and crashes, so such inputs have no reference
     answer; the product and the port skip that source instead (DESIGN.md §2 divergences)."""
-    live = [s for s in srcs if s is not None][:9]
+    live = [s for s in srcs if s is not None]
     if len(live) < 2:
         return False
-    k = len(live)
+    k = len(live)  # the layout is computed for ALL sources with video (stream.c:670), only the first 9 are placed (:687)
     ws = (C.c_int * k)(*[s.shape[1] for s in live])
     hs = (C.c_int * k)(*[s.shape[0] for s in live])
     c, r = C.c_int(0), C.c_int(0)
     port().orc_grid_layout(ws, hs, k, width, height, C.byref(c), C.byref(r))
+    live = live[:9]
     cw, ch = width // c.value, (height * 2) // r.value
     if cw <= 0 or ch <= 0:
         return True
