@@ -686,11 +686,11 @@ char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, si
   if (render_device(cfg, pl, d_rgb, (size_t)cfg.src_w * cfg.src_h * 3, 0, 1, arena, pl.frame_capacity, lens,
                     cx->d_scratch, cx->stream, nullptr, nullptr, &cx->lb) != E_OK)
     return nullptr;
-  // stream.c:1085-1127 cuts a frame that does not END in ESC[0m after its LAST ESC[0m.  That is the identity for every
-  // grammar the renderers emit: 256 / 16 / truecolor-fg / dithered-bg and the three coloured half-block modes end the
-  // frame with ESC[0m (per-row or final reset, SURVEY §8a grammar table), and the two mono modes contain no SGR at
-  // all, so there is no ESC[0m to cut after.  The launch is kept for any mode outside that list.
-  const bool cut_is_identity = pl.mode >= EM_MONO_FG && pl.mode <= EM_DITHER_BG;
+  // stream.c:1085-1127 cuts a frame that does not END in ESC[0m after its LAST ESC[0m.  Frames of the 256 / 16 /
+  // truecolor-fg / dithered-bg grammars and of the three coloured half-block grammars always end in ESC[0m (per-row or
+  // final reset, SURVEY §8a grammar table), so for them the cut is the identity and the launch is skipped.  The two
+  // mono grammars emit no SGR of their own, but a palette may contain the bytes, so they keep the device check.
+  const bool cut_is_identity = pl.mode != EM_MONO_FG && pl.mode != EM_HB_MONO;
   if (opts.reset_fixup && !cut_is_identity && launch_reset_fixup(arena, pl.frame_capacity, lens, 1, cx->stream) != E_OK)
     return nullptr;
   if (opts.packet && launch_frame_packets(arena, pl.frame_capacity, lens, 1, mc, opts.pk_w, opts.pk_h, d_words + 16,

@@ -10,8 +10,8 @@
 //   create_multi_source_composite (:664-779)    k_composite_all: one launch writes the whole W x 2H device composite
 //   convert_composite_to_ascii (:789-853)       plan_convert_with_caps(width, HALF_BLOCK ? 2*height : height,
 //                                                 aspect=true, stretch=false) + render_one_device
-//   trailing-reset fix-up (:1085-1127)          the identity for every grammar we emit (engine.cu: render_one_device);
-//                                                 k_trailing_reset_fixup (effects.cu) is its device form
+//   trailing-reset fix-up (:1085-1127)          k_trailing_reset_fixup (effects.cu) for the mono grammars; the identity
+//                                                 (frame ends in ESC[0m) for all others (engine.cu: render_one_device)
 //   acip_send_ascii_frame (acip/server.c:188)   acb200_mixed_frame_packet: CRC32-C scan + 24-byte header (effects.cu)
 //
 // Every client's render thread calls acb200_mixed_frame concurrently (one per client at 60 fps in the
