@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libasciichat_b200.so")
+LIB_PATH = os.path.join(HERE, "lib", os.environ.get("ACB200_LIB_NAME", "libasciichat_b200.so"))  # experiments: other name
 
 TERM_COLOR_NONE, TERM_COLOR_16, TERM_COLOR_256, TERM_COLOR_TRUECOLOR = 0, 1, 2, 3
 RENDER_MODE_FOREGROUND, RENDER_MODE_BACKGROUND, RENDER_MODE_HALF_BLOCK = 0, 1, 2

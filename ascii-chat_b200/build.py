@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "lib", "libasciichat_b200.so")
+OUT = os.path.join(HERE, "lib", os.environ.get("ACB200_LIB_NAME", "libasciichat_b200.so"))  # experiments: other name
 SOURCES = ["render_kernels.cu", "engine.cu", "dropin.cu", "grid.cu", "server.cu", "effects.cu"] + ["rk_mode%d.cu" % k for k in range(8)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=hidden", "--extended-lambda",
@@ -32,8 +32,8 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(HERE, "lib", s.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        o = os.path.join(HERE, "lib", os.environ.get("ACB200_OBJ_PREFIX", "") + s.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("ACB200_EXTRA_NVCC", "").split() + ["-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
