@@ -391,17 +391,17 @@ __device__ __forceinline__ void cells_box_generic(const RenderParams &p, const u
 // the source is read exactly once, so it is marked evict-first in L2 (+2.3 % bandwidth: it stops pushing the output
 // rows out of L2 before they are complete sectors); the output rows are marked evict-last (+0.2 % on top).
 // `.L2::256B` prefetch granularity on the loads and `.cs` stores measured neutral / slightly negative.
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-__device__ __forceinline__ uint4 ldg_stream(const uint4 *p, uint64_t pol) { // read-once data: no L1 allocation, L2 evict-first
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) { // read-once data: no L1 allocation, L2 evict-first
+  // The policy word is re-created at every load on purpose: ptxas rematerialises it where it is used (createpolicy is
+  // one uniform-datapath instruction) instead of holding a 64-bit value across the band loop.  Passing one value in
+  // from the caller cost two registers under the kernel's 56-register cap, spilled, and LOST 5 % (r01zz visit).
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
@@ -439,12 +439,11 @@ __device__ __forceinline__ void acc16x2(uint32_t (&a)[8], const uint4 &u, const 
 
 // NR rows of one 16-byte column: NR independent, UNPREDICATED loads in flight, then the pairwise sums.  (A predicated
 // "row r+k exists" form costs an ISETP and four zeroing moves per load: 12% of the kernel's instructions, measured.)
-template <int NR>
-__device__ __forceinline__ void band_trip(uint32_t (&a)[8], const uint8_t *&q, uint32_t R, uint64_t pol) {
+template <int NR> __device__ __forceinline__ void band_trip(uint32_t (&a)[8], const uint8_t *&q, uint32_t R) {
   uint4 v[NR];
 #pragma unroll
   for (int k = 0; k < NR; k++) {
-    v[k] = ldg_stream(reinterpret_cast<const uint4 *>(q), pol);
+    v[k] = ldg_stream(reinterpret_cast<const uint4 *>(q));
     q += R;
   }
 #pragma unroll
@@ -465,26 +464,25 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
   const int nrow = y1 - y0;
   if (p.flip_y) y0 = p.src_h - y1; // the band of the mirrored image is the mirrored band (sums do not care about order)
   const uint8_t *band = frame + (size_t)y0 * (size_t)R;
-  const uint64_t pol = l2_policy_evict_first();
   for (int c = threadIdx.x; c < nchunk; c += NT) {
     uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const uint8_t *q = band + ((size_t)c << 4);
     // whole batches of kBandUnroll rows, then one batch of exactly the rows that are left (a typical band — 11 or 12
     // rows at 4K -> 192 pixel rows — is a single batch: one memory latency per column)
     int r = nrow;
-    for (; r >= kBandUnroll; r -= kBandUnroll) band_trip<kBandUnroll>(a, q, R, pol);
+    for (; r >= kBandUnroll; r -= kBandUnroll) band_trip<kBandUnroll>(a, q, R);
     switch (r) {
-    case 11: band_trip<11>(a, q, R, pol); break;
-    case 10: band_trip<10>(a, q, R, pol); break;
-    case 9: band_trip<9>(a, q, R, pol); break;
-    case 8: band_trip<8>(a, q, R, pol); break;
-    case 7: band_trip<7>(a, q, R, pol); break;
-    case 6: band_trip<6>(a, q, R, pol); break;
-    case 5: band_trip<5>(a, q, R, pol); break;
-    case 4: band_trip<4>(a, q, R, pol); break;
-    case 3: band_trip<3>(a, q, R, pol); break;
-    case 2: band_trip<2>(a, q, R, pol); break;
-    case 1: band_trip<1>(a, q, R, pol); break;
+    case 11: band_trip<11>(a, q, R); break;
+    case 10: band_trip<10>(a, q, R); break;
+    case 9: band_trip<9>(a, q, R); break;
+    case 8: band_trip<8>(a, q, R); break;
+    case 7: band_trip<7>(a, q, R); break;
+    case 6: band_trip<6>(a, q, R); break;
+    case 5: band_trip<5>(a, q, R); break;
+    case 4: band_trip<4>(a, q, R); break;
+    case 3: band_trip<3>(a, q, R); break;
+    case 2: band_trip<2>(a, q, R); break;
+    case 1: band_trip<1>(a, q, R); break;
     default: break;
     }
     // byte j of word k is column 16c + 4k + j:  even reg = {b0 | b2<<16}, odd reg = {b1 | b3<<16}
