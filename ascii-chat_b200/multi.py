@@ -112,6 +112,18 @@ def _render_clients_to_grid(acb, client_frames, cfg, grid_w, grid_h, dst, group,
     return canvas[:size].cpu().numpy().tobytes(), n_clients
 
 
+def arena_slot(item, world, per_rank):
+    """index of item's fixed-pitch slot inside the all-gathered arena: rank-major, then the rank's k-th own item"""
+    return owner_of(item, world) * per_rank + item // world
+
+
+def gather_fixed(arena, lens, all_arena, all_lens, group=None):
+    """The exchange step of the steady-state grid loop: every rank contributes its fixed-pitch arena (per_rank slots)
+    and its per-slot lengths; two fixed-shape all-gathers, no host round trip.  Backend-agnostic (NCCL / gloo)."""
+    dist.all_gather_into_tensor(all_arena, arena, group=group)
+    dist.all_gather_into_tensor(all_lens, lens, group=group)
+
+
 class GridPipeline:
     """BASELINE config 4 as a steady-state loop: everything render_clients_to_grid() sizes and allocates per call is
     set up once (fixed-pitch device arenas, gather buffers, pinned host mirrors, one stream), so a grid costs one render
@@ -148,8 +160,7 @@ class GridPipeline:
                 assert batch.is_contiguous() and batch.shape[0] == len(self.mine)
                 acb.render_batch_device(self.cfg, batch.data_ptr(), len(self.mine), self.arena.data_ptr(), self.cap,
                                         self.lens.data_ptr(), self.scr.data_ptr(), s.cuda_stream)
-            dist.all_gather_into_tensor(self.all_arena, self.arena, group=self.group)
-            dist.all_gather_into_tensor(self.all_lens, self.lens, group=self.group)
+            gather_fixed(self.arena, self.lens, self.all_arena, self.all_lens, group=self.group)
             if self.rank != self.dst:
                 return None
             self.h_lens.copy_(self.all_lens, non_blocking=True)
@@ -157,7 +168,7 @@ class GridPipeline:
             base = self.all_arena.data_ptr()
             ptrs, sizes = [], []
             for i in range(self.n):
-                k = owner_of(i, self.world) * self.per_rank + i // self.world
+                k = arena_slot(i, self.world, self.per_rank)
                 ptrs.append(base + k * self.cap)
                 sizes.append(int(self.h_lens[k]))
             size = acb.create_grid_device(ptrs, sizes, self.W, self.H, self.canvas.data_ptr(), s.cuda_stream)

@@ -48,6 +48,58 @@ def _worker(rank, world, port, n_clients, q):
     dist.destroy_process_group()
 
 
+def _worker_fixed(rank, world, port, n_clients, q):
+    """the steady-state exchange of multi.GridPipeline (fixed-pitch arena + lengths, two all-gathers) over gloo"""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("acb_multi", os.path.join(ROOT, "ascii-chat_b200", "multi.py"))
+    multi = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(multi)
+    import oracle_bind as ob
+
+    cap = 4096
+    per_rank = (n_clients + world - 1) // world
+    arena = torch.zeros(per_rank * cap, dtype=torch.uint8)
+    lens = torch.zeros(per_rank, dtype=torch.int32)
+    for k, c in enumerate(multi.shard_indices(n_clients, rank, world)):
+        s = ob.port_convert(ob.gen(("noise", "bars", "gradient")[c % 3], 96, 64, c), 10 + c, 4 + (c % 3), 2, 0)
+        assert len(s) <= cap
+        arena[k * cap: k * cap + len(s)] = torch.frombuffer(bytearray(s), dtype=torch.uint8)
+        lens[k] = len(s)
+    all_arena = torch.empty(world * per_rank * cap, dtype=torch.uint8)
+    all_lens = torch.empty(world * per_rank, dtype=torch.int32)
+    for _ in range(2):  # the buffers are reused every step
+        multi.gather_fixed(arena, lens, all_arena, all_lens)
+    if rank == 0:
+        frames = []
+        for i in range(n_clients):
+            k = multi.arena_slot(i, world, per_rank)
+            frames.append(all_arena[k * cap: k * cap + int(all_lens[k])].numpy().tobytes())
+        q.put(frames)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_clients", [(2, 8), (2, 5), (3, 7)])
+def test_fixed_pitch_gather_addressing(world, n_clients):
+    sys.path[:0] = [os.path.join(ROOT, "tests")]
+    import oracle_bind as ob
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_fixed, args=(r, world, port, n_clients, q)) for r in range(world)]
+    [p.start() for p in procs]
+    frames = q.get(timeout=120)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    exp = [ob.port_convert(ob.gen(("noise", "bars", "gradient")[c % 3], 96, 64, c), 10 + c, 4 + (c % 3), 2, 0)
+           for c in range(n_clients)]
+    assert frames == exp
+
+
 @pytest.mark.parametrize("world,n_clients", [(2, 8), (2, 5), (3, 7), (2, 1)])
 def test_sharded_gather_equals_single_process(world, n_clients):
     sys.path[:0] = [os.path.join(ROOT, "tests")]
