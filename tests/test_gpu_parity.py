@@ -490,6 +490,33 @@ def test_color_filter_whole_image(acb, ob, golden):
     assert (d.cpu().numpy() == ob.port_color_filter(big, 3)[1]).all()
 
 
+def test_reference_unit_test_kats_on_the_device(acb, ob):
+    """the known answers the reference's own unit tests hold for the 8f rows (tests/unit/video/color_filter_test.c,
+    tests/unit/network/crc32_hw_test.c), asked of the device path"""
+    import test_oracle
+    import torch
+    test_oracle.check_color_filter_kats(acb.apply_color_filter)
+    for w, h, st in ((0, 1, 3), (1, 0, 3), (1, 1, 0)):
+        buf = np.full(3, 255, np.uint8)
+        assert acb.lib().apply_color_filter(buf.ctypes.data, w, h, st, 3, 0.0) == -1
+    msgs = [b"", b"Hello, World!", b"\x42", b"ascii-chat", bytes(range(256)) * 4, b"\0" * 100, b"\xff" * 100]
+    pitch = 1040
+    arena = np.zeros((len(msgs), pitch), np.uint8)
+    for i, m in enumerate(msgs):
+        arena[i, :len(m)] = np.frombuffer(m, np.uint8)
+    d_out = torch.from_numpy(arena).cuda()
+    d_len = torch.tensor([len(m) for m in msgs], dtype=torch.int32, device="cuda")
+    d_hdr = torch.zeros(len(msgs) * 24, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    acb.frame_packets_device(d_out.data_ptr(), pitch, d_len.data_ptr(), len(msgs), 80, 24, d_hdr.data_ptr(), None)
+    acb.synchronize()
+    hdr = d_hdr.cpu().numpy().reshape(len(msgs), 24)
+    crcs = [int.from_bytes(hdr[i, 16:20].tobytes(), "big") for i in range(len(msgs))]
+    assert crcs[0] == 0 and crcs[1] == 0x4D551068 and crcs[2] != 0          # crc32_hw_test.c:14-50
+    for i, m in enumerate(msgs):
+        assert crcs[i] == ob.port().orc_crc32c(m, len(m))
+
+
 # ---------------------------------------------------------------- wire packaging (acip/server.c:188-236, crc32.c)
 def test_frame_packets_device(acb, ob):
     """CRC32-C + ascii_frame_packet_t headers of a resident batch against the oracle's header for the same strings"""

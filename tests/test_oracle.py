@@ -399,3 +399,47 @@ def test_port_vs_ref_crc32c(ob, ref_lib):
         d = rng.integers(0, 256, L, dtype=np.uint8).tobytes()
         assert ref_lib.ref_oracle_crc32(d, L) == ref_lib.ref_oracle_crc32_sw(d, L) == ob.port().orc_crc32c(d, L), L
         assert ob.ref_packet_header(d, 203, 61) == ob.port_packet_header(d, 203, 61)
+
+
+# ----------------------------------------------------------------- 3b. the reference's own KATs for the 8f rows
+# tests/unit/video/color_filter_test.c and tests/unit/network/crc32_hw_test.c of the reference checkout
+REF_FILTER_COLOURS = {1: (0, 0, 0), 2: (255, 255, 255), 3: (0, 255, 65), 4: (255, 0, 255), 5: (255, 0, 170),
+                      6: (255, 136, 0), 7: (0, 221, 221), 8: (0, 255, 255), 9: (255, 182, 193), 10: (255, 51, 51),
+                      11: (255, 235, 153)}  # color_filter_test.c:197-212 (metadata_colors)
+
+
+def check_color_filter_kats(apply):
+    """apply(img (h,w,3) uint8, filter, time) -> (rc, filtered); shared by the port (here) and the GPU test"""
+    px = np.array([[[0, 0, 0], [255, 255, 255]], [[128, 128, 128], [64, 64, 64]]], np.uint8)
+    rc, out = apply(px, 8, 0.0)                                   # colorize_white_on_color (cyan), :95-128
+    assert rc == 0 and out[0, 0].tolist() == [0, 0, 0] and out[0, 1].tolist() == [0, 255, 255]
+    rc, out = apply(px[:1], 1, 0.0)                               # colorize_black_on_white, :133-152
+    assert rc == 0 and all(v < 50 for v in out[0, 0]) and out[0, 1].tolist() == [255, 255, 255]
+    one = np.array([[[100, 150, 200]]], np.uint8)
+    rc, out = apply(one, 0, 0.0)                                  # apply_none_filter, :157-165
+    assert rc == 0 and (out == one).all()
+    assert apply(one, 999, 0.0)[0] == -1                          # apply_invalid_params, :190-191
+    white = np.full((1, 1, 3), 255, np.uint8)
+    for f, rgb in REF_FILTER_COLOURS.items():                     # a white pixel takes the filter's own colour
+        if f != 1:
+            assert apply(white, f, 0.0)[1][0, 0].tolist() == list(rgb), f
+
+
+def test_kat_color_filter_reference_unit_tests(ob):
+    check_color_filter_kats(ob.port_color_filter)
+    # rgb_to_grayscale_* (:19-48) through a white-on-white filter: out = gray * 255 / 255 = gray
+    for rgb, lo, hi in (((255, 0, 0), 75, 79), ((0, 255, 0), 148, 152), ((0, 0, 255), 27, 31),
+                        ((255, 255, 255), 255, 255), ((0, 0, 0), 0, 0), ((128, 128, 128), 126, 130)):
+        g = int(ob.port_color_filter(np.array([[rgb]], np.uint8), 2, 0.0)[1][0, 0, 0])
+        assert lo <= g <= hi, (rgb, g)
+    assert ob.port().orc_apply_color_filter(None, 1, 1, 3, 3, 0.0) == -1
+    buf = (C.c_uint8 * 3)(255, 255, 255)
+    for w, h, st in ((0, 1, 3), (1, 0, 3), (1, 1, 0)):            # apply_invalid_params, :174-187
+        assert ob.port().orc_apply_color_filter(buf, w, h, st, 3, 0.0) == -1
+
+
+def test_kat_crc32c_reference_unit_tests(ob):
+    crc = lambda b: ob.port().orc_crc32c(b, len(b))  # noqa: E731
+    assert crc(b"") == 0                                          # crc32_hw_test.c:14-21
+    assert crc(b"Hello, World!") == 0x4D551068                    # :32-50, the one literal the reference pins
+    assert crc(b"\x42") != 0 and crc(b"abc") != crc(b"abd") and crc(b"ascii-chat") == crc(b"ascii-chat")
