@@ -278,7 +278,8 @@ static int text_grid_device(const uint8_t *const *d_srcs, const size_t *sizes, i
   // parameter block + scratch in one device allocation of the thread context
   const size_t nl = (size_t)n * p.maxlines;
   const size_t head = al16((uint32_t)(n * sizeof(void *))) + al16((uint32_t)(n * 4));
-  const size_t bytes = head + 4 * al16((uint32_t)(nl * 4)) + 2 * al16((uint32_t)(n * 4)) + al16(total * 4u);
+  const size_t order_bytes = ((size_t)total * 4 + 15) & ~(size_t)15; // 64-bit: total may be close to 2^30
+  const size_t bytes = head + 4 * al16((uint32_t)(nl * 4)) + 2 * al16((uint32_t)(n * 4)) + order_bytes;
   if (!grow_device(&cx->d_scratch, &cx->d_scratch_cap, bytes)) return acb200_last_error();
   cx->scratch_dirty = true; // the render path must re-zero its look-back area before reusing this buffer
   uint8_t *b = cx->d_scratch;
@@ -333,6 +334,8 @@ int acb200_create_grid_device(const uint8_t *const *d_srcs, const size_t *sizes,
                               uint8_t *d_out, size_t *out_size, void *stream) {
   if (!d_srcs || !sizes || n <= 0 || width <= 0 || height <= 0 || !d_out || !out_size)
     return set_error(E_INVALID_PARAM, "acb200_create_grid_device: bad argument");
+  if ((size_t)width * (size_t)height > (size_t)1 << 30) // same bound as ascii_create_grid (ascii.c:616-631 + device sanity)
+    return set_error(E_INVALID_PARAM, "acb200_create_grid_device: dimensions would overflow: %dx%d", width, height);
   ThreadCtx *cx = thread_ctx();
   if (!cx) return acb200_last_error();
   return text_grid_device(d_srcs, sizes, n, width, height, d_out, out_size, stream ? (cudaStream_t)stream : cx->stream,
