@@ -64,6 +64,9 @@ EXPORTS = [  # every symbol include/asciichat_b200.h declares
     "acb200_mixed_frame", "apply_color_filter", "color_filter_calculate_rainbow", "acb200_display_convert",
     "acb200_color_filter_device", "acb200_frame_packets_device", "acb200_mixed_frame_packet",
     "acb200_trailing_reset_fixup_device", "acb200_source_update_wire",
+    "acb200_init_devices", "acb200_device_count", "acb200_device_at", "acb200_bind_thread", "acb200_thread_device",
+    "acb200_set_sync_mode", "acb200_source_acquire", "acb200_source_commit", "acb200_source_device",
+    "acb200_grid_frame",
 ]
 
 
@@ -159,6 +162,18 @@ def lib():
     L.acb200_trailing_reset_fixup_device.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
     L.acb200_mixed_frame_packet.restype = C.c_void_p
     L.acb200_mixed_frame_packet.argtypes = L.acb200_mixed_frame.argtypes
+    L.acb200_init_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
+    L.acb200_device_at.argtypes = [C.c_int]
+    L.acb200_bind_thread.argtypes = [C.c_int]
+    L.acb200_set_sync_mode.restype = None
+    L.acb200_set_sync_mode.argtypes = [C.c_int, C.c_int]
+    L.acb200_source_acquire.restype = C.c_void_p
+    L.acb200_source_acquire.argtypes = [C.c_int, C.c_size_t]
+    L.acb200_source_commit.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.acb200_source_device.argtypes = [C.c_int]
+    L.acb200_grid_frame.restype = C.c_void_p
+    L.acb200_grid_frame.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(terminal_capabilities_t),
+                                    C.c_bool, C.c_bool, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
     _lib = L
     return L
 
@@ -267,6 +282,38 @@ def source_update_wire(slot, payload):
 
 def source_clear(slot):
     return lib().acb200_source_clear(slot)
+
+
+def source_update_pinned(slot, image):
+    """the zero-staging-copy ingest: receive into the slot's pinned buffer, then commit"""
+    a = np.ascontiguousarray(image, dtype=np.uint8)
+    p = lib().acb200_source_acquire(slot, a.nbytes)
+    if not p:
+        return last_error()[0] or -1
+    C.memmove(p, a.ctypes.data, a.nbytes)  # stands in for the transport's recv() into the buffer
+    return lib().acb200_source_commit(slot, a.shape[1], a.shape[0])
+
+
+def init_devices(devices=None):
+    """one process, several GPUs (acb200_init_devices); None = every visible device"""
+    if devices is None:
+        return lib().acb200_init_devices(None, 0)
+    arr = (C.c_int * len(devices))(*devices)
+    return lib().acb200_init_devices(arr, len(devices))
+
+
+def grid_frame(slots, cell_w, cell_h, caps, palette_chars, grid_w, grid_h, use_aspect_ratio=False, stretch=False):
+    """-> (bytes | None, out_size): the discovery host's tick (host.c:664-717) with resident sources"""
+    k = len(slots)
+    arr = (C.c_int * max(k, 1))(*slots)
+    n = C.c_size_t(0)
+    r = lib().acb200_grid_frame(arr, k, cell_w, cell_h, C.byref(caps), use_aspect_ratio, stretch, _pal(palette_chars),
+                                grid_w, grid_h, C.byref(n))
+    if not r:
+        return None, n.value
+    s = C.string_at(r)
+    _libc.free(r)
+    return s, n.value
 
 
 def mixed_frame(slots, width, height, caps, palette_chars):

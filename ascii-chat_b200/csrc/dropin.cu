@@ -294,7 +294,7 @@ void image_resize(const image_t *source, image_t *dest) {
   if (cudaMemcpyAsync(cx->d_in, cx->h_in, in_bytes, cudaMemcpyHostToDevice, cx->stream) != cudaSuccess ||
       launch_resize_nn_only(cx->d_in, sw, sh, cx->d_out, dw, dh, gather ? 1 : 0, cx->stream) != cudaSuccess ||
       cudaMemcpyAsync(cx->h_out, cx->d_out, out_bytes, cudaMemcpyDeviceToHost, cx->stream) != cudaSuccess ||
-      cudaStreamSynchronize(cx->stream) != cudaSuccess) {
+      wait_stream(cx) != E_OK) {
     set_error(E_INVALID_STATE, "image_resize: CUDA failure (%s)", cudaGetErrorString(cudaGetLastError()));
     return;
   }

@@ -118,16 +118,7 @@ __global__ void __launch_bounds__(CF_NT) k_color_filter_rows(uint8_t *pixels, ui
   }
 }
 
-int sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+int sm_count() { return device_sms(); }
 
 int filter_device(uint8_t *d_pixels, uint32_t width, uint32_t height, uint32_t stride, int mode, uint32_t frgb,
                   cudaStream_t st) {
@@ -185,17 +176,22 @@ __host__ __device__ inline uint32_t gf_xpow8(const uint32_t *x2n, uint64_t n_byt
   return p;
 }
 
-std::once_flag g_crc_once;
-cudaError_t g_crc_status = cudaSuccess;
-void crc_tables_init() {
-  std::call_once(g_crc_once, [] {
-    CrcTables t;
-    uint32_t p = 0x40000000u; // x^1
-    t.x2n[0] = p;
-    for (int k = 1; k < 32; k++) t.x2n[k] = p = gf_mul(p, p);
-    for (int k = 0; k < 256; k++) t.seg[k] = gf_xpow8(t.x2n, (uint64_t)CRC_SEG * k);
-    g_crc_status = cudaMemcpyToSymbol(c_crc, &t, sizeof(t));
-  });
+// __constant__ memory is per device: the tables are uploaded once on every device the library runs on
+std::mutex g_crc_mu;
+uint64_t g_crc_done = 0; // bit per CUDA ordinal
+int crc_tables_init() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return E_INVALID_STATE;
+  std::lock_guard<std::mutex> lk(g_crc_mu);
+  if ((g_crc_done >> dev) & 1ull) return E_OK;
+  CrcTables t;
+  uint32_t p = 0x40000000u; // x^1
+  t.x2n[0] = p;
+  for (int k = 1; k < 32; k++) t.x2n[k] = p = gf_mul(p, p);
+  for (int k = 0; k < 256; k++) t.seg[k] = gf_xpow8(t.x2n, (uint64_t)CRC_SEG * k);
+  if (cudaMemcpyToSymbol(c_crc, &t, sizeof(t)) != cudaSuccess) return E_INVALID_STATE;
+  g_crc_done |= 1ull << dev;
+  return E_OK;
 }
 
 __device__ __forceinline__ uint4 ld_stream16(const uint4 *p) { // read once; volatile asm = issued where written
@@ -345,15 +341,18 @@ __global__ void __launch_bounds__(256) k_trailing_reset_fixup(uint8_t *out, size
   if (is_reset(L - 4u)) return; // uniform: every thread reads the same bytes
   if (tid == 0) s_found = -1;
   __syncthreads();
+  int found = -1;
   for (long long hi = (long long)L - 4; hi >= 0; hi -= 256) { // candidate starts hi, hi-1, ... in blocks of 256
     const long long p = hi - tid;
     if (p >= 0 && is_reset((uint32_t)p)) atomicMax(&s_found, (int)p);
     __syncthreads();
-    if (s_found >= 0) break;
+    found = s_found; // every thread reads the block's verdict before anyone can start the next block's atomics
+    __syncthreads();
+    if (found >= 0) break;
   }
-  if (tid == 0 && s_found >= 0) {
-    s[s_found + 4] = 0;
-    out_len[f] = (uint32_t)s_found + 4u;
+  if (tid == 0 && found >= 0) {
+    s[found + 4] = 0;
+    out_len[f] = (uint32_t)found + 4u;
   }
 }
 
@@ -374,8 +373,7 @@ int launch_reset_fixup(uint8_t *d_out, size_t out_pitch, uint32_t *d_out_len, in
 int launch_frame_packets(const uint8_t *d_out, size_t out_pitch, const uint32_t *d_out_len, int n_frames, int max_chunks,
                          uint32_t width, uint32_t height, uint32_t *d_part, uint8_t *headers, size_t header_pitch,
                          uint8_t *copy_dst, size_t copy_pitch, cudaStream_t st) {
-  crc_tables_init();
-  if (g_crc_status != cudaSuccess) return set_error(E_INVALID_STATE, "CUDA: CRC table upload failed");
+  if (crc_tables_init() != E_OK) return set_error(E_INVALID_STATE, "CUDA: CRC table upload failed");
   // measurement knob (never set in production): run the table recurrence on synthetic words, no global loads
   static const int crc_noload = getenv("ACB200_CRC_NOLOAD") ? atoi(getenv("ACB200_CRC_NOLOAD")) : 0;
   for (int f0 = 0; f0 < n_frames; f0 += 65535) { // gridDim.y limit
@@ -458,7 +456,7 @@ int apply_color_filter(uint8_t *pixels, uint32_t width, uint32_t height, uint32_
   if (cudaMemcpyAsync(cx->d_in, cx->h_in, bytes, cudaMemcpyHostToDevice, cx->stream) != cudaSuccess ||
       filter_device(cx->d_in, width, height, stride, mode, rgb, cx->stream) != E_OK ||
       cudaMemcpyAsync(cx->h_in, cx->d_in, bytes, cudaMemcpyDeviceToHost, cx->stream) != cudaSuccess ||
-      cudaStreamSynchronize(cx->stream) != cudaSuccess) {
+      wait_stream(cx) != E_OK) {
     set_error(E_INVALID_STATE, "apply_color_filter: CUDA failure (%s)", cudaGetErrorString(cudaGetLastError()));
     return -1;
   }
@@ -522,9 +520,7 @@ int acb200_frame_packets_device(const uint8_t *d_out, size_t out_pitch, const ui
   const int mc = max_crc_chunks(out_pitch);
   // the chunk CRCs live in this thread's context: work queued on a different stream by the previous call must have
   // drained before they are overwritten (same stream = ordered anyway; cudaFree inside grow_device synchronises)
-  static thread_local cudaStream_t last_stream = nullptr;
-  if (last_stream && last_stream != st) ACB_CUDA(cudaStreamSynchronize(last_stream));
-  last_stream = st;
+  if (sync_foreign(cx, st) != E_OK) return acb200_last_error();
   if (!grow_device((uint8_t **)&cx->d_len, &cx->d_len_cap, (size_t)(16 + (size_t)n_frames * mc) * sizeof(uint32_t)))
     return acb200_last_error();
   return launch_frame_packets(d_out, out_pitch, d_out_len, n_frames, mc, width, height, cx->d_len + 16, d_headers,

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <mutex>
 #include <string>
@@ -47,35 +48,114 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 int option_render_mode() { return g_opt_render_mode.load(); }
 int default_scale() { return g_default_scale.load(); }
 
-// ------------------------------------------------------------------ device / thread context
-static std::once_flag g_dev_once;
-static int g_dev_status = -1;
-static int g_device = -1;
+// ------------------------------------------------------------------ devices / thread contexts
+// One process may drive several GPUs (acb200_init_devices): the reference server is ONE process with a render thread
+// per client (src/server/render.c:340-652), so the device pool lives behind the C ABI — calling threads are leased a
+// context on one device of the pool, round-robin, the first time they call in, and keep it for their lifetime.
+struct DeviceState {
+  int sms = 148;
+  bool in_pool = false;
+  std::mutex mu;                              // pool + LUT cache of this device
+  std::vector<ThreadCtx *> pool;              // warm contexts handed back by exited threads
+  std::map<std::string, GlyphLut *> luts;     // key = which + palette bytes
+  std::vector<GlyphLut *> retired;            // evicted, possibly still referenced by a launch being prepared
+};
+static DeviceState g_ds[kMaxDevices]; // indexed by CUDA ordinal
+static std::mutex g_dev_mu;
+static int g_dev_status = -1;         // -1 not initialised, 0 ready, else the error code
+static int g_pool_devs[kMaxDevices];  // ordinals in use
+static int g_npool = 0;
+static int g_requested_device = -1;   // acb200_init(device) before the first use
+static bool g_peer[kMaxDevices][kMaxDevices];
+static std::atomic<unsigned> g_rr{0};
+static std::atomic<int> g_sync_mode{2}, g_spin_us{30}; // 0 spin (cudaStreamSynchronize), 1 block, 2 hybrid
+
+static int init_pool_locked(const int *devs, int n) { // g_dev_mu held
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return set_error(E_INVALID_STATE, "asciichat_b200: no CUDA device (%s); this library has no CPU path",
+                     e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  int cur = 0;
+  cudaGetDevice(&cur);
+  int list[kMaxDevices], m = 0;
+  if (!devs || n <= 0) {
+    list[m++] = cur;
+  } else {
+    for (int i = 0; i < n && m < kMaxDevices; i++) {
+      if (devs[i] < 0 || devs[i] >= count || devs[i] >= kMaxDevices)
+        return set_error(E_INVALID_PARAM, "asciichat_b200: device %d out of range (%d visible)", devs[i], count);
+      bool dup = false;
+      for (int j = 0; j < m; j++) dup |= list[j] == devs[i];
+      if (!dup) list[m++] = devs[i];
+    }
+  }
+  for (int i = 0; i < m; i++) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, list[i]) != cudaSuccess)
+      return set_error(E_INVALID_STATE, "asciichat_b200: cannot query device %d", list[i]);
+    if (pr.major < 10)
+      return set_error(E_INVALID_STATE, "asciichat_b200: device %s is sm_%d%d; this build is sm_100a only", pr.name,
+                       pr.major, pr.minor);
+    g_ds[list[i]].sms = pr.multiProcessorCount > 0 ? pr.multiProcessorCount : 148;
+  }
+  // peer access between every pair of the pool: a viewer's kernels read the sources of clients resident on other GPUs
+  // straight over NVLink (server.cu), and the grid's cell renders store into the composing GPU's arena
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < m; j++) {
+      const int a = list[i], b = list[j];
+      if (a == b) {
+        g_peer[a][b] = true;
+        continue;
+      }
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) {
+        cudaSetDevice(a);
+        cudaError_t pe = cudaDeviceEnablePeerAccess(b, 0);
+        if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        g_peer[a][b] = pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled;
+      }
+    }
+  cudaSetDevice(cur);
+  for (int i = 0; i < m; i++) {
+    g_pool_devs[i] = list[i];
+    g_ds[list[i]].in_pool = true;
+  }
+  g_npool = m;
+  if (const char *e = getenv("ACB200_SYNC")) { // measurement knob: spin | block | hybrid[:microseconds]
+    if (!strncmp(e, "spin", 4)) g_sync_mode.store(0);
+    else if (!strncmp(e, "block", 5)) g_sync_mode.store(1);
+    else if (!strncmp(e, "hybrid", 6)) {
+      g_sync_mode.store(2);
+      if (e[6] == ':') g_spin_us.store(atoi(e + 7));
+    }
+  }
+  return 0;
+}
 
 int ensure_device() {
-  std::call_once(g_dev_once, [] {
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n <= 0) {
-      g_dev_status = set_error(E_INVALID_STATE, "asciichat_b200: no CUDA device (%s); this library has no CPU path",
-                               e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
-      return;
+  if (g_dev_status != 0) {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (g_dev_status == -1) {
+      if (g_requested_device >= 0) {
+        const int d = g_requested_device;
+        g_dev_status = init_pool_locked(&d, 1);
+      } else {
+        g_dev_status = init_pool_locked(nullptr, 0);
+      }
     }
-    if (g_device >= 0) cudaSetDevice(g_device);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceProp pr;
-    cudaGetDeviceProperties(&pr, dev);
-    if (pr.major < 10) {
-      g_dev_status = set_error(E_INVALID_STATE, "asciichat_b200: device %s is sm_%d%d; this build is sm_100a only",
-                               pr.name, pr.major, pr.minor);
-      return;
-    }
-    g_device = dev;
-    g_dev_status = 0;
-  });
+  }
   if (g_dev_status != 0 && t_err == 0) set_error(E_INVALID_STATE, "asciichat_b200: CUDA device unavailable");
   return g_dev_status;
+}
+
+int device_sms() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? g_ds[dev].sms : 148;
+}
+bool peer_ok(int from_dev, int to_dev) {
+  return from_dev >= 0 && to_dev >= 0 && from_dev < kMaxDevices && to_dev < kMaxDevices && g_peer[from_dev][to_dev];
 }
 
 bool grow_pinned(uint8_t **p, size_t *cap, size_t need) {
@@ -107,63 +187,149 @@ bool grow_device(uint8_t **p, size_t *cap, size_t need) {
 
 // Streams and pinned staging are expensive to create (cudaHostAlloc is a multi-millisecond call), while the
 // reference's callers are threads that come and go with clients.  A thread leases a context on first use and
-// hands it back to a process-wide pool when it exits; a new thread picks up a warm one.
-static std::mutex g_pool_mu;
-static std::vector<ThreadCtx *> g_pool;
-
+// hands it back to its device's pool when it exits; a new thread picks up a warm one.
 struct CtxLease {
   ThreadCtx *c = nullptr;
-  ~CtxLease() {
+  ~CtxLease() { release(); }
+  void release() {
     if (!c) return;
-    std::lock_guard<std::mutex> lk(g_pool_mu);
-    g_pool.push_back(c);
+    DeviceState &ds = g_ds[c->device];
+    std::lock_guard<std::mutex> lk(ds.mu);
+    ds.pool.push_back(c);
+    c = nullptr;
   }
 };
+static thread_local CtxLease t_lease;
+static thread_local int t_bind = -1; // pool index requested by acb200_bind_thread, -1 = round-robin
 
 ThreadCtx *thread_ctx() {
-  static thread_local CtxLease lease;
-  if (lease.c) return lease.c;
+  if (t_lease.c) {
+    int cur = -1;
+    if (g_npool > 1 && (cudaGetDevice(&cur) != cudaSuccess || cur != t_lease.c->device)) cudaSetDevice(t_lease.c->device);
+    return t_lease.c;
+  }
   if (ensure_device() != 0) return nullptr;
-  if (cudaSetDevice(g_device) != cudaSuccess) {
-    set_error(E_INVALID_STATE, "cudaSetDevice(%d) failed", g_device);
+  const int k = t_bind >= 0 ? t_bind % g_npool : (int)(g_rr.fetch_add(1) % (unsigned)g_npool);
+  const int dev = g_pool_devs[k];
+  if (cudaSetDevice(dev) != cudaSuccess) {
+    set_error(E_INVALID_STATE, "cudaSetDevice(%d) failed", dev);
     return nullptr;
   }
+  DeviceState &ds = g_ds[dev];
   {
-    std::lock_guard<std::mutex> lk(g_pool_mu);
-    if (!g_pool.empty()) {
-      lease.c = g_pool.back();
-      g_pool.pop_back();
-      return lease.c;
+    std::lock_guard<std::mutex> lk(ds.mu);
+    if (!ds.pool.empty()) {
+      t_lease.c = ds.pool.back();
+      ds.pool.pop_back();
+      return t_lease.c;
     }
   }
   ThreadCtx *c = new ThreadCtx();
+  c->device = dev;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
     set_error(E_INVALID_STATE, "cannot create CUDA stream");
     return nullptr;
   }
   for (auto &e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDefault);
-  lease.c = c;
+  cudaEventCreateWithFlags(&c->done, cudaEventBlockingSync | cudaEventDisableTiming);
+  t_lease.c = c;
   return c;
 }
 
-static void destroy_ctx_pool() { // acb200_shutdown: contexts still leased by live threads stay with them
-  std::lock_guard<std::mutex> lk(g_pool_mu);
-  for (ThreadCtx *c : g_pool) {
-    if (c->h_in) cudaFreeHost(c->h_in);
-    if (c->h_out) cudaFreeHost(c->h_out);
-    if (c->h_len) cudaFreeHost(c->h_len);
-    if (c->d_in) cudaFree(c->d_in);
-    if (c->d_out) cudaFree(c->d_out);
-    if (c->d_scratch) cudaFree(c->d_scratch);
-    if (c->d_len) cudaFree(c->d_len);
-    if (c->d_frame) cudaFree(c->d_frame);
-    for (auto &e : c->ev)
-      if (e) cudaEventDestroy(e);
-    if (c->stream) cudaStreamDestroy(c->stream);
-    delete c;
+// Waiting for the frame.  cudaStreamSynchronize spins on a host core for the whole GPU + PCIe time of the call; with one
+// caller thread per client (src/server/render.c) those are the cores the staging copies of the other callers need.
+// Default: poll for a few tens of microseconds (a single caller keeps its latency), then sleep on a blocking-sync event.
+int wait_stream(ThreadCtx *cx) {
+  const int mode = g_sync_mode.load(std::memory_order_relaxed);
+  if (mode == 0 || !cx->done) {
+    ACB_CUDA(cudaStreamSynchronize(cx->stream));
+    return E_OK;
   }
-  g_pool.clear();
+  ACB_CUDA(cudaEventRecord(cx->done, cx->stream));
+  if (mode == 2) {
+    const int spin_us = g_spin_us.load(std::memory_order_relaxed);
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (;;) {
+      cudaError_t q = cudaEventQuery(cx->done);
+      if (q == cudaSuccess) return E_OK;
+      if (q != cudaErrorNotReady) return set_error(E_INVALID_STATE, "CUDA: %s (cudaEventQuery)", cudaGetErrorString(q));
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      if ((t1.tv_sec - t0.tv_sec) * 1000000L + (t1.tv_nsec - t0.tv_nsec) / 1000L >= spin_us) break;
+    }
+  }
+  ACB_CUDA(cudaEventSynchronize(cx->done));
+  return E_OK;
+}
+
+// Entry points that take a caller-owned stream still keep their tables in this thread's scratch.  Before that scratch is
+// touched on another stream, whatever the previous caller-owned stream queued on it must have drained.
+int sync_foreign(ThreadCtx *cx, cudaStream_t st) {
+  if (cx->foreign && cx->foreign != st) ACB_CUDA(cudaStreamSynchronize(cx->foreign));
+  cx->foreign = st != cx->stream ? st : nullptr;
+  return E_OK;
+}
+
+PeerHelper *peer_helper(ThreadCtx *cx, int device) {
+  if (device < 0 || device >= kMaxDevices || !g_ds[device].in_pool) {
+    set_error(E_INVALID_PARAM, "device %d is not in the pool", device);
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    set_error(E_INVALID_STATE, "cudaSetDevice(%d) failed", device);
+    return nullptr;
+  }
+  PeerHelper *h = cx->helper[device];
+  if (h) return h;
+  h = new PeerHelper();
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming) != cudaSuccess) {
+    delete h;
+    set_error(E_INVALID_STATE, "cannot create the helper stream on device %d", device);
+    return nullptr;
+  }
+  cx->helper[device] = h;
+  return h;
+}
+
+static void free_ctx(ThreadCtx *c) {
+  for (int d = 0; d < kMaxDevices; d++)
+    if (PeerHelper *h = c->helper[d]) {
+      cudaSetDevice(d);
+      if (h->scratch) cudaFree(h->scratch);
+      if (h->out) cudaFree(h->out);
+      if (h->ev) cudaEventDestroy(h->ev);
+      if (h->stream) cudaStreamDestroy(h->stream);
+      delete h;
+    }
+  cudaSetDevice(c->device);
+  if (c->h_in) cudaFreeHost(c->h_in);
+  if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->h_len) cudaFreeHost(c->h_len);
+  if (c->d_in) cudaFree(c->d_in);
+  if (c->d_out) cudaFree(c->d_out);
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  if (c->d_len) cudaFree(c->d_len);
+  if (c->d_frame) cudaFree(c->d_frame);
+  for (auto &e : c->ev)
+    if (e) cudaEventDestroy(e);
+  if (c->done) cudaEventDestroy(c->done);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  free(c->nn_off);
+  delete c;
+}
+
+static void destroy_ctx_pool() { // acb200_shutdown: contexts still leased by live threads stay with them
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int i = 0; i < g_npool; i++) {
+    DeviceState &ds = g_ds[g_pool_devs[i]];
+    std::lock_guard<std::mutex> lk(ds.mu);
+    for (ThreadCtx *c : ds.pool) free_ctx(c);
+    ds.pool.clear();
+  }
+  cudaSetDevice(cur);
 }
 
 // ------------------------------------------------------------------ glyph LUTs
@@ -207,16 +373,19 @@ static bool build_lut_host(const char *palette, int which, GlyphLut &L) {
   return true;
 }
 
-static std::mutex g_lut_mu;
-static std::map<std::string, GlyphLut *> g_luts; // key = which + palette bytes
-static std::vector<GlyphLut *> g_retired_luts;   // evicted, possibly still referenced by a launch being prepared
-
+// cached per (current device, palette, mapping)
 const GlyphLut *device_lut(const char *palette, int which) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+    set_error(E_INVALID_STATE, "no current CUDA device");
+    return nullptr;
+  }
+  DeviceState &ds = g_ds[dev];
   std::string key(1, (char)('0' + which));
   key += palette;
-  std::lock_guard<std::mutex> lk(g_lut_mu);
-  auto it = g_luts.find(key);
-  if (it != g_luts.end()) return it->second;
+  std::lock_guard<std::mutex> lk(ds.mu);
+  auto it = ds.luts.find(key);
+  if (it != ds.luts.end()) return it->second;
   GlyphLut h;
   if (!build_lut_host(palette, which, h)) {
     set_error(E_INVALID_STATE, "empty palette");
@@ -228,23 +397,34 @@ const GlyphLut *device_lut(const char *palette, int which) {
     set_error(E_MEMORY, "cannot upload glyph LUT");
     return nullptr;
   }
-  if (g_luts.size() >= 2048) { // same bound as the reference's palette cache (common.c:132)
+  if (ds.luts.size() >= 2048) { // same bound as the reference's palette cache (common.c:132)
     // another thread may hold a pointer it has not launched with yet: retire this generation and free the one retired
     // a whole generation (2048 new palettes) ago
-    for (GlyphLut *old : g_retired_luts) cudaFree(old);
-    g_retired_luts.clear();
-    for (auto &kv : g_luts) g_retired_luts.push_back(kv.second);
-    g_luts.clear();
+    for (GlyphLut *old : ds.retired) cudaFree(old);
+    ds.retired.clear();
+    for (auto &kv : ds.luts) ds.retired.push_back(kv.second);
+    ds.luts.clear();
   }
-  g_luts[key] = d;
+  ds.luts[key] = d;
   return d;
 }
+// simd_caches_destroy_all / acb200_shutdown.  A launch that is being prepared on another thread may still hold a LUT
+// pointer, so the tables are RETIRED here (unreachable for new lookups) and freed by the next destroy: the reference's
+// callers tear down after their render threads have stopped (lib/common.c:235), this only keeps a racing call safe.
 void destroy_lut_cache() {
-  std::lock_guard<std::mutex> lk(g_lut_mu);
-  for (auto &kv : g_luts) cudaFree(kv.second);
-  g_luts.clear();
-  for (GlyphLut *old : g_retired_luts) cudaFree(old);
-  g_retired_luts.clear();
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int dev = 0; dev < kMaxDevices; dev++) {
+    DeviceState &ds = g_ds[dev];
+    std::lock_guard<std::mutex> lk(ds.mu);
+    if (ds.luts.empty() && ds.retired.empty()) continue;
+    cudaSetDevice(dev);
+    for (GlyphLut *old : ds.retired) cudaFree(old);
+    ds.retired.clear();
+    for (auto &kv : ds.luts) ds.retired.push_back(kv.second);
+    ds.luts.clear();
+  }
+  cudaSetDevice(cur);
 }
 
 // ------------------------------------------------------------------ client display steps (display.c:484-671)
@@ -384,7 +564,7 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
   return true;
 }
 
-static size_t scratch_bytes(const Plan &pl, int n) {
+size_t scratch_bytes(const Plan &pl, int n) {
   return 256 /* header: tile ticket */ + al256(pl.rows_bytes * n) + al256(pl.meta_bytes * n) +
          al256(pl.cells_bytes * n) + al256(pl.err_bytes * n);
 }
@@ -458,7 +638,8 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
   if (phase_a_only && pl.mode != EM_DITHER_BG) { // downscale only: rows == nullptr makes the kernel return after phase A
     rp.rows = nullptr;
     if (k0) cudaEventRecord(k0, st);
-    ACB_CUDA(launch_render_rows(rp, pl.mode, pl.scale_path >= SP_BOX_TMA ? (int)SP_BOX_STREAM : pl.scale_path, st));
+    rp.direct = 0;
+    ACB_CUDA(launch_render_rows(rp, pl.mode, pl.scale_path >= SP_BOX_TMA ? (int)SP_BOX_STREAM : pl.scale_path, st, nullptr));
     if (k1) cudaEventRecord(k1, st);
     count_launch();
     return E_OK;
@@ -471,8 +652,6 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
   rp.direct = direct ? 1 : 0;
   rp.ticket = reinterpret_cast<int *>(d_scratch);
   const bool uses_ticket = direct || pl.scale_path == SP_BOX_SPLIT;
-  const uint32_t tickets_taken =
-      pl.scale_path == SP_BOX_SPLIT ? 0u /* + grid, added below */ : (uint32_t)n_frames * (uint32_t)pl.text_rows;
   if (ls && uses_ticket) {
     // library-owned scratch (host path): it was zeroed when allocated; instead of clearing per launch, every launch
     // gets a fresh epoch for the look-back records and knows how many tickets its predecessors took
@@ -504,20 +683,21 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
     count_launch();
     if (ls) ls->tickets += (uint32_t)n_frames * (uint32_t)pl.text_rows + grid; // every CTA draws one ticket past the end
   } else if (pl.mode != EM_DITHER_BG) {
-    ACB_CUDA(launch_render_rows(rp, pl.mode, kernel_sp, st));
+    unsigned grid = 0; // direct: persistent CTAs that draw tiles from the ticket, one ticket past the end each
+    ACB_CUDA(launch_render_rows(rp, pl.mode, kernel_sp, st, &grid));
     count_launch();
+    if (ls && direct) ls->tickets += (uint32_t)n_frames * (uint32_t)pl.text_rows + grid;
   } else {
     rp.rows = nullptr;
     rp.cells_out = cells;
     rp.use_smem_out = 0;
-    ACB_CUDA(launch_render_rows(rp, EM_256_FG, kernel_sp, st)); // resize-only pass
+    ACB_CUDA(launch_render_rows(rp, EM_256_FG, kernel_sp, st, nullptr)); // resize-only pass
     ACB_CUDA(cudaMemsetAsync(err, 0, pl.err_bytes * n_frames, st));
     ACB_CUDA(launch_dither_bg(cells, cfg.cols, cfg.rows_px, n_frames, cfg.pad_left, lut, rows, pl.row_pitch, meta, err,
                               st));
     count_launch(2);
   }
   if (k1) cudaEventRecord(k1, st);
-  if (ls && uses_ticket && pl.scale_path != SP_BOX_SPLIT) ls->tickets += tickets_taken;
   if (direct) return E_OK;
 
   StitchParams sp{};
@@ -537,10 +717,69 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
 }
 
 // ------------------------------------------------------------------ host-buffer path
-static inline uint32_t nn_src_row(int y, int src_h, int rows_px) { // image.c:294,300-302
-  uint32_t yr = (uint32_t)((((uint64_t)src_h << 16) / (uint64_t)rows_px) + 1);
-  uint32_t sy = ((uint32_t)y * yr) >> 16;
-  return sy >= (uint32_t)src_h ? (uint32_t)src_h - 1 : sy;
+// Transfer plans for nearest neighbour.  image_resize reads dst_w x dst_h of the src_w x src_h pixels (image.c:293-325:
+// sx = (x * x_ratio) >> 16, sy = (y * y_ratio) >> 16, clamped); which ones is index arithmetic the host can do while
+// it stages the frame, so only those bytes cross PCIe:
+//   NN_PIXELS  the dst_w x dst_h sampled pixels (184 KB of a 24.9 MB 4K frame at 320 x 192); the device then renders a
+//              1:1 image (x_ratio = 65537 -> sx = x), flips already applied by the gather
+//   NN_ROWS    the dst_h sampled rows (2.2 MB): when dst_w >= src_w (nothing to save per row), or ACB200_NN_PLAN=rows
+//   FULL       everything: box filter, or nearest neighbour that upscales in both axes
+enum { PLAN_FULL = 0, PLAN_NN_ROWS = 1, PLAN_NN_PIXELS = 2 };
+
+static inline uint32_t nn_ratio(int src, int dst) { return (uint32_t)((((uint64_t)src << 16) / (uint64_t)dst) + 1); } // image.c:293-294
+static inline uint32_t nn_src_index(int i, uint32_t ratio, int src) { // image.c:300-302, 315-317
+  uint32_t s = ((uint32_t)i * ratio) >> 16;
+  return s >= (uint32_t)src ? (uint32_t)src - 1 : s;
+}
+
+static bool nn_column_table(ThreadCtx *cx, int src_w, int cols, int flip_x) {
+  if (cx->nn_off && cx->nn_src_w == src_w && cx->nn_cols == cols && cx->nn_flip == flip_x) return true;
+  if (cols > cx->nn_off_cap) {
+    free(cx->nn_off);
+    cx->nn_off = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)cols);
+    cx->nn_off_cap = cx->nn_off ? cols : 0;
+    if (!cx->nn_off) {
+      set_error(E_MEMORY, "out of memory for the column table");
+      return false;
+    }
+  }
+  const uint32_t xr = nn_ratio(src_w, cols);
+  for (int x = 0; x < cols; x++) {
+    uint32_t sx = nn_src_index(x, xr, src_w);
+    if (flip_x) sx = (uint32_t)src_w - 1u - sx; // display.c:563-577: the image is mirrored before it is resized
+    cx->nn_off[x] = sx * 3u;
+  }
+  cx->nn_src_w = src_w;
+  cx->nn_cols = cols;
+  cx->nn_flip = flip_x;
+  return true;
+}
+
+// dst receives cols x rows packed RGB24 (+ up to 1 byte of slack: pixels are moved as overlapping 4-byte words)
+static void gather_nn_pixels(const uint8_t *src, int src_w, int src_h, int cols, int rows, bool flip_y,
+                             const uint32_t *off, uint8_t *dst) {
+  const size_t R = (size_t)src_w * 3;
+  const uint32_t yr = nn_ratio(src_h, rows);
+  for (int y = 0; y < rows; y++) {
+    uint32_t sy = nn_src_index(y, yr, src_h);
+    if (flip_y) sy = (uint32_t)src_h - 1u - sy;
+    const uint8_t *row = src + (size_t)sy * R;
+    uint8_t *d = dst + (size_t)y * cols * 3u;
+    if (sy + 1u < (uint32_t)src_h) { // a 4-byte read of the row's last pixel stays inside the image
+      for (int x = 0; x < cols; x++) {
+        uint32_t v;
+        memcpy(&v, row + off[x], 4);
+        memcpy(d + 3 * x, &v, 4);
+      }
+    } else {
+      for (int x = 0; x < cols; x++) {
+        const uint8_t *q = row + off[x];
+        d[3 * x] = q[0];
+        d[3 * x + 1] = q[1];
+        d[3 * x + 2] = q[2];
+      }
+    }
+  }
 }
 
 static bool is_pinned(const void *p) {
@@ -554,27 +793,47 @@ static bool is_pinned(const void *p) {
 
 static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t *const *frames, int n_frames,
                                   char **out, size_t *out_len) {
-  Plan pl;
-  if (!make_plan(cfg, pl)) return t_err;
+  Plan pl0;
+  if (!make_plan(cfg, pl0)) return t_err; // validates the caller's configuration as given
+  if (n_frames <= 0) return E_OK;         // an empty batch is legal
   ThreadCtx *cx = thread_ctx();
   if (!cx) return t_err;
   const size_t R = (size_t)cfg.src_w * 3;
-  // nearest neighbour reads rows_px of the src_h rows: move only those (row-granular transfer plan);
-  // the box filter reads every row.
-  const bool gather = cfg.scale == ACB200_SCALE_NN && cfg.rows_px < cfg.src_h;
-  const bool gather_flip_y = cfg.flip_y && cfg.src_w > 1 && cfg.src_h > 1; // display.c:548,580-590
-  const size_t in_per_frame = gather ? R * cfg.rows_px : R * cfg.src_h;
+  static const char *plan_env = getenv("ACB200_NN_PLAN"); // measurement knob: "rows" = the row-granular plan only
+  const bool rows_only = plan_env && !strcmp(plan_env, "rows");
+  const bool flips = (cfg.flip_x || cfg.flip_y) && cfg.src_w > 1 && cfg.src_h > 1; // display.c:548
+  const bool flip_x = flips && cfg.flip_x, flip_y = flips && cfg.flip_y;
+  int tplan = PLAN_FULL;
+  if (cfg.scale == ACB200_SCALE_NN) {
+    if (cfg.cols < cfg.src_w && !rows_only) tplan = PLAN_NN_PIXELS;
+    else if (cfg.rows_px < cfg.src_h) tplan = PLAN_NN_ROWS;
+  }
+  // what the device sees: the gathered image at 1:1 (NN_PIXELS), else the caller's geometry
+  acb200_render_cfg_t dcfg = cfg;
+  Plan pl = pl0;
+  if (tplan == PLAN_NN_PIXELS) {
+    dcfg.src_w = cfg.cols;
+    dcfg.src_h = cfg.rows_px;
+    dcfg.flip_x = dcfg.flip_y = 0;
+    if (!make_plan(dcfg, pl)) return t_err;
+    if (!nn_column_table(cx, cfg.src_w, cfg.cols, flip_x ? 1 : 0)) return t_err;
+  }
+  const size_t in_per_frame = tplan == PLAN_NN_PIXELS ? (size_t)cfg.cols * cfg.rows_px * 3
+                              : tplan == PLAN_NN_ROWS ? R * cfg.rows_px
+                                                      : R * cfg.src_h;
+  const size_t in_pitch = al256(in_per_frame + 4); // + slack for the gather's overlapping word stores
   const size_t cap = pl.frame_capacity;
-  int chunk = (int)((size_t)(64u << 20) / (in_per_frame + cap));
+  int chunk = (int)((size_t)(64u << 20) / (in_pitch + cap));
   if (chunk < 1) chunk = 1;
   if (chunk > n_frames) chunk = n_frames;
   const int nchunks = (n_frames + chunk - 1) / chunk;
   const int nslot = nchunks > 1 ? 2 : 1; // two slots: the host drains chunk k-1 while the GPU works on chunk k
-  const size_t in_slot = al256(in_per_frame * chunk), out_slot = al256(cap * chunk), len_slot = al256(4u * chunk);
+  const size_t in_slot = in_pitch * chunk, out_slot = al256(cap * chunk), len_slot = al256(4u * chunk);
   for (int i = 0; i < n_frames; i++) out[i] = nullptr;
-  bool need_stage = gather;
+  bool need_stage = tplan != PLAN_FULL;
   for (int i = 0; i < n_frames && !need_stage; i++) need_stage = frames[i] && !is_pinned(frames[i]);
   const size_t scratch_cap_before = cx->d_scratch_cap; // a regrown buffer may come back at the same address
+  if (sync_foreign(cx, cx->stream) != E_OK) return t_err;
   if (!grow_device(&cx->d_in, &cx->d_in_cap, in_slot * nslot) ||
       !grow_device(&cx->d_scratch, &cx->d_scratch_cap, scratch_bytes(pl, chunk)) ||
       !grow_pinned(&cx->h_out, &cx->h_out_cap, out_slot * nslot) ||
@@ -593,35 +852,41 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
     }
   }
 
-  // The stitch kernel writes the finished strings and their lengths straight into mapped pinned host memory
-  // (UVA: the host pointer is the device pointer), so a chunk costs one event wait, no D2H memcpy calls.
+  // The emitters write the finished strings and their lengths straight into mapped pinned host memory
+  // (UVA: the host pointer is the device pointer), so a chunk costs one wait, no D2H memcpy calls.
   auto issue = [&](int k) -> int {
     const int slot = k & 1, f0 = k * chunk;
     const int n = (n_frames - f0 < chunk) ? n_frames - f0 : chunk;
     uint8_t *d_in = cx->d_in + (size_t)slot * in_slot;
     uint8_t *st_base = need_stage ? cx->h_in + (size_t)slot * in_slot : nullptr;
+    // gathered frames are small: the whole chunk goes up as one H2D.  Full frames go up one by one, so that the staging
+    // copy of frame i+1 overlaps the DMA of frame i.
+    const bool all_staged = tplan != PLAN_FULL;
     for (int i = 0; i < n; i++) {
       const uint8_t *src = frames[f0 + i];
       if (!src) return set_error(E_INVALID_PARAM, "frame %d is NULL", f0 + i);
-      uint8_t *dst = d_in + (size_t)i * in_per_frame;
-      if (gather) {
-        uint8_t *st = st_base + (size_t)i * in_per_frame;
+      uint8_t *dst = d_in + (size_t)i * in_pitch;
+      uint8_t *st = st_base ? st_base + (size_t)i * in_pitch : nullptr;
+      if (tplan == PLAN_NN_PIXELS) {
+        gather_nn_pixels(src, cfg.src_w, cfg.src_h, cfg.cols, cfg.rows_px, flip_y, cx->nn_off, st);
+      } else if (tplan == PLAN_NN_ROWS) {
+        const uint32_t yr = nn_ratio(cfg.src_h, cfg.rows_px);
         for (int y = 0; y < cfg.rows_px; y++) {
-          uint32_t sy = nn_src_row(y, cfg.src_h, cfg.rows_px);
-          if (gather_flip_y) sy = (uint32_t)cfg.src_h - 1u - sy;
+          uint32_t sy = nn_src_index(y, yr, cfg.src_h);
+          if (flip_y) sy = (uint32_t)cfg.src_h - 1u - sy;
           memcpy(st + (size_t)y * R, src + (size_t)sy * R, R);
         }
-        ACB_CUDA(cudaMemcpyAsync(dst, st, in_per_frame, cudaMemcpyHostToDevice, cx->stream));
       } else if (is_pinned(src)) {
         ACB_CUDA(cudaMemcpyAsync(dst, src, in_per_frame, cudaMemcpyHostToDevice, cx->stream));
       } else {
-        uint8_t *st = st_base + (size_t)i * in_per_frame;
         memcpy(st, src, in_per_frame);
         ACB_CUDA(cudaMemcpyAsync(dst, st, in_per_frame, cudaMemcpyHostToDevice, cx->stream));
       }
     }
-    int rc = render_device(cfg, pl, d_in, in_per_frame, gather ? 1 : 0, n, cx->h_out + (size_t)slot * out_slot, cap,
-                           reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(cx->h_len) + (size_t)slot * len_slot),
+    if (all_staged)
+      ACB_CUDA(cudaMemcpyAsync(d_in, st_base, (size_t)(n - 1) * in_pitch + in_per_frame, cudaMemcpyHostToDevice, cx->stream));
+    int rc = render_device(dcfg, pl, d_in, in_pitch, tplan == PLAN_NN_ROWS ? 1 : 0, n, cx->h_out + (size_t)slot * out_slot,
+                           cap, reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(cx->h_len) + (size_t)slot * len_slot),
                            cx->d_scratch, cx->stream, nullptr, nullptr, &cx->lb);
     if (rc) return rc;
     if (nchunks > 1) ACB_CUDA(cudaEventRecord(cx->ev[2 + slot], cx->stream)); // single chunk: collect() waits on the stream
@@ -631,7 +896,7 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
     const int slot = k & 1, f0 = k * chunk;
     const int n = (n_frames - f0 < chunk) ? n_frames - f0 : chunk;
     if (nchunks > 1) ACB_CUDA(cudaEventSynchronize(cx->ev[2 + slot]));
-    else ACB_CUDA(cudaStreamSynchronize(cx->stream));
+    else if (wait_stream(cx) != E_OK) return t_err;
     const uint32_t *lens =
         reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(cx->h_len) + (size_t)slot * len_slot);
     const uint8_t *arena = cx->h_out + (size_t)slot * out_slot;
@@ -664,6 +929,7 @@ char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, si
   if (!cx) return nullptr;
   const size_t scratch_cap_before = cx->d_scratch_cap; // a regrown buffer may come back at the same address
   const int mc = max_crc_chunks(pl.frame_capacity);
+  if (sync_foreign(cx, cx->stream) != E_OK) return nullptr;
   if (!grow_device(&cx->d_scratch, &cx->d_scratch_cap, scratch_bytes(pl, 1)) ||
       !grow_pinned(&cx->h_out, &cx->h_out_cap, pl.frame_capacity + 32) ||
       !grow_pinned((uint8_t **)&cx->h_len, &cx->h_len_cap, 256))
@@ -696,7 +962,7 @@ char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, si
   if (opts.packet && launch_frame_packets(arena, pl.frame_capacity, lens, 1, mc, opts.pk_w, opts.pk_h, d_words + 16,
                                           cx->h_out + 8, 24, cx->h_out + 32, 0, cx->stream) != E_OK)
     return nullptr;
-  if (cudaStreamSynchronize(cx->stream) != cudaSuccess) {
+  if (wait_stream(cx) != E_OK) {
     set_error(E_INVALID_STATE, "CUDA failure while rendering a resident frame");
     return nullptr;
   }
@@ -739,9 +1005,53 @@ using namespace acb;
 extern "C" {
 
 int acb200_init(int device) {
-  if (device >= 0 && g_dev_status == -1) g_device = device;
+  {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (device >= 0 && g_dev_status == -1) g_requested_device = device;
+  }
   if (ensure_device() != 0) return t_err ? t_err : E_INVALID_STATE;
   return thread_ctx() ? E_OK : t_err;
+}
+// One process, several GPUs: the pool calling threads are spread over.  devices == NULL / n <= 0: every visible device.
+int acb200_init_devices(const int *devices, int n) {
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (g_dev_status == 0) return set_error(E_INVALID_STATE, "acb200_init_devices: the library is already initialised");
+  int all[kMaxDevices], count = 0;
+  if (!devices || n <= 0) {
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+      return g_dev_status = set_error(E_INVALID_STATE, "asciichat_b200: no CUDA device; this library has no CPU path");
+    if (count > kMaxDevices) count = kMaxDevices;
+    for (int i = 0; i < count; i++) all[i] = i;
+    devices = all;
+    n = count;
+  }
+  g_dev_status = init_pool_locked(devices, n);
+  return g_dev_status;
+}
+int acb200_device_count(void) { return g_dev_status == 0 ? g_npool : 0; }
+int acb200_device_at(int k) { return (g_dev_status == 0 && k >= 0 && k < g_npool) ? g_pool_devs[k] : -1; }
+// Pin the calling thread to the k-th device of the pool (k < 0: back to round-robin).  A context the thread already
+// holds on another device goes back to that device's pool.
+int acb200_bind_thread(int k) {
+  if (ensure_device() != 0) return t_err;
+  if (k >= g_npool) return set_error(E_INVALID_PARAM, "acb200_bind_thread: %d >= %d devices", k, g_npool);
+  t_bind = k;
+  if (t_lease.c && k >= 0 && t_lease.c->device != g_pool_devs[k]) {
+    cudaSetDevice(t_lease.c->device);
+    cudaStreamSynchronize(t_lease.c->stream);
+    t_lease.release();
+  }
+  return thread_ctx() ? E_OK : t_err;
+}
+int acb200_thread_device(void) {
+  ThreadCtx *cx = thread_ctx();
+  return cx ? cx->device : -1;
+}
+// how a caller waits for its frame: 0 spin (cudaStreamSynchronize), 1 sleep on a blocking-sync event, 2 poll for spin_us
+// microseconds, then sleep (default, 30 us)
+void acb200_set_sync_mode(int mode, int spin_us) {
+  if (mode >= 0 && mode <= 2) g_sync_mode.store(mode);
+  if (spin_us >= 0) g_spin_us.store(spin_us);
 }
 void acb200_shutdown(void) {
   destroy_sources();
@@ -794,8 +1104,7 @@ int acb200_render_batch_device(const acb200_render_cfg_t *cfg, const uint8_t *d_
 int acb200_synchronize(void) {
   ThreadCtx *cx = thread_ctx();
   if (!cx) return t_err;
-  ACB_CUDA(cudaStreamSynchronize(cx->stream));
-  return E_OK;
+  return wait_stream(cx);
 }
 
 int acb200_render_batch_host(const acb200_render_cfg_t *cfg, const uint8_t *const *frames, int n_frames, char **out,

@@ -34,8 +34,22 @@ struct LookbackState {
   uint32_t epoch = 0, tickets = 0;
 };
 
-// per-thread stream + growable staging buffers
+constexpr int kMaxDevices = 64; // CUDA ordinals this library can address
+
+// what a thread context keeps on ANOTHER device of the pool, for work it farms out there (acb200_grid_frame renders
+// every client's cell on the GPU that holds the client's frames)
+struct PeerHelper {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev = nullptr;
+  uint8_t *scratch = nullptr; size_t scratch_cap = 0;
+  uint8_t *out = nullptr;     size_t out_cap = 0;   // staging arena when the composing GPU is not peer-accessible
+  LookbackState lb;
+  bool dirty = true;
+};
+
+// per-thread stream + growable staging buffers; bound to ONE device of the pool for its whole life
 struct ThreadCtx {
+  int device = 0;            // CUDA ordinal this context lives on
   LookbackState lb;
   bool scratch_dirty = true; // d_scratch holds something other than zeros / look-back records
   cudaStream_t stream = nullptr;
@@ -48,8 +62,21 @@ struct ThreadCtx {
   uint8_t *d_frame = nullptr; size_t d_frame_cap = 0; // one-frame packet path: device arena + length + CRC chunk words
   uint32_t *h_len = nullptr; size_t h_len_cap = 0;  // pinned
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t done = nullptr;   // cudaEventBlockingSync: the waiting caller sleeps instead of spinning (wait_stream)
+  cudaStream_t foreign = nullptr; // last caller-owned stream that used d_scratch / d_len (ordered by sync_foreign)
+  // nearest-neighbour transfer plan (host side of image.c:293-325): byte offset of the source column each output
+  // column samples, cached per (src_w, cols, flip_x)
+  uint32_t *nn_off = nullptr; int nn_off_cap = 0, nn_src_w = 0, nn_cols = 0, nn_flip = -1;
+  PeerHelper *helper[kMaxDevices] = {};
 };
-ThreadCtx *thread_ctx(); // nullptr => error set
+PeerHelper *peer_helper(ThreadCtx *cx, int device); // lazily created; makes `device` current.  nullptr => error set
+ThreadCtx *thread_ctx(); // nullptr => error set.  Leases a context on this thread's device and makes that device current
+// wait until everything queued on cx->stream has finished: short query spin, then a blocking (sleeping) wait
+int wait_stream(ThreadCtx *cx);
+// d_scratch / d_len are about to be used on `st`: first drain the caller-owned stream that used them last, if different
+int sync_foreign(ThreadCtx *cx, cudaStream_t st);
+int device_sms();                  // SM count of the current device
+bool peer_ok(int from_dev, int to_dev); // kernels running on from_dev may dereference pointers of to_dev
 bool grow_pinned(uint8_t **p, size_t *cap, size_t need);
 bool grow_device(uint8_t **p, size_t *cap, size_t need);
 
@@ -82,6 +109,12 @@ struct OneFrameOpts {
 };
 char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, size_t *out_len,
                         const OneFrameOpts &opts = OneFrameOpts());
+
+// grid.cu: ascii_create_grid on device-resident sources (sizes on the host, or d_sizes[i] + size_bias on the device)
+int text_grid_device(const uint8_t *const *d_srcs, const size_t *sizes, int n, int width, int height, uint8_t *d_out,
+                     size_t *out_size, cudaStream_t st, ThreadCtx *cx, const uint32_t *d_sizes, uint32_t size_bias,
+                     bool *size_is_exact); // *size_is_exact: report *out_size as is (else the caller reports strlen)
+size_t scratch_bytes(const Plan &pl, int n);
 
 // effects.cu
 int max_crc_chunks(size_t frame_capacity);

@@ -22,6 +22,8 @@ struct TextGridParams {
   const uint32_t *size;      // [n]                     }
   const uint8_t *src_in[TG_INLINE]; // the same tables inline (n <= TG_INLINE): no upload, no lifetime to manage
   uint32_t size_in[TG_INLINE];
+  const uint32_t *size_dev;  // optional: lengths still on the device (written by the render kernels), + size_bias each
+  uint32_t size_bias;
   int n, W, H;
   int gcols, grows, cw, ch;  // layout (multi-source path)
   int single;                // n == 1: centre the lone frame (ascii.c:610-707)
@@ -66,6 +68,7 @@ __device__ __forceinline__ const uint8_t *tg_src(const TextGridParams &p, int s)
   return p.n <= TG_INLINE ? p.src_in[s] : p.src[s];
 }
 __device__ __forceinline__ uint32_t tg_size(const TextGridParams &p, int s) {
+  if (p.size_dev) return p.size_dev[s] + p.size_bias;
   return p.n <= TG_INLINE ? p.size_in[s] : p.size[s];
 }
 __device__ __forceinline__ uint32_t tg_line_id(const TextGridParams &p, int s, int r) { // 1-based, reference order
@@ -249,10 +252,17 @@ static void text_grid_layout(int n, int width, int height, int *cols, int *rows,
   *ch = (height - (best_rows - 1)) / best_rows;
 }
 
-static int text_grid_device(const uint8_t *const *d_srcs, const size_t *sizes, int n, int width, int height,
-                            uint8_t *d_out, size_t *out_size, cudaStream_t st, ThreadCtx *cx) {
+// sizes: host lengths — or nullptr with d_sizes = device-resident lengths (each + size_bias), which saves the read-back
+// between the render and the grid (acb200_grid_frame)
+int text_grid_device(const uint8_t *const *d_srcs, const size_t *sizes, int n, int width, int height, uint8_t *d_out,
+                     size_t *out_size, cudaStream_t st, ThreadCtx *cx, const uint32_t *d_sizes, uint32_t size_bias,
+                     bool *size_is_exact) {
+  if (size_is_exact) *size_is_exact = n == 1; // ascii.c:650,705: the single-source path reports the canvas size
   const uint32_t total = (uint32_t)((size_t)width * height + height + 1);
+  if (d_sizes && n > TG_INLINE) return set_error(E_INVALID_PARAM, "device-resident sizes: at most %d sources", TG_INLINE);
   TextGridParams p{};
+  p.size_dev = d_sizes;
+  p.size_bias = size_bias;
   p.n = n;
   p.W = width;
   p.H = height;
@@ -267,10 +277,18 @@ static int text_grid_device(const uint8_t *const *d_srcs, const size_t *sizes, i
   } else {
     text_grid_layout(n, width, height, &p.gcols, &p.grows, &p.cw, &p.ch);
     if (p.cw < 10 || p.ch < 3) { // too small for a grid: first source as-is (ascii.c:778-792)
-      if (d_srcs[0] && sizes[0] > 0) ACB_CUDA(cudaMemcpyAsync(d_out, d_srcs[0], sizes[0], cudaMemcpyDeviceToDevice, st));
-      const size_t z = (d_srcs[0] && sizes[0] > 0) ? sizes[0] : 0;
+      size_t z0 = sizes ? sizes[0] : 0;
+      if (d_sizes) { // rare path: fetch the one length that decides the copy
+        uint32_t v = 0;
+        ACB_CUDA(cudaMemcpyAsync(&v, d_sizes, sizeof(v), cudaMemcpyDeviceToHost, st));
+        ACB_CUDA(cudaStreamSynchronize(st));
+        z0 = (size_t)v + size_bias;
+      }
+      if (d_srcs[0] && z0 > 0) ACB_CUDA(cudaMemcpyAsync(d_out, d_srcs[0], z0, cudaMemcpyDeviceToDevice, st));
+      const size_t z = (d_srcs[0] && z0 > 0) ? z0 : 0;
       ACB_CUDA(cudaMemsetAsync(d_out + z, 0, 1, st));
       *out_size = z;
+      if (size_is_exact) *size_is_exact = true; // ascii.c:785: frame_size as given
       return E_OK;
     }
     p.maxlines = p.ch;
@@ -280,13 +298,17 @@ static int text_grid_device(const uint8_t *const *d_srcs, const size_t *sizes, i
   const size_t head = al16((uint32_t)(n * sizeof(void *))) + al16((uint32_t)(n * 4));
   const size_t order_bytes = ((size_t)total * 4 + 15) & ~(size_t)15; // 64-bit: total may be close to 2^30
   const size_t bytes = head + 4 * al16((uint32_t)(nl * 4)) + 2 * al16((uint32_t)(n * 4)) + order_bytes;
+  // the tables live in this thread's scratch: drain whatever another (caller-owned) stream still has queued on it, and
+  // remember `st` so that the render path does the same before it re-zeroes the buffer on the internal stream
+  if (sync_foreign(cx, st) != E_OK) return acb200_last_error();
+  if (st != cx->stream) ACB_CUDA(cudaStreamSynchronize(cx->stream));
   if (!grow_device(&cx->d_scratch, &cx->d_scratch_cap, bytes)) return acb200_last_error();
   cx->scratch_dirty = true; // the render path must re-zero its look-back area before reusing this buffer
   uint8_t *b = cx->d_scratch;
   if (n <= TG_INLINE) { // tables ride in the kernel parameters
     for (int i = 0; i < n; i++) {
       p.src_in[i] = d_srcs[i];
-      p.size_in[i] = d_srcs[i] ? (uint32_t)sizes[i] : 0u;
+      p.size_in[i] = (d_srcs[i] && sizes) ? (uint32_t)sizes[i] : 0u;
     }
   } else {
     std::vector<uint8_t> h(head);
@@ -339,7 +361,7 @@ int acb200_create_grid_device(const uint8_t *const *d_srcs, const size_t *sizes,
   ThreadCtx *cx = thread_ctx();
   if (!cx) return acb200_last_error();
   return text_grid_device(d_srcs, sizes, n, width, height, d_out, out_size, stream ? (cudaStream_t)stream : cx->stream,
-                          cx);
+                          cx, nullptr, 0, nullptr);
 }
 
 // lib/video/ascii/ascii.c:602-885
@@ -375,10 +397,11 @@ char *ascii_create_grid(ascii_frame_source_t *sources, int source_count, int wid
     o += (z + 15) & ~(size_t)15;
   }
   size_t res = 0;
+  bool exact = false;
   if ((in_total && cudaMemcpyAsync(cx->d_in, cx->h_in, in_total, cudaMemcpyHostToDevice, cx->stream) != cudaSuccess) ||
-      text_grid_device(dptr.data(), sizes.data(), n, width, height, cx->d_out, &res, cx->stream, cx) != E_OK ||
+      text_grid_device(dptr.data(), sizes.data(), n, width, height, cx->d_out, &res, cx->stream, cx, nullptr, 0, &exact) != E_OK ||
       cudaMemcpyAsync(cx->h_out, cx->d_out, res + 1, cudaMemcpyDeviceToHost, cx->stream) != cudaSuccess ||
-      cudaStreamSynchronize(cx->stream) != cudaSuccess) {
+      wait_stream(cx) != E_OK) {
     if (!acb200_last_error()) set_error(E_INVALID_STATE, "ascii_create_grid: CUDA failure");
     return nullptr;
   }
@@ -387,7 +410,7 @@ char *ascii_create_grid(ascii_frame_source_t *sources, int source_count, int wid
   memcpy(r, cx->h_out, res + 1);
   r[res] = '\0';
   // single-source path reports the canvas size (ascii.c:650,705); the multi-source path reports strlen (ascii.c:883)
-  *out_size = (n == 1) ? res : strlen(r);
+  *out_size = exact ? res : strlen(r);
   return r;
 }
 
@@ -514,7 +537,7 @@ int acb200_composite_host(const uint8_t *const *srcs, const int *ws, const int *
     count_launch();
   }
   ACB_CUDA(cudaMemcpyAsync(cx->h_out, cx->d_out, comp_bytes, cudaMemcpyDeviceToHost, cx->stream));
-  ACB_CUDA(cudaStreamSynchronize(cx->stream));
+  if (wait_stream(cx) != E_OK) return acb200_last_error();
   memcpy(out_rgb, cx->h_out, comp_bytes);
   return E_OK;
 }

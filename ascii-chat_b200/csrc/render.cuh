@@ -111,7 +111,8 @@ uint32_t row_capacity_bytes(int mode, int cols, int pad_left);
 static constexpr int kSmemOutMax = 48 * 1024;      // rows up to this many bytes are staged in shared memory
 static constexpr uint32_t kMaxDynSmem = 224u * 1024u; // dynamic smem ceiling (227 KB opt-in minus static, incl. the 1 KB digit table)
 
-cudaError_t launch_render_rows(const RenderParams &p, int mode, int scale_path, cudaStream_t st);
+// *grid_out (optional) = CTAs launched; with p.direct the kernel is persistent and every CTA draws one ticket past the end
+cudaError_t launch_render_rows(const RenderParams &p, int mode, int scale_path, cudaStream_t st, unsigned *grid_out);
 cudaError_t launch_render_rows_ws(const RenderParams &p, int mode, cudaStream_t st);
 cudaError_t launch_render_rows_ws2(const RenderParams &p, int mode, cudaStream_t st, unsigned *grid_out);
 size_t ws2_smem_total(int mode, int cols, int src_w, uint32_t row_pitch);

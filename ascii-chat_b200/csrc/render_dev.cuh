@@ -1,6 +1,7 @@
 // render_dev.cuh — device code of the row kernels (templates), shared by the per-mode instantiation units
 // (rk_mode*.cu) and render_kernels.cu.  See render_kernels.cu for the overview.
 #pragma once
+#include <atomic>
 #include <cstdlib>
 
 #include "render.cuh"
@@ -305,6 +306,18 @@ __host__ __device__ inline Layout make_layout(int mode, int sp, int cols, int sr
 __device__ __forceinline__ uint32_t load_px(const uint8_t *p) {
   return ((uint32_t)p[0] << 16) | ((uint32_t)p[1] << 8) | (uint32_t)p[2];
 }
+// The same pixel out of aligned 32-bit words: one load when the three bytes sit inside a word, two when they straddle
+// it (never a read past the pixel's last byte's word), then a funnel shift and a byte swap — instead of three dependent
+// byte loads per sample.  Adjacent samples of a 1:1 (pre-gathered) image share their words, so a warp's loads coalesce.
+__device__ __forceinline__ uint32_t load_px_w(const uint8_t *p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t sh = (uint32_t)(a & 3u);
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(a - sh);
+  const uint32_t w0 = __ldg(w);
+  const uint32_t w1 = sh >= 2u ? __ldg(w + 1) : 0u;
+  const uint32_t v = __funnelshift_r(w0, w1, sh * 8u); // bytes r,g,b in memory order: r | g<<8 | b<<16
+  return __byte_perm(v, 0u, 0x4012);                   // -> 0x00RRGGBB
+}
 
 // apply_color_filter on one pixel (color_filter.c:238-267, 305-318, 338-341; rgb_to_grayscale color_filter.h:172).
 // A pointwise map commutes with nearest-neighbour sampling, so the reference's whole-image pre-pass
@@ -340,7 +353,7 @@ __device__ __forceinline__ void cells_nn(const RenderParams &p, const uint8_t *f
     uint32_t sx = ((uint32_t)x * xr) >> 16;
     if (sx >= (uint32_t)p.src_w) sx = (uint32_t)p.src_w - 1;
     if (p.flip_x) sx = (uint32_t)p.src_w - 1u - sx;
-    out[x] = filter_px(load_px(row + (size_t)sx * 3u), p.filt_mode, p.filt_rgb);
+    out[x] = filter_px(load_px_w(row + (size_t)sx * 3u), p.filt_mode, p.filt_rgb);
   }
 }
 
@@ -916,6 +929,12 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
 }
 
 // Emission-bound variants (NN sampling) want occupancy: eight 256-thread CTAs per SM = 32 registers per thread.
+//
+// Scratch-row output (p.direct == 0): one CTA per (frame, text row), tile = blockIdx.x.
+// Direct output (p.direct == 1): PERSISTENT CTAs (grid = resident CTAs, launch_rows_t) that draw tiles from the atomic
+// ticket until it runs past the end — the glyph LUT copy and the decimal table are built once per CTA lifetime, not once
+// per text row, and the next tile's ticket is requested while the current one is being emitted.  Whoever holds tile X
+// knows every tile < X is held by a running CTA, so the look-back spin cannot deadlock.
 template <int MODE, int SP, int NT>
 __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) : 1) k_render_rows(const RenderParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -926,18 +945,10 @@ __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) :
   constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
 
   const int tid = threadIdx.x;
-  __shared__ int s_tile;
+  __shared__ int s_tile[2];
   __shared__ uint32_t s_lb[2];
-  // direct output: rows find their place by look-back over earlier tiles, so tiles are taken from an atomic ticket
-  // (every lower tile is then known to be held by a running CTA); scratch-row output keeps the plain blockIdx mapping
-  if (p.direct) {
-    if (tid == 0) s_tile = (int)((uint32_t)atomicAdd(p.ticket, 1) - p.ticket_base);
-    __syncthreads();
-  }
-  const unsigned tile = p.direct ? (unsigned)s_tile : blockIdx.x;
-  const int t = (int)(tile % (unsigned)p.text_rows);
-  const int f = (int)(tile / (unsigned)p.text_rows);
   const int w = p.cols;
+  const unsigned total = (unsigned)p.n_frames * (unsigned)p.text_rows;
 
   const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
   const Layout L = make_layout(MODE, SP, w, p.src_w, cap, p.tune_flags & 1);
@@ -951,58 +962,72 @@ __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) :
   uint16_t *V = reinterpret_cast<uint16_t *>(smem + L.V);
   uint8_t *outb = smem + L.outb;
 
+  if (p.direct && tid == 0) s_tile[0] = (int)((uint32_t)atomicAdd(p.ticket, 1) - p.ticket_base);
   if (USES_LUT) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
     uint32_t *dst = reinterpret_cast<uint32_t *>(lut);
     for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += NT) dst[i] = src[i];
   }
   init_dec3<NT>(tid);
-
-  // ---- phase A
-  const uint8_t *frame = p.frames + (size_t)f * p.frame_stride;
-  const int yT = HB ? 2 * t : t;
-  const bool hasB = HB && (2 * t + 1 < p.rows_px);
-  if (SP == SP_NN) {
-    cells_nn<NT>(p, frame, yT, cT);
-    if (hasB) cells_nn<NT>(p, frame, yT + 1, cB);
-  } else if (SP == SP_BOX_GENERIC) {
-    cells_box_generic<NT>(p, frame, yT, cT);
-    if (hasB) cells_box_generic<NT>(p, frame, yT + 1, cB);
-  } else {
-#pragma unroll 1
-    for (int hrow = 0; hrow < (hasB ? 2 : 1); hrow++) cells_box_stream<NT>(p, frame, yT + hrow, hrow ? cB : cT, V);
-  }
   __syncthreads();
-  if (HB && !hasB) { // odd pixel height: bottom := top (halfblock.c:73,82-88)
-    for (int x = tid; x < w; x += NT) cB[x] = cT[x];
+
+#pragma unroll 1
+  for (int it = 0;; it++) {
+    const unsigned tile = p.direct ? (unsigned)s_tile[it & 1] : blockIdx.x;
+    if (tile >= total) return;
+    // prefetch the next ticket: its round trip overlaps this tile's loads (the slot it lands in was last read one
+    // iteration ago, and every thread has passed several barriers since)
+    if (p.direct && tid == 0) s_tile[(it + 1) & 1] = (int)((uint32_t)atomicAdd(p.ticket, 1) - p.ticket_base);
+    const int t = (int)(tile % (unsigned)p.text_rows);
+    const int f = (int)(tile / (unsigned)p.text_rows);
+
+    // ---- phase A
+    const uint8_t *frame = p.frames + (size_t)f * p.frame_stride;
+    const int yT = HB ? 2 * t : t;
+    const bool hasB = HB && (2 * t + 1 < p.rows_px);
+    if (SP == SP_NN) {
+      cells_nn<NT>(p, frame, yT, cT);
+      if (hasB) cells_nn<NT>(p, frame, yT + 1, cB);
+    } else if (SP == SP_BOX_GENERIC) {
+      cells_box_generic<NT>(p, frame, yT, cT);
+      if (hasB) cells_box_generic<NT>(p, frame, yT + 1, cB);
+    } else {
+#pragma unroll 1
+      for (int hrow = 0; hrow < (hasB ? 2 : 1); hrow++) cells_box_stream<NT>(p, frame, yT + hrow, hrow ? cB : cT, V);
+    }
     __syncthreads();
-  }
-  if (p.cells_out) {
-    uint8_t *co = p.cells_out + ((size_t)f * p.rows_px + yT) * (size_t)w * 3u;
-    for (int x = tid; x < w; x += NT) {
-      uint32_t c = cT[x];
-      co[3 * x] = (uint8_t)(c >> 16);
-      co[3 * x + 1] = (uint8_t)(c >> 8);
-      co[3 * x + 2] = (uint8_t)c;
-      if (hasB) {
-        uint32_t d = cB[x];
-        uint8_t *cb = co + (size_t)w * 3u;
-        cb[3 * x] = (uint8_t)(d >> 16);
-        cb[3 * x + 1] = (uint8_t)(d >> 8);
-        cb[3 * x + 2] = (uint8_t)d;
+    if (HB && !hasB) { // odd pixel height: bottom := top (halfblock.c:73,82-88)
+      for (int x = tid; x < w; x += NT) cB[x] = cT[x];
+      __syncthreads();
+    }
+    if (p.cells_out) {
+      uint8_t *co = p.cells_out + ((size_t)f * p.rows_px + yT) * (size_t)w * 3u;
+      for (int x = tid; x < w; x += NT) {
+        uint32_t c = cT[x];
+        co[3 * x] = (uint8_t)(c >> 16);
+        co[3 * x + 1] = (uint8_t)(c >> 8);
+        co[3 * x + 2] = (uint8_t)c;
+        if (hasB) {
+          uint32_t d = cB[x];
+          uint8_t *cb = co + (size_t)w * 3u;
+          cb[3 * x] = (uint8_t)(d >> 16);
+          cb[3 * x + 1] = (uint8_t)(d >> 8);
+          cb[3 * x + 2] = (uint8_t)d;
+        }
       }
     }
-  }
-  if (p.rows == nullptr) return; // resize-only invocation
+    if (p.rows == nullptr) return; // resize-only invocation (never direct)
 
-  if (p.direct) {
+    if (!p.direct) {
+      emit_row<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond, tid);
+      return;
+    }
     uint16_t *off16 = reinterpret_cast<uint16_t *>(off);
     const uint32_t bytes =
         emit_direct_prepare<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off16, s_tmp, s_cond, tid);
     emit_direct_finish<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off16, outb, s_cond, s_lb, bytes, tid);
-    return;
+    // emit_direct_finish ends on a barrier: cT/cB, the staging buffer and s_tile[it & 1] are free again
   }
-  emit_row<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond, tid);
 }
 
 // ------------------------------------------------------------------ warp-specialised persistent row kernel
@@ -1412,23 +1437,32 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32, 4) k_render_r
   }
 }
 
+// kernel attributes are per device: one bit per CUDA ordinal, set once the opt-in has been made on that device
+static inline bool attr_done(std::atomic<uint64_t> &mask, int dev) { return (mask.load(std::memory_order_acquire) >> dev) & 1ull; }
+static inline void attr_set(std::atomic<uint64_t> &mask, int dev) { mask.fetch_or(1ull << dev, std::memory_order_release); }
+static inline int current_sms(int *dev_out) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  if (dev_out) *dev_out = dev;
+  return sms;
+}
+
 template <int MODE> static cudaError_t launch_ws2_mode(const RenderParams &p, cudaStream_t st, unsigned *grid_out) {
   const Layout2 L = make_layout2(MODE, p.direct, p.cols, p.src_w, p.row_pitch);
   if (L.total > kMaxDynSmem) return cudaErrorInvalidConfiguration;
-  static bool configured = false;
-  static int ctas_per_sm = 1, sms = 148;
-  static size_t cfg_smem = 0;
-  if (!configured || cfg_smem != L.total) {
+  // nothing cached across calls except the per-device opt-in: callers with different geometries run concurrently
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  const int sms = current_sms(&dev);
+  if (!attr_done(configured, dev)) {
     cudaError_t e = allow_max_dyn_smem(k_render_rows_ws2<MODE>);
     if (e != cudaSuccess) return e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_render_rows_ws2<MODE>, WS2_ST + 32, L.total);
-    if (e != cudaSuccess || ctas_per_sm < 1) return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
-    cfg_smem = L.total;
-    configured = true;
+    attr_set(configured, dev);
   }
+  int ctas_per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_render_rows_ws2<MODE>, WS2_ST + 32, L.total);
+  if (e != cudaSuccess || ctas_per_sm < 1) return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
   const long long total = (long long)p.n_frames * p.text_rows;
   long long grid = (long long)sms * ctas_per_sm;
   if (grid > total) grid = total;
@@ -1452,32 +1486,44 @@ template <class K> static cudaError_t allow_max_dyn_smem(K kernel) {
 // passes, because five CTAs per SM keep more loads in flight than three)
 __host__ inline int pick_nt(int cols) { return cols <= 128 ? 128 : 256; }
 
-template <int MODE, int SP, int NT> static cudaError_t launch_rows_t(const RenderParams &p, cudaStream_t st) {
+template <int MODE, int SP, int NT>
+static cudaError_t launch_rows_t(const RenderParams &p, cudaStream_t st, unsigned *grid_out) {
   const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
   const Layout L = make_layout(MODE, SP, p.cols, p.src_w, cap, p.tune_flags & 1);
   if (L.total > kMaxDynSmem) return cudaErrorInvalidConfiguration;
-  static bool configured = false; // benign race: the attribute is idempotent
-  if (!configured) {
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  const int sms = current_sms(&dev);
+  if (!attr_done(configured, dev)) {
     // opt-in limit is 227 KB per CTA for static + dynamic together; the kernel has < 1 KB static
     cudaError_t e = allow_max_dyn_smem(k_render_rows<MODE, SP, NT>);
     if (e != cudaSuccess) return e;
-    configured = true;
+    attr_set(configured, dev);
   }
-  const unsigned grid = (unsigned)p.n_frames * (unsigned)p.text_rows;
+  unsigned grid = (unsigned)p.n_frames * (unsigned)p.text_rows;
+  if (p.direct) { // persistent: as many CTAs as are resident at once, tiles drawn from the ticket
+    int ctas_per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_render_rows<MODE, SP, NT>, NT, L.total);
+    if (e != cudaSuccess || ctas_per_sm < 1) return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
+    const unsigned resident = (unsigned)sms * (unsigned)ctas_per_sm;
+    if (grid > resident) grid = resident;
+  }
+  if (grid_out) *grid_out = grid;
   k_render_rows<MODE, SP, NT><<<grid, NT, L.total, st>>>(p);
   return cudaGetLastError();
 }
-template <int MODE, int SP> static cudaError_t launch_rows_nt(const RenderParams &p, cudaStream_t st) {
+template <int MODE, int SP> static cudaError_t launch_rows_nt(const RenderParams &p, cudaStream_t st, unsigned *grid_out) {
   switch (pick_nt(p.cols)) {
-  case 128: return launch_rows_t<MODE, SP, 128>(p, st);
-  default: return launch_rows_t<MODE, SP, 256>(p, st);
+  case 128: return launch_rows_t<MODE, SP, 128>(p, st, grid_out);
+  default: return launch_rows_t<MODE, SP, 256>(p, st, grid_out);
   }
 }
-template <int MODE> static cudaError_t launch_rows_mode(const RenderParams &p, int sp, cudaStream_t st) {
+template <int MODE>
+static cudaError_t launch_rows_mode(const RenderParams &p, int sp, cudaStream_t st, unsigned *grid_out) {
   switch (sp) {
-  case SP_NN: return launch_rows_nt<MODE, SP_NN>(p, st);
-  case SP_BOX_GENERIC: return launch_rows_nt<MODE, SP_BOX_GENERIC>(p, st);
-  default: return launch_rows_nt<MODE, SP_BOX_STREAM>(p, st);
+  case SP_NN: return launch_rows_nt<MODE, SP_NN>(p, st, grid_out);
+  case SP_BOX_GENERIC: return launch_rows_nt<MODE, SP_BOX_GENERIC>(p, st, grid_out);
+  default: return launch_rows_nt<MODE, SP_BOX_STREAM>(p, st, grid_out);
   }
 }
 
@@ -1485,20 +1531,17 @@ template <int MODE, int CPT, int NT> static cudaError_t launch_ws_t(const Render
   const Layout L = make_layout(MODE, SP_BOX_STREAM, p.cols, p.src_w, p.row_pitch, 0);
   const size_t smem = ((L.total + 127u) & ~127u) + (size_t)p.ring_depth * p.src_w * 3u;
   if (smem > kMaxDynSmem) return cudaErrorInvalidConfiguration;
-  static bool configured = false;
-  static int ctas_per_sm = 1, sms = 148;
-  static size_t cfg_smem = 0;
-  if (!configured || smem != cfg_smem) {
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  const int sms = current_sms(&dev);
+  if (!attr_done(configured, dev)) {
     cudaError_t e = allow_max_dyn_smem(k_render_rows_ws<MODE, CPT, NT>);
     if (e != cudaSuccess) return e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_render_rows_ws<MODE, CPT, NT>, NT + 32, smem);
-    if (e != cudaSuccess || ctas_per_sm < 1) return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
-    cfg_smem = smem;
-    configured = true;
+    attr_set(configured, dev);
   }
+  int ctas_per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_render_rows_ws<MODE, CPT, NT>, NT + 32, smem);
+  if (e != cudaSuccess || ctas_per_sm < 1) return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
   const long long total = (long long)p.n_frames * p.text_rows;
   long long grid = (long long)sms * ctas_per_sm;
   if (grid > total) grid = total;

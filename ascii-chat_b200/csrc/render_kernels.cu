@@ -266,21 +266,21 @@ __global__ void __launch_bounds__(256) k_dither_bg(const uint8_t *cells, int w, 
 }
 
 // ------------------------------------------------------------------ launchers
-cudaError_t launch_rows_m0(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_rows_m0(const RenderParams &p, int sp, cudaStream_t st, unsigned *grid_out);
 cudaError_t launch_ws_m0(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_rows_m1(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_rows_m1(const RenderParams &p, int sp, cudaStream_t st, unsigned *grid_out);
 cudaError_t launch_ws_m1(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_rows_m2(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_rows_m2(const RenderParams &p, int sp, cudaStream_t st, unsigned *grid_out);
 cudaError_t launch_ws_m2(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_rows_m3(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_rows_m3(const RenderParams &p, int sp, cudaStream_t st, unsigned *grid_out);
 cudaError_t launch_ws_m3(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_rows_m4(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_rows_m4(const RenderParams &p, int sp, cudaStream_t st, unsigned *grid_out);
 cudaError_t launch_ws_m4(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_rows_m5(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_rows_m5(const RenderParams &p, int sp, cudaStream_t st, unsigned *grid_out);
 cudaError_t launch_ws_m5(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_rows_m6(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_rows_m6(const RenderParams &p, int sp, cudaStream_t st, unsigned *grid_out);
 cudaError_t launch_ws_m6(const RenderParams &p, cudaStream_t st);
-cudaError_t launch_rows_m7(const RenderParams &p, int sp, cudaStream_t st);
+cudaError_t launch_rows_m7(const RenderParams &p, int sp, cudaStream_t st, unsigned *grid_out);
 cudaError_t launch_ws_m7(const RenderParams &p, cudaStream_t st);
 cudaError_t launch_ws2_m0(const RenderParams &p, cudaStream_t st, unsigned *grid_out);
 cudaError_t launch_ws2_m1(const RenderParams &p, cudaStream_t st, unsigned *grid_out);
@@ -291,16 +291,16 @@ cudaError_t launch_ws2_m5(const RenderParams &p, cudaStream_t st, unsigned *grid
 cudaError_t launch_ws2_m6(const RenderParams &p, cudaStream_t st, unsigned *grid_out);
 cudaError_t launch_ws2_m7(const RenderParams &p, cudaStream_t st, unsigned *grid_out);
 
-cudaError_t launch_render_rows(const RenderParams &p, int mode, int sp, cudaStream_t st) {
+cudaError_t launch_render_rows(const RenderParams &p, int mode, int sp, cudaStream_t st, unsigned *grid_out) {
   switch (mode) {
-  case EM_MONO_FG: return launch_rows_m0(p, sp, st);
-  case EM_256_FG: return launch_rows_m1(p, sp, st);
-  case EM_16_FG: return launch_rows_m2(p, sp, st);
-  case EM_TRUE_FG: return launch_rows_m3(p, sp, st);
-  case EM_HB_TRUE: return launch_rows_m4(p, sp, st);
-  case EM_HB_256: return launch_rows_m5(p, sp, st);
-  case EM_HB_16: return launch_rows_m6(p, sp, st);
-  case EM_HB_MONO: return launch_rows_m7(p, sp, st);
+  case EM_MONO_FG: return launch_rows_m0(p, sp, st, grid_out);
+  case EM_256_FG: return launch_rows_m1(p, sp, st, grid_out);
+  case EM_16_FG: return launch_rows_m2(p, sp, st, grid_out);
+  case EM_TRUE_FG: return launch_rows_m3(p, sp, st, grid_out);
+  case EM_HB_TRUE: return launch_rows_m4(p, sp, st, grid_out);
+  case EM_HB_256: return launch_rows_m5(p, sp, st, grid_out);
+  case EM_HB_16: return launch_rows_m6(p, sp, st, grid_out);
+  case EM_HB_MONO: return launch_rows_m7(p, sp, st, grid_out);
   default: return cudaErrorInvalidValue;
   }
 }

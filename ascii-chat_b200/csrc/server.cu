@@ -22,11 +22,16 @@
 #include <cstring>
 #include <mutex>
 #include <shared_mutex>
+#include <vector>
 
 #include "engine.h"
 
 using namespace acb;
 
+// Several GPUs in one process (acb200_init_devices): slot s lives on device s % pool size — client frames shard
+// across the GPUs of the box, SURVEY.md §8e — and is uploaded on a stream of that device.  A viewer whose render thread
+// is leased to another GPU reads the sources it needs straight out of the owner's HBM over NVLink (peer access is
+// enabled between all devices of the pool); without peer access the frame is first copied to the viewer's GPU.
 namespace {
 
 struct Slot {
@@ -35,7 +40,12 @@ struct Slot {
   int front = 0;
   int w = 0, h = 0;
   bool valid = false;
-  std::mutex writer; // serialises updates of one slot
+  int device = -1;             // CUDA ordinal the buffers live on (fixed at first use)
+  cudaStream_t up = nullptr;   // upload stream on that device
+  cudaEvent_t done = nullptr;  // blocking-sync event: the receive thread sleeps while its frame crosses PCIe
+  uint8_t *recv = nullptr;     // pinned receive buffer handed to the transport (acb200_source_acquire)
+  size_t recv_cap = 0;
+  std::mutex writer;           // serialises updates of one slot
 };
 
 Slot g_slots[ACB200_MAX_SOURCES];
@@ -43,20 +53,78 @@ std::shared_mutex g_table;
 
 bool slot_ok(int slot) { return slot >= 0 && slot < ACB200_MAX_SOURCES; }
 
+// s.writer held.  Makes the slot's device current; the caller restores its own.
+bool slot_device(Slot &s, int slot) {
+  if (s.device < 0) {
+    const int n = acb200_device_count();
+    s.device = n > 0 ? acb200_device_at(slot % n) : -1;
+    if (s.device < 0) return false;
+  }
+  if (cudaSetDevice(s.device) != cudaSuccess) return false;
+  if (!s.up && cudaStreamCreateWithFlags(&s.up, cudaStreamNonBlocking) != cudaSuccess) return false;
+  if (!s.done && cudaEventCreateWithFlags(&s.done, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess)
+    return false;
+  return true;
+}
+
+// s.writer held, slot device current.  `staged` = the frame is already in pinned memory (no staging copy).
+int upload_locked(Slot &s, const uint8_t *rgb, bool staged, int w, int h, ThreadCtx *cx) {
+  const size_t bytes = (size_t)w * h * 3;
+  const int back = s.front ^ 1;
+  if (!grow_device(&s.buf[back], &s.cap[back], bytes + 16)) return acb200_last_error();
+  if (staged) {
+    ACB_CUDA(cudaMemcpyAsync(s.buf[back], rgb, bytes, cudaMemcpyHostToDevice, s.up));
+  } else {
+    // pageable source: staged through this thread's pinned buffer in slices, so that the host copy of slice k+1 runs
+    // while slice k crosses PCIe (the copy, not the link, is the slower of the two)
+    if (!grow_pinned(&cx->h_in, &cx->h_in_cap, bytes)) return acb200_last_error();
+    const size_t slice = 512u << 10;
+    for (size_t o = 0; o < bytes; o += slice) {
+      const size_t n = bytes - o < slice ? bytes - o : slice;
+      memcpy(cx->h_in + o, rgb + o, n);
+      ACB_CUDA(cudaMemcpyAsync(s.buf[back] + o, cx->h_in + o, n, cudaMemcpyHostToDevice, s.up));
+    }
+  }
+  ACB_CUDA(cudaEventRecord(s.done, s.up));
+  ACB_CUDA(cudaEventSynchronize(s.done));
+  std::unique_lock<std::shared_mutex> lk(g_table);
+  s.front = back;
+  s.w = w;
+  s.h = h;
+  s.valid = true;
+  return E_OK;
+}
+
 } // namespace
 
 namespace acb {
+// acb200_shutdown.  Lock order as in an update: the slot's writer mutex, then the table — so no upload is in flight
+// into a buffer that is being freed, and no reader holds a pointer (readers hold the shared table lock across their
+// launches and the stream wait).
 void destroy_sources() {
-  std::unique_lock<std::shared_mutex> lk(g_table);
+  int cur = 0;
+  cudaGetDevice(&cur);
   for (Slot &s : g_slots) {
+    std::lock_guard<std::mutex> w(s.writer);
+    std::unique_lock<std::shared_mutex> lk(g_table);
+    if (s.device >= 0) cudaSetDevice(s.device);
     for (int b = 0; b < 2; b++) {
       if (s.buf[b]) cudaFree(s.buf[b]);
       s.buf[b] = nullptr;
       s.cap[b] = 0;
     }
+    if (s.recv) cudaFreeHost(s.recv);
+    s.recv = nullptr;
+    s.recv_cap = 0;
+    if (s.up) cudaStreamDestroy(s.up);
+    if (s.done) cudaEventDestroy(s.done);
+    s.up = nullptr;
+    s.done = nullptr;
+    s.device = -1;
     s.valid = false;
     s.w = s.h = 0;
   }
+  cudaSetDevice(cur);
 }
 } // namespace acb
 
@@ -68,6 +136,12 @@ int acb200_source_clear(int slot) {
   std::unique_lock<std::shared_mutex> lk(g_table);
   g_slots[slot].valid = false;
   return E_OK;
+}
+
+int acb200_source_device(int slot) {
+  if (!slot_ok(slot)) return -1;
+  std::lock_guard<std::mutex> w(g_slots[slot].writer);
+  return g_slots[slot].device;
 }
 
 int acb200_source_update(int slot, const uint8_t *rgb, int w, int h) {
@@ -82,19 +156,49 @@ int acb200_source_update(int slot, const uint8_t *rgb, int w, int h) {
   ThreadCtx *cx = thread_ctx();
   if (!cx) return acb200_last_error();
   std::lock_guard<std::mutex> wl(s.writer);
-  const size_t bytes = (size_t)w * h * 3;
-  const int back = s.front ^ 1;
-  if (!grow_pinned(&cx->h_in, &cx->h_in_cap, bytes) || !grow_device(&s.buf[back], &s.cap[back], bytes + 16))
-    return acb200_last_error();
-  memcpy(cx->h_in, rgb, bytes);
-  ACB_CUDA(cudaMemcpyAsync(s.buf[back], cx->h_in, bytes, cudaMemcpyHostToDevice, cx->stream));
-  ACB_CUDA(cudaStreamSynchronize(cx->stream));
-  std::unique_lock<std::shared_mutex> lk(g_table);
-  s.front = back;
-  s.w = w;
-  s.h = h;
-  s.valid = true;
-  return E_OK;
+  if (!slot_device(s, slot)) {
+    cudaSetDevice(cx->device);
+    return set_error(E_INVALID_STATE, "acb200_source_update: cannot set up slot %d on its device", slot);
+  }
+  const bool staged = s.recv && rgb >= s.recv && rgb + (size_t)w * h * 3 <= s.recv + s.recv_cap;
+  const int rc = upload_locked(s, rgb, staged, w, h, cx);
+  cudaSetDevice(cx->device);
+  return rc;
+}
+
+// The transport can receive straight into pinned memory: acquire a buffer of `bytes` for the slot, fill it (the RGB24
+// payload of one IMAGE_FRAME), then acb200_source_commit uploads it without a staging copy.  The buffer belongs to the
+// slot and stays valid until the next acquire that needs a larger one, or acb200_shutdown.
+uint8_t *acb200_source_acquire(int slot, size_t bytes) {
+  if (!slot_ok(slot) || bytes == 0) {
+    set_error(E_INVALID_PARAM, "acb200_source_acquire: bad argument");
+    return nullptr;
+  }
+  if (ensure_device() != 0) return nullptr;
+  Slot &s = g_slots[slot];
+  std::lock_guard<std::mutex> wl(s.writer);
+  if (!grow_pinned(&s.recv, &s.recv_cap, bytes)) return nullptr;
+  return s.recv;
+}
+int acb200_source_commit(int slot, int w, int h) {
+  if (!slot_ok(slot)) return set_error(E_INVALID_PARAM, "acb200_source_commit: slot %d out of range", slot);
+  Slot &s = g_slots[slot];
+  if (w <= 0 || h <= 0 || w > 4096 || h > 2160) { // stream.c:342
+    acb200_source_clear(slot);
+    return set_error(E_INVALID_PARAM, "acb200_source_commit: rejected dimensions %dx%d", w, h);
+  }
+  ThreadCtx *cx = thread_ctx();
+  if (!cx) return acb200_last_error();
+  std::lock_guard<std::mutex> wl(s.writer);
+  if (!s.recv || (size_t)w * h * 3 > s.recv_cap)
+    return set_error(E_INVALID_PARAM, "acb200_source_commit: no acquired buffer of %zu bytes", (size_t)w * h * 3);
+  if (!slot_device(s, slot)) {
+    cudaSetDevice(cx->device);
+    return set_error(E_INVALID_STATE, "acb200_source_commit: cannot set up slot %d on its device", slot);
+  }
+  const int rc = upload_locked(s, s.recv, true, w, h, cx);
+  cudaSetDevice(cx->device);
+  return rc;
 }
 
 // The wire form of a received frame, IMAGE_FRAME payload = [width:be32][height:be32][RGB24] — the checks of
@@ -137,14 +241,18 @@ static char *mixed_frame_impl(const int *slots, int n, unsigned short width, uns
 
   std::shared_lock<std::shared_mutex> lk(g_table);
   const uint8_t *src[ACB200_MAX_SOURCES];
-  int ws[ACB200_MAX_SOURCES], hs[ACB200_MAX_SOURCES];
+  int ws[ACB200_MAX_SOURCES], hs[ACB200_MAX_SOURCES], devs[ACB200_MAX_SOURCES];
   int live = 0;
+  size_t remote_bytes = 0;
   for (int i = 0; i < n; i++) {
     const Slot &s = g_slots[slots[i]];
     if (!s.valid) continue;
     src[live] = s.buf[s.front];
     ws[live] = s.w;
     hs[live] = s.h;
+    devs[live] = s.device;
+    if (live < 9 && s.device != cx->device && !peer_ok(cx->device, s.device))
+      remote_bytes += ((size_t)s.w * s.h * 3 + 255) & ~(size_t)255;
     live++;
   }
   if (out_sources_count) *out_sources_count = live;
@@ -152,6 +260,22 @@ static char *mixed_frame_impl(const int *slots, int n, unsigned short width, uns
   if (!caps || !palette) {       // convert_composite_to_ascii: caps/palette of the target not known yet (:816-826)
     set_error(E_INVALID_STATE, "acb200_mixed_frame: terminal capabilities / palette not set");
     return nullptr;
+  }
+  // Sources on another GPU of the pool are read in place over NVLink (peer access).  Where the topology offers no peer
+  // access, the (at most nine) frames this viewer composes are first copied to its own GPU.
+  if (remote_bytes) {
+    if (!grow_device(&cx->d_in, &cx->d_in_cap, remote_bytes)) return nullptr;
+    size_t o = 0;
+    for (int v = 0; v < live && v < 9; v++) {
+      if (devs[v] == cx->device || peer_ok(cx->device, devs[v])) continue;
+      const size_t bytes = (size_t)ws[v] * hs[v] * 3;
+      if (cudaMemcpyPeerAsync(cx->d_in + o, cx->device, src[v], devs[v], bytes, cx->stream) != cudaSuccess) {
+        set_error(E_INVALID_STATE, "CUDA: peer copy of a source frame failed");
+        return nullptr;
+      }
+      src[v] = cx->d_in + o;
+      o += (bytes + 255) & ~(size_t)255;
+    }
   }
 
   const uint8_t *comp = src[0];
@@ -229,6 +353,141 @@ static char *mixed_frame_impl(const int *slots, int n, unsigned short width, uns
   if (!frame) return nullptr;
   *out_size = len;
   return frame;
+}
+
+// The discovery host's render tick (src/common/session/host.c:664-717) with resident sources, across the GPUs of the pool:
+// every client with video is converted (ascii_convert_with_capabilities) ON THE GPU THAT HOLDS ITS FRAMES, the emitters
+// store the finished rows straight into the composing GPU's arena (peer stores over NVLink — the gather is part of the
+// render kernel's output phase, there is no separate collective; a staged peer copy where the topology has no peer
+// access), and ascii_create_grid composes there, reading the string lengths where the kernels left them.
+char *acb200_grid_frame(const int *slots, int n, int cell_width, int cell_height, const terminal_capabilities_t *caps,
+                        bool use_aspect_ratio, bool stretch, const char *palette, int grid_width, int grid_height,
+                        size_t *out_size) {
+  if (!out_size || !slots || n <= 0 || n > ACB200_MAX_SOURCES || !caps || !palette || cell_width <= 0 ||
+      cell_height <= 0 || grid_width <= 0 || grid_height <= 0) {
+    set_error(E_INVALID_PARAM, "acb200_grid_frame: bad argument");
+    return nullptr;
+  }
+  *out_size = 0;
+  for (int i = 0; i < n; i++)
+    if (!slot_ok(slots[i])) {
+      set_error(E_INVALID_PARAM, "acb200_grid_frame: slot %d out of range", slots[i]);
+      return nullptr;
+    }
+  if ((size_t)grid_width * (size_t)grid_height > (size_t)1 << 30) {
+    set_error(E_INVALID_PARAM, "acb200_grid_frame: dimensions would overflow: %dx%d", grid_width, grid_height);
+    return nullptr;
+  }
+  ThreadCtx *cx = thread_ctx();
+  if (!cx) return nullptr;
+  const int D = cx->device;
+  struct Job {
+    const uint8_t *src;
+    int dev;
+    acb200_render_cfg_t cfg;
+    Plan pl;
+  };
+  std::vector<Job> jobs;
+  std::shared_lock<std::shared_mutex> lk(g_table); // held until the strings are composed: the sources must not move
+  size_t pitch = 0;
+  for (int i = 0; i < n; i++) {
+    const Slot &s = g_slots[slots[i]];
+    if (!s.valid) continue; // host.c:672: only participants with video take a cell
+    Job j;
+    j.src = s.buf[s.front];
+    j.dev = s.device;
+    if (!plan_convert_with_caps(s.w, s.h, cell_width, cell_height, caps, use_aspect_ratio, stretch, palette, &j.cfg) ||
+        !make_plan(j.cfg, j.pl))
+      return nullptr;
+    if (j.pl.frame_capacity > pitch) pitch = j.pl.frame_capacity;
+    jobs.push_back(j);
+  }
+  const int live = (int)jobs.size();
+  if (live == 0) return nullptr; // nothing to show, not an error
+  // composing GPU: arena (live x pitch), then the length words
+  const size_t arena_bytes = (size_t)live * pitch, canvas = (size_t)grid_width * grid_height + grid_height + 1;
+  const size_t out_cap = (canvas > pitch + 1 ? canvas : pitch + 1) + 16;
+  if (sync_foreign(cx, cx->stream) != E_OK) return nullptr;
+  if (!grow_device(&cx->d_frame, &cx->d_frame_cap, arena_bytes + 256) || !grow_device(&cx->d_out, &cx->d_out_cap, out_cap) ||
+      !grow_pinned(&cx->h_out, &cx->h_out_cap, out_cap))
+    return nullptr;
+  uint8_t *arena = cx->d_frame;
+  uint32_t *lens = reinterpret_cast<uint32_t *>(cx->d_frame + arena_bytes); // arena_bytes is a multiple of 16
+  bool used[kMaxDevices] = {};
+  for (int i = 0; i < live; i++) {
+    Job &j = jobs[i];
+    cudaStream_t st;
+    uint8_t **scratch;
+    size_t *scratch_cap;
+    LookbackState *lb;
+    bool *dirty;
+    PeerHelper *h = nullptr;
+    if (j.dev == D) {
+      st = cx->stream, scratch = &cx->d_scratch, scratch_cap = &cx->d_scratch_cap, lb = &cx->lb, dirty = &cx->scratch_dirty;
+    } else {
+      h = peer_helper(cx, j.dev);
+      if (!h) {
+        cudaSetDevice(D);
+        return nullptr;
+      }
+      st = h->stream, scratch = &h->scratch, scratch_cap = &h->scratch_cap, lb = &h->lb, dirty = &h->dirty;
+      used[j.dev] = true;
+    }
+    const size_t cap_before = *scratch_cap;
+    bool ok = grow_device(scratch, scratch_cap, scratch_bytes(j.pl, 1));
+    const bool will_be_direct = j.pl.mode != EM_DITHER_BG && j.pl.use_smem_out && j.pl.scale_path != SP_BOX_TMA;
+    if (ok && (*scratch_cap != cap_before || *dirty || !will_be_direct)) {
+      ok = cudaMemsetAsync(*scratch, 0, *scratch_cap, st) == cudaSuccess;
+      *lb = LookbackState();
+      *dirty = !will_be_direct;
+    }
+    uint8_t *dst = arena + (size_t)i * pitch;
+    uint32_t *dlen = lens + i;
+    const bool direct_peer = j.dev == D || peer_ok(j.dev, D);
+    if (ok && !direct_peer) { // no peer access: render next to the source, then a staged peer copy
+      ok = grow_device(&h->out, &h->out_cap, (size_t)live * (pitch + 16));
+      dst = h->out + (size_t)i * pitch;
+      dlen = reinterpret_cast<uint32_t *>(h->out + (size_t)live * pitch) + i;
+    }
+    if (ok)
+      ok = render_device(j.cfg, j.pl, j.src, (size_t)j.cfg.src_w * j.cfg.src_h * 3, 0, 1, dst, pitch, dlen, *scratch, st,
+                         nullptr, nullptr, lb) == E_OK;
+    if (ok && !direct_peer)
+      ok = cudaMemcpyPeerAsync(arena + (size_t)i * pitch, D, dst, j.dev, pitch, st) == cudaSuccess &&
+           cudaMemcpyPeerAsync(lens + i, D, dlen, j.dev, sizeof(uint32_t), st) == cudaSuccess;
+    if (!ok) {
+      cudaSetDevice(D);
+      if (!acb200_last_error()) set_error(E_INVALID_STATE, "acb200_grid_frame: CUDA failure while rendering a cell");
+      return nullptr;
+    }
+  }
+  for (int d = 0; d < kMaxDevices; d++)
+    if (used[d]) {
+      cudaSetDevice(d);
+      cudaEventRecord(cx->helper[d]->ev, cx->helper[d]->stream);
+    }
+  cudaSetDevice(D);
+  for (int d = 0; d < kMaxDevices; d++)
+    if (used[d]) cudaStreamWaitEvent(cx->stream, cx->helper[d]->ev, 0);
+  const uint8_t *ptrs[ACB200_MAX_SOURCES];
+  for (int i = 0; i < live; i++) ptrs[i] = arena + (size_t)i * pitch;
+  size_t res = 0;
+  bool exact = false;
+  // host.c:701-702: frame_size = strlen + 1 (the terminator rides along)
+  if (text_grid_device(ptrs, nullptr, live, grid_width, grid_height, cx->d_out, &res, cx->stream, cx, lens, 1u, &exact) != E_OK ||
+      cudaMemcpyAsync(cx->h_out, cx->d_out, res + 1, cudaMemcpyDeviceToHost, cx->stream) != cudaSuccess ||
+      wait_stream(cx) != E_OK) {
+    if (!acb200_last_error()) set_error(E_INVALID_STATE, "acb200_grid_frame: CUDA failure");
+    for (int d = 0; d < kMaxDevices; d++) // leave nothing in flight that reads the sources after the lock is dropped
+      if (used[d]) cudaStreamSynchronize(cx->helper[d]->stream);
+    return nullptr;
+  }
+  char *r = (char *)user_alloc(res + 1);
+  if (!r) return nullptr;
+  memcpy(r, cx->h_out, res + 1);
+  r[res] = '\0';
+  *out_size = exact ? res : strlen(r); // ascii.c:650,705,785 vs :883
+  return r;
 }
 
 char *acb200_mixed_frame(const int *slots, int n, unsigned short width, unsigned short height,

@@ -167,6 +167,21 @@ typedef struct {
 
 /* 0 on success, else an ERROR_* code.  device < 0 keeps the current device. */
 int acb200_init(int device);
+/* Several GPUs behind ONE process — the reference server is one process with a render thread per client
+ * (src/server/render.c:340-652, 1201-1253).  Call before any other entry point: `devices` lists the CUDA ordinals of
+ * the pool (NULL / n <= 0: every visible device).  Calling threads are leased a per-thread context (stream, staging) on
+ * one device of the pool, round-robin, the first time they call in; acb200_bind_thread(k) pins the calling thread to the
+ * k-th device instead (k < 0: round-robin).  Peer access is enabled between all devices of the pool.  Entry points that
+ * take a caller-owned stream run on the calling thread's device: the stream must belong to it. */
+int acb200_init_devices(const int *devices, int n);
+int acb200_device_count(void);   /* devices in the pool (0 before initialisation) */
+int acb200_device_at(int k);     /* CUDA ordinal of the k-th pool device, -1 if out of range */
+int acb200_bind_thread(int k);
+int acb200_thread_device(void);  /* CUDA ordinal the calling thread is leased to (leases one if it has none), -1 on error */
+/* How a caller waits for its frame: 0 = spin (cudaStreamSynchronize), 1 = sleep on a blocking-sync event, 2 = poll for
+ * spin_us microseconds, then sleep (default, 30 us).  Sleeping callers leave their cores to the staging copies of the
+ * other render threads. */
+void acb200_set_sync_mode(int mode, int spin_us);
 void acb200_shutdown(void);
 int acb200_last_error(void);            /* thread-local, cleared on read */
 const char *acb200_last_error_message(void);
@@ -280,6 +295,14 @@ int acb200_source_update(int slot, const uint8_t *rgb, int w, int h);
  * 1..3840 x 1..2160 (image_validate_dimensions), len == 8 + w*h*3; anything else is ERROR_INVALID_PARAM and the slot
  * keeps its previous frame (the reference disconnects the client, which then calls acb200_source_clear). */
 int acb200_source_update_wire(int slot, const uint8_t *payload, size_t len);
+/* Receive without a staging copy: acb200_source_acquire returns a pinned host buffer of at least `bytes` owned by the
+ * slot (valid until a later acquire needs a larger one, or acb200_shutdown); the transport receives the RGB24 payload of
+ * one frame into it and acb200_source_commit uploads it (same checks and effects as acb200_source_update).
+ * acb200_source_update() on a pointer inside that buffer takes the same path. */
+uint8_t *acb200_source_acquire(int slot, size_t bytes);
+int acb200_source_commit(int slot, int w, int h);
+/* CUDA ordinal the slot's frames live on (slot % pool size; -1 before its first update) */
+int acb200_source_device(int slot);
 /* client stopped sending video / disconnected (is_sending_video = false) */
 int acb200_source_clear(int slot);
 /* One output frame for one receiving client.  `slots` lists the active clients in g_client_manager order;
@@ -294,6 +317,17 @@ int acb200_source_clear(int slot);
 char *acb200_mixed_frame(const int *slots, int n, unsigned short width, unsigned short height,
                          const terminal_capabilities_t *caps, const char *palette, size_t *out_size,
                          int *out_sources_count);
+
+/* ---- the discovery host's render tick with RESIDENT sources, over the GPUs of the pool ------------------------
+ * Replaces the body of host_render_thread's video tick (src/common/session/host.c:664-717): for every listed slot that
+ * has video, ascii_convert_with_capabilities(frame, cell_width, cell_height, caps, use_aspect_ratio, stretch, palette)
+ * — rendered on the GPU that owns the slot (slot % pool size), its rows stored directly into the composing GPU's arena
+ * over NVLink — then ascii_create_grid(sources, n_with_video, grid_width, grid_height, out_size) with
+ * frame_size = strlen + 1 as host.c:701-702 passes it.  The composing GPU is the calling thread's.  Returns the
+ * allocator-owned grid (NULL with *out_size = 0 and no error when no listed slot has video). */
+char *acb200_grid_frame(const int *slots, int n, int cell_width, int cell_height, const terminal_capabilities_t *caps,
+                        bool use_aspect_ratio, bool stretch, const char *palette, int grid_width, int grid_height,
+                        size_t *out_size);
 
 #pragma GCC visibility pop
 #ifdef __cplusplus

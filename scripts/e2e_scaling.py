@@ -1,4 +1,10 @@
-"""e2e drop-in call throughput vs caller threads (tuning aid): where does the host path saturate?"""
+"""e2e drop-in call throughput vs caller threads x wait mode (tuning aid): where does the host path saturate?
+
+    python scripts/e2e_scaling.py [--devices N] [--box]
+
+ACB200_NN_PLAN=rows in the environment selects the round-1 row-granular transfer plan (A/B against the default
+pixel-granular plan).  --devices N > 1: one process, N GPUs behind the C ABI (acb200_init_devices)."""
+import argparse
 import ctypes as C
 import os
 import sys
@@ -8,15 +14,31 @@ sys.path[:0] = [ROOT]
 import bench  # noqa: E402
 import ascii_chat_b200 as acb  # noqa: E402
 
-assert acb.lib().acb200_init(0) == 0
+ap = argparse.ArgumentParser()
+ap.add_argument("--devices", type=int, default=1)
+ap.add_argument("--box", action="store_true")
+ap.add_argument("--threads", default="1,2,4,8,12,16,24,32,48,64")
+ap.add_argument("--modes", default="spin,block,hybrid")
+ap.add_argument("--seconds", type=float, default=1.2)
+a = ap.parse_args()
+if a.devices > 1:
+    assert acb.init_devices(list(range(a.devices))) == 0, acb.last_error()
+else:
+    assert acb.lib().acb200_init(0) == 0
 H = bench.load_harness()
 frames = bench.host_ring()
 caps = acb.make_caps(bench.LEVEL, bench.MODE)
 fn = C.cast(acb.lib().ascii_convert_with_capabilities, C.c_void_p)
-for scale, name in ((acb.SCALE_NN, "nn"), (acb.SCALE_BOX, "box")):
+plan = os.environ.get("ACB200_NN_PLAN", "pixels")
+print("cores %d  devices %d  nn plan %s" % (os.cpu_count(), a.devices, plan))
+scales = [(acb.SCALE_NN, "nn")] + ([(acb.SCALE_BOX, "box")] if a.box else [])
+for scale, name in scales:
     acb.lib().acb200_set_default_scale(scale)
-    for t in (1, 2, 4, 8, 16, 32):
-        r = bench.run_callers(H, fn, frames, caps, t, 1.5)
-        fps = r["calls"] / r["seconds"]
-        print("%s threads %2d: %8.0f frames/s  %6.3f ms per call per thread  H2D %.1f GB/s  D2H %.1f GB/s" % (
-            name, t, fps, 1e3 * t / fps, fps * (2.2118 if name == "nn" else 24.8832) / 1e3, fps * r["bytes"] / r["calls"] / 1e9))
+    for mode in a.modes.split(","):
+        acb.lib().acb200_set_sync_mode({"spin": 0, "block": 1, "hybrid": 2}[mode], 30)
+        for t in [int(x) for x in a.threads.split(",")]:
+            r = bench.run_callers(H, fn, frames, caps, t, a.seconds)
+            fps = r["calls"] / r["seconds"]
+            print("%s %-6s threads %2d: %8.0f frames/s  %7.1f Gpix/s  %6.3f ms per call per thread  D2H %.1f GB/s" % (
+                name, mode, t, fps, fps * bench.MPIX / 1e3, 1e3 * t / fps, fps * r["bytes"] / max(1, r["calls"]) / 1e9),
+                flush=True)

@@ -9,11 +9,16 @@ import torch  # noqa: E402
 import ascii_chat_b200 as acb  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+content = sys.argv[2] if len(sys.argv) > 2 else "noise"  # "flat": horizontal colour bands, long runs
 assert acb.lib().acb200_init(0) == 0
 for scale in (acb.SCALE_BOX, acb.SCALE_NN):
     cfg = acb.make_cfg(3840, 2160, 320, 192, 3, 2, "standard", scale=scale)
     cap = acb.frame_capacity(cfg)
-    d_in = torch.randint(0, 256, (n, 2160, 3840, 3), dtype=torch.uint8, device="cuda")
+    if content == "flat":
+        band = torch.randint(0, 256, (n, 2160 // 40 + 1, 1, 3), dtype=torch.uint8, device="cuda")
+        d_in = band.repeat_interleave(40, dim=1)[:, :2160].expand(n, 2160, 3840, 3).contiguous()
+    else:
+        d_in = torch.randint(0, 256, (n, 2160, 3840, 3), dtype=torch.uint8, device="cuda")
     d_out = torch.empty(n * cap, dtype=torch.uint8, device="cuda")
     d_len = torch.empty(n, dtype=torch.int32, device="cuda")
     d_scr = torch.empty(acb.scratch_bytes(cfg, n), dtype=torch.uint8, device="cuda")
