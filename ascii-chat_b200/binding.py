@@ -66,7 +66,8 @@ EXPORTS = [  # every symbol include/asciichat_b200.h declares
     "acb200_trailing_reset_fixup_device", "acb200_source_update_wire",
     "acb200_init_devices", "acb200_device_count", "acb200_device_at", "acb200_bind_thread", "acb200_thread_device",
     "acb200_set_sync_mode", "acb200_source_acquire", "acb200_source_commit", "acb200_source_device",
-    "acb200_grid_frame",
+    "acb200_grid_frame", "acb200_quantize_table_device", "image_print_16color_dithered",
+    "rainbow_replace_ansi_colors",
 ]
 
 
@@ -162,6 +163,11 @@ def lib():
     L.acb200_trailing_reset_fixup_device.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
     L.acb200_mixed_frame_packet.restype = C.c_void_p
     L.acb200_mixed_frame_packet.argtypes = L.acb200_mixed_frame.argtypes
+    L.image_print_16color_dithered.restype = C.c_void_p
+    L.image_print_16color_dithered.argtypes = [ip, C.c_char_p]
+    L.rainbow_replace_ansi_colors.restype = C.c_void_p
+    L.rainbow_replace_ansi_colors.argtypes = [C.c_char_p, C.c_float]
+    L.acb200_quantize_table_device.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
     L.acb200_init_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
     L.acb200_device_at.argtypes = [C.c_int]
     L.acb200_bind_thread.argtypes = [C.c_int]
@@ -364,6 +370,19 @@ def apply_color_filter(image, color_filter, time_seconds=0.0, stride=None):
     st = a.shape[1] * 3 if stride is None else stride
     rc = lib().apply_color_filter(a.ctypes.data, a.shape[1], a.shape[0], st, int(color_filter), float(time_seconds))
     return rc, a
+
+
+def rainbow_replace_ansi_colors(ansi_string, time_seconds):
+    """color_filter.c:348-408 on a finished string; None where the reference returns NULL"""
+    return _take(lib().rainbow_replace_ansi_colors(ansi_string, float(time_seconds)))
+
+
+def image_print_16color_dithered(image, palette, use_background=None):
+    """use_background None: image_print_16color_dithered (foreground.c:650); else ..._with_background(img, flag) (:752)"""
+    a, im = _img(image)
+    if use_background is None:
+        return _take(lib().image_print_16color_dithered(C.byref(im), _pal(palette)))
+    return _take(lib().image_print_16color_dithered_with_background(C.byref(im), bool(use_background), _pal(palette)))
 
 
 def calculate_rainbow(t):

@@ -174,7 +174,7 @@ char *ascii_convert(image_t *original, const ssize_t width, const ssize_t height
                         mode, pad_w, pad_h, palette_chars);
 }
 
-static char *print_image(const uint8_t *rgb, int w, int h, int level, int mode, const char *palette) {
+static char *print_image(const uint8_t *rgb, int w, int h, int level, int mode, const char *palette, int leaf_mode = -1) {
   acb200_render_cfg_t cfg{};
   cfg.src_w = w;
   cfg.src_h = h;
@@ -184,7 +184,7 @@ static char *print_image(const uint8_t *rgb, int w, int h, int level, int mode, 
   cfg.render_mode = mode;
   cfg.scale = ACB200_SCALE_NN; // 1:1, the identity for both scalers
   cfg.palette = palette;
-  return render_one_host(cfg, rgb, nullptr);
+  return render_one_host(cfg, rgb, nullptr, leaf_mode);
 }
 
 static char *dup_empty() {
@@ -207,23 +207,25 @@ char *image_print_with_capabilities(const image_t *image, const terminal_capabil
 }
 
 // leaf printers — each is one fixed (colour depth, mode) of the same kernels
-static char *leaf(const image_t *p, const char *palette, int level, int mode) {
+static char *leaf(const image_t *p, const char *palette, int level, int mode, int leaf_mode = -1) {
   if (!p || !palette || !p->pixels || p->w <= 0 || p->h <= 0) {
     set_error(E_INVALID_PARAM, "image or palette invalid");
     return nullptr;
   }
-  return print_image(reinterpret_cast<const uint8_t *>(p->pixels), p->w, p->h, level, mode, palette);
+  return print_image(reinterpret_cast<const uint8_t *>(p->pixels), p->w, p->h, level, mode, palette, leaf_mode);
 }
 char *image_print(const image_t *p, const char *palette) { return leaf(p, palette, TERM_COLOR_NONE, 0); }
 char *image_print_color(const image_t *p, const char *palette) { return leaf(p, palette, TERM_COLOR_TRUECOLOR, 0); }
 char *image_print_256color(const image_t *p, const char *palette) { return leaf(p, palette, TERM_COLOR_256, 0); }
 char *image_print_16color(const image_t *p, const char *palette) { return leaf(p, palette, TERM_COLOR_16, 0); }
+// foreground.c:752-846.  use_background = false has no caller on the capability path (sgr.c:429-435 only asks for the
+// background form) but it is the same recurrence with one SGR per cell instead of two.
 char *image_print_16color_dithered_with_background(const image_t *image, bool use_background, const char *palette) {
-  if (!use_background) { // the fg-only dithered variant has no caller on the capability path (sgr.c:429-435)
-    set_error(E_INVALID_PARAM, "dithered foreground-only rendering is not part of the render path");
-    return nullptr;
-  }
-  return leaf(image, palette, TERM_COLOR_TRUECOLOR, RENDER_MODE_BACKGROUND);
+  return leaf(image, palette, TERM_COLOR_TRUECOLOR, RENDER_MODE_BACKGROUND, use_background ? (int)EM_DITHER_BG : (int)EM_DITHER_FG);
+}
+// foreground.c:650-749: foreground-only, glyph through char_index_ramp (the Q2 mapping of image_print_16color)
+char *image_print_16color_dithered(const image_t *image, const char *palette) {
+  return leaf(image, palette, TERM_COLOR_TRUECOLOR, RENDER_MODE_BACKGROUND, (int)EM_DITHER_FG_RAMP);
 }
 
 static char *leaf_hb(const uint8_t *rgb, int width, int height, int stride_bytes, int level) {

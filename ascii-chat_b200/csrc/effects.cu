@@ -8,6 +8,7 @@
 //     it is still in HBM (k_crc32c_chunks + k_crc32c_finish) and the 24-byte big-endian ascii_frame_packet_t;
 //     k_trailing_reset_fixup is the device form of the server's "frame must end in ESC[0m" cut (stream.c:1085-1127).
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -391,8 +392,247 @@ int launch_frame_packets(const uint8_t *d_out, size_t out_pitch, const uint32_t 
 
 } // namespace acb
 
+// ====================================================================== rainbow replace on a finished string
+// rainbow_replace_ansi_colors (lib/video/rgba/color_filter.c:348-408): every "ESC[38;2;...m" of the string is replaced
+// by one fixed colour code.  The reference scans serially: find the next "ESC[38;2;", copy what precedes it, skip to
+// the first 'm' at or after match + 7, continue behind it.  As cell-local rules over byte positions:
+//   * a match at p "owns" the bytes p .. e(p), e(p) = first 'm' at >= p + 7;
+//   * a match that starts inside an earlier match's span shares its e() and is swallowed (the pattern holds no 'm', so
+//     it cannot straddle the span's end): a match is ACTIVE iff the nearest earlier match has an 'm' in [p' + 7, p);
+//   * byte i is dropped iff the nearest match p <= i has no 'm' in [p + 7, i); an active match emits the new code.
+// Two running maxima (last match start, last 'm') and one running sum (output offset) — three small launches over
+// 4 KB chunks: per-chunk maxima, per-chunk output counts, write.  A match with no 'm' anywhere behind it (malformed
+// tail) is copied unchanged; the reference's loop re-copies its prefix once per byte there (color_filter.c:398-400).
+namespace {
+
+constexpr int RR_NT = 256, RR_PER = 16, RR_CHUNK = RR_NT * RR_PER;
+
+struct RainbowParams {
+  const uint8_t *in;
+  uint32_t n;
+  uint8_t *out;
+  int *chunk_match, *chunk_m; // [chunks] last match start / last 'm' inside the chunk, -1 = none
+  uint32_t *chunk_count;      // [chunks] output bytes of the chunk
+  int *last_m_total;          // last 'm' of the whole string
+  uint32_t *out_len;          // [0] = output length, [1] = 1 if anything was replaced
+  uint8_t code[24];
+  uint32_t code_len;
+};
+
+__device__ __forceinline__ bool rr_match(const uint8_t *s, uint32_t n, uint32_t i) {
+  return i + 7u <= n && s[i] == 0x1b && s[i + 1] == '[' && s[i + 2] == '3' && s[i + 3] == '8' && s[i + 4] == ';' &&
+         s[i + 5] == '2' && s[i + 6] == ';';
+}
+__device__ __forceinline__ int rr_block_max(int v, int *s_red) { // all threads get the block maximum
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  int r = s_red[0];
+#pragma unroll
+  for (int k = 1; k < RR_NT / 32; k++) r = max(r, s_red[k]);
+  return r;
+}
+
+__global__ void __launch_bounds__(RR_NT) k_rr_summary(const RainbowParams p) {
+  __shared__ int s_red[RR_NT / 32];
+  const uint32_t b0 = blockIdx.x * RR_CHUNK + threadIdx.x * RR_PER;
+  int lm = -1, ll = -1;
+  for (uint32_t i = b0; i < b0 + RR_PER && i < p.n; i++) {
+    if (rr_match(p.in, p.n, i)) lm = (int)i;
+    if (p.in[i] == 'm') ll = (int)i;
+  }
+  lm = rr_block_max(lm, s_red);
+  ll = rr_block_max(ll, s_red);
+  if (threadIdx.x == 0) {
+    p.chunk_match[blockIdx.x] = lm;
+    p.chunk_m[blockIdx.x] = ll;
+    if (ll >= 0) atomicMax(p.last_m_total, ll);
+  }
+}
+
+template <bool WRITE> __global__ void __launch_bounds__(RR_NT) k_rr_apply(const RainbowParams p) {
+  __shared__ int s_red[RR_NT / 32];
+  __shared__ int s_wm[RR_NT / 32], s_wl[RR_NT / 32];
+  __shared__ uint32_t s_ws[RR_NT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = blockIdx.x;
+  // carry-in from the chunks before this one
+  int cm = -1, cl = -1;
+  uint32_t base = 0;
+  for (int k = tid; k < c; k += RR_NT) {
+    cm = max(cm, p.chunk_match[k]);
+    cl = max(cl, p.chunk_m[k]);
+    if (WRITE) base += p.chunk_count[k];
+  }
+  cm = rr_block_max(cm, s_red);
+  cl = rr_block_max(cl, s_red);
+  if (WRITE) { // block sum of the counts before this chunk
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) base += __shfl_xor_sync(0xffffffffu, base, d);
+    __syncthreads();
+    if (lane == 0) s_ws[warp] = base;
+    __syncthreads();
+    base = 0;
+    for (int k = 0; k < RR_NT / 32; k++) base += s_ws[k];
+    __syncthreads();
+  }
+  const int last_m_total = *p.last_m_total;
+  const uint32_t b0 = (uint32_t)c * RR_CHUNK + (uint32_t)tid * RR_PER;
+  // this thread's own maxima, then an exclusive max-scan over the threads of the chunk
+  int lm = -1, ll = -1;
+  for (uint32_t i = b0; i < b0 + RR_PER && i < p.n; i++) {
+    if (rr_match(p.in, p.n, i)) lm = (int)i;
+    if (p.in[i] == 'm') ll = (int)i;
+  }
+  int im = lm, il = ll;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int om = __shfl_up_sync(0xffffffffu, im, d), ol = __shfl_up_sync(0xffffffffu, il, d);
+    if (lane >= d) {
+      im = max(im, om);
+      il = max(il, ol);
+    }
+  }
+  if (lane == 31) {
+    s_wm[warp] = im;
+    s_wl[warp] = il;
+  }
+  int em = __shfl_up_sync(0xffffffffu, im, 1), el = __shfl_up_sync(0xffffffffu, il, 1);
+  if (lane == 0) em = el = -1;
+  __syncthreads();
+  for (int k = 0; k < warp; k++) {
+    em = max(em, s_wm[k]);
+    el = max(el, s_wl[k]);
+  }
+  int curM = max(em, cm), curL = max(el, cl); // last match start <= b0 - 1, last 'm' <= b0 - 1
+  auto wf = [&](int q) { return last_m_total >= q + 7; };
+  // pass 1: output bytes of this thread's 16 positions
+  uint32_t cnt = 0;
+  uint32_t kind[RR_PER]; // 0 drop, 1 copy, 2 emit the code
+  {
+    int M = curM, L = curL;
+#pragma unroll
+    for (int k = 0; k < RR_PER; k++) {
+      const uint32_t i = b0 + k;
+      uint32_t kd = 0;
+      if (i < p.n) {
+        const uint8_t ch = p.in[i];
+        bool active = false;
+        if (rr_match(p.in, p.n, i)) {
+          active = wf((int)i) && !(M >= 0 && wf(M) && L < M + 7);
+          M = (int)i;
+        }
+        const bool region = M >= 0 && wf(M) && L < M + 7;
+        kd = active ? 2u : region ? 0u : 1u;
+        if (ch == 'm') L = (int)i;
+      }
+      kind[k] = kd;
+      cnt += kd == 2u ? p.code_len : kd;
+    }
+  }
+  // exclusive sum-scan of cnt over the chunk
+  uint32_t inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_ws[warp] = inc;
+  __syncthreads();
+  uint32_t pre = 0, total = 0;
+  for (int k = 0; k < RR_NT / 32; k++) {
+    if (k < warp) pre += s_ws[k];
+    total += s_ws[k];
+  }
+  if (!WRITE) {
+    if (tid == 0) p.chunk_count[c] = total;
+    return;
+  }
+  uint32_t o = base + pre + inc - cnt;
+#pragma unroll
+  for (int k = 0; k < RR_PER; k++) {
+    if (kind[k] == 1u) p.out[o++] = p.in[b0 + k];
+    else if (kind[k] == 2u) {
+      for (uint32_t j = 0; j < p.code_len; j++) p.out[o + j] = p.code[j];
+      o += p.code_len;
+    }
+  }
+  if (c == (int)gridDim.x - 1 && tid == RR_NT - 1) {
+    p.out[base + total] = 0;
+    p.out_len[0] = base + total;
+    p.out_len[1] = (max(cm, p.chunk_match[c]) >= 0) ? 1u : 0u;
+  }
+}
+
+} // namespace
+
 // ====================================================================== C ABI
 extern "C" {
+
+// lib/video/rgba/color_filter.c:348-408.  NULL when ansi_string is NULL or holds no "ESC[38;2;" (the reference's
+// "no replacement needed"), else an allocator-owned string.
+char *rainbow_replace_ansi_colors(const char *ansi_string, float time_seconds) {
+  if (!ansi_string) return nullptr;
+  const size_t n = strlen(ansi_string);
+  if (n == 0 || n > 0x7fffff00u) return nullptr;
+  ThreadCtx *cx = thread_ctx();
+  if (!cx) return nullptr;
+  RainbowParams p{};
+  uint8_t r, g, b;
+  color_filter_calculate_rainbow(time_seconds, &r, &g, &b);
+  p.code_len = (uint32_t)snprintf(reinterpret_cast<char *>(p.code), sizeof(p.code), "\x1b[38;2;%d;%d;%dm", r, g, b);
+  const int chunks = (int)((n + RR_CHUNK - 1) / RR_CHUNK);
+  // every match is at least 8 bytes ("ESC[38;2;" + 'm') and becomes at most 19
+  const size_t out_cap = n + (n / 8 + 1) * 11 + 32;
+  const size_t words = (size_t)3 * chunks + 8;
+  if (sync_foreign(cx, cx->stream) != E_OK) return nullptr;
+  if (!grow_pinned(&cx->h_in, &cx->h_in_cap, n + 16) || !grow_device(&cx->d_in, &cx->d_in_cap, n + 16) ||
+      !grow_device(&cx->d_out, &cx->d_out_cap, out_cap) || !grow_pinned(&cx->h_out, &cx->h_out_cap, out_cap) ||
+      !grow_device((uint8_t **)&cx->d_len, &cx->d_len_cap, words * 4) ||
+      !grow_pinned((uint8_t **)&cx->h_len, &cx->h_len_cap, 256))
+    return nullptr;
+  memcpy(cx->h_in, ansi_string, n);
+  int *w = reinterpret_cast<int *>(cx->d_len);
+  p.in = cx->d_in;
+  p.n = (uint32_t)n;
+  p.out = cx->d_out;
+  p.last_m_total = w;
+  p.out_len = reinterpret_cast<uint32_t *>(w + 2);
+  p.chunk_match = w + 8;
+  p.chunk_m = w + 8 + chunks;
+  p.chunk_count = reinterpret_cast<uint32_t *>(w + 8 + 2 * chunks);
+  bool ok = cudaMemcpyAsync(cx->d_in, cx->h_in, n, cudaMemcpyHostToDevice, cx->stream) == cudaSuccess &&
+            cudaMemsetAsync(w, 0xFF, 4, cx->stream) == cudaSuccess;
+  if (ok) {
+    k_rr_summary<<<(unsigned)chunks, RR_NT, 0, cx->stream>>>(p);
+    k_rr_apply<false><<<(unsigned)chunks, RR_NT, 0, cx->stream>>>(p);
+    k_rr_apply<true><<<(unsigned)chunks, RR_NT, 0, cx->stream>>>(p);
+    count_launch(3);
+    ok = cudaGetLastError() == cudaSuccess &&
+         cudaMemcpyAsync(cx->h_len, p.out_len, 8, cudaMemcpyDeviceToHost, cx->stream) == cudaSuccess &&
+         wait_stream(cx) == E_OK;
+  }
+  if (!ok) {
+    set_error(E_INVALID_STATE, "rainbow_replace_ansi_colors: CUDA failure (%s)", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  if (!cx->h_len[1]) return nullptr; // no colour code in the string: nothing to replace (color_filter.c:363-365)
+  const size_t len = cx->h_len[0];
+  if (cudaMemcpyAsync(cx->h_out, cx->d_out, len, cudaMemcpyDeviceToHost, cx->stream) != cudaSuccess ||
+      wait_stream(cx) != E_OK) {
+    set_error(E_INVALID_STATE, "rainbow_replace_ansi_colors: CUDA failure while reading the result back");
+    return nullptr;
+  }
+  char *res = (char *)user_alloc(len + 1);
+  if (!res) return nullptr;
+  memcpy(res, cx->h_out, len);
+  res[len] = '\0';
+  return res;
+}
+
 
 // lib/video/rgba/color_filter.c:165-236 — host float on purpose, expression for expression (like aspect_ratio):
 // fmodf / floorf / fminf are exactly rounded, so the host compiler's result is the reference's.

@@ -68,7 +68,10 @@ static int g_npool = 0;
 static int g_requested_device = -1;   // acb200_init(device) before the first use
 static bool g_peer[kMaxDevices][kMaxDevices];
 static std::atomic<unsigned> g_rr{0};
-static std::atomic<int> g_sync_mode{2}, g_spin_us{30}; // 0 spin (cudaStreamSynchronize), 1 block, 2 hybrid
+// 0 spin (cudaStreamSynchronize, default), 1 block, 2 hybrid.  Measured on the 16-core B200 box (profiles/r02a_e2e_sweep):
+// spinning callers deliver 35.5 k frames/s at 16 threads, sleeping ones 20 k (28 k at 64 threads) — the wake-up latency
+// of a blocking event costs more than the core the spin burns, even with four callers per core.
+static std::atomic<int> g_sync_mode{0}, g_spin_us{30};
 
 static int init_pool_locked(const int *devs, int n) { // g_dev_mu held
   int count = 0;
@@ -237,9 +240,9 @@ ThreadCtx *thread_ctx() {
   return c;
 }
 
-// Waiting for the frame.  cudaStreamSynchronize spins on a host core for the whole GPU + PCIe time of the call; with one
-// caller thread per client (src/server/render.c) those are the cores the staging copies of the other callers need.
-// Default: poll for a few tens of microseconds (a single caller keeps its latency), then sleep on a blocking-sync event.
+// Waiting for the frame.  cudaStreamSynchronize spins on a host core for the whole GPU + PCIe time of the call; the
+// alternatives (sleep on a blocking-sync event, or poll briefly and then sleep) are selectable for hosts where the
+// cores are scarcer than on the boxes measured — see g_sync_mode.
 int wait_stream(ThreadCtx *cx) {
   const int mode = g_sync_mode.load(std::memory_order_relaxed);
   if (mode == 0 || !cx->done) {
@@ -477,7 +480,7 @@ static DisplayOps display_ops(const acb200_render_cfg_t &cfg) {
 // ------------------------------------------------------------------ plans
 static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
+bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl, int leaf_mode) {
   if (cfg.src_w <= 0 || cfg.src_w > 10000 || cfg.src_h <= 0 || cfg.src_h > 10000) { // ascii.c:204
     set_error(E_INVALID_PARAM, "invalid source dimensions %dx%d", cfg.src_w, cfg.src_h);
     return false;
@@ -503,12 +506,13 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
               : cfg.color_level == TERM_COLOR_16  ? EM_16_FG
                                                   : EM_MONO_FG;
   }
+  if (leaf_mode >= 0) pl.mode = leaf_mode; // a leaf printer the capability dispatch never selects (dropin.cu)
   if (!half && cfg.palette[0] == '\0') { // get_utf8_palette_cache rejects "" (common.c:275)
     set_error(E_INVALID_STATE, "empty palette");
     return false;
   }
   pl.text_rows = half ? (cfg.rows_px + 1) / 2 : cfg.rows_px;
-  pl.lut_which = pl.mode == EM_MONO_FG ? 1 : pl.mode == EM_16_FG ? 2 : 0;
+  pl.lut_which = pl.mode == EM_MONO_FG ? 1 : (pl.mode == EM_16_FG || pl.mode == EM_DITHER_FG_RAMP) ? 2 : 0;
   pl.row_pitch = row_capacity_bytes(pl.mode, cfg.cols, cfg.pad_left);
 
   int sp = SP_NN;
@@ -521,7 +525,7 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
     set_error(E_INVALID_PARAM, "unknown scale mode %d", cfg.scale);
     return false;
   }
-  const int kmode = pl.mode == EM_DITHER_BG ? (int)EM_256_FG : pl.mode;
+  const int kmode = is_dither_mode(pl.mode) ? (int)EM_256_FG : pl.mode;
   pl.use_smem_out = pl.row_pitch <= (uint32_t)kSmemOutMax;
   size_t sm = rows_smem_total(kmode, sp, cfg.cols, cfg.src_w, pl.use_smem_out ? pl.row_pitch : 0);
   if (sm > kMaxDynSmem && sp == SP_BOX_STREAM) {
@@ -541,7 +545,7 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
   // Persistent variants of the streaming box kernel (downscaling geometry whose text row fits the shared staging
   // buffer).  Default: the role-split kernel (streamer warps + emitter warp).  ACB200_BOX_KERNEL=ldg|tma|split
   // selects one explicitly (A/B measurements; "ldg" is the one-tile-per-CTA kernel).
-  if (sp == SP_BOX_STREAM && pl.mode != EM_DITHER_BG && pl.use_smem_out && cfg.src_h >= cfg.rows_px) {
+  if (sp == SP_BOX_STREAM && !is_dither_mode(pl.mode) && pl.use_smem_out && cfg.src_h >= cfg.rows_px) {
     static const char *which_env = getenv("ACB200_BOX_KERNEL");
     const char *which = which_env ? which_env : "split";
     if (!strcmp(which, "split") && ws2_smem_total(pl.mode, cfg.cols, cfg.src_w, pl.row_pitch) <= kMaxDynSmem) {
@@ -559,8 +563,8 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl) {
   pl.frame_capacity = (((size_t)cfg.pad_top + (size_t)pl.text_rows * pl.row_pitch + 1) + 15) & ~(size_t)15;
   pl.rows_bytes = (size_t)pl.text_rows * pl.row_pitch;
   pl.meta_bytes = (size_t)pl.text_rows * sizeof(RowMeta);
-  pl.cells_bytes = pl.mode == EM_DITHER_BG ? (size_t)cfg.cols * cfg.rows_px * 3 : 0;
-  pl.err_bytes = pl.mode == EM_DITHER_BG ? (size_t)cfg.cols * cfg.rows_px * 3 * sizeof(int) : 0;
+  pl.cells_bytes = is_dither_mode(pl.mode) ? (size_t)cfg.cols * cfg.rows_px * 3 : 0;
+  pl.err_bytes = is_dither_mode(pl.mode) ? (size_t)cfg.cols * cfg.rows_px * 3 * sizeof(int) : 0;
   return true;
 }
 
@@ -635,7 +639,7 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
                       (double)h[0] / h[3], (double)h[1] / h[3], (double)h[2] / h[3], h[3]);
     cudaMemset(d_dbg, 0, sizeof(h));
   }
-  if (phase_a_only && pl.mode != EM_DITHER_BG) { // downscale only: rows == nullptr makes the kernel return after phase A
+  if (phase_a_only && !is_dither_mode(pl.mode)) { // downscale only: rows == nullptr makes the kernel return after phase A
     rp.rows = nullptr;
     if (k0) cudaEventRecord(k0, st);
     rp.direct = 0;
@@ -648,7 +652,7 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
   // Direct output (default wherever the text row is staged in shared memory): rows are placed in the final arena by a
   // look-back over per-row records, so there is no stitch pass.  ACB200_DIRECT=0 forces scratch rows + k_stitch.
   static const int direct_env = getenv("ACB200_DIRECT") ? atoi(getenv("ACB200_DIRECT")) : 1; // measurement knob
-  const bool direct = direct_env && pl.mode != EM_DITHER_BG && pl.use_smem_out && pl.scale_path != SP_BOX_TMA;
+  const bool direct = direct_env && !is_dither_mode(pl.mode) && pl.use_smem_out && pl.scale_path != SP_BOX_TMA;
   rp.direct = direct ? 1 : 0;
   rp.ticket = reinterpret_cast<int *>(d_scratch);
   const bool uses_ticket = direct || pl.scale_path == SP_BOX_SPLIT;
@@ -673,16 +677,16 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
   if (uses_ticket && !ls) ACB_CUDA(cudaMemsetAsync(rp.ticket, 0, sizeof(int), st));
   if (k0) cudaEventRecord(k0, st);
   const int kernel_sp = pl.scale_path >= SP_BOX_TMA ? (int)SP_BOX_STREAM : pl.scale_path;
-  if (pl.mode != EM_DITHER_BG && pl.scale_path == SP_BOX_TMA) {
+  if (!is_dither_mode(pl.mode) && pl.scale_path == SP_BOX_TMA) {
     rp.ring_depth = pl.ring_depth;
     ACB_CUDA(launch_render_rows_ws(rp, pl.mode, st));
     count_launch();
-  } else if (pl.mode != EM_DITHER_BG && pl.scale_path == SP_BOX_SPLIT) {
+  } else if (!is_dither_mode(pl.mode) && pl.scale_path == SP_BOX_SPLIT) {
     unsigned grid = 0;
     ACB_CUDA(launch_render_rows_ws2(rp, pl.mode, st, &grid));
     count_launch();
     if (ls) ls->tickets += (uint32_t)n_frames * (uint32_t)pl.text_rows + grid; // every CTA draws one ticket past the end
-  } else if (pl.mode != EM_DITHER_BG) {
+  } else if (!is_dither_mode(pl.mode)) {
     unsigned grid = 0; // direct: persistent CTAs that draw tiles from the ticket, one ticket past the end each
     ACB_CUDA(launch_render_rows(rp, pl.mode, kernel_sp, st, &grid));
     count_launch();
@@ -694,7 +698,7 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
     ACB_CUDA(launch_render_rows(rp, EM_256_FG, kernel_sp, st, nullptr)); // resize-only pass
     ACB_CUDA(cudaMemsetAsync(err, 0, pl.err_bytes * n_frames, st));
     ACB_CUDA(launch_dither_bg(cells, cfg.cols, cfg.rows_px, n_frames, cfg.pad_left, lut, rows, pl.row_pitch, meta, err,
-                              st));
+                              pl.mode != EM_DITHER_BG, st));
     count_launch(2);
   }
   if (k1) cudaEventRecord(k1, st);
@@ -792,9 +796,9 @@ static bool is_pinned(const void *p) {
 }
 
 static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t *const *frames, int n_frames,
-                                  char **out, size_t *out_len) {
+                                  char **out, size_t *out_len, int leaf_mode = -1) {
   Plan pl0;
-  if (!make_plan(cfg, pl0)) return t_err; // validates the caller's configuration as given
+  if (!make_plan(cfg, pl0, leaf_mode)) return t_err; // validates the caller's configuration as given
   if (n_frames <= 0) return E_OK;         // an empty batch is legal
   ThreadCtx *cx = thread_ctx();
   if (!cx) return t_err;
@@ -815,7 +819,7 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
     dcfg.src_w = cfg.cols;
     dcfg.src_h = cfg.rows_px;
     dcfg.flip_x = dcfg.flip_y = 0;
-    if (!make_plan(dcfg, pl)) return t_err;
+    if (!make_plan(dcfg, pl, leaf_mode)) return t_err;
     if (!nn_column_table(cx, cfg.src_w, cfg.cols, flip_x ? 1 : 0)) return t_err;
   }
   const size_t in_per_frame = tplan == PLAN_NN_PIXELS ? (size_t)cfg.cols * cfg.rows_px * 3
@@ -844,7 +848,7 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
   // library-owned scratch keeps its look-back state across calls (epochs + ticket base) as long as nothing else
   // wrote into it; otherwise it is zeroed once here and the state restarts
   {
-    const bool will_be_direct = pl.mode != EM_DITHER_BG && pl.use_smem_out && pl.scale_path != SP_BOX_TMA;
+    const bool will_be_direct = !is_dither_mode(pl.mode) && pl.use_smem_out && pl.scale_path != SP_BOX_TMA;
     if (cx->scratch_dirty || !will_be_direct) {
       ACB_CUDA(cudaMemsetAsync(cx->d_scratch, 0, cx->d_scratch_cap, cx->stream));
       cx->lb = LookbackState();
@@ -939,7 +943,7 @@ char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, si
     return nullptr;
   uint32_t *d_words = reinterpret_cast<uint32_t *>(cx->d_frame + pl.frame_capacity); // frame_capacity is a multiple of 16
   if (cx->d_scratch_cap != scratch_cap_before) cx->scratch_dirty = true;
-  const bool will_be_direct = pl.mode != EM_DITHER_BG && pl.use_smem_out && pl.scale_path != SP_BOX_TMA;
+  const bool will_be_direct = !is_dither_mode(pl.mode) && pl.use_smem_out && pl.scale_path != SP_BOX_TMA;
   if (cx->scratch_dirty || !will_be_direct) {
     if (cudaMemsetAsync(cx->d_scratch, 0, cx->d_scratch_cap, cx->stream) != cudaSuccess) return nullptr;
     cx->lb = LookbackState();
@@ -985,11 +989,11 @@ char *render_one_device(const acb200_render_cfg_t &cfg, const uint8_t *d_rgb, si
   return sp;
 }
 
-char *render_one_host(const acb200_render_cfg_t &cfg, const uint8_t *rgb, size_t *out_len) {
+char *render_one_host(const acb200_render_cfg_t &cfg, const uint8_t *rgb, size_t *out_len, int leaf_mode) {
   char *s = nullptr;
   size_t n = 0;
   const uint8_t *fr[1] = {rgb};
-  if (render_batch_host_impl(cfg, fr, 1, &s, &n) != E_OK) {
+  if (render_batch_host_impl(cfg, fr, 1, &s, &n, leaf_mode) != E_OK) {
     if (s) user_free(s);
     return nullptr;
   }
@@ -1153,6 +1157,22 @@ int acb200_time_batch_device(const acb200_render_cfg_t *cfg, const uint8_t *d_fr
   if (ms_total) *ms_total = tot;
   if (ms_kernel) *ms_kernel = ker;
   return rc;
+}
+
+// parity aid: the device's quantisers over the whole colour space, d_out[r<<16|g<<8|b] (16 MiB); which 0 = 256c, 1 = 16c
+int acb200_quantize_table_device(int which, uint8_t *d_out, void *stream) {
+  if (!d_out || which < 0 || which > 1) return set_error(E_INVALID_PARAM, "acb200_quantize_table_device: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!st) {
+    ThreadCtx *cx = thread_ctx();
+    if (!cx) return t_err;
+    st = cx->stream;
+  } else if (ensure_device() != 0) {
+    return t_err;
+  }
+  ACB_CUDA(launch_quantize_table(which, d_out, st));
+  count_launch();
+  return E_OK;
 }
 
 uint64_t acb200_launch_count(void) { return g_launches.load(); }

@@ -26,7 +26,7 @@ struct Plan {
 };
 
 int set_error(int code, const char *fmt, ...);
-bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl); // false => error set
+bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl, int leaf_mode = -1); // false => error set; leaf_mode: EmitMode override
 int ensure_device();                                       // 0 or error code
 
 // look-back bookkeeping for a library-owned scratch buffer (zeroed once when allocated)
@@ -100,7 +100,7 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
                   LookbackState *ls = nullptr);
 
 // one frame from a host RGB24 buffer -> allocator-owned string (used by every drop-in entry point)
-char *render_one_host(const acb200_render_cfg_t &cfg, const uint8_t *rgb, size_t *out_len);
+char *render_one_host(const acb200_render_cfg_t &cfg, const uint8_t *rgb, size_t *out_len, int leaf_mode = -1);
 // reset_fixup: apply stream.c:1085-1127 (cut after the last ESC[0m) on the device.  packet: return header||frame
 // (lib/network/acip/server.c:203-236) for a terminal of pk_w x pk_h; *out_len then counts the 24 header bytes too.
 struct OneFrameOpts {

@@ -16,8 +16,12 @@ enum EmitMode : int {
   EM_HB_256 = 5,   // rgb_to_256color_halfblocks_scalar  halfblock.c:416-524
   EM_HB_16 = 6,    // rgb_to_16color_halfblocks_scalar   halfblock.c:297-405
   EM_HB_MONO = 7,  // rgb_to_halfblocks_scalar           halfblock.c:184-286
-  EM_DITHER_BG = 8 // image_print_16color_dithered_with_background foreground.c:752-846 (own kernel)
+  EM_DITHER_BG = 8, // image_print_16color_dithered_with_background(img, true)  foreground.c:752-846 (own kernel)
+  // leaf printers without a capability route (sgr.c:429-435 only ever asks for the background form):
+  EM_DITHER_FG = 9,      // image_print_16color_dithered_with_background(img, false): fg SGR only, glyph = cache[Y]
+  EM_DITHER_FG_RAMP = 10 // image_print_16color_dithered  foreground.c:650-749: fg SGR only, glyph per quirk Q2
 };
+__host__ __device__ inline bool is_dither_mode(int m) { return m >= EM_DITHER_BG && m <= EM_DITHER_FG_RAMP; }
 
 enum ScalePath : int {
   SP_NN = 0,        // nearest neighbour, image.c:267-328
@@ -115,14 +119,17 @@ static constexpr uint32_t kMaxDynSmem = 224u * 1024u; // dynamic smem ceiling (2
 cudaError_t launch_render_rows(const RenderParams &p, int mode, int scale_path, cudaStream_t st, unsigned *grid_out);
 cudaError_t launch_render_rows_ws(const RenderParams &p, int mode, cudaStream_t st);
 cudaError_t launch_render_rows_ws2(const RenderParams &p, int mode, cudaStream_t st, unsigned *grid_out);
+cudaError_t launch_quantize_table(int which, uint8_t *d_out, cudaStream_t st);
 size_t ws2_smem_total(int mode, int cols, int src_w, uint32_t row_pitch);
 int ws_ring_depth(int mode, int cols, int src_w, uint32_t row_pitch);
 cudaError_t launch_stitch(const StitchParams &p, int n_frames, cudaStream_t st);
 cudaError_t launch_resize_nn_only(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh, int pregathered,
                                   cudaStream_t st);
 // Floyd–Steinberg 16-colour background renderer (serial wavefront): one CTA per frame, reads the resized image
+// fg_only: print the dithered colour as the foreground (the two foreground-only leaf printers) instead of bg + contrast fg
 cudaError_t launch_dither_bg(const uint8_t *cells, int w, int h, int n_frames, int pad_left, const GlyphLut *lut,
-                             uint8_t *rows, uint32_t row_pitch, RowMeta *meta, int *err_scratch, cudaStream_t st);
+                             uint8_t *rows, uint32_t row_pitch, RowMeta *meta, int *err_scratch, int fg_only,
+                             cudaStream_t st);
 // the whole pixel-space composite in one launch (stream.c:664-779): up to 9 sources (stream.c:687)
 struct CompositeCell {
   const uint8_t *src; // nullptr: the cell stays black (no video / degenerate fit)

@@ -231,13 +231,19 @@ struct OpMax {
 };
 
 // Scans value_of(x), x in [0,w), in x order over NT threads; calls store(x, inclusive, exclusive).
-// Returns the total (valid in every thread).  s_tmp: (NT / 32)+1 ints of shared memory.
+// Returns the total (valid in every thread).  s_tmp: 2 * (NT / 32) ints of shared memory.
+// One barrier per pass of NT cells plus one at the end: the warp totals of a pass go to one of two alternating
+// buffers, every thread folds all of them itself (broadcast reads) to get both its prefix and the running carry, so
+// there is no single-thread carry update to wait for.  (The first version took four barriers per pass and two around
+// the loop — at 8 CTAs per SM the nearest-neighbour kernels spent most of their time in them, profiles/r02a_nn_*.)
 template <class Op, class Sync, int NT, class F, class G>
 __device__ __forceinline__ int row_scan(int w, F value_of, G store, int *s_tmp, int tid) {
+  constexpr int NW = NT / 32;
   const int lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tmp[(NT / 32)] = Op::id();
-  Sync::sync();
-  for (int base = 0; base < w; base += NT) {
+  int carry = Op::id();
+  int pass = 0;
+  for (int base = 0; base < w; base += NT, pass ^= 1) {
+    int *buf = s_tmp + pass * NW;
     int x = base + tid;
     int v = x < w ? value_of(x) : Op::id();
     int inc = v;
@@ -247,20 +253,20 @@ __device__ __forceinline__ int row_scan(int w, F value_of, G store, int *s_tmp, 
       if (lane >= d) inc = Op::ap(o, inc);
     }
     int up = __shfl_up_sync(0xffffffffu, inc, 1);
-    if (lane == 31) s_tmp[warp] = inc;
+    if (lane == 31) buf[warp] = inc;
     Sync::sync();
-    int pre = s_tmp[(NT / 32)];
-    for (int i = 0; i < warp; i++) pre = Op::ap(pre, s_tmp[i]);
-    int incl = Op::ap(pre, inc);
-    int excl = lane == 0 ? pre : Op::ap(pre, up);
-    if (x < w) store(x, incl, excl);
-    Sync::sync();
-    if (tid == NT - 1) s_tmp[(NT / 32)] = incl;
-    Sync::sync();
+    int pre = carry, all = carry;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+      const int t = buf[i];
+      if (i < warp) pre = Op::ap(pre, t);
+      all = Op::ap(all, t);
+    }
+    if (x < w) store(x, Op::ap(pre, inc), lane == 0 ? pre : Op::ap(pre, up));
+    carry = all;
   }
-  const int total = s_tmp[(NT / 32)];
-  Sync::sync(); // the next scan re-initialises s_tmp[(NT / 32)]
-  return total;
+  Sync::sync(); // the next scan (or whoever reads what store() wrote) starts from a quiet s_tmp
+  return carry;
 }
 
 // ------------------------------------------------------------------ shared-memory layout
@@ -938,14 +944,14 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
 template <int MODE, int SP, int NT>
 __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) : 1) k_render_rows(const RenderParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ int s_tmp[(NT / 32) + 1];
+  __shared__ int s_tmp[2 * (NT / 32)];
   __shared__ uint32_t s_cond[4]; // TRUE_FG: {cond_off, cond_len, last_rgb, first_rgb}
 
   constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
   constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
 
   const int tid = threadIdx.x;
-  __shared__ int s_tile[2];
+  __shared__ int s_tile;
   __shared__ uint32_t s_lb[2];
   const int w = p.cols;
   const unsigned total = (unsigned)p.n_frames * (unsigned)p.text_rows;
@@ -962,7 +968,6 @@ __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) :
   uint16_t *V = reinterpret_cast<uint16_t *>(smem + L.V);
   uint8_t *outb = smem + L.outb;
 
-  if (p.direct && tid == 0) s_tile[0] = (int)((uint32_t)atomicAdd(p.ticket, 1) - p.ticket_base);
   if (USES_LUT) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(p.lut);
     uint32_t *dst = reinterpret_cast<uint32_t *>(lut);
@@ -972,12 +977,16 @@ __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) :
   __syncthreads();
 
 #pragma unroll 1
-  for (int it = 0;; it++) {
-    const unsigned tile = p.direct ? (unsigned)s_tile[it & 1] : blockIdx.x;
+  for (;;) {
+    // The ticket is drawn when the CTA is ready to start the tile, NOT ahead of time: a tile that is held but not yet
+    // started keeps every later row of its frame spinning in the look-back for a whole tile period (measured: a
+    // prefetched ticket made this kernel 3x slower, profiles/r02a_nn_*: 63 barrier-stall cycles per issue).
+    if (p.direct) {
+      if (tid == 0) s_tile = (int)((uint32_t)atomicAdd(p.ticket, 1) - p.ticket_base);
+      __syncthreads();
+    }
+    const unsigned tile = p.direct ? (unsigned)s_tile : blockIdx.x;
     if (tile >= total) return;
-    // prefetch the next ticket: its round trip overlaps this tile's loads (the slot it lands in was last read one
-    // iteration ago, and every thread has passed several barriers since)
-    if (p.direct && tid == 0) s_tile[(it + 1) & 1] = (int)((uint32_t)atomicAdd(p.ticket, 1) - p.ticket_base);
     const int t = (int)(tile % (unsigned)p.text_rows);
     const int f = (int)(tile / (unsigned)p.text_rows);
 
@@ -1026,7 +1035,7 @@ __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) :
     const uint32_t bytes =
         emit_direct_prepare<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off16, s_tmp, s_cond, tid);
     emit_direct_finish<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off16, outb, s_cond, s_lb, bytes, tid);
-    // emit_direct_finish ends on a barrier: cT/cB, the staging buffer and s_tile[it & 1] are free again
+    // emit_direct_finish ends on a barrier: cT/cB, the staging buffer and s_tile are free again
   }
 }
 
@@ -1088,7 +1097,7 @@ template <bool HB> __device__ __forceinline__ WsBand ws_band(const RenderParams 
 template <int MODE, int CPT, int NT>
 __global__ void __launch_bounds__(NT + 32) k_render_rows_ws(const RenderParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ int s_tmp[(NT / 32) + 1];
+  __shared__ int s_tmp[2 * (NT / 32)];
   __shared__ uint32_t s_cond[4];
   __shared__ __align__(8) uint64_t s_full[WS_MAXD], s_empty[WS_MAXD];
 

@@ -30,7 +30,7 @@ uint32_t row_capacity_bytes(int mode, int cols, int pad_left) {
   case EM_HB_256: per = 11 + 11 + 3; break;
   case EM_HB_16: per = 5 + 6 + 3; break;
   case EM_HB_MONO: per = 3; break;
-  default: per = 6 + 5 + 4; break; // EM_DITHER_BG
+  default: per = 6 + 5 + 4; break; // EM_DITHER_BG (and its foreground-only forms, which need less)
   }
   // a run head may also own a REP tail (<= 2+5+1 bytes) or a reset before a transparent run (4 bytes):
   // both replace glyph bytes of other cells, so `per` per cell + 16 slack bounds the row
@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(256) k_composite_all(const CompositeParams p) 
 // (x-1,y) and (x-1..x+1, y-1), so row y may trail row y-1 by 3 pixels: one thread per row, a skewed wavefront of
 // w + 3*(rows-1) steps.  Integer += is order independent, so the sums equal the serial ones.
 __global__ void __launch_bounds__(256) k_dither_bg(const uint8_t *cells, int w, int h, int pad_left, const GlyphLut *lut,
-                                                   uint8_t *rows, uint32_t row_pitch, RowMeta *meta, int *err_all) {
+                                                   uint8_t *rows, uint32_t row_pitch, RowMeta *meta, int *err_all,
+                                                   int fg_only) {
   const int f = blockIdx.x;
   const uint8_t *img = cells + (size_t)f * w * h * 3u;
   int *err = err_all + (size_t)f * w * h * 3u;
@@ -245,9 +246,13 @@ __global__ void __launch_bounds__(256) k_dither_bg(const uint8_t *cells, int w, 
         }
         const int bl = ((int)c_ansi16[q][0] * 77 + (int)c_ansi16[q][1] * 150 + (int)c_ansi16[q][2] * 29) / 256;
         WriteSink ws{out + o};
-        put_sgr_16(ws, true, (uint32_t)q);                // foreground.c:807
-        put_sgr_16(ws, false, bl < 127 ? 15u : 0u);       // foreground.c:804-808
-        put_glyph(ws, lut->glyph[luma_of(load_px(px))]);  // cache[Y], foreground.c:820
+        if (fg_only) {
+          put_sgr_16(ws, false, (uint32_t)q);             // foreground.c:713, 811
+        } else {
+          put_sgr_16(ws, true, (uint32_t)q);              // foreground.c:807
+          put_sgr_16(ws, false, bl < 127 ? 15u : 0u);     // foreground.c:804-808
+        }
+        put_glyph(ws, lut->glyph[luma_of(load_px(px))]);  // cache[Y] (:820) or, through the Q2 table, cache[ramp] (:722)
         o = (uint32_t)(ws.p - out);
       }
       __syncthreads();
@@ -263,6 +268,18 @@ __global__ void __launch_bounds__(256) k_dither_bg(const uint8_t *cells, int w, 
     }
     __syncthreads();
   }
+}
+
+// ------------------------------------------------------------------ exhaustive quantiser tables (parity aid)
+// out[r << 16 | g << 8 | b] = rgb_to_256color (which = 0) / rgb_to_16color (which = 1) exactly as the emitters compute
+// them: the whole 2^24 colour space in one launch, compared against the reference's table in the tests.
+__global__ void __launch_bounds__(256) k_quantize_table(int which, uint8_t *out) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  out[i] = (uint8_t)(which == 0 ? q256_of(i) : q16_of(i));
+}
+cudaError_t launch_quantize_table(int which, uint8_t *d_out, cudaStream_t st) {
+  k_quantize_table<<<(1u << 24) / 256u, 256, 0, st>>>(which, d_out);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ launchers
@@ -370,8 +387,9 @@ cudaError_t launch_resize_nn_only(const uint8_t *src, int sw, int sh, uint8_t *d
 }
 
 cudaError_t launch_dither_bg(const uint8_t *cells, int w, int h, int n_frames, int pad_left, const GlyphLut *lut,
-                             uint8_t *rows, uint32_t row_pitch, RowMeta *meta, int *err_scratch, cudaStream_t st) {
-  k_dither_bg<<<(unsigned)n_frames, 256, 0, st>>>(cells, w, h, pad_left, lut, rows, row_pitch, meta, err_scratch);
+                             uint8_t *rows, uint32_t row_pitch, RowMeta *meta, int *err_scratch, int fg_only,
+                             cudaStream_t st) {
+  k_dither_bg<<<(unsigned)n_frames, 256, 0, st>>>(cells, w, h, pad_left, lut, rows, row_pitch, meta, err_scratch, fg_only);
   return cudaGetLastError();
 }
 

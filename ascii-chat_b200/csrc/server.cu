@@ -435,7 +435,7 @@ char *acb200_grid_frame(const int *slots, int n, int cell_width, int cell_height
     }
     const size_t cap_before = *scratch_cap;
     bool ok = grow_device(scratch, scratch_cap, scratch_bytes(j.pl, 1));
-    const bool will_be_direct = j.pl.mode != EM_DITHER_BG && j.pl.use_smem_out && j.pl.scale_path != SP_BOX_TMA;
+    const bool will_be_direct = !is_dither_mode(j.pl.mode) && j.pl.use_smem_out && j.pl.scale_path != SP_BOX_TMA;
     if (ok && (*scratch_cap != cap_before || *dirty || !will_be_direct)) {
       ok = cudaMemsetAsync(*scratch, 0, *scratch_cap, st) == cudaSuccess;
       *lb = LookbackState();

@@ -110,11 +110,12 @@ char *image_print_with_capabilities(const image_t *image, const terminal_capabil
 /* lib/video/rgba/image.c:256-328 (image.h:574) — nearest-neighbour resize into dest->pixels */
 void image_resize(const image_t *source, image_t *dest);
 
-/* leaf printers, lib/video/ascii/scalar/foreground.c:27,195,433,535,752 and halfblock.c:48,184,297,416 */
+/* leaf printers, lib/video/ascii/scalar/foreground.c:27,195,433,535,650,752 and halfblock.c:48,184,297,416 */
 char *image_print(const image_t *p, const char *palette);
 char *image_print_color(const image_t *p, const char *palette);
 char *image_print_256color(const image_t *image, const char *palette);
 char *image_print_16color(const image_t *image, const char *palette);
+char *image_print_16color_dithered(const image_t *image, const char *palette);                     /* :650-749 */
 char *image_print_16color_dithered_with_background(const image_t *image, bool use_background, const char *palette);
 char *rgb_to_truecolor_halfblocks_scalar(const uint8_t *rgb, int width, int height, int stride_bytes);
 char *rgb_to_halfblocks_scalar(const uint8_t *rgb, int width, int height, int stride_bytes, const char *palette);
@@ -134,6 +135,11 @@ char *ascii_create_grid(ascii_frame_source_t *sources, int source_count, int wid
  * host buffer (H2D, k_color_filter, D2H).  0 on success, -1 on NULL / zero size / unknown filter, like the
  * reference.  filter = color_filter_t (0 none .. 12 rainbow, include/ascii-chat/platform/terminal.h:601-627). */
 int apply_color_filter(uint8_t *pixels, uint32_t width, uint32_t height, uint32_t stride, int filter, float time);
+/* lib/video/rgba/color_filter.c:348-408 — every truecolor-foreground SGR of a finished string replaced by the rainbow
+ * colour at time_seconds (H2D, three scan launches, D2H).  NULL when the string is NULL or holds no "ESC[38;2;".
+ * (acb200_display_convert fuses the same replacement into the emitters; this is the entry for a caller that already
+ * holds a string, src/common/session/display.c:640-649.) */
+char *rainbow_replace_ansi_colors(const char *ansi_string, float time_seconds);
 /* lib/video/rgba/color_filter.c:165-236 — hue of the rainbow filter at `time` (host float, like aspect_ratio) */
 void color_filter_calculate_rainbow(float time, uint8_t *r, uint8_t *g, uint8_t *b);
 
@@ -178,9 +184,9 @@ int acb200_device_count(void);   /* devices in the pool (0 before initialisation
 int acb200_device_at(int k);     /* CUDA ordinal of the k-th pool device, -1 if out of range */
 int acb200_bind_thread(int k);
 int acb200_thread_device(void);  /* CUDA ordinal the calling thread is leased to (leases one if it has none), -1 on error */
-/* How a caller waits for its frame: 0 = spin (cudaStreamSynchronize), 1 = sleep on a blocking-sync event, 2 = poll for
- * spin_us microseconds, then sleep (default, 30 us).  Sleeping callers leave their cores to the staging copies of the
- * other render threads. */
+/* How a caller waits for its frame: 0 = spin (cudaStreamSynchronize; default — fastest on every box measured, see
+ * profiles/r02a_e2e_sweep_pixels.txt), 1 = sleep on a blocking-sync event, 2 = poll for spin_us microseconds, then sleep.
+ * Sleeping callers leave their cores to the other render threads at the price of the wake-up latency. */
 void acb200_set_sync_mode(int mode, int spin_us);
 void acb200_shutdown(void);
 int acb200_last_error(void);            /* thread-local, cleared on read */
@@ -229,6 +235,10 @@ void acb200_grid_layout(const int *ws, const int *hs, int n, int term_w, int ter
 /* aspect fit (host float arithmetic, lib/util/aspect_ratio.c:70-93) */
 void acb200_aspect_ratio(ssize_t img_w, ssize_t img_h, ssize_t width, ssize_t height, bool stretch, ssize_t *out_w,
                          ssize_t *out_h);
+
+/* parity aid: rgb_to_256color (which = 0) / rgb_to_16color (which = 1) as the kernels compute them, over the whole
+ * colour space: d_out[r << 16 | g << 8 | b], 16 MiB of device memory */
+int acb200_quantize_table_device(int which, uint8_t *d_out, void *stream);
 
 /* number of kernel launches issued by this library since load (bench "gpu_launches") */
 uint64_t acb200_launch_count(void);

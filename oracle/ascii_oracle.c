@@ -378,12 +378,19 @@ static char *print_true_fg(const uint8_t *rgb, int w, int h, const char *pal, si
   return bb_finish(&o, out_len);
 }
 
-/* 16-colour Floyd–Steinberg with background — image_print_16color_dithered_with_background
- * (foreground.c:752-846) + rgb_to_16color_dithered (ansi.c:511-583).  Reached for
- * TRUECOLOR+BACKGROUND in SIMD builds (sgr.c:429-430, quirk Q4).  Serial by nature. */
-static char *print_dither_bg(const uint8_t *rgb, int w, int h, const char *pal, size_t *out_len) {
+/* 16-colour Floyd–Steinberg — the three dithered printers of foreground.c, one raster-order recurrence
+ * (rgb_to_16color_dithered, ansi.c:511-583):
+ *   variant 0  image_print_16color_dithered_with_background(img, true)  (foreground.c:752-846): bg = dithered colour,
+ *              fg = 15/0 by the luminance of the QUANTISED colour, glyph = cache[Y].  Reached for
+ *              TRUECOLOR+BACKGROUND in SIMD builds (sgr.c:429-430, quirk Q4).
+ *   variant 1  image_print_16color_dithered_with_background(img, false): fg = dithered colour, glyph = cache[Y]
+ *   variant 2  image_print_16color_dithered(img) (foreground.c:650-749): fg = dithered colour,
+ *              glyph = cache[char_index_ramp[Y>>2]] (the Q2 double mapping of image_print_16color)
+ * Serial by nature. */
+char *orc_print_dither(const uint8_t *rgb, int w, int h, const char *pal, int variant, size_t *out_len) {
   uint8_t lut[256][5];
-  if (orc_build_glyph_lut(pal, 0, lut, NULL) < 0) return NULL;
+  if (!rgb || !pal || w <= 0 || h <= 0) return NULL;
+  if (orc_build_glyph_lut(pal, variant == 2 ? 2 : 0, lut, NULL) < 0) return NULL;
   int *err = calloc((size_t)w * h * 3, sizeof(int));
   bb_t o = {0};
   for (int y = 0; y < h; y++) {
@@ -405,9 +412,13 @@ static char *print_dither_bg(const uint8_t *rgb, int w, int h, const char *pal, 
           if (x + 1 < w) err[(i + w + 1) * 3 + k] += (e * 1) / 16;
         }
       }
-      int bl = (k_ansi16[q][0] * 77 + k_ansi16[q][1] * 150 + k_ansi16[q][2] * 29) / 256;
-      put_sgr_16(&o, 1, q);
-      put_sgr_16(&o, 0, bl < 127 ? 15 : 0);
+      if (variant == 0) {
+        int bl = (k_ansi16[q][0] * 77 + k_ansi16[q][1] * 150 + k_ansi16[q][2] * 29) / 256;
+        put_sgr_16(&o, 1, q);
+        put_sgr_16(&o, 0, bl < 127 ? 15 : 0);
+      } else {
+        put_sgr_16(&o, 0, q);
+      }
       put_glyph(&o, lut[orc_luma(p[0], p[1], p[2])]);
     }
     put_reset(&o);
@@ -415,6 +426,9 @@ static char *print_dither_bg(const uint8_t *rgb, int w, int h, const char *pal, 
   }
   free(err);
   return bb_finish(&o, out_len);
+}
+static char *print_dither_bg(const uint8_t *rgb, int w, int h, const char *pal, size_t *out_len) {
+  return orc_print_dither(rgb, w, h, pal, 0, out_len);
 }
 
 /* half-block family — halfblock.c:48-165 (truecolor), 416-524 (256), 297-405 (16), 184-286 (mono).

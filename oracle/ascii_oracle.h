@@ -47,6 +47,10 @@ void orc_resize_box(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, in
 char *orc_print(const uint8_t *rgb, int w, int h, int color_level, int render_mode, const char *palette,
                 size_t *out_len);
 
+/* the dithered leaf printers (foreground.c:650-846): variant 0 = ..._with_background(img, true), 1 = ..._with_background(img,
+ * false), 2 = image_print_16color_dithered(img) */
+char *orc_print_dither(const uint8_t *rgb, int w, int h, const char *palette, int variant, size_t *out_len);
+
 /* full convert (ascii_convert_with_capabilities, ascii.c:194-387), scale = ORC_SCALE_* */
 char *orc_convert_caps(const uint8_t *rgb, int w, int h, long width, long height, int color_level, int render_mode,
                        int wants_padding, int use_aspect_ratio, int stretch, const char *palette, int scale,

@@ -136,6 +136,8 @@ def port():
     L.orc_apply_color_filter.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_float]
     L.orc_rainbow_replace.restype = C.c_void_p
     L.orc_rainbow_replace.argtypes = [C.c_char_p, C.c_float]
+    L.orc_print_dither.restype = C.c_void_p
+    L.orc_print_dither.argtypes = [u8p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_size_t)]
     L.orc_display_convert.restype = C.c_void_p
     L.orc_display_convert.argtypes = [u8p, C.c_int, C.c_int, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
@@ -209,6 +211,10 @@ def ref():
     L.color_filter_calculate_rainbow.argtypes = [C.c_float, u8p, u8p, u8p]
     L.rainbow_replace_ansi_colors.restype = C.c_void_p
     L.rainbow_replace_ansi_colors.argtypes = [C.c_char_p, C.c_float]
+    L.image_print_16color_dithered.restype = C.c_void_p
+    L.image_print_16color_dithered.argtypes = [ip, C.c_char_p]
+    L.image_print_16color_dithered_with_background.restype = C.c_void_p
+    L.image_print_16color_dithered_with_background.argtypes = [ip, C.c_bool, C.c_char_p]
     L.ref_oracle_display_convert.restype = C.c_void_p
     L.ref_oracle_display_convert.argtypes = [u8p, C.c_int, C.c_int, C.c_long, C.c_long, cp, C.c_int, C.c_int,
                                              C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_size_t)]
@@ -285,6 +291,38 @@ def ref_print(img, level, mode, palette="standard"):
     im = Image(a.shape[1], a.shape[0], a.ctypes.data, 0)
     caps = make_caps(level, mode)
     return _take(ref().image_print_with_capabilities(C.byref(im), C.byref(caps), pal_bytes(palette)))
+
+
+def port_print_dither(img, palette="standard", variant=0):
+    """variant 0 = ..._with_background(img, true), 1 = ..._with_background(img, false), 2 = image_print_16color_dithered"""
+    a, p = as_u8(img)
+    n = C.c_size_t(0)
+    return _take(port().orc_print_dither(p, a.shape[1], a.shape[0], pal_bytes(palette), variant, C.byref(n)))
+
+
+def ref_print_dither(img, palette="standard", variant=0):
+    a, _ = as_u8(img)
+    im = Image(a.shape[1], a.shape[0], a.ctypes.data, 0)
+    if variant == 2:
+        return _take(ref().image_print_16color_dithered(C.byref(im), pal_bytes(palette)))
+    return _take(ref().image_print_16color_dithered_with_background(C.byref(im), variant == 0, pal_bytes(palette)))
+
+
+def ref_rainbow_replace(s, t):
+    return _take(ref().rainbow_replace_ansi_colors(s, float(t)))
+
+
+def port_rainbow_replace(s, t):
+    return _take(port().orc_rainbow_replace(s, float(t)))
+
+
+def ref_box_convert(img, cols, rows, level, mode, palette="standard"):
+    """box mode's checker is the COMPILED reference's printer fed the box-filtered image (the box filter
+    itself is this repo's specification, orc_resize_box; the reference has none)"""
+    a, _ = as_u8(img)
+    rows_px = rows * 2 if mode == 2 else rows
+    small = port_resize(a, cols, rows_px, scale=SCALE_BOX)
+    return ref_print(small, level, mode, palette)
 
 
 def ref_convert_legacy(img, cols, rows, color, aspect, stretch, palette="standard", opt_mode=0):

@@ -443,3 +443,22 @@ def test_kat_crc32c_reference_unit_tests(ob):
     assert crc(b"") == 0                                          # crc32_hw_test.c:14-21
     assert crc(b"Hello, World!") == 0x4D551068                    # :32-50, the one literal the reference pins
     assert crc(b"\x42") != 0 and crc(b"abc") != crc(b"abd") and crc(b"ascii-chat") == crc(b"ascii-chat")
+
+
+def test_port_vs_ref_dithered_printers(ob, ref_lib):
+    """the three Floyd–Steinberg leaf printers (foreground.c:650-749, 752-846 with and without background)"""
+    rng = np.random.default_rng(17)
+    for it in range(40):
+        w, h = int(rng.integers(1, 90)), int(rng.integers(1, 50))
+        img = ob.gen(("noise", "gradient", "bars", "grey")[it % 4], w, h, it)
+        for pal in ("standard", "blocks", "minimal"):
+            for variant in (0, 1, 2):
+                assert ob.port_print_dither(img, pal, variant) == ob.ref_print_dither(img, pal, variant), (it, pal, variant)
+
+
+def test_box_checker_agrees_with_port(ob, ref_lib):
+    """compiled reference's printer on the box-filtered image == the port's box convert"""
+    for (W, H, c, r) in ((640, 480, 80, 24), (333, 127, 47, 13), (100, 50, 130, 70)):
+        img = ob.gen("noise", W, H, 1)
+        for level, mode in ((0, 0), (1, 0), (2, 0), (3, 0), (3, 1), (0, 2), (1, 2), (2, 2), (3, 2)):
+            assert ob.ref_box_convert(img, c, r, level, mode) == ob.port_convert(img, c, r, level, mode, scale=ob.SCALE_BOX)
