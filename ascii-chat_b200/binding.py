@@ -67,7 +67,7 @@ EXPORTS = [  # every symbol include/asciichat_b200.h declares
     "acb200_init_devices", "acb200_device_count", "acb200_device_at", "acb200_bind_thread", "acb200_thread_device",
     "acb200_set_sync_mode", "acb200_source_acquire", "acb200_source_commit", "acb200_source_device",
     "acb200_grid_frame", "acb200_quantize_table_device", "image_print_16color_dithered",
-    "rainbow_replace_ansi_colors",
+    "rainbow_replace_ansi_colors", "acb200_mixed_cell_size", "acb200_resize_nn_device", "acb200_mixed_frame_device",
 ]
 
 
@@ -168,6 +168,13 @@ def lib():
     L.rainbow_replace_ansi_colors.restype = C.c_void_p
     L.rainbow_replace_ansi_colors.argtypes = [C.c_char_p, C.c_float]
     L.acb200_quantize_table_device.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    L.acb200_mixed_cell_size.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_ushort,
+                                         C.c_ushort, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.acb200_resize_nn_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.acb200_mixed_frame_device.restype = C.c_void_p
+    L.acb200_mixed_frame_device.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                                            C.c_int, C.c_ushort, C.c_ushort, C.POINTER(terminal_capabilities_t),
+                                            C.c_char_p, C.POINTER(C.c_size_t)]
     L.acb200_init_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
     L.acb200_device_at.argtypes = [C.c_int]
     L.acb200_bind_thread.argtypes = [C.c_int]
@@ -298,6 +305,36 @@ def source_update_pinned(slot, image):
         return last_error()[0] or -1
     C.memmove(p, a.ctypes.data, a.nbytes)  # stands in for the transport's recv() into the buffer
     return lib().acb200_source_commit(slot, a.shape[1], a.shape[0])
+
+
+def mixed_cell_size(ws, hs, i, width, height):
+    n = len(ws)
+    tw, th = C.c_int(0), C.c_int(0)
+    rc = lib().acb200_mixed_cell_size((C.c_int * n)(*ws), (C.c_int * n)(*hs), n, i, width, height, C.byref(tw),
+                                      C.byref(th))
+    if rc:
+        raise RuntimeError("acb200_mixed_cell_size failed: %s" % (last_error(),))
+    return tw.value, th.value
+
+
+def resize_nn_device(d_src, sw, sh, d_dst, dw, dh, stream=None):
+    rc = lib().acb200_resize_nn_device(d_src, sw, sh, d_dst, dw, dh, stream)
+    if rc:
+        raise RuntimeError("acb200_resize_nn_device failed: %s" % (last_error(),))
+
+
+def mixed_frame_device(d_ptrs, ws, hs, prefit, width, height, caps, palette_chars):
+    """-> bytes | None; the frames (or pre-fitted cell images) are on the calling thread's device"""
+    n = len(d_ptrs)
+    sz = C.c_size_t(0)
+    r = lib().acb200_mixed_frame_device((C.c_void_p * n)(*d_ptrs), (C.c_int * n)(*ws), (C.c_int * n)(*hs), n,
+                                        1 if prefit else 0, width, height, C.byref(caps), _pal(palette_chars),
+                                        C.byref(sz))
+    if not r:
+        return None
+    s = C.string_at(r, sz.value)
+    _libc.free(r)
+    return s
 
 
 def init_devices(devices=None):

@@ -217,6 +217,95 @@ int acb200_source_update_wire(int slot, const uint8_t *payload, size_t len) {
   return acb200_source_update(slot, payload + 8, (int)w, (int)h);
 }
 
+// stream.c:708-716: the contain-fitted size of source (w, h) inside a cellw x cellh pixel cell
+static void fit_in_cell(int w, int h, int cellw, int cellh, int *tw, int *th) {
+  const float src_aspect = (float)w / (float)h;
+  const float cell_visual_aspect = (float)cellw / (float)cellh;
+  if (src_aspect > cell_visual_aspect) {
+    *tw = cellw;
+    *th = (int)((cellw / src_aspect) + 0.5f);
+  } else {
+    *th = cellh;
+    *tw = (int)((cellh * src_aspect) + 0.5f);
+  }
+}
+
+// create_single_source_composite / create_multi_source_composite (stream.c:476-500, 664-779) + convert_composite_to_ascii
+// (:789-853) + the trailing-reset fix-up (:1085-1127) on `live` device-resident sources of ORIGINAL sizes ws x hs.
+// prefit: src[v] already holds source v nearest-neighbour-resized to its fitted size (the multi-GPU pixel-space gather:
+// every rank resizes its own clients, only the few-KB cell images travel) — sampling it 1:1 is the reference's blit.
+static char *compose_and_render(ThreadCtx *cx, const uint8_t *const *src, const int *ws, const int *hs, int live,
+                                bool prefit, unsigned short width, unsigned short height,
+                                const terminal_capabilities_t *caps, const char *palette, size_t *out_size, bool packet) {
+  const uint8_t *comp = src[0];
+  int comp_w = ws[0], comp_h = hs[0];
+  if (live > 1) { // create_multi_source_composite, stream.c:664-779
+    int gc, gr;
+    acb200_grid_layout(ws, hs, live, width, height, &gc, &gr);
+    const int CW = width, CH = (int)height * 2;
+    const size_t comp_bytes = (size_t)CW * CH * 3;
+    if (!grow_device(&cx->d_out, &cx->d_out_cap, comp_bytes + 16)) return nullptr;
+    const int cellw = CW / gc, cellh = CH / gr;
+    CompositeParams cp{};
+    cp.comp = cx->d_out;
+    cp.cw = CW;
+    cp.ch = CH;
+    cp.cellw = cellw;
+    cp.cellh = cellh;
+    cp.gcols = gc;
+    cp.grows = gr;
+    cp.n = live < 9 ? live : 9; // max 9 sources (:687)
+    for (int v = 0; v < cp.n && cellw > 0 && cellh > 0; v++) {
+      int tw, th;
+      fit_in_cell(ws[v], hs[v], cellw, cellh, &tw, &th);
+      CompositeCell &c = cp.cell[v];
+      if (tw <= 0 || th <= 0) continue; // the reference crashes here (NULL image, :723); we leave the cell black
+      c.src = src[v];
+      c.sw = prefit ? tw : ws[v];
+      c.sh = prefit ? th : hs[v];
+      c.tw = tw;
+      c.th = th;
+      c.xp = (cellw - tw) / 2; // :741-742
+      c.yp = (cellh - th) / 2;
+      c.xr = (uint32_t)((((uint64_t)c.sw << 16) / (uint64_t)tw) + 1);
+      c.yr = (uint32_t)((((uint64_t)c.sh << 16) / (uint64_t)th) + 1);
+    }
+    // clear (image_clear, :683) + every source's NN resize + clipped blit (:723-773) in one launch
+    if (cellw <= 0 || cellh <= 0) { // more grid columns/rows than pixels: nothing fits, the canvas stays black
+      if (cudaMemsetAsync(cx->d_out, 0, comp_bytes, cx->stream) != cudaSuccess) {
+        set_error(E_INVALID_STATE, "CUDA: clearing the composite failed");
+        return nullptr;
+      }
+    } else {
+      if (launch_composite_all(cp, cx->stream) != cudaSuccess) {
+        set_error(E_INVALID_STATE, "CUDA: composite launch failed");
+        return nullptr;
+      }
+      count_launch();
+    }
+    comp = cx->d_out;
+    comp_w = CW;
+    comp_h = CH;
+  }
+
+  // convert_composite_to_ascii, stream.c:829-842
+  const ssize_t h = caps->render_mode == RENDER_MODE_HALF_BLOCK ? (ssize_t)height * 2 : (ssize_t)height;
+  acb200_render_cfg_t cfg;
+  if (!plan_convert_with_caps(comp_w, comp_h, width, h, caps, true, false, palette, &cfg)) return nullptr;
+  // stream.c:1085-1127 (a frame must end in ESC[0m; otherwise it is cut after its last ESC[0m, if it has one) runs
+  // on the device (k_trailing_reset_fixup); packet = also CRC32-C + ascii_frame_packet_t header in front
+  OneFrameOpts opts;
+  opts.reset_fixup = true;
+  opts.packet = packet;
+  opts.pk_w = width;
+  opts.pk_h = height;
+  size_t len = 0;
+  char *frame = render_one_device(cfg, comp, &len, opts);
+  if (!frame) return nullptr;
+  *out_size = len;
+  return frame;
+}
+
 static char *mixed_frame_impl(const int *slots, int n, unsigned short width, unsigned short height,
                               const terminal_capabilities_t *caps, const char *palette, size_t *out_size,
                               int *out_sources_count, bool packet) {
@@ -278,81 +367,7 @@ static char *mixed_frame_impl(const int *slots, int n, unsigned short width, uns
     }
   }
 
-  const uint8_t *comp = src[0];
-  int comp_w = ws[0], comp_h = hs[0];
-  if (live > 1) { // create_multi_source_composite, stream.c:664-779
-    int gc, gr;
-    acb200_grid_layout(ws, hs, live, width, height, &gc, &gr);
-    const int CW = width, CH = (int)height * 2;
-    const size_t comp_bytes = (size_t)CW * CH * 3;
-    if (!grow_device(&cx->d_out, &cx->d_out_cap, comp_bytes + 16)) return nullptr;
-    const int cellw = CW / gc, cellh = CH / gr;
-    CompositeParams cp{};
-    cp.comp = cx->d_out;
-    cp.cw = CW;
-    cp.ch = CH;
-    cp.cellw = cellw;
-    cp.cellh = cellh;
-    cp.gcols = gc;
-    cp.grows = gr;
-    cp.n = live < 9 ? live : 9; // max 9 sources (:687)
-    for (int v = 0; v < cp.n; v++) {
-      const float src_aspect = (float)ws[v] / (float)hs[v];
-      const float cell_visual_aspect = (float)cellw / (float)cellh;
-      int tw, th;
-      if (src_aspect > cell_visual_aspect) { // :708-716
-        tw = cellw;
-        th = (int)((cellw / src_aspect) + 0.5f);
-      } else {
-        th = cellh;
-        tw = (int)((cellh * src_aspect) + 0.5f);
-      }
-      CompositeCell &c = cp.cell[v];
-      if (tw <= 0 || th <= 0) continue; // the reference crashes here (NULL image, :723); we leave the cell black
-      c.src = src[v];
-      c.sw = ws[v];
-      c.sh = hs[v];
-      c.tw = tw;
-      c.th = th;
-      c.xp = (cellw - tw) / 2; // :741-742
-      c.yp = (cellh - th) / 2;
-      c.xr = (uint32_t)((((uint64_t)ws[v] << 16) / (uint64_t)tw) + 1);
-      c.yr = (uint32_t)((((uint64_t)hs[v] << 16) / (uint64_t)th) + 1);
-    }
-    // clear (image_clear, :683) + every source's NN resize + clipped blit (:723-773) in one launch
-    if (cellw <= 0 || cellh <= 0) { // more grid columns/rows than pixels: nothing fits, the canvas stays black
-      if (cudaMemsetAsync(cx->d_out, 0, comp_bytes, cx->stream) != cudaSuccess) {
-        set_error(E_INVALID_STATE, "CUDA: clearing the composite failed");
-        return nullptr;
-      }
-    } else {
-      if (launch_composite_all(cp, cx->stream) != cudaSuccess) {
-        set_error(E_INVALID_STATE, "CUDA: composite launch failed");
-        return nullptr;
-      }
-      count_launch();
-    }
-    comp = cx->d_out;
-    comp_w = CW;
-    comp_h = CH;
-  }
-
-  // convert_composite_to_ascii, stream.c:829-842
-  const ssize_t h = caps->render_mode == RENDER_MODE_HALF_BLOCK ? (ssize_t)height * 2 : (ssize_t)height;
-  acb200_render_cfg_t cfg;
-  if (!plan_convert_with_caps(comp_w, comp_h, width, h, caps, true, false, palette, &cfg)) return nullptr;
-  // stream.c:1085-1127 (a frame must end in ESC[0m; otherwise it is cut after its last ESC[0m, if it has one) runs
-  // on the device (k_trailing_reset_fixup); packet = also CRC32-C + ascii_frame_packet_t header in front
-  OneFrameOpts opts;
-  opts.reset_fixup = true;
-  opts.packet = packet;
-  opts.pk_w = width;
-  opts.pk_h = height;
-  size_t len = 0;
-  char *frame = render_one_device(cfg, comp, &len, opts);
-  if (!frame) return nullptr;
-  *out_size = len;
-  return frame;
+  return compose_and_render(cx, src, ws, hs, live, false, width, height, caps, palette, out_size, packet);
 }
 
 // The discovery host's render tick (src/common/session/host.c:664-717) with resident sources, across the GPUs of the pool:
@@ -488,6 +503,64 @@ char *acb200_grid_frame(const int *slots, int n, int cell_width, int cell_height
   r[res] = '\0';
   *out_size = exact ? res : strlen(r); // ascii.c:650,705,785 vs :883
   return r;
+}
+
+// ---- pixel-space composition from device pointers (the multi-process gather path) ----------------
+// The fitted size of source i inside its grid cell for a width x height terminal — what create_multi_source_composite
+// resizes it to (stream.c:690-724).  One source: its own size (create_single_source_composite uses the frame as is).
+int acb200_mixed_cell_size(const int *ws, const int *hs, int n, int i, unsigned short width, unsigned short height,
+                           int *tw, int *th) {
+  if (!ws || !hs || !tw || !th || n <= 0 || i < 0 || i >= n || width == 0 || height == 0)
+    return set_error(E_INVALID_PARAM, "acb200_mixed_cell_size: bad argument");
+  *tw = *th = 0;
+  if (n == 1) {
+    *tw = ws[0], *th = hs[0];
+    return E_OK;
+  }
+  if (i >= 9) return E_OK; // only nine are placed (stream.c:687)
+  int gc, gr;
+  acb200_grid_layout(ws, hs, n, width, height, &gc, &gr);
+  const int cellw = width / gc, cellh = (int)height * 2 / gr;
+  if (cellw > 0 && cellh > 0) fit_in_cell(ws[i], hs[i], cellw, cellh, tw, th);
+  if (*tw <= 0 || *th <= 0) *tw = *th = 0;
+  return E_OK;
+}
+// image_resize (image.c:256-328) between device buffers, asynchronous on `stream` (NULL = the thread's own stream)
+int acb200_resize_nn_device(const uint8_t *d_src, int sw, int sh, uint8_t *d_dst, int dw, int dh, void *stream) {
+  if (!d_src || !d_dst || sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0)
+    return set_error(E_INVALID_PARAM, "acb200_resize_nn_device: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!st) {
+    ThreadCtx *cx = thread_ctx();
+    if (!cx) return acb200_last_error();
+    st = cx->stream;
+  } else if (ensure_device() != 0) {
+    return acb200_last_error();
+  }
+  ACB_CUDA(launch_resize_nn_only(d_src, sw, sh, d_dst, dw, dh, 0, st));
+  count_launch();
+  return E_OK;
+}
+// create_mixed_ascii_frame_for_client's composite + convert on n sources that are on this thread's device already:
+// d_srcs[i] = frame i at its ORIGINAL size ws[i] x hs[i] (prefit = 0), or already resized to acb200_mixed_cell_size()
+// (prefit = 1; n == 1: the frame itself).  Runs on the thread's own stream; returns like acb200_mixed_frame.
+char *acb200_mixed_frame_device(const uint8_t *const *d_srcs, const int *ws, const int *hs, int n, int prefit,
+                                unsigned short width, unsigned short height, const terminal_capabilities_t *caps,
+                                const char *palette, size_t *out_size) {
+  if (!out_size || width == 0 || height == 0 || !d_srcs || !ws || !hs || n <= 0 || n > ACB200_MAX_SOURCES || !caps ||
+      !palette) {
+    set_error(E_INVALID_PARAM, "acb200_mixed_frame_device: bad argument");
+    return nullptr;
+  }
+  *out_size = 0;
+  for (int i = 0; i < n; i++)
+    if (ws[i] <= 0 || hs[i] <= 0 || (!d_srcs[i] && i < 9)) {
+      set_error(E_INVALID_PARAM, "acb200_mixed_frame_device: source %d invalid", i);
+      return nullptr;
+    }
+  ThreadCtx *cx = thread_ctx();
+  if (!cx) return nullptr;
+  return compose_and_render(cx, d_srcs, ws, hs, n, prefit != 0, width, height, caps, palette, out_size, false);
 }
 
 char *acb200_mixed_frame(const int *slots, int n, unsigned short width, unsigned short height,

@@ -162,6 +162,8 @@ class GridPipeline:
                                         self.lens.data_ptr(), self.scr.data_ptr(), s.cuda_stream)
             gather_fixed(self.arena, self.lens, self.all_arena, self.all_lens, group=self.group)
             if self.rank != self.dst:
+                # the caller may reuse `batch` as soon as this returns: its stream must wait for the render queued here
+                torch.cuda.current_stream().wait_stream(s)
                 return None
             self.h_lens.copy_(self.all_lens, non_blocking=True)
             s.synchronize()
@@ -175,3 +177,49 @@ class GridPipeline:
             self.h_canvas[:size].copy_(self.canvas[:size], non_blocking=True)
             s.synchronize()
             return self.h_canvas[:size].numpy().tobytes()
+
+
+class PixelGridPipeline:
+    """BASELINE config 4, pixel-space (the server's compositor, src/server/stream.c:664-779), sharded over the ranks:
+    SURVEY.md §8e "gather the NN-resized cell images".  Rank r holds the frames of clients c % world == r, resizes
+    each to the size create_multi_source_composite would give it in a W x 2H composite (acb200_mixed_cell_size +
+    acb200_resize_nn_device: a few KB per client instead of 6.2 MB), one fixed-pitch all-gather moves the cell images,
+    and the composing rank blits + converts them with acb200_mixed_frame_device(prefit=1): byte-identical to
+    create_mixed_ascii_frame_for_client on the full frames."""
+
+    def __init__(self, acb, sizes, W, H, caps, palette, dst=0, group=None):
+        """sizes: [(w, h)] of ALL n clients (every rank knows the geometry; only pixels are sharded)"""
+        self.acb, self.W, self.H, self.caps, self.palette, self.dst, self.group = acb, W, H, caps, palette, dst, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n = len(sizes)
+        self.ws, self.hs = [s[0] for s in sizes], [s[1] for s in sizes]
+        self.mine = shard_indices(self.n, self.rank, self.world)
+        self.per_rank = (self.n + self.world - 1) // self.world
+        self.cell = [acb.mixed_cell_size(self.ws, self.hs, i, W, H) for i in range(self.n)]
+        self.pitch = (max(tw * th * 3 for tw, th in self.cell) + 255) // 256 * 256 or 256
+        dev = torch.device("cuda")
+        self.local = torch.zeros(self.per_rank * self.pitch, dtype=torch.uint8, device=dev)
+        self.all = torch.empty(self.world * self.per_rank * self.pitch, dtype=torch.uint8, device=dev)
+        self.stream = torch.cuda.Stream()
+
+    def step(self, frames):
+        """frames: list of contiguous uint8 CUDA tensors (h, w, 3), frames[k] = client self.mine[k].
+        Returns the frame string on dst, None elsewhere."""
+        acb, s = self.acb, self.stream
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for k, i in enumerate(self.mine):
+                tw, th = self.cell[i]
+                if tw > 0 and th > 0 and self.n > 1:
+                    acb.resize_nn_device(frames[k].data_ptr(), self.ws[i], self.hs[i],
+                                         self.local.data_ptr() + k * self.pitch, tw, th, s.cuda_stream)
+                elif self.n == 1:
+                    self.local[: frames[k].numel()] = frames[k].reshape(-1)
+            dist.all_gather_into_tensor(self.all, self.local, group=self.group)
+            if self.rank != self.dst:
+                torch.cuda.current_stream().wait_stream(s)
+                return None
+            s.synchronize()  # acb200_mixed_frame_device runs on the library's own stream for this thread
+            base = self.all.data_ptr()
+            ptrs = [base + arena_slot(i, self.world, self.per_rank) * self.pitch for i in range(self.n)]
+            return acb.mixed_frame_device(ptrs, self.ws, self.hs, True, self.W, self.H, self.caps, self.palette)

@@ -7,18 +7,25 @@ with the reference's CPU path timed on the same box.
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU)
 
 Workload (config.workload): BASELINE configs[2]/[4] — 3840x2160 RGB24 -> 320x96 truecolor half-block cells.
-  value     resident path: box-filter downscale (every source pixel read once: 3 B/px algorithmic), a ring of 256
-            distinct frames per GPU already in HBM (6.37 GB per pass >> 126 MB L2, so no L2 flush is needed).
-            A step = one pass of the render path over the 256-frame batch, device-timed with CUDA events.
-  e2e       the reference-facing call ascii_convert_with_capabilities() (reference-exact nearest-neighbour mode:
-            same bytes as the reference) from HOST frames, driven by the same neutral pthread harness as the
-            reference arm (bench_harness/caller_threads.c: one caller thread per client, like src/server/render.c).
-  e2e_box   same call with the library's downscale switched to the box filter: full frames cross PCIe.
+  value      resident path: box-filter downscale (every source pixel read once: 3 B/px algorithmic), a ring of 256
+             distinct frames per GPU already in HBM (6.37 GB per pass >> 126 MB L2, so no L2 flush is needed).
+             A step = one pass of the render path over the 256-frame batch, device-timed with CUDA events.
+  sustained  BASELINE config 5: 100 000 frame-renders (391 passes over the ring), same kernel, clocks sampled inside.
+  e2e        the reference-facing call ascii_convert_with_capabilities() (reference-exact nearest-neighbour mode:
+             same bytes as the reference) from HOST frames, driven by the same neutral pthread harness as the
+             reference arm (bench_harness/caller_threads.c: one caller thread per client, like src/server/render.c),
+             ONE process driving all N GPUs through the C ABI (acb200_init_devices) — the server's own structure.
+             e2e_per_rank_processes: the same call with one process per GPU (N > 1 only).
+  e2e_box    same call with the library's downscale switched to the box filter: full frames cross PCIe (N = 1).
+  c4         BASELINE config 4 at every N: 8 clients x 1080p -> 160x48 ANSI-256 -> 320x96 grid, text-space
+             (ascii_create_grid) and pixel-space (the server compositor), sharded over the GPUs — NCCL gather between
+             rank processes, and peer stores/loads over NVLink inside one process.
 Frames are independent, so ranks take disjoint rings with no data-path collective ("scaling": "weak").
 One JSON line is printed by rank 0.  See DESIGN.md §6 for what each field means.
 """
 import argparse
 import ctypes as C
+import datetime
 import json
 import os
 import statistics
@@ -37,6 +44,8 @@ FRAME_BYTES = SRC_W * SRC_H * 3
 MPIX = SRC_W * SRC_H / 1e6
 METRIC = "Mpixels/s fused RGB->glyph render at 4K"
 PALETTE = b"   ...',;:clodxkO0KXNWM"
+C5_FRAMES = 100000  # BASELINE config 5
+CALLERS_PER_GPU = 16  # knee of the caller sweep on one PCIe link (profiles/r02a_e2e_sweep_pixels.txt)
 
 
 def peaks():
@@ -89,7 +98,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
@@ -97,13 +106,14 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------- shared harness
@@ -171,6 +181,48 @@ def cpu_reference_leg(H, frames, threads, seconds_target):
     return r, kind, fp
 
 
+def cpu_box_leg(frames, threads, seconds_target):
+    """Same-work CPU baseline for `value`: the box filter of DESIGN.md §3 on the CPU
+    (oracle's column-sum arrangement, AVX2) + the compiled reference's own printer on the filtered image."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_bind as ob
+    u8p = C.POINTER(C.c_uint8)
+    R = ob.ref()
+    fn = C.cast(R.image_print_with_capabilities, C.c_void_p) if R is not None else None
+    caps = ob.make_caps(LEVEL, MODE)
+    nb = C.c_uint64(0)
+
+    def run(calls):
+        return ob.port().orc_bench_box(frames.ctypes.data_as(u8p), frames.shape[0], SRC_W, SRC_H, COLS, ROWS * 2, LEVEL,
+                                       MODE, PALETTE, calls, threads, fn, C.byref(caps) if fn else None, C.byref(nb))
+    w = threads * 2
+    t = run(w)
+    calls = max(w, int(seconds_target / max(t / w, 1e-6)))
+    t = run(calls)
+    return {"value": calls * MPIX / t, "unit": "Mpix/s", "cores": threads, "calls": calls, "seconds": t,
+            "kind": "port box filter + %s printer" % ("reference" if fn else "port")}
+
+
+def host_bytes_per_frame(out_bytes):
+    """host DRAM traffic one e2e frame causes: 64-byte lines of the source the gather touches, the
+    staged pixels written and DMA-read, the string DMA-written into pinned memory, then copied into malloc'd memory"""
+    xr = ((SRC_W << 16) // COLS) + 1
+    yr = ((SRC_H << 16) // (ROWS * 2)) + 1
+    lines = set()
+    R = SRC_W * 3
+    for y in range(ROWS * 2):
+        sy = min((y * yr) >> 16, SRC_H - 1)
+        for x in range(COLS):
+            o = sy * R + min((x * xr) >> 16, SRC_W - 1) * 3
+            lines.add(o >> 6)
+            lines.add((o + 2) >> 6)
+    staged = COLS * ROWS * 2 * 3
+    return {"source_lines_read": len(lines) * 64, "staging_written": staged, "h2d_dma_read": staged,
+            "d2h_dma_written": out_bytes, "string_copy_read": out_bytes, "string_copy_written": out_bytes,
+            "total": len(lines) * 64 + 2 * staged + 3 * out_bytes}
+
+
+# ------------------------------------------------------------------------------------------- legs
 def server_path_leg(acb, with_reference):
     """the server's per-client entry (stream.c:958-1191) with the senders' frames resident in
     HBM — 9 clients sending 720p, each receiving client a 240x67 truecolor half-block terminal, one render thread
@@ -181,12 +233,22 @@ def server_path_leg(acb, with_reference):
     n, sw, sh, W, H = 9, 1280, 720, 240, 67
     rng = np.random.default_rng(777)
     srcs = [rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8) for _ in range(n)]
+    upd = upd_pinned = 0.0
     for rnd in range(3):  # the first rounds size the slots' double buffers and the staging; time the steady state
         t0 = time.perf_counter()
         for i, s in enumerate(srcs):
             if acb.source_update(i, s) != 0:
                 return {"error": str(acb.last_error())}
         upd = (time.perf_counter() - t0) / n
+    for i in range(n):  # the receive-into-pinned form: the transport's buffer is the slot's registered one
+        acb.lib().acb200_source_acquire(i, srcs[i].nbytes)
+    for rnd in range(3):
+        t0 = time.perf_counter()
+        for i, s in enumerate(srcs):
+            acb.lib().acb200_source_commit(i, sw, sh)
+        upd_pinned = (time.perf_counter() - t0) / n
+    for i, s in enumerate(srcs):
+        acb.source_update(i, s)
     caps = acb.make_caps(LEVEL, MODE, True)
     slots = list(range(n))
     first = acb.mixed_frame(slots, W, H, caps, "standard")
@@ -207,7 +269,8 @@ def server_path_leg(acb, with_reference):
     out = {"workload": "9 senders x 1280x720 RGB24 resident, 9 receiving clients x 240x67 truecolor half-block, padded",
            "api": "acb200_source_update() per received frame + acb200_mixed_frame() per (client, output frame)",
            "frames_per_s_9_render_threads": n * per / allc, "ms_per_frame_single_thread": one * 1e3,
-           "ms_per_source_update": upd * 1e3, "frame_bytes": first[1]}
+           "ms_per_source_update": upd * 1e3, "ms_per_source_commit_pinned": upd_pinned * 1e3,
+           "frame_bytes": first[1]}
     if with_reference:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_bind as ob
@@ -270,6 +333,41 @@ def device_extras_leg(acb, torch, d_out, cap, d_len, n, peak):
     return out
 
 
+def resident_variants_leg(acb, torch, peak):
+    """the other resident-batch shapes next to the headline (device-timed, 64-frame 4K batches): the reference-exact
+    nearest-neighbour mode on noise and on flat frames (latency/output-bound, not HBM-bound), and the box render with
+    a colour filter fused in."""
+    n = 64
+    out = {}
+    g = torch.Generator(device="cuda")
+    g.manual_seed(99)
+    noise = torch.randint(0, 256, (n, SRC_H, SRC_W, 3), dtype=torch.uint8, device="cuda", generator=g)
+    band = torch.randint(0, 256, (n, SRC_H // 40 + 1, 1, 3), dtype=torch.uint8, device="cuda", generator=g)
+    flat = band.repeat_interleave(40, dim=1)[:, :SRC_H].expand(n, SRC_H, SRC_W, 3).contiguous()
+
+    def run(d_in, **kw):
+        cfg = acb.make_cfg(SRC_W, SRC_H, COLS, ROWS * 2, LEVEL, MODE, "standard", **kw)
+        cap = acb.frame_capacity(cfg)
+        d_out = torch.empty(n * cap, dtype=torch.uint8, device="cuda")
+        d_len = torch.empty(n, dtype=torch.int32, device="cuda")
+        d_scr = torch.empty(acb.scratch_bytes(cfg, n), dtype=torch.uint8, device="cuda")
+        a = (cfg, d_in.data_ptr(), n, d_out.data_ptr(), cap, d_len.data_ptr(), d_scr.data_ptr())
+        acb.time_batch_device(*a, 8)
+        tot, ker = acb.time_batch_device(*a, 20)
+        return tot / 20, ker / 20
+    for name, d_in in (("noise", noise), ("flat", flat)):
+        ms, _ = run(d_in, scale=acb.SCALE_NN)
+        out["nn_" + name] = {"ms_per_256_frames": ms * 256 / n, "frames_per_s": n / ms * 1e3,
+                             "Mcells_per_s": n * COLS * ROWS / ms / 1e3}
+    ms, ker = run(noise, scale=acb.SCALE_BOX, color_filter=3)
+    gbs = n * FRAME_BYTES / (ker * 1e-3) / 1e9
+    out["box_filtered"] = {"filter": "green (apply_color_filter fused into the band sums)", "ms_per_64_frames": ms,
+                           "achieved": gbs, "unit": "GB/s", "peak": peak, "frac": gbs / peak}
+    del noise, flat, band
+    torch.cuda.empty_cache()
+    return out
+
+
 def display_path_leg(acb, with_reference):
     """SURVEY.md §8f rows 1+3: the client's display conversion (display.c:484-671) — flip X, green colour filter,
     4K -> 320x96 truecolor half-block — as ONE call from a host frame; the reference leg runs its own functions in
@@ -305,6 +403,146 @@ def display_path_leg(acb, with_reference):
     return out
 
 
+# ---- BASELINE config 4: 8 clients x 1080p -> 160x48 ANSI-256 -> 320x96 grid
+C4_N, C4_W, C4_H, C4_COLS, C4_ROWS, C4_LEVEL, C4_MODE, C4_GW, C4_GH = 8, 1920, 1080, 160, 48, 2, 0, 320, 96
+
+
+def c4_sources(ob):
+    return [ob.gen(("noise", "bars", "gradient")[c % 3], C4_W, C4_H, c) for c in range(C4_N)]
+
+
+def c4_expected(ob, srcs, nul):
+    """the checker's answers: text grid of the checker's cells, and the server's mixed frame (both viewer sizes)"""
+    conv = ob.ref_convert if ob.ref() is not None else ob.port_convert
+    grid = ob.ref_create_grid if ob.ref() is not None else ob.port_create_grid
+    mixed = ob.ref_mixed_frame if ob.ref() is not None else ob.port_mixed_frame
+    cells = [conv(s, C4_COLS, C4_ROWS, C4_LEVEL, C4_MODE) for s in srcs]
+    g = grid([c + (b"\0" if nul else b"") for c in cells], C4_GW, C4_GH)
+    m = {(w, h): mixed(srcs, w, h, C4_LEVEL, C4_MODE, "standard", True)[0] for (w, h) in ((C4_COLS, C4_ROWS), (C4_GW, C4_GH))}
+    return g, m, "reference" if ob.ref() is not None else "port"
+
+
+def c4_nccl_leg(acb, torch, dist, rank, world):
+    """one process per GPU: clients sharded c % world, text-space = render + all-gather of the fixed-pitch arenas +
+    ascii_create_grid on rank 0 (multi.GridPipeline); pixel-space = NN-resize to the cell images + all-gather +
+    composite/convert on rank 0 (multi.PixelGridPipeline).  Wall clock around K steps, max over ranks."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_bind as ob
+    from ascii_chat_b200 import multi
+    srcs = c4_sources(ob)
+    mine = multi.shard_indices(C4_N, rank, world)
+    d_mine = [torch.from_numpy(srcs[c]).cuda() for c in mine]
+    res = {}
+
+    def timed(step, K=200, warm=20):
+        out = None
+        for _ in range(warm):
+            out = step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            out = step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return out, float(dt) / K
+    cfg = acb.make_cfg(C4_W, C4_H, C4_COLS, C4_ROWS, C4_LEVEL, C4_MODE)
+    pipe = multi.GridPipeline(acb, cfg, C4_N, C4_GW, C4_GH)
+    batch = torch.stack(d_mine).contiguous() if d_mine else None
+    g, t_text = timed(lambda: pipe.step(batch))
+    pix = {}
+    for (w, h) in ((C4_COLS, C4_ROWS), (C4_GW, C4_GH)):
+        pp = multi.PixelGridPipeline(acb, [(C4_W, C4_H)] * C4_N, w, h, acb.make_caps(C4_LEVEL, C4_MODE, True), "standard")
+        pix[(w, h)] = timed(lambda: pp.step(d_mine))
+    if rank == 0:
+        eg, em, kind = c4_expected(ob, srcs, nul=False)
+        res = {"text_space": {"ms_per_grid": t_text * 1e3, "grids_per_s": 1 / t_text,
+                              "collective": "all_gather(fixed-pitch string arenas) + all_gather(lengths)",
+                              "bytes_identical": bool(g == eg[0] or g == eg[0][:eg[1]]), "grid_bytes": len(g or b"")},
+               "pixel_space": {"%dx%d" % k: {"ms_per_frame": v[1] * 1e3, "frames_per_s": 1 / v[1],
+                                             "bytes_identical": bool(v[0] == em[k]), "frame_bytes": len(v[0] or b"")}
+                               for k, v in pix.items()},
+               "pixel_space_collective": "all_gather(NN-resized cell images, %d B per client)" % (53 * 30 * 3),
+               "checker": kind, "transport": "NCCL over NVLink, one process per GPU" if world > 1 else "NCCL, one rank"}
+    del d_mine, batch
+    return res
+
+
+def c4_inprocess(n_gpus):
+    """ONE process, n_gpus GPUs behind the C ABI: slots sharded c % n_gpus; acb200_grid_frame renders every cell on the
+    GPU that owns the client and stores its rows into the composing GPU's arena over NVLink; acb200_mixed_frame reads the
+    remote sources in place (peer loads).  Runs in its own process (the pool must be set up before any other call)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_bind as ob
+    import ascii_chat_b200 as acb
+    assert acb.init_devices(list(range(n_gpus))) == 0, acb.last_error()
+    acb.lib().acb200_bind_thread(0)
+    srcs = c4_sources(ob)
+    for rnd in range(2):
+        for i, s in enumerate(srcs):
+            assert acb.source_update(i, s) == 0, acb.last_error()
+    slots = list(range(C4_N))
+    eg, em, kind = c4_expected(ob, srcs, nul=True)
+
+    def timed(fn, K=300, warm=30):
+        out = None
+        for _ in range(warm):
+            out = fn()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            out = fn()
+        return out, (time.perf_counter() - t0) / K
+    caps_cell = acb.make_caps(C4_LEVEL, C4_MODE)
+    g, t_text = timed(lambda: acb.grid_frame(slots, C4_COLS, C4_ROWS, caps_cell, "standard", C4_GW, C4_GH))
+    res = {"n_gpus": n_gpus, "slot_devices": [acb.lib().acb200_source_device(i) for i in slots],
+           "text_space": {"ms_per_grid": t_text * 1e3, "grids_per_s": 1 / t_text, "api": "acb200_grid_frame()",
+                          "bytes_identical": bool(g == (eg[0], eg[1])), "grid_bytes": len(g[0] or b"")},
+           "pixel_space": {}, "checker": kind,
+           "transport": "peer stores / loads over NVLink inside one process" if n_gpus > 1 else "one GPU"}
+    caps_v = acb.make_caps(C4_LEVEL, C4_MODE, True)
+    for (w, h) in ((C4_COLS, C4_ROWS), (C4_GW, C4_GH)):
+        m, t = timed(lambda: acb.mixed_frame(slots, w, h, caps_v, "standard"))
+        res["pixel_space"]["%dx%d" % (w, h)] = {"ms_per_frame": t * 1e3, "frames_per_s": 1 / t,
+                                                "api": "acb200_mixed_frame()", "bytes_identical": bool(m[0] == em[(w, h)]),
+                                                "frame_bytes": len(m[0] or b"")}
+    for i in slots:
+        acb.source_clear(i)
+    acb.lib().acb200_shutdown()
+    return res
+
+
+def e2e_inprocess(n_gpus, threads, seconds):
+    """ONE process, n_gpus GPUs behind the C ABI, `threads` caller threads leased round-robin to the GPUs"""
+    import ascii_chat_b200 as acb
+    assert acb.init_devices(list(range(n_gpus))) == 0, acb.last_error()
+    H = load_harness()
+    frames = host_ring()
+    caps = acb.make_caps(LEVEL, MODE)
+    fn = C.cast(acb.lib().ascii_convert_with_capabilities, C.c_void_p)
+    acb.lib().acb200_set_default_scale(acb.SCALE_NN)
+    r = run_callers(H, fn, frames, caps, threads, seconds)
+    fp = H.harness_ring_fingerprint(fn, frames.ctypes.data, frames.shape[0], SRC_W, SRC_H, COLS, ROWS, C.byref(caps),
+                                    PALETTE)
+    one = run_callers(H, fn, frames, caps, 1, 1.0, warm_calls=8)
+    r.update({"threads": threads, "n_gpus": n_gpus, "ring_fingerprint": "%016x" % fp,
+              "single_caller_ms": 1e3 * one["seconds"] / one["calls"], "launches": acb.launch_count()})
+    acb.lib().acb200_shutdown()
+    return r
+
+
+def run_leg_subprocess(leg, n_gpus, extra=()):
+    """a leg that needs its own process (its own device pool): python bench.py --leg ... ; returns its JSON"""
+    cmd = [sys.executable, os.path.abspath(__file__), "--leg", leg, "--gpus", str(n_gpus)] + list(extra)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE",
+                                                             "GROUP_RANK", "ROLE_RANK", "TORCHELASTIC_RUN_ID")}
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"error": (r.stderr or r.stdout)[-600:]}
+    return json.loads(lines[-1])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -314,7 +552,17 @@ def main():
     ap.add_argument("--ring", type=int, default=RING)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident-only", action="store_true", help="profiling aid: only the device-timed resident loop")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--leg", default=None, choices=[None, "e2e-inprocess", "c4-inprocess"], help="internal")
+    ap.add_argument("--threads", type=int, default=0, help="internal (with --leg)")
     args = ap.parse_args()
+
+    if args.leg == "e2e-inprocess":
+        print(json.dumps(e2e_inprocess(args.gpus, args.threads or CALLERS_PER_GPU, 4.0)))
+        return
+    if args.leg == "c4-inprocess":
+        print(json.dumps(c4_inprocess(args.gpus)))
+        return
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -360,9 +608,11 @@ def main():
     import torch
     import ascii_chat_b200 as acb
 
+    store = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        store = dist.distributed_c10d._get_default_store()
     torch.cuda.set_device(local_rank)
     assert acb.lib().acb200_init(local_rank) == 0, acb.last_error()
 
@@ -377,6 +627,19 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(v) for v in t]
+
+    def rank0_alone(key, fn):
+        """rank 0 runs fn() while the other ranks SLEEP on the rendezvous store (an NCCL barrier would spin their cores,
+        which are the cores the host-side legs are measuring)"""
+        if world == 1:
+            return fn()
+        if rank == 0:
+            try:
+                return fn()
+            finally:
+                store.set(key, b"1")
+        store.wait([key], datetime.timedelta(seconds=1800))
+        return None
 
     # ---- resident (HBM -> HBM) throughput: device-timed with CUDA events on the launch stream
     n = args.ring
@@ -401,11 +664,30 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_total_max, ms_kernel_max = max_over_ranks([ms_total, ms_kernel])
     out_bytes = int(d_len.sum().item())
+
+    # ---- BASELINE config 5: 100 000 frame-renders over the resident ring, one timed region, clocks sampled inside
+    sustained = None
+    if not args.no_sustained and not args.resident_only:
+        passes = (C5_FRAMES + n - 1) // n
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        barrier()
+        s_total, s_kernel = acb.time_batch_device(*targs, passes)
+        barrier()
+        clocks2 = sampler2.stop() if rank == 0 else None
+        s_total_max, s_kernel_max = max_over_ranks([s_total, s_kernel])
+        sustained = {"frames_per_gpu": passes * n, "passes": passes, "seconds": s_total_max / 1e3,
+                     "value": world * passes * n * MPIX / (s_total_max * 1e-3), "unit": "Mpix/s",
+                     "kernel_GBs": passes * n * FRAME_BYTES / (s_kernel_max * 1e-3) / 1e9, "clocks": clocks2,
+                     "workload": "BASELINE config 5: %d frame-renders per GPU cycling the %d-frame resident ring" % (passes * n, n)}
     extras = None
     if rank == 0 and world == 1 and not args.resident_only:
         extras = device_extras_leg(acb, torch, d_out, cap, d_len, n, peaks()[0])
     del d_in, d_out, d_scr
     torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.resident_only:
+        extras.update(resident_variants_leg(acb, torch, peaks()[0]))
 
     if args.resident_only:
         if rank == 0:
@@ -415,10 +697,10 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- end to end: the reference-facing call from host frames, T caller threads (one per "client")
+    # ---- end to end, one process per GPU: every rank drives its own GPU with its share of the caller threads
     H = load_harness()
     frames = host_ring()
-    threads = max(4, min(32, ncores // max(1, world)))  # MAX_CLIENTS is 32 (include/ascii-chat/common/limits.h:26)
+    threads = max(2, min(CALLERS_PER_GPU, ncores // max(1, world)))
     caps = acb.make_caps(LEVEL, MODE)
     fn = C.cast(acb.lib().ascii_convert_with_capabilities, C.c_void_p)
     acb.lib().acb200_set_default_scale(acb.SCALE_NN)
@@ -427,74 +709,127 @@ def main():
     barrier()
     fp_nn = H.harness_ring_fingerprint(fn, frames.ctypes.data, frames.shape[0], SRC_W, SRC_H, COLS, ROWS,
                                        C.byref(caps), PALETTE)
-    acb.lib().acb200_set_default_scale(acb.SCALE_BOX)
-    barrier()
-    e_box = run_callers(H, fn, frames, caps, threads, 4.0)
-    barrier()
-    acb.lib().acb200_set_default_scale(acb.SCALE_NN)
-    nn_s, box_s = max_over_ranks([e_nn["seconds"], e_box["seconds"]])
-    calls_nn, calls_box = e_nn["calls"], e_box["calls"]  # same calibration on every rank is not guaranteed: sum them
-    tc = torch.tensor([calls_nn, calls_box, e_nn["failures"] + e_box["failures"]], dtype=torch.float64, device="cuda")
+    (nn_s,) = max_over_ranks([e_nn["seconds"]])
+    tc = torch.tensor([e_nn["calls"], e_nn["failures"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tc, op=dist.ReduceOp.SUM)
-    calls_nn_all, calls_box_all, failures = float(tc[0]), float(tc[1]), int(tc[2])
-
-    # single-caller latency of the drop-in call (what one render thread sees)
-    one = run_callers(H, fn, frames, caps, 1, 1.0, warm_calls=8)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peak, peak_src = peaks()
-    alg_bytes_launch = n * FRAME_BYTES  # 3 B per source pixel, x frames per launch
-    achieved = alg_bytes_launch / (ms_kernel_max / args.steps * 1e-3) / 1e9
-    value = world * args.steps * n * MPIX / (ms_total_max * 1e-3)
-    gathered = ROWS * 2 * SRC_W * 3  # NN mode moves only the 192 sampled source rows per frame
-    line = {
-        "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic (uniform-noise RGB24, worst case "
-        "for run-length: ~1.18 MB of ANSI per frame)", "config": config,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "kernel": "k_render_rows_ws2<EM_HB_TRUE> (role-split persistent, direct output)",
-                     "algorithmic_bytes_per_launch": alg_bytes_launch,
-                     "kernel_ms_per_launch": ms_kernel_max / args.steps,
-                     "output_bytes_per_launch": out_bytes,
-                     "achieved_incl_output_GBs": (alg_bytes_launch + out_bytes) / (ms_kernel_max / args.steps * 1e-3) / 1e9,
-                     "traffic": traffic_from_profiles()},
-        "e2e": {"value": calls_nn_all * MPIX / nn_s, "unit": "Mpix/s", "h2d_bytes_per_step": gathered,
-                "d2h_bytes_per_step": int(e_nn["bytes"] / max(1, e_nn["calls"])) + 4, "step": "one frame through the call",
-                "calls": int(calls_nn_all), "seconds": nn_s, "caller_threads_per_gpu": threads, "failures": failures,
-                "api": "ascii_convert_with_capabilities() — reference-exact nearest-neighbour mode, pageable host "
-                       "RGB24 in, malloc'd string out, same pthread harness as the reference arm",
-                "ring_fingerprint": "%016x" % fp_nn},
-        "e2e_box": {"value": calls_box_all * MPIX / box_s, "unit": "Mpix/s", "h2d_bytes_per_step": FRAME_BYTES,
-                    "d2h_bytes_per_step": int(e_box["bytes"] / max(1, e_box["calls"])) + 4, "calls": int(calls_box_all),
-                    "seconds": box_s, "api": "same call, acb200_set_default_scale(ACB200_SCALE_BOX): whole frames "
-                                             "cross PCIe (24.9 MB per frame)"},
-        "dropin_single_caller": {"ms_per_call": 1e3 * one["seconds"] / one["calls"],
-                                 "mpix_s": one["calls"] * MPIX / one["seconds"]},
-        "gpu_launches": int(launches), "clocks": clocks,
-    }
-    if not args.no_cpu_baseline:
-        r, kind, fp_ref = cpu_reference_leg(H, frames, ncores, 12.0)
-        line["cpu_baseline"] = {"value": r["calls"] * MPIX / r["seconds"], "unit": "Mpix/s", "cores": ncores,
-                                "kind": kind,
-                                "sample": "%d calls over a ring of %d uniform-noise 4K frames, %d caller threads, %.1f s"
-                                          % (r["calls"], frames.shape[0], ncores, r["seconds"]),
-                                "note": "reference path is nearest-neighbour: Mpix/s nominal (source px / time)"}
-        if fp_ref is not None:
-            line["e2e"]["bytes_identical_to_cpu_baseline"] = bool(fp_ref == fp_nn)
+    calls_nn_all, failures = float(tc[0]), int(tc[1])
+    e_box = one = None
     if world == 1:
-        line["server_path"] = server_path_leg(acb, not args.no_cpu_baseline)
-        line["display_path"] = display_path_leg(acb, not args.no_cpu_baseline)
-        if extras:
-            line.update(extras)
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        acb.lib().acb200_set_default_scale(acb.SCALE_BOX)
+        e_box = run_callers(H, fn, frames, caps, threads, 3.0)
+        acb.lib().acb200_set_default_scale(acb.SCALE_NN)
+        one = run_callers(H, fn, frames, caps, 1, 1.0, warm_calls=8)  # what one render thread sees
+
+    # ---- BASELINE config 4 over NCCL (all ranks), then the single-process legs (rank 0; the others sleep)
+    c4 = c4_nccl_leg(acb, torch, dist if world > 1 else _SingleRankDist(torch), rank, world)
+    t_inproc = max(2, min(ncores, CALLERS_PER_GPU * world))
+    e_in = rank0_alone("e2e_inproc", lambda: run_leg_subprocess("e2e-inprocess", world, ["--threads", str(t_inproc)])
+                       ) if world > 1 else None
+    c4_in = rank0_alone("c4_inproc", lambda: run_leg_subprocess("c4-inprocess", world))
+
+    def rank0_tail():
+        peak, peak_src = peaks()
+        alg_bytes_launch = n * FRAME_BYTES  # 3 B per source pixel, x frames per launch
+        achieved = alg_bytes_launch / (ms_kernel_max / args.steps * 1e-3) / 1e9
+        value = world * args.steps * n * MPIX / (ms_total_max * 1e-3)
+        out_per_frame = int(e_nn["bytes"] / max(1, e_nn["calls"]))
+        gathered = COLS * ROWS * 2 * 3  # NN mode moves only the sampled pixels (pixel-granular transfer plan)
+        per_rank = {"value": calls_nn_all * MPIX / nn_s, "unit": "Mpix/s", "calls": int(calls_nn_all), "seconds": nn_s,
+                    "caller_threads_per_gpu": threads, "processes": world, "failures": failures,
+                    "ring_fingerprint": "%016x" % fp_nn}
+        if world > 1 and e_in and "error" not in e_in:
+            e2e = {"value": e_in["calls"] * MPIX / e_in["seconds"], "unit": "Mpix/s", "calls": e_in["calls"],
+                   "seconds": e_in["seconds"], "caller_threads": e_in["threads"], "processes": 1,
+                   "failures": e_in["failures"], "ring_fingerprint": e_in["ring_fingerprint"],
+                   "structure": "ONE process, %d GPUs behind the C ABI (acb200_init_devices), caller threads leased "
+                                "round-robin" % world}
+        else:
+            e2e = dict(per_rank)
+            e2e["structure"] = "one process, one GPU" if world == 1 else "one process per GPU (in-process leg failed: %s)" % (e_in or {}).get("error")
+        e2e.update({"h2d_bytes_per_step": gathered, "d2h_bytes_per_step": out_per_frame + 4,
+                    "host_bytes_per_step": host_bytes_per_frame(out_per_frame), "step": "one frame through the call",
+                    "api": "ascii_convert_with_capabilities() — reference-exact nearest-neighbour mode, pageable host "
+                           "RGB24 in, malloc'd string out, same pthread harness as the reference arm"})
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic (uniform-noise RGB24, worst case "
+            "for run-length: ~1.18 MB of ANSI per frame)", "config": config,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "kernel": "k_render_rows_ws2<EM_HB_TRUE> (role-split persistent, direct output)",
+                         "algorithmic_bytes_per_launch": alg_bytes_launch,
+                         "kernel_ms_per_launch": ms_kernel_max / args.steps,
+                         "output_bytes_per_launch": out_bytes,
+                         "achieved_incl_output_GBs": (alg_bytes_launch + out_bytes) / (ms_kernel_max / args.steps * 1e-3) / 1e9,
+                         "traffic": traffic_from_profiles()},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if sustained:
+            line["sustained"] = sustained
+        if world > 1:
+            line["e2e_per_rank_processes"] = per_rank
+        if e_box:
+            line["e2e_box"] = {"value": e_box["calls"] * MPIX / e_box["seconds"], "unit": "Mpix/s",
+                               "h2d_bytes_per_step": FRAME_BYTES,
+                               "d2h_bytes_per_step": int(e_box["bytes"] / max(1, e_box["calls"])) + 4,
+                               "calls": e_box["calls"], "seconds": e_box["seconds"],
+                               "api": "same call, acb200_set_default_scale(ACB200_SCALE_BOX): whole frames cross PCIe "
+                                      "(24.9 MB per frame)"}
+        if one:
+            line["dropin_single_caller"] = {"ms_per_call": 1e3 * one["seconds"] / one["calls"],
+                                            "mpix_s": one["calls"] * MPIX / one["seconds"]}
+        line["c4"] = {"workload": "BASELINE config 4: %d clients x %dx%d -> %dx%d ANSI-256 -> %dx%d grid; pixel-space: "
+                                  "the server compositor for %dx%d and %dx%d viewers" % (
+                                      C4_N, C4_W, C4_H, C4_COLS, C4_ROWS, C4_GW, C4_GH, C4_COLS, C4_ROWS, C4_GW, C4_GH),
+                      "rank_processes_nccl": c4, "one_process": c4_in}
+        if not args.no_cpu_baseline:
+            r, kind, fp_ref = cpu_reference_leg(H, frames, ncores, 10.0)
+            line["cpu_baseline"] = {"value": r["calls"] * MPIX / r["seconds"], "unit": "Mpix/s", "cores": ncores,
+                                    "kind": kind,
+                                    "sample": "%d calls over a ring of %d uniform-noise 4K frames, %d caller threads, %.1f s"
+                                              % (r["calls"], frames.shape[0], ncores, r["seconds"]),
+                                    "note": "reference path is nearest-neighbour: Mpix/s nominal (source px / time)"}
+            if fp_ref is not None:
+                line["e2e"]["bytes_identical_to_cpu_baseline"] = bool("%016x" % fp_ref == e2e["ring_fingerprint"])
+            r1, _, _ = cpu_reference_leg(H, frames, 1, 2.0)
+            line["cpu_baseline_1thread"] = {"value": r1["calls"] * MPIX / r1["seconds"], "unit": "Mpix/s", "cores": 1,
+                                            "kind": kind, "ms_per_frame": 1e3 * r1["seconds"] / r1["calls"]}
+            # the same work as `value` (every source pixel read): CPU box filter + the reference's printer
+            line["cpu_baseline_box"] = cpu_box_leg(frames, ncores, 5.0)
+            line["cpu_baseline_box_1thread"] = cpu_box_leg(frames, 1, 2.0)
+            line["same_work_ratio"] = {"value_over_cpu_baseline_box": value / line["cpu_baseline_box"]["value"],
+                                       "note": "both arms read all 8.3 M pixels of every frame (box filter)"}
+        if world == 1:
+            line["server_path"] = server_path_leg(acb, not args.no_cpu_baseline)
+            line["display_path"] = display_path_leg(acb, not args.no_cpu_baseline)
+            if extras:
+                line.update(extras)
+        print(json.dumps(line))
+
+    rank0_alone("tail", rank0_tail)
+    import torch.distributed as _d
+    if _d.is_initialized():
+        _d.destroy_process_group()
+
+
+class _SingleRankDist:
+    """world == 1: the NCCL leg's collectives degenerate; torch.distributed is still used (one-rank gloo-free group)"""
+
+    def __init__(self, torch):
+        import torch.distributed as dist
+        self._d = dist
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", str(29500 + os.getpid() % 2000))
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", torch.cuda.current_device()))
+        self.ReduceOp = dist.ReduceOp
+
+    def barrier(self):
+        self._d.barrier()
+
+    def all_reduce(self, t, op=None):
+        self._d.all_reduce(t, op=op)
 
 
 if __name__ == "__main__":

@@ -328,6 +328,17 @@ char *acb200_mixed_frame(const int *slots, int n, unsigned short width, unsigned
                          const terminal_capabilities_t *caps, const char *palette, size_t *out_size,
                          int *out_sources_count);
 
+/* ---- pixel-space composition from device pointers: the multi-process form of the server grid ("gather
+ * the NN-resized cell images").  Every rank resizes its own clients' frames to acb200_mixed_cell_size() with
+ * acb200_resize_nn_device(), the few-KB cell images are gathered (NCCL), and the composing rank calls
+ * acb200_mixed_frame_device(prefit = 1): same bytes as acb200_mixed_frame on the full frames. */
+int acb200_mixed_cell_size(const int *ws, const int *hs, int n, int i, unsigned short width, unsigned short height,
+                           int *tw, int *th);
+int acb200_resize_nn_device(const uint8_t *d_src, int sw, int sh, uint8_t *d_dst, int dw, int dh, void *stream);
+char *acb200_mixed_frame_device(const uint8_t *const *d_srcs, const int *ws, const int *hs, int n, int prefit,
+                                unsigned short width, unsigned short height, const terminal_capabilities_t *caps,
+                                const char *palette, size_t *out_size);
+
 /* ---- the discovery host's render tick with RESIDENT sources, over the GPUs of the pool ------------------------
  * Replaces the body of host_render_thread's video tick (src/common/session/host.c:664-717): for every listed slot that
  * has video, ascii_convert_with_capabilities(frame, cell_width, cell_height, caps, use_aspect_ratio, stretch, palette)

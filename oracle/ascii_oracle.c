@@ -237,6 +237,50 @@ void orc_resize_box(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, in
   }
 }
 
+/* The same specification arranged for a CPU that is asked to be fast (bench.py's box-mode CPU baseline): every source
+ * row of a band is added into 16-bit column sums (one streaming pass over the band; the compiler vectorises the byte ->
+ * u16 accumulate), then each destination pixel adds its x-range of column sums.  Falls back to orc_resize_box when a
+ * band is taller than 257 rows (the u16 sums would overflow).  Checked equal to orc_resize_box in tests/test_oracle.py. */
+__attribute__((optimize("O3"), target("avx2"))) void orc_resize_box_fast(const uint8_t *src, int sw, int sh, uint8_t *dst,
+                                                                         int dw, int dh) {
+  if (sh / dh + 2 > 257) {
+    orc_resize_box(src, sw, sh, dst, dw, dh);
+    return;
+  }
+  const size_t R = (size_t)sw * 3;
+  uint16_t *col = malloc(sizeof(uint16_t) * R);
+  for (int dy = 0; dy < dh; dy++) {
+    int y0 = (int)(((int64_t)dy * sh) / dh), y1 = (int)(((int64_t)(dy + 1) * sh) / dh);
+    if (y1 <= y0) y1 = y0 + 1;
+    if (y1 > sh) y1 = sh;
+    if (y0 >= sh) y0 = sh - 1;
+    memset(col, 0, sizeof(uint16_t) * R);
+    for (int y = y0; y < y1; y++) {
+      const uint8_t *restrict row = src + (size_t)y * R;
+      uint16_t *restrict c = col;
+      for (size_t i = 0; i < R; i++) c[i] = (uint16_t)(c[i] + row[i]);
+    }
+    for (int dx = 0; dx < dw; dx++) {
+      int x0 = (int)(((int64_t)dx * sw) / dw), x1 = (int)(((int64_t)(dx + 1) * sw) / dw);
+      if (x1 <= x0) x1 = x0 + 1;
+      if (x1 > sw) x1 = sw;
+      if (x0 >= sw) x0 = sw - 1;
+      uint32_t s0 = 0, s1 = 0, s2 = 0;
+      for (int x = x0; x < x1; x++) {
+        s0 += col[3 * x];
+        s1 += col[3 * x + 1];
+        s2 += col[3 * x + 2];
+      }
+      uint32_t n = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+      uint8_t *d = dst + ((size_t)dy * dw + dx) * 3;
+      d[0] = (uint8_t)((s0 + n / 2) / n);
+      d[1] = (uint8_t)((s1 + n / 2) / n);
+      d[2] = (uint8_t)((s2 + n / 2) / n);
+    }
+  }
+  free(col);
+}
+
 /* ---------------------------------------------------------------------- emitters */
 static void put_sgr_rgb(bb_t *o, int layer /*38|48*/, int r, int g, int b) { /* ansi.c:143-195, output_buffer.c:186-214 */
   bb_put(o, "\033[", 2);
@@ -967,6 +1011,66 @@ static void *bench_worker(void *vp) {
     free(s);
   }
   return NULL;
+}
+
+/* Box-mode CPU baseline (SURVEY.md §8d last bullet): CPU box filter (this repo's specification) + the printer.
+ * print_fn = the compiled reference's image_print_with_capabilities(const image_t *, const caps *, const char *palette)
+ * with its caps blob, or NULL for the port's printer.  Frame-parallel over `threads` pthreads like orc_bench_convert. */
+typedef char *(*ref_print_fn)(const ref_image_t *, const void *, const char *);
+typedef struct {
+  const uint8_t *src;
+  int ring, w, h, cols, rows_px, color_level, render_mode, frames, threads, tid;
+  const char *palette;
+  ref_print_fn print_fn;
+  const void *caps;
+  uint64_t bytes;
+} box_arg_t;
+
+static void *box_worker(void *vp) {
+  box_arg_t *a = (box_arg_t *)vp;
+  const size_t fsz = (size_t)a->w * a->h * 3;
+  uint8_t *small = malloc((size_t)a->cols * a->rows_px * 3);
+  for (int i = a->tid; i < a->frames; i += a->threads) {
+    orc_resize_box_fast(a->src + (size_t)(i % a->ring) * fsz, a->w, a->h, small, a->cols, a->rows_px);
+    char *s;
+    size_t n = 0;
+    if (a->print_fn) {
+      ref_image_t img = {a->cols, a->rows_px, small, 0};
+      s = a->print_fn(&img, a->caps, a->palette);
+      n = s ? strlen(s) : 0;
+    } else {
+      s = orc_print(small, a->cols, a->rows_px, a->color_level, a->render_mode, a->palette, &n);
+    }
+    a->bytes += n;
+    free(s);
+  }
+  free(small);
+  return NULL;
+}
+
+double orc_bench_box(const uint8_t *src, int ring, int w, int h, int cols, int rows_px, int color_level, int render_mode,
+                     const char *palette, int frames, int threads, void *print_fn, const void *caps,
+                     uint64_t *out_bytes) {
+  if (threads < 1) threads = 1;
+  pthread_t *th = malloc(sizeof(pthread_t) * (size_t)threads);
+  box_arg_t *args = calloc((size_t)threads, sizeof(box_arg_t));
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int t = 0; t < threads; t++) {
+    args[t] = (box_arg_t){src, ring, w, h, cols, rows_px, color_level, render_mode, frames, threads, t,
+                          palette, (ref_print_fn)print_fn, caps, 0};
+    pthread_create(&th[t], NULL, box_worker, &args[t]);
+  }
+  uint64_t bytes = 0;
+  for (int t = 0; t < threads; t++) {
+    pthread_join(th[t], NULL);
+    bytes += args[t].bytes;
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (out_bytes) *out_bytes = bytes;
+  free(th);
+  free(args);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
 double orc_bench_convert(const uint8_t *src, int ring, int w, int h, long width, long height, int color_level,

@@ -41,6 +41,7 @@ int orc_build_glyph_lut(const char *palette, int which, uint8_t out[256][5], uin
 /* downscale */
 void orc_resize_nn(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh);   /* image.c:267-328 */
 void orc_resize_box(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh);  /* our spec, DESIGN.md */
+void orc_resize_box_fast(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh); /* same result, column sums */
 
 /* print an already-resized image (image_print_with_capabilities, ascii.c:955-1002).
  * Returns malloc'd NUL-terminated string, *out_len = strlen. */
@@ -104,6 +105,12 @@ void orc_fill_table(int which, void *fn, uint8_t *out);
 double orc_bench_convert(const uint8_t *src, int ring, int w, int h, long width, long height, int color_level,
                          int render_mode, const char *palette, int scale, int frames, int threads,
                          void *ref_fn, const void *ref_caps, uint64_t *out_bytes);
+
+/* box-mode CPU baseline: orc_resize_box_fast + printer (print_fn = compiled reference's image_print_with_capabilities
+ * and its caps blob, or NULL = the port's orc_print); frame-parallel, returns seconds */
+double orc_bench_box(const uint8_t *src, int ring, int w, int h, int cols, int rows_px, int color_level, int render_mode,
+                     const char *palette, int frames, int threads, void *print_fn, const void *caps,
+                     uint64_t *out_bytes);
 
 #ifdef __cplusplus
 }

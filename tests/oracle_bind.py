@@ -111,6 +111,10 @@ def port():
     L.orc_pad_height.argtypes = [C.c_char_p, C.c_size_t]
     L.orc_resize_nn.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
     L.orc_resize_box.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
+    L.orc_resize_box_fast.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
+    L.orc_bench_box.restype = C.c_double
+    L.orc_bench_box.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int,
+                                C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
     L.orc_gen_pattern.argtypes = [C.c_int, C.c_uint32, u8p, C.c_int, C.c_int]
     L.orc_fnv1a32.restype = C.c_uint32
     L.orc_fnv1a32.argtypes = [C.c_char_p, C.c_size_t]

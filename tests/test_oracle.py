@@ -462,3 +462,20 @@ def test_box_checker_agrees_with_port(ob, ref_lib):
         img = ob.gen("noise", W, H, 1)
         for level, mode in ((0, 0), (1, 0), (2, 0), (3, 0), (3, 1), (0, 2), (1, 2), (2, 2), (3, 2)):
             assert ob.ref_box_convert(img, c, r, level, mode) == ob.port_convert(img, c, r, level, mode, scale=ob.SCALE_BOX)
+
+
+def test_box_fast_equals_box(ob):
+    """the column-sum arrangement used by the box-mode CPU baseline is the same function as orc_resize_box"""
+    rng = np.random.default_rng(5)
+    u8p = C.POINTER(C.c_uint8)
+    for it in range(40):
+        sw, sh, dw, dh = (int(rng.integers(1, 400)) for _ in range(4))
+        if it == 0:
+            sw, sh, dw, dh = 3840, 2160, 320, 192
+        if it == 1:
+            sw, sh, dw, dh = 16, 3000, 4, 5  # tall bands: the u16 guard
+        src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        a = ob.port_resize(src, dw, dh, scale=ob.SCALE_BOX)
+        b = np.empty((dh, dw, 3), np.uint8)
+        ob.port().orc_resize_box_fast(src.ctypes.data_as(u8p), sw, sh, b.ctypes.data_as(u8p), dw, dh)
+        assert np.array_equal(a, b), (sw, sh, dw, dh)
