@@ -516,11 +516,13 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl, int leaf_mode) {
   pl.row_pitch = row_capacity_bytes(pl.mode, cfg.cols, cfg.pad_left);
 
   int sp = SP_NN;
+  bool pixel_filter = false;
   if (cfg.scale == ACB200_SCALE_BOX) {
     const int band = cfg.src_h / cfg.rows_px + 2;
-    // a pixel filter is not linear (truncating /255 per pixel), so the band cannot be summed as raw bytes
-    const bool pixel_filter = cfg.color_filter >= 1 && cfg.color_filter <= 11;
-    sp = ((3 * cfg.src_w) % 16 == 0 && band <= 256 && !pixel_filter) ? SP_BOX_STREAM : SP_BOX_GENERIC;
+    // a pixel filter is not linear (truncating /255 per pixel), so the band cannot be summed as raw bytes: the filtered
+    // streaming form (role-split kernel only) owns whole pixels, 48 bytes per thread and row
+    pixel_filter = cfg.color_filter >= 1 && cfg.color_filter <= 11;
+    sp = ((3 * cfg.src_w) % 16 == 0 && band <= 256 && (!pixel_filter || cfg.src_w % 16 == 0)) ? SP_BOX_STREAM : SP_BOX_GENERIC;
   } else if (cfg.scale != ACB200_SCALE_NN) {
     set_error(E_INVALID_PARAM, "unknown scale mode %d", cfg.scale);
     return false;
@@ -548,8 +550,11 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl, int leaf_mode) {
   if (sp == SP_BOX_STREAM && !is_dither_mode(pl.mode) && pl.use_smem_out && cfg.src_h >= cfg.rows_px) {
     static const char *which_env = getenv("ACB200_BOX_KERNEL");
     const char *which = which_env ? which_env : "split";
-    if (!strcmp(which, "split") && ws2_smem_total(pl.mode, cfg.cols, cfg.src_w, pl.row_pitch) <= kMaxDynSmem) {
+    if ((pixel_filter || !strcmp(which, "split")) &&
+        ws2_smem_total(pl.mode, cfg.cols, cfg.src_w, pl.row_pitch) <= kMaxDynSmem) {
       pl.scale_path = SP_BOX_SPLIT;
+    } else if (pixel_filter) {
+      pl.scale_path = SP_BOX_GENERIC; // only the role-split kernel has the filtered band sums
     } else if (!strcmp(which, "tma") && ((3 * cfg.src_w) >> 4) <= 2048 && !cfg.flip_x && !cfg.flip_y) {
       int d = ws_ring_depth(pl.mode, cfg.cols, cfg.src_w, pl.row_pitch);
       static const int d_env = getenv("ACB200_RING_DEPTH") ? atoi(getenv("ACB200_RING_DEPTH")) : 0; // tuning knob
@@ -560,6 +565,7 @@ bool make_plan(const acb200_render_cfg_t &cfg, Plan &pl, int leaf_mode) {
       }
     }
   }
+  if (pixel_filter && pl.scale_path == SP_BOX_STREAM) pl.scale_path = SP_BOX_GENERIC; // one-tile kernel: byte-load form
   pl.frame_capacity = (((size_t)cfg.pad_top + (size_t)pl.text_rows * pl.row_pitch + 1) + 15) & ~(size_t)15;
   pl.rows_bytes = (size_t)pl.text_rows * pl.row_pitch;
   pl.meta_bytes = (size_t)pl.text_rows * sizeof(RowMeta);
@@ -837,7 +843,12 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
   bool need_stage = tplan != PLAN_FULL;
   for (int i = 0; i < n_frames && !need_stage; i++) need_stage = frames[i] && !is_pinned(frames[i]);
   const size_t scratch_cap_before = cx->d_scratch_cap; // a regrown buffer may come back at the same address
+  // How the strings leave the device.  Default: the emitters store them straight into mapped pinned host memory.
+  // ACB200_D2H=ce (measurement knob): the emitters write to HBM, the lengths come back first, then the copy engine moves
+  // exactly the bytes of each string (full-size PCIe payloads, one more wait per chunk).
+  static const bool d2h_ce = getenv("ACB200_D2H") && !strcmp(getenv("ACB200_D2H"), "ce");
   if (sync_foreign(cx, cx->stream) != E_OK) return t_err;
+  if (d2h_ce && !grow_device(&cx->d_out, &cx->d_out_cap, out_slot * nslot)) return t_err;
   if (!grow_device(&cx->d_in, &cx->d_in_cap, in_slot * nslot) ||
       !grow_device(&cx->d_scratch, &cx->d_scratch_cap, scratch_bytes(pl, chunk)) ||
       !grow_pinned(&cx->h_out, &cx->h_out_cap, out_slot * nslot) ||
@@ -889,7 +900,8 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
     }
     if (all_staged)
       ACB_CUDA(cudaMemcpyAsync(d_in, st_base, (size_t)(n - 1) * in_pitch + in_per_frame, cudaMemcpyHostToDevice, cx->stream));
-    int rc = render_device(dcfg, pl, d_in, in_pitch, tplan == PLAN_NN_ROWS ? 1 : 0, n, cx->h_out + (size_t)slot * out_slot,
+    int rc = render_device(dcfg, pl, d_in, in_pitch, tplan == PLAN_NN_ROWS ? 1 : 0, n,
+                           (d2h_ce ? cx->d_out : cx->h_out) + (size_t)slot * out_slot,
                            cap, reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(cx->h_len) + (size_t)slot * len_slot),
                            cx->d_scratch, cx->stream, nullptr, nullptr, &cx->lb);
     if (rc) return rc;
@@ -904,6 +916,13 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
     const uint32_t *lens =
         reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(cx->h_len) + (size_t)slot * len_slot);
     const uint8_t *arena = cx->h_out + (size_t)slot * out_slot;
+    if (d2h_ce) {
+      for (int i = 0; i < n; i++)
+        ACB_CUDA(cudaMemcpyAsync(cx->h_out + (size_t)slot * out_slot + (size_t)i * cap,
+                                 cx->d_out + (size_t)slot * out_slot + (size_t)i * cap, lens[i], cudaMemcpyDeviceToHost,
+                                 cx->stream));
+      if (wait_stream(cx) != E_OK) return t_err;
+    }
     for (int i = 0; i < n; i++) {
       const size_t len = lens[i];
       char *sp = (char *)user_alloc(len + 1);

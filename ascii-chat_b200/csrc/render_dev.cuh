@@ -342,10 +342,7 @@ __device__ __forceinline__ uint32_t filter_px(uint32_t c, int mode, uint32_t frg
 
 // nearest neighbour — image.c:293-325 (u32 fixed-point, wraps like the reference); the sampled coordinate is
 // mirrored when the display path flips the image first (display.c:563-590)
-template <int NT>
-__device__ __forceinline__ void cells_nn(const RenderParams &p, const uint8_t *frame, int y, uint32_t *out) {
-  const uint32_t xr = (uint32_t)((((uint64_t)p.src_w << 16) / (uint64_t)p.cols) + 1);
-  const uint32_t yr = (uint32_t)((((uint64_t)p.src_h << 16) / (uint64_t)p.rows_px) + 1);
+__device__ __forceinline__ const uint8_t *nn_row(const RenderParams &p, const uint8_t *frame, int y, uint32_t yr) {
   uint32_t sy;
   if (p.pregathered) {
     sy = (uint32_t)y;
@@ -354,12 +351,25 @@ __device__ __forceinline__ void cells_nn(const RenderParams &p, const uint8_t *f
     if (sy >= (uint32_t)p.src_h) sy = (uint32_t)p.src_h - 1;
     if (p.flip_y) sy = (uint32_t)p.src_h - 1u - sy;
   }
-  const uint8_t *row = frame + (size_t)sy * (size_t)p.src_w * 3u;
+  return frame + (size_t)sy * (size_t)p.src_w * 3u;
+}
+// One pass samples the top pixel row of the text row and, for half blocks, the bottom one too: both loads of a cell are
+// in flight together (one memory latency per tile instead of two).  outB == nullptr: single pixel row.
+template <int NT>
+__device__ __forceinline__ void cells_nn(const RenderParams &p, const uint8_t *frame, int y, uint32_t *outT,
+                                         uint32_t *outB) {
+  const uint32_t xr = (uint32_t)((((uint64_t)p.src_w << 16) / (uint64_t)p.cols) + 1);
+  const uint32_t yr = (uint32_t)((((uint64_t)p.src_h << 16) / (uint64_t)p.rows_px) + 1);
+  const uint8_t *rowT = nn_row(p, frame, y, yr);
+  const uint8_t *rowB = outB ? nn_row(p, frame, y + 1, yr) : rowT;
   for (int x = threadIdx.x; x < p.cols; x += NT) {
     uint32_t sx = ((uint32_t)x * xr) >> 16;
     if (sx >= (uint32_t)p.src_w) sx = (uint32_t)p.src_w - 1;
     if (p.flip_x) sx = (uint32_t)p.src_w - 1u - sx;
-    out[x] = filter_px(load_px_w(row + (size_t)sx * 3u), p.filt_mode, p.filt_rgb);
+    const uint32_t a = load_px_w(rowT + (size_t)sx * 3u);
+    const uint32_t b = outB ? load_px_w(rowB + (size_t)sx * 3u) : 0u;
+    outT[x] = filter_px(a, p.filt_mode, p.filt_rgb);
+    if (outB) outB[x] = filter_px(b, p.filt_mode, p.filt_rgb);
   }
 }
 
@@ -470,10 +480,94 @@ template <int NR> __device__ __forceinline__ void band_trip(uint32_t (&a)[8], co
   if (NR & 1) acc16x2(a, v[NR - 1], make_uint4(0u, 0u, 0u, 0u));
 }
 
+// ---- colour filter fused into the streaming box filter (display path in box mode) -------------
+// apply_color_filter is a function of the pixel's BT.601 grey value only (color_filter.c:238-267, 338-341), so the
+// filtered image is T[gray(px)] with a 256-entry table.  It is not linear (truncating /255 per pixel), so the band cannot
+// be summed first and filtered afterwards: every source pixel goes through the table, then into the same packed u16
+// column sums as the unfiltered path.  A thread owns whole pixels — 48 bytes = 16 pixels = three 16-byte loads per
+// row — takes four rows per trip (12 independent loads in flight, like the unfiltered band), and per 4 pixels spends
+// 2 PRMT + 1 SHR (cut the pixels out of 3 words), 4 DP4A + 4 SHR (grey), 4 LDS (table), 8 ops (re-pack to 3 words).
+static __shared__ uint32_t s_filt[256]; // [gray] = filtered pixel in memory byte order: r | g << 8 | b << 16
+template <int NT> __device__ __forceinline__ void init_filt(const RenderParams &p, int tid) {
+  for (int v = tid; v < 256; v += NT)
+    s_filt[v] = __byte_perm(filter_px((uint32_t)v * 0x010101u, p.filt_mode, p.filt_rgb), 0u, 0x4012); // gray(v,v,v) = v
+}
+__device__ __forceinline__ uint32_t gray_rgbx(uint32_t rgbx) { // bytes r,g,b,(ignored): (77r+150g+29b)>>8, color_filter.h:172
+  return __dp4a(rgbx, 0x001D964Du, 0u) >> 8;
+}
+__device__ __forceinline__ void filt4px(uint32_t &w0, uint32_t &w1, uint32_t &w2) { // 4 pixels live in 3 words
+  const uint32_t p0 = s_filt[gray_rgbx(w0)];
+  const uint32_t p1 = s_filt[gray_rgbx(__byte_perm(w0, w1, 0x6543))];
+  const uint32_t p2 = s_filt[gray_rgbx(__byte_perm(w1, w2, 0x5432))];
+  const uint32_t p3 = s_filt[gray_rgbx(w2 >> 8)];
+  w0 = p0 | (p1 << 24);
+  w1 = (p1 >> 8) | (p2 << 16);
+  w2 = (p2 >> 16) | (p3 << 8);
+}
+__device__ __forceinline__ void filt16px(uint4 &a, uint4 &b, uint4 &c) { // 48 bytes = 16 pixels, in place
+  filt4px(a.x, a.y, a.z);
+  filt4px(a.w, b.x, b.y);
+  filt4px(b.z, b.w, c.x);
+  filt4px(c.y, c.z, c.w);
+}
+template <int NR> __device__ __forceinline__ void band_trip_filt(uint32_t (&a)[3][8], const uint8_t *&q, uint32_t R) {
+  uint4 v[NR][3];
+#pragma unroll
+  for (int k = 0; k < NR; k++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) v[k][j] = ldg_stream(reinterpret_cast<const uint4 *>(q) + j);
+    q += R;
+  }
+#pragma unroll
+  for (int k = 0; k < NR; k++) filt16px(v[k][0], v[k][1], v[k][2]);
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+#pragma unroll
+    for (int k = 0; k + 1 < NR; k += 2) acc16x2(a[j], v[k][j], v[k + 1][j]);
+    if (NR & 1) acc16x2(a[j], v[NR - 1][j], make_uint4(0u, 0u, 0u, 0u));
+  }
+}
+// column sums of the FILTERED band into V (same layout as the unfiltered path); requires (3 * src_w) % 48 == 0
+template <int NT>
+__device__ __forceinline__ void band_sums_filtered(const uint8_t *band, uint32_t R, int nrow, uint16_t *V) {
+  const int ngroup = (int)(R / 48u);
+  for (int c = threadIdx.x; c < ngroup; c += NT) {
+    uint32_t a[3][8];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int k = 0; k < 8; k++) a[j][k] = 0u;
+    const uint8_t *q = band + (size_t)c * 48u;
+    int r = nrow;
+    for (; r >= 4; r -= 4) band_trip_filt<4>(a, q, R);
+    switch (r) {
+    case 3: band_trip_filt<3>(a, q, R); break;
+    case 2: band_trip_filt<2>(a, q, R); break;
+    case 1: band_trip_filt<1>(a, q, R); break;
+    default: break;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      uint4 lo, hi;
+      lo.x = __byte_perm(a[j][0], a[j][1], 0x5410);
+      lo.y = __byte_perm(a[j][0], a[j][1], 0x7632);
+      lo.z = __byte_perm(a[j][2], a[j][3], 0x5410);
+      lo.w = __byte_perm(a[j][2], a[j][3], 0x7632);
+      hi.x = __byte_perm(a[j][4], a[j][5], 0x5410);
+      hi.y = __byte_perm(a[j][4], a[j][5], 0x7632);
+      hi.z = __byte_perm(a[j][6], a[j][7], 0x5410);
+      hi.w = __byte_perm(a[j][6], a[j][7], 0x7632);
+      uint4 *dst = reinterpret_cast<uint4 *>(V + ((size_t)c * 3 + j) * 16);
+      dst[0] = lo;
+      dst[1] = hi;
+    }
+  }
+}
+
 // box filter, streaming: the band of source rows [y0,y1) is one contiguous byte range; every thread owns
 // 16-byte columns of it, sums them down the band in registers (u16 lanes, band <= 256 rows), parks the
 // column sums V[3*src_w] in shared memory, then one thread per destination pixel adds its x-range.
-template <int NT, class Sync = SyncAll>
+template <int NT, class Sync = SyncAll, bool FILT = false>
 __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const uint8_t *frame, int y, uint32_t *out,
                                                  uint16_t *V) {
   int y0, y1;
@@ -483,7 +577,8 @@ __device__ __forceinline__ void cells_box_stream(const RenderParams &p, const ui
   const int nrow = y1 - y0;
   if (p.flip_y) y0 = p.src_h - y1; // the band of the mirrored image is the mirrored band (sums do not care about order)
   const uint8_t *band = frame + (size_t)y0 * (size_t)R;
-  for (int c = threadIdx.x; c < nchunk; c += NT) {
+  if (FILT) band_sums_filtered<NT>(band, R, nrow, V);
+  for (int c = threadIdx.x; c < (FILT ? 0 : nchunk); c += NT) {
     uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const uint8_t *q = band + ((size_t)c << 4);
     // whole batches of kBandUnroll rows, then one batch of exactly the rows that are left (a typical band — 11 or 12
@@ -995,8 +1090,7 @@ __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) :
     const int yT = HB ? 2 * t : t;
     const bool hasB = HB && (2 * t + 1 < p.rows_px);
     if (SP == SP_NN) {
-      cells_nn<NT>(p, frame, yT, cT);
-      if (hasB) cells_nn<NT>(p, frame, yT + 1, cB);
+      cells_nn<NT>(p, frame, yT, cT, hasB ? cB : nullptr);
     } else if (SP == SP_BOX_GENERIC) {
       cells_box_generic<NT>(p, frame, yT, cT);
       if (hasB) cells_box_generic<NT>(p, frame, yT + 1, cB);
@@ -1312,8 +1406,10 @@ template <int N> __device__ __forceinline__ void nbar_arrive_id(int id) {
   }
 }
 
-// four CTAs per SM (56 registers): the occupancy every measurement in DESIGN.md §7 was taken at
-template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32, 4) k_render_rows_ws2(const RenderParams p) {
+// four CTAs per SM (56 registers): the occupancy every measurement in DESIGN.md §7 was taken at.  FILT (a colour
+// filter fused into the band sums) keeps 12 x 16 bytes of loads plus 48 column sums in registers: two CTAs per SM.
+template <int MODE, bool FILT>
+__global__ void __launch_bounds__(WS2_ST + 32, FILT ? 2 : 4) k_render_rows_ws2(const RenderParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_tmp[2];
   __shared__ uint32_t s_cond[2][4];
@@ -1339,6 +1435,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32, 4) k_render_r
     for (int i = tid; i < (int)(sizeof(GlyphLut) / 4); i += NB) dst[i] = src[i];
   }
   init_dec3<NB>(tid);
+  if (FILT) init_filt<NB>(p, tid);
   __syncthreads();
 
   if (tid < WS2_ST) { // ---------------- streamers
@@ -1374,7 +1471,7 @@ template <int MODE> __global__ void __launch_bounds__(WS2_ST + 32, 4) k_render_r
       const bool hasB = HB && (2 * t + 1 < p.rows_px);
 #pragma unroll 1
       for (int hrow = 0; hrow < (hasB ? 2 : 1); hrow++) // one inlined copy of the band code for both pixel rows
-        cells_box_stream<WS2_ST, SyncConsumers<WS2_ST>>(p, frame, yT + hrow, hrow ? cB : cT, V);
+        cells_box_stream<WS2_ST, SyncConsumers<WS2_ST>, FILT>(p, frame, yT + hrow, hrow ? cB : cT, V);
       if (HB && !hasB)
         for (int x = tid; x < w; x += WS2_ST) cB[x] = cT[x];
       __threadfence_block();
@@ -1457,7 +1554,8 @@ static inline int current_sms(int *dev_out) {
   return sms;
 }
 
-template <int MODE> static cudaError_t launch_ws2_mode(const RenderParams &p, cudaStream_t st, unsigned *grid_out) {
+template <int MODE, bool FILT>
+static cudaError_t launch_ws2_mode_f(const RenderParams &p, cudaStream_t st, unsigned *grid_out) {
   const Layout2 L = make_layout2(MODE, p.direct, p.cols, p.src_w, p.row_pitch);
   if (L.total > kMaxDynSmem) return cudaErrorInvalidConfiguration;
   // nothing cached across calls except the per-device opt-in: callers with different geometries run concurrently
@@ -1465,19 +1563,24 @@ template <int MODE> static cudaError_t launch_ws2_mode(const RenderParams &p, cu
   int dev = 0;
   const int sms = current_sms(&dev);
   if (!attr_done(configured, dev)) {
-    cudaError_t e = allow_max_dyn_smem(k_render_rows_ws2<MODE>);
+    cudaError_t e = allow_max_dyn_smem(k_render_rows_ws2<MODE, FILT>);
     if (e != cudaSuccess) return e;
     attr_set(configured, dev);
   }
   int ctas_per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_render_rows_ws2<MODE>, WS2_ST + 32, L.total);
+  cudaError_t e =
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_render_rows_ws2<MODE, FILT>, WS2_ST + 32, L.total);
   if (e != cudaSuccess || ctas_per_sm < 1) return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
   const long long total = (long long)p.n_frames * p.text_rows;
   long long grid = (long long)sms * ctas_per_sm;
   if (grid > total) grid = total;
   if (grid_out) *grid_out = (unsigned)grid;
-  k_render_rows_ws2<MODE><<<(unsigned)grid, WS2_ST + 32, L.total, st>>>(p);
+  k_render_rows_ws2<MODE, FILT><<<(unsigned)grid, WS2_ST + 32, L.total, st>>>(p);
   return cudaGetLastError();
+}
+template <int MODE> static cudaError_t launch_ws2_mode(const RenderParams &p, cudaStream_t st, unsigned *grid_out) {
+  return p.filt_mode != FM_NONE ? launch_ws2_mode_f<MODE, true>(p, st, grid_out)
+                                : launch_ws2_mode_f<MODE, false>(p, st, grid_out);
 }
 
 // opt in to the largest dynamic shared memory the kernel can have: 227 KB per CTA minus its static allocation

@@ -154,6 +154,26 @@ def run_callers(H, fn_ptr, frames, caps, threads, seconds_target, warm_calls=Non
     return {"seconds": t, "calls": calls, "bytes": nb.value, "failures": nf.value}
 
 
+def pick_threads(H, fn_ptr, frames, caps, candidates, seconds=0.6):
+    """caller-thread count at the knee: probe each candidate briefly (untimed region), keep the fastest.  The knee moves
+    with the box (cores per GPU, PCIe links in use): 16 callers on 16 cores and one GPU, 16 on 24 cores and two GPUs
+    (profiles/r02a_e2e_sweep_pixels.txt, r02b_e2e_inproc2.txt), and a caller per core is past it."""
+    best, best_fps, probes = None, 0.0, {}
+    for t in sorted(set(int(c) for c in candidates if c >= 1)):
+        r = run_callers(H, fn_ptr, frames, caps, t, seconds)
+        fps = r["calls"] / r["seconds"]
+        probes[t] = round(fps)
+        if fps > best_fps:
+            best, best_fps = t, fps
+    return best, probes
+
+
+def thread_candidates(ncores, n_gpus):
+    cap = CALLERS_PER_GPU * n_gpus
+    return [min(cap, c) for c in (max(2, ncores // 2), max(2, (2 * ncores) // 3), max(2, ncores - 2), ncores,
+                                  (3 * ncores) // 2)]
+
+
 def reference_entry():
     """(fn pointer, caps struct, kind) of the reference's own CPU implementation: oracle/_ref, else the port shim"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -521,11 +541,14 @@ def e2e_inprocess(n_gpus, threads, seconds):
     caps = acb.make_caps(LEVEL, MODE)
     fn = C.cast(acb.lib().ascii_convert_with_capabilities, C.c_void_p)
     acb.lib().acb200_set_default_scale(acb.SCALE_NN)
+    probes = None
+    if threads <= 0:
+        threads, probes = pick_threads(H, fn, frames, caps, thread_candidates(os.cpu_count() or 1, n_gpus))
     r = run_callers(H, fn, frames, caps, threads, seconds)
     fp = H.harness_ring_fingerprint(fn, frames.ctypes.data, frames.shape[0], SRC_W, SRC_H, COLS, ROWS, C.byref(caps),
                                     PALETTE)
     one = run_callers(H, fn, frames, caps, 1, 1.0, warm_calls=8)
-    r.update({"threads": threads, "n_gpus": n_gpus, "ring_fingerprint": "%016x" % fp,
+    r.update({"threads": threads, "thread_probes_fps": probes, "n_gpus": n_gpus, "ring_fingerprint": "%016x" % fp,
               "single_caller_ms": 1e3 * one["seconds"] / one["calls"], "launches": acb.launch_count()})
     acb.lib().acb200_shutdown()
     return r
@@ -558,7 +581,7 @@ def main():
     args = ap.parse_args()
 
     if args.leg == "e2e-inprocess":
-        print(json.dumps(e2e_inprocess(args.gpus, args.threads or CALLERS_PER_GPU, 4.0)))
+        print(json.dumps(e2e_inprocess(args.gpus, args.threads, 4.0)))
         return
     if args.leg == "c4-inprocess":
         print(json.dumps(c4_inprocess(args.gpus)))
@@ -700,10 +723,14 @@ def main():
     # ---- end to end, one process per GPU: every rank drives its own GPU with its share of the caller threads
     H = load_harness()
     frames = host_ring()
-    threads = max(2, min(CALLERS_PER_GPU, ncores // max(1, world)))
     caps = acb.make_caps(LEVEL, MODE)
     fn = C.cast(acb.lib().ascii_convert_with_capabilities, C.c_void_p)
     acb.lib().acb200_set_default_scale(acb.SCALE_NN)
+    probes = None
+    if world == 1:
+        threads, probes = pick_threads(H, fn, frames, caps, thread_candidates(ncores, 1))
+    else:
+        threads = max(2, min(CALLERS_PER_GPU, ncores // world))
     barrier()
     e_nn = run_callers(H, fn, frames, caps, threads, 4.0)
     barrier()
@@ -723,9 +750,7 @@ def main():
 
     # ---- BASELINE config 4 over NCCL (all ranks), then the single-process legs (rank 0; the others sleep)
     c4 = c4_nccl_leg(acb, torch, dist if world > 1 else _SingleRankDist(torch), rank, world)
-    t_inproc = max(2, min(ncores, CALLERS_PER_GPU * world))
-    e_in = rank0_alone("e2e_inproc", lambda: run_leg_subprocess("e2e-inprocess", world, ["--threads", str(t_inproc)])
-                       ) if world > 1 else None
+    e_in = rank0_alone("e2e_inproc", lambda: run_leg_subprocess("e2e-inprocess", world)) if world > 1 else None
     c4_in = rank0_alone("c4_inproc", lambda: run_leg_subprocess("c4-inprocess", world))
 
     def rank0_tail():
@@ -736,11 +761,12 @@ def main():
         out_per_frame = int(e_nn["bytes"] / max(1, e_nn["calls"]))
         gathered = COLS * ROWS * 2 * 3  # NN mode moves only the sampled pixels (pixel-granular transfer plan)
         per_rank = {"value": calls_nn_all * MPIX / nn_s, "unit": "Mpix/s", "calls": int(calls_nn_all), "seconds": nn_s,
-                    "caller_threads_per_gpu": threads, "processes": world, "failures": failures,
-                    "ring_fingerprint": "%016x" % fp_nn}
+                    "caller_threads_per_gpu": threads, "thread_probes_fps": probes, "processes": world,
+                    "failures": failures, "ring_fingerprint": "%016x" % fp_nn}
         if world > 1 and e_in and "error" not in e_in:
             e2e = {"value": e_in["calls"] * MPIX / e_in["seconds"], "unit": "Mpix/s", "calls": e_in["calls"],
-                   "seconds": e_in["seconds"], "caller_threads": e_in["threads"], "processes": 1,
+                   "seconds": e_in["seconds"], "caller_threads": e_in["threads"],
+                   "thread_probes_fps": e_in.get("thread_probes_fps"), "processes": 1,
                    "failures": e_in["failures"], "ring_fingerprint": e_in["ring_fingerprint"],
                    "structure": "ONE process, %d GPUs behind the C ABI (acb200_init_devices), caller threads leased "
                                 "round-robin" % world}

@@ -168,3 +168,20 @@ def test_grid_frame_single_device(acb, ob):
     for i in range(8):
         acb.source_clear(i)
     assert acb.grid_frame([0, 1], 80, 24, acb.make_caps(0, 0), "standard", 80, 24) == (None, 0)
+
+
+def test_filtered_box_streaming_all_filters(acb, ob):
+    """the colour filter fused into the streaming band sums (k_render_rows_ws2<MODE, FILT>): every pixel filter id, both
+    arithmetic forms, bands of 4k, 4k+1, 4k+2, 4k+3 rows, flips — against the port's filter + box + print"""
+    for (W, H, c, r, mode) in ((3840, 2160, 320, 96, 2), (1920, 1080, 160, 48, 0), (640, 480, 80, 24, 2), (1280, 650, 80, 50, 0),
+                               (64, 36, 16, 9, 2)):
+        img = ob.gen("noise" if W > 100 else "gradient", W, H, 6)
+        for filt in range(1, 12):
+            fx, fy = filt % 2, (filt // 2) % 2
+            level = (3, 2, 1, 0)[filt % 4]
+            cfg = acb.make_cfg(W, H, c, r * 2 if mode == 2 else r, level, mode, scale=acb.SCALE_BOX, flip_x=fx, flip_y=fy,
+                               color_filter=filt, filter_time=0.5)
+            got = acb.render_batch_host(cfg, [img])[0]
+            exp = ob.port_display_convert(img, c, r, level, mode, flip_x=fx, flip_y=fy, color_filter=filt, time_s=0.5,
+                                          scale=ob.SCALE_BOX)
+            assert got == exp, (W, H, c, r, mode, filt, fx, fy, level)
