@@ -616,6 +616,8 @@ int render_device(const acb200_render_cfg_t &cfg, const Plan &pl, const uint8_t 
     rp.box_nrow0 = n0;
     for (int d = 0; d < 2; d++) rp.box_M[d] = ok ? 0xFFFFFFFFu / ((uint32_t)bx * (uint32_t)(n0 + d)) + 1u : 0u;
   }
+  rp.nn_xr = (uint32_t)((((uint64_t)cfg.src_w << 16) / (uint64_t)cfg.cols) + 1);
+  rp.nn_yr = (uint32_t)((((uint64_t)cfg.src_h << 16) / (uint64_t)cfg.rows_px) + 1);
   {
     const DisplayOps d = display_ops(cfg);
     rp.flip_x = d.flip_x;

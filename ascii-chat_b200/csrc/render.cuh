@@ -83,6 +83,7 @@ struct RenderParams {
   // bands are box_nrow0 or box_nrow0 + 1 rows tall; box_M[d] = ceil(2^32 / (box_bx * (box_nrow0 + d)))
   int box_bx, box_nrow0;
   uint32_t box_M[2];
+  uint32_t nn_xr, nn_yr;  // nearest neighbour: ((src_w << 16) / cols) + 1, ((src_h << 16) / rows_px) + 1  (image.c:293-294)
   unsigned long long *dbg; // measurement counters (tune_flags bit 2): streamer wait, emitter wait, emitter busy, tiles
   int tune_flags;         // measurement knobs: bit0 no V/staging alias, bit1 no emission, bit2 counters, bit3 generic horizontal sums
 };

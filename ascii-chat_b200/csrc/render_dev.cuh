@@ -255,15 +255,18 @@ __device__ __forceinline__ int row_scan(int w, F value_of, G store, int *s_tmp, 
     int up = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 31) buf[warp] = inc;
     Sync::sync();
-    int pre = carry, all = carry;
+    // fold the NW warp totals with one more shuffle scan (lane i holds warp i's total): lane w-1 ends up with the
+    // prefix of warp w, the last lane with the pass total
+    int tot = lane < NW ? buf[lane] : Op::id();
 #pragma unroll
-    for (int i = 0; i < NW; i++) {
-      const int t = buf[i];
-      if (i < warp) pre = Op::ap(pre, t);
-      all = Op::ap(all, t);
+    for (int d = 1; d < NW; d <<= 1) {
+      int o = __shfl_up_sync(0xffffffffu, tot, d);
+      if (lane >= d) tot = Op::ap(o, tot);
     }
+    const int before = __shfl_sync(0xffffffffu, tot, warp > 0 ? warp - 1 : 0);
+    const int pre = warp > 0 ? Op::ap(carry, before) : carry;
     if (x < w) store(x, Op::ap(pre, inc), lane == 0 ? pre : Op::ap(pre, up));
-    carry = all;
+    carry = Op::ap(carry, __shfl_sync(0xffffffffu, tot, NW - 1));
   }
   Sync::sync(); // the next scan (or whoever reads what store() wrote) starts from a quiet s_tmp
   return carry;
@@ -358,8 +361,7 @@ __device__ __forceinline__ const uint8_t *nn_row(const RenderParams &p, const ui
 template <int NT>
 __device__ __forceinline__ void cells_nn(const RenderParams &p, const uint8_t *frame, int y, uint32_t *outT,
                                          uint32_t *outB) {
-  const uint32_t xr = (uint32_t)((((uint64_t)p.src_w << 16) / (uint64_t)p.cols) + 1);
-  const uint32_t yr = (uint32_t)((((uint64_t)p.src_h << 16) / (uint64_t)p.rows_px) + 1);
+  const uint32_t xr = p.nn_xr, yr = p.nn_yr; // 64-bit divisions done once on the host
   const uint8_t *rowT = nn_row(p, frame, y, yr);
   const uint8_t *rowB = outB ? nn_row(p, frame, y + 1, yr) : rowT;
   for (int x = threadIdx.x; x < p.cols; x += NT) {
@@ -885,6 +887,18 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// A look-back record is ONE aligned 16-byte word {ready = epoch, len, first_rgb, last_rgb}, published with a single
+// 16-byte store and polled with a single 16-byte load: the memory system moves it as one transaction (the same
+// single-word protocol CUB's decoupled look-back uses for 16-byte tile descriptors), so whoever sees the new epoch sees
+// the payload that was stored with it — no fences on either side, one load per poll instead of four.
+__device__ __forceinline__ uint4 ld_record(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_record(uint4 *p, const uint4 &v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ uint32_t sgr_rgb_len(uint32_t c) { // bytes of ESC[38;2;R;G;Bm
   uint32_t r = (c >> 16) & 255u, g = (c >> 8) & 255u, b = c & 255u;
   return 10u + (r >= 100u ? 3u : r >= 10u ? 2u : 1u) + (g >= 100u ? 3u : g >= 10u ? 2u : 1u) +
@@ -915,12 +929,10 @@ __device__ __forceinline__ uint32_t emit_direct_prepare(const RenderParams &p, i
   constexpr bool row_reset = MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16;
   const uint32_t term_len = (row_reset ? 4u : 0u) + ((MODE == EM_TRUE_FG && last_row) ? 4u : 0u) + (last_row ? 0u : 1u);
   if (tid == 0) {
-    uint32_t *me = reinterpret_cast<uint32_t *>(p.agg + (size_t)f * p.text_rows + t);
-    me[1] = (uint32_t)p.pad_left + cells_bytes + term_len;
-    me[2] = MODE == EM_TRUE_FG ? s_cond[3] : 0u;
-    me[3] = MODE == EM_TRUE_FG ? s_cond[2] : 0u;
-    __threadfence();
-    *reinterpret_cast<volatile uint32_t *>(me) = p.epoch; // "ready" = this launch's epoch: no clearing between launches
+    // "ready" = this launch's epoch: no clearing between launches
+    st_record(p.agg + (size_t)f * p.text_rows + t,
+              make_uint4(p.epoch, (uint32_t)p.pad_left + cells_bytes + term_len, MODE == EM_TRUE_FG ? s_cond[3] : 0u,
+                         MODE == EM_TRUE_FG ? s_cond[2] : 0u));
   }
   return cells_bytes;
 }
@@ -943,19 +955,29 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
 
   if (tid < 32) {
     const int lane = tid;
-    const uint32_t *agg = reinterpret_cast<const uint32_t *>(p.agg + (size_t)f * p.text_rows); // 4 words per row
+    const uint4 *agg = p.agg + (size_t)f * p.text_rows;
     uint32_t prefix = 0, carry = 0;
-    for (int base = 0; base < t; base += 32) {
-      const int j = base + lane;
-      uint32_t len = 0, fj = 0, lj = 0;
-      if (j < t) {
-        const uint32_t *rec = agg + 4 * (size_t)j;
-        while (ld_volatile_u32(rec) != p.epoch) __nanosleep(64);
-        __threadfence();
-        len = ld_volatile_u32(rec + 1);
-        fj = ld_volatile_u32(rec + 2);
-        lj = ld_volatile_u32(rec + 3);
+    // the records of up to 96 rows above are requested in one go (three independent loads per lane in flight), then
+    // only the ones that were not published yet are polled again: one L2 round trip in the common case
+    for (int base0 = 0; base0 < t; base0 += 96) {
+      uint4 rec[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int j = base0 + 32 * k + lane;
+        rec[k] = j < t ? ld_record(agg + j) : make_uint4(p.epoch, 0u, 0u, 0u);
       }
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int j = base0 + 32 * k + lane;
+        while (rec[k].x != p.epoch) {
+          __nanosleep(32);
+          rec[k] = ld_record(agg + j);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+      if (base0 + 32 * k >= t) break;
+      uint32_t len = rec[k].y, fj = rec[k].z, lj = rec[k].w;
       if (MODE == EM_TRUE_FG) {
         uint32_t inc = lj; // inclusive "last non-zero" scan = colour state after row j
 #pragma unroll
@@ -973,6 +995,7 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
 #pragma unroll
       for (int d = 16; d >= 1; d >>= 1) len += __shfl_xor_sync(0xffffffffu, len, d);
       prefix += len;
+      }
     }
     if (lane == 0) {
       s_lb[0] = prefix;

@@ -44,7 +44,31 @@ for level, mode in ((3, 2), (0, 0), (2, 0)):
     bad += acb.mixed_frame([0, 1, 2], 40, 12, caps, "standard") != exp
     pkt = acb.mixed_frame_packet([0, 1, 2], 40, 12, caps, "standard")
     bad += pkt[0] != ob.port_packet_header(exp[0], 40, 12) + exp[0]
+# round 2: the foreground-only dithered printers, rainbow replace on a string, the in-process grid, pinned ingest,
+# pixel-space composition from pre-fitted cell images
+img = ob.gen("noise", 37, 11, 5)
+for variant in (0, 1, 2):
+    bad += acb.image_print_16color_dithered(img, "standard", None if variant == 2 else variant == 0) != \
+        ob.port_print_dither(img, "standard", variant)
+s_true = ob.port_convert(ob.gen("noise", 96, 64, 2), 40, 12, 3, 0)
+bad += acb.rainbow_replace_ansi_colors(s_true * 3, 1.1) != ob.port_rainbow_replace(s_true * 3, 1.1)
+bad += acb.rainbow_replace_ansi_colors(b"no colour", 1.1) is not None
+for i, s_ in enumerate(srcs):
+    acb.source_update_pinned(i, s_)
+cells = [ob.port_convert(s_, 20, 6, 2, 0) + b"\0" for s_ in srcs]
+bad += acb.grid_frame([0, 1, 2], 20, 6, acb.make_caps(2, 0), "standard", 60, 20) != ob.port_create_grid(cells, 60, 20)
 import torch
+ws, hs = [s_.shape[1] for s_ in srcs], [s_.shape[0] for s_ in srcs]
+d_src = [torch.from_numpy(s_).cuda() for s_ in srcs]
+d_cell = []
+for i in range(3):
+    tw, th = acb.mixed_cell_size(ws, hs, i, 40, 12)
+    d_cell.append(torch.zeros(max(1, tw * th * 3), dtype=torch.uint8, device="cuda"))
+    torch.cuda.synchronize()
+    acb.resize_nn_device(d_src[i].data_ptr(), ws[i], hs[i], d_cell[i].data_ptr(), tw, th, None)
+acb.synchronize()
+got = acb.mixed_frame_device([t.data_ptr() for t in d_cell], ws, hs, True, 40, 12, acb.make_caps(2, 0, True), "standard")
+bad += got != ob.port_mixed_frame(srcs, 40, 12, 2, 0, "standard", True)[0]
 lens = [0, 1, 63, 64, 65, 16384, 16385, 40000]
 pitch = 40016
 arena = np.random.default_rng(1).integers(0, 256, (len(lens), pitch), dtype=np.uint8)
