@@ -40,6 +40,18 @@ class terminal_capabilities_t(C.Structure):  # platform/terminal.h:707-738
     ]
 
 
+class digital_rain_column_t(C.Structure):  # video/anim/digital_rain.h
+    _fields_ = [("time_offset", C.c_float), ("speed_multiplier", C.c_float), ("phase_offset", C.c_float)]
+
+
+class digital_rain_t(C.Structure):  # video/anim/digital_rain.h (previous_brightness: device memory here)
+    _fields_ = [("columns", C.POINTER(digital_rain_column_t)), ("num_columns", C.c_int), ("num_rows", C.c_int),
+                ("time", C.c_float), ("fall_speed", C.c_float), ("raindrop_length", C.c_float),
+                ("brightness_decay", C.c_float), ("animation_speed", C.c_float), ("color_r", C.c_uint8),
+                ("color_g", C.c_uint8), ("color_b", C.c_uint8), ("cursor_brightness", C.c_float),
+                ("rainbow_mode", C.c_bool), ("first_frame", C.c_bool), ("previous_brightness", C.c_void_p)]
+
+
 class ascii_frame_source_t(C.Structure):  # ascii.h:358-361
     _fields_ = [("frame_data", C.c_char_p), ("frame_size", C.c_size_t)]
 
@@ -68,6 +80,9 @@ EXPORTS = [  # every symbol include/asciichat_b200.h declares
     "acb200_set_sync_mode", "acb200_source_acquire", "acb200_source_commit", "acb200_source_device",
     "acb200_grid_frame", "acb200_quantize_table_device", "image_print_16color_dithered",
     "rainbow_replace_ansi_colors", "acb200_mixed_cell_size", "acb200_resize_nn_device", "acb200_mixed_frame_device",
+    "digital_rain_init", "digital_rain_destroy", "digital_rain_apply", "digital_rain_reset",
+    "digital_rain_set_fall_speed", "digital_rain_set_raindrop_length", "digital_rain_set_color",
+    "digital_rain_set_color_from_filter",
 ]
 
 
@@ -175,6 +190,22 @@ def lib():
     L.acb200_mixed_frame_device.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
                                             C.c_int, C.c_ushort, C.c_ushort, C.POINTER(terminal_capabilities_t),
                                             C.c_char_p, C.POINTER(C.c_size_t)]
+    rp = C.POINTER(digital_rain_t)
+    L.digital_rain_init.restype = rp
+    L.digital_rain_init.argtypes = [C.c_int, C.c_int]
+    L.digital_rain_destroy.restype = None
+    L.digital_rain_destroy.argtypes = [rp]
+    L.digital_rain_apply.restype = C.c_void_p
+    L.digital_rain_apply.argtypes = [rp, C.c_char_p, C.c_float]
+    L.digital_rain_reset.restype = None
+    L.digital_rain_reset.argtypes = [rp]
+    for name in ("digital_rain_set_fall_speed", "digital_rain_set_raindrop_length"):
+        getattr(L, name).restype = None
+        getattr(L, name).argtypes = [rp, C.c_float]
+    L.digital_rain_set_color.restype = None
+    L.digital_rain_set_color.argtypes = [rp, C.c_uint8, C.c_uint8, C.c_uint8]
+    L.digital_rain_set_color_from_filter.restype = None
+    L.digital_rain_set_color_from_filter.argtypes = [rp, C.c_int]
     L.acb200_init_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
     L.acb200_device_at.argtypes = [C.c_int]
     L.acb200_bind_thread.argtypes = [C.c_int]
@@ -420,6 +451,27 @@ def image_print_16color_dithered(image, palette, use_background=None):
     if use_background is None:
         return _take(lib().image_print_16color_dithered(C.byref(im), _pal(palette)))
     return _take(lib().image_print_16color_dithered_with_background(C.byref(im), bool(use_background), _pal(palette)))
+
+
+class DigitalRain:
+    """digital_rain_t (lib/video/anim/digital_rain.c) — state on the GPU, the string work on the device"""
+
+    def __init__(self, cols, rows, color_filter=0):
+        self.p = lib().digital_rain_init(cols, rows)
+        if not self.p:
+            raise RuntimeError("digital_rain_init failed: %s" % (last_error(),))
+        lib().digital_rain_set_color_from_filter(self.p, int(color_filter))
+
+    def apply(self, frame, delta_time):
+        return _take(lib().digital_rain_apply(self.p, frame, float(delta_time)))
+
+    def reset(self):
+        lib().digital_rain_reset(self.p)
+
+    def close(self):
+        if self.p:
+            lib().digital_rain_destroy(self.p)
+            self.p = None
 
 
 def calculate_rainbow(t):

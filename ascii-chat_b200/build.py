@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", os.environ.get("ACB200_LIB_NAME", "libasciichat_b200.so"))  # experiments: other name
-SOURCES = ["render_kernels.cu", "engine.cu", "dropin.cu", "grid.cu", "server.cu", "effects.cu"] + ["rk_mode%d.cu" % k for k in range(8)]
+SOURCES = ["render_kernels.cu", "engine.cu", "dropin.cu", "grid.cu", "server.cu", "effects.cu", "rain.cu"] + ["rk_mode%d.cu" % k for k in range(8)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=hidden", "--extended-lambda",
               "-cudart", "static"]

@@ -489,28 +489,33 @@ template <int NR> __device__ __forceinline__ void band_trip(uint32_t (&a)[8], co
 // column sums as the unfiltered path.  A thread owns whole pixels — 48 bytes = 16 pixels = three 16-byte loads per
 // row — takes four rows per trip (12 independent loads in flight, like the unfiltered band), and per 4 pixels spends
 // 2 PRMT + 1 SHR (cut the pixels out of 3 words), 4 DP4A + 4 SHR (grey), 4 LDS (table), 8 ops (re-pack to 3 words).
-static __shared__ uint32_t s_filt[256]; // [gray] = filtered pixel in memory byte order: r | g << 8 | b << 16
+// The table is replicated once per lane (entry v of lane l at word v*32 + l, i.e. in bank l): a warp's 32 lookups with
+// 32 unrelated grey values then hit 32 different banks.  (One shared 1 KB table cost ~3.5 wavefronts per lookup:
+// 41.9 M bank conflicts per 64 frames, profiles/r02c_ncu_filtered_summary.txt.)
+static __shared__ uint32_t s_filt[256 * 32]; // [gray][lane] = filtered pixel in memory byte order: r | g << 8 | b << 16
 template <int NT> __device__ __forceinline__ void init_filt(const RenderParams &p, int tid) {
-  for (int v = tid; v < 256; v += NT)
-    s_filt[v] = __byte_perm(filter_px((uint32_t)v * 0x010101u, p.filt_mode, p.filt_rgb), 0u, 0x4012); // gray(v,v,v) = v
+  for (int w = tid; w < 256 * 32; w += NT) {
+    const uint32_t v = (uint32_t)w >> 5; // gray(v,v,v) = v
+    s_filt[w] = __byte_perm(filter_px(v * 0x010101u, p.filt_mode, p.filt_rgb), 0u, 0x4012);
+  }
 }
 __device__ __forceinline__ uint32_t gray_rgbx(uint32_t rgbx) { // bytes r,g,b,(ignored): (77r+150g+29b)>>8, color_filter.h:172
   return __dp4a(rgbx, 0x001D964Du, 0u) >> 8;
 }
-__device__ __forceinline__ void filt4px(uint32_t &w0, uint32_t &w1, uint32_t &w2) { // 4 pixels live in 3 words
-  const uint32_t p0 = s_filt[gray_rgbx(w0)];
-  const uint32_t p1 = s_filt[gray_rgbx(__byte_perm(w0, w1, 0x6543))];
-  const uint32_t p2 = s_filt[gray_rgbx(__byte_perm(w1, w2, 0x5432))];
-  const uint32_t p3 = s_filt[gray_rgbx(w2 >> 8)];
+__device__ __forceinline__ void filt4px(const uint32_t *T, uint32_t &w0, uint32_t &w1, uint32_t &w2) { // 4 px in 3 words
+  const uint32_t p0 = T[gray_rgbx(w0) << 5]; // T = s_filt + lane
+  const uint32_t p1 = T[gray_rgbx(__byte_perm(w0, w1, 0x6543)) << 5];
+  const uint32_t p2 = T[gray_rgbx(__byte_perm(w1, w2, 0x5432)) << 5];
+  const uint32_t p3 = T[gray_rgbx(w2 >> 8) << 5];
   w0 = p0 | (p1 << 24);
   w1 = (p1 >> 8) | (p2 << 16);
   w2 = (p2 >> 16) | (p3 << 8);
 }
-__device__ __forceinline__ void filt16px(uint4 &a, uint4 &b, uint4 &c) { // 48 bytes = 16 pixels, in place
-  filt4px(a.x, a.y, a.z);
-  filt4px(a.w, b.x, b.y);
-  filt4px(b.z, b.w, c.x);
-  filt4px(c.y, c.z, c.w);
+__device__ __forceinline__ void filt16px(const uint32_t *T, uint4 &a, uint4 &b, uint4 &c) { // 48 bytes = 16 pixels, in place
+  filt4px(T, a.x, a.y, a.z);
+  filt4px(T, a.w, b.x, b.y);
+  filt4px(T, b.z, b.w, c.x);
+  filt4px(T, c.y, c.z, c.w);
 }
 template <int NR> __device__ __forceinline__ void band_trip_filt(uint32_t (&a)[3][8], const uint8_t *&q, uint32_t R) {
   uint4 v[NR][3];
@@ -520,8 +525,9 @@ template <int NR> __device__ __forceinline__ void band_trip_filt(uint32_t (&a)[3
     for (int j = 0; j < 3; j++) v[k][j] = ldg_stream(reinterpret_cast<const uint4 *>(q) + j);
     q += R;
   }
+  const uint32_t *T = s_filt + (threadIdx.x & 31);
 #pragma unroll
-  for (int k = 0; k < NR; k++) filt16px(v[k][0], v[k][1], v[k][2]);
+  for (int k = 0; k < NR; k++) filt16px(T, v[k][0], v[k][1], v[k][2]);
 #pragma unroll
   for (int j = 0; j < 3; j++) {
 #pragma unroll

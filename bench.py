@@ -408,6 +408,15 @@ def display_path_leg(acb, with_reference):
     ours = (time.perf_counter() - t0) / R
     out = {"workload": "one 3840x2160 host frame, flip_x + green filter -> 320x96 truecolor half-block",
            "api": "acb200_display_convert()", "ms_per_call": ours * 1e3, "frame_bytes": len(first)}
+    # the digital-rain stage on that string (display.c:657-671): state on the GPU, string work on the device
+    rain = acb.DigitalRain(COLS, ROWS, 3)
+    r_first = rain.apply(first, 0.016)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        rain.apply(first, 0.016)
+    out["digital_rain"] = {"api": "digital_rain_apply()", "ms_per_call": (time.perf_counter() - t0) / 50 * 1e3,
+                           "in_bytes": len(first), "out_bytes": len(r_first or b"")}
+    rain.close()
     if with_reference:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_bind as ob
@@ -420,6 +429,14 @@ def display_path_leg(acb, with_reference):
         out.update({"bytes_identical_to_reference": bool(exp == first),
                     "reference_ms_per_call": (time.perf_counter() - t0) / 5 * 1e3,
                     "reference_kind": "reference" if ob.ref() is not None else "port"})
+        rr = (ob.RefRain if ob.ref() is not None else ob.PortRain)(COLS, ROWS, 3)
+        r_exp = rr.apply(first, 0.016)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            rr.apply(first, 0.016)
+        out["digital_rain"].update({"bytes_identical_to_reference": bool(r_exp == r_first),
+                                    "reference_ms_per_call": (time.perf_counter() - t0) / 5 * 1e3})
+        rr.close()
     return out
 
 

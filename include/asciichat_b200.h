@@ -84,6 +84,30 @@ typedef struct {
   size_t frame_size;
 } ascii_frame_source_t;
 
+/* include/ascii-chat/video/anim/digital_rain.h — same layout; previous_brightness is DEVICE memory in this library */
+typedef struct {
+  float time_offset;
+  float speed_multiplier;
+  float phase_offset;
+} digital_rain_column_t;
+typedef struct {
+  digital_rain_column_t *columns; /* host, num_columns entries */
+  int num_columns;
+  int num_rows;
+  float time;
+  float fall_speed;
+  float raindrop_length;
+  float brightness_decay;
+  float animation_speed;
+  uint8_t color_r;
+  uint8_t color_g;
+  uint8_t color_b;
+  float cursor_brightness;
+  bool rainbow_mode;
+  bool first_frame;
+  float *previous_brightness; /* num_rows x num_columns filtered brightness, resident on the GPU */
+} digital_rain_t;
+
 #endif /* ASCIICHAT_B200_NO_TYPES */
 
 /* ---- drop-in entry points.  Inputs are borrowed and never modified; every returned
@@ -142,6 +166,20 @@ int apply_color_filter(uint8_t *pixels, uint32_t width, uint32_t height, uint32_
 char *rainbow_replace_ansi_colors(const char *ansi_string, float time_seconds);
 /* lib/video/rgba/color_filter.c:165-236 — hue of the rainbow filter at `time` (host float, like aspect_ratio) */
 void color_filter_calculate_rainbow(float time, uint8_t *r, uint8_t *g, uint8_t *b);
+
+/* lib/video/anim/digital_rain.c (include/ascii-chat/video/anim/digital_rain.h) — the Matrix rain laid over a finished
+ * frame string (src/common/session/display.c:657-671).  The string work (tokenising, the per-cell brightness filter
+ * against the state kept on the GPU, colour scaling, re-emission) runs on the device; the brightness field itself is
+ * evaluated on the host with libm's sinf, in the reference's order of operations — its values are truncated into colour
+ * components, so byte-exactness means the reference's own sinf (see csrc/rain.cu).  filter = color_filter_t. */
+digital_rain_t *digital_rain_init(int num_columns, int num_rows);
+void digital_rain_destroy(digital_rain_t *rain);
+char *digital_rain_apply(digital_rain_t *rain, const char *frame, float delta_time);
+void digital_rain_reset(digital_rain_t *rain);
+void digital_rain_set_fall_speed(digital_rain_t *rain, float speed);
+void digital_rain_set_raindrop_length(digital_rain_t *rain, float length);
+void digital_rain_set_color(digital_rain_t *rain, uint8_t r, uint8_t g, uint8_t b);
+void digital_rain_set_color_from_filter(digital_rain_t *rain, int filter);
 
 /* lib/video/ascii/common.c:601-604, 497-538 — table init / teardown (device LUT cache here) */
 void ascii_simd_init(void);

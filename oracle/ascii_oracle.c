@@ -1260,3 +1260,137 @@ void orc_frame_packet_header(const uint8_t *frame, size_t frame_size, uint32_t w
   put_be32(out24 + 16, orc_crc32c(frame, frame_size));
   put_be32(out24 + 20, 0);
 }
+
+/* ------------------------------------------------------------------ digital rain (second half)
+ * lib/video/anim/digital_rain.c restated: a Matrix-style brightness field laid over a finished frame string.
+ *   brightness(col,row,t) = 1 - fract(wobble((offset[col] + t * fall_speed * speed[col] - row) / raindrop_length)),
+ *   wobble(x) = x + 0.3 sin(sqrt2 x) + 0.2 sin(sqrt5 x)                                  (:35-46, 70-91), 0 beyond the last column
+ * Walking the string with a (col,row) cursor (:405-502): a truecolor SGR (fg or bg) is re-emitted with its components
+ * scaled by the cell's brightness; every other escape sequence is copied; every visible character is preceded by the rain
+ * colour scaled the same way; '\n' resets the column.  Each such VISIT of a cell inside the grid also low-pass filters the
+ * brightness against the value stored for the cell (:421-430), so a cell visited three times in one frame (fg SGR, bg SGR,
+ * glyph) is filtered three times — the order of visits is part of the result.  All float, single precision, in the
+ * reference's order of operations; sinf/fmodf/floorf are libm's. */
+static float rain_hash(float x, float y) { /* :31-35 */
+  float dt = x * 12.9898f + y * 78.233f;
+  float sn = fmodf(dt, (float)M_PI);
+  return fmodf(sinf(sn) * 43758.5453f, 1.0f);
+}
+orc_rain_t *orc_rain_init(int cols, int rows) { /* :97-153 */
+  if (cols <= 0 || rows <= 0) return NULL;
+  orc_rain_t *r = calloc(1, sizeof(*r));
+  r->cols = cols, r->rows = rows;
+  r->offset = malloc(sizeof(float) * (size_t)cols);
+  r->speed = malloc(sizeof(float) * (size_t)cols);
+  r->prev = calloc((size_t)cols * rows, sizeof(float));
+  for (int c = 0; c < cols; c++) {
+    r->offset[c] = rain_hash((float)c, 0.0f) * 1000.0f;
+    r->speed[c] = rain_hash((float)c + 0.1f, 0.0f) * 0.5f + 0.5f;
+  }
+  r->fall_speed = 3.0f, r->drop_len = 12.0f, r->decay = 0.1f, r->anim_speed = 1.0f;
+  r->cr = 0, r->cg = 255, r->cb = 80;
+  r->first = 1;
+  return r;
+}
+void orc_rain_destroy(orc_rain_t *r) {
+  if (!r) return;
+  free(r->offset);
+  free(r->speed);
+  free(r->prev);
+  free(r);
+}
+void orc_rain_set_filter(orc_rain_t *r, int filter) { /* :205-230 */
+  if (!r) return;
+  r->rainbow = 0;
+  if (filter == ORC_FILTER_NONE) r->cr = 0, r->cg = 255, r->cb = 80;
+  else if (filter == ORC_FILTER_RAINBOW) r->rainbow = 1, r->cr = 255, r->cg = 0, r->cb = 0;
+  else if (filter > 0 && filter < ORC_FILTER_COUNT) r->cr = k_filters[filter].r, r->cg = k_filters[filter].g, r->cb = k_filters[filter].b;
+}
+float orc_rain_target(const orc_rain_t *r, int col, int row, float t) { /* get_rain_brightness, :70-91 */
+  if (col < 0 || col >= r->cols) return 0.0f;
+  float column_time = r->offset[col] + t * r->fall_speed * r->speed[col];
+  float x = (column_time - (float)row) / r->drop_len;
+  x = x + 0.3f * sinf((float)1.4142135623730951 * x) + 0.2f * sinf((float)2.23606797749979 * x);
+  return 1.0f - (x - floorf(x));
+}
+/* one visit of cell (col,row): filtered brightness, whether the cell is a drop's cursor (:413-430) */
+static float rain_visit(orc_rain_t *r, int col, int row, float t, int *cursor) {
+  float b = orc_rain_target(r, col, row, t);
+  *cursor = b > orc_rain_target(r, col, row + 1, t);
+  if (row < r->rows && col < r->cols) {
+    float *p = &r->prev[(size_t)row * r->cols + col];
+    if (!r->first) b = *p + (b - *p) * r->decay;
+    *p = b;
+  }
+  return b;
+}
+static void rain_code(bb_t *o, int layer, int red, int green, int blue, float b, int cursor) { /* :326-364 */
+  if (cursor) b *= 2.0f;
+  if (b < 0.0f) b = 0.0f;
+  if (b > 1.0f) b = 1.0f;
+  int v[3] = {(int)((float)red * b), (int)((float)green * b), (int)((float)blue * b)};
+  for (int k = 0; k < 3; k++) v[k] = v[k] < 0 ? 0 : v[k] > 255 ? 255 : v[k];
+  put_sgr_rgb(o, layer, v[0], v[1], v[2]);
+}
+/* ESC [ (38|48) ;2; R ; G ; B m — returns the byte after it, or NULL (:240-301) */
+static const char *rain_parse_sgr(const char *s, int *rgb, int *layer) {
+  if (s[0] != 0x1b || s[1] != '[') return NULL;
+  if (s[2] == '3' && s[3] == '8') *layer = 38;
+  else if (s[2] == '4' && s[3] == '8') *layer = 48;
+  else return NULL;
+  if (s[4] != ';' || s[5] != '2' || s[6] != ';') return NULL;
+  const char *p = s + 7;
+  for (int k = 0; k < 3; k++) {
+    rgb[k] = 0;
+    while (*p >= '0' && *p <= '9') rgb[k] = rgb[k] * 10 + (*p++ - '0');
+    if (*p != (k < 2 ? ';' : 'm')) return NULL;
+    p++;
+  }
+  return p;
+}
+static int rain_utf8_len(const unsigned char *s) { /* utf8_decode's length rule, lib/util/utf8.c:18-44; invalid = 1 */
+  int n = s[0] < 0x80 ? 1 : (s[0] & 0xE0) == 0xC0 ? 2 : (s[0] & 0xF0) == 0xE0 ? 3 : (s[0] & 0xF8) == 0xF0 ? 4 : 0;
+  for (int k = 1; k < n; k++)
+    if ((s[k] & 0xC0) != 0x80) return 1;
+  return n ? n : 1;
+}
+char *orc_rain_apply(orc_rain_t *r, const char *frame, float dt, size_t *out_len) { /* :366-520 */
+  if (!r || !frame) return NULL;
+  r->time += dt * r->anim_speed;
+  const float t = r->time;
+  if (r->rainbow) orc_calculate_rainbow(t, &r->cr, &r->cg, &r->cb);
+  bb_t o = {0};
+  int col = 0, row = 0;
+  for (const char *s = frame; *s;) {
+    int rgb[3], layer, cursor;
+    const char *after;
+    if (*s == 0x1b) {
+      if ((after = rain_parse_sgr(s, rgb, &layer)) != NULL) {
+        float b = rain_visit(r, col, row, t, &cursor);
+        rain_code(&o, layer, rgb[0], rgb[1], rgb[2], b, cursor);
+        s = after;
+      } else { /* any other sequence is copied: ESC alone, or ESC [ ... up to and including a byte in @..~ (:306-324) */
+        const char *e = s + 1;
+        if (*e == '[') {
+          e++;
+          while (*e && !(*e >= '@' && *e <= '~')) e++;
+          if (*e) e++;
+        }
+        bb_put(&o, s, (size_t)(e - s));
+        s = e;
+      }
+    } else if (*s == '\n') {
+      bb_c(&o, '\n');
+      s++, row++, col = 0;
+    } else {
+      float b = rain_visit(r, col, row, t, &cursor);
+      rain_code(&o, 38, r->cr, r->cg, r->cb, b, cursor);
+      int n = rain_utf8_len((const unsigned char *)s);
+      bb_put(&o, s, (size_t)n);
+      s += n, col++;
+    }
+  }
+  r->first = 0;
+  return bb_finish(&o, out_len);
+}
+

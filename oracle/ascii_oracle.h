@@ -87,6 +87,19 @@ char *orc_display_convert(const uint8_t *rgb, int w, int h, long width, long hei
                           int wants_padding, int preserve_aspect, int stretch, const char *palette, int flip_x,
                           int flip_y, int filter, float time_seconds, int scale, size_t *out_len);
 
+/* ---- digital rain (lib/video/anim/digital_rain.c): stateful brightness field over a finished frame string */
+typedef struct {
+  int cols, rows, first, rainbow;
+  float *offset, *speed, *prev; /* per-column time offset / speed multiplier (:131-136); per-cell filtered brightness */
+  float time, fall_speed, drop_len, decay, anim_speed;
+  uint8_t cr, cg, cb;
+} orc_rain_t;
+orc_rain_t *orc_rain_init(int cols, int rows);
+void orc_rain_destroy(orc_rain_t *r);
+void orc_rain_set_filter(orc_rain_t *r, int filter);                /* digital_rain_set_color_from_filter */
+float orc_rain_target(const orc_rain_t *r, int col, int row, float t); /* get_rain_brightness */
+char *orc_rain_apply(orc_rain_t *r, const char *frame, float delta_time, size_t *out_len);
+
 /* ---- wire packaging (lib/network/crc32.c, lib/network/acip/server.c:203-214) */
 uint32_t orc_crc32c(const uint8_t *p, size_t n);
 void orc_frame_packet_header(const uint8_t *frame, size_t frame_size, uint32_t width, uint32_t height,

@@ -205,16 +205,7 @@ bool timer_is_initialized(void) { return false; }
 bool timer_start(const char *name) { (void)name; return false; }
 double timer_stop(const char *name) { (void)name; return 0.0; }
 
-/* ---- utf8 helpers: only reached from validate_palette_chars(), not rendering -- */
-int utf8_display_width(const char *str) { return str ? (int)strlen(str) : 0; }
-int utf8_display_width_n(const char *str, size_t max_bytes) {
-  return str ? (int)strnlen(str, max_bytes) : 0;
-}
-size_t utf8_to_codepoints(const char *str, uint32_t *out_codepoints, size_t max_codepoints) {
-  size_t n = 0;
-  while (str && *str && n < max_codepoints) out_codepoints[n++] = (unsigned char)*str++;
-  return n;
-}
+/* utf8 helpers: the reference's own lib/util/utf8.c + the vendored utf8proc are compiled in (oracle/Makefile) */
 
 /* lib/options/common.c:376-379 — written by precalc_rgb_palettes, read by no renderer */
 unsigned short int RED[256], GREEN[256], BLUE[256], GRAY[256];

@@ -69,6 +69,12 @@ for i in range(3):
 acb.synchronize()
 got = acb.mixed_frame_device([t.data_ptr() for t in d_cell], ws, hs, True, 40, 12, acb.make_caps(2, 0, True), "standard")
 bad += got != ob.port_mixed_frame(srcs, 40, 12, 2, 0, "standard", True)[0]
+for cols, rows, filt, frames in ob.rain_sequences()[3:]:
+    a, b = acb.DigitalRain(cols, rows, filt), ob.PortRain(cols, rows, filt)
+    for s_, dt in frames[:4]:
+        bad += a.apply(s_, dt) != b.apply(s_, dt)
+    a.close()
+    b.close()
 lens = [0, 1, 63, 64, 65, 16384, 16385, 40000]
 pitch = 40016
 arena = np.random.default_rng(1).integers(0, 256, (len(lens), pitch), dtype=np.uint8)

@@ -140,6 +140,14 @@ def port():
     L.orc_apply_color_filter.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_float]
     L.orc_rainbow_replace.restype = C.c_void_p
     L.orc_rainbow_replace.argtypes = [C.c_char_p, C.c_float]
+    L.orc_rain_init.restype = C.c_void_p
+    L.orc_rain_init.argtypes = [C.c_int, C.c_int]
+    L.orc_rain_destroy.restype = None
+    L.orc_rain_destroy.argtypes = [C.c_void_p]
+    L.orc_rain_set_filter.restype = None
+    L.orc_rain_set_filter.argtypes = [C.c_void_p, C.c_int]
+    L.orc_rain_apply.restype = C.c_void_p
+    L.orc_rain_apply.argtypes = [C.c_void_p, C.c_char_p, C.c_float, C.POINTER(C.c_size_t)]
     L.orc_print_dither.restype = C.c_void_p
     L.orc_print_dither.argtypes = [u8p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_size_t)]
     L.orc_display_convert.restype = C.c_void_p
@@ -219,6 +227,16 @@ def ref():
     L.image_print_16color_dithered.argtypes = [ip, C.c_char_p]
     L.image_print_16color_dithered_with_background.restype = C.c_void_p
     L.image_print_16color_dithered_with_background.argtypes = [ip, C.c_bool, C.c_char_p]
+    L.digital_rain_init.restype = C.c_void_p
+    L.digital_rain_init.argtypes = [C.c_int, C.c_int]
+    L.digital_rain_destroy.restype = None
+    L.digital_rain_destroy.argtypes = [C.c_void_p]
+    L.digital_rain_apply.restype = C.c_void_p
+    L.digital_rain_apply.argtypes = [C.c_void_p, C.c_char_p, C.c_float]
+    L.digital_rain_set_color_from_filter.restype = None
+    L.digital_rain_set_color_from_filter.argtypes = [C.c_void_p, C.c_int]
+    L.digital_rain_reset.restype = None
+    L.digital_rain_reset.argtypes = [C.c_void_p]
     L.ref_oracle_display_convert.restype = C.c_void_p
     L.ref_oracle_display_convert.argtypes = [u8p, C.c_int, C.c_int, C.c_long, C.c_long, cp, C.c_int, C.c_int,
                                              C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_size_t)]
@@ -310,6 +328,61 @@ def ref_print_dither(img, palette="standard", variant=0):
     if variant == 2:
         return _take(ref().image_print_16color_dithered(C.byref(im), pal_bytes(palette)))
     return _take(ref().image_print_16color_dithered_with_background(C.byref(im), variant == 0, pal_bytes(palette)))
+
+
+class RefRain:
+    """the compiled reference's digital_rain_t (lib/video/anim/digital_rain.c), driven frame by frame"""
+
+    def __init__(self, cols, rows, color_filter=0):
+        self.p = ref().digital_rain_init(cols, rows)
+        ref().digital_rain_set_color_from_filter(self.p, int(color_filter))
+
+    def apply(self, frame, dt):
+        return _take(ref().digital_rain_apply(self.p, frame, float(dt)))
+
+    def reset(self):
+        ref().digital_rain_reset(self.p)
+
+    def close(self):
+        ref().digital_rain_destroy(self.p)
+
+
+class PortRain:
+    def __init__(self, cols, rows, color_filter=0):
+        self.p = port().orc_rain_init(cols, rows)
+        port().orc_rain_set_filter(self.p, int(color_filter))
+
+    def apply(self, frame, dt):
+        n = C.c_size_t(0)
+        return _take(port().orc_rain_apply(self.p, frame, float(dt), C.byref(n)))
+
+    def close(self):
+        port().orc_rain_destroy(self.p)
+
+
+def rain_sequences():
+    """deterministic multi-frame inputs for the digital-rain checks: (cols, rows, filter, [(frame string, dt), ...])"""
+    out = []
+    for k, (cols, rows, level, mode, filt, pal) in enumerate(((80, 24, 3, 0, 0, "standard"), (80, 24, 0, 0, 3, "standard"),
+                                                           (160, 48, 3, 2, 12, "standard"), (40, 12, 2, 0, 7, "blocks"),
+                                                           (100, 30, 3, 0, 1, "cool"), (64, 20, 1, 2, 0, "standard"))):
+        frames = []
+        for f in range(8):
+            s = port_convert(gen(("noise", "bars", "gradient")[(f + k) % 3], 320, 240, f), cols, rows, level, mode, pal)
+            if f == 5:
+                s = s + b"\n\n" + s[:300] + b"\n"      # more rows than the grid, trailing newline
+            if f == 6:
+                s = s[: len(s) // 2]                       # cut mid-frame (fewer rows, maybe mid-sequence)
+            frames.append((s, 0.033 * (1 + f % 3)))
+        out.append((cols, rows, filt, frames))
+    # hand-made strings: other escape sequences, lone ESC, ESC before newline, invalid UTF-8, a CSI that swallows a
+    # newline (the serial fallback), bg+fg pairs on one cell, colours beyond 255, an empty frame
+    e = b"\x1b"
+    odd = [b"plain\ntext", e + b"[0m" + b"A" + e + b"[7bB\n" + e + b"\n" + e, b"\xe2\x96\x80\xe2\x96x\xff\xc3(\n\xf0\x9f\x98\x80!",
+           e + b"[38;2;300;2;1mX" + e + b"[48;2;9;9;9m" + e + b"[38;2;1;2;3mY\n" + e + b"[38;2;1;2mZ" + e + b"[38;5;7mQ",
+           b"ab" + e + b"[12\n34mcd\nef", b"", b"\n\n\n", b"x" * 300 + b"\n" + b"y" * 5]
+    out.append((10, 3, 5, [(s, 0.05) for s in odd] + [(s, 0.1) for s in odd]))
+    return out
 
 
 def ref_rainbow_replace(s, t):

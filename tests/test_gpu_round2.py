@@ -185,3 +185,29 @@ def test_filtered_box_streaming_all_filters(acb, ob):
             exp = ob.port_display_convert(img, c, r, level, mode, flip_x=fx, flip_y=fy, color_filter=filt, time_s=0.5,
                                           scale=ob.SCALE_BOX)
             assert got == exp, (W, H, c, r, mode, filt, fx, fy, level)
+
+
+def test_digital_rain(acb, ob):
+    """digital_rain_init / _apply / _reset on the device against the compiled reference, frame after frame (the filtered
+    brightness is state carried on the GPU), including strings whose escape sequences swallow newlines (serial path)"""
+    mk = ob.RefRain if ob.ref() is not None else ob.PortRain
+    n = 0
+    for cols, rows, filt, frames in ob.rain_sequences():
+        want, ours = mk(cols, rows, filt), acb.DigitalRain(cols, rows, filt)
+        for i, (s, dt) in enumerate(frames):
+            got, exp = ours.apply(s, dt), want.apply(s, dt)
+            assert got == exp, (cols, rows, filt, i, len(s), None if got is None else len(got), len(exp))
+            n += 1
+        ours.close()
+        want.close()
+    assert n > 60
+    # reset: the next frame is a first frame again
+    s = ob.port_convert(ob.gen("noise", 320, 240, 1), 80, 24, 3, 0)
+    a, b = acb.DigitalRain(80, 24), acb.DigitalRain(80, 24)
+    first = a.apply(s, 0.1)
+    a.apply(s, 0.1)
+    a.reset()
+    assert a.apply(s, 0.1) == first == b.apply(s, 0.1)
+    a.close()
+    b.close()
+    assert not acb.lib().digital_rain_init(0, 5) and acb.last_error()[0] == 86

@@ -479,3 +479,17 @@ def test_box_fast_equals_box(ob):
         b = np.empty((dh, dw, 3), np.uint8)
         ob.port().orc_resize_box_fast(src.ctypes.data_as(u8p), sw, sh, b.ctypes.data_as(u8p), dw, dh)
         assert np.array_equal(a, b), (sw, sh, dw, dh)
+
+
+def test_port_vs_ref_digital_rain(ob, ref_lib):
+    """digital_rain_apply (lib/video/anim/digital_rain.c:366-520) frame after frame: the state carried between frames,
+    the per-visit filter, cursor cells, the rain colour per filter, rainbow mode, malformed strings"""
+    n = 0
+    for cols, rows, filt, frames in ob.rain_sequences():
+        a, b = ob.RefRain(cols, rows, filt), ob.PortRain(cols, rows, filt)
+        for i, (s, dt) in enumerate(frames):
+            assert a.apply(s, dt) == b.apply(s, dt), (cols, rows, filt, i)
+            n += 1
+        a.close()
+        b.close()
+    assert n > 60
