@@ -33,7 +33,8 @@ struct RainImpl {
 };
 
 constexpr int RN_NT = 256, RN_PER = 16, RN_CHUNK = RN_NT * RN_PER;
-constexpr int RN_LPB = 4; // lines per block in the walk kernels: few threads per SM, each with the L1 to itself
+constexpr int RN_LPB = 4;          // lines per block in the walk kernels
+constexpr uint32_t RN_STAGE = 12288; // bytes of a line staged in shared memory (4 lines = 48 KB); the rest is read from L2
 
 struct RainParams {
   const uint8_t *in;
@@ -138,11 +139,13 @@ __device__ __forceinline__ void put_scaled(O &o, bool fg, int r, int g, int b, f
 
 // The reference's loop (digital_rain.c:405-502) over the byte range [i0, i1) of the string, cursor starting at
 // (col 0, row0).  Returns the number of output bytes; *complex is raised when an escape sequence runs past i1.
+// The walker reads its line out of a shared-memory copy (stage[0 .. staged) = bytes i0 ..): a serial byte-at-a-time loop
+// is bound by load latency, and shared memory answers ten times faster than L2.
 template <class O> __device__ void rain_walk(const RainParams &p, uint32_t i0, uint32_t i1, int row0, O &o, bool write_state,
-                                             uint32_t *complex) {
+                                             uint32_t *complex, const uint8_t *stage, uint32_t staged) {
   const uint8_t *s = p.in;
   const uint32_t n = p.n;
-  auto at = [&](uint32_t i) -> uint32_t { return i < n ? s[i] : 0u; };
+  auto at = [&](uint32_t i) -> uint32_t { return (i - i0) < staged ? stage[i - i0] : (i < n ? s[i] : 0u); };
   int col = 0, row = row0;
   int run_col = -1, run_row = -1; // the cell the running filtered value belongs to
   float run_val = 0.0f;
@@ -165,7 +168,7 @@ template <class O> __device__ void rain_walk(const RainParams &p, uint32_t i0, u
   };
   uint32_t i = i0;
   while (i < i1) {
-    const uint32_t c = s[i];
+    const uint32_t c = at(i);
     if (c == 0x1b) {
       // parse_ansi_color (:240-301): ESC [ (38|48) ;2; R ; G ; B m
       bool colour = false, fg = false;
@@ -195,11 +198,11 @@ template <class O> __device__ void rain_walk(const RainParams &p, uint32_t i0, u
         j = i + 1;
         if (at(j) == '[') {
           j++;
-          while (j < n && !(s[j] >= '@' && s[j] <= '~')) j++;
+          while (j < n && !(at(j) >= '@' && at(j) <= '~')) j++;
           if (j < n) j++;
         }
         if (j > i1) *complex = 1u; // the sequence swallowed this line's newline
-        for (uint32_t k = i; k < j; k++) o.put(s[k]);
+        for (uint32_t k = i; k < j; k++) o.put((uint8_t)at(k));
         i = j;
       }
     } else if (c == '\n') {
@@ -216,23 +219,37 @@ template <class O> __device__ void rain_walk(const RainParams &p, uint32_t i0, u
           len = 1;
           break;
         }
-      for (int k = 0; k < len; k++) o.put(s[i + k]);
+      for (int k = 0; k < len; k++) o.put((uint8_t)at(i + k));
       i += len, col++;
     }
   }
 }
 
 template <bool WRITE> __global__ void __launch_bounds__(32) k_rain_walk(const RainParams p) {
+  extern __shared__ uint8_t s_stage[]; // RN_LPB x RN_STAGE
+  // all 32 threads copy the block's lines (plus a few bytes of look-ahead) into shared memory, then RN_LPB of them walk
+  for (int l = 0; l < RN_LPB; l++) {
+    const uint32_t line = blockIdx.x * RN_LPB + l;
+    if (line >= p.nlines) break;
+    const uint32_t i0 = p.line_start[line], i1 = line + 1 < p.nlines ? p.line_start[line + 1] : p.n;
+    uint32_t len = min(i1 - i0 + 32u, RN_STAGE);
+    if (i0 + len > p.n) len = p.n - i0;
+    for (uint32_t k = threadIdx.x; k < len; k += 32) s_stage[l * RN_STAGE + k] = p.in[i0 + k];
+  }
+  __syncthreads();
   const uint32_t line = blockIdx.x * RN_LPB + threadIdx.x;
   if (threadIdx.x >= RN_LPB || line >= p.nlines) return;
   const uint32_t i0 = p.line_start[line], i1 = line + 1 < p.nlines ? p.line_start[line + 1] : p.n;
+  uint32_t staged = min(i1 - i0 + 32u, RN_STAGE);
+  if (i0 + staged > p.n) staged = p.n - i0;
+  const uint8_t *stage = s_stage + threadIdx.x * RN_STAGE;
   uint32_t complex = 0;
   if (WRITE) {
     ByteOut o{p.out + p.line_off[line]};
-    rain_walk(p, i0, i1, (int)line, o, true, &complex);
+    rain_walk(p, i0, i1, (int)line, o, true, &complex, stage, staged);
   } else {
     CountOut o;
-    rain_walk(p, i0, i1, (int)line, o, false, &complex);
+    rain_walk(p, i0, i1, (int)line, o, false, &complex, stage, staged);
     p.line_len[line] = o.n;
     if (complex) atomicOr(&p.result[1], 1u);
   }
@@ -448,7 +465,8 @@ char *digital_rain_apply(digital_rain_t *rain, const char *frame, float delta_ti
   k_rain_nl_count<<<(unsigned)chunks, RN_NT, 0, st>>>(p);
   k_rain_line_starts<<<(unsigned)chunks, RN_NT, 0, st>>>(p);
   const unsigned walk_grid = (unsigned)((nlines + RN_LPB - 1) / RN_LPB);
-  k_rain_walk<false><<<walk_grid, 32, 0, st>>>(p);
+  constexpr size_t walk_smem = (size_t)RN_LPB * RN_STAGE;
+  k_rain_walk<false><<<walk_grid, 32, walk_smem, st>>>(p);
   k_rain_scan<<<1, RN_NT, 0, st>>>(p);
   count_launch(4);
   if (cudaGetLastError() != cudaSuccess ||
@@ -459,7 +477,7 @@ char *digital_rain_apply(digital_rain_t *rain, const char *frame, float delta_ti
     if (cudaMemsetAsync(p.line_start, 0, sizeof(uint32_t), st) != cudaSuccess ||
         cudaMemsetAsync(p.result, 0, 16 * sizeof(uint32_t), st) != cudaSuccess)
       return fail("fallback setup");
-    k_rain_walk<false><<<1, 32, 0, st>>>(p);
+    k_rain_walk<false><<<1, 32, walk_smem, st>>>(p);
     k_rain_scan<<<1, RN_NT, 0, st>>>(p);
     count_launch(2);
     if (cudaGetLastError() != cudaSuccess ||
@@ -471,7 +489,7 @@ char *digital_rain_apply(digital_rain_t *rain, const char *frame, float delta_ti
     if (total + 1 > out_cap) set_error(E_INVALID_STATE, "digital_rain_apply: output larger than its bound");
     return nullptr;
   }
-  k_rain_walk<true><<<(unsigned)((p.nlines + RN_LPB - 1) / RN_LPB), 32, 0, st>>>(p);
+  k_rain_walk<true><<<(unsigned)((p.nlines + RN_LPB - 1) / RN_LPB), 32, walk_smem, st>>>(p);
   count_launch();
   if (cudaGetLastError() != cudaSuccess ||
       cudaMemcpyAsync(cx->h_out, cx->d_out, total, cudaMemcpyDeviceToHost, st) != cudaSuccess || wait_stream(cx) != E_OK)

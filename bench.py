@@ -308,6 +308,52 @@ def server_path_leg(acb, with_reference):
     return out
 
 
+def crc_overlap_leg(acb, torch, cfg, d_in, n, cap):
+    """the CRC32-C scan is bound by its byte recurrence, not by HBM, so it hides behind the NEXT
+    batch's render when the two run on different streams (double-buffered arenas): K batches rendered + packaged,
+    serial on one stream vs overlapped on two.  Event-timed on the render stream."""
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    bufs = []
+    for _ in range(2):
+        bufs.append((torch.empty(n * cap, dtype=torch.uint8, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda"),
+                     torch.empty(acb.scratch_bytes(cfg, n), dtype=torch.uint8, device="cuda"),
+                     torch.zeros(n * 24, dtype=torch.uint8, device="cuda")))
+    K = 12
+
+    def run(overlap):
+        torch.cuda.synchronize()
+        crc_done = [None, None]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(sa)
+        for i in range(K):
+            out, ln, scr, hdr = bufs[i & 1]
+            if overlap and crc_done[i & 1] is not None:
+                sa.wait_event(crc_done[i & 1])  # the arena is free once its previous scan has finished
+            acb.render_batch_device(cfg, d_in.data_ptr(), n, out.data_ptr(), cap, ln.data_ptr(), scr.data_ptr(), sa.cuda_stream)
+            if overlap:
+                ev = torch.cuda.Event()
+                ev.record(sa)
+                sb.wait_event(ev)
+                acb.frame_packets_device(out.data_ptr(), cap, ln.data_ptr(), n, COLS, ROWS, hdr.data_ptr(), sb.cuda_stream)
+                crc_done[i & 1] = torch.cuda.Event()
+                crc_done[i & 1].record(sb)
+            else:
+                acb.frame_packets_device(out.data_ptr(), cap, ln.data_ptr(), n, COLS, ROWS, hdr.data_ptr(), sa.cuda_stream)
+        if overlap:
+            sa.wait_stream(sb)
+        e1.record(sa)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / K
+    run(False), run(True)
+    serial, over = run(False), run(True)
+    hdr_ok = bool(torch.equal(bufs[0][3], bufs[1][3]))  # both arenas hold the same batch: same headers
+    del bufs
+    torch.cuda.empty_cache()
+    return {"ms_per_batch_serial": serial, "ms_per_batch_overlapped": over, "batches": K, "frames_per_batch": n,
+            "headers_equal": hdr_ok,
+            "note": "render (stream A) || CRC32-C + packet headers of the previous batch (stream B), double-buffered arenas"}
+
+
 def device_extras_leg(acb, torch, d_out, cap, d_len, n, peak):
     """SURVEY.md §8f rows 1 and 4 on resident data, device-timed with CUDA events on torch's current stream (the
     kernels are launched on that stream): the whole-image colour filter (apply_color_filter as an in-place map,
@@ -724,6 +770,10 @@ def main():
     extras = None
     if rank == 0 and world == 1 and not args.resident_only:
         extras = device_extras_leg(acb, torch, d_out, cap, d_len, n, peaks()[0])
+        del d_out, d_scr
+        torch.cuda.empty_cache()
+        extras["frame_packets_overlapped"] = crc_overlap_leg(acb, torch, cfg, d_in, n, cap)
+        d_out = d_scr = None
     del d_in, d_out, d_scr
     torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.resident_only:
