@@ -17,6 +17,7 @@
 // escape sequence swallows a newline, so the device form is one thread per line, each running the reference's loop over
 // its own byte range (pass 1 counts the output bytes, a scan places the lines, pass 2 writes); a string in which a CSI
 // sequence does run across a '\n' is detected in pass 1 and re-run as a single range by one thread — slow, exact.
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -34,7 +35,9 @@ struct RainImpl {
 
 constexpr int RN_NT = 256, RN_PER = 16, RN_CHUNK = RN_NT * RN_PER;
 constexpr int RN_LPB = 4;          // lines per block in the walk kernels
-constexpr uint32_t RN_STAGE = 12288; // bytes of a line staged in shared memory (4 lines = 48 KB); the rest is read from L2
+constexpr uint32_t RN_STAGE = 12288; // bytes of a line staged in shared memory; the rest is read from L2
+constexpr int RN_SCOLS = 512;        // columns of the line's brightness rows (this row, the row below, the state) staged too
+constexpr size_t RN_LINE_SMEM = RN_STAGE + 3u * RN_SCOLS * sizeof(float);
 
 struct RainParams {
   const uint8_t *in;
@@ -141,8 +144,10 @@ __device__ __forceinline__ void put_scaled(O &o, bool fg, int r, int g, int b, f
 // (col 0, row0).  Returns the number of output bytes; *complex is raised when an escape sequence runs past i1.
 // The walker reads its line out of a shared-memory copy (stage[0 .. staged) = bytes i0 ..): a serial byte-at-a-time loop
 // is bound by load latency, and shared memory answers ten times faster than L2.
+// So are the three float rows a line's visits read (un-filtered brightness of its row and of the row below, the state of
+// its row): a visit is three dependent loads, ~1.5 us from L2 and there are ~900 per line.
 template <class O> __device__ void rain_walk(const RainParams &p, uint32_t i0, uint32_t i1, int row0, O &o, bool write_state,
-                                             uint32_t *complex, const uint8_t *stage, uint32_t staged) {
+                                             uint32_t *complex, const uint8_t *stage, uint32_t staged, const float *frows) {
   const uint8_t *s = p.in;
   const uint32_t n = p.n;
   auto at = [&](uint32_t i) -> uint32_t { return (i - i0) < staged ? stage[i - i0] : (i < n ? s[i] : 0u); };
@@ -150,7 +155,9 @@ template <class O> __device__ void rain_walk(const RainParams &p, uint32_t i0, u
   int run_col = -1, run_row = -1; // the cell the running filtered value belongs to
   float run_val = 0.0f;
   auto target = [&](int c, int r) -> float { // get_rain_brightness: 0 beyond the last column (:71-73)
-    return (c < p.cols && r < p.rows_tab) ? p.target[(size_t)r * p.cols + c] : 0.0f;
+    if (c >= p.cols || r >= p.rows_tab) return 0.0f;
+    if (c < RN_SCOLS && (unsigned)(r - row0) < 2u) return frows[(r - row0) * RN_SCOLS + c];
+    return p.target[(size_t)r * p.cols + c];
   };
   auto visit = [&](bool *cursor) -> float { // :413-430
     float b = target(col, row);
@@ -158,7 +165,9 @@ template <class O> __device__ void rain_walk(const RainParams &p, uint32_t i0, u
     if (row < p.rows && col < p.cols) {
       const size_t idx = (size_t)row * p.cols + col;
       if (!p.first_frame) {
-        const float prev = (run_col == col && run_row == row) ? run_val : p.prev[idx];
+        const float prev = (run_col == col && run_row == row) ? run_val
+                           : (row == row0 && col < RN_SCOLS) ? frows[2 * RN_SCOLS + col]
+                                                             : p.prev[idx];
         b = __fadd_rn(prev, __fmul_rn(__fsub_rn(b, prev), p.decay));
       }
       run_col = col, run_row = row, run_val = b;
@@ -226,15 +235,24 @@ template <class O> __device__ void rain_walk(const RainParams &p, uint32_t i0, u
 }
 
 template <bool WRITE> __global__ void __launch_bounds__(32) k_rain_walk(const RainParams p) {
-  extern __shared__ uint8_t s_stage[]; // RN_LPB x RN_STAGE
-  // all 32 threads copy the block's lines (plus a few bytes of look-ahead) into shared memory, then RN_LPB of them walk
+  extern __shared__ __align__(16) uint8_t s_stage[]; // RN_LPB x RN_LINE_SMEM
+  // all 32 threads copy the block's lines (plus a few bytes of look-ahead) and their float rows into shared memory,
+  // then RN_LPB of them walk
   for (int l = 0; l < RN_LPB; l++) {
     const uint32_t line = blockIdx.x * RN_LPB + l;
     if (line >= p.nlines) break;
+    uint8_t *base = s_stage + (size_t)l * RN_LINE_SMEM;
     const uint32_t i0 = p.line_start[line], i1 = line + 1 < p.nlines ? p.line_start[line + 1] : p.n;
     uint32_t len = min(i1 - i0 + 32u, RN_STAGE);
     if (i0 + len > p.n) len = p.n - i0;
-    for (uint32_t k = threadIdx.x; k < len; k += 32) s_stage[l * RN_STAGE + k] = p.in[i0 + k];
+    for (uint32_t k = threadIdx.x; k < len; k += 32) base[k] = p.in[i0 + k];
+    float *fr = reinterpret_cast<float *>(base + RN_STAGE);
+    const int nc = min(p.cols, RN_SCOLS);
+    for (int c = threadIdx.x; c < nc; c += 32) {
+      fr[c] = (int)line < p.rows_tab ? p.target[(size_t)line * p.cols + c] : 0.0f;
+      fr[RN_SCOLS + c] = (int)line + 1 < p.rows_tab ? p.target[(size_t)(line + 1) * p.cols + c] : 0.0f;
+      fr[2 * RN_SCOLS + c] = (int)line < p.rows ? p.prev[(size_t)line * p.cols + c] : 0.0f;
+    }
   }
   __syncthreads();
   const uint32_t line = blockIdx.x * RN_LPB + threadIdx.x;
@@ -242,14 +260,15 @@ template <bool WRITE> __global__ void __launch_bounds__(32) k_rain_walk(const Ra
   const uint32_t i0 = p.line_start[line], i1 = line + 1 < p.nlines ? p.line_start[line + 1] : p.n;
   uint32_t staged = min(i1 - i0 + 32u, RN_STAGE);
   if (i0 + staged > p.n) staged = p.n - i0;
-  const uint8_t *stage = s_stage + threadIdx.x * RN_STAGE;
+  const uint8_t *stage = s_stage + (size_t)threadIdx.x * RN_LINE_SMEM;
+  const float *frows = reinterpret_cast<const float *>(stage + RN_STAGE);
   uint32_t complex = 0;
   if (WRITE) {
     ByteOut o{p.out + p.line_off[line]};
-    rain_walk(p, i0, i1, (int)line, o, true, &complex, stage, staged);
+    rain_walk(p, i0, i1, (int)line, o, true, &complex, stage, staged, frows);
   } else {
     CountOut o;
-    rain_walk(p, i0, i1, (int)line, o, false, &complex, stage, staged);
+    rain_walk(p, i0, i1, (int)line, o, false, &complex, stage, staged, frows);
     p.line_len[line] = o.n;
     if (complex) atomicOr(&p.result[1], 1u);
   }
@@ -465,7 +484,16 @@ char *digital_rain_apply(digital_rain_t *rain, const char *frame, float delta_ti
   k_rain_nl_count<<<(unsigned)chunks, RN_NT, 0, st>>>(p);
   k_rain_line_starts<<<(unsigned)chunks, RN_NT, 0, st>>>(p);
   const unsigned walk_grid = (unsigned)((nlines + RN_LPB - 1) / RN_LPB);
-  constexpr size_t walk_smem = (size_t)RN_LPB * RN_STAGE;
+  constexpr size_t walk_smem = (size_t)RN_LPB * RN_LINE_SMEM; // 72 KB: above the 48 KB default, opted in per device
+  {
+    static std::atomic<uint64_t> configured{0};
+    if (!((configured.load(std::memory_order_acquire) >> cx->device) & 1ull)) {
+      if (cudaFuncSetAttribute(k_rain_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem) != cudaSuccess ||
+          cudaFuncSetAttribute(k_rain_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem) != cudaSuccess)
+        return fail("shared-memory opt-in");
+      configured.fetch_or(1ull << cx->device, std::memory_order_release);
+    }
+  }
   k_rain_walk<false><<<walk_grid, 32, walk_smem, st>>>(p);
   k_rain_scan<<<1, RN_NT, 0, st>>>(p);
   count_launch(4);

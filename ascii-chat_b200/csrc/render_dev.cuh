@@ -944,44 +944,30 @@ __device__ __forceinline__ uint32_t emit_direct_prepare(const RenderParams &p, i
 }
 
 // finish: look-back for the row's offset (and, truecolor-fg, the colour state above), materialise, store.
-// The look-back is done by the first warp of the NT threads; s_lb (2 words of shared memory) broadcasts its result.
-template <int MODE, class Sync, int NT>
-__device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT,
-                                                   uint32_t *cB, uint16_t *key, uint16_t *hpos, uint16_t *rend,
-                                                   const uint16_t *off, uint8_t *outb, const uint32_t *s_cond,
-                                                   uint32_t *s_lb, uint32_t cells_bytes, int tid) {
-  const int w = p.cols;
-  const bool last_row = t == p.text_rows - 1;
-  constexpr bool row_reset = MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16;
-  const uint32_t term_len = (row_reset ? 4u : 0u) + ((MODE == EM_TRUE_FG && last_row) ? 4u : 0u) + (last_row ? 0u : 1u);
-  const uint32_t body_end = (uint32_t)p.pad_left + cells_bytes;
-  const uint32_t row_len = body_end + term_len;
-  const uint32_t first = MODE == EM_TRUE_FG ? s_cond[3] : 0u;
-  const uint32_t first_x = s_cond[0];
-
-  if (tid < 32) {
-    const int lane = tid;
-    const uint4 *agg = p.agg + (size_t)f * p.text_rows;
-    uint32_t prefix = 0, carry = 0;
-    // the records of up to 96 rows above are requested in one go (three independent loads per lane in flight), then
-    // only the ones that were not published yet are polled again: one L2 round trip in the common case
-    for (int base0 = 0; base0 < t; base0 += 96) {
-      uint4 rec[3];
+// The look-back is done by ONE warp (lane = 0..31 of it); s_lb (2 words of shared memory) carries its result.
+template <int MODE>
+__device__ __forceinline__ void row_lookback(const RenderParams &p, int f, int t, int lane, uint32_t *s_lb) {
+  const uint4 *agg = p.agg + (size_t)f * p.text_rows;
+  uint32_t prefix = 0, carry = 0;
+  // the records of up to 96 rows above are requested in one go (three independent loads per lane in flight), then
+  // only the ones that were not published yet are polled again: one L2 round trip in the common case
+  for (int base0 = 0; base0 < t; base0 += 96) {
+    uint4 rec[3];
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const int j = base0 + 32 * k + lane;
-        rec[k] = j < t ? ld_record(agg + j) : make_uint4(p.epoch, 0u, 0u, 0u);
+    for (int k = 0; k < 3; k++) {
+      const int j = base0 + 32 * k + lane;
+      rec[k] = j < t ? ld_record(agg + j) : make_uint4(p.epoch, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int j = base0 + 32 * k + lane;
+      while (rec[k].x != p.epoch) {
+        __nanosleep(32);
+        rec[k] = ld_record(agg + j);
       }
+    }
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const int j = base0 + 32 * k + lane;
-        while (rec[k].x != p.epoch) {
-          __nanosleep(32);
-          rec[k] = ld_record(agg + j);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < 3; k++) {
       if (base0 + 32 * k >= t) break;
       uint32_t len = rec[k].y, fj = rec[k].z, lj = rec[k].w;
       if (MODE == EM_TRUE_FG) {
@@ -1001,29 +987,23 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
 #pragma unroll
       for (int d = 16; d >= 1; d >>= 1) len += __shfl_xor_sync(0xffffffffu, len, d);
       prefix += len;
-      }
-    }
-    if (lane == 0) {
-      s_lb[0] = prefix;
-      s_lb[1] = carry;
     }
   }
-  Sync::sync();
-  const uint32_t prefix = s_lb[0], carry = s_lb[1];
-  const uint32_t drop =
-      (MODE == EM_TRUE_FG && first && carry && first == carry) ? sgr_rgb_len(fg_print(first, p.fg_over)) : 0u;
-  const uint32_t dst_off = (uint32_t)p.pad_top + prefix;
-  const uint32_t final_len = row_len - drop;
-  uint8_t *frame_out = p.out + (size_t)f * p.out_pitch;
-  uint8_t *dst = frame_out + dst_off;
-  const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u); // stage with the destination's alignment
-  uint8_t *sb = outb + shift;
+  if (lane == 0) {
+    s_lb[0] = prefix;
+    s_lb[1] = carry;
+  }
+}
 
-  // ---- B4: the row's bytes, already in their final form, into shared memory
-  RowCtx ctx{lut, cT, cB, key, hpos, rend, drop ? 1u : 0u, p.fg_over};
-  for (int i = tid; i < p.pad_left; i += NT) sb[i] = ' ';
+// B4: the row's bytes, already in their final form, into shared memory at sb; NTB threads (tid 0..NTB-1) share the cells
+template <int MODE, int NTB>
+__device__ __forceinline__ void row_materialise(const RenderParams &p, const RowCtx &ctx, const uint16_t *off, uint8_t *sb,
+                                                uint32_t body_end, uint32_t drop, uint32_t first_x, bool last_row, int tid) {
+  constexpr bool row_reset = MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16;
+  const int w = p.cols;
+  for (int i = tid; i < p.pad_left; i += NTB) sb[i] = ' ';
   const uint32_t sb32 = (uint32_t)__cvta_generic_to_shared(sb);
-  for (int x = tid; x < w; x += NT) {
+  for (int x = tid; x < w; x += NTB) {
     const uint32_t o = (uint32_t)off[x] - ((MODE == EM_TRUE_FG && drop && (uint32_t)x > first_x) ? drop : 0u);
     SmemSink ss{sb32 + o};
     emit_cell<MODE>(ss, x, ctx);
@@ -1034,6 +1014,84 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
     if (MODE == EM_TRUE_FG && last_row) put_reset(ws); // ansi_rle_finish, ansi.c:303-314
     if (!last_row) ws.put('\n');
   }
+}
+
+template <int MODE, class Sync, int NT>
+__device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f, int t, GlyphLut *lut, uint32_t *cT,
+                                                   uint32_t *cB, uint16_t *key, uint16_t *hpos, uint16_t *rend,
+                                                   const uint16_t *off, uint8_t *outb, const uint32_t *s_cond,
+                                                   uint32_t *s_lb, uint32_t cells_bytes, int tid) {
+  const bool last_row = t == p.text_rows - 1;
+  constexpr bool row_reset = MODE == EM_256_FG || MODE == EM_16_FG || MODE == EM_HB_TRUE || MODE == EM_HB_256 || MODE == EM_HB_16;
+  const uint32_t term_len = (row_reset ? 4u : 0u) + ((MODE == EM_TRUE_FG && last_row) ? 4u : 0u) + (last_row ? 0u : 1u);
+  const uint32_t body_end = (uint32_t)p.pad_left + cells_bytes;
+  const uint32_t row_len = body_end + term_len;
+  const uint32_t first = MODE == EM_TRUE_FG ? s_cond[3] : 0u;
+  const uint32_t first_x = s_cond[0];
+  uint8_t *frame_out = p.out + (size_t)f * p.out_pitch;
+  // Several warps, and nothing in the row's bytes depends on the rows above (every mode but truecolor-fg, whose first
+  // SGR may be dropped): the last warp polls the rows above WHILE the others materialise the row at a fixed phase of
+  // the staging buffer; the copy-out then realigns to the destination (two LDS.128 + funnel shifts per 16 bytes).
+  // One warp (the role-split kernel's emitter) or truecolor-fg: look-back first, then materialise with the
+  // destination's 16-byte phase, so that the copy-out is plain vector moves.
+  constexpr bool PAR = NT >= 64 && MODE != EM_TRUE_FG;
+
+  if (PAR) {
+    RowCtx ctx{lut, cT, cB, key, hpos, rend, 0u, p.fg_over};
+    if (tid >= NT - 32) row_lookback<MODE>(p, f, t, tid - (NT - 32), s_lb);
+    else row_materialise<MODE, (NT >= 64 ? NT - 32 : 32)>(p, ctx, off, outb, body_end, 0u, first_x, last_row, tid);
+    Sync::sync();
+    const uint32_t dst_off = (uint32_t)p.pad_top + s_lb[0];
+    uint8_t *dst = frame_out + dst_off;
+    uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+    if (head > row_len) head = row_len;
+    if ((uint32_t)tid < head) dst[tid] = outb[tid];
+    const uint32_t nvec = (row_len - head) >> 4;
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(outb);
+    const uint32_t q = head >> 2, ksh = (head & 3u) * 8u; // vector i starts at word 4i + q, byte phase head & 3
+    {
+      const uint64_t keep = l2_policy_evict_last();
+      for (uint32_t i = tid; i < nvec; i += NT) {
+        const uint4 A = s4[i], B = s4[i + 1]; // words 4i .. 4i+7 (the staging buffer keeps 16 spare bytes behind the row)
+        uint32_t w0, w1, w2, w3, w4;
+        switch (q) { // uniform across the CTA
+        case 0: w0 = A.x, w1 = A.y, w2 = A.z, w3 = A.w, w4 = B.x; break;
+        case 1: w0 = A.y, w1 = A.z, w2 = A.w, w3 = B.x, w4 = B.y; break;
+        case 2: w0 = A.z, w1 = A.w, w2 = B.x, w3 = B.y, w4 = B.z; break;
+        default: w0 = A.w, w1 = B.x, w2 = B.y, w3 = B.z, w4 = B.w; break;
+        }
+        stg_keep(d4 + i,
+                 make_uint4(__funnelshift_r(w0, w1, ksh), __funnelshift_r(w1, w2, ksh), __funnelshift_r(w2, w3, ksh),
+                            __funnelshift_r(w3, w4, ksh)),
+                 keep);
+      }
+    }
+    const uint32_t done = head + (nvec << 4);
+    if ((uint32_t)tid < row_len - done) dst[done + tid] = outb[done + tid];
+    if (t == 0)
+      for (int i = tid; i < p.pad_top; i += NT) frame_out[i] = '\n';
+    if (last_row && tid == 0) {
+      frame_out[dst_off + row_len] = 0;
+      p.out_len[f] = dst_off + row_len;
+    }
+    Sync::sync(); // the staging buffer and s_lb are reused by the next row
+    return;
+  }
+
+  if (tid < 32) row_lookback<MODE>(p, f, t, tid, s_lb);
+  Sync::sync();
+  const uint32_t prefix = s_lb[0], carry = s_lb[1];
+  const uint32_t drop =
+      (MODE == EM_TRUE_FG && first && carry && first == carry) ? sgr_rgb_len(fg_print(first, p.fg_over)) : 0u;
+  const uint32_t dst_off = (uint32_t)p.pad_top + prefix;
+  const uint32_t final_len = row_len - drop;
+  uint8_t *dst = frame_out + dst_off;
+  const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u); // stage with the destination's alignment
+  uint8_t *sb = outb + shift;
+
+  RowCtx ctx{lut, cT, cB, key, hpos, rend, drop ? 1u : 0u, p.fg_over};
+  row_materialise<MODE, NT>(p, ctx, off, sb, body_end, drop, first_x, last_row, tid);
   Sync::sync();
 
   // ---- copy out: unaligned head bytes, 16-byte body (source and destination share their alignment), tail bytes

@@ -23,7 +23,12 @@ want_grid = ob.ref_create_grid if use_ref else ob.port_create_grid
 want_hdr = ob.ref_packet_header if use_ref else ob.port_packet_header
 PATS = ("noise", "bars", "gradient", "grey", "solid")
 PALS = ("standard", "blocks", "digital", "minimal", "cool")
-counts = {"display": 0, "mixed+packet": 0, "grid": 0, "filter": 0}
+want_dither = ob.ref_print_dither if use_ref else ob.port_print_dither
+want_rainbow = ob.ref_rainbow_replace if use_ref else ob.port_rainbow_replace
+want_conv = ob.ref_convert if use_ref else ob.port_convert
+mk_rain = ob.RefRain if use_ref else ob.PortRain
+counts = {"display": 0, "mixed+packet": 0, "grid": 0, "filter": 0, "dither": 0, "rainbow": 0, "rain": 0, "grid_frame": 0,
+          "box": 0}
 _trace = open(os.environ["FUZZ_TRACE"], "w") if os.environ.get("FUZZ_TRACE") else None
 
 
@@ -54,8 +59,70 @@ def rnd_img(i):
 i = 0
 while time.time() < t_end:
     i += 1
-    fam = i % 8
-    if fam < 5:
+    fam = i % 12
+    if fam == 8:  # the three dithered leaf printers (foreground.c:650-846)
+        w, h = int(rng.integers(1, 120)), int(rng.integers(1, 60))
+        img = ob.gen(PATS[int(rng.integers(0, 5))], w, h, i)
+        pal, variant = PALS[int(rng.integers(0, 5))], int(rng.integers(0, 3))
+        trace("dither", i, w, h, pal, variant)
+        if acb.image_print_16color_dithered(img, pal, None if variant == 2 else variant == 0) != want_dither(img, pal, variant):
+            fail("dither", (w, h, pal, variant))
+        counts["dither"] += 1
+    elif fam == 9:  # rainbow_replace_ansi_colors + digital rain on rendered strings (two frames: the carried state)
+        img = rnd_img(i)
+        cols, rows, level, mode = int(rng.integers(1, 200)), int(rng.integers(1, 60)), int(rng.integers(0, 4)), int(rng.integers(0, 3))
+        pal = PALS[int(rng.integers(0, 5))]
+        s1 = ob.port_convert(img, cols, rows, level, mode, pal)
+        t = float(rng.random() * 20)
+        trace("rainbow", i, img.shape, cols, rows, level, mode, pal, t)
+        if acb.rainbow_replace_ansi_colors(s1 + b"!", t) != want_rainbow(s1 + b"!", t):
+            fail("rainbow", (img.shape, cols, rows, level, mode, pal, t))
+        counts["rainbow"] += 1
+        filt = int(rng.integers(0, 13))
+        gc, gr = max(1, cols + int(rng.integers(-3, 4))), max(1, rows + int(rng.integers(-3, 4)))
+        a, b = acb.DigitalRain(gc, gr, filt), mk_rain(gc, gr, filt)
+        for k in range(2):
+            dt = float(rng.random() * 0.1)
+            if a.apply(s1, dt) != b.apply(s1, dt):
+                fail("rain", (img.shape, cols, rows, level, mode, pal, filt, gc, gr, k))
+        a.close()
+        b.close()
+        counts["rain"] += 1
+    elif fam == 10:  # acb200_grid_frame: resident slots -> cells -> ascii_create_grid (host.c:664-717)
+        n = int(rng.integers(1, 10))
+        srcs = [ob.gen(PATS[int(rng.integers(0, 4))], int(rng.integers(20, 400)), int(rng.integers(16, 300)), k) for k in range(n)]
+        cw, ch = int(rng.integers(4, 100)), int(rng.integers(2, 30))
+        W, H = int(rng.integers(10, 260)), int(rng.integers(3, 80))
+        level, mode = int(rng.integers(0, 4)), int(rng.choice([0, 2]))
+        trace("grid_frame", i, n, cw, ch, W, H, level, mode)
+        for k, s_ in enumerate(srcs):
+            acb.source_update(k, s_)
+        got = acb.grid_frame(list(range(n)), cw, ch, acb.make_caps(level, mode), "standard", W, H)
+        exp = want_grid([want_conv(s_, cw, ch, level, mode) + b"\0" for s_ in srcs], W, H)
+        canvas = W * H + H
+        if got != (exp[0], exp[1]) and not (exp[0] is not None and len(exp[0]) > canvas and got[0] == exp[0][:canvas]):
+            fail("grid_frame", (n, cw, ch, W, H, level, mode, [s_.shape for s_ in srcs]))
+        for k in range(n):
+            acb.source_clear(k)
+        counts["grid_frame"] += 1
+    elif fam == 11:  # box mode: the compiled reference's printer on the box-filtered image; filters on the streaming path
+        W16, H = 16 * int(rng.integers(2, 60)), int(rng.integers(8, 400))
+        img = ob.gen(PATS[int(rng.integers(0, 5))], W16, H, i)
+        c, r = int(rng.integers(1, W16 + 1)), int(rng.integers(1, 60))
+        level, mode, pal = int(rng.integers(0, 4)), int(rng.integers(0, 3)), PALS[int(rng.integers(0, 5))]
+        filt, fx, fy = int(rng.integers(0, 13)), bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        trace("box", i, W16, H, c, r, level, mode, pal, filt, fx, fy)
+        cfg = acb.make_cfg(W16, H, c, r * 2 if mode == 2 else r, level, mode, pal, scale=acb.SCALE_BOX, flip_x=fx, flip_y=fy,
+                           color_filter=filt, filter_time=1.0)
+        got = acb.render_batch_host(cfg, [img])[0]
+        exp = ob.port_display_convert(img, c, r, level, mode, pal, flip_x=fx, flip_y=fy, color_filter=filt, time_s=1.0,
+                                      scale=ob.SCALE_BOX)
+        if got != exp:
+            fail("box", (W16, H, c, r, level, mode, pal, filt, fx, fy))
+        if use_ref and filt == 0 and not fx and not fy and got != ob.ref_box_convert(img, c, r, level, mode, pal):
+            fail("box/ref printer", (W16, H, c, r, level, mode, pal))
+        counts["box"] += 1
+    elif fam < 5:
         img = rnd_img(i)
         kw = dict(cols=int(rng.integers(1, 260)), rows=int(rng.integers(1, 90)), level=int(rng.integers(-1, 4)),
                   mode=int(rng.integers(0, 3)), palette=PALS[int(rng.integers(0, 5))], aspect=bool(rng.integers(0, 2)),
