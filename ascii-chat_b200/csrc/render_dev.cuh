@@ -275,15 +275,19 @@ __device__ __forceinline__ int row_scan(int w, F value_of, G store, int *s_tmp, 
 // ------------------------------------------------------------------ shared-memory layout
 struct Layout {
   uint32_t lut, cT, cB, key, hpos, rend, off, V, outb, total;
+  uint32_t set2; // byte distance from an array of the first per-tile set (cT .. off) to the same array of the second set
 };
 // V (column sums, phase A only) and the row staging buffer (phase B4 only) never live at the same time, so they
 // share one region unless `no_alias` (tuning knob ACB200_TUNE_NOALIAS) asks for separate ones.
+// two_sets: the persistent direct-output kernel prepares tile k+1 before it writes out tile k, so the per-tile arrays
+// (cells, run keys, heads, ends, offsets) exist twice.
 __host__ __device__ inline Layout make_layout(int mode, int sp, int cols, int src_w, uint32_t out_bytes,
-                                              int no_alias = 0) {
+                                              int no_alias = 0, int two_sets = 0) {
   Layout L;
   uint32_t o = 0;
   L.lut = o;
-  o += al16((uint32_t)sizeof(GlyphLut));
+  o += (mode <= EM_TRUE_FG) ? al16((uint32_t)sizeof(GlyphLut)) : 0u; // the half-block grammars print no palette glyph
+  const uint32_t set_begin = o;
   L.cT = o;
   o += al16(4u * cols);
   L.cB = o;
@@ -296,6 +300,8 @@ __host__ __device__ inline Layout make_layout(int mode, int sp, int cols, int sr
   o += al16(2u * cols);
   L.off = o;
   o += al16(4u * cols);
+  L.set2 = o - set_begin;
+  if (two_sets) o += L.set2;
   const uint32_t vbytes = sp == SP_BOX_STREAM ? al16(2u * 3u * src_w) : 0u;
   const uint32_t obytes = out_bytes ? al16(out_bytes) + 16u : 0u; // + room to stage with the destination's phase
   L.V = o;
@@ -1127,7 +1133,7 @@ template <int MODE, int SP, int NT>
 __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) : 1) k_render_rows(const RenderParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_tmp[2 * (NT / 32)];
-  __shared__ uint32_t s_cond[4]; // TRUE_FG: {cond_off, cond_len, last_rgb, first_rgb}
+  __shared__ uint32_t s_cond2[2][4]; // per tile set; TRUE_FG: {cond_off, cond_len, last_rgb, first_rgb}
 
   constexpr bool HB = MODE >= EM_HB_TRUE && MODE <= EM_HB_MONO;
   constexpr bool USES_LUT = MODE <= EM_TRUE_FG;
@@ -1139,14 +1145,8 @@ __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) :
   const unsigned total = (unsigned)p.n_frames * (unsigned)p.text_rows;
 
   const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
-  const Layout L = make_layout(MODE, SP, w, p.src_w, cap, p.tune_flags & 1);
+  const Layout L = make_layout(MODE, SP, w, p.src_w, cap, p.tune_flags & 1, p.direct);
   GlyphLut *lut = reinterpret_cast<GlyphLut *>(smem + L.lut);
-  uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.cT);
-  uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.cB);
-  uint16_t *key = reinterpret_cast<uint16_t *>(smem + L.key);
-  uint16_t *hpos = reinterpret_cast<uint16_t *>(smem + L.hpos);
-  uint16_t *rend = reinterpret_cast<uint16_t *>(smem + L.rend);
-  uint32_t *off = reinterpret_cast<uint32_t *>(smem + L.off);
   uint16_t *V = reinterpret_cast<uint16_t *>(smem + L.V);
   uint8_t *outb = smem + L.outb;
 
@@ -1158,6 +1158,11 @@ __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) :
   init_dec3<NT>(tid);
   __syncthreads();
 
+  // Direct output is software-pipelined by one tile, like the role-split kernel's emitter: iteration k samples,
+  // prepares and PUBLISHES tile k (never waits), then looks back and writes out tile k-1 — whose predecessors have had a
+  // whole tile period to publish, so the look-back finds them ready.  The per-tile arrays exist twice (set = k & 1).
+  int prev_tile = -1, set = 0;
+  uint32_t prev_bytes = 0;
 #pragma unroll 1
   for (;;) {
     // The ticket is drawn when the CTA is ready to start the tile, NOT ahead of time: a tile that is held but not yet
@@ -1168,55 +1173,79 @@ __global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) :
       __syncthreads();
     }
     const unsigned tile = p.direct ? (unsigned)s_tile : blockIdx.x;
-    if (tile >= total) return;
-    const int t = (int)(tile % (unsigned)p.text_rows);
-    const int f = (int)(tile / (unsigned)p.text_rows);
+    const bool have = tile < total;
+    uint32_t bytes = 0;
+    if (have) {
+      const uint32_t so = set ? L.set2 : 0u;
+      uint32_t *cT = reinterpret_cast<uint32_t *>(smem + L.cT + so);
+      uint32_t *cB = reinterpret_cast<uint32_t *>(smem + L.cB + so);
+      uint16_t *key = reinterpret_cast<uint16_t *>(smem + L.key + so);
+      uint16_t *hpos = reinterpret_cast<uint16_t *>(smem + L.hpos + so);
+      uint16_t *rend = reinterpret_cast<uint16_t *>(smem + L.rend + so);
+      uint32_t *off = reinterpret_cast<uint32_t *>(smem + L.off + so);
+      const int t = (int)(tile % (unsigned)p.text_rows);
+      const int f = (int)(tile / (unsigned)p.text_rows);
 
-    // ---- phase A
-    const uint8_t *frame = p.frames + (size_t)f * p.frame_stride;
-    const int yT = HB ? 2 * t : t;
-    const bool hasB = HB && (2 * t + 1 < p.rows_px);
-    if (SP == SP_NN) {
-      cells_nn<NT>(p, frame, yT, cT, hasB ? cB : nullptr);
-    } else if (SP == SP_BOX_GENERIC) {
-      cells_box_generic<NT>(p, frame, yT, cT);
-      if (hasB) cells_box_generic<NT>(p, frame, yT + 1, cB);
-    } else {
+      // ---- phase A
+      const uint8_t *frame = p.frames + (size_t)f * p.frame_stride;
+      const int yT = HB ? 2 * t : t;
+      const bool hasB = HB && (2 * t + 1 < p.rows_px);
+      if (SP == SP_NN) {
+        cells_nn<NT>(p, frame, yT, cT, hasB ? cB : nullptr);
+      } else if (SP == SP_BOX_GENERIC) {
+        cells_box_generic<NT>(p, frame, yT, cT);
+        if (hasB) cells_box_generic<NT>(p, frame, yT + 1, cB);
+      } else {
 #pragma unroll 1
-      for (int hrow = 0; hrow < (hasB ? 2 : 1); hrow++) cells_box_stream<NT>(p, frame, yT + hrow, hrow ? cB : cT, V);
-    }
-    __syncthreads();
-    if (HB && !hasB) { // odd pixel height: bottom := top (halfblock.c:73,82-88)
-      for (int x = tid; x < w; x += NT) cB[x] = cT[x];
+        for (int hrow = 0; hrow < (hasB ? 2 : 1); hrow++) cells_box_stream<NT>(p, frame, yT + hrow, hrow ? cB : cT, V);
+      }
       __syncthreads();
-    }
-    if (p.cells_out) {
-      uint8_t *co = p.cells_out + ((size_t)f * p.rows_px + yT) * (size_t)w * 3u;
-      for (int x = tid; x < w; x += NT) {
-        uint32_t c = cT[x];
-        co[3 * x] = (uint8_t)(c >> 16);
-        co[3 * x + 1] = (uint8_t)(c >> 8);
-        co[3 * x + 2] = (uint8_t)c;
-        if (hasB) {
-          uint32_t d = cB[x];
-          uint8_t *cb = co + (size_t)w * 3u;
-          cb[3 * x] = (uint8_t)(d >> 16);
-          cb[3 * x + 1] = (uint8_t)(d >> 8);
-          cb[3 * x + 2] = (uint8_t)d;
+      if (HB && !hasB) { // odd pixel height: bottom := top (halfblock.c:73,82-88)
+        for (int x = tid; x < w; x += NT) cB[x] = cT[x];
+        __syncthreads();
+      }
+      if (p.cells_out) {
+        uint8_t *co = p.cells_out + ((size_t)f * p.rows_px + yT) * (size_t)w * 3u;
+        for (int x = tid; x < w; x += NT) {
+          uint32_t c = cT[x];
+          co[3 * x] = (uint8_t)(c >> 16);
+          co[3 * x + 1] = (uint8_t)(c >> 8);
+          co[3 * x + 2] = (uint8_t)c;
+          if (hasB) {
+            uint32_t d = cB[x];
+            uint8_t *cb = co + (size_t)w * 3u;
+            cb[3 * x] = (uint8_t)(d >> 16);
+            cb[3 * x + 1] = (uint8_t)(d >> 8);
+            cb[3 * x + 2] = (uint8_t)d;
+          }
         }
       }
-    }
-    if (p.rows == nullptr) return; // resize-only invocation (never direct)
+      if (p.rows == nullptr) return; // resize-only invocation (never direct)
 
-    if (!p.direct) {
-      emit_row<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond, tid);
+      if (!p.direct) {
+        emit_row<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off, outb, s_tmp, s_cond2[0], tid);
+        return;
+      }
+      bytes = emit_direct_prepare<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend,
+                                                     reinterpret_cast<uint16_t *>(off), s_tmp, s_cond2[set], tid);
+    } else if (!p.direct) {
       return;
     }
-    uint16_t *off16 = reinterpret_cast<uint16_t *>(off);
-    const uint32_t bytes =
-        emit_direct_prepare<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off16, s_tmp, s_cond, tid);
-    emit_direct_finish<MODE, SyncAll, NT>(p, f, t, lut, cT, cB, key, hpos, rend, off16, outb, s_cond, s_lb, bytes, tid);
-    // emit_direct_finish ends on a barrier: cT/cB, the staging buffer and s_tile are free again
+    if (prev_tile >= 0) {
+      const uint32_t so = set ? 0u : L.set2; // the other set
+      const int t = (int)((unsigned)prev_tile % (unsigned)p.text_rows);
+      const int f = (int)((unsigned)prev_tile / (unsigned)p.text_rows);
+      emit_direct_finish<MODE, SyncAll, NT>(
+          p, f, t, lut, reinterpret_cast<uint32_t *>(smem + L.cT + so), reinterpret_cast<uint32_t *>(smem + L.cB + so),
+          reinterpret_cast<uint16_t *>(smem + L.key + so), reinterpret_cast<uint16_t *>(smem + L.hpos + so),
+          reinterpret_cast<uint16_t *>(smem + L.rend + so), reinterpret_cast<const uint16_t *>(smem + L.off + so), outb,
+          s_cond2[set ^ 1], s_lb, prev_bytes, tid);
+      // emit_direct_finish ends on a barrier: that set, the staging buffer and s_tile are free again
+    }
+    if (!have) return;
+    prev_tile = (int)tile;
+    prev_bytes = bytes;
+    set ^= 1;
   }
 }
 
@@ -1688,7 +1717,7 @@ __host__ inline int pick_nt(int cols) { return cols <= 128 ? 128 : 256; }
 template <int MODE, int SP, int NT>
 static cudaError_t launch_rows_t(const RenderParams &p, cudaStream_t st, unsigned *grid_out) {
   const uint32_t cap = p.use_smem_out ? p.row_pitch : 0u;
-  const Layout L = make_layout(MODE, SP, p.cols, p.src_w, cap, p.tune_flags & 1);
+  const Layout L = make_layout(MODE, SP, p.cols, p.src_w, cap, p.tune_flags & 1, p.direct);
   if (L.total > kMaxDynSmem) return cudaErrorInvalidConfiguration;
   static std::atomic<uint64_t> configured{0};
   int dev = 0;

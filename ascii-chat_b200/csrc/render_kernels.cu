@@ -367,7 +367,7 @@ int ws_ring_depth(int mode, int cols, int src_w, uint32_t row_pitch) {
 }
 
 size_t rows_smem_total(int mode, int sp, int cols, int src_w, uint32_t out_bytes) {
-  return make_layout(mode, sp, cols, src_w, out_bytes, 1).total; // worst case (no aliasing)
+  return make_layout(mode, sp, cols, src_w, out_bytes, 1, 1).total; // worst case (no aliasing, both tile sets)
 }
 
 cudaError_t launch_stitch(const StitchParams &p, int n_frames, cudaStream_t st) {
