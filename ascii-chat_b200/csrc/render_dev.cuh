@@ -1130,7 +1130,7 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
 // per text row, and the next tile's ticket is requested while the current one is being emitted.  Whoever holds tile X
 // knows every tile < X is held by a running CTA, so the look-back spin cannot deadlock.
 template <int MODE, int SP, int NT>
-__global__ void __launch_bounds__(NT, SP == SP_NN ? (NT <= 256 ? 2048 / NT : 5) : 1) k_render_rows(const RenderParams p) {
+__global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) : 1) k_render_rows(const RenderParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_tmp[2 * (NT / 32)];
   __shared__ uint32_t s_cond2[2][4]; // per tile set; TRUE_FG: {cond_off, cond_len, last_rgb, first_rgb}
@@ -1741,10 +1741,8 @@ static cudaError_t launch_rows_t(const RenderParams &p, cudaStream_t st, unsigne
   return cudaGetLastError();
 }
 template <int MODE, int SP> static cudaError_t launch_rows_nt(const RenderParams &p, cudaStream_t st, unsigned *grid_out) {
-  // Nearest neighbour is instruction-bound once the look-back is off the critical path (profiles/r02i_ncu_nn_flat:
-  // 76 % issue utilisation): a 320-column row on 256 threads runs every per-cell loop and every scan pass twice, the
-  // second time with a quarter of the lanes; 384 threads do it in one pass (12 warp-passes instead of 16).
-  if (SP == SP_NN && p.cols > 256 && p.cols <= 384) return launch_rows_t<MODE, SP, SP == SP_NN ? 384 : 256>(p, st, grid_out);
+  // (384 threads for 257..384 columns — one pass over the row instead of two — measured slower: five CTAs per SM keep
+  // fewer tiles in flight than eight, 0.248 vs 0.228 ms on flat C3 frames, profiles/r02j_configs.txt)
   switch (pick_nt(p.cols)) {
   case 128: return launch_rows_t<MODE, SP, 128>(p, st, grid_out);
   default: return launch_rows_t<MODE, SP, 256>(p, st, grid_out);
