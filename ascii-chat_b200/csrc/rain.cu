@@ -31,6 +31,7 @@ namespace {
 struct RainImpl {
   digital_rain_t pub; // first member: the pointer handed to the caller
   int device = 0;     // CUDA ordinal previous_brightness lives on
+  float *alt = nullptr; // the other state buffer: a frame reads pub.previous_brightness and writes this one, then they swap
 };
 
 constexpr int RN_NT = 256, RN_PER = 16, RN_CHUNK = RN_NT * RN_PER;
@@ -51,7 +52,9 @@ struct RainParams {
   uint32_t nlines;
   const float *target;   // [rows_tab][cols] un-filtered brightness of the frame
   int cols, rows, rows_tab;
-  float *prev;           // [rows][cols] filtered brightness kept between frames
+  const float *prev;     // [rows][cols] filtered brightness of the frame before (read only)
+  float *prev_new;       // same grid, this frame's values (the two buffers swap roles every frame)
+  uint32_t *lane_off;    // [nlines][32] output offset of every lane's segment inside its line
   float decay;
   int first_frame;
   uint32_t rain_rgb;     // 0x00RRGGBB
@@ -140,43 +143,37 @@ __device__ __forceinline__ void put_scaled(O &o, bool fg, int r, int g, int b, f
   o.put('m');
 }
 
-// The reference's loop (digital_rain.c:405-502) over the byte range [i0, i1) of the string, cursor starting at
-// (col 0, row0).  Returns the number of output bytes; *complex is raised when an escape sequence runs past i1.
-// The walker reads its line out of a shared-memory copy (stage[0 .. staged) = bytes i0 ..): a serial byte-at-a-time loop
-// is bound by load latency, and shared memory answers ten times faster than L2.
-// So are the three float rows a line's visits read (un-filtered brightness of its row and of the row below, the state of
-// its row): a visit is three dependent loads, ~1.5 us from L2 and there are ~900 per line.
-template <class O> __device__ void rain_walk(const RainParams &p, uint32_t i0, uint32_t i1, int row0, O &o, bool write_state,
-                                             uint32_t *complex, const uint8_t *stage, uint32_t staged, const float *frows) {
-  const uint8_t *s = p.in;
-  const uint32_t n = p.n;
-  auto at = [&](uint32_t i) -> uint32_t { return (i - i0) < staged ? stage[i - i0] : (i < n ? s[i] : 0u); };
-  int col = 0, row = row0;
-  int run_col = -1, run_row = -1; // the cell the running filtered value belongs to
-  float run_val = 0.0f;
-  auto target = [&](int c, int r) -> float { // get_rain_brightness: 0 beyond the last column (:71-73)
-    if (c >= p.cols || r >= p.rows_tab) return 0.0f;
-    if (c < RN_SCOLS && (unsigned)(r - row0) < 2u) return frows[(r - row0) * RN_SCOLS + c];
-    return p.target[(size_t)r * p.cols + c];
-  };
-  auto visit = [&](bool *cursor) -> float { // :413-430
-    float b = target(col, row);
-    *cursor = b > target(col, row + 1);
-    if (row < p.rows && col < p.cols) {
-      const size_t idx = (size_t)row * p.cols + col;
-      if (!p.first_frame) {
-        const float prev = (run_col == col && run_row == row) ? run_val
-                           : (row == row0 && col < RN_SCOLS) ? frows[2 * RN_SCOLS + col]
-                                                             : p.prev[idx];
-        b = __fadd_rn(prev, __fmul_rn(__fsub_rn(b, prev), p.decay));
-      }
-      run_col = col, run_row = row, run_val = b;
-      if (write_state) p.prev[idx] = b;
-    }
-    return b;
-  };
-  uint32_t i = i0;
-  while (i < i1) {
+// ---- tokens --------------------------------------------------------------------------------------------------
+// The reference's loop (digital_rain.c:405-502) is a tokeniser with three byte-level states — N (normal), E (right after
+// an ESC), C (inside ESC [ ... up to a byte in @..~) — and four kinds of token: a truecolor SGR (re-emitted scaled: a
+// VISIT of the cursor's cell), any other escape sequence (copied), '\n' (row++, col = 0), a visible UTF-8 character
+// (a visit, the rain colour in front, col++).  Whether an ESC [ sequence is a colour sequence is decided where it
+// starts; both kinds end at the first byte in @..~ (a colour sequence holds only digits and ';' before its 'm'), so
+// the state machine does not depend on the kind — which is what lets a warp cut a line into 32 segments: every lane
+// computes how its segment maps each entry state to an exit state, the maps are chained, and every lane then walks the
+// tokens that START in its segment from the right state.
+enum { RS_N = 0, RS_E = 1, RS_C = 2 };
+__device__ __forceinline__ int rain_step(int st, uint32_t c) {
+  if (st == RS_C) return (c >= '@' && c <= '~') ? RS_N : RS_C;
+  if (c == 0x1b) return RS_E;
+  return (st == RS_E && c == '[') ? RS_C : RS_N;
+}
+
+// Walks the tokens that start in [from, to) (a token may run past `to`; the owner of its first byte handles all of it).
+// entry = state in front of byte `from`.  Sink callbacks: colour(fg, r, g, b), raw(i, j), newline(), glyph(i, len).
+template <class At, class Sink>
+__device__ __forceinline__ void rain_tokens(const At &at, uint32_t n, uint32_t from, uint32_t to, uint32_t line_end, int entry,
+                                            Sink &sk, uint32_t *complex) {
+  uint32_t i = from;
+  if (entry == RS_E && i < to && at(i) == '[') { // the CSI was opened by the ESC in front of this segment
+    entry = RS_C;
+    i++;
+  }
+  if (entry == RS_C) { // inside somebody else's sequence: it ends behind the first byte in @..~
+    while (i < n && !(at(i) >= '@' && at(i) <= '~')) i++;
+    if (i < n) i++;
+  }
+  while (i < to) {
     const uint32_t c = at(i);
     if (c == 0x1b) {
       // parse_ansi_color (:240-301): ESC [ (38|48) ;2; R ; G ; B m
@@ -199,9 +196,7 @@ template <class O> __device__ void rain_walk(const RainParams &p, uint32_t i0, u
         }
       }
       if (colour) {
-        bool cursor;
-        const float b = visit(&cursor);
-        put_scaled(o, fg, rgb[0], rgb[1], rgb[2], b, cursor);
+        sk.colour(fg, rgb[0], rgb[1], rgb[2]);
         i = j;
       } else { // skip_ansi_sequence (:306-324): copied as it is
         j = i + 1;
@@ -210,66 +205,215 @@ template <class O> __device__ void rain_walk(const RainParams &p, uint32_t i0, u
           while (j < n && !(at(j) >= '@' && at(j) <= '~')) j++;
           if (j < n) j++;
         }
-        if (j > i1) *complex = 1u; // the sequence swallowed this line's newline
-        for (uint32_t k = i; k < j; k++) o.put((uint8_t)at(k));
+        if (j > line_end) *complex = 1u; // the sequence swallowed this line's newline
+        sk.raw(i, j);
         i = j;
       }
     } else if (c == '\n') {
-      o.put('\n');
-      i++, row++, col = 0;
-    } else { // a visible character: the rain colour in front of it (:466-501)
-      bool cursor;
-      const float b = visit(&cursor);
-      put_scaled(o, true, (int)((p.rain_rgb >> 16) & 255u), (int)((p.rain_rgb >> 8) & 255u), (int)(p.rain_rgb & 255u), b, cursor);
-      // utf8_decode's length rule (lib/util/utf8.c:18-44): an invalid sequence counts as one byte
+      sk.newline();
+      i++;
+    } else { // a visible character; utf8_decode's length rule (lib/util/utf8.c:18-44): an invalid sequence is one byte
       int len = c < 0x80u ? 1 : (c & 0xE0u) == 0xC0u ? 2 : (c & 0xF0u) == 0xE0u ? 3 : (c & 0xF8u) == 0xF0u ? 4 : 1;
       for (int k = 1; k < len; k++)
         if ((at(i + k) & 0xC0u) != 0x80u) {
           len = 1;
           break;
         }
-      for (int k = 0; k < len; k++) o.put((uint8_t)at(i + k));
-      i += len, col++;
+      sk.glyph(i, len);
+      i += len;
     }
   }
 }
 
-template <bool WRITE> __global__ void __launch_bounds__(32) k_rain_walk(const RainParams p) {
-  extern __shared__ __align__(16) uint8_t s_stage[]; // RN_LPB x RN_LINE_SMEM
-  // all 32 threads copy the block's lines (plus a few bytes of look-ahead) and their float rows into shared memory,
-  // then RN_LPB of them walk
-  for (int l = 0; l < RN_LPB; l++) {
-    const uint32_t line = blockIdx.x * RN_LPB + l;
-    if (line >= p.nlines) break;
-    uint8_t *base = s_stage + (size_t)l * RN_LINE_SMEM;
-    const uint32_t i0 = p.line_start[line], i1 = line + 1 < p.nlines ? p.line_start[line + 1] : p.n;
-    uint32_t len = min(i1 - i0 + 32u, RN_STAGE);
-    if (i0 + len > p.n) len = p.n - i0;
-    for (uint32_t k = threadIdx.x; k < len; k += 32) base[k] = p.in[i0 + k];
-    float *fr = reinterpret_cast<float *>(base + RN_STAGE);
-    const int nc = min(p.cols, RN_SCOLS);
-    for (int c = threadIdx.x; c < nc; c += 32) {
-      fr[c] = (int)line < p.rows_tab ? p.target[(size_t)line * p.cols + c] : 0.0f;
-      fr[RN_SCOLS + c] = (int)line + 1 < p.rows_tab ? p.target[(size_t)(line + 1) * p.cols + c] : 0.0f;
-      fr[2 * RN_SCOLS + c] = (int)line < p.rows ? p.prev[(size_t)line * p.cols + c] : 0.0f;
-    }
+// structure only: how many characters start here, how many colour visits before the first / after the last of them
+struct StructSink {
+  int nchar = 0, v_head = 0, v_tail = 0;
+  __device__ __forceinline__ void colour(bool, int, int, int) {
+    if (nchar == 0) v_head++;
+    v_tail++;
   }
-  __syncthreads();
-  const uint32_t line = blockIdx.x * RN_LPB + threadIdx.x;
-  if (threadIdx.x >= RN_LPB || line >= p.nlines) return;
+  __device__ __forceinline__ void raw(uint32_t, uint32_t) {}
+  __device__ __forceinline__ void newline() {}
+  __device__ __forceinline__ void glyph(uint32_t, int) {
+    nchar++;
+    v_tail = 0;
+  }
+};
+
+// bytes (counted or written) + the brightness filter.  State is READ from p.prev (the frame before) and WRITTEN to
+// p.prev_new, so the order in which lanes and lines run cannot matter; within a cell the visits chain through run_val.
+template <class At, class O> struct EmitSink {
+  const RainParams &p;
+  const At &at;
+  O &o;
+  const float *frows; // staged rows (row0: brightness, row0 + 1: brightness below, state of row0), or nullptr
+  int row0, col, row;
+  bool write_state;   // the write pass
+  bool every_visit;   // serial walk: every visit stores; warp walk: only a character's visit does (the last of its cell)
+  int run_col = -1, run_row = -1;
+  float run_val = 0.0f;
+  int tail_visits = 0; // colour visits since the last character (their cell's final value is run_val)
+
+  __device__ __forceinline__ float target(int c, int r) const { // get_rain_brightness: 0 beyond the last column (:71-73)
+    if (c >= p.cols || r >= p.rows_tab) return 0.0f;
+    if (frows && c < RN_SCOLS && (unsigned)(r - row0) < 2u) return frows[(r - row0) * RN_SCOLS + c];
+    return p.target[(size_t)r * p.cols + c];
+  }
+  __device__ __forceinline__ float old_state(int c, int r) const {
+    if (frows && r == row0 && c < RN_SCOLS) return frows[2 * RN_SCOLS + c];
+    return p.prev[(size_t)r * p.cols + c];
+  }
+  // the cell already had `ord` visits in front of this walker's first token: replay the filter that often
+  __device__ __forceinline__ void catch_up(int ord) {
+    if (ord <= 0 || p.first_frame || !(row < p.rows && col < p.cols)) return;
+    const float tg = target(col, row);
+    float v = old_state(col, row);
+    for (int k = 0; k < ord; k++) v = __fadd_rn(v, __fmul_rn(__fsub_rn(tg, v), p.decay));
+    run_col = col, run_row = row, run_val = v;
+  }
+  __device__ __forceinline__ float visit(bool *cursor, bool is_char) { // :413-430
+    float b = target(col, row);
+    *cursor = b > target(col, row + 1);
+    if (row < p.rows && col < p.cols) {
+      if (!p.first_frame) {
+        const float prev = (run_col == col && run_row == row) ? run_val : old_state(col, row);
+        b = __fadd_rn(prev, __fmul_rn(__fsub_rn(b, prev), p.decay));
+      }
+      run_col = col, run_row = row, run_val = b;
+      if (write_state && (every_visit || is_char)) p.prev_new[(size_t)row * p.cols + col] = b;
+    }
+    return b;
+  }
+  __device__ __forceinline__ void colour(bool fg, int r, int g, int b) {
+    bool cursor;
+    const float br = visit(&cursor, false);
+    put_scaled(o, fg, r, g, b, br, cursor);
+    tail_visits++;
+  }
+  __device__ __forceinline__ void raw(uint32_t i, uint32_t j) {
+    for (uint32_t k = i; k < j; k++) o.put((uint8_t)at(k));
+  }
+  __device__ __forceinline__ void newline() {
+    o.put('\n');
+    if (!every_visit) flush_tail(); // colour visits between the last character and the newline: their cell ends here
+    row++, col = 0, tail_visits = 0;
+  }
+  __device__ __forceinline__ void glyph(uint32_t i, int len) { // the rain colour in front of the character (:466-501)
+    bool cursor;
+    const float br = visit(&cursor, true);
+    put_scaled(o, true, (int)((p.rain_rgb >> 16) & 255u), (int)((p.rain_rgb >> 8) & 255u), (int)(p.rain_rgb & 255u), br, cursor);
+    for (int k = 0; k < len; k++) o.put((uint8_t)at(i + k));
+    col++, tail_visits = 0;
+  }
+  // warp walk, end of the line's last visiting lane: colour visits behind the last character belong to a cell that
+  // never gets one — their final value is the cell's new state
+  __device__ __forceinline__ void flush_tail() {
+    if (write_state && tail_visits > 0 && run_col == col && run_row == row && row < p.rows && col < p.cols)
+      p.prev_new[(size_t)row * p.cols + col] = run_val;
+  }
+};
+
+// One thread walks the range [i0, i1) serially (the fallback for strings in which an escape sequence swallows a
+// newline: the whole string as one range).
+template <bool WRITE> __global__ void __launch_bounds__(32) k_rain_serial(const RainParams p) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const uint8_t *s = p.in;
+  const uint32_t n = p.n;
+  auto at = [&](uint32_t i) -> uint32_t { return i < n ? s[i] : 0u; };
+  uint32_t complex = 0;
+  if (WRITE) {
+    ByteOut o{p.out};
+    EmitSink<decltype(at), ByteOut> sk{p, at, o, nullptr, 0, 0, 0, true, true};
+    rain_tokens(at, n, 0u, n, n, RS_N, sk, &complex);
+  } else {
+    CountOut o;
+    EmitSink<decltype(at), CountOut> sk{p, at, o, nullptr, 0, 0, 0, false, true};
+    rain_tokens(at, n, 0u, n, n, RS_N, sk, &complex);
+    p.line_len[0] = o.n;
+  }
+}
+
+// One WARP per line.  The line (and the three float rows its visits read) is staged in shared memory; lane l owns the
+// tokens that start in its 1/32 of the line.
+template <bool WRITE> __global__ void __launch_bounds__(32 * RN_LPB) k_rain_warp(const RainParams p) {
+  extern __shared__ __align__(16) uint8_t s_stage[]; // RN_LPB x RN_LINE_SMEM
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t line = blockIdx.x * RN_LPB + wib;
+  if (line >= p.nlines) return;
+  uint8_t *stage = s_stage + (size_t)wib * RN_LINE_SMEM;
+  float *fr = reinterpret_cast<float *>(stage + RN_STAGE);
   const uint32_t i0 = p.line_start[line], i1 = line + 1 < p.nlines ? p.line_start[line + 1] : p.n;
   uint32_t staged = min(i1 - i0 + 32u, RN_STAGE);
   if (i0 + staged > p.n) staged = p.n - i0;
-  const uint8_t *stage = s_stage + (size_t)threadIdx.x * RN_LINE_SMEM;
-  const float *frows = reinterpret_cast<const float *>(stage + RN_STAGE);
+  for (uint32_t k = lane; k < staged; k += 32) stage[k] = p.in[i0 + k];
+  const int nc = min(p.cols, RN_SCOLS);
+  for (int c = lane; c < nc; c += 32) {
+    fr[c] = (int)line < p.rows_tab ? p.target[(size_t)line * p.cols + c] : 0.0f;
+    fr[RN_SCOLS + c] = (int)line + 1 < p.rows_tab ? p.target[(size_t)(line + 1) * p.cols + c] : 0.0f;
+    fr[2 * RN_SCOLS + c] = (int)line < p.rows ? p.prev[(size_t)line * p.cols + c] : 0.0f;
+  }
+  __syncwarp();
+  const uint8_t *s = p.in;
+  const uint32_t n = p.n;
+  auto at = [&](uint32_t i) -> uint32_t { return (i - i0) < staged ? stage[i - i0] : (i < n ? s[i] : 0u); };
+
+  // segments: nominal start i0 + l * S, moved forward off UTF-8 continuation bytes (they belong to the lane in front,
+  // whether a lead byte consumes them or they stand alone)
+  const uint32_t len = i1 - i0, S = (len + 31u) / 32u;
+  uint32_t from = min(i0 + (uint32_t)lane * S, i1);
+  if (lane > 0)
+    while (from < i1 && (at(from) & 0xC0u) == 0x80u) from++;
+  uint32_t to = __shfl_down_sync(0xffffffffu, from, 1);
+  if (lane == 31) to = i1;
+  // state maps of the segments, chained from N at the start of the line
+  int ex[3] = {RS_N, RS_E, RS_C};
+  for (uint32_t i = from; i < to; i++) {
+    const uint32_t c = at(i);
+#pragma unroll
+    for (int e = 0; e < 3; e++) ex[e] = rain_step(ex[e], c);
+  }
+  const int map = ex[0] | (ex[1] << 2) | (ex[2] << 4);
+  int entry = RS_N, cur = RS_N;
+  for (int l = 0; l < 32; l++) {
+    const int m = __shfl_sync(0xffffffffu, map, l);
+    if (l == lane) entry = cur;
+    cur = (m >> (2 * cur)) & 3;
+  }
+  // structure: characters and visits per segment -> every lane's column and the visits its first cell already had
   uint32_t complex = 0;
+  StructSink st;
+  rain_tokens(at, n, from, to, i1, entry, st, &complex);
+  const int visits = st.nchar ? st.v_tail : st.v_head; // colour visits pending behind this segment's last character
+  int col0 = 0, ord0 = 0, ccol = 0, cord = 0;
+  bool later = false; // does any later lane visit anything
+  for (int l = 0; l < 32; l++) {
+    const int nch = __shfl_sync(0xffffffffu, st.nchar, l), vh = __shfl_sync(0xffffffffu, st.v_head, l),
+              vt = __shfl_sync(0xffffffffu, visits, l);
+    if (l == lane) col0 = ccol, ord0 = cord;
+    if (l > lane && (nch > 0 || vh > 0)) later = true;
+    ccol += nch;
+    cord = nch ? vt : cord + vh;
+  }
   if (WRITE) {
-    ByteOut o{p.out + p.line_off[line]};
-    rain_walk(p, i0, i1, (int)line, o, true, &complex, stage, staged, frows);
+    ByteOut o{p.out + p.line_off[line] + p.lane_off[(size_t)line * 32 + lane]};
+    EmitSink<decltype(at), ByteOut> sk{p, at, o, fr, (int)line, col0, (int)line, true, false};
+    sk.catch_up(ord0);
+    sk.tail_visits = ord0; // visits of the first cell made by the lanes in front count as pending, too
+    rain_tokens(at, n, from, to, i1, entry, sk, &complex);
+    if (!later) sk.flush_tail();
   } else {
     CountOut o;
-    rain_walk(p, i0, i1, (int)line, o, false, &complex, stage, staged, frows);
-    p.line_len[line] = o.n;
+    EmitSink<decltype(at), CountOut> sk{p, at, o, fr, (int)line, col0, (int)line, false, false};
+    sk.catch_up(ord0);
+    rain_tokens(at, n, from, to, i1, entry, sk, &complex);
+    uint32_t inc = o.n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += v;
+    }
+    p.lane_off[(size_t)line * 32 + lane] = inc - o.n;
+    if (lane == 31) p.line_len[line] = inc;
     if (complex) atomicOr(&p.result[1], 1u);
   }
 }
@@ -336,10 +480,12 @@ digital_rain_t *digital_rain_init(int num_columns, int num_rows) {
   r->columns = (digital_rain_column_t *)calloc((size_t)num_columns, sizeof(digital_rain_column_t));
   const size_t grid = (size_t)num_columns * (size_t)num_rows;
   if (!r->columns || cudaMalloc((void **)&r->previous_brightness, grid * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void **)&im->alt, grid * sizeof(float)) != cudaSuccess ||
       cudaMemset(r->previous_brightness, 0, grid * sizeof(float)) != cudaSuccess) {
     set_error(E_MEMORY, "digital_rain_init: cannot allocate a %dx%d grid", num_columns, num_rows);
     free(r->columns);
     if (r->previous_brightness) cudaFree(r->previous_brightness);
+    if (im->alt) cudaFree(im->alt);
     delete im;
     return nullptr;
   }
@@ -365,6 +511,7 @@ void digital_rain_destroy(digital_rain_t *rain) {
   RainImpl *im = reinterpret_cast<RainImpl *>(rain);
   free(rain->columns);
   if (rain->previous_brightness) cudaFree(rain->previous_brightness);
+  if (im->alt) cudaFree(im->alt);
   delete im;
 }
 
@@ -442,7 +589,7 @@ char *digital_rain_apply(digital_rain_t *rain, const char *frame, float delta_ti
   const size_t in_bytes = ((n + 15) & ~(size_t)15) + tab_bytes;
   // worst case: every byte a visible character -> 19 bytes of code + the byte itself
   const size_t out_cap = n * 20 + 64;
-  const size_t words = (size_t)chunks + 3 * nlines + 16;
+  const size_t words = (size_t)chunks + 3 * nlines + 32 * nlines + 16;
   if (sync_foreign(cx, cx->stream) != E_OK) return nullptr;
   if (!grow_pinned(&cx->h_in, &cx->h_in_cap, in_bytes) || !grow_device(&cx->d_in, &cx->d_in_cap, in_bytes) ||
       !grow_device(&cx->d_out, &cx->d_out_cap, out_cap) || !grow_device((uint8_t **)&cx->d_len, &cx->d_len_cap, words * 4) ||
@@ -463,12 +610,14 @@ char *digital_rain_apply(digital_rain_t *rain, const char *frame, float delta_ti
   p.line_start = p.chunk_nl + chunks;
   p.line_len = p.line_start + nlines;
   p.line_off = p.line_len + nlines;
+  p.lane_off = p.line_off + nlines;
   p.nlines = (uint32_t)nlines;
   p.target = reinterpret_cast<const float *>(cx->d_in + ((n + 15) & ~(size_t)15));
   p.cols = rain->num_columns;
   p.rows = rain->num_rows;
   p.rows_tab = (int)rows_tab;
   p.prev = rain->previous_brightness;
+  p.prev_new = im->alt;
   p.decay = rain->brightness_decay;
   p.first_frame = rain->first_frame ? 1 : 0;
   p.rain_rgb = ((uint32_t)rain->color_r << 16) | ((uint32_t)rain->color_g << 8) | rain->color_b;
@@ -488,24 +637,25 @@ char *digital_rain_apply(digital_rain_t *rain, const char *frame, float delta_ti
   {
     static std::atomic<uint64_t> configured{0};
     if (!((configured.load(std::memory_order_acquire) >> cx->device) & 1ull)) {
-      if (cudaFuncSetAttribute(k_rain_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem) != cudaSuccess ||
-          cudaFuncSetAttribute(k_rain_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem) != cudaSuccess)
+      if (cudaFuncSetAttribute(k_rain_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem) != cudaSuccess ||
+          cudaFuncSetAttribute(k_rain_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem) != cudaSuccess)
         return fail("shared-memory opt-in");
       configured.fetch_or(1ull << cx->device, std::memory_order_release);
     }
   }
-  k_rain_walk<false><<<walk_grid, 32, walk_smem, st>>>(p);
+  k_rain_warp<false><<<walk_grid, 32 * RN_LPB, walk_smem, st>>>(p);
   k_rain_scan<<<1, RN_NT, 0, st>>>(p);
   count_launch(4);
   if (cudaGetLastError() != cudaSuccess ||
       cudaMemcpyAsync(cx->h_len, p.result, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || wait_stream(cx) != E_OK)
     return fail("count pass");
-  if (cx->h_len[1]) { // an escape sequence swallowed a newline: one range, one thread, the reference's loop as it is
+  const bool serial = cx->h_len[1] != 0;
+  if (serial) { // an escape sequence swallowed a newline: one range, one thread, the reference's loop as it is
     p.nlines = 1;
     if (cudaMemsetAsync(p.line_start, 0, sizeof(uint32_t), st) != cudaSuccess ||
         cudaMemsetAsync(p.result, 0, 16 * sizeof(uint32_t), st) != cudaSuccess)
       return fail("fallback setup");
-    k_rain_walk<false><<<1, 32, walk_smem, st>>>(p);
+    k_rain_serial<false><<<1, 32, 0, st>>>(p);
     k_rain_scan<<<1, RN_NT, 0, st>>>(p);
     count_launch(2);
     if (cudaGetLastError() != cudaSuccess ||
@@ -517,11 +667,21 @@ char *digital_rain_apply(digital_rain_t *rain, const char *frame, float delta_ti
     if (total + 1 > out_cap) set_error(E_INVALID_STATE, "digital_rain_apply: output larger than its bound");
     return nullptr;
   }
-  k_rain_walk<true><<<(unsigned)((p.nlines + RN_LPB - 1) / RN_LPB), 32, walk_smem, st>>>(p);
+  // cells this frame does not visit keep their value: the new state starts as a copy of the old one
+  if (cudaMemcpyAsync(im->alt, rain->previous_brightness, (size_t)rain->num_columns * rain->num_rows * sizeof(float),
+                      cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return fail("state copy");
+  if (serial) k_rain_serial<true><<<1, 32, 0, st>>>(p);
+  else k_rain_warp<true><<<walk_grid, 32 * RN_LPB, walk_smem, st>>>(p);
   count_launch();
   if (cudaGetLastError() != cudaSuccess ||
       cudaMemcpyAsync(cx->h_out, cx->d_out, total, cudaMemcpyDeviceToHost, st) != cudaSuccess || wait_stream(cx) != E_OK)
     return fail("write pass");
+  { // the buffers swap roles
+    float *t = rain->previous_brightness;
+    rain->previous_brightness = im->alt;
+    im->alt = t;
+  }
   rain->first_frame = false; // :517
   char *res = (char *)user_alloc(total + 1);
   if (!res) return nullptr;

@@ -14,13 +14,56 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 99)
 assert ob.ref() is not None
 PATS = ("noise", "bars", "gradient", "grey", "solid")
 PALS = ("standard", "blocks", "digital", "minimal", "cool")
-counts = {"display": 0, "mixed": 0, "grid": 0, "filter": 0, "crc": 0}
+counts = {"display": 0, "mixed": 0, "grid": 0, "filter": 0, "crc": 0, "dither": 0, "rain": 0, "rainbow": 0, "box": 0}
 t_end = time.time() + budget
 i = 0
 while time.time() < t_end:
     i += 1
-    fam = i % 8
-    if fam < 4:
+    fam = i % 12
+    if fam == 8:  # the three dithered leaf printers
+        w, h = int(rng.integers(1, 140)), int(rng.integers(1, 70))
+        img = ob.gen(PATS[int(rng.integers(0, 5))], w, h, i)
+        pal, v = PALS[int(rng.integers(0, 5))], int(rng.integers(0, 3))
+        assert ob.ref_print_dither(img, pal, v) == ob.port_print_dither(img, pal, v), (w, h, pal, v)
+        counts["dither"] += 1
+    elif fam == 9:  # digital rain over three frames (state), random grid sizes around the frame's
+        cols, rows = int(rng.integers(1, 160)), int(rng.integers(1, 50))
+        level, mode, pal = int(rng.integers(0, 4)), int(rng.integers(0, 3)), PALS[int(rng.integers(0, 5))]
+        filt = int(rng.integers(0, 13))
+        gc, gr = max(1, cols + int(rng.integers(-4, 5))), max(1, rows + int(rng.integers(-4, 5)))
+        a, b = ob.RefRain(gc, gr, filt), ob.PortRain(gc, gr, filt)
+        for k in range(3):
+            s_ = ob.port_convert(ob.gen(PATS[int(rng.integers(0, 5))], int(rng.integers(8, 300)), int(rng.integers(8, 200)), i + k),
+                                 cols, rows, level, mode, pal)
+            if rng.random() < 0.2:
+                cut = int(rng.integers(0, len(s_) + 1))
+                s_ = s_[:cut].replace(b"\0", b"")
+            dt = float(rng.random() * 0.2)
+            assert a.apply(s_, dt) == b.apply(s_, dt), (cols, rows, level, mode, pal, filt, gc, gr, k)
+        a.close()
+        b.close()
+        counts["rain"] += 1
+    elif fam == 10:  # rainbow replace on rendered strings (never ending exactly on a colour code)
+        s_ = ob.port_convert(ob.gen(PATS[int(rng.integers(0, 5))], int(rng.integers(8, 300)), int(rng.integers(8, 200)), i),
+                             int(rng.integers(1, 160)), int(rng.integers(1, 50)), int(rng.integers(0, 4)), int(rng.integers(0, 3)),
+                             PALS[int(rng.integers(0, 5))]) + b"."
+        t = float(rng.random() * 30)
+        assert ob.ref_rainbow_replace(s_, t) == ob.port_rainbow_replace(s_, t), (len(s_), t)
+        counts["rainbow"] += 1
+    elif fam == 11:  # the box-mode checker and the fast box filter
+        W, H = int(rng.integers(1, 500)), int(rng.integers(1, 400))
+        img = ob.gen(PATS[int(rng.integers(0, 5))], W, H, i)
+        c, r = int(rng.integers(1, 200)), int(rng.integers(1, 60))
+        level, mode = int(rng.integers(0, 4)), int(rng.integers(0, 3))
+        assert ob.ref_box_convert(img, c, r, level, mode) == ob.port_convert(img, c, r, level, mode, scale=ob.SCALE_BOX), \
+            (W, H, c, r, level, mode)
+        import ctypes as C
+        u8p = C.POINTER(C.c_uint8)
+        out = np.empty((r, c, 3), np.uint8)
+        ob.port().orc_resize_box_fast(img.ctypes.data_as(u8p), W, H, out.ctypes.data_as(u8p), c, r)
+        assert np.array_equal(out, ob.port_resize(img, c, r, scale=ob.SCALE_BOX)), (W, H, c, r)
+        counts["box"] += 1
+    elif fam < 4:
         W, H = int(rng.integers(1, 500)), int(rng.integers(1, 400))
         img = ob.gen(PATS[int(rng.integers(0, 5))], W, H, i)
         if rng.random() < 0.3:
