@@ -82,7 +82,8 @@ EXPORTS = [  # every symbol include/asciichat_b200.h declares
     "rainbow_replace_ansi_colors", "acb200_mixed_cell_size", "acb200_resize_nn_device", "acb200_mixed_frame_device",
     "digital_rain_init", "digital_rain_destroy", "digital_rain_apply", "digital_rain_reset",
     "digital_rain_set_fall_speed", "digital_rain_set_raindrop_length", "digital_rain_set_color",
-    "digital_rain_set_color_from_filter",
+    "digital_rain_set_color_from_filter", "acb200_host_phase_stats",
+    "acb200_register_host_memory", "acb200_unregister_host_memory", "acb200_set_fetch_depth",
 ]
 
 
@@ -211,6 +212,12 @@ def lib():
     L.acb200_bind_thread.argtypes = [C.c_int]
     L.acb200_set_sync_mode.restype = None
     L.acb200_set_sync_mode.argtypes = [C.c_int, C.c_int]
+    L.acb200_register_host_memory.argtypes = [C.c_void_p, C.c_size_t]
+    L.acb200_unregister_host_memory.argtypes = [C.c_void_p]
+    L.acb200_set_fetch_depth.restype = None
+    L.acb200_set_fetch_depth.argtypes = [C.c_int]
+    L.acb200_host_phase_stats.restype = None
+    L.acb200_host_phase_stats.argtypes = [C.POINTER(C.c_uint64), C.c_int]
     L.acb200_source_acquire.restype = C.c_void_p
     L.acb200_source_acquire.argtypes = [C.c_int, C.c_size_t]
     L.acb200_source_commit.argtypes = [C.c_int, C.c_int, C.c_int]

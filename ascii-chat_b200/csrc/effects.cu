@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "engine.h"
 
@@ -154,11 +155,22 @@ namespace {
 constexpr uint32_t CRC_POLY = 0x82F63B78u;
 constexpr int CRC_NT = 256, CRC_SEG = 256, CRC_CHUNK = CRC_NT * CRC_SEG; // 64 KB per CTA, 256 B per thread
 
+constexpr int CRC_ROW = 512;          // row kernel: bytes a warp consumes per step (32 lanes x 16 bytes)
+constexpr int CRC_ROWPOW = 4096;      // rows covered by the constant shift table (2 MB frames; longer ones square-and-multiply)
+constexpr int CRC_NSETS = 7;          // slice tables: multiply by x^32, x^128, x^256, x^512, x^1024, x^2048, x^4096
+constexpr int CRC_ROWS_NT = 1024;     // row kernel: threads per CTA (one CTA per SM: 152 KB of tables)
+constexpr size_t CRC_ROWS_SMEM = (size_t)(4 * 256 * 32 + 6 * 4 * 256) * sizeof(uint32_t);
+
 struct CrcTables {
   uint32_t x2n[32];   // x^(2^k) mod P, reflected
   uint32_t seg[256];  // x^(8 * CRC_SEG * k) mod P: shift past k whole segments
+  uint32_t rowpow[CRC_ROWPOW]; // x^(8 * CRC_ROW * k) mod P: shift past k whole rows
+  uint32_t bytepow[CRC_ROW];   // x^(8 * k) mod P
 };
 __constant__ CrcTables c_crc;
+// z[s][j][b] = (b << 8j) * x^k mod P for k = 32, 128, 256, 512, 1024, 2048, 4096: multiplying a 32-bit state by x^k is
+// four lookups.  Global memory, one copy per device; the row kernel's CTAs copy them into shared memory.
+uint32_t *g_crc_slices[kMaxDevices] = {};
 
 __host__ __device__ inline uint32_t gf_mul(uint32_t a, uint32_t b) { // a * b mod P (reflected representation)
   uint32_t p = 0;
@@ -177,6 +189,7 @@ __host__ __device__ inline uint32_t gf_xpow8(const uint32_t *x2n, uint64_t n_byt
   return p;
 }
 
+cudaError_t crc_rows_opt_in(); // the row kernel's shared-memory opt-in (defined behind the kernel)
 // __constant__ memory is per device: the tables are uploaded once on every device the library runs on
 std::mutex g_crc_mu;
 uint64_t g_crc_done = 0; // bit per CUDA ordinal
@@ -190,7 +203,24 @@ int crc_tables_init() {
   t.x2n[0] = p;
   for (int k = 1; k < 32; k++) t.x2n[k] = p = gf_mul(p, p);
   for (int k = 0; k < 256; k++) t.seg[k] = gf_xpow8(t.x2n, (uint64_t)CRC_SEG * k);
+  const uint32_t xrow = gf_xpow8(t.x2n, CRC_ROW);
+  t.rowpow[0] = t.bytepow[0] = 0x80000000u;
+  for (int k = 1; k < CRC_ROWPOW; k++) t.rowpow[k] = gf_mul(t.rowpow[k - 1], xrow);
+  for (int k = 1; k < CRC_ROW; k++) t.bytepow[k] = gf_mul(t.bytepow[k - 1], t.x2n[3]);
   if (cudaMemcpyToSymbol(c_crc, &t, sizeof(t)) != cudaSuccess) return E_INVALID_STATE;
+  std::vector<uint32_t> z((size_t)CRC_NSETS * 4 * 256);
+  static const int kBits[CRC_NSETS] = {32, 128, 256, 512, 1024, 2048, 4096};
+  for (int si = 0; si < CRC_NSETS; si++) {
+    const uint32_t K = gf_xpow8(t.x2n, (uint64_t)kBits[si] / 8);
+    for (int j = 0; j < 4; j++)
+      for (int b = 0; b < 256; b++) z[((size_t)si * 4 + j) * 256 + b] = gf_mul((uint32_t)b << (8 * j), K);
+  }
+  if (cudaMalloc((void **)&g_crc_slices[dev], z.size() * sizeof(uint32_t)) != cudaSuccess ||
+      cudaMemcpy(g_crc_slices[dev], z.data(), z.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+      crc_rows_opt_in() != cudaSuccess) {
+    cudaGetLastError();
+    return E_INVALID_STATE;
+  }
   g_crc_done |= 1ull << dev;
   return E_OK;
 }
@@ -330,6 +360,187 @@ __global__ void __launch_bounds__(32) k_crc32c_finish(const uint32_t *part, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The row form (default).  The segment form above walks 256 contiguous bytes per thread through a byte table: four
+// DEPENDENT lookups per word, and every lane of a warp reads a different 128-byte line.  Here a warp reads whole
+// 512-byte rows (lane l the 16 bytes at 16 l: coalesced) and every one of its 128 word positions is its own stream —
+// a stream sees one word per row, 4096 bits apart, so its recurrence is  t' = t * x^4096 + w  (mod P): multiplying a
+// 32-bit state by a fixed power of x is linear, i.e. FOUR INDEPENDENT lookups (one table per state byte) and three
+// XORs, and the four streams of a thread are independent chains.  The x^4096 tables are lane-private in shared memory
+// (entry b of lane l in bank l: 4 x 32 KB, conflict-free).  At the end of a run of rows the 128 stream states are
+// folded: inside a thread by Horner with x^32, across lanes by a butterfly whose level d multiplies the earlier half by
+// x^(128 d) — shared 1 KB tables, five levels.  The work is split by ROWS over all warps of a persistent grid (a
+// warp's share may straddle frames); a run's remainder, shifted past the full rows of its frame that follow it
+// (constant-memory table of x^(4096 k)), is XORed into the frame's accumulator.  k_crc32c_tail (one warp per frame)
+// adds the < 512 bytes behind the last full row, applies the init / final complement and writes the header.
+//   words: acc[n_frames] | prefix[n_frames + 1]  (prefix = exclusive scan of full rows per frame)
+__device__ __forceinline__ uint32_t z_private(const uint32_t *Al, uint32_t t) { // Al = table + lane
+  return Al[(t & 255u) << 5] ^ Al[8192u + (((t >> 8) & 255u) << 5)] ^ Al[16384u + (((t >> 16) & 255u) << 5)] ^
+         Al[24576u + ((t >> 24) << 5)];
+}
+__device__ __forceinline__ uint32_t z_shared(const uint32_t *S, uint32_t t) { // S = one 4 x 256 set
+  return S[t & 255u] ^ S[256u + ((t >> 8) & 255u)] ^ S[512u + ((t >> 16) & 255u)] ^ S[768u + (t >> 24)];
+}
+
+__global__ void __launch_bounds__(1024) k_crc32c_plan(const uint32_t *out_len, int n_frames, uint32_t *words) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  uint32_t *acc = words, *prefix = words + n_frames;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_carry = 0u;
+  __syncthreads();
+  for (int base = 0; base < n_frames; base += 1024) {
+    const int f = base + tid;
+    const uint32_t r = f < n_frames ? out_len[f] / CRC_ROW : 0u;
+    if (f < n_frames) acc[f] = 0u;
+    uint32_t inc = r;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    uint32_t before = s_carry;
+    for (int w = 0; w < wid; w++) before += s_warp[w];
+    if (f < n_frames) prefix[f] = before + inc - r;
+    __syncthreads();
+    if (tid == 1023) s_carry = before + inc;
+    __syncthreads();
+  }
+  if (tid == 0) prefix[n_frames] = s_carry;
+}
+
+__global__ void __launch_bounds__(CRC_ROWS_NT, 1) k_crc32c_rows(const uint8_t *out, size_t out_pitch, int n_frames,
+                                                               uint32_t *words, const uint32_t *slices,
+                                                               uint8_t *copy_dst, size_t copy_pitch) {
+  extern __shared__ uint32_t s_crc[];
+  uint32_t *A = s_crc;                  // [4][256][32]: x^4096, lane-private
+  uint32_t *S = s_crc + 4 * 256 * 32;   // [6][4][256]: x^32, x^128 .. x^2048
+  uint32_t *acc = words;
+  const uint32_t *prefix = words + n_frames;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t total = prefix[n_frames];
+  const uint32_t nwarps = gridDim.x * (CRC_ROWS_NT / 32);
+  uint32_t K = (total + nwarps - 1u) / nwarps;
+  if (K < 4u) K = 4u; // short inputs: fewer, longer runs (the fold costs about as much as two rows)
+  if ((uint64_t)blockIdx.x * (CRC_ROWS_NT / 32) * K >= total) return; // uniform per CTA: nothing to do, no table fill
+  for (int i = tid; i < 4 * 256 * 32; i += CRC_ROWS_NT) A[i] = slices[6 * 1024 + (i >> 5)];
+  for (int i = tid; i < 6 * 4 * 256; i += CRC_ROWS_NT) S[i] = slices[i];
+  __syncthreads();
+  const uint32_t *Al = A + lane;
+  const uint32_t gw = blockIdx.x * (CRC_ROWS_NT / 32) + (tid >> 5);
+  uint64_t s64 = (uint64_t)gw * K;
+  if (s64 >= total) return;
+  uint32_t s = (uint32_t)s64;
+  const uint32_t e = (s64 + K < total) ? s + K : total;
+  // frame that holds row s: the largest f with prefix[f] <= s (32-ary search, every lane probes)
+  int lo = 0, hi = n_frames; // answer in [lo, hi)
+  while (hi - lo > 1) {
+    const int step = (hi - lo + 31) / 32;
+    const int idx = lo + lane * step;
+    const bool le = idx < hi && prefix[idx] <= s;
+    const int cnt = __popc(__ballot_sync(0xffffffffu, le)); // lanes 0 .. cnt-1 (prefix is non-decreasing), cnt >= 1
+    lo = lo + (cnt - 1) * step;
+    hi = (lo + step < hi) ? lo + step : hi;
+  }
+  int f = lo;
+  while (s < e) {
+    while (prefix[f + 1] <= s) f++; // frames without a full row
+    const uint32_t p0 = prefix[f], p1 = prefix[f + 1];
+    const uint32_t r0 = s - p0, r1 = (e < p1 ? e : p1) - p0; // rows [r0, r1) of frame f
+    const uint4 *src = reinterpret_cast<const uint4 *>(out + (size_t)f * out_pitch + (size_t)r0 * CRC_ROW) + lane;
+    uint4 *dst = copy_dst ? reinterpret_cast<uint4 *>(copy_dst + (size_t)f * copy_pitch + (size_t)r0 * CRC_ROW) + lane : nullptr;
+    const int n = (int)(r1 - r0);
+    uint32_t t0 = 0u, t1 = 0u, t2 = 0u, t3 = 0u;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    // four rows in flight per warp: with 32 warps a step comes round every few hundred cycles, DRAM takes longer
+    uint4 q0 = ld_stream16(src), q1 = n > 1 ? ld_stream16(src + 32) : zero, q2 = n > 2 ? ld_stream16(src + 64) : zero,
+          q3 = n > 3 ? ld_stream16(src + 96) : zero;
+    auto step = [&](const uint4 &v, int k) {
+      if (dst) dst[(size_t)k * 32] = v;
+      t0 = z_private(Al, t0) ^ v.x;
+      t1 = z_private(Al, t1) ^ v.y;
+      t2 = z_private(Al, t2) ^ v.z;
+      t3 = z_private(Al, t3) ^ v.w;
+    };
+    for (int k = 0; k < n; k += 4) {
+      const uint4 *nx = src + (size_t)(k + 4) * 32;
+      step(q0, k);
+      q0 = k + 4 < n ? ld_stream16(nx) : zero;
+      if (k + 1 < n) step(q1, k + 1);
+      q1 = k + 5 < n ? ld_stream16(nx + 32) : zero;
+      if (k + 2 < n) step(q2, k + 2);
+      q2 = k + 6 < n ? ld_stream16(nx + 64) : zero;
+      if (k + 3 < n) step(q3, k + 3);
+      q3 = k + 7 < n ? ld_stream16(nx + 96) : zero;
+    }
+    // fold the 128 streams: words of a thread by Horner with x^32, lanes by a butterfly with x^128, x^256, ...
+    uint32_t u = z_shared(S, z_shared(S, z_shared(S, t0) ^ t1) ^ t2) ^ t3;
+#pragma unroll
+    for (int lvl = 0; lvl < 5; lvl++) {
+      const int d = 1 << lvl;
+      const uint32_t o = __shfl_xor_sync(0xffffffffu, u, d);
+      const bool upper = (lane & d) != 0;
+      u = z_shared(S + (1 + lvl) * 1024, upper ? o : u) ^ (upper ? u : o);
+    }
+    u = z_shared(S, u); // remainder of the run's bytes * x^32 (state form of the table recurrence, start value 0)
+    const uint32_t after = (p1 - p0) - r1; // full rows of this frame behind the run
+    if (lane == 0) {
+      const uint32_t shift = after < (uint32_t)CRC_ROWPOW ? c_crc.rowpow[after] : gf_xpow8(c_crc.x2n, (uint64_t)after * CRC_ROW);
+      atomicXor(&acc[f], after ? gf_mul(shift, u) : u);
+    }
+    s = p0 + r1;
+  }
+}
+
+// one warp per frame: the bytes behind the last full row, init / final complement, header (server.c:206-214)
+__global__ void __launch_bounds__(32) k_crc32c_tail(const uint8_t *out, size_t out_pitch, const uint32_t *out_len,
+                                                    const uint32_t *words, uint32_t width, uint32_t height,
+                                                    uint8_t *headers, size_t header_pitch, uint8_t *copy_dst,
+                                                    size_t copy_pitch) {
+  __shared__ uint32_t T[256];
+  const int f = blockIdx.x, lane = threadIdx.x;
+  for (int i = lane; i < 256; i += 32) {
+    uint32_t v = (uint32_t)i;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v = (v >> 1) ^ ((v & 1u) ? CRC_POLY : 0u);
+    T[i] = v;
+  }
+  __syncwarp();
+  const uint32_t L = out_len[f];
+  const uint32_t full = (L / CRC_ROW) * CRC_ROW, r = L - full; // r < 512: lane l takes tail bytes [16 l, 16 l + 16)
+  const uint8_t *tail = out + (size_t)f * out_pitch + full;
+  uint8_t *dst = copy_dst ? copy_dst + (size_t)f * copy_pitch + full : nullptr;
+  uint32_t c = 0u;
+  const uint32_t b0 = 16u * lane, b1 = b0 + 16u < r ? b0 + 16u : r;
+  if (b0 < r) {
+    uint32_t st = 0u;
+    for (uint32_t i = b0; i < b1; i++) {
+      const uint8_t b = tail[i];
+      if (dst) dst[i] = b;
+      st = T[(st ^ b) & 255u] ^ (st >> 8);
+    }
+    c = gf_mul(c_crc.bytepow[r - b1], st);
+  }
+  if (lane == 0) c ^= gf_mul(c_crc.bytepow[r], words[f]); // the full rows, shifted past the tail
+  if (lane == 1) c ^= gf_mul(gf_xpow8(c_crc.x2n, L), 0xFFFFFFFFu); // the initial value, shifted past the whole frame
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, d);
+  const uint32_t crc = ~c;
+  if (lane < 6) {
+    const uint32_t v = lane == 0 ? width : lane == 1 ? height : lane == 2 ? L : lane == 4 ? crc : 0u;
+    uint8_t *h = headers + (size_t)f * header_pitch + 4 * lane;
+    h[0] = (uint8_t)(v >> 24);
+    h[1] = (uint8_t)(v >> 16);
+    h[2] = (uint8_t)(v >> 8);
+    h[3] = (uint8_t)v;
+  }
+}
+cudaError_t crc_rows_opt_in() {
+  return cudaFuncSetAttribute(k_crc32c_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CRC_ROWS_SMEM);
+}
+
 // stream.c:1085-1127 on the device: a frame that does not end in ESC[0m is cut after its last ESC[0m, if it has one.
 // One CTA per frame, scanning backwards; almost always decided by the first four bytes looked at.
 __global__ void __launch_bounds__(256) k_trailing_reset_fixup(uint8_t *out, size_t out_pitch, uint32_t *out_len) {
@@ -361,7 +572,11 @@ __global__ void __launch_bounds__(256) k_trailing_reset_fixup(uint8_t *out, size
 
 namespace acb {
 
-int max_crc_chunks(size_t frame_capacity) { return (int)((frame_capacity + CRC_CHUNK - 1) / CRC_CHUNK); }
+// words of device scratch per frame that launch_frame_packets needs (>= 4: the row form keeps 2 n + 1 words)
+int max_crc_chunks(size_t frame_capacity) {
+  const int c = (int)((frame_capacity + CRC_CHUNK - 1) / CRC_CHUNK);
+  return c < 4 ? 4 : c;
+}
 
 int launch_reset_fixup(uint8_t *d_out, size_t out_pitch, uint32_t *d_out_len, int n_frames, cudaStream_t st) {
   k_trailing_reset_fixup<<<(unsigned)n_frames, 256, 0, st>>>(d_out, out_pitch, d_out_len);
@@ -377,6 +592,28 @@ int launch_frame_packets(const uint8_t *d_out, size_t out_pitch, const uint32_t 
   if (crc_tables_init() != E_OK) return set_error(E_INVALID_STATE, "CUDA: CRC table upload failed");
   // measurement knob (never set in production): run the table recurrence on synthetic words, no global loads
   static const int crc_noload = getenv("ACB200_CRC_NOLOAD") ? atoi(getenv("ACB200_CRC_NOLOAD")) : 0;
+  // ACB200_CRC_KERNEL=segments (measurement knob): the round-1 form, one thread per 256 contiguous bytes
+  static const bool segments = getenv("ACB200_CRC_KERNEL") && !strcmp(getenv("ACB200_CRC_KERNEL"), "segments");
+  if (!segments && !crc_noload) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    k_crc32c_plan<<<1, 1024, 0, st>>>(d_out_len, n_frames, d_part);
+    ACB_CUDA(cudaGetLastError());
+    // at least four rows per warp; one CTA per SM at most (persistent, 152 KB of tables each)
+    const uint64_t rows_max = (uint64_t)n_frames * (out_pitch / CRC_ROW);
+    uint64_t ctas = (rows_max + 4u * (CRC_ROWS_NT / 32) - 1u) / (4u * (CRC_ROWS_NT / 32));
+    const uint64_t sms = (uint64_t)device_sms();
+    if (ctas > sms) ctas = sms;
+    if (ctas < 1) ctas = 1;
+    k_crc32c_rows<<<(unsigned)ctas, CRC_ROWS_NT, CRC_ROWS_SMEM, st>>>(d_out, out_pitch, n_frames, d_part, g_crc_slices[dev],
+                                                                     copy_dst, copy_pitch);
+    ACB_CUDA(cudaGetLastError());
+    k_crc32c_tail<<<(unsigned)n_frames, 32, 0, st>>>(d_out, out_pitch, d_out_len, d_part, width, height, headers,
+                                                    header_pitch, copy_dst, copy_pitch);
+    ACB_CUDA(cudaGetLastError());
+    count_launch(3);
+    return E_OK;
+  }
   for (int f0 = 0; f0 < n_frames; f0 += 65535) { // gridDim.y limit
     const int nf = n_frames - f0 < 65535 ? n_frames - f0 : 65535;
     k_crc32c_chunks<<<dim3((unsigned)max_chunks, (unsigned)nf), CRC_NT, 0, st>>>(

@@ -13,10 +13,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <immintrin.h>
 #include <map>
 #include <mutex>
 #include <string>
 #include <vector>
+
+#include <sched.h>
 
 // forwarded to when the host binary provides it (include/ascii-chat/asciichat_errno.h:429)
 extern "C" void asciichat_set_errno_with_message(int code, const char *file, int line, const char *function,
@@ -59,6 +62,7 @@ struct DeviceState {
   std::vector<ThreadCtx *> pool;              // warm contexts handed back by exited threads
   std::map<std::string, GlyphLut *> luts;     // key = which + palette bytes
   std::vector<GlyphLut *> retired;            // evicted, possibly still referenced by a launch being prepared
+  std::atomic<int> fetch_inflight{0};         // drop-in calls whose frame the GPU is fetching from pinned host memory
 };
 static DeviceState g_ds[kMaxDevices]; // indexed by CUDA ordinal
 static std::mutex g_dev_mu;
@@ -68,10 +72,32 @@ static int g_npool = 0;
 static int g_requested_device = -1;   // acb200_init(device) before the first use
 static bool g_peer[kMaxDevices][kMaxDevices];
 static std::atomic<unsigned> g_rr{0};
-// 0 spin (cudaStreamSynchronize, default), 1 block, 2 hybrid.  Measured on the 16-core B200 box (profiles/r02a_e2e_sweep):
-// spinning callers deliver 35.5 k frames/s at 16 threads, sleeping ones 20 k (28 k at 64 threads) — the wake-up latency
-// of a blocking event costs more than the core the spin burns, even with four callers per core.
+// 0 spin (cudaStreamSynchronize), 1 block, 2 hybrid, 3 yield (poll a completion word the stream writes into mapped
+// memory; sched_yield between polls).  Measured on the 16-core B200 box (profiles/r02a_e2e_sweep): spinning callers
+// deliver 35.5 k frames/s at 16 threads, sleeping ones 20 k (28 k at 64 threads) — the wake-up latency of a blocking
+// event costs more than the core the spin burns.  But a spinning caller also keeps its core from the callers that have
+// a gather or a copy-out to do, which is what stops the call from scaling once several GPUs share the host's cores
+// (DESIGN §9): mode 3 spins only while nobody else wants the core.
 static std::atomic<int> g_sync_mode{0}, g_spin_us{30};
+// Frames in page-locked host memory (acb200_register_host_memory, or cudaHostAlloc'd by the caller) need no host-side
+// gather: the COPY ENGINE fetches the source rows nearest-neighbour sampling reads (2.2 MB of a 4K frame, as a few
+// strided 2-D copies) and a small kernel samples the columns on the device.  That frees the caller's core — the gather
+// is 130-250 us of a ~330 us call, profiles/r02l_e2e_inproc2.txt — but the link carries 12 x the bytes of the
+// host-gathered plan (0.18 MB), so it is used for at most this many calls per GPU at a time and the rest keep
+// gathering on their cores: -1 = always, 0 = never.  (Letting the SMs read the rows out of mapped host memory instead
+// was measured first: 9.5 GB/s for a frame on its own, ~34 GB/s with 24 callers — sector-sized PCIe reads;
+// profiles/r02m_e2e_registered1.txt.)
+static std::atomic<int> g_fetch_depth{3};
+// cuStreamWriteValue32 through the runtime's driver-entry-point lookup (the library links no libcuda symbol directly)
+typedef int (*StreamWriteValue32)(cudaStream_t, unsigned long long, uint32_t, unsigned);
+static StreamWriteValue32 g_write_value32 = nullptr;
+// where a drop-in call's host time goes (ns, summed over calls): gather/staging, enqueue, wait, copy-out; [4] = calls
+static std::atomic<uint64_t> g_phase_ns[5];
+static inline uint64_t now_ns() {
+  timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec;
+}
 
 static int init_pool_locked(const int *devs, int n) { // g_dev_mu held
   int count = 0;
@@ -131,7 +157,17 @@ static int init_pool_locked(const int *devs, int n) { // g_dev_mu held
     else if (!strncmp(e, "hybrid", 6)) {
       g_sync_mode.store(2);
       if (e[6] == ':') g_spin_us.store(atoi(e + 7));
-    }
+    } else if (!strncmp(e, "yield", 5)) g_sync_mode.store(3);
+  }
+  if (const char *e = getenv("ACB200_FETCH_DEPTH")) g_fetch_depth.store(atoi(e)); // measurement knob
+  {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      g_write_value32 = (StreamWriteValue32)fn;
+    else
+      cudaGetLastError();
   }
   return 0;
 }
@@ -236,6 +272,15 @@ ThreadCtx *thread_ctx() {
   }
   for (auto &e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDefault);
   cudaEventCreateWithFlags(&c->done, cudaEventBlockingSync | cudaEventDisableTiming);
+  {
+    void *f = nullptr;
+    if (cudaHostAlloc(&f, 64, cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess) {
+      memset(f, 0, 64);
+      c->h_flag = (volatile uint32_t *)f;
+    } else {
+      cudaGetLastError();
+    }
+  }
   t_lease.c = c;
   return c;
 }
@@ -245,7 +290,30 @@ ThreadCtx *thread_ctx() {
 // cores are scarcer than on the boxes measured — see g_sync_mode.
 int wait_stream(ThreadCtx *cx) {
   const int mode = g_sync_mode.load(std::memory_order_relaxed);
-  if (mode == 0 || !cx->done) {
+  if (mode == 3 && cx->h_flag && g_write_value32) {
+    const uint32_t seq = ++cx->flag_seq;
+    // the write is ordered behind everything queued so far and preceded by a system-wide fence (no NO_MEMORY_BARRIER
+    // flag): when the word shows `seq`, the strings the kernels stored into mapped memory are visible
+    if (g_write_value32(cx->stream, (unsigned long long)(uintptr_t)cx->h_flag, seq, 0) == 0) {
+      volatile uint32_t *f = cx->h_flag;
+      for (unsigned rounds = 1;; rounds++) {
+        for (int i = 0; i < 48; i++) {
+          if (*f == seq) {
+            std::atomic_thread_fence(std::memory_order_acquire);
+            return E_OK;
+          }
+          _mm_pause();
+        }
+        sched_yield();
+        if ((rounds & 2047u) == 0) { // a faulted stream never writes the word
+          cudaError_t q = cudaStreamQuery(cx->stream);
+          if (q == cudaSuccess) return E_OK;
+          if (q != cudaErrorNotReady) return set_error(E_INVALID_STATE, "CUDA: %s (cudaStreamQuery)", cudaGetErrorString(q));
+        }
+      }
+    }
+  }
+  if (mode == 0 || mode == 3 || !cx->done) {
     ACB_CUDA(cudaStreamSynchronize(cx->stream));
     return E_OK;
   }
@@ -310,8 +378,10 @@ static void free_ctx(ThreadCtx *c) {
   if (c->h_in) cudaFreeHost(c->h_in);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_len) cudaFreeHost(c->h_len);
+  if (c->h_flag) cudaFreeHost((void *)c->h_flag);
   if (c->d_in) cudaFree(c->d_in);
   if (c->d_out) cudaFree(c->d_out);
+  if (c->d_rows) cudaFree(c->d_rows);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->d_len) cudaFree(c->d_len);
   if (c->d_frame) cudaFree(c->d_frame);
@@ -767,18 +837,54 @@ static bool nn_column_table(ThreadCtx *cx, int src_w, int cols, int flip_x) {
   return true;
 }
 
-// dst receives cols x rows packed RGB24 (+ up to 1 byte of slack: pixels are moved as overlapping 4-byte words)
+// dst receives cols x rows packed RGB24 (+ up to 1 byte of slack: pixels are moved as overlapping 4-byte words).
+// A sampled source row is used exactly once and its neighbours not at all (192 of 2160 rows at C3, ~11 rows = 129 KB
+// apart).  ACB200_GATHER_AHEAD=k asks for the row k ahead while the current one is copied (non-temporal hint): on an
+// AMD EPYC (Zen 5) host that halves the gather (155 -> 73 us per 4K frame), on the Xeon hosts of the B200 boxes it
+// DOUBLES it (131-142 -> 242-283 us, profiles/r02m_gather_prefetch_ab.txt) — software prefetches compete with the
+// demand loads for the same fill buffers there — so the default is 0 (none).
 static void gather_nn_pixels(const uint8_t *src, int src_w, int src_h, int cols, int rows, bool flip_y,
                              const uint32_t *off, uint8_t *dst) {
   const size_t R = (size_t)src_w * 3;
   const uint32_t yr = nn_ratio(src_h, rows);
-  for (int y = 0; y < rows; y++) {
+  static const int kAhead = getenv("ACB200_GATHER_AHEAD") ? atoi(getenv("ACB200_GATHER_AHEAD")) : 0; // 0 = no prefetch
+  auto src_row = [&](int y) -> const uint8_t * {
     uint32_t sy = nn_src_index(y, yr, src_h);
     if (flip_y) sy = (uint32_t)src_h - 1u - sy;
-    const uint8_t *row = src + (size_t)sy * R;
+    return src + (size_t)sy * R;
+  };
+  for (int y = 0; y < kAhead && y < rows; y++) {
+    const uint8_t *row = src_row(y);
+    for (int x = 0; x < cols; x++) _mm_prefetch((const char *)row + off[x], _MM_HINT_NTA);
+  }
+  if (kAhead <= 0) { // plain form
+    for (int y = 0; y < rows; y++) {
+      const uint8_t *row = src_row(y);
+      uint8_t *d = dst + (size_t)y * cols * 3u;
+      if (row + R < src + R * (size_t)src_h) {
+        for (int x = 0; x < cols; x++) {
+          uint32_t v;
+          memcpy(&v, row + off[x], 4);
+          memcpy(d + 3 * x, &v, 4);
+        }
+      } else {
+        for (int x = 0; x < cols; x++) {
+          const uint8_t *q = row + off[x];
+          d[3 * x] = q[0];
+          d[3 * x + 1] = q[1];
+          d[3 * x + 2] = q[2];
+        }
+      }
+    }
+    return;
+  }
+  for (int y = 0; y < rows; y++) {
+    const uint8_t *row = src_row(y);
+    const uint8_t *ahead = (kAhead > 0 && y + kAhead < rows) ? src_row(y + kAhead) : row;
     uint8_t *d = dst + (size_t)y * cols * 3u;
-    if (sy + 1u < (uint32_t)src_h) { // a 4-byte read of the row's last pixel stays inside the image
+    if (row + R < src + R * (size_t)src_h) { // a 4-byte read of the row's last pixel stays inside the image
       for (int x = 0; x < cols; x++) {
+        _mm_prefetch((const char *)ahead + off[x], _MM_HINT_NTA);
         uint32_t v;
         memcpy(&v, row + off[x], 4);
         memcpy(d + 3 * x, &v, 4);
@@ -794,14 +900,74 @@ static void gather_nn_pixels(const uint8_t *src, int src_w, int src_h, int cols,
   }
 }
 
-static bool is_pinned(const void *p) {
+// device-side address of `p` if it lies in page-locked host memory the current device can read, else nullptr
+static const uint8_t *pinned_dev_ptr(const void *p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();
-    return false;
+    return nullptr;
   }
-  return a.type == cudaMemoryTypeHost;
+  return a.type == cudaMemoryTypeHost ? (const uint8_t *)a.devicePointer : nullptr;
 }
+static bool is_pinned(const void *p) { return pinned_dev_ptr(p) != nullptr; }
+
+// The source rows NN sampling reads, in ascending order (with flip_y the list is walked backwards: row j of the list is
+// output row rows-1-j), as P interleaved arithmetic progressions: list[j + P] - list[j] == D for every j.  Any integer
+// or k/4-type ratio has a small P (2160 -> 192: rows 0,11,22,33,45,...: P = 4, D = 45); geometries without one keep the
+// host gather.
+struct RowSchedule {
+  int src_h = 0, rows = 0, flip = -1, P = 0, D = 0; // P == 0: no progression with P <= kMaxP
+  int first[8];
+};
+static constexpr int kMaxP = 8;
+static void row_schedule(RowSchedule &rs, int src_h, int rows, bool flip_y) {
+  if (rs.src_h == src_h && rs.rows == rows && rs.flip == (flip_y ? 1 : 0)) return;
+  rs.src_h = src_h;
+  rs.rows = rows;
+  rs.flip = flip_y ? 1 : 0;
+  rs.P = 0;
+  const uint32_t yr = nn_ratio(src_h, rows);
+  auto at = [&](int j) -> int { // ascending
+    if (!flip_y) return (int)nn_src_index(j, yr, src_h);
+    return src_h - 1 - (int)nn_src_index(rows - 1 - j, yr, src_h);
+  };
+  for (int P = 1; P <= kMaxP && P <= rows; P++) {
+    if (rows <= P) { // fewer rows than progressions: each is a single row
+      rs.P = rows;
+      rs.D = 1;
+      for (int k = 0; k < rows; k++) rs.first[k] = at(k);
+      return;
+    }
+    const int D = at(P) - at(0);
+    bool ok = D > 0;
+    for (int j = 0; ok && j + P < rows; j++) ok = at(j + P) - at(j) == D;
+    if (ok) {
+      rs.P = P;
+      rs.D = D;
+      for (int k = 0; k < P; k++) rs.first[k] = at(k);
+      return;
+    }
+  }
+}
+
+struct FetchSlot { // one of the per-GPU "the device fetches my frame" slots (g_fetch_depth), released on scope exit
+  std::atomic<int> *ctr = nullptr;
+  bool held = false;
+  bool try_take(std::atomic<int> *c) {
+    const int depth = g_fetch_depth.load(std::memory_order_relaxed);
+    if (depth == 0) return false;
+    if (depth < 0) return held = true;
+    if (c->fetch_add(1, std::memory_order_relaxed) >= depth) {
+      c->fetch_sub(1, std::memory_order_relaxed);
+      return false;
+    }
+    ctr = c;
+    return held = true;
+  }
+  ~FetchSlot() {
+    if (ctr) ctr->fetch_sub(1, std::memory_order_relaxed);
+  }
+};
 
 static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t *const *frames, int n_frames,
                                   char **out, size_t *out_len, int leaf_mode = -1) {
@@ -830,6 +996,18 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
     if (!make_plan(dcfg, pl, leaf_mode)) return t_err;
     if (!nn_column_table(cx, cfg.src_w, cfg.cols, flip_x ? 1 : 0)) return t_err;
   }
+  // pinned frames: let the GPU do the sampling reads, if one of the device's fetch slots is free
+  FetchSlot fetch;
+  static thread_local RowSchedule rsched;
+  if (tplan == PLAN_NN_PIXELS && R + 32u <= 48u * 1024u && g_fetch_depth.load(std::memory_order_relaxed) != 0) {
+    bool all_pinned = true;
+    for (int i = 0; i < n_frames && all_pinned; i++) all_pinned = frames[i] && is_pinned(frames[i]);
+    if (all_pinned) {
+      row_schedule(rsched, cfg.src_h, cfg.rows_px, flip_y);
+      if (rsched.P > 0) fetch.try_take(&g_ds[cx->device].fetch_inflight);
+    }
+  }
+  const bool dev_fetch = fetch.held;
   const size_t in_per_frame = tplan == PLAN_NN_PIXELS ? (size_t)cfg.cols * cfg.rows_px * 3
                               : tplan == PLAN_NN_ROWS ? R * cfg.rows_px
                                                       : R * cfg.src_h;
@@ -842,15 +1020,22 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
   const int nslot = nchunks > 1 ? 2 : 1; // two slots: the host drains chunk k-1 while the GPU works on chunk k
   const size_t in_slot = in_pitch * chunk, out_slot = al256(cap * chunk), len_slot = al256(4u * chunk);
   for (int i = 0; i < n_frames; i++) out[i] = nullptr;
-  bool need_stage = tplan != PLAN_FULL;
-  for (int i = 0; i < n_frames && !need_stage; i++) need_stage = frames[i] && !is_pinned(frames[i]);
+  bool need_stage = tplan != PLAN_FULL && !dev_fetch;
+  for (int i = 0; i < n_frames && !need_stage && !dev_fetch; i++) need_stage = frames[i] && !is_pinned(frames[i]);
   const size_t scratch_cap_before = cx->d_scratch_cap; // a regrown buffer may come back at the same address
   // How the strings leave the device.  Default: the emitters store them straight into mapped pinned host memory.
   // ACB200_D2H=ce (measurement knob): the emitters write to HBM, the lengths come back first, then the copy engine moves
   // exactly the bytes of each string (full-size PCIe payloads, one more wait per chunk).
   static const bool d2h_ce = getenv("ACB200_D2H") && !strcmp(getenv("ACB200_D2H"), "ce");
+  // How the gathered pixels reach the device.  Default: one H2D copy of the staged chunk.  ACB200_H2D=zc (measurement
+  // knob): the sampler reads them where the gather left them, in mapped pinned memory (every pixel is read once).
+  static const bool h2d_zc = getenv("ACB200_H2D") && !strcmp(getenv("ACB200_H2D"), "zc");
+  const bool zero_copy_in = h2d_zc && tplan == PLAN_NN_PIXELS && !dev_fetch;
+  uint64_t ph[4] = {0, 0, 0, 0}; // gather/staging, enqueue, wait, copy-out
   if (sync_foreign(cx, cx->stream) != E_OK) return t_err;
   if (d2h_ce && !grow_device(&cx->d_out, &cx->d_out_cap, out_slot * nslot)) return t_err;
+  const size_t rows_per_frame = al256(R * (size_t)cfg.rows_px);
+  if (dev_fetch && !grow_device(&cx->d_rows, &cx->d_rows_cap, rows_per_frame * chunk * nslot)) return t_err;
   if (!grow_device(&cx->d_in, &cx->d_in_cap, in_slot * nslot) ||
       !grow_device(&cx->d_scratch, &cx->d_scratch_cap, scratch_bytes(pl, chunk)) ||
       !grow_pinned(&cx->h_out, &cx->h_out_cap, out_slot * nslot) ||
@@ -878,13 +1063,27 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
     uint8_t *st_base = need_stage ? cx->h_in + (size_t)slot * in_slot : nullptr;
     // gathered frames are small: the whole chunk goes up as one H2D.  Full frames go up one by one, so that the staging
     // copy of frame i+1 overlaps the DMA of frame i.
-    const bool all_staged = tplan != PLAN_FULL;
+    const bool all_staged = tplan != PLAN_FULL && !dev_fetch;
+    const uint64_t t_issue = now_ns();
     for (int i = 0; i < n; i++) {
       const uint8_t *src = frames[f0 + i];
       if (!src) return set_error(E_INVALID_PARAM, "frame %d is NULL", f0 + i);
       uint8_t *dst = d_in + (size_t)i * in_pitch;
       uint8_t *st = st_base ? st_base + (size_t)i * in_pitch : nullptr;
-      if (tplan == PLAN_NN_PIXELS) {
+      if (dev_fetch) {
+        // copy engine: progression k = rows first[k], first[k] + D, ... of the frame -> rows k, k + P, ... of the list
+        uint8_t *rows_dev = cx->d_rows + ((size_t)slot * chunk + i) * rows_per_frame;
+        const int P = rsched.P;
+        for (int k = 0; k < P; k++) {
+          const int cnt = (cfg.rows_px - k + P - 1) / P;
+          ACB_CUDA(cudaMemcpy2DAsync(rows_dev + (size_t)k * R, (size_t)P * R, src + (size_t)rsched.first[k] * R,
+                                     (size_t)rsched.D * R, R, (size_t)cnt, cudaMemcpyHostToDevice, cx->stream));
+        }
+        // ... and the columns on the device: the list is 1:1 in y (walked backwards when the image is flipped)
+        ACB_CUDA(launch_gather_nn_rows(rows_dev, cfg.src_w, cfg.rows_px, cfg.cols, cfg.rows_px, flip_x ? 1 : 0,
+                                       flip_y ? 1 : 0, dst, cx->stream));
+        count_launch(1);
+      } else if (tplan == PLAN_NN_PIXELS) {
         gather_nn_pixels(src, cfg.src_w, cfg.src_h, cfg.cols, cfg.rows_px, flip_y, cx->nn_off, st);
       } else if (tplan == PLAN_NN_ROWS) {
         const uint32_t yr = nn_ratio(cfg.src_h, cfg.rows_px);
@@ -900,7 +1099,10 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
         ACB_CUDA(cudaMemcpyAsync(dst, st, in_per_frame, cudaMemcpyHostToDevice, cx->stream));
       }
     }
-    if (all_staged)
+    const uint64_t t_staged = now_ns();
+    if (zero_copy_in)
+      d_in = st_base;
+    else if (all_staged)
       ACB_CUDA(cudaMemcpyAsync(d_in, st_base, (size_t)(n - 1) * in_pitch + in_per_frame, cudaMemcpyHostToDevice, cx->stream));
     int rc = render_device(dcfg, pl, d_in, in_pitch, tplan == PLAN_NN_ROWS ? 1 : 0, n,
                            (d2h_ce ? cx->d_out : cx->h_out) + (size_t)slot * out_slot,
@@ -908,11 +1110,14 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
                            cx->d_scratch, cx->stream, nullptr, nullptr, &cx->lb);
     if (rc) return rc;
     if (nchunks > 1) ACB_CUDA(cudaEventRecord(cx->ev[2 + slot], cx->stream)); // single chunk: collect() waits on the stream
+    ph[0] += t_staged - t_issue;
+    ph[1] += now_ns() - t_staged;
     return E_OK;
   };
   auto collect = [&](int k) -> int {
     const int slot = k & 1, f0 = k * chunk;
     const int n = (n_frames - f0 < chunk) ? n_frames - f0 : chunk;
+    const uint64_t t_wait = now_ns();
     if (nchunks > 1) ACB_CUDA(cudaEventSynchronize(cx->ev[2 + slot]));
     else if (wait_stream(cx) != E_OK) return t_err;
     const uint32_t *lens =
@@ -925,6 +1130,8 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
                                  cx->stream));
       if (wait_stream(cx) != E_OK) return t_err;
     }
+    const uint64_t t_copy = now_ns();
+    ph[2] += t_copy - t_wait;
     for (int i = 0; i < n; i++) {
       const size_t len = lens[i];
       char *sp = (char *)user_alloc(len + 1);
@@ -934,6 +1141,7 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
       out[f0 + i] = sp;
       if (out_len) out_len[f0 + i] = len;
     }
+    ph[3] += now_ns() - t_copy;
     return E_OK;
   };
   int rc = E_OK;
@@ -943,6 +1151,8 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
   }
   if (rc == E_OK) rc = collect(nchunks - 1);
   if (rc != E_OK) cudaStreamSynchronize(cx->stream); // leave no work in flight that targets our staging
+  for (int k = 0; k < 4; k++) g_phase_ns[k].fetch_add(ph[k], std::memory_order_relaxed);
+  g_phase_ns[4].fetch_add((uint64_t)n_frames, std::memory_order_relaxed);
   return rc;
 }
 
@@ -1072,10 +1282,34 @@ int acb200_thread_device(void) {
   ThreadCtx *cx = thread_ctx();
   return cx ? cx->device : -1;
 }
+int acb200_register_host_memory(void *p, size_t bytes) {
+  if (!p || !bytes) return set_error(E_INVALID_PARAM, "acb200_register_host_memory: empty range");
+  if (!thread_ctx()) return t_err; // registration needs a current device
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return E_OK;
+  }
+  if (e != cudaSuccess) return set_error(E_MEMORY, "cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  return E_OK;
+}
+int acb200_unregister_host_memory(void *p) {
+  if (!p) return E_OK;
+  cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) return set_error(E_INVALID_PARAM, "cudaHostUnregister: %s", cudaGetErrorString(e));
+  return E_OK;
+}
+void acb200_set_fetch_depth(int depth) { g_fetch_depth.store(depth); }
+void acb200_host_phase_stats(uint64_t out[5], int reset) {
+  for (int k = 0; k < 5; k++) {
+    if (out) out[k] = g_phase_ns[k].load(std::memory_order_relaxed);
+    if (reset) g_phase_ns[k].store(0, std::memory_order_relaxed);
+  }
+}
 // how a caller waits for its frame: 0 spin (cudaStreamSynchronize), 1 sleep on a blocking-sync event, 2 poll for spin_us
-// microseconds, then sleep (default, 30 us)
+// microseconds, then sleep, 3 poll the stream's completion word and yield the core between polls
 void acb200_set_sync_mode(int mode, int spin_us) {
-  if (mode >= 0 && mode <= 2) g_sync_mode.store(mode);
+  if (mode >= 0 && mode <= 3) g_sync_mode.store(mode);
   if (spin_us >= 0) g_spin_us.store(spin_us);
 }
 void acb200_shutdown(void) {

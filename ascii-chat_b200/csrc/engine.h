@@ -57,12 +57,16 @@ struct ThreadCtx {
   uint8_t *h_out = nullptr;  size_t h_out_cap = 0;  // pinned
   uint8_t *d_in = nullptr;   size_t d_in_cap = 0;
   uint8_t *d_out = nullptr;  size_t d_out_cap = 0;
+  uint8_t *d_rows = nullptr; size_t d_rows_cap = 0; // source rows the copy engine fetched from page-locked frames
   uint8_t *d_scratch = nullptr; size_t d_scratch_cap = 0;
   uint32_t *d_len = nullptr; size_t d_len_cap = 0;   // CRC chunk words of acb200_frame_packets_device (effects.cu)
   uint8_t *d_frame = nullptr; size_t d_frame_cap = 0; // one-frame packet path: device arena + length + CRC chunk words
   uint32_t *h_len = nullptr; size_t h_len_cap = 0;  // pinned
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t done = nullptr;   // cudaEventBlockingSync: the waiting caller sleeps instead of spinning (wait_stream)
+  // completion word in mapped pinned memory, written by the stream itself (cuStreamWriteValue32) behind the frame's
+  // work: a waiting caller polls plain memory and yields its core between polls (wait_stream, sync mode 3)
+  volatile uint32_t *h_flag = nullptr; uint32_t flag_seq = 0;
   cudaStream_t foreign = nullptr; // last caller-owned stream that used d_scratch / d_len (ordered by sync_foreign)
   // nearest-neighbour transfer plan (host side of image.c:293-325): byte offset of the source column each output
   // column samples, cached per (src_w, cols, flip_x)
@@ -71,7 +75,7 @@ struct ThreadCtx {
 };
 PeerHelper *peer_helper(ThreadCtx *cx, int device); // lazily created; makes `device` current.  nullptr => error set
 ThreadCtx *thread_ctx(); // nullptr => error set.  Leases a context on this thread's device and makes that device current
-// wait until everything queued on cx->stream has finished: short query spin, then a blocking (sleeping) wait
+// wait until everything queued on cx->stream has finished, in the way acb200_set_sync_mode selected
 int wait_stream(ThreadCtx *cx);
 // d_scratch / d_len are about to be used on `st`: first drain the caller-owned stream that used them last, if different
 int sync_foreign(ThreadCtx *cx, cudaStream_t st);

@@ -126,6 +126,9 @@ int ws_ring_depth(int mode, int cols, int src_w, uint32_t row_pitch);
 cudaError_t launch_stitch(const StitchParams &p, int n_frames, cudaStream_t st);
 cudaError_t launch_resize_nn_only(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh, int pregathered,
                                   cudaStream_t st);
+// NN sampling, one CTA per sampled row (whole rows read with 16-byte loads, any alignment): dst = cols x rows RGB24
+cudaError_t launch_gather_nn_rows(const uint8_t *src_dev, int sw, int sh, int cols, int rows, int flip_x, int flip_y,
+                                      uint8_t *dst, cudaStream_t st);
 // Floyd–Steinberg 16-colour background renderer (serial wavefront): one CTA per frame, reads the resized image
 // fg_only: print the dithered colour as the foreground (the two foreground-only leaf printers) instead of bg + contrast fg
 cudaError_t launch_dither_bg(const uint8_t *cells, int w, int h, int n_frames, int pad_left, const GlyphLut *lut,

@@ -149,6 +149,55 @@ __global__ void k_resize_nn(const uint8_t *src, int sw, int sh, uint8_t *dst, in
   }
 }
 
+// ------------------------------------------------------------------ NN sampling, a CTA per sampled row
+// image_resize's sampling (image.c:293-325): one CTA per SAMPLED source row reads the whole row with 16-byte loads,
+// parks it in shared memory and writes the row's `cols` sampled pixels.  Used behind the copy engine when a frame lives
+// in page-locked host memory (engine.cu: the rows NN reads are fetched by strided 2-D copies, this kernel then samples
+// the columns at 1:1 in y).  It also runs on rows in mapped host memory directly, but the SMs' PCIe reads are
+// sector-sized: 9.5 GB/s for a lone 4K frame (profiles/r02m_e2e_registered1.txt), which is why the copy engine does the
+// fetch.  Any alignment of `src`: the 16-byte chunks that lie wholly inside the row are loaded as vectors, the ragged
+// ends byte by byte (never a byte outside the row).
+__global__ void __launch_bounds__(256) k_gather_nn_rows(const uint8_t *src, int sw, int sh, int cols, int rows,
+                                                            uint32_t xr, uint32_t yr, int flip_x, int flip_y,
+                                                            uint8_t *dst) {
+  extern __shared__ uint4 s_row4[];
+  uint8_t *s_row = reinterpret_cast<uint8_t *>(s_row4);
+  const int y = blockIdx.x, tid = threadIdx.x;
+  uint32_t sy = ((uint32_t)y * yr) >> 16;
+  if (sy >= (uint32_t)sh) sy = (uint32_t)sh - 1u;
+  if (flip_y) sy = (uint32_t)sh - 1u - sy;
+  const size_t R = (size_t)sw * 3u;
+  const uint8_t *row = src + (size_t)sy * R;
+  const uintptr_t b = reinterpret_cast<uintptr_t>(row), e = b + R;
+  const uintptr_t a0 = b & ~(uintptr_t)15;              // s_row[i] mirrors the byte at a0 + i
+  const uintptr_t lo = (b + 15u) & ~(uintptr_t)15, hi = e & ~(uintptr_t)15;
+  if (lo < hi) {
+    for (uintptr_t a = lo + (uintptr_t)tid * 16u; a < hi; a += 256u * 16u) {
+      uint4 v;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "l"(a));
+      *reinterpret_cast<uint4 *>(s_row + (a - a0)) = v;
+    }
+    if ((uintptr_t)tid < lo - b) s_row[(b - a0) + tid] = row[tid];
+    if (tid >= 32 && (uintptr_t)(tid - 32) < e - hi) s_row[(hi - a0) + (tid - 32)] = *reinterpret_cast<const uint8_t *>(hi + (tid - 32));
+  } else {
+    for (size_t i = tid; i < R; i += 256) s_row[(b - a0) + i] = row[i];
+  }
+  __syncthreads();
+  const uint8_t *q0 = s_row + (b - a0);
+  for (int x = tid; x < cols; x += 256) {
+    uint32_t sx = ((uint32_t)x * xr) >> 16;
+    if (sx >= (uint32_t)sw) sx = (uint32_t)sw - 1u;
+    if (flip_x) sx = (uint32_t)sw - 1u - sx;
+    const uint8_t *q = q0 + sx * 3u;
+    uint8_t *d = dst + ((size_t)y * cols + x) * 3u;
+    d[0] = q[0];
+    d[1] = q[1];
+    d[2] = q[2];
+  }
+}
+
 // ------------------------------------------------------------------ pixel-space composite cell (stream.c:723-773)
 __global__ void k_composite_cell(const uint8_t *src, int sw, int sh, uint8_t *comp, int cw, int ch, int tw, int th,
                                  int x0, int y0, int cellw, int cellh) {
@@ -383,6 +432,16 @@ cudaError_t launch_resize_nn_only(const uint8_t *src, int sw, int sh, uint8_t *d
   if (grid > 148u * 16u) grid = 148u * 16u;
   if (grid == 0) grid = 1;
   k_resize_nn<<<grid, 256, 0, st>>>(src, sw, sh, dst, dw, dh, pregathered);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_nn_rows(const uint8_t *src_dev, int sw, int sh, int cols, int rows, int flip_x, int flip_y,
+                                      uint8_t *dst, cudaStream_t st) {
+  const uint32_t xr = (uint32_t)((((uint64_t)sw << 16) / (uint64_t)cols) + 1);
+  const uint32_t yr = (uint32_t)((((uint64_t)sh << 16) / (uint64_t)rows) + 1);
+  const size_t smem = (size_t)sw * 3u + 32u;
+  if (smem > 48u * 1024u) return cudaErrorInvalidValue; // callers keep such rows on the staged plan
+  k_gather_nn_rows<<<(unsigned)rows, 256, smem, st>>>(src_dev, sw, sh, cols, rows, xr, yr, flip_x, flip_y, dst);
   return cudaGetLastError();
 }
 

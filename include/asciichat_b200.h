@@ -222,10 +222,27 @@ int acb200_device_count(void);   /* devices in the pool (0 before initialisation
 int acb200_device_at(int k);     /* CUDA ordinal of the k-th pool device, -1 if out of range */
 int acb200_bind_thread(int k);
 int acb200_thread_device(void);  /* CUDA ordinal the calling thread is leased to (leases one if it has none), -1 on error */
-/* How a caller waits for its frame: 0 = spin (cudaStreamSynchronize; default — fastest on every box measured, see
- * profiles/r02a_e2e_sweep_pixels.txt), 1 = sleep on a blocking-sync event, 2 = poll for spin_us microseconds, then sleep.
- * Sleeping callers leave their cores to the other render threads at the price of the wake-up latency. */
+/* How a caller waits for its frame: 0 = spin (cudaStreamSynchronize), 1 = sleep on a blocking-sync event, 2 = poll for
+ * spin_us microseconds, then sleep, 3 = poll a completion word the stream writes into mapped memory and sched_yield()
+ * between polls.  Sleeping callers leave their cores to the other render threads at the price of the wake-up latency
+ * (profiles/r02a_e2e_sweep_pixels.txt); yielding callers give the core up only while another thread wants it. */
 void acb200_set_sync_mode(int mode, int spin_us);
+/* Frames in page-locked memory.  The drop-in calls take frames from ordinary (pageable) memory: the calling thread then
+ * gathers the pixels nearest-neighbour sampling will read (image.c:293-325) into the library's pinned staging, which is
+ * most of the call's host time.  A host that keeps its frame buffers for a while — the server's per-client
+ * video_frame_buffer_t double buffers (lib/video/rgba/video_frame.c), a capture ring — can page-lock them ONCE:
+ * acb200_register_host_memory(base, bytes) (cudaHostRegister, portable + mapped: a multi-millisecond call, not for the
+ * frame loop) makes every frame inside [base, base + bytes) readable by the GPUs, and the calls then let the device
+ * fetch the sampled rows itself.  Unregister before the memory is freed.  acb200_set_fetch_depth(k): at most k calls
+ * per GPU use the device-side fetch at a time (it moves whole source rows over PCIe, 12 x the gathered bytes at 4K),
+ * the others gather on their cores; -1 = always, 0 = never; default 3. */
+int acb200_register_host_memory(void *base, size_t bytes);
+int acb200_unregister_host_memory(void *base);
+void acb200_set_fetch_depth(int depth);
+/* Where the host time of the drop-in / batch-host calls went since the last reset, summed over all calling threads:
+ * out[0..3] = nanoseconds spent gathering/staging the input, enqueueing (copies + launches), waiting for the device,
+ * copying the strings into allocator-owned memory; out[4] = frames.  reset != 0 clears the counters. */
+void acb200_host_phase_stats(uint64_t out[5], int reset);
 void acb200_shutdown(void);
 int acb200_last_error(void);            /* thread-local, cleared on read */
 const char *acb200_last_error_message(void);

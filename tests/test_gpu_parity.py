@@ -546,7 +546,8 @@ def test_crc32c_lengths_and_fixup_device(acb, ob, golden):
     frames, the golden CRCs; and the trailing-reset cut of stream.c:1085-1127 on synthetic strings"""
     import torch
     lens = [0, 1, 3, 63, 64, 65, 127, 128, 255, 256, 257, 319, 320, 4095, 16383, 16384, 16385, 32768, 65535, 65536,
-            65537, 65600, 100001, 131072, 1180548]
+            65537, 65600, 100001, 131072, 1180548,
+            15, 16, 17, 511, 512, 513, 527, 528, 1023, 1024, 1025, 2047, 2048, 2049, 4096 + 16, 512 * 5 - 1, 512 * 5 + 31]
     pitch = (max(lens) + 1 + 15) & ~15
     arena = np.zeros((len(lens), pitch), np.uint8)
     data = []
@@ -566,6 +567,25 @@ def test_crc32c_lengths_and_fixup_device(acb, ob, golden):
         assert hdr[i].tobytes() == ob.port_packet_header(data[i], 320, 96), L
         if L in by_len:
             assert hdr[i].tobytes().hex() == by_len[L]["header"], L
+
+    # many frames of unrelated lengths in one arena: the row kernel's warps take equal shares of ROWS, so their runs
+    # start and end anywhere, straddle frames and skip frames without a full row; the plan's scan spans several blocks
+    rng = np.random.default_rng(5)
+    for n, hi in ((2500, 3000), (37, 70000), (1, 5000), (300, 700)):
+        lens2 = rng.integers(0, hi, n)
+        pitch = (int(lens2.max()) + 1 + 15) & ~15
+        arena = rng.integers(0, 256, (n, pitch), dtype=np.uint8)
+        d_out = torch.from_numpy(arena).cuda()
+        d_len = torch.tensor(lens2, dtype=torch.int32, device="cuda")
+        d_hdr = torch.zeros(n * 24, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        acb.frame_packets_device(d_out.data_ptr(), pitch, d_len.data_ptr(), n, 7, 9, d_hdr.data_ptr(), None)
+        acb.synchronize()
+        hdr = d_hdr.cpu().numpy().reshape(n, 24)
+        for i in range(n):
+            m = arena[i, :lens2[i]].tobytes()
+            assert int.from_bytes(hdr[i, 16:20].tobytes(), "big") == ob.port().orc_crc32c(m, len(m)), (n, i, lens2[i])
+            assert int.from_bytes(hdr[i, 8:12].tobytes(), "big") == lens2[i]
 
     rst = b"\x1b[0m"
     cases = [b"", b"abc", rst, b"row" + rst, b"ab" + rst + b"cd", rst + b"x" * 1000, b"y" * 700 + rst + b"z" * 3,

@@ -152,6 +152,54 @@ def test_nn_transfer_plans(acb, ob):
             assert got == exp, (W, H, c, r, fx, fy, filt, level, mode)
 
 
+def test_device_fetch_from_registered_frames(acb, ob):
+    """frames in page-locked memory (acb200_register_host_memory): the copy engine fetches the rows nearest-neighbour
+    sampling reads (strided 2-D copies), k_gather_nn_rows samples the columns — same bytes as the host-gathered plan and
+    the reference, at every alignment of the frame, with the display flips, with the fetch forced (-1), rationed (1)
+    and off (0); geometries whose sampled rows are no small set of arithmetic progressions keep the host gather"""
+    chk = ob.ref_display_convert if ob.ref() is not None else ob.port_display_convert
+    L = acb.lib()
+    buf = np.zeros(3840 * 2160 * 3 + 4096, np.uint8)
+    assert L.acb200_register_host_memory(buf.ctypes.data, buf.nbytes) == 0, acb.last_error()
+    assert L.acb200_register_host_memory(buf.ctypes.data, buf.nbytes) == 0  # idempotent
+    try:
+        n = 0
+        for (W, H, c, r), off in itertools.product(((640, 480, 80, 24), (97, 301, 40, 40), (3840, 2160, 320, 96),
+                                                    (5, 3, 4, 2), (2, 700, 1, 9), (1023, 77, 333, 20)), (0, 1, 7, 16, 61)):
+            img = buf[off:off + W * H * 3].reshape(H, W, 3)
+            img[...] = ob.gen("noise", W, H, 9 + off)
+            for fx, fy, filt, (level, mode) in itertools.product((False, True), (False, True), (0, 3), ((3, 2), (2, 0))):
+                exp = chk(img, c, r, level, mode, "standard", flip_x=fx, flip_y=fy, color_filter=filt, time_s=0.7)
+                launches = {}
+                for depth in (-1, 1, 0):
+                    L.acb200_set_fetch_depth(depth)
+                    before = acb.launch_count()
+                    got = acb.display_convert(img, c, r, acb.make_caps(level, mode), False, False, "standard", fx, fy,
+                                              filt, 0.7)
+                    launches[depth] = acb.launch_count() - before
+                    assert got == exp, (W, H, c, r, off, depth, fx, fy, filt, level, mode)
+                    n += 1
+                # the sampling kernel ran when it was allowed to (pixel-granular plan, rows in progressions), never else
+                assert launches[-1] == launches[1] and launches[-1] - launches[0] in (0, 1), (W, c, launches)
+                if (W, H) in ((640, 480), (3840, 2160)):  # 480 -> 24/48 rows: every 20th/10th; 2160 -> 96/192: period 4
+                    assert launches[-1] == launches[0] + 1, (W, H, c, r, launches)
+        assert n == 6 * 5 * 3 * 2 * 2 * 2 * 2
+        # a batch whose frames are all registered, and one with a pageable frame in it (falls back as a whole)
+        cfg = acb.make_cfg(640, 480, 80, 48, 3, 2)
+        L.acb200_set_fetch_depth(-1)
+        a = buf[0:640 * 480 * 3].reshape(480, 640, 3)
+        b = buf[1000000:1000000 + 640 * 480 * 3].reshape(480, 640, 3)
+        a[...] = ob.gen("bars", 640, 480, 1)
+        b[...] = ob.gen("noise", 640, 480, 2)
+        conv = ob.ref_convert if ob.ref() is not None else ob.port_convert
+        want = [conv(x, 80, 24, 3, 2, "standard") for x in (a, b)]
+        assert acb.render_batch_host(cfg, [a, b]) == want
+        assert acb.render_batch_host(cfg, [a, np.array(b)]) == want
+    finally:
+        L.acb200_set_fetch_depth(3)
+        assert L.acb200_unregister_host_memory(buf.ctypes.data) == 0, acb.last_error()
+
+
 def test_grid_frame_single_device(acb, ob):
     """acb200_grid_frame (host.c:664-717 with resident sources) on a pool of one device"""
     conv = ob.ref_convert if ob.ref() is not None else ob.port_convert
