@@ -158,8 +158,8 @@ constexpr int CRC_NT = 256, CRC_SEG = 256, CRC_CHUNK = CRC_NT * CRC_SEG; // 64 K
 constexpr int CRC_ROW = 512;          // row kernel: bytes a warp consumes per step (32 lanes x 16 bytes)
 constexpr int CRC_ROWPOW = 4096;      // rows covered by the constant shift table (2 MB frames; longer ones square-and-multiply)
 constexpr int CRC_NSETS = 7;          // slice tables: multiply by x^32, x^128, x^256, x^512, x^1024, x^2048, x^4096
-constexpr int CRC_ROWS_NT = 1024;     // row kernel: threads per CTA (one CTA per SM: 152 KB of tables)
-constexpr size_t CRC_ROWS_SMEM = (size_t)(4 * 256 * 32 + 6 * 4 * 256) * sizeof(uint32_t);
+constexpr int CRC_ROWS_NT = 1024;     // row kernel: threads per CTA (one CTA per SM: 152 KB of tables + 64 KB of rows in flight)
+constexpr size_t CRC_ROWS_SMEM = (size_t)(4 * 256 * 32 + 6 * 4 * 256) * sizeof(uint32_t) + (size_t)32 * 4 * 512; // tables + row ring
 
 struct CrcTables {
   uint32_t x2n[32];   // x^(2^k) mod P, reflected
@@ -414,9 +414,10 @@ __global__ void __launch_bounds__(1024) k_crc32c_plan(const uint32_t *out_len, i
 __global__ void __launch_bounds__(CRC_ROWS_NT, 1) k_crc32c_rows(const uint8_t *out, size_t out_pitch, int n_frames,
                                                                uint32_t *words, const uint32_t *slices,
                                                                uint8_t *copy_dst, size_t copy_pitch) {
-  extern __shared__ uint32_t s_crc[];
+  extern __shared__ __align__(16) uint32_t s_crc[];
   uint32_t *A = s_crc;                  // [4][256][32]: x^4096, lane-private
   uint32_t *S = s_crc + 4 * 256 * 32;   // [6][4][256]: x^32, x^128 .. x^2048
+  uint4 *R = reinterpret_cast<uint4 *>(s_crc + 4 * 256 * 32 + 6 * 4 * 256); // [32 warps][4 slots][32 lanes]: row ring
   uint32_t *acc = words;
   const uint32_t *prefix = words + n_frames;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -453,28 +454,44 @@ __global__ void __launch_bounds__(CRC_ROWS_NT, 1) k_crc32c_rows(const uint8_t *o
     uint4 *dst = copy_dst ? reinterpret_cast<uint4 *>(copy_dst + (size_t)f * copy_pitch + (size_t)r0 * CRC_ROW) + lane : nullptr;
     const int n = (int)(r1 - r0);
     uint32_t t0 = 0u, t1 = 0u, t2 = 0u, t3 = 0u;
-    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    // four rows in flight per warp: with 32 warps a step comes round every few hundred cycles, DRAM takes longer
-    uint4 q0 = ld_stream16(src), q1 = n > 1 ? ld_stream16(src + 32) : zero, q2 = n > 2 ? ld_stream16(src + 64) : zero,
-          q3 = n > 3 ? ld_stream16(src + 96) : zero;
-    auto step = [&](const uint4 &v, int k) {
+    // Four rows in flight per warp, staged through a private ring in shared memory by cp.async: the copy of row k + 4
+    // is issued when row k is taken out, a full four steps (~2500 issue cycles with 32 warps) before it is needed, and
+    // it occupies no registers while it flies.  (With the rows loaded into registers the compiler gathered the four
+    // loads of a group at the group's end — one step of distance or less, 2.6 warps per issue waiting on the long
+    // scoreboard, 4.2 TB/s: profiles/r02o_ncu_crc_rows_summary.txt.)
+    uint4 *slot0 = R + ((tid >> 5) * 4) * 32 + lane; // this lane's 16 bytes of slot 0; slot j is 512 bytes on
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(slot0);
+    auto fetch = [&](int k, int j) { // row k -> slot j = k & 3 (an empty group when the row does not exist: the count stays uniform)
+      if (k < n)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (uint32_t)j * 512u), "l"(src + (size_t)k * 32)
+                     : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto step = [&](int k, int j) {
+      asm volatile("cp.async.wait_group 3;" ::: "memory"); // all but the three youngest groups: row k has landed
+      const uint4 v = slot0[j * 32];
+      fetch(k + 4, j);
       if (dst) dst[(size_t)k * 32] = v;
       t0 = z_private(Al, t0) ^ v.x;
       t1 = z_private(Al, t1) ^ v.y;
       t2 = z_private(Al, t2) ^ v.z;
       t3 = z_private(Al, t3) ^ v.w;
     };
-    for (int k = 0; k < n; k += 4) {
-      const uint4 *nx = src + (size_t)(k + 4) * 32;
-      step(q0, k);
-      q0 = k + 4 < n ? ld_stream16(nx) : zero;
-      if (k + 1 < n) step(q1, k + 1);
-      q1 = k + 5 < n ? ld_stream16(nx + 32) : zero;
-      if (k + 2 < n) step(q2, k + 2);
-      q2 = k + 6 < n ? ld_stream16(nx + 64) : zero;
-      if (k + 3 < n) step(q3, k + 3);
-      q3 = k + 7 < n ? ld_stream16(nx + 96) : zero;
+    fetch(0, 0);
+    fetch(1, 1);
+    fetch(2, 2);
+    fetch(3, 3);
+    int k = 0;
+    for (; k + 4 <= n; k += 4) {
+      step(k, 0);
+      step(k + 1, 1);
+      step(k + 2, 2);
+      step(k + 3, 3);
     }
+    if (k < n) step(k, 0);
+    if (k + 1 < n) step(k + 1, 1);
+    if (k + 2 < n) step(k + 2, 2);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // fold the 128 streams: words of a thread by Horner with x^32, lanes by a butterfly with x^128, x^256, ...
     uint32_t u = z_shared(S, z_shared(S, z_shared(S, t0) ^ t1) ^ t2) ^ t3;
 #pragma unroll
@@ -515,16 +532,28 @@ __global__ void __launch_bounds__(32) k_crc32c_tail(const uint8_t *out, size_t o
   uint32_t c = 0u;
   const uint32_t b0 = 16u * lane, b1 = b0 + 16u < r ? b0 + 16u : r;
   if (b0 < r) {
+    // one 16-byte load (the arena's pitch is a multiple of 16, so the bytes behind the string's end exist), then the
+    // byte recurrence out of registers
+    const uint4 v = *reinterpret_cast<const uint4 *>(tail + b0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t cnt = b1 - b0;
     uint32_t st = 0u;
-    for (uint32_t i = b0; i < b1; i++) {
-      const uint8_t b = tail[i];
-      if (dst) dst[i] = b;
-      st = T[(st ^ b) & 255u] ^ (st >> 8);
+#pragma unroll
+    for (uint32_t i = 0; i < 16u; i++) {
+      const uint32_t b = (w[i >> 2] >> (8u * (i & 3u))) & 255u;
+      if (i < cnt) {
+        if (dst) dst[b0 + i] = (uint8_t)b;
+        st = T[(st ^ b) & 255u] ^ (st >> 8);
+      }
     }
     c = gf_mul(c_crc.bytepow[r - b1], st);
   }
   if (lane == 0) c ^= gf_mul(c_crc.bytepow[r], words[f]); // the full rows, shifted past the tail
-  if (lane == 1) c ^= gf_mul(gf_xpow8(c_crc.x2n, L), 0xFFFFFFFFu); // the initial value, shifted past the whole frame
+  if (lane == 1) { // the initial value, shifted past the whole frame: x^(8 L) = x^(8 * 512 * rows) * x^(8 r)
+    const uint32_t nrow = L / CRC_ROW;
+    const uint32_t xr = nrow < (uint32_t)CRC_ROWPOW ? c_crc.rowpow[nrow] : gf_xpow8(c_crc.x2n, (uint64_t)nrow * CRC_ROW);
+    c ^= gf_mul(gf_mul(xr, c_crc.bytepow[r]), 0xFFFFFFFFu);
+  }
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, d);
   const uint32_t crc = ~c;

@@ -80,14 +80,13 @@ static std::atomic<unsigned> g_rr{0};
 // (DESIGN §9): mode 3 spins only while nobody else wants the core.
 static std::atomic<int> g_sync_mode{0}, g_spin_us{30};
 // Frames in page-locked host memory (acb200_register_host_memory, or cudaHostAlloc'd by the caller) need no host-side
-// gather: the COPY ENGINE fetches the source rows nearest-neighbour sampling reads (2.2 MB of a 4K frame, as a few
-// strided 2-D copies) and a small kernel samples the columns on the device.  That frees the caller's core — the gather
-// is 130-250 us of a ~330 us call, profiles/r02l_e2e_inproc2.txt — but the link carries 12 x the bytes of the
-// host-gathered plan (0.18 MB), so it is used for at most this many calls per GPU at a time and the rest keep
-// gathering on their cores: -1 = always, 0 = never.  (Letting the SMs read the rows out of mapped host memory instead
-// was measured first: 9.5 GB/s for a frame on its own, ~34 GB/s with 24 callers — sector-sized PCIe reads;
-// profiles/r02m_e2e_registered1.txt.)
-static std::atomic<int> g_fetch_depth{3};
+// gather: the GPU fetches the source rows nearest-neighbour sampling reads itself (2.2 MB of a 4K frame) and samples
+// the columns.  That frees the caller's core — the gather is 100-250 us of a ~330 us call, profiles/r02l_e2e_inproc2.txt
+// — but the link carries 12 x the bytes of the host-gathered plan (0.18 MB) and tops out at 13-15 k frames/s per GPU,
+// below what 16 gathering cores deliver (34 k, bounded by the strings going the other way).  So it pays where cores
+// are scarcer than GPUs, and the depth rations it: at most this many calls per GPU fetch at a time, the rest gather
+// on their cores; -1 = always, 0 = never (default; acb200_set_fetch_depth / ACB200_FETCH_DEPTH).
+static std::atomic<int> g_fetch_depth{0};
 // cuStreamWriteValue32 through the runtime's driver-entry-point lookup (the library links no libcuda symbol directly)
 typedef int (*StreamWriteValue32)(cudaStream_t, unsigned long long, uint32_t, unsigned);
 static StreamWriteValue32 g_write_value32 = nullptr;
@@ -950,6 +949,18 @@ static void row_schedule(RowSchedule &rs, int src_h, int rows, bool flip_y) {
   }
 }
 
+// Who fetches: 1 = k_gather_nn_rows reads the rows out of the mapped host memory itself (default: one launch, any
+// geometry, 34 GB/s of source rows per link with 16 callers), 2 = the same with 256-byte L2 fetches (no difference
+// measured), 0 = the copy engine moves the rows as strided 2-D copies and the kernel samples the columns on the device
+// (28 GB/s: four copies per frame serialise on the engine).  profiles/r02o_fetch_variants.txt.  ACB200_FETCH=ce|sm|sm256.
+static int fetch_kind() {
+  static const int kind = [] {
+    const char *e = getenv("ACB200_FETCH");
+    return !e ? 1 : !strcmp(e, "ce") ? 0 : !strcmp(e, "sm256") ? 2 : 1;
+  }();
+  return kind;
+}
+
 struct FetchSlot { // one of the per-GPU "the device fetches my frame" slots (g_fetch_depth), released on scope exit
   std::atomic<int> *ctr = nullptr;
   bool held = false;
@@ -1004,7 +1015,7 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
     for (int i = 0; i < n_frames && all_pinned; i++) all_pinned = frames[i] && is_pinned(frames[i]);
     if (all_pinned) {
       row_schedule(rsched, cfg.src_h, cfg.rows_px, flip_y);
-      if (rsched.P > 0) fetch.try_take(&g_ds[cx->device].fetch_inflight);
+      if (rsched.P > 0 || fetch_kind() != 0) fetch.try_take(&g_ds[cx->device].fetch_inflight);
     }
   }
   const bool dev_fetch = fetch.held;
@@ -1070,7 +1081,14 @@ static int render_batch_host_impl(const acb200_render_cfg_t &cfg, const uint8_t 
       if (!src) return set_error(E_INVALID_PARAM, "frame %d is NULL", f0 + i);
       uint8_t *dst = d_in + (size_t)i * in_pitch;
       uint8_t *st = st_base ? st_base + (size_t)i * in_pitch : nullptr;
-      if (dev_fetch) {
+      if (dev_fetch && fetch_kind() != 0) {
+        // measurement knob: the SMs read the rows out of mapped host memory themselves (one launch, any geometry)
+        const uint8_t *src_dev = pinned_dev_ptr(src);
+        if (!src_dev) return set_error(E_INVALID_STATE, "frame %d is not page-locked", f0 + i);
+        ACB_CUDA(launch_gather_nn_rows(src_dev, cfg.src_w, cfg.src_h, cfg.cols, cfg.rows_px, flip_x ? 1 : 0,
+                                       flip_y ? 1 : 0, dst, cx->stream, fetch_kind() == 2));
+        count_launch(1);
+      } else if (dev_fetch) {
         // copy engine: progression k = rows first[k], first[k] + D, ... of the frame -> rows k, k + P, ... of the list
         uint8_t *rows_dev = cx->d_rows + ((size_t)slot * chunk + i) * rows_per_frame;
         const int P = rsched.P;

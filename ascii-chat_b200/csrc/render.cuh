@@ -128,7 +128,7 @@ cudaError_t launch_resize_nn_only(const uint8_t *src, int sw, int sh, uint8_t *d
                                   cudaStream_t st);
 // NN sampling, one CTA per sampled row (whole rows read with 16-byte loads, any alignment): dst = cols x rows RGB24
 cudaError_t launch_gather_nn_rows(const uint8_t *src_dev, int sw, int sh, int cols, int rows, int flip_x, int flip_y,
-                                      uint8_t *dst, cudaStream_t st);
+                                  uint8_t *dst, cudaStream_t st, int wide = 0);
 // Floyd–Steinberg 16-colour background renderer (serial wavefront): one CTA per frame, reads the resized image
 // fg_only: print the dithered colour as the foreground (the two foreground-only leaf printers) instead of bg + contrast fg
 cudaError_t launch_dither_bg(const uint8_t *cells, int w, int h, int n_frames, int pad_left, const GlyphLut *lut,

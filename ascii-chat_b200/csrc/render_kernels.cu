@@ -157,9 +157,10 @@ __global__ void k_resize_nn(const uint8_t *src, int sw, int sh, uint8_t *dst, in
 // sector-sized: 9.5 GB/s for a lone 4K frame (profiles/r02m_e2e_registered1.txt), which is why the copy engine does the
 // fetch.  Any alignment of `src`: the 16-byte chunks that lie wholly inside the row are loaded as vectors, the ragged
 // ends byte by byte (never a byte outside the row).
+template <bool WIDE>
 __global__ void __launch_bounds__(256) k_gather_nn_rows(const uint8_t *src, int sw, int sh, int cols, int rows,
-                                                            uint32_t xr, uint32_t yr, int flip_x, int flip_y,
-                                                            uint8_t *dst) {
+                                                        uint32_t xr, uint32_t yr, int flip_x, int flip_y,
+                                                        uint8_t *dst) {
   extern __shared__ uint4 s_row4[];
   uint8_t *s_row = reinterpret_cast<uint8_t *>(s_row4);
   const int y = blockIdx.x, tid = threadIdx.x;
@@ -174,9 +175,14 @@ __global__ void __launch_bounds__(256) k_gather_nn_rows(const uint8_t *src, int 
   if (lo < hi) {
     for (uintptr_t a = lo + (uintptr_t)tid * 16u; a < hi; a += 256u * 16u) {
       uint4 v;
-      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                   : "l"(a));
+      if (WIDE) // rows in mapped host memory: ask the L2 for 256-byte fetches (fewer, larger PCIe reads)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(a));
+      else
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(a));
       *reinterpret_cast<uint4 *>(s_row + (a - a0)) = v;
     }
     if ((uintptr_t)tid < lo - b) s_row[(b - a0) + tid] = row[tid];
@@ -436,12 +442,15 @@ cudaError_t launch_resize_nn_only(const uint8_t *src, int sw, int sh, uint8_t *d
 }
 
 cudaError_t launch_gather_nn_rows(const uint8_t *src_dev, int sw, int sh, int cols, int rows, int flip_x, int flip_y,
-                                      uint8_t *dst, cudaStream_t st) {
+                                  uint8_t *dst, cudaStream_t st, int wide) {
   const uint32_t xr = (uint32_t)((((uint64_t)sw << 16) / (uint64_t)cols) + 1);
   const uint32_t yr = (uint32_t)((((uint64_t)sh << 16) / (uint64_t)rows) + 1);
   const size_t smem = (size_t)sw * 3u + 32u;
   if (smem > 48u * 1024u) return cudaErrorInvalidValue; // callers keep such rows on the staged plan
-  k_gather_nn_rows<<<(unsigned)rows, 256, smem, st>>>(src_dev, sw, sh, cols, rows, xr, yr, flip_x, flip_y, dst);
+  if (wide)
+    k_gather_nn_rows<true><<<(unsigned)rows, 256, smem, st>>>(src_dev, sw, sh, cols, rows, xr, yr, flip_x, flip_y, dst);
+  else
+    k_gather_nn_rows<false><<<(unsigned)rows, 256, smem, st>>>(src_dev, sw, sh, cols, rows, xr, yr, flip_x, flip_y, dst);
   return cudaGetLastError();
 }
 

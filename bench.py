@@ -174,6 +174,77 @@ def thread_candidates(ncores, n_gpus):
                                   (3 * ncores) // 2)]
 
 
+SYNC_NAMES = {0: "spin", 1: "block", 2: "hybrid", 3: "yield"}
+
+
+def pick_config(lib, H, fn_ptr, frames, caps, combos, seconds=0.5):
+    """probe (caller threads, fetch depth, wait mode) combinations briefly (untimed region), keep the fastest"""
+    best, probes = None, []
+    for (t, depth, sync) in combos:
+        lib.acb200_set_fetch_depth(depth)
+        lib.acb200_set_sync_mode(sync, 30)
+        r = run_callers(H, fn_ptr, frames, caps, t, seconds)
+        fps = r["calls"] / r["seconds"]
+        probes.append({"threads": t, "fetch_depth": depth, "wait": SYNC_NAMES[sync], "fps": round(fps)})
+        if best is None or fps > best[0]:
+            best = (fps, t, depth, sync)
+    return best[1:], probes
+
+
+def e2e_api_legs(acb, H, frames, caps, n_gpus, seconds):
+    """The drop-in call end to end, two ways.  `pageable`: frames in ordinary memory — the calling thread gathers the
+    sampled pixels (0.18 MB per 4K frame cross PCIe).  `registered`: the SAME frames page-locked once, untimed
+    (acb200_register_host_memory — what a server does with its per-client frame buffers): a call may then let the
+    device fetch the sampled rows (2.2 MB per frame) and spend no core time on the input at all.  Caller threads, wait
+    mode and — registered — whether the fetch is used are probed per box: hosts with few cores per GPU win with the
+    fetch, hosts with many do not (profiles/r02n_e2e_registered*.txt)."""
+    lib = acb.lib()
+    fn = C.cast(lib.ascii_convert_with_capabilities, C.c_void_p)
+    lib.acb200_set_default_scale(acb.SCALE_NN)
+    ncores = os.cpu_count() or 1
+    cand = sorted(set(thread_candidates(ncores, n_gpus)))
+
+    def measure(cfg3, probes):
+        t, depth, sync = cfg3
+        lib.acb200_set_fetch_depth(depth)
+        lib.acb200_set_sync_mode(sync, 30)
+        ph = (C.c_uint64 * 5)()
+        lib.acb200_host_phase_stats(ph, 1)
+        r = run_callers(H, fn, frames, caps, t, seconds)
+        lib.acb200_host_phase_stats(ph, 1)
+        fp = H.harness_ring_fingerprint(fn, frames.ctypes.data, frames.shape[0], SRC_W, SRC_H, COLS, ROWS,
+                                        C.byref(caps), PALETTE)
+        r.update({"threads": t, "fetch_depth": depth, "wait": SYNC_NAMES[sync], "probes": probes, "n_gpus": n_gpus,
+                  "ring_fingerprint": "%016x" % fp,
+                  "host_us_per_call": {k: round(ph[i] / max(1, ph[4]) / 1e3, 1)
+                                       for i, k in enumerate(("gather", "enqueue", "wait", "copy_out"))}})
+        return r
+
+    # pageable frames: caller count first (spinning wait), then the yielding wait at the best count
+    (t0, _, _), p1 = pick_config(lib, H, fn, frames, caps, [(t, 0, 0) for t in cand])
+    best_pg, p2 = pick_config(lib, H, fn, frames, caps, [(t0, 0, 0), (t0, 0, 3), (min(2 * t0, 2 * ncores), 0, 3)])
+    pageable = measure(best_pg, p1 + p2)
+    one = run_callers(H, fn, frames, caps, 1, 1.0, warm_calls=8)
+    pageable["single_caller_ms"] = 1e3 * one["seconds"] / one["calls"]
+    # the same frames page-locked
+    registered = None
+    if lib.acb200_register_host_memory(frames.ctypes.data, frames.nbytes) == 0:
+        fetch_t = sorted(set(max(2, c) for c in (ncores // 2, ncores, (3 * ncores) // 2, 2 * ncores)))
+        best_rg, p3 = pick_config(lib, H, fn, frames, caps,
+                                  [best_pg] + [(t, -1, w) for t in fetch_t for w in (0, 3)])
+        registered = measure(best_rg, p3)
+        lib.acb200_set_fetch_depth(-1)
+        lib.acb200_set_sync_mode(0, 30)
+        one = run_callers(H, fn, frames, caps, 1, 1.0, warm_calls=8)
+        registered["single_caller_ms_fetch"] = 1e3 * one["seconds"] / one["calls"]
+        lib.acb200_unregister_host_memory(frames.ctypes.data)
+    else:
+        acb.last_error()
+    lib.acb200_set_fetch_depth(0)
+    lib.acb200_set_sync_mode(0, 30)
+    return {"pageable": pageable, "registered": registered, "launches": acb.launch_count()}
+
+
 def reference_entry():
     """(fn pointer, caps struct, kind) of the reference's own CPU implementation: oracle/_ref, else the port shim"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -381,7 +452,7 @@ def device_extras_leg(acb, torch, d_out, cap, d_len, n, peak):
     ms = timed(lambda: acb.frame_packets_device(d_out.data_ptr(), cap, d_len.data_ptr(), n, COLS, ROWS,
                                                 d_hdr.data_ptr(), st), 10)
     sbytes = int(d_len.sum().item())
-    out["frame_packets"] = {"kernels": "k_crc32c_chunks + k_crc32c_finish", "frames": n, "string_bytes": sbytes,
+    out["frame_packets"] = {"kernels": "k_crc32c_plan + k_crc32c_rows + k_crc32c_tail", "frames": n, "string_bytes": sbytes,
                             "ms_per_batch": ms, "GBs_of_string_bytes": sbytes / (ms * 1e-3) / 1e9,
                             "note": "CRC32-C (lib/network/crc32.c) + 24-byte ascii_frame_packet_t per frame "
                                     "(acip/server.c:203-214)"}
@@ -596,23 +667,13 @@ def c4_inprocess(n_gpus):
 
 
 def e2e_inprocess(n_gpus, threads, seconds):
-    """ONE process, n_gpus GPUs behind the C ABI, `threads` caller threads leased round-robin to the GPUs"""
+    """ONE process, n_gpus GPUs behind the C ABI, caller threads leased round-robin to the GPUs"""
     import ascii_chat_b200 as acb
     assert acb.init_devices(list(range(n_gpus))) == 0, acb.last_error()
     H = load_harness()
     frames = host_ring()
     caps = acb.make_caps(LEVEL, MODE)
-    fn = C.cast(acb.lib().ascii_convert_with_capabilities, C.c_void_p)
-    acb.lib().acb200_set_default_scale(acb.SCALE_NN)
-    probes = None
-    if threads <= 0:
-        threads, probes = pick_threads(H, fn, frames, caps, thread_candidates(os.cpu_count() or 1, n_gpus))
-    r = run_callers(H, fn, frames, caps, threads, seconds)
-    fp = H.harness_ring_fingerprint(fn, frames.ctypes.data, frames.shape[0], SRC_W, SRC_H, COLS, ROWS, C.byref(caps),
-                                    PALETTE)
-    one = run_callers(H, fn, frames, caps, 1, 1.0, warm_calls=8)
-    r.update({"threads": threads, "thread_probes_fps": probes, "n_gpus": n_gpus, "ring_fingerprint": "%016x" % fp,
-              "single_caller_ms": 1e3 * one["seconds"] / one["calls"], "launches": acb.launch_count()})
+    r = e2e_api_legs(acb, H, frames, caps, n_gpus, seconds)
     acb.lib().acb200_shutdown()
     return r
 
@@ -787,37 +848,37 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- end to end, one process per GPU: every rank drives its own GPU with its share of the caller threads
+    # ---- end to end through the drop-in call
     H = load_harness()
     frames = host_ring()
     caps = acb.make_caps(LEVEL, MODE)
     fn = C.cast(acb.lib().ascii_convert_with_capabilities, C.c_void_p)
     acb.lib().acb200_set_default_scale(acb.SCALE_NN)
-    probes = None
+    legs = per_rank = e_box = None
     if world == 1:
-        threads, probes = pick_threads(H, fn, frames, caps, thread_candidates(ncores, 1))
-    else:
-        threads = max(2, min(CALLERS_PER_GPU, ncores // world))
-    barrier()
-    e_nn = run_callers(H, fn, frames, caps, threads, 4.0)
-    barrier()
-    fp_nn = H.harness_ring_fingerprint(fn, frames.ctypes.data, frames.shape[0], SRC_W, SRC_H, COLS, ROWS,
-                                       C.byref(caps), PALETTE)
-    (nn_s,) = max_over_ranks([e_nn["seconds"]])
-    tc = torch.tensor([e_nn["calls"], e_nn["failures"]], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tc, op=dist.ReduceOp.SUM)
-    calls_nn_all, failures = float(tc[0]), int(tc[1])
-    e_box = one = None
-    if world == 1:
+        legs = e2e_api_legs(acb, H, frames, caps, 1, 4.0)
         acb.lib().acb200_set_default_scale(acb.SCALE_BOX)
-        e_box = run_callers(H, fn, frames, caps, threads, 3.0)
+        e_box = run_callers(H, fn, frames, caps, legs["pageable"]["threads"], 3.0)
         acb.lib().acb200_set_default_scale(acb.SCALE_NN)
-        one = run_callers(H, fn, frames, caps, 1, 1.0, warm_calls=8)  # what one render thread sees
+    else:
+        # one process per GPU (pageable frames): every rank drives its own GPU with its share of the caller threads
+        threads = max(2, min(CALLERS_PER_GPU, ncores // world))
+        barrier()
+        e_nn = run_callers(H, fn, frames, caps, threads, 4.0)
+        barrier()
+        fp_nn = H.harness_ring_fingerprint(fn, frames.ctypes.data, frames.shape[0], SRC_W, SRC_H, COLS, ROWS,
+                                           C.byref(caps), PALETTE)
+        (nn_s,) = max_over_ranks([e_nn["seconds"]])
+        tc = torch.tensor([e_nn["calls"], e_nn["failures"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+        per_rank = {"value": float(tc[0]) * MPIX / nn_s, "unit": "Mpix/s", "calls": int(tc[0]), "seconds": nn_s,
+                    "caller_threads_per_gpu": threads, "processes": world, "failures": int(tc[1]),
+                    "ring_fingerprint": "%016x" % fp_nn, "frames": "pageable"}
 
     # ---- BASELINE config 4 over NCCL (all ranks), then the single-process legs (rank 0; the others sleep)
     c4 = c4_nccl_leg(acb, torch, dist if world > 1 else _SingleRankDist(torch), rank, world)
-    e_in = rank0_alone("e2e_inproc", lambda: run_leg_subprocess("e2e-inprocess", world)) if world > 1 else None
+    if world > 1: # ONE process drives all the GPUs (a sub-process of rank 0; the other ranks sleep)
+        legs = rank0_alone("e2e_inproc", lambda: run_leg_subprocess("e2e-inprocess", world))
     c4_in = rank0_alone("c4_inproc", lambda: run_leg_subprocess("c4-inprocess", world))
 
     def rank0_tail():
@@ -825,25 +886,41 @@ def main():
         alg_bytes_launch = n * FRAME_BYTES  # 3 B per source pixel, x frames per launch
         achieved = alg_bytes_launch / (ms_kernel_max / args.steps * 1e-3) / 1e9
         value = world * args.steps * n * MPIX / (ms_total_max * 1e-3)
-        out_per_frame = int(e_nn["bytes"] / max(1, e_nn["calls"]))
-        gathered = COLS * ROWS * 2 * 3  # NN mode moves only the sampled pixels (pixel-granular transfer plan)
-        per_rank = {"value": calls_nn_all * MPIX / nn_s, "unit": "Mpix/s", "calls": int(calls_nn_all), "seconds": nn_s,
-                    "caller_threads_per_gpu": threads, "thread_probes_fps": probes, "processes": world,
-                    "failures": failures, "ring_fingerprint": "%016x" % fp_nn}
-        if world > 1 and e_in and "error" not in e_in:
-            e2e = {"value": e_in["calls"] * MPIX / e_in["seconds"], "unit": "Mpix/s", "calls": e_in["calls"],
-                   "seconds": e_in["seconds"], "caller_threads": e_in["threads"],
-                   "thread_probes_fps": e_in.get("thread_probes_fps"), "processes": 1,
-                   "failures": e_in["failures"], "ring_fingerprint": e_in["ring_fingerprint"],
-                   "structure": "ONE process, %d GPUs behind the C ABI (acb200_init_devices), caller threads leased "
-                                "round-robin" % world}
-        else:
-            e2e = dict(per_rank)
-            e2e["structure"] = "one process, one GPU" if world == 1 else "one process per GPU (in-process leg failed: %s)" % (e_in or {}).get("error")
-        e2e.update({"h2d_bytes_per_step": gathered, "d2h_bytes_per_step": out_per_frame + 4,
-                    "host_bytes_per_step": host_bytes_per_frame(out_per_frame), "step": "one frame through the call",
-                    "api": "ascii_convert_with_capabilities() — reference-exact nearest-neighbour mode, pageable host "
-                           "RGB24 in, malloc'd string out, same pthread harness as the reference arm"})
+        def e2e_record(r, frames_kind):
+            out_per_frame = int(r["bytes"] / max(1, r["calls"]))
+            fetched = r["fetch_depth"] != 0
+            # the host gather ships the sampled pixels; the device-side fetch reads the sampled ROWS over the link
+            h2d = ROWS * 2 * SRC_W * 3 if fetched else COLS * ROWS * 2 * 3
+            hb = host_bytes_per_frame(out_per_frame)
+            if fetched:  # no core touches the source; the DMA reads the rows
+                hb.update({"source_lines_read": 0, "staging_written": 0, "h2d_dma_read": h2d})
+                hb["total"] = h2d + 3 * out_per_frame
+            return {"value": r["calls"] * MPIX / r["seconds"], "unit": "Mpix/s", "calls": r["calls"],
+                    "seconds": r["seconds"], "frames_per_s": r["calls"] / r["seconds"], "caller_threads": r["threads"],
+                    "wait": r["wait"], "input": "the device fetches the sampled rows from the page-locked frame" if fetched else "the caller gathers the sampled pixels",
+                    "probes": r["probes"], "processes": 1, "failures": r["failures"],
+                    "ring_fingerprint": r["ring_fingerprint"], "host_us_per_call": r["host_us_per_call"],
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_per_frame + 4, "host_bytes_per_step": hb,
+                    "step": "one frame through the call", "frames": frames_kind,
+                    "structure": "one process, one GPU" if world == 1 else
+                    "ONE process, %d GPUs behind the C ABI (acb200_init_devices), caller threads leased round-robin" % world,
+                    "api": "ascii_convert_with_capabilities() — reference-exact nearest-neighbour mode, host RGB24 in, "
+                           "malloc'd string out, same pthread harness as the reference arm"}
+
+        if legs and "error" not in legs:
+            e2e_pg = e2e_record(legs["pageable"], "pageable host memory")
+            if legs.get("registered"):
+                e2e = e2e_record(legs["registered"], "the same frames page-locked once, outside the timed region "
+                                                     "(acb200_register_host_memory)")
+                e2e["single_caller_ms_fetch"] = legs["registered"].get("single_caller_ms_fetch")
+            else:
+                e2e = dict(e2e_pg)
+                e2e["note"] = "cudaHostRegister of the frame ring failed on this box: pageable frames"
+        else:  # the single-process leg failed: fall back to the per-rank-process numbers
+            e2e = dict(per_rank or {})
+            e2e.update({"h2d_bytes_per_step": COLS * ROWS * 2 * 3, "d2h_bytes_per_step": None,
+                        "structure": "one process per GPU (in-process leg failed: %s)" % (legs or {}).get("error")})
+            e2e_pg = None
         line = {
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
@@ -860,7 +937,9 @@ def main():
         }
         if sustained:
             line["sustained"] = sustained
-        if world > 1:
+        if e2e_pg:
+            line["e2e_pageable"] = e2e_pg
+        if per_rank:
             line["e2e_per_rank_processes"] = per_rank
         if e_box:
             line["e2e_box"] = {"value": e_box["calls"] * MPIX / e_box["seconds"], "unit": "Mpix/s",
@@ -869,9 +948,9 @@ def main():
                                "calls": e_box["calls"], "seconds": e_box["seconds"],
                                "api": "same call, acb200_set_default_scale(ACB200_SCALE_BOX): whole frames cross PCIe "
                                       "(24.9 MB per frame)"}
-        if one:
-            line["dropin_single_caller"] = {"ms_per_call": 1e3 * one["seconds"] / one["calls"],
-                                            "mpix_s": one["calls"] * MPIX / one["seconds"]}
+        if legs and "error" not in legs:
+            ms1 = legs["pageable"]["single_caller_ms"]
+            line["dropin_single_caller"] = {"ms_per_call": ms1, "mpix_s": MPIX / (ms1 * 1e-3)}
         line["c4"] = {"workload": "BASELINE config 4: %d clients x %dx%d -> %dx%d ANSI-256 -> %dx%d grid; pixel-space: "
                                   "the server compositor for %dx%d and %dx%d viewers" % (
                                       C4_N, C4_W, C4_H, C4_COLS, C4_ROWS, C4_GW, C4_GH, C4_COLS, C4_ROWS, C4_GW, C4_GH),

@@ -232,10 +232,10 @@ void acb200_set_sync_mode(int mode, int spin_us);
  * most of the call's host time.  A host that keeps its frame buffers for a while — the server's per-client
  * video_frame_buffer_t double buffers (lib/video/rgba/video_frame.c), a capture ring — can page-lock them ONCE:
  * acb200_register_host_memory(base, bytes) (cudaHostRegister, portable + mapped: a multi-millisecond call, not for the
- * frame loop) makes every frame inside [base, base + bytes) readable by the GPUs, and the calls then let the device
- * fetch the sampled rows itself.  Unregister before the memory is freed.  acb200_set_fetch_depth(k): at most k calls
- * per GPU use the device-side fetch at a time (it moves whole source rows over PCIe, 12 x the gathered bytes at 4K),
- * the others gather on their cores; -1 = always, 0 = never; default 3. */
+ * frame loop) makes every frame inside [base, base + bytes) readable by the GPUs.  Unregister before the memory is
+ * freed.  acb200_set_fetch_depth(k) then lets up to k calls per GPU at a time have the DEVICE fetch the sampled source
+ * rows (whole rows over PCIe: 12 x the gathered bytes at 4K, no core time), the others gather on their cores;
+ * -1 = always, 0 = never (default).  Worth it where cores are scarcer than GPUs. */
 int acb200_register_host_memory(void *base, size_t bytes);
 int acb200_unregister_host_memory(void *base);
 void acb200_set_fetch_depth(int depth);

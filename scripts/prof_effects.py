@@ -15,7 +15,7 @@ torch.cuda.synchronize()
 for _ in range(4):
     assert acb.color_filter_device(img.data_ptr(), 3840, k * 2160, 3840 * 3, 3) == 0
 acb.synchronize()
-n = 32
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 cfg = acb.make_cfg(3840, 2160, 320, 192, 3, 2, "standard", scale=acb.SCALE_BOX)
 cap = acb.frame_capacity(cfg)
 d_in = torch.randint(0, 256, (n, 2160, 3840, 3), dtype=torch.uint8, device="cuda")

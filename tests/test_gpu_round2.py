@@ -153,10 +153,10 @@ def test_nn_transfer_plans(acb, ob):
 
 
 def test_device_fetch_from_registered_frames(acb, ob):
-    """frames in page-locked memory (acb200_register_host_memory): the copy engine fetches the rows nearest-neighbour
-    sampling reads (strided 2-D copies), k_gather_nn_rows samples the columns — same bytes as the host-gathered plan and
-    the reference, at every alignment of the frame, with the display flips, with the fetch forced (-1), rationed (1)
-    and off (0); geometries whose sampled rows are no small set of arithmetic progressions keep the host gather"""
+    """frames in page-locked memory (acb200_register_host_memory): the device fetches the rows nearest-neighbour
+    sampling reads (k_gather_nn_rows on the mapped frame; ACB200_FETCH=ce: strided 2-D copies by the copy engine, then
+    the same kernel on the device copy) — same bytes as the host-gathered plan and the reference, at every alignment of
+    the frame, with the display flips, with the fetch forced (-1), rationed (1) and off (0)"""
     chk = ob.ref_display_convert if ob.ref() is not None else ob.port_display_convert
     L = acb.lib()
     buf = np.zeros(3840 * 2160 * 3 + 4096, np.uint8)
@@ -196,7 +196,7 @@ def test_device_fetch_from_registered_frames(acb, ob):
         assert acb.render_batch_host(cfg, [a, b]) == want
         assert acb.render_batch_host(cfg, [a, np.array(b)]) == want
     finally:
-        L.acb200_set_fetch_depth(3)
+        L.acb200_set_fetch_depth(0)
         assert L.acb200_unregister_host_memory(buf.ctypes.data) == 0, acb.last_error()
 
 
