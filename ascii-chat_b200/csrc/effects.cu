@@ -374,9 +374,35 @@ __global__ void __launch_bounds__(32) k_crc32c_finish(const uint32_t *part, int 
 // (constant-memory table of x^(4096 k)), is XORed into the frame's accumulator.  k_crc32c_tail (one warp per frame)
 // adds the < 512 bytes behind the last full row, applies the init / final complement and writes the header.
 //   words: acc[n_frames] | prefix[n_frames + 1]  (prefix = exclusive scan of full rows per frame)
-__device__ __forceinline__ uint32_t z_private(const uint32_t *Al, uint32_t t) { // Al = table + lane
-  return Al[(t & 255u) << 5] ^ Al[8192u + (((t >> 8) & 255u) << 5)] ^ Al[16384u + (((t >> 16) & 255u) << 5)] ^
-         Al[24576u + ((t >> 24) << 5)];
+// The integer pipes are the bound here (first capture: alu pipe 80 % busy, profiles/r02p_ncu_crc_rows_summary.txt):
+// LOP3 / SHF / PRMT / LEA all issue on the alu pipe at one warp instruction per two cycles, IMAD on the fma pipe at the
+// same rate.  A lookup therefore costs one PRMT (cut the state byte out: alu) and one IMAD (byte * 128 + table address:
+// fma; the factor lives in a register so that it stays a multiply), the four results fold with two three-input LOP3.
+__device__ __forceinline__ uint32_t lds_at(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+template <int OFF, bool PIN> __device__ __forceinline__ uint32_t lds_off(uint32_t addr) {
+  uint32_t v;
+  if (PIN) // volatile: keeps its place among the (volatile) row loads, see k_crc32c_rows<false>
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+  else
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// Al = shared-space BYTE address of (x^4096 table + lane); c128 = 128 in a register
+template <bool PIN> __device__ __forceinline__ uint32_t z_private(uint32_t Al, uint32_t c128, uint32_t t) {
+  const uint32_t a0 = mad_lo(__byte_perm(t, 0u, 0x4440), c128, Al);
+  const uint32_t a1 = mad_lo(__byte_perm(t, 0u, 0x4441), c128, Al);
+  const uint32_t a2 = mad_lo(__byte_perm(t, 0u, 0x4442), c128, Al);
+  const uint32_t a3 = mad_lo(__byte_perm(t, 0u, 0x4443), c128, Al);
+  return lds_off<0, PIN>(a0) ^ lds_off<32768, PIN>(a1) ^ lds_off<65536, PIN>(a2) ^ lds_off<98304, PIN>(a3);
 }
 __device__ __forceinline__ uint32_t z_shared(const uint32_t *S, uint32_t t) { // S = one 4 x 256 set
   return S[t & 255u] ^ S[256u + ((t >> 8) & 255u)] ^ S[512u + ((t >> 16) & 255u)] ^ S[768u + (t >> 24)];
@@ -411,6 +437,7 @@ __global__ void __launch_bounds__(1024) k_crc32c_plan(const uint32_t *out_len, i
   if (tid == 0) prefix[n_frames] = s_carry;
 }
 
+template <bool RING>
 __global__ void __launch_bounds__(CRC_ROWS_NT, 1) k_crc32c_rows(const uint8_t *out, size_t out_pitch, int n_frames,
                                                                uint32_t *words, const uint32_t *slices,
                                                                uint8_t *copy_dst, size_t copy_pitch) {
@@ -429,7 +456,9 @@ __global__ void __launch_bounds__(CRC_ROWS_NT, 1) k_crc32c_rows(const uint8_t *o
   for (int i = tid; i < 4 * 256 * 32; i += CRC_ROWS_NT) A[i] = slices[6 * 1024 + (i >> 5)];
   for (int i = tid; i < 6 * 4 * 256; i += CRC_ROWS_NT) S[i] = slices[i];
   __syncthreads();
-  const uint32_t *Al = A + lane;
+  const uint32_t Al = (uint32_t)__cvta_generic_to_shared(A + lane);
+  uint32_t c128;
+  asm volatile("mov.u32 %0, 128;" : "=r"(c128)); // opaque to the compiler: see z_private
   const uint32_t gw = blockIdx.x * (CRC_ROWS_NT / 32) + (tid >> 5);
   uint64_t s64 = (uint64_t)gw * K;
   if (s64 >= total) return;
@@ -454,44 +483,71 @@ __global__ void __launch_bounds__(CRC_ROWS_NT, 1) k_crc32c_rows(const uint8_t *o
     uint4 *dst = copy_dst ? reinterpret_cast<uint4 *>(copy_dst + (size_t)f * copy_pitch + (size_t)r0 * CRC_ROW) + lane : nullptr;
     const int n = (int)(r1 - r0);
     uint32_t t0 = 0u, t1 = 0u, t2 = 0u, t3 = 0u;
-    // Four rows in flight per warp, staged through a private ring in shared memory by cp.async: the copy of row k + 4
-    // is issued when row k is taken out, a full four steps (~2500 issue cycles with 32 warps) before it is needed, and
-    // it occupies no registers while it flies.  (With the rows loaded into registers the compiler gathered the four
-    // loads of a group at the group's end — one step of distance or less, 2.6 warps per issue waiting on the long
-    // scoreboard, 4.2 TB/s: profiles/r02o_ncu_crc_rows_summary.txt.)
-    uint4 *slot0 = R + ((tid >> 5) * 4) * 32 + lane; // this lane's 16 bytes of slot 0; slot j is 512 bytes on
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(slot0);
-    auto fetch = [&](int k, int j) { // row k -> slot j = k & 3 (an empty group when the row does not exist: the count stays uniform)
-      if (k < n)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (uint32_t)j * 512u), "l"(src + (size_t)k * 32)
-                     : "memory");
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto step = [&](int k, int j) {
-      asm volatile("cp.async.wait_group 3;" ::: "memory"); // all but the three youngest groups: row k has landed
-      const uint4 v = slot0[j * 32];
-      fetch(k + 4, j);
-      if (dst) dst[(size_t)k * 32] = v;
-      t0 = z_private(Al, t0) ^ v.x;
-      t1 = z_private(Al, t1) ^ v.y;
-      t2 = z_private(Al, t2) ^ v.z;
-      t3 = z_private(Al, t3) ^ v.w;
-    };
-    fetch(0, 0);
-    fetch(1, 1);
-    fetch(2, 2);
-    fetch(3, 3);
-    int k = 0;
-    for (; k + 4 <= n; k += 4) {
-      step(k, 0);
-      step(k + 1, 1);
-      step(k + 2, 2);
-      step(k + 3, 3);
+    // Four rows in flight per warp.  RING: staged through a private ring in shared memory by cp.async — the copy of
+    // row k + 4 is issued when row k is taken out, four steps (~2000 issue cycles with 32 warps) before it is needed,
+    // and occupies no registers while it flies; costs a 512-byte shared-memory write and read per row in the l1tex
+    // pipe, which the sixteen lookups per row already keep 60 % busy.  !RING (measurement knob): the rows are loaded
+    // into a register ring.  A row's registers are read by the last XORs of its step, so its successor cannot be asked
+    // for earlier, and ptxas moves all four loads of a group to the group's end even with volatile lookups — one step
+    // of distance or less, 2.6 warps per issue waiting on the long scoreboard (profiles/r02o_ncu_crc_rows_summary.txt).
+    if (RING) {
+      uint4 *slot0 = R + ((tid >> 5) * 4) * 32 + lane; // this lane's 16 bytes of slot 0; slot j is 512 bytes on
+      const uint32_t ring = (uint32_t)__cvta_generic_to_shared(slot0);
+      auto fetch = [&](int k, int j) { // row k -> slot j = k & 3 (an empty group when the row does not exist: the count stays uniform)
+        if (k < n)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (uint32_t)j * 512u), "l"(src + (size_t)k * 32)
+                       : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      auto step = [&](int k, int j) {
+        asm volatile("cp.async.wait_group 3;" ::: "memory"); // all but the three youngest groups: row k has landed
+        const uint4 v = slot0[j * 32];
+        fetch(k + 4, j);
+        if (dst) dst[(size_t)k * 32] = v;
+        t0 = z_private<false>(Al, c128, t0) ^ v.x;
+        t1 = z_private<false>(Al, c128, t1) ^ v.y;
+        t2 = z_private<false>(Al, c128, t2) ^ v.z;
+        t3 = z_private<false>(Al, c128, t3) ^ v.w;
+      };
+      fetch(0, 0);
+      fetch(1, 1);
+      fetch(2, 2);
+      fetch(3, 3);
+      int k = 0;
+      for (; k + 4 <= n; k += 4) {
+        step(k, 0);
+        step(k + 1, 1);
+        step(k + 2, 2);
+        step(k + 3, 3);
+      }
+      if (k < n) step(k, 0);
+      if (k + 1 < n) step(k + 1, 1);
+      if (k + 2 < n) step(k + 2, 2);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      auto load = [&](int k) { return k < n ? ld_stream16(src + (size_t)k * 32) : zero; };
+      uint4 q0 = load(0), q1 = load(1), q2 = load(2), q3 = load(3);
+      auto step = [&](uint4 &q, int k) { // consume row k, then ask for row k + 4 into the same registers
+        const uint4 v = q;
+        if (dst) dst[(size_t)k * 32] = v;
+        t0 = z_private<true>(Al, c128, t0) ^ v.x;
+        t1 = z_private<true>(Al, c128, t1) ^ v.y;
+        t2 = z_private<true>(Al, c128, t2) ^ v.z;
+        t3 = z_private<true>(Al, c128, t3) ^ v.w;
+        q = load(k + 4);
+      };
+      int k = 0;
+      for (; k + 4 <= n; k += 4) {
+        step(q0, k);
+        step(q1, k + 1);
+        step(q2, k + 2);
+        step(q3, k + 3);
+      }
+      if (k < n) step(q0, k);
+      if (k + 1 < n) step(q1, k + 1);
+      if (k + 2 < n) step(q2, k + 2);
     }
-    if (k < n) step(k, 0);
-    if (k + 1 < n) step(k + 1, 1);
-    if (k + 2 < n) step(k + 2, 2);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // fold the 128 streams: words of a thread by Horner with x^32, lanes by a butterfly with x^128, x^256, ...
     uint32_t u = z_shared(S, z_shared(S, z_shared(S, t0) ^ t1) ^ t2) ^ t3;
 #pragma unroll
@@ -532,18 +588,17 @@ __global__ void __launch_bounds__(32) k_crc32c_tail(const uint8_t *out, size_t o
   uint32_t c = 0u;
   const uint32_t b0 = 16u * lane, b1 = b0 + 16u < r ? b0 + 16u : r;
   if (b0 < r) {
-    // one 16-byte load (the arena's pitch is a multiple of 16, so the bytes behind the string's end exist), then the
-    // byte recurrence out of registers
-    const uint4 v = *reinterpret_cast<const uint4 *>(tail + b0);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    // sixteen independent byte loads (none behind the string's end), then the byte recurrence out of registers
     const uint32_t cnt = b1 - b0;
+    uint32_t bytes[16];
+#pragma unroll
+    for (uint32_t i = 0; i < 16u; i++) bytes[i] = i < cnt ? (uint32_t)tail[b0 + i] : 0u;
     uint32_t st = 0u;
 #pragma unroll
     for (uint32_t i = 0; i < 16u; i++) {
-      const uint32_t b = (w[i >> 2] >> (8u * (i & 3u))) & 255u;
       if (i < cnt) {
-        if (dst) dst[b0 + i] = (uint8_t)b;
-        st = T[(st ^ b) & 255u] ^ (st >> 8);
+        if (dst) dst[b0 + i] = (uint8_t)bytes[i];
+        st = T[(st ^ bytes[i]) & 255u] ^ (st >> 8);
       }
     }
     c = gf_mul(c_crc.bytepow[r - b1], st);
@@ -567,7 +622,8 @@ __global__ void __launch_bounds__(32) k_crc32c_tail(const uint8_t *out, size_t o
   }
 }
 cudaError_t crc_rows_opt_in() {
-  return cudaFuncSetAttribute(k_crc32c_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CRC_ROWS_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(k_crc32c_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CRC_ROWS_SMEM);
+  return e != cudaSuccess ? e : cudaFuncSetAttribute(k_crc32c_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CRC_ROWS_SMEM);
 }
 
 // stream.c:1085-1127 on the device: a frame that does not end in ESC[0m is cut after its last ESC[0m, if it has one.
@@ -634,8 +690,14 @@ int launch_frame_packets(const uint8_t *d_out, size_t out_pitch, const uint32_t 
     const uint64_t sms = (uint64_t)device_sms();
     if (ctas > sms) ctas = sms;
     if (ctas < 1) ctas = 1;
-    k_crc32c_rows<<<(unsigned)ctas, CRC_ROWS_NT, CRC_ROWS_SMEM, st>>>(d_out, out_pitch, n_frames, d_part, g_crc_slices[dev],
-                                                                     copy_dst, copy_pitch);
+    // ACB200_CRC_ROWS=regs (measurement knob): rows loaded into a register ring instead of the cp.async ring
+    static const bool ring = !(getenv("ACB200_CRC_ROWS") && !strcmp(getenv("ACB200_CRC_ROWS"), "regs"));
+    if (ring)
+      k_crc32c_rows<true><<<(unsigned)ctas, CRC_ROWS_NT, CRC_ROWS_SMEM, st>>>(d_out, out_pitch, n_frames, d_part,
+                                                                             g_crc_slices[dev], copy_dst, copy_pitch);
+    else
+      k_crc32c_rows<false><<<(unsigned)ctas, CRC_ROWS_NT, CRC_ROWS_SMEM, st>>>(d_out, out_pitch, n_frames, d_part,
+                                                                              g_crc_slices[dev], copy_dst, copy_pitch);
     ACB_CUDA(cudaGetLastError());
     k_crc32c_tail<<<(unsigned)n_frames, 32, 0, st>>>(d_out, out_pitch, d_out_len, d_part, width, height, headers,
                                                     header_pitch, copy_dst, copy_pitch);

@@ -229,9 +229,13 @@ def e2e_api_legs(acb, H, frames, caps, n_gpus, seconds):
     # the same frames page-locked
     registered = None
     if lib.acb200_register_host_memory(frames.ctypes.data, frames.nbytes) == 0:
-        fetch_t = sorted(set(max(2, c) for c in (ncores // 2, ncores, (3 * ncores) // 2, 2 * ncores)))
+        # fetching callers mostly wait (the link is the bound: ~8-16 of them per GPU saturate it), so more callers than
+        # cores make sense — with the yielding wait; spinning ones only up to one per core
+        fetch_t = sorted(set(max(2, c) for c in (ncores // 2, ncores, (3 * ncores) // 2, 2 * ncores, 3 * ncores,
+                                                 4 * ncores) if c <= 16 * n_gpus or c <= ncores))
         best_rg, p3 = pick_config(lib, H, fn, frames, caps,
-                                  [best_pg] + [(t, -1, w) for t in fetch_t for w in (0, 3)])
+                                  [best_pg] + [(t, -1, 0) for t in fetch_t if t <= ncores] +
+                                  [(t, -1, 3) for t in fetch_t])
         registered = measure(best_rg, p3)
         lib.acb200_set_fetch_depth(-1)
         lib.acb200_set_sync_mode(0, 30)

@@ -75,7 +75,18 @@ for cols, rows, filt, frames in ob.rain_sequences()[3:]:
         bad += a.apply(s_, dt) != b.apply(s_, dt)
     a.close()
     b.close()
-lens = [0, 1, 63, 64, 65, 16384, 16385, 40000]
+# page-locked frames fetched by the device (k_gather_nn_rows on mapped host memory), unaligned frame starts, flips
+buf = np.zeros(97 * 61 * 3 + 256, np.uint8)
+assert acb.lib().acb200_register_host_memory(buf.ctypes.data, buf.nbytes) == 0
+acb.lib().acb200_set_fetch_depth(-1)
+for off, fx, fy in ((0, 0, 0), (1, 1, 0), (7, 0, 1), (16, 1, 1)):
+    im = buf[off:off + 97 * 61 * 3].reshape(61, 97, 3)
+    im[...] = ob.gen("noise", 97, 61, off)
+    got = acb.display_convert(im, 40, 12, acb.make_caps(3, 2), False, False, "standard", bool(fx), bool(fy), 3, 0.7)
+    bad += got != ob.port_display_convert(im, 40, 12, 3, 2, flip_x=fx, flip_y=fy, color_filter=3, time_s=0.7)
+acb.lib().acb200_set_fetch_depth(0)
+assert acb.lib().acb200_unregister_host_memory(buf.ctypes.data) == 0
+lens = [0, 1, 63, 64, 65, 511, 512, 513, 2048 + 17, 16384, 16385, 40000]
 pitch = 40016
 arena = np.random.default_rng(1).integers(0, 256, (len(lens), pitch), dtype=np.uint8)
 d_out, d_len = torch.from_numpy(arena).cuda(), torch.tensor(lens, dtype=torch.int32, device="cuda")
