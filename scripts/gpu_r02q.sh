@@ -15,7 +15,7 @@ for k in ("pageable", "registered"):
           "frames/s", round(r["calls"] / r["seconds"]) if r else None)
     print("   probes", r.get("probes"))
 PY
-echo "== sweep"; timeout 600 python scripts/e2e_scaling.py --devices 8 --register --modes spin,yield --depths -1,4 --threads 32,48,64,96 --seconds 0.8 2>&1 | tee $O/${TAG}_e2e_inproc8.txt
+echo "== sweep"; timeout 600 python scripts/e2e_scaling.py --devices 8 --register --modes spin,yield --depths=-1,4 --threads 32,48,64,96 --seconds 0.8 2>&1 | tee $O/${TAG}_e2e_inproc8.txt
 echo "== reference arm"; timeout 600 python bench.py --impl reference --gpus 8 --steps 3 --warmup 1 > $O/${TAG}_bench_reference.json 2>/dev/null; cut -c1-200 $O/${TAG}_bench_reference.json
 echo "== same leg, 1 GPU of this box"; timeout 600 python bench.py --leg e2e-inprocess --gpus 1 > $O/${TAG}_e2e_leg_n1.json 2>/dev/null
 python - <<'PY'
