@@ -1318,6 +1318,15 @@ int acb200_unregister_host_memory(void *p) {
   return E_OK;
 }
 void acb200_set_fetch_depth(int depth) { g_fetch_depth.store(depth); }
+int acb200_nn_row_schedule(int src_h, int rows, int flip_y, int *period, int *stride, int *first) {
+  if (src_h <= 0 || rows <= 0 || !period || !stride || !first) return set_error(E_INVALID_PARAM, "acb200_nn_row_schedule: bad argument");
+  RowSchedule rs;
+  row_schedule(rs, src_h, rows, flip_y != 0);
+  *period = rs.P;
+  *stride = rs.D;
+  for (int k = 0; k < rs.P; k++) first[k] = rs.first[k];
+  return E_OK;
+}
 void acb200_host_phase_stats(uint64_t out[5], int reset) {
   for (int k = 0; k < 5; k++) {
     if (out) out[k] = g_phase_ns[k].load(std::memory_order_relaxed);

@@ -239,6 +239,11 @@ void acb200_set_sync_mode(int mode, int spin_us);
 int acb200_register_host_memory(void *base, size_t bytes);
 int acb200_unregister_host_memory(void *base);
 void acb200_set_fetch_depth(int depth);
+/* Host arithmetic behind the copy-engine form of the fetch (ACB200_FETCH=ce), exported for the CPU tests: the source rows
+ * nearest-neighbour sampling reads (image.c:294,315-317; mirrored and listed backwards with flip_y), in ascending order,
+ * as *period interleaved arithmetic progressions of common *stride: row j of the list = first[j % period] +
+ * (j / period) * stride.  *period = 0: no such decomposition with period <= 8 (first[] must hold 8 ints). */
+int acb200_nn_row_schedule(int src_h, int rows, int flip_y, int *period, int *stride, int *first);
 /* Where the host time of the drop-in / batch-host calls went since the last reset, summed over all calling threads:
  * out[0..3] = nanoseconds spent gathering/staging the input, enqueueing (copies + launches), waiting for the device,
  * copying the strings into allocator-owned memory; out[4] = frames.  reset != 0 clears the counters. */

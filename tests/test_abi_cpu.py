@@ -85,6 +85,34 @@ def test_host_float_helpers_match_oracle(acb, ob):
         assert (a.value, b.value) == (c.value, d.value)
 
 
+def test_nn_row_schedule_matches_image_resize_indices(acb):
+    """the row list behind the copy-engine fetch (engine.cu: row_schedule) == image.c:294,315-317's sy(y), mirrored and
+    walked backwards with flip_y, whenever a decomposition into <= 8 arithmetic progressions is reported"""
+    import ctypes as C
+    import random
+    rnd = random.Random(3)
+    cases = [(2160, 192), (2160, 96), (2160, 180), (1080, 96), (1080, 48), (480, 48), (480, 24), (720, 134), (5, 3),
+             (1, 1), (7, 7), (3, 9), (2160, 1), (2160, 2)] + [(rnd.randint(1, 2200), rnd.randint(1, 400)) for _ in range(300)]
+    found = 0
+    for (sh, rows), flip in [(c, f) for c in cases for f in (0, 1)]:
+        P, D, first = C.c_int(), C.c_int(), (C.c_int * 8)()
+        assert acb.lib().acb200_nn_row_schedule(sh, rows, flip, C.byref(P), C.byref(D), first) == 0
+        yr = ((sh << 16) // rows) + 1
+        sy = [min(((y * yr) & 0xFFFFFFFF) >> 16, sh - 1) for y in range(rows)]
+        want = sy if not flip else [sh - 1 - v for v in reversed(sy)]  # ascending list; row j is output row rows-1-j
+        if P.value == 0:
+            continue
+        found += 1
+        assert 1 <= P.value <= 8
+        got = [first[j % P.value] + (j // P.value) * D.value for j in range(rows)]
+        assert got == want, (sh, rows, flip, P.value, D.value)
+    assert found >= 40  # the BASELINE geometries and every integer ratio have one
+    for sh, rows in ((2160, 192), (2160, 96), (1080, 96), (480, 48)):
+        P, D, first = C.c_int(), C.c_int(), (C.c_int * 8)()
+        acb.lib().acb200_nn_row_schedule(sh, rows, 0, C.byref(P), C.byref(D), first)
+        assert P.value in (1, 2, 4), (sh, rows, P.value)
+
+
 def test_no_gpu_means_loud_failure(acb):
     import torch
     if torch.cuda.is_available():
