@@ -84,7 +84,7 @@ EXPORTS = [  # every symbol include/asciichat_b200.h declares
     "digital_rain_set_fall_speed", "digital_rain_set_raindrop_length", "digital_rain_set_color",
     "digital_rain_set_color_from_filter", "acb200_host_phase_stats",
     "acb200_register_host_memory", "acb200_unregister_host_memory", "acb200_set_fetch_depth",
-    "acb200_nn_row_schedule",
+    "acb200_nn_row_schedule", "acb200_set_crc_form",
 ]
 
 
@@ -217,6 +217,8 @@ def lib():
     L.acb200_unregister_host_memory.argtypes = [C.c_void_p]
     L.acb200_nn_row_schedule.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int)]
+    L.acb200_set_crc_form.restype = None
+    L.acb200_set_crc_form.argtypes = [C.c_int]
     L.acb200_set_fetch_depth.restype = None
     L.acb200_set_fetch_depth.argtypes = [C.c_int]
     L.acb200_host_phase_stats.restype = None

@@ -7,6 +7,7 @@
 //   * wire packaging, lib/network/acip/server.c:188-236 + lib/network/crc32.c: CRC32-C of every finished frame while
 //     it is still in HBM (k_crc32c_chunks + k_crc32c_finish) and the 24-byte big-endian ascii_frame_packet_t;
 //     k_trailing_reset_fixup is the device form of the server's "frame must end in ESC[0m" cut (stream.c:1085-1127).
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -190,6 +191,11 @@ __host__ __device__ inline uint32_t gf_xpow8(const uint32_t *x2n, uint64_t n_byt
 }
 
 cudaError_t crc_rows_opt_in(); // the row kernel's shared-memory opt-in (defined behind the kernel)
+// 0 = by arena size (launch_frame_packets), 1 = row form, 2 = segment form
+std::atomic<int> g_crc_form{[] {
+  const char *e = getenv("ACB200_CRC_KERNEL");
+  return !e ? 0 : !strcmp(e, "rows") ? 1 : !strcmp(e, "segments") ? 2 : 0;
+}()};
 // __constant__ memory is per device: the tables are uploaded once on every device the library runs on
 std::mutex g_crc_mu;
 uint64_t g_crc_done = 0; // bit per CUDA ordinal
@@ -677,8 +683,13 @@ int launch_frame_packets(const uint8_t *d_out, size_t out_pitch, const uint32_t 
   if (crc_tables_init() != E_OK) return set_error(E_INVALID_STATE, "CUDA: CRC table upload failed");
   // measurement knob (never set in production): run the table recurrence on synthetic words, no global loads
   static const int crc_noload = getenv("ACB200_CRC_NOLOAD") ? atoi(getenv("ACB200_CRC_NOLOAD")) : 0;
-  // ACB200_CRC_KERNEL=segments (measurement knob): the round-1 form, one thread per 256 contiguous bytes
-  static const bool segments = getenv("ACB200_CRC_KERNEL") && !strcmp(getenv("ACB200_CRC_KERNEL"), "segments");
+  // Which form: the row form wins from ~20 4K-frame strings on (32 frames: 30.7 vs 35.6 us, 256 frames: 87 vs 178 us);
+  // below that its three launches and the 128 KB table fill per CTA cost more than they save (one frame: 23.6 vs 18.5 us,
+  // profiles/r02u_crc_small.txt), so small arenas — the server's one-frame packet path — keep the segment form.
+  // acb200_set_crc_form / ACB200_CRC_KERNEL=rows|segments force one.
+  int form = g_crc_form.load(std::memory_order_relaxed);
+  if (form == 0) form = (uint64_t)n_frames * out_pitch >= (24u << 20) ? 1 : 2;
+  const bool segments = form == 2;
   if (!segments && !crc_noload) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1073,6 +1084,10 @@ int acb200_trailing_reset_fixup_device(uint8_t *d_out, size_t out_pitch, uint32_
     return acb200_last_error();
   }
   return launch_reset_fixup(d_out, out_pitch, d_out_len, n_frames, st);
+}
+
+void acb200_set_crc_form(int form) {
+  if (form >= 0 && form <= 2) g_crc_form.store(form);
 }
 
 int acb200_frame_packets_device(const uint8_t *d_out, size_t out_pitch, const uint32_t *d_out_len, int n_frames,

@@ -336,6 +336,9 @@ int acb200_color_filter_device(uint8_t *d_pixels, uint32_t width, uint32_t heigh
 int acb200_trailing_reset_fixup_device(uint8_t *d_out, size_t out_pitch, uint32_t *d_out_len, int n_frames,
                                        void *stream);
 #define ACB200_FRAME_HEADER_BYTES 24
+/* Which CRC32-C kernels run: 0 = chosen by arena size (default: the row form from 24 MB of arena on, the segment form
+ * below — the one-frame packet path), 1 = row form, 2 = segment form.  Same result either way; for tests and A/B. */
+void acb200_set_crc_form(int form);
 int acb200_frame_packets_device(const uint8_t *d_out, size_t out_pitch, const uint32_t *d_out_len, int n_frames,
                                 uint32_t width, uint32_t height, uint8_t *d_headers, void *stream);
 /* acb200_mixed_frame + the packet header in front: returns header||frame (allocator-owned, *out_size =

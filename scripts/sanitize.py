@@ -92,7 +92,14 @@ arena = np.random.default_rng(1).integers(0, 256, (len(lens), pitch), dtype=np.u
 d_out, d_len = torch.from_numpy(arena).cuda(), torch.tensor(lens, dtype=torch.int32, device="cuda")
 d_hdr = torch.zeros(len(lens) * 24, dtype=torch.uint8, device="cuda")
 torch.cuda.synchronize()
-acb.frame_packets_device(d_out.data_ptr(), pitch, d_len.data_ptr(), len(lens), 80, 24, d_hdr.data_ptr(), None)
+for form in (2, 1):  # segment form, then the row form (the ladder's arena is small: the default would pick segments)
+    acb.lib().acb200_set_crc_form(form)
+    acb.frame_packets_device(d_out.data_ptr(), pitch, d_len.data_ptr(), len(lens), 80, 24, d_hdr.data_ptr(), None)
+    acb.synchronize()
+    hdr = d_hdr.cpu().numpy().reshape(len(lens), 24)
+    for i, L in enumerate(lens):
+        bad += hdr[i].tobytes() != ob.port_packet_header(arena[i, :L].tobytes(), 80, 24)
+acb.lib().acb200_set_crc_form(0)
 acb.trailing_reset_fixup_device(d_out.data_ptr(), pitch, d_len.data_ptr(), len(lens), None)
 acb.synchronize()
 hdr = d_hdr.cpu().numpy().reshape(len(lens), 24)

@@ -541,10 +541,13 @@ def test_frame_packets_device(acb, ob):
             assert hdr[i].tobytes() == want(out[i, :lens[i]].tobytes(), c, r), (W, H, level, mode, i)
 
 
-def test_crc32c_lengths_and_fixup_device(acb, ob, golden):
-    """arbitrary byte strings in a device arena: chunk-boundary lengths (64 KB chunks, 256-byte segments), empty
-    frames, the golden CRCs; and the trailing-reset cut of stream.c:1085-1127 on synthetic strings"""
+@pytest.mark.parametrize("crc_form", [1, 2, 0])
+def test_crc32c_lengths_and_fixup_device(acb, ob, golden, crc_form):
+    """arbitrary byte strings in a device arena: chunk-boundary lengths (64 KB chunks, 256-byte segments, 512-byte
+    rows), empty frames, the golden CRCs — through the row form (1), the segment form (2) and the size-based choice
+    (0); and the trailing-reset cut of stream.c:1085-1127 on synthetic strings"""
     import torch
+    acb.lib().acb200_set_crc_form(crc_form)
     lens = [0, 1, 3, 63, 64, 65, 127, 128, 255, 256, 257, 319, 320, 4095, 16383, 16384, 16385, 32768, 65535, 65536,
             65537, 65600, 100001, 131072, 1180548,
             15, 16, 17, 511, 512, 513, 527, 528, 1023, 1024, 1025, 2047, 2048, 2049, 4096 + 16, 512 * 5 - 1, 512 * 5 + 31]
@@ -587,6 +590,7 @@ def test_crc32c_lengths_and_fixup_device(acb, ob, golden):
             assert int.from_bytes(hdr[i, 16:20].tobytes(), "big") == ob.port().orc_crc32c(m, len(m)), (n, i, lens2[i])
             assert int.from_bytes(hdr[i, 8:12].tobytes(), "big") == lens2[i]
 
+    acb.lib().acb200_set_crc_form(0)
     rst = b"\x1b[0m"
     cases = [b"", b"abc", rst, b"row" + rst, b"ab" + rst + b"cd", rst + b"x" * 1000, b"y" * 700 + rst + b"z" * 3,
              b"plain text without any reset" * 40, (b"q" + rst) * 300 + b"tail", b"\x1b[0", b"a" + rst + rst + b"\x1b[0"]
