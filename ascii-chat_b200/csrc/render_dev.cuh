@@ -1130,7 +1130,8 @@ __device__ __forceinline__ void emit_direct_finish(const RenderParams &p, int f,
 // per text row, and the next tile's ticket is requested while the current one is being emitted.  Whoever holds tile X
 // knows every tile < X is held by a running CTA, so the look-back spin cannot deadlock.
 template <int MODE, int SP, int NT>
-__global__ void __launch_bounds__(NT, (SP == SP_NN && NT <= 256) ? (2048 / NT) : 1) k_render_rows(const RenderParams p) {
+__global__ void __launch_bounds__(NT, SP != SP_NN ? 1 : NT == 160 ? 9 : NT == 320 ? 6 : NT <= 256 ? 2048 / NT : 1)
+    k_render_rows(const RenderParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_tmp[2 * (NT / 32)];
   __shared__ uint32_t s_cond2[2][4]; // per tile set; TRUE_FG: {cond_off, cond_len, last_rgb, first_rgb}
@@ -1743,6 +1744,19 @@ static cudaError_t launch_rows_t(const RenderParams &p, cudaStream_t st, unsigne
 template <int MODE, int SP> static cudaError_t launch_rows_nt(const RenderParams &p, cudaStream_t st, unsigned *grid_out) {
   // (384 threads for 257..384 columns — one pass over the row instead of two — measured slower: five CTAs per SM keep
   // fewer tiles in flight than eight, 0.248 vs 0.228 ms on flat C3 frames, profiles/r02j_configs.txt)
+  // Nearest neighbour is instruction-bound (profiles/r02i_ncu_nn_flat: 76 % issue utilisation), so the CTA width is
+  // chosen to leave no lane idle: a 320-column row on 256 threads runs every per-cell loop and scan pass twice, the
+  // second time with a quarter of the lanes (16 warp-passes); 160 threads do it in two FULL passes (10 warp-passes) and
+  // eight such CTAs are resident per SM, as many tiles in flight as before.  Measured on 256 x C3 frames
+  // (profiles/r02w_nn_nt.txt): 0.319 / 0.228 ms (noise / flat) with 256 threads, 0.317 / 0.226 with 320 (one pass, but
+  // six CTAs per SM), **0.282 / 0.191** with 160.  Rows of 129..160 columns take 160 threads for the same reason (one
+  // full pass instead of 256 threads with three idle warps).  ACB200_NN_NT=256|320 forces the other widths (A/B).
+  static const int nn_nt = getenv("ACB200_NN_NT") ? atoi(getenv("ACB200_NN_NT")) : 0;
+  if (SP == SP_NN && nn_nt != 256) {
+    if (nn_nt == 320 && p.cols > 256 && p.cols <= 320) return launch_rows_t<MODE, SP, SP == SP_NN ? 320 : 256>(p, st, grid_out);
+    if ((p.cols > 256 && p.cols <= 320) || (p.cols > 128 && p.cols <= 160))
+      return launch_rows_t<MODE, SP, SP == SP_NN ? 160 : 256>(p, st, grid_out);
+  }
   switch (pick_nt(p.cols)) {
   case 128: return launch_rows_t<MODE, SP, 128>(p, st, grid_out);
   default: return launch_rows_t<MODE, SP, 256>(p, st, grid_out);

@@ -11,7 +11,11 @@ CASES = [("C1 640x480->80x24 mono fg", 640, 480, 80, 24, 0, 0, 2048),
          ("C2 1920x1080->160x48 ANSI-256 fg", 1920, 1080, 160, 48, 2, 0, 1024),
          ("C3 3840x2160->320x96 truecolor half-block", 3840, 2160, 320, 96, 3, 2, 256),
          ("3840x2160->320x96 truecolor fg", 3840, 2160, 320, 96, 3, 0, 256)]
+ONLY = os.environ.get("MEASURE_ONLY")      # substring of the config name, e.g. "320x96" (tuning aid)
+SCALES = os.environ.get("MEASURE_SCALES", "box,nn").split(",")
 for name, W, H, c, r, level, mode, n in CASES:
+    if ONLY and ONLY not in name:
+        continue
     for content in ("noise", "flat"):
         if content == "noise":
             d_in = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, device="cuda")
@@ -19,6 +23,8 @@ for name, W, H, c, r, level, mode, n in CASES:
             band = torch.randint(0, 256, (n, H // 40 + 1, 1, 3), dtype=torch.uint8, device="cuda")
             d_in = band.repeat_interleave(40, dim=1)[:, :H].expand(n, H, W, 3).contiguous()
         for scale, sname in ((acb.SCALE_BOX, "box"), (acb.SCALE_NN, "nn")):
+            if sname not in SCALES:
+                continue
             cfg = acb.make_cfg(W, H, c, r * 2 if mode == 2 else r, level, mode, "standard", scale=scale)
             cap = acb.frame_capacity(cfg)
             d_out = torch.empty(n * cap, dtype=torch.uint8, device="cuda")
